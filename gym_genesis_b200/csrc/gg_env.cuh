@@ -1,0 +1,698 @@
+// Per-env pipeline of one env.step (one rigid substep of dt = 0.01 s), written once as
+// host/device code: the CUDA kernels in gg_kernels.cu map one thread to one env and call these
+// functions; tests/hostsim compiles the same header for the CPU as a debugging harness only.
+//
+// Replaces, for this path, what Genesis' `scene.step()` does for the reference
+// (gym_genesis/tasks/franka/cube_pick.py:125; pipeline per SURVEY.md Appendix A):
+//   PD torque -> FK -> CRBA (+armature, +dt*(damping+kv)) -> Cholesky -> RNEA bias -> smooth acc
+//   -> narrow phase (box-plane, pad-box vs cube) -> soft-constraint Newton solve -> semi-implicit Euler.
+#pragma once
+#include "gg_b200.h"
+#include "gg_math.cuh"
+
+namespace gg {
+
+template <int NU> struct EnvState {
+    float q[NU], qd[NU];
+    V3 cp; Q4 cq; V3 cv, cw;      // cube position, quaternion (wxyz), linear velocity (world), angular velocity (body frame)
+    float qacc[NU + 6];           // previous solution = warm start
+};
+
+struct StepInfo { int ncon; int iters; float grad; };
+
+// ---------------------------------------------------------------------------------------------
+// Robot kinematics + dynamics.  World-frame spatial algebra about the world origin: composite
+// inertias and forces of a subtree are plain sums, M(i,j) = S_i . (Ic_j S_j), c_j = S_j . Fc_j.
+// ---------------------------------------------------------------------------------------------
+template <int NA, int NF> struct RobotDyn {
+    float Mt[(NA + NF) * (NA + NF + 1) / 2];   // M + armature + dt*(damping+kv), packed lower
+    float fs[NA + NF];                         // tau - bias
+    V3 jk[NA], jo[NA];                         // hinge axes / anchors (world)
+    V3 fk[NF > 0 ? NF : 1], fo[NF > 0 ? NF : 1];   // finger slide direction or hinge axis, anchor
+    Q4 lq; V3 lp; M3 lR;                       // last arm link frame
+    M3 fR[NF > 0 ? NF : 1]; V3 fp[NF > 0 ? NF : 1];   // finger frames
+};
+
+template <int NA, int NF, bool FH>
+GG_HD void robot_dynamics(const GgModel& M, const float* q, const float* qd, const float* target, RobotDyn<NA, NF>& D) {
+    constexpr int NU = NA + NF;
+    SV S[NA]; SI I[NA]; SV F[NA];
+    float bias[NU];
+    Q4 ql = ldq(M.base_quat);
+    V3 pl = ld3(M.base_pos);
+    M3 Rl = qmat(ql);
+    SV V; V.a = mk(0.f, 0.f, 0.f); V.l = mk(0.f, 0.f, 0.f);
+    SV A; A.a = mk(0.f, 0.f, 0.f); A.l = mk(0.f, 0.f, M.gravity);   // gravity as base acceleration
+#pragma unroll
+    for (int l = 0; l < NA; l++) {
+        pl = pl + mul(Rl, ld3(M.link_pos[l]));
+        float s, c;
+        gg_sincos(0.5f * q[l], &s, &c);
+        ql = qmul_z(qmul(ql, ldq(M.link_quat[l])), c, s);
+        Rl = qmat(ql);
+        D.jk[l] = Rl.c2; D.jo[l] = pl;
+        S[l].a = Rl.c2; S[l].l = cross(pl, Rl.c2);
+        A = A + crm(V, S[l]) * qd[l];
+        V = V + S[l] * qd[l];
+        I[l] = body_inertia(M.link_mass[l], ld3(M.link_com[l]), M.link_inertia[l], Rl, pl);
+        F[l] = apply(I[l], A) + crf(V, apply(I[l], V));
+    }
+    D.lq = ql; D.lp = pl; D.lR = Rl;
+    SI Ic; Ic.m = 0.f; Ic.h = mk(0.f, 0.f, 0.f); Ic.I.xx = Ic.I.yy = Ic.I.zz = Ic.I.xy = Ic.I.xz = Ic.I.yz = 0.f;
+    SV Fc; Fc.a = mk(0.f, 0.f, 0.f); Fc.l = mk(0.f, 0.f, 0.f);
+#pragma unroll
+    for (int f = 0; f < NF; f++) {
+        Q4 qf = qmul(ql, ldq(M.fing_quat[f]));
+        V3 p0 = pl + mul(Rl, ld3(M.fing_pos[f]));
+        SV Sf; M3 Rf; V3 pf;
+        if (FH) {
+            float s, c;
+            gg_sincos(0.5f * q[NA + f], &s, &c);
+            qf = qmul_z(qf, c, s);
+            Rf = qmat(qf);
+            Sf.a = Rf.c2; Sf.l = cross(p0, Rf.c2); pf = p0;
+            D.fk[f] = Rf.c2; D.fo[f] = p0;
+        } else {
+            Rf = qmat(qf);
+            V3 a = mul(Rf, ld3(M.fing_axis[f]));
+            Sf.a = mk(0.f, 0.f, 0.f); Sf.l = a; pf = p0 + a * q[NA + f];
+            D.fk[f] = a; D.fo[f] = pf;
+        }
+        D.fR[f] = Rf; D.fp[f] = pf;
+        SV Af = A + crm(V, Sf) * qd[NA + f];
+        SV Vf = V + Sf * qd[NA + f];
+        SI If = body_inertia(M.fing_mass[f], ld3(M.fing_com[f]), M.fing_inertia[f], Rf, pf);
+        SV Ff = apply(If, Af) + crf(Vf, apply(If, Vf));
+        SV G = apply(If, Sf);
+        D.Mt[GG_TRI(NA + f, NA + f)] = sdot(Sf, G);
+#pragma unroll
+        for (int i = 0; i < NA; i++) D.Mt[GG_TRI(NA + f, i)] = sdot(S[i], G);
+#pragma unroll
+        for (int g = 0; g < f; g++) D.Mt[GG_TRI(NA + f, NA + g)] = 0.f;
+        bias[NA + f] = sdot(Sf, Ff);
+        Ic = Ic + If; Fc = Fc + Ff;
+    }
+#pragma unroll
+    for (int l = NA - 1; l >= 0; l--) {
+        Ic = Ic + I[l]; Fc = Fc + F[l];
+        SV G = apply(Ic, S[l]);
+#pragma unroll
+        for (int i = 0; i <= l; i++) D.Mt[GG_TRI(l, i)] = sdot(S[i], G);
+        bias[l] = sdot(S[l], Fc);
+    }
+    // PD position control with force clamp; passive damping; approximate implicit-fast diagonal
+#pragma unroll
+    for (int d = 0; d < NU; d++) {
+        float t = M.kp[d] * (target[d] - q[d]) - M.kv[d] * qd[d];
+        t = fminf(fmaxf(t, M.frc_lo[d]), M.frc_hi[d]);
+        D.fs[d] = t - M.damping[d] * qd[d] - bias[d];
+        D.Mt[GG_TRI(d, d)] += M.armature[d] + M.dt * (M.damping[d] + M.kv[d]);
+    }
+}
+
+// pose of the end-effector frame and finger coordinates only (post-step observation refresh)
+template <int NA, int NF>
+GG_HD void robot_eef(const GgModel& M, const float* q, V3& ep, Q4& eq) {
+    Q4 ql = ldq(M.base_quat);
+    V3 pl = ld3(M.base_pos);
+    M3 Rl = qmat(ql);
+#pragma unroll
+    for (int l = 0; l < NA; l++) {
+        pl = pl + mul(Rl, ld3(M.link_pos[l]));
+        float s, c;
+        gg_sincos(0.5f * q[l], &s, &c);
+        ql = qmul_z(qmul(ql, ldq(M.link_quat[l])), c, s);
+        Rl = qmat(ql);
+    }
+    ep = pl + mul(Rl, ld3(M.eef_pos));
+    eq = qmul(ql, ldq(M.eef_quat));
+}
+
+// ---------------------------------------------------------------------------------------------
+// Narrow phase.  Contact code: 0 = plane-cube, 1+r = plane-robot body r, 4+r = robot body r-cube
+// (r: 0 = last arm link, 1+f = finger f).  Normal points from the first body to the second.
+// ---------------------------------------------------------------------------------------------
+struct Contacts {
+    V3 p[GG_MAX_CONTACTS];
+    V3 n[GG_MAX_CONTACTS];
+    float depth[GG_MAX_CONTACTS];
+    int code[GG_MAX_CONTACTS];
+    int count;
+};
+
+GG_HD void add_contact(Contacts& C, int maxc, V3 p, V3 n, float depth, int code) {
+    if (C.count < maxc) { C.p[C.count] = p; C.n[C.count] = n; C.depth[C.count] = depth; C.code[C.count] = code; C.count++; }
+}
+
+// plane z = h against a box: the first <= 4 corners (corner-index order) with signed distance <= 0
+GG_HD void plane_box(float h, V3 c, const M3& R, V3 half, int code, int maxc, Contacts& C) {
+    int cnt = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        V3 l = mk((i & 1) ? half.x : -half.x, (i & 2) ? half.y : -half.y, (i & 4) ? half.z : -half.z);
+        V3 w = c + mul(R, l);
+        float dist = w.z - h;
+        if (dist <= 0.f && cnt < 4) {
+            add_contact(C, maxc, mk(w.x, w.y, w.z - 0.5f * dist), mk(0.f, 0.f, 1.f), -dist, code);
+            cnt++;
+        }
+    }
+}
+
+GG_HD float sgn1(float x) { return x < 0.f ? -1.f : 1.f; }
+
+// clip polygon (u, v, w) against s * coord[ax] <= lim (Sutherland-Hodgman, <= 8 vertices)
+GG_HD int clip_poly(const V3* in, int n, V3* out, int ax, float s, float lim) {
+    int m = 0;
+    for (int i = 0; i < n; i++) {
+        V3 a = in[i], b = in[(i + 1) == n ? 0 : i + 1];
+        float da = s * comp(a, ax) - lim, db = s * comp(b, ax) - lim;
+        if (da <= 0.f) { if (m < 8) out[m++] = a; }
+        if ((da <= 0.f) != (db <= 0.f)) {
+            float t = da / (da - db);
+            if (m < 8) out[m++] = a + t * (b - a);
+        }
+    }
+    return m;
+}
+
+// box A (robot pad) against box B (cube): SAT over 15 axes; A faces win ties, B faces and edge axes
+// must be better by 5 %.  Face case: incident face clipped to the reference face, contacts at the
+// mid-surface; edge case: midpoint of the closest points of the two supporting edges.
+GG_HD void box_box(V3 cA, const M3& RA, V3 hA3, V3 cB, const M3& RB, V3 hB3, int code, int maxc, Contacts& C) {
+    const float FUDGE = 1.05f;
+    V3 A[3] = {RA.c0, RA.c1, RA.c2}, B[3] = {RB.c0, RB.c1, RB.c2};
+    float hA[3] = {hA3.x, hA3.y, hA3.z}, hB[3] = {hB3.x, hB3.y, hB3.z};
+    V3 t = cB - cA;
+    float Cm[3][3], aC[3][3], tA[3], tB[3];
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        tA[i] = dot(t, A[i]); tB[i] = dot(t, B[i]);
+#pragma unroll
+        for (int j = 0; j < 3; j++) { Cm[i][j] = dot(A[i], B[j]); aC[i][j] = fabsf(Cm[i][j]); }
+    }
+    int best = -1; float bestpen = 0.f;
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        float pen = hA[i] + hB[0] * aC[i][0] + hB[1] * aC[i][1] + hB[2] * aC[i][2] - fabsf(tA[i]);
+        if (pen < 0.f) return;
+        if (best < 0 || pen < bestpen) { best = i; bestpen = pen; }
+    }
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+        float pen = hB[j] + hA[0] * aC[0][j] + hA[1] * aC[1][j] + hA[2] * aC[2][j] - fabsf(tB[j]);
+        if (pen < 0.f) return;
+        if (pen * FUDGE < bestpen) { best = 3 + j; bestpen = pen; }
+    }
+    V3 bestL = mk(0.f, 0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+            V3 L = cross(A[i], B[j]);
+            float l2 = dot(L, L);
+            if (l2 < 1e-6f) continue;
+            float l = sqrtf(l2);
+            const int i1 = (i + 1) % 3, i2 = (i + 2) % 3, j1 = (j + 1) % 3, j2 = (j + 2) % 3;
+            float rA = hA[i1] * aC[i2][j] + hA[i2] * aC[i1][j];
+            float rB = hB[j1] * aC[i][j2] + hB[j2] * aC[i][j1];
+            float pen = (rA + rB - fabsf(dot(t, L))) / l;
+            if (pen < 0.f) return;
+            if (pen * FUDGE < bestpen) { best = 6 + i * 3 + j; bestpen = pen; bestL = L * (1.f / l); }
+        }
+    }
+    if (best >= 6) {
+        int i = (best - 6) / 3, j = (best - 6) % 3;
+        V3 n = bestL * sgn1(dot(t, bestL));
+        V3 pA = cA, pB = cB;
+        for (int k = 0; k < 3; k++) {
+            if (k != i) pA = pA + A[k] * (sgn1(dot(n, A[k])) * hA[k]);
+            if (k != j) pB = pB - B[k] * (sgn1(dot(n, B[k])) * hB[k]);
+        }
+        V3 d = pB - pA;
+        float ab = Cm[i][j], da = dot(d, A[i]), db = dot(d, B[j]);
+        float den = 1.f - ab * ab;
+        float sa = (da - ab * db) / den, sb = (ab * da - db) / den;
+        add_contact(C, maxc, 0.5f * (pA + A[i] * sa + pB + B[j] * sb), n, bestpen, code);
+        return;
+    }
+    const bool refA = best < 3;
+    const int ax = refA ? best : best - 3;
+    V3 Rf[3], In[3]; float hR[3], hI[3];
+    for (int k = 0; k < 3; k++) { Rf[k] = refA ? A[k] : B[k]; In[k] = refA ? B[k] : A[k]; hR[k] = refA ? hA[k] : hB[k]; hI[k] = refA ? hB[k] : hA[k]; }
+    V3 cR = refA ? cA : cB, cI = refA ? cB : cA;
+    V3 nref = Rf[ax] * sgn1(dot(cI - cR, Rf[ax]));
+    int jf = 0; float bd = -1.f; float dj[3];
+    for (int j = 0; j < 3; j++) { dj[j] = dot(nref, In[j]); if (fabsf(dj[j]) > bd) { bd = fabsf(dj[j]); jf = j; } }
+    float fs = -sgn1(dj[jf]);
+    int j1 = (jf + 1) % 3, j2 = (jf + 2) % 3, u = (ax + 1) % 3, v = (ax + 2) % 3;
+    V3 poly0[8], poly1[8];
+    for (int k = 0; k < 4; k++) {
+        float s1 = (k == 0 || k == 3) ? 1.f : -1.f, s2 = (k < 2) ? 1.f : -1.f;
+        V3 wv = cI + In[jf] * (fs * hI[jf]) + In[j1] * (s1 * hI[j1]) + In[j2] * (s2 * hI[j2]) - cR;
+        poly0[k] = mk(dot(wv, Rf[u]), dot(wv, Rf[v]), dot(wv, nref));
+    }
+    int n = 4;
+    n = clip_poly(poly0, n, poly1, 0, 1.f, hR[u]);
+    n = clip_poly(poly1, n, poly0, 0, -1.f, hR[u]);
+    n = clip_poly(poly0, n, poly1, 1, 1.f, hR[v]);
+    n = clip_poly(poly1, n, poly0, 1, -1.f, hR[v]);
+    for (int k = 0; k < n; k++) {
+        float depth = hR[ax] - poly0[k].z;
+        if (depth < 0.f) continue;
+        float wn = poly0[k].z + 0.5f * depth;
+        V3 p = cR + Rf[u] * poly0[k].x + Rf[v] * poly0[k].y + nref * wn;
+        add_contact(C, maxc, p, refA ? nref : -nref, depth, code);
+    }
+}
+
+GG_HD void tangent_basis(V3 n, V3& t1, V3& t2) {
+    V3 ref = fabsf(n.x) < 0.57735f ? mk(1.f, 0.f, 0.f) : mk(0.f, 1.f, 0.f);
+    V3 t = ref - n * dot(ref, n);
+    t1 = t * (1.f / sqrtf(dot(t, t)));
+    t2 = cross(n, t1);
+}
+
+// solref / solimp impedance (power fixed at 2, checked by the host model compiler)
+GG_HD void imp_aref(const GgModel& M, float pos, float vel, float& imp, float& aref) {
+    float x = fabsf(pos) / M.width;
+    if (x >= 1.f) imp = M.dmax;
+    else if (x <= 0.f) imp = M.dmin;
+    else {
+        float y = x <= M.mid ? x * x / M.mid : 1.f - (1.f - x) * (1.f - x) / (1.f - M.mid);
+        imp = M.dmin + y * (M.dmax - M.dmin);
+    }
+    float Bc = 2.f / (M.dmax * M.tc), Kc = 1.f / (M.dmax * M.dmax * M.tc * M.tc * M.dr * M.dr);
+    aref = -Bc * vel - Kc * imp * pos;
+}
+
+// pads + cube narrow phase in the oracle's deterministic order: cube-plane, pads-plane, pads-cube
+template <int NA, int NF>
+GG_HD void collide(const GgModel& M, const RobotDyn<NA, NF>& D, V3 cp, const M3& cR, Contacts& C) {
+    C.count = 0;
+    const int maxc = M.max_contacts < GG_MAX_CONTACTS ? M.max_contacts : GG_MAX_CONTACTS;
+    V3 ch = ld3(M.cube_half);
+    plane_box(M.plane_z, cp, cR, ch, 0, maxc, C);
+    const float rc = sqrtf(dot(ch, ch));
+    bool any = false;
+    for (int g = 0; g < M.n_pads; g++) {       // bounding-sphere broad phase
+        int b = M.pad_body[g];
+        const M3& Rb = b == 0 ? D.lR : D.fR[b - 1 < NF ? (b - 1 < 0 ? 0 : b - 1) : 0];
+        V3 pb = b == 0 ? D.lp : D.fp[b - 1 < NF ? (b - 1 < 0 ? 0 : b - 1) : 0];
+        V3 c = pb + mul(Rb, ld3(M.pad_pos[g]));
+        V3 h = ld3(M.pad_half[g]);
+        float r = sqrtf(dot(h, h));
+        V3 d = c - cp;
+        any = any || (c.z - r <= M.plane_z) || (dot(d, d) <= (r + rc) * (r + rc));
+    }
+    if (!any) return;
+    for (int pass = 0; pass < 2; pass++) {
+        for (int g = 0; g < M.n_pads; g++) {
+            int b = M.pad_body[g];
+            int fi = b - 1 < 0 ? 0 : (b - 1 < NF ? b - 1 : 0);
+            M3 Rb = b == 0 ? D.lR : D.fR[fi];
+            V3 pb = b == 0 ? D.lp : D.fp[fi];
+            V3 c = pb + mul(Rb, ld3(M.pad_pos[g]));
+            M3 R = mmul(Rb, qmat(ldq(M.pad_quat[g])));
+            V3 h = ld3(M.pad_half[g]);
+            if (pass == 0) plane_box(M.plane_z, c, R, h, 1 + b, maxc, C);
+            else box_box(c, R, h, cp, cR, ch, 4 + b, maxc, C);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Contact-frame Jacobian rows (normal, tangent 1, tangent 2) of one contact: J (v_b - v_a) at p.
+// ---------------------------------------------------------------------------------------------
+template <int NA, int NF, bool FH>
+GG_HD void contact_jac(const RobotDyn<NA, NF>& D, V3 cp, const M3& cR, V3 p, V3 n, V3 t1, V3 t2, int code,
+                       float* Jn, float* Jt1, float* Jt2) {
+    constexpr int NU = NA + NF;
+    const int rb = code == 0 ? -1 : (code - 1) % 3;
+    const float sg = code >= 4 ? -1.f : 1.f;
+    const bool cube = code == 0 || code >= 4;
+#pragma unroll
+    for (int i = 0; i < NA; i++) {
+        V3 c = cross(D.jk[i], p - D.jo[i]);
+        bool on = rb >= 0;
+        Jn[i] = on ? sg * dot(n, c) : 0.f; Jt1[i] = on ? sg * dot(t1, c) : 0.f; Jt2[i] = on ? sg * dot(t2, c) : 0.f;
+    }
+#pragma unroll
+    for (int f = 0; f < NF; f++) {
+        V3 c = FH ? cross(D.fk[f], p - D.fo[f]) : D.fk[f];
+        bool on = rb == 1 + f;
+        Jn[NA + f] = on ? sg * dot(n, c) : 0.f; Jt1[NA + f] = on ? sg * dot(t1, c) : 0.f; Jt2[NA + f] = on ? sg * dot(t2, c) : 0.f;
+    }
+    V3 r = p - cp;
+    V3 a0 = cross(cR.c0, r), a1 = cross(cR.c1, r), a2 = cross(cR.c2, r);
+    Jn[NU + 0] = cube ? n.x : 0.f; Jn[NU + 1] = cube ? n.y : 0.f; Jn[NU + 2] = cube ? n.z : 0.f;
+    Jt1[NU + 0] = cube ? t1.x : 0.f; Jt1[NU + 1] = cube ? t1.y : 0.f; Jt1[NU + 2] = cube ? t1.z : 0.f;
+    Jt2[NU + 0] = cube ? t2.x : 0.f; Jt2[NU + 1] = cube ? t2.y : 0.f; Jt2[NU + 2] = cube ? t2.z : 0.f;
+    Jn[NU + 3] = cube ? dot(n, a0) : 0.f; Jn[NU + 4] = cube ? dot(n, a1) : 0.f; Jn[NU + 5] = cube ? dot(n, a2) : 0.f;
+    Jt1[NU + 3] = cube ? dot(t1, a0) : 0.f; Jt1[NU + 4] = cube ? dot(t1, a1) : 0.f; Jt1[NU + 5] = cube ? dot(t1, a2) : 0.f;
+    Jt2[NU + 3] = cube ? dot(t2, a0) : 0.f; Jt2[NU + 4] = cube ? dot(t2, a1) : 0.f; Jt2[NU + 5] = cube ? dot(t2, a2) : 0.f;
+}
+
+template <int N> GG_HD float dotn(const float* a, const float* b) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < N; i++) s += a[i] * b[i];
+    return s;
+}
+
+// per-contact solver scalars kept between passes
+struct ConRow {
+    float aref[GG_MAX_CONTACTS][4];
+    float D[GG_MAX_CONTACTS];
+    float u[GG_MAX_CONTACTS][3];    // Jc a
+    float w[GG_MAX_CONTACTS][3];    // Jc s
+};
+
+// row k of a contact: k = 0: n - mu t1, 1: n + mu t1, 2: n - mu t2, 3: n + mu t2
+GG_HD float rowval(const float* v3, float mu, int k) {
+    float t = k < 2 ? v3[1] : v3[2];
+    return v3[0] + ((k & 1) ? mu : -mu) * t;
+}
+
+// ---------------------------------------------------------------------------------------------
+// One substep.  General coupled Newton solve over all NU + 6 dofs (A.4): minimise
+//   1/2 (a - a_s)^T Mt (a - a_s) + sum_active 1/2 D (J a - aref)^2,  exact line search.
+// ---------------------------------------------------------------------------------------------
+template <int NA, int NF, bool FH>
+GG_HD void env_substep(const GgModel& M, EnvState<NA + NF>& s, const float* target, int iterations, float tol, StepInfo& info) {
+    constexpr int NU = NA + NF, NV = NU + 6, NH = NV * (NV + 1) / 2;
+    RobotDyn<NA, NF> D;
+    robot_dynamics<NA, NF, FH>(M, s.q, s.qd, target, D);
+    const M3 cR = qmat(s.cq);
+
+    // ---- smooth (unconstrained) acceleration a_s
+    float Mc[6] = {M.cube_mass, M.cube_mass, M.cube_mass, M.cube_inertia[0], M.cube_inertia[1], M.cube_inertia[2]};
+    float as[NV], qdv[NV];
+    {
+        float L[NU * (NU + 1) / 2];
+#pragma unroll
+        for (int i = 0; i < NU * (NU + 1) / 2; i++) L[i] = D.Mt[i];
+        chol_packed<NU>(L);
+        chol_solve_packed<NU>(L, D.fs, as);
+        V3 Iw = mk(Mc[3] * s.cw.x, Mc[4] * s.cw.y, Mc[5] * s.cw.z);
+        V3 gyro = cross(s.cw, Iw);
+        as[NU + 0] = 0.f; as[NU + 1] = 0.f; as[NU + 2] = -M.gravity;
+        as[NU + 3] = -gyro.x / Mc[3]; as[NU + 4] = -gyro.y / Mc[4]; as[NU + 5] = -gyro.z / Mc[5];
+#pragma unroll
+        for (int i = 0; i < NU; i++) qdv[i] = s.qd[i];
+        qdv[NU + 0] = s.cv.x; qdv[NU + 1] = s.cv.y; qdv[NU + 2] = s.cv.z;
+        qdv[NU + 3] = s.cw.x; qdv[NU + 4] = s.cw.y; qdv[NU + 5] = s.cw.z;
+    }
+
+    // ---- constraints: joint limits (one possible row per dof) and contacts
+    float lsg[NU], laref[NU], lD[NU];
+    int nlim = 0;
+#pragma unroll
+    for (int d = 0; d < NU; d++) {
+        float plo = s.q[d] - M.lim_lo[d], phi = M.lim_hi[d] - s.q[d];
+        float sg = plo < 0.f ? 1.f : (phi < 0.f ? -1.f : 0.f);
+        float pos = plo < 0.f ? plo : phi;
+        float imp, aref;
+        imp_aref(M, pos, sg * s.qd[d], imp, aref);
+        lsg[d] = sg; laref[d] = aref;
+        lD[d] = 1.f / fmaxf(M.minval, (1.f - imp) / imp * M.dof_invweight[d]);
+        nlim += sg != 0.f;
+    }
+    Contacts C;
+    collide<NA, NF>(M, D, s.cp, cR, C);
+    info.ncon = C.count;
+
+    float a[NV];
+    if (nlim == 0 && C.count == 0) {
+#pragma unroll
+        for (int i = 0; i < NV; i++) a[i] = as[i];
+        info.iters = 0; info.grad = 0.f;
+    } else {
+        ConRow R;
+        const float mu = M.friction;
+        // pass 0: aref / D per contact, J a for both warm-start candidates, their costs
+        float costw = 0.f, costs = 0.f;
+        {
+            float e[NV];
+#pragma unroll
+            for (int i = 0; i < NV; i++) e[i] = s.qacc[i] - as[i];
+            // 1/2 e^T Mt e
+#pragma unroll
+            for (int i = 0; i < NU; i++) {
+                float r = 0.f;
+#pragma unroll
+                for (int j = 0; j < NU; j++) r += D.Mt[i >= j ? GG_TRI(i, j) : GG_TRI(j, i)] * e[j];
+                costw += 0.5f * e[i] * r;
+            }
+#pragma unroll
+            for (int i = 0; i < 6; i++) costw += 0.5f * Mc[i] * e[NU + i] * e[NU + i];
+#pragma unroll
+            for (int d = 0; d < NU; d++) {
+                if (lsg[d] != 0.f) {
+                    float jw = lsg[d] * s.qacc[d] - laref[d], js = lsg[d] * as[d] - laref[d];
+                    if (jw < 0.f) costw += 0.5f * lD[d] * jw * jw;
+                    if (js < 0.f) costs += 0.5f * lD[d] * js * js;
+                }
+            }
+        }
+        float uw[3], us[3];
+        for (int c = 0; c < C.count; c++) {
+            float Jn[NV], Jt1[NV], Jt2[NV];
+            V3 t1, t2;
+            tangent_basis(C.n[c], t1, t2);
+            contact_jac<NA, NF, FH>(D, s.cp, cR, C.p[c], C.n[c], t1, t2, C.code[c], Jn, Jt1, Jt2);
+            float vel[3] = {dotn<NV>(Jn, qdv), dotn<NV>(Jt1, qdv), dotn<NV>(Jt2, qdv)};
+            uw[0] = dotn<NV>(Jn, s.qacc); uw[1] = dotn<NV>(Jt1, s.qacc); uw[2] = dotn<NV>(Jt2, s.qacc);
+            us[0] = dotn<NV>(Jn, as); us[1] = dotn<NV>(Jt1, as); us[2] = dotn<NV>(Jt2, as);
+            int code = C.code[c];
+            int rb = code == 0 ? -1 : (code - 1) % 3;
+            float wsum = (rb >= 0 ? M.body_invweight[rb] : 0.f) + ((code == 0 || code >= 4) ? M.cube_invweight : 0.f);
+            float imp = 0.f, ar = 0.f;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                imp_aref(M, -C.depth[c], rowval(vel, mu, k), imp, ar);
+                R.aref[c][k] = ar;
+                float jw = rowval(uw, mu, k) - ar, js = rowval(us, mu, k) - ar;
+                float Dk = 1.f / fmaxf(M.minval, 2.f * mu * mu * (1.f - imp) / imp * wsum * (1.f + mu * mu));
+                R.D[c] = Dk;
+                if (jw < 0.f) costw += 0.5f * Dk * jw * jw;
+                if (js < 0.f) costs += 0.5f * Dk * js * js;
+            }
+            // provisional: keep both, decide below
+            R.u[c][0] = uw[0]; R.u[c][1] = uw[1]; R.u[c][2] = uw[2];
+            R.w[c][0] = us[0]; R.w[c][1] = us[1]; R.w[c][2] = us[2];
+        }
+        const bool warm = costw < costs;
+#pragma unroll
+        for (int i = 0; i < NV; i++) a[i] = warm ? s.qacc[i] : as[i];
+        if (!warm) for (int c = 0; c < C.count; c++) { R.u[c][0] = R.w[c][0]; R.u[c][1] = R.w[c][1]; R.u[c][2] = R.w[c][2]; }
+
+        float meaninertia = 0.f;
+#pragma unroll
+        for (int i = 0; i < NU; i++) meaninertia += D.Mt[GG_TRI(i, i)];
+#pragma unroll
+        for (int i = 0; i < 6; i++) meaninertia += Mc[i];
+        const float scale = 1.f / meaninertia;      // = 1 / (mean * NV)
+        int it = 0; float gnorm = 0.f;
+        for (; it < iterations; it++) {
+            float H[NH], g[NV];
+            // H = Mt, g = Mt (a - a_s)
+#pragma unroll
+            for (int i = 0; i < NH; i++) H[i] = 0.f;
+#pragma unroll
+            for (int i = 0; i < NU * (NU + 1) / 2; i++) H[i] = D.Mt[i];
+#pragma unroll
+            for (int i = 0; i < 6; i++) H[GG_TRI(NU + i, NU + i)] = Mc[i];
+            {
+                float e[NV];
+#pragma unroll
+                for (int i = 0; i < NV; i++) e[i] = a[i] - as[i];
+#pragma unroll
+                for (int i = 0; i < NU; i++) {
+                    float r = 0.f;
+#pragma unroll
+                    for (int j = 0; j < NU; j++) r += D.Mt[i >= j ? GG_TRI(i, j) : GG_TRI(j, i)] * e[j];
+                    g[i] = r;
+                }
+#pragma unroll
+                for (int i = 0; i < 6; i++) g[NU + i] = Mc[i] * e[NU + i];
+            }
+#pragma unroll
+            for (int d = 0; d < NU; d++) {
+                float jar = lsg[d] * a[d] - laref[d];
+                if (lsg[d] != 0.f && jar < 0.f) { H[GG_TRI(d, d)] += lD[d]; g[d] += lD[d] * jar * lsg[d]; }
+            }
+            for (int c = 0; c < C.count; c++) {
+                float Wnn = 0.f, Wn1 = 0.f, W11 = 0.f, Wn2 = 0.f, W22 = 0.f, gn = 0.f, g1 = 0.f, g2 = 0.f;
+                const float Dk = R.D[c];
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    float jar = rowval(R.u[c], mu, k) - R.aref[c][k];
+                    if (jar < 0.f) {
+                        float sm = (k & 1) ? mu : -mu;
+                        Wnn += Dk; gn += Dk * jar;
+                        if (k < 2) { Wn1 += Dk * sm; W11 += Dk * mu * mu; g1 += Dk * jar * sm; }
+                        else { Wn2 += Dk * sm; W22 += Dk * mu * mu; g2 += Dk * jar * sm; }
+                    }
+                }
+                if (Wnn == 0.f) continue;
+                float Jn[NV], Jt1[NV], Jt2[NV];
+                V3 t1, t2;
+                tangent_basis(C.n[c], t1, t2);
+                const int code = C.code[c];
+                contact_jac<NA, NF, FH>(D, s.cp, cR, C.p[c], C.n[c], t1, t2, code, Jn, Jt1, Jt2);
+                float Pn[NV], P1[NV], P2[NV];
+#pragma unroll
+                for (int i = 0; i < NV; i++) {
+                    g[i] += Jn[i] * gn + Jt1[i] * g1 + Jt2[i] * g2;
+                    Pn[i] = Wnn * Jn[i] + Wn1 * Jt1[i] + Wn2 * Jt2[i];
+                    P1[i] = Wn1 * Jn[i] + W11 * Jt1[i];
+                    P2[i] = Wn2 * Jn[i] + W22 * Jt2[i];
+                }
+                if (code == 0) {            // cube block only
+#pragma unroll
+                    for (int i = NU; i < NV; i++)
+#pragma unroll
+                        for (int j = NU; j <= i; j++) H[GG_TRI(i, j)] += Jn[i] * Pn[j] + Jt1[i] * P1[j] + Jt2[i] * P2[j];
+                } else if (code < 4) {      // robot block only
+#pragma unroll
+                    for (int i = 0; i < NU; i++)
+#pragma unroll
+                        for (int j = 0; j <= i; j++) H[GG_TRI(i, j)] += Jn[i] * Pn[j] + Jt1[i] * P1[j] + Jt2[i] * P2[j];
+                } else {
+#pragma unroll
+                    for (int i = 0; i < NV; i++)
+#pragma unroll
+                        for (int j = 0; j <= i; j++) H[GG_TRI(i, j)] += Jn[i] * Pn[j] + Jt1[i] * P1[j] + Jt2[i] * P2[j];
+                }
+            }
+            gnorm = sqrtf(dotn<NV>(g, g)) * scale;
+            if (gnorm < tol) break;
+            if (!chol_packed<NV>(H)) break;
+            float sdir[NV];
+#pragma unroll
+            for (int i = 0; i < NV; i++) g[i] = -g[i];
+            chol_solve_packed<NV>(H, g, sdir);
+            // line-search quadratic part: q1 = s^T Mt (a - a_s), q2 = s^T Mt s
+            float q1 = 0.f, q2 = 0.f;
+#pragma unroll
+            for (int i = 0; i < NU; i++) {
+                float r = 0.f;
+#pragma unroll
+                for (int j = 0; j < NU; j++) r += D.Mt[i >= j ? GG_TRI(i, j) : GG_TRI(j, i)] * sdir[j];
+                q1 += r * (a[i] - as[i]); q2 += r * sdir[i];
+            }
+#pragma unroll
+            for (int i = 0; i < 6; i++) { q1 += Mc[i] * sdir[NU + i] * (a[NU + i] - as[NU + i]); q2 += Mc[i] * sdir[NU + i] * sdir[NU + i]; }
+            for (int c = 0; c < C.count; c++) {
+                float Jn[NV], Jt1[NV], Jt2[NV];
+                V3 t1, t2;
+                tangent_basis(C.n[c], t1, t2);
+                contact_jac<NA, NF, FH>(D, s.cp, cR, C.p[c], C.n[c], t1, t2, C.code[c], Jn, Jt1, Jt2);
+                R.w[c][0] = dotn<NV>(Jn, sdir); R.w[c][1] = dotn<NV>(Jt1, sdir); R.w[c][2] = dotn<NV>(Jt2, sdir);
+            }
+            // safeguarded Newton on phi'(alpha) (piecewise linear, increasing)
+            float al = 0.f, lo = 0.f, hi = -1.f, d0 = 0.f, d1 = 0.f, d2 = 1.f;
+            for (int ls = 0; ls < 12; ls++) {
+                if (ls > 0) {
+                    float nx = al - d1 / d2;
+                    if (hi >= 0.f && (nx <= lo || nx >= hi)) nx = 0.5f * (lo + hi);
+                    if (nx <= 0.f) nx = hi >= 0.f ? 0.5f * (lo + hi) : 1e-3f;
+                    al = nx;
+                }
+                d1 = q1 + al * q2; d2 = q2;
+#pragma unroll
+                for (int d = 0; d < NU; d++) {
+                    if (lsg[d] != 0.f) {
+                        float jv = lsg[d] * sdir[d];
+                        float x = lsg[d] * a[d] - laref[d] + al * jv;
+                        if (x < 0.f) { d1 += lD[d] * x * jv; d2 += lD[d] * jv * jv; }
+                    }
+                }
+                for (int c = 0; c < C.count; c++) {
+                    const float Dk = R.D[c];
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        float jv = rowval(R.w[c], mu, k);
+                        float x = rowval(R.u[c], mu, k) - R.aref[c][k] + al * jv;
+                        if (x < 0.f) { d1 += Dk * x * jv; d2 += Dk * jv * jv; }
+                    }
+                }
+                if (ls == 0) { d0 = d1; continue; }
+                if (d1 < 0.f) lo = al; else hi = al;
+                if (fabsf(d1) <= fabsf(d0) * 1e-6f) break;
+            }
+#pragma unroll
+            for (int i = 0; i < NV; i++) a[i] += al * sdir[i];
+            for (int c = 0; c < C.count; c++) { R.u[c][0] += al * R.w[c][0]; R.u[c][1] += al * R.w[c][1]; R.u[c][2] += al * R.w[c][2]; }
+        }
+        info.iters = it; info.grad = gnorm;
+    }
+
+    // ---- semi-implicit Euler
+    const float dt = M.dt;
+#pragma unroll
+    for (int i = 0; i < NV; i++) s.qacc[i] = a[i];
+#pragma unroll
+    for (int i = 0; i < NU; i++) { s.qd[i] += a[i] * dt; s.q[i] += s.qd[i] * dt; }
+    s.cv = s.cv + mk(a[NU], a[NU + 1], a[NU + 2]) * dt;
+    s.cw = s.cw + mk(a[NU + 3], a[NU + 4], a[NU + 5]) * dt;
+    s.cp = s.cp + s.cv * dt;
+    {
+        V3 w = s.cw * dt;
+        float ang = sqrtf(dot(w, w));
+        Q4 dq = mkq(1.f, 0.f, 0.f, 0.f);
+        if (ang > 0.f) {
+            float sn, cs;
+            gg_sincos(0.5f * ang, &sn, &cs);
+            float k = sn / ang;
+            dq = mkq(cs, w.x * k, w.y * k, w.z * k);
+        }
+        Q4 nq = qmul(s.cq, dq);
+        float inv = 1.f / sqrtf(nq.w * nq.w + nq.x * nq.x + nq.y * nq.y + nq.z * nq.z);
+        s.cq = mkq(nq.w * inv, nq.x * inv, nq.y * inv, nq.z * inv);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Observation / reward / success of the reference task classes
+// (franka/cube_pick.py:130-157; env.py:63-65).  agent: 7 + NF floats, envs: 11 floats.
+// ---------------------------------------------------------------------------------------------
+template <int NA, int NF>
+GG_HD void env_observe(const GgModel& M, const EnvState<NA + NF>& s, float* agent, float* envs, float& reward, bool& success) {
+    V3 ep; Q4 eq;
+    robot_eef<NA, NF>(M, s.q, ep, eq);
+    agent[0] = ep.x; agent[1] = ep.y; agent[2] = ep.z;
+    agent[3] = eq.w; agent[4] = eq.x; agent[5] = eq.y; agent[6] = eq.z;
+#pragma unroll
+    for (int f = 0; f < NF; f++) agent[7 + f] = s.q[NA + f];
+    envs[0] = s.cp.x; envs[1] = s.cp.y; envs[2] = s.cp.z;
+    envs[3] = s.cq.w; envs[4] = s.cq.x; envs[5] = s.cq.y; envs[6] = s.cq.z;
+    V3 d = ep - s.cp;
+    envs[7] = d.x; envs[8] = d.y; envs[9] = d.z;
+    envs[10] = sqrtf(dot(d, d));
+    success = s.cp.z > M.success_z;
+    reward = success ? 1.f : 0.f;
+}
+
+// reset one env: home pose, zero velocities / warm start, cube at (x, y, spawn_z) with the spawn quaternion
+template <int NU>
+GG_HD void env_reset(const GgModel& M, EnvState<NU>& s, float x, float y) {
+#pragma unroll
+    for (int i = 0; i < NU; i++) { s.q[i] = M.home_q[i]; s.qd[i] = 0.f; }
+#pragma unroll
+    for (int i = 0; i < NU + 6; i++) s.qacc[i] = 0.f;
+    s.cp = mk(x, y, M.spawn_z);
+    s.cq = ldq(M.spawn_quat);
+    s.cv = mk(0.f, 0.f, 0.f); s.cw = mk(0.f, 0.f, 0.f);
+}
+
+// device-side spawn draw: Philox counter (global env id, episode, 0, 0), key = seed
+GG_HD void spawn_draw(const GgModel& M, uint64_t seed, uint32_t gid, uint32_t episode, float& x, float& y) {
+    uint32_t o[4];
+    philox4x32_10(gid, episode, 0u, 0u, (uint32_t)seed, (uint32_t)(seed >> 32), o);
+    x = fmaf(u01(o[0]), M.spawn_hi[0] - M.spawn_lo[0], M.spawn_lo[0]);
+    y = fmaf(u01(o[1]), M.spawn_hi[1] - M.spawn_lo[1], M.spawn_lo[1]);
+}
+
+}  // namespace gg

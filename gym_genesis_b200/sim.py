@@ -1,0 +1,164 @@
+"""Torch-facing host wrapper of the C-ABI simulator (`include/gg_b200.h`).
+
+PyTorch is plumbing here: it owns the device memory (state, observations, flags) and supplies the
+CUDA stream; every computation of the step path happens inside `libgg_b200.so`.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import cabi
+from .model import SceneModel
+
+
+class GgError(RuntimeError):
+    pass
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+class BatchedSim:
+    """N independent worlds (arm + gripper + free cube + plane) stepped by one CUDA kernel per env.step.
+
+    Replaces, for this path, the Genesis `Scene`/`RigidSolver` objects the reference task holds
+    (`gym_genesis/tasks/franka/cube_pick.py:37-68`).
+    """
+
+    def __init__(self, scene_model: SceneModel, n_envs: int, device="cuda", solver_iterations: int = 10,
+                 solver_tolerance: float = 1e-6, auto_reset: bool = False, time_limit: bool = False, reset_prob: float = 0.0,
+                 seed: int = 0, first_env_id: int = 0):
+        if not torch.cuda.is_available():
+            raise GgError("gym_genesis_b200 needs a CUDA device: the env.step path has no CPU fallback")
+        self.lib = cabi.load_library()
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise ValueError(f"device must be a CUDA device, got {device}")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        self.scene_model = scene_model
+        self.gg_model = cabi.compile_gg(scene_model)
+        self.n_envs = int(n_envs)
+        self.nu = scene_model.nu
+        self.nq, self.nv = self.nu + 7, self.nu + 6
+        self.agent_dim = 7 + scene_model.n_fing
+        h = C.c_void_p()
+        self._check(self.lib.gg_create(C.byref(self.gg_model), self.n_envs, self.device.index, C.byref(h)))
+        self._h = h
+        rows, stride = self.lib.gg_state_rows(h), self.lib.gg_state_stride(h)
+        dev = self.device
+        # struct-of-arrays state: [field component][env], env fastest (coalesced per warp)
+        self.state = torch.zeros((rows, stride), dtype=torch.float32, device=dev)
+        self.step_count = torch.zeros(self.n_envs, dtype=torch.int32, device=dev)
+        self.episode = torch.zeros(self.n_envs, dtype=torch.int32, device=dev)
+        self._check(self.lib.gg_bind_state(h, _ptr(self.state), _ptr(self.step_count), _ptr(self.episode)))
+        self.obs_agent = torch.zeros((self.n_envs, self.agent_dim), dtype=torch.float32, device=dev)
+        self.obs_env = torch.zeros((self.n_envs, 11), dtype=torch.float32, device=dev)
+        self.reward = torch.zeros(self.n_envs, dtype=torch.float32, device=dev)
+        self.terminated = torch.zeros(self.n_envs, dtype=torch.uint8, device=dev)
+        self.truncated = torch.zeros(self.n_envs, dtype=torch.uint8, device=dev)
+        self._stats = torch.zeros(8, dtype=torch.float64, device=dev)
+        self.cfg = cabi.GgConfig(solver_iterations, solver_tolerance, int(auto_reset), int(time_limit), float(reset_prob),
+                                 int(seed) & (2 ** 64 - 1), int(first_env_id))
+        self._check(self.lib.gg_configure(h, C.byref(self.cfg)))
+
+    # ------------------------------------------------------------------------------------------
+    def _check(self, rc):
+        if rc != 0:
+            raise GgError(self.lib.gg_last_error().decode())
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def configure(self, **kw):
+        for k, v in kw.items():
+            if not hasattr(self.cfg, k):
+                raise AttributeError(k)
+            setattr(self.cfg, k, v)
+        self._check(self.lib.gg_configure(self._h, C.byref(self.cfg)))
+
+    def close(self):
+        if getattr(self, "_h", None) is not None:
+            self.lib.gg_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------------------------------
+    def _as_action(self, action) -> torch.Tensor:
+        if not isinstance(action, torch.Tensor):
+            action = torch.as_tensor(np.asarray(action), dtype=torch.float32)
+        if action.shape != (self.n_envs, self.nu):
+            raise ValueError(f"action must have shape ({self.n_envs}, {self.nu}), got {tuple(action.shape)}")
+        if action.device != self.device or action.dtype != torch.float32 or not action.is_contiguous():
+            action = action.to(device=self.device, dtype=torch.float32, non_blocking=True).contiguous()
+        return action
+
+    def _as_mask(self, mask) -> Optional[torch.Tensor]:
+        if mask is None:
+            return None
+        if not isinstance(mask, torch.Tensor):
+            mask = torch.as_tensor(np.asarray(mask))
+        if mask.shape != (self.n_envs,):
+            raise ValueError(f"mask must have shape ({self.n_envs},), got {tuple(mask.shape)}")
+        return mask.to(device=self.device, dtype=torch.uint8).contiguous()
+
+    def step(self, action, reset_mask=None):
+        """One env.step (= one 0.01 s substep) for all envs; results land in the preallocated
+        obs_agent / obs_env / reward / terminated / truncated tensors (no host sync)."""
+        a = self._as_action(action)
+        m = self._as_mask(reset_mask)
+        self._last_action = a          # PD targets persist (reference: control_dofs_position semantics)
+        self._check(self.lib.gg_step(self._h, _ptr(a), _ptr(self.obs_agent), _ptr(self.obs_env), _ptr(self.reward),
+                                     _ptr(self.terminated), _ptr(self.truncated), _ptr(m), self._stream()))
+
+    def reset(self, mask=None, cube_xy=None):
+        m = self._as_mask(mask)
+        xy = None
+        if cube_xy is not None:
+            xy = torch.as_tensor(np.asarray(cube_xy, dtype=np.float32) if not isinstance(cube_xy, torch.Tensor) else cube_xy)
+            if xy.shape != (self.n_envs, 2):
+                raise ValueError(f"cube_xy must have shape ({self.n_envs}, 2)")
+            xy = xy.to(device=self.device, dtype=torch.float32).contiguous()
+        self._last_action = None
+        self._check(self.lib.gg_reset(self._h, _ptr(m), _ptr(xy), _ptr(self.obs_agent), _ptr(self.obs_env), self._stream()))
+
+    def observe(self):
+        self._check(self.lib.gg_observe(self._h, _ptr(self.obs_agent), _ptr(self.obs_env), _ptr(self.reward), _ptr(self.terminated),
+                                        self._stream()))
+
+    def get_state(self):
+        q = torch.empty((self.n_envs, self.nq), dtype=torch.float32, device=self.device)
+        qd = torch.empty((self.n_envs, self.nv), dtype=torch.float32, device=self.device)
+        qacc = torch.empty((self.n_envs, self.nv), dtype=torch.float32, device=self.device)
+        self._check(self.lib.gg_get_state(self._h, _ptr(q), _ptr(qd), _ptr(qacc), self._stream()))
+        return q, qd, qacc
+
+    def set_state(self, q=None, qd=None, qacc=None):
+        def prep(t, k):
+            if t is None:
+                return None
+            t = torch.as_tensor(t, dtype=torch.float32).to(self.device).contiguous()
+            if t.shape != (self.n_envs, k):
+                raise ValueError(f"expected shape ({self.n_envs}, {k}), got {tuple(t.shape)}")
+            return t
+        q, qd, qacc = prep(q, self.nq), prep(qd, self.nv), prep(qacc, self.nv)
+        self._check(self.lib.gg_set_state(self._h, _ptr(q), _ptr(qd), _ptr(qacc), self._stream()))
+
+    def stats(self, clear=False) -> torch.Tensor:
+        """[env-steps, episodes finished, successes, return sum, length sum, non-finite resets, solver iterations, contacts]."""
+        self._check(self.lib.gg_stats(self._h, _ptr(self._stats), int(clear), self._stream()))
+        return self._stats
+
+    @staticmethod
+    def launch_count() -> int:
+        return int(cabi.load_library().gg_launch_count())

@@ -1,0 +1,125 @@
+/* gg_b200.h -- C ABI of the B200-native batched env.step for the gym-genesis manipulation tasks.
+ *
+ * The reference has no FFI: its hot path is Python calling the Genesis entity API.  Each entry
+ * point below replaces one group of those calls (citations are into /root/reference):
+ *
+ *   gg_create        <- scene.build(n_envs=N)                      gym_genesis/tasks/franka/cube_pick.py:65
+ *                       (+ model upload: add_entity Plane/MJCF/Box  :50-54, SimOptions dt=0.01 :45)
+ *   gg_bind_state    <- Genesis-internal field allocation (same call; torch owns the memory here)
+ *   gg_reset         <- cube.set_pos/set_quat, franka.set_qpos(zero_velocity=True),
+ *                       control_dofs_position(home) x2, scene.step(), get_obs()          :86-112
+ *   gg_step          <- control_dofs_position(action[:, :7]) / (action[:, 7:]), scene.step(),
+ *                       compute_reward(), get_obs()                                     :122-157
+ *                       and GenesisEnv.step's is_success / terminated / truncated        gym_genesis/env.py:61-69
+ *   gg_get_state /
+ *   gg_set_state     <- entity.get_qpos / get_dofs_velocity / set_qpos / set_dofs_velocity (state injection,
+ *                       used by the parity harness)
+ *   gg_stats         <- (new) per-shard episode statistics for the optional NCCL all-gather
+ *
+ * Conventions: plain pointers and sizes only; every pointer argument of gg_step / gg_reset is a
+ * DEVICE pointer into caller-owned (torch) memory unless stated otherwise; all work is enqueued
+ * asynchronously on `stream`; no allocation and no host synchronisation after gg_create.
+ * Return value: 0 = ok, negative = error (message via gg_last_error()).
+ */
+#ifndef GG_B200_H
+#define GG_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GG_MAX_ARM 7        /* serial hinge chain (Panda 7, SO-101 5)                     */
+#define GG_MAX_FING 2       /* gripper dofs hanging off the last arm link (Panda 2 slides) */
+#define GG_MAX_DOF 9
+#define GG_MAX_PADS 12      /* box collision geoms on the gripper                          */
+#define GG_MAX_CONTACTS 64  /* per-env contact cap (deterministic order)    */
+#define GG_ENV_STATE_DIM 11 /* cube pos3 + quat4 + (eef - cube)3 + |.|1                    */
+
+typedef struct CUstream_st* gg_stream_t;
+typedef struct GgSim GgSim;
+
+/* Compiled scene constants (host fills this once; copied to the device at gg_create).
+ * Arm link l is a hinge about its own local z axis; the last arm link carries its fixed children
+ * (Panda "hand") merged into mass/com/inertia.  Fingers are children of the last arm link. */
+typedef struct GgModel {
+    int32_t n_arm, n_fing, fing_hinge, n_pads;
+    int32_t settle_steps, horizon, max_contacts, reserved0;
+    float base_pos[3], base_quat[4];
+    float link_pos[GG_MAX_ARM][3], link_quat[GG_MAX_ARM][4];
+    float link_mass[GG_MAX_ARM], link_com[GG_MAX_ARM][3], link_inertia[GG_MAX_ARM][6]; /* xx yy zz xy xz yz */
+    float fing_pos[GG_MAX_FING][3], fing_quat[GG_MAX_FING][4], fing_axis[GG_MAX_FING][3];
+    float fing_mass[GG_MAX_FING], fing_com[GG_MAX_FING][3], fing_inertia[GG_MAX_FING][6];
+    float eef_pos[3], eef_quat[4];               /* observed end-effector frame in the last arm link */
+    float armature[GG_MAX_DOF], damping[GG_MAX_DOF], kp[GG_MAX_DOF], kv[GG_MAX_DOF];
+    float frc_lo[GG_MAX_DOF], frc_hi[GG_MAX_DOF], lim_lo[GG_MAX_DOF], lim_hi[GG_MAX_DOF];
+    float dof_invweight[GG_MAX_DOF];
+    float body_invweight[1 + GG_MAX_FING];        /* last arm link, finger 0, finger 1 */
+    int32_t pad_body[GG_MAX_PADS];                /* 0 = last arm link, 1 + f = finger f */
+    float pad_half[GG_MAX_PADS][3], pad_pos[GG_MAX_PADS][3], pad_quat[GG_MAX_PADS][4];
+    float cube_half[3], cube_mass, cube_inertia[3], cube_invweight;
+    float dt, gravity, plane_z, friction;
+    float tc, dr, dmin, dmax, width, mid, power, minval;   /* solref / solimp */
+    float home_q[GG_MAX_DOF];
+    float spawn_lo[2], spawn_hi[2], spawn_z, spawn_quat[4], success_z;
+} GgModel;
+
+/* Run-time options; defaults (all zero except iterations/tolerance) reproduce the reference. */
+typedef struct GgConfig {
+    int32_t solver_iterations;   /* Newton iteration cap per substep (default 10)                  */
+    float solver_tolerance;      /* scaled-gradient stop criterion (default 1e-6)                  */
+    int32_t auto_reset;          /* 1: envs that finished (terminated|truncated) reset on next step */
+    int32_t time_limit;          /* 1: truncated = step_count >= model.horizon (reference: always 0)*/
+    float reset_prob;            /* per-env Bernoulli reset probability per step (benchmark C3)      */
+    uint64_t seed;               /* Philox key for device-side spawn draws and random resets         */
+    int64_t first_env_id;        /* global id of local env 0 (multi-GPU sharding)                    */
+} GgConfig;
+
+const char* gg_last_error(void);
+int gg_version(void);
+
+int gg_create(const GgModel* model, int n_envs, int device, GgSim** out);
+int gg_destroy(GgSim* sim);
+int gg_configure(GgSim* sim, const GgConfig* cfg);
+
+/* State lives in ONE caller-owned float32 device buffer of gg_state_rows() x gg_state_stride()
+ * (struct-of-arrays, env index fastest) plus two int32[n_envs] counters. */
+int gg_state_rows(const GgSim* sim);
+int gg_state_stride(const GgSim* sim);
+int gg_bind_state(GgSim* sim, float* state, int32_t* step_count, int32_t* episode);
+
+/* One env.step for every env.  action: (n_envs, n_dof) row-major absolute joint targets.
+ * obs_agent: (n_envs, 7 + n_fing); obs_env: (n_envs, 11); reward: (n_envs); terminated /
+ * truncated: (n_envs) bytes.  reset_mask (nullable): envs with a non-zero byte are reset (spawn
+ * draw + home pose + settle step) instead of stepped. */
+int gg_step(GgSim* sim, const float* action, float* obs_agent, float* obs_env, float* reward,
+            uint8_t* terminated, uint8_t* truncated, const uint8_t* reset_mask, gg_stream_t stream);
+
+/* Reset envs selected by mask (NULL = all).  cube_xy (nullable): (n_envs, 2) explicit spawn
+ * positions (the host RandomState stream of the reference); NULL -> device Philox draw keyed by
+ * (cfg.seed, global env id, episode).  Runs model.settle_steps substeps holding the home target
+ * for the reset envs, then writes observations for all envs. */
+int gg_reset(GgSim* sim, const uint8_t* mask, const float* cube_xy, float* obs_agent, float* obs_env,
+             gg_stream_t stream);
+
+/* Env-major copies for state injection / inspection: q (n_envs, n_dof + 7), qd and qacc (n_envs, n_dof + 6). */
+int gg_get_state(GgSim* sim, float* q, float* qd, float* qacc, gg_stream_t stream);
+int gg_set_state(GgSim* sim, const float* q, const float* qd, const float* qacc, gg_stream_t stream);
+
+/* Recompute observations / reward / terminated from the current state without stepping. */
+int gg_observe(GgSim* sim, float* obs_agent, float* obs_env, float* reward, uint8_t* terminated, gg_stream_t stream);
+
+/* Device-side episode statistics accumulated by gg_step (8 doubles written to `out8`, DEVICE pointer):
+ * [0] env-steps, [1] episodes finished, [2] successes, [3] return sum, [4] length sum,
+ * [5] non-finite envs auto-reset, [6] solver iterations sum, [7] contacts sum. */
+int gg_stats(GgSim* sim, double* out8, int clear, gg_stream_t stream);
+
+/* Number of kernels this library has launched since load (for bench.py's gpu_launches). */
+int64_t gg_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GG_B200_H */

@@ -1,0 +1,184 @@
+"""ctypes loader for the CPU oracle (`oracle/liboracle.so`).
+
+TEST INFRASTRUCTURE ONLY (parity unpinned, see oracle/oracle.cpp header).  Only `tests/`,
+`__graft_entry__.smoke()` and `bench.py`'s cpu_baseline / `--impl reference` legs may import this.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "liboracle.so")
+
+_INT_FIELDS = ["parent", "jtype", "dofadr", "qadr", "limited", "ctrl", "geom_body", "geom_group"]
+_DBL_FIELDS = ["pos", "quat", "axis", "mass", "com", "inertia", "body_invweight", "dof_invweight",
+               "armature", "damping", "kp", "kv", "frc_lo", "frc_hi", "lim_lo", "lim_hi",
+               "geom_half", "geom_pos", "geom_quat", "opt", "spawn_quat", "home_q"]
+_SCALARS = ["nb", "nv", "nq", "nu", "ngeom", "eef_body", "cube_body", "max_contacts"]
+
+
+class _OrcModel(C.Structure):
+    _fields_ = ([(n, C.c_int32) for n in _SCALARS]
+                + [(n, C.POINTER(C.c_int32)) for n in _INT_FIELDS]
+                + [(n, C.POINTER(C.c_double)) for n in _DBL_FIELDS])
+
+
+def build(force: bool = False) -> str:
+    src = os.path.join(_HERE, "oracle.cpp")
+    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "-s"] + (["-B"] if force else []))
+    return _LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB_PATH):
+            build()
+        _lib = C.CDLL(_LIB_PATH)
+        _lib.orc_create.restype = C.c_void_p
+        _lib.orc_create.argtypes = [C.POINTER(_OrcModel)]
+        _lib.orc_destroy.argtypes = [C.c_void_p]
+        _lib.orc_num_threads.restype = C.c_int
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class Oracle:
+    """Generic-tree CPU oracle bound to one `SceneModel` (gym_genesis_b200.model)."""
+
+    def __init__(self, scene_model, dtype=np.float64):
+        self.model = scene_model
+        self.flat = scene_model.flat()
+        self.dtype = np.dtype(dtype)
+        self.suf = "f64" if self.dtype == np.float64 else "f32"
+        self.ct = C.c_double if self.dtype == np.float64 else C.c_float
+        cm = _OrcModel()
+        self._keep = []
+        for n in _SCALARS:
+            setattr(cm, n, int(self.flat[n]))
+        for n in _INT_FIELDS:
+            a = np.ascontiguousarray(self.flat[n], dtype=np.int32)
+            self._keep.append(a)
+            setattr(cm, n, a.ctypes.data_as(C.POINTER(C.c_int32)))
+        for n in _DBL_FIELDS:
+            a = np.ascontiguousarray(self.flat[n], dtype=np.float64)
+            self._keep.append(a)
+            setattr(cm, n, a.ctypes.data_as(C.POINTER(C.c_double)))
+        self.h = C.c_void_p(lib().orc_create(C.byref(cm)))
+        for k in ("nb", "nv", "nq", "nu"):
+            setattr(self, k, int(self.flat[k]))
+        self.agent_dim = 7 + scene_model.n_fing
+
+    def __del__(self):
+        try:
+            lib().orc_destroy(self.h)
+        except Exception:
+            pass
+
+    def _fn(self, name):
+        return getattr(lib(), f"orc_{name}_{self.suf}")
+
+    def _a(self, x, shape=None):
+        a = np.ascontiguousarray(x, dtype=self.dtype)
+        if shape is not None:
+            a = a.reshape(shape)
+        return a
+
+    # ---- diagnostics -------------------------------------------------------------------------
+    def fk(self, q):
+        q = self._a(q)
+        xpos = np.zeros((self.nb, 3), self.dtype)
+        xquat = np.zeros((self.nb, 4), self.dtype)
+        self._fn("fk")(self.h, _p(q), _p(xpos), _p(xquat))
+        return xpos, xquat
+
+    def dynamics(self, q, qd, target):
+        q, qd, target = self._a(q), self._a(qd), self._a(target)
+        nv = self.nv
+        M, Mt = np.zeros((nv, nv), self.dtype), np.zeros((nv, nv), self.dtype)
+        bias, tau, a_s = (np.zeros(nv, self.dtype) for _ in range(3))
+        self._fn("dynamics")(self.h, _p(q), _p(qd), _p(target), _p(M), _p(Mt), _p(bias), _p(tau), _p(a_s))
+        return dict(M=M, Mt=Mt, bias=bias, tau=tau, a_smooth=a_s)
+
+    def contacts(self, q, cap=128):
+        q = self._a(q)
+        out = np.zeros((cap, 9), self.dtype)
+        f = self._fn("contacts")
+        f.restype = C.c_int
+        n = f(self.h, _p(q), _p(out), C.c_int(cap))
+        return out[: min(n, cap)]
+
+    def rows(self, q, qd, cap=512):
+        q, qd = self._a(q), self._a(qd)
+        J = np.zeros((cap, self.nv), self.dtype)
+        aref, D = np.zeros(cap, self.dtype), np.zeros(cap, self.dtype)
+        f = self._fn("rows")
+        f.restype = C.c_int
+        n = f(self.h, _p(q), _p(qd), _p(J), _p(aref), _p(D), C.c_int(cap))
+        n = min(n, cap)
+        return J[:n], aref[:n], D[:n]
+
+    def invweight(self, q0_full):
+        q0 = self._a(q0_full)
+        bw, dw = np.zeros(self.nb, self.dtype), np.zeros(self.nv, self.dtype)
+        self._fn("invweight")(self.h, _p(q0), _p(bw), _p(dw))
+        return bw, dw
+
+    # ---- batched env-major API ---------------------------------------------------------------
+    def step(self, q, qd, qacc, target, iterations=100, tol=1e-12, nthreads=1):
+        """In-place substep of n envs. q (n,nq), qd (n,nv), qacc (n,nv) warm start, target (n,nu)."""
+        n = q.shape[0]
+        assert q.dtype == self.dtype and q.flags.c_contiguous and qd.flags.c_contiguous and qacc.flags.c_contiguous
+        target = self._a(target, (n, self.nu))
+        info = np.zeros((n, 4), np.int32)
+        grad = np.zeros(n, np.float64)
+        self._fn("step")(self.h, C.c_int(n), _p(q), _p(qd), _p(qacc), _p(target), C.c_int(iterations),
+                         C.c_double(tol), _p(info), _p(grad), C.c_int(nthreads))
+        return info, grad
+
+    def obs(self, q):
+        q = self._a(q)
+        n = q.shape[0]
+        agent = np.zeros((n, self.agent_dim), self.dtype)
+        envs = np.zeros((n, 11), self.dtype)
+        reward = np.zeros(n, self.dtype)
+        term = np.zeros(n, np.uint8)
+        self._fn("obs")(self.h, C.c_int(n), _p(q), _p(agent), C.c_int(self.agent_dim), _p(envs), _p(reward), _p(term))
+        return agent, envs, reward, term.astype(bool)
+
+    def reset(self, q, qd, qacc, xy, mask=None):
+        n = q.shape[0]
+        xy = self._a(xy, (n, 2))
+        m = None if mask is None else np.ascontiguousarray(mask, dtype=np.uint8)
+        self._fn("reset")(self.h, C.c_int(n), _p(q), _p(qd), _p(qacc), _p(m) if m is not None else None, _p(xy))
+
+    def new_state(self, n):
+        return (np.zeros((n, self.nq), self.dtype), np.zeros((n, self.nv), self.dtype), np.zeros((n, self.nv), self.dtype))
+
+    def spawn_xy(self, seed, env_id, episode):
+        out = np.zeros(2, np.float32)
+        lib().orc_spawn_xy(self.h, C.c_uint64(seed), C.c_uint32(env_id), C.c_uint32(episode), _p(out))
+        return out
+
+
+def philox(ctr, key):
+    c = np.asarray(ctr, dtype=np.uint32)
+    k = np.asarray(key, dtype=np.uint32)
+    o = np.zeros(4, np.uint32)
+    lib().orc_philox(_p(c), _p(k), _p(o))
+    return o
+
+
+def num_threads():
+    return int(lib().orc_num_threads())

@@ -1,0 +1,111 @@
+"""Shared helpers for the parity tests: scripted-grasp state generator, host-harness wrappers, tolerances."""
+import ctypes as C
+
+import numpy as np
+
+from gym_genesis_b200.model import FRANKA_HOME, quat_to_mat
+
+# ---- parity tolerances (stated once; see DESIGN.md "Parity") -----------------------------------
+# Single substep, CUDA fp32 vs oracle fp64 run to convergence.  Velocity deltas are compared relative
+# to the larger of the net delta and a floor: in contact-rich states the net delta is the small
+# difference of large constraint/actuator terms and the fp32 penetration depth (|p| ~ 0.6 m, depth
+# ~ 1e-4 m) carries ~1e-3 relative quantisation, which the stiffness K = 2770 1/s^2 turns into
+# ~2e-4 m/s^2 of reference acceleration per row (the fp32 build of the oracle shows the same spread).
+TOL_Q_ABS = 2e-6            # positions / quaternion components after one substep
+TOL_DQD_REL = 1e-4          # |dqd - dqd_ref|_inf <= TOL_DQD_REL * max(|dqd_ref|_inf, |a_smooth|_inf * dt) + floor
+TOL_DQD_FLOOR = 3e-5        # rad/s (= 3e-3 rad/s^2 * dt): fp32 geometry quantisation floor with ~50 contacts
+ROLLOUT_POS_TOL = 1e-2      # 100-step closed-form-free rollout, free-space / light contact
+
+
+def ik_numpy(m, target_pos, target_R, q0, iters=60):
+    """Damped least-squares IK on the numpy model (stands in for robot.inverse_kinematics of the expert,
+    reference examples/franka/pick_cube_state.py:46-51)."""
+    q = q0.copy()
+    for _ in range(iters):
+        fq = m.full_q(q)
+        xp, xm = m.fk(fq)
+        ep = target_pos - xp[m.eef_body]
+        Re = target_R @ xm[m.eef_body].T
+        ang = np.arccos(np.clip((np.trace(Re) - 1) / 2, -1, 1))
+        er = np.zeros(3) if ang < 1e-9 else ang / (2 * np.sin(ang)) * np.array([Re[2, 1] - Re[1, 2], Re[0, 2] - Re[2, 0], Re[1, 0] - Re[0, 1]])
+        Jv, Jw = m.jacobian(fq, m.eef_body, xp[m.eef_body])
+        J = np.vstack([Jv[:, :m.n_arm], Jw[:, :m.n_arm]])
+        e = np.concatenate([ep, er])
+        q[:m.n_arm] += J.T @ np.linalg.solve(J @ J.T + 1e-6 * np.eye(6), e)
+        if np.linalg.norm(e) < 1e-10:
+            break
+    return q
+
+
+def scripted_grasp_states(m, orc, cube_xy=(0.6, 0.1), stride=1):
+    """Run the reference expert's stage machine (hover/stabilize/grasp/grasp/lift x 40 steps) in the oracle and
+    return the visited (q, qd, qacc, action) tuples plus the final reward."""
+    Rdown = quat_to_mat([0, 1, 0, 0])
+    Q, QD, QA = orc.new_state(1)
+    orc.reset(Q, QD, QA, np.array([cube_xy]))
+    out = []
+    act = FRANKA_HOME.copy()[None]
+    out.append((Q.copy(), QD.copy(), QA.copy(), act.copy()))
+    orc.step(Q, QD, QA, act)
+    k = 0
+    for dz, grip in [(0.115, 0.04), (0.115, 0.04), (0.03, -0.02), (0.03, -0.02), (0.25, -0.02)]:
+        for _ in range(40):
+            qt = ik_numpy(m, Q[0, 9:12] + np.array([0, 0, dz]), Rdown, Q[0, :9].copy())
+            act = np.concatenate([qt[:7], [grip, grip]])[None]
+            if k % stride == 0:
+                out.append((Q.copy(), QD.copy(), QA.copy(), act.copy()))
+            orc.step(Q, QD, QA, act, iterations=100, tol=1e-10)
+            k += 1
+    return out, orc.obs(Q)[2][0]
+
+
+def f32(x):
+    return np.ascontiguousarray(x, dtype=np.float32)
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def hostsim_step(hs, gg_model, Q, QD, QA, T, iters=10, tol=1e-6):
+    q, qd, qa, t = f32(Q).copy(), f32(QD).copy(), f32(QA).copy(), f32(T)
+    n = q.shape[0]
+    info = np.zeros((n, 3), np.int32)
+    grad = np.zeros(n, np.float32)
+    hs.hs_step(C.byref(gg_model), n, _p(q), _p(qd), _p(qa), _p(t), iters, C.c_float(tol), _p(info), _p(grad))
+    return q, qd, qa, info, grad
+
+
+def random_states(m, rng, n, cube_on_ground=True):
+    """Random robot configurations near home with random velocities; cube either resting or in flight."""
+    nu = m.nu
+    Q = np.zeros((n, nu + 7))
+    QD = np.zeros((n, nu + 6))
+    Q[:, :nu] = m.home_q + rng.uniform(-0.3, 0.3, (n, nu))
+    Q[:, m.n_arm:nu] = rng.uniform(0.0, 0.04, (n, m.n_fing))
+    Q[:, nu] = rng.uniform(0.45, 0.8, n)
+    Q[:, nu + 1] = rng.uniform(-0.25, 0.25, n)
+    if cube_on_ground:
+        Q[:, nu + 2] = 0.02 - rng.uniform(0, 2e-4, n)
+        yaw = rng.uniform(-np.pi, np.pi, n)
+        Q[:, nu + 3] = np.cos(yaw / 2)
+        Q[:, nu + 6] = np.sin(yaw / 2)
+        QD[:, nu:nu + 2] = rng.normal(0, 0.05, (n, 2))
+    else:
+        Q[:, nu + 2] = rng.uniform(0.1, 0.4, n)
+        qq = rng.normal(size=(n, 4))
+        Q[:, nu + 3:nu + 7] = qq / np.linalg.norm(qq, axis=1, keepdims=True)
+        QD[:, nu:] = rng.normal(0, 0.5, (n, 6))
+    QD[:, :nu] = rng.normal(0, 0.5, (n, nu))
+    T = m.home_q + rng.uniform(-0.3, 0.3, (n, nu))
+    T[:, m.n_arm:] = rng.uniform(-0.02, 0.04, (n, m.n_fing))
+    return f32(Q).astype(np.float64), f32(QD).astype(np.float64), f32(T).astype(np.float64)
+
+
+def substep_errors(q0, qd0, q_ref, qd_ref, q, qd, a_smooth_scale):
+    """(|q err|_inf, velocity-delta error normalised by TOL: <= 1 passes)."""
+    eq = np.abs(q - q_ref).max(axis=1)
+    d_ref = np.abs(qd_ref - qd0).max(axis=1)
+    ev = np.abs(qd - qd_ref).max(axis=1)
+    bound = TOL_DQD_REL * np.maximum(d_ref, a_smooth_scale) + TOL_DQD_FLOOR
+    return eq, ev / bound

@@ -1,0 +1,89 @@
+"""CPU tier: the per-env DEVICE pipeline (gg_env.cuh, compiled for the host as a test harness) against the
+oracle.  Catches kernel-math bugs without a GPU; the GPU tier repeats these through the C ABI."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from gym_genesis_b200 import cabi
+from gym_genesis_b200 import model as mdl
+from helpers import (TOL_Q_ABS, _p, f32, hostsim_step, random_states, scripted_grasp_states, substep_errors)
+
+
+@pytest.fixture(scope="module")
+def gg(franka_model):
+    return cabi.compile_gg(franka_model)
+
+
+def test_struct_layout_matches_header(hostsim):
+    assert hostsim.hs_sizeof_model() == C.sizeof(cabi.GgModel)
+
+
+def test_robot_dynamics(hostsim, gg, franka_model, oracle64):
+    rng = np.random.default_rng(3)
+    Q, QD, T = random_states(franka_model, rng, 8, cube_on_ground=False)
+    for k in range(8):
+        d = oracle64.dynamics(Q[k], QD[k], T[k])
+        Mt, fs = np.zeros((9, 9), np.float32), np.zeros(9, np.float32)
+        hostsim.hs_dynamics(C.byref(gg), _p(f32(Q[k])), _p(f32(QD[k])), _p(f32(T[k])), _p(Mt), _p(fs))
+        assert np.abs(Mt - d["Mt"][:9, :9]).max() < 5e-6
+        fs_ref = (d["tau"] - d["bias"])[:9]
+        assert np.abs(fs - fs_ref).max() < 1e-4 * max(1.0, np.abs(fs_ref).max())
+
+
+def _a_smooth_scale(o, Q, QD, T):
+    return np.array([np.abs(o.dynamics(Q[k], QD[k], T[k])["a_smooth"]).max() * 0.01 for k in range(Q.shape[0])])
+
+
+@pytest.mark.parametrize("on_ground", [True, False])
+def test_substep_random_states(hostsim, gg, franka_model, oracle64, on_ground):
+    rng = np.random.default_rng(4 + on_ground)
+    Q, QD, T = random_states(franka_model, rng, 64, cube_on_ground=on_ground)
+    QA = np.zeros_like(QD)
+    qo, qdo, qao = Q.copy(), QD.copy(), QA.copy()
+    info, _ = oracle64.step(qo, qdo, qao, T, iterations=100, tol=1e-12)
+    q, qd, qa, hinfo, _ = hostsim_step(hostsim, gg, Q, QD, QA, T)
+    assert (hinfo[:, 0] == info[:, 0]).all()                    # identical contact counts
+    eq, ev = substep_errors(Q, QD, qo, qdo, q, qd, _a_smooth_scale(oracle64, Q, QD, T))
+    assert eq.max() < TOL_Q_ABS and ev.max() < 1.0, (eq.max(), ev.max())
+
+
+def test_substep_along_scripted_grasp(hostsim, gg, franka_model, oracle64):
+    states, reward = scripted_grasp_states(franka_model, oracle64, stride=3)
+    assert reward == 1.0
+    worst_q = worst_v = 0.0
+    seen_heavy = False
+    for Q, QD, QA, T in states:
+        Q, QD, QA, T = (f32(x).astype(np.float64) for x in (Q, QD, QA, T))
+        qo, qdo, qao = Q.copy(), QD.copy(), QA.copy()
+        info, _ = oracle64.step(qo, qdo, qao, T, iterations=100, tol=1e-12)
+        q, qd, qa, hinfo, _ = hostsim_step(hostsim, gg, Q, QD, QA, T)
+        assert hinfo[0, 0] == info[0, 0]
+        seen_heavy |= info[0, 0] >= 32
+        eq, ev = substep_errors(Q, QD, qo, qdo, q, qd, _a_smooth_scale(oracle64, Q, QD, T))
+        worst_q, worst_v = max(worst_q, eq.max()), max(worst_v, ev.max())
+    assert seen_heavy                                            # pad-cube and pad-plane manifolds were exercised
+    assert worst_q < TOL_Q_ABS and worst_v < 1.0, (worst_q, worst_v)
+
+
+def test_observation_and_flags(hostsim, gg, franka_model, oracle64):
+    rng = np.random.default_rng(6)
+    Q, _, _ = random_states(franka_model, rng, 32, cube_on_ground=False)
+    Q[:8, 11] = np.float32(0.1)            # exactly on the strict threshold: z > 0.1f is False
+    Q[8:16, 11] = np.nextafter(np.float32(0.1), np.float32(1.0))
+    a, e, r, t = oracle64.obs(Q)
+    agent, envs = np.zeros((32, 9), np.float32), np.zeros((32, 11), np.float32)
+    rew, term = np.zeros(32, np.float32), np.zeros(32, np.uint8)
+    hostsim.hs_observe(C.byref(gg), 32, _p(f32(Q)), _p(agent), _p(envs), _p(rew), _p(term))
+    assert np.abs(agent - a).max() < 2e-6 and np.abs(envs - e).max() < 2e-6
+    assert (term.astype(bool) == t).all() and (rew == r).all()            # bit-exact flags
+    assert not t[:8].any() and t[8:16].all()
+
+
+def test_spawn_draw_bit_exact(hostsim, gg, oracle64):
+    for seed, gid, epi in [(0, 0, 0), (42, 7, 3), (2 ** 40 + 5, 131071, 200), (2 ** 64 - 1, 2 ** 31, 1)]:
+        xy = np.zeros(2, np.float32)
+        hostsim.hs_spawn(C.byref(gg), C.c_uint64(seed), C.c_uint32(gid), C.c_uint32(epi), _p(xy))
+        ref = oracle64.spawn_xy(seed, gid, epi)
+        assert xy.tobytes() == ref.tobytes()
+        assert 0.45 <= xy[0] <= 0.80 and -0.25 <= xy[1] <= 0.25
