@@ -1,0 +1,312 @@
+#!/usr/bin/env python
+"""Headline benchmark: env-steps/s of the batched CubePick-v0 (Franka) env.step, 16384 envs per GPU.
+
+    python bench.py --gpus 1 --steps K --warmup W             (driver: N=1)
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference ...                       (CPU arm: the oracle port on the host cores)
+
+Workload (BASELINE.json configs[2], the config the metric "16k envs/GPU" is quoted on): state-only Franka CubePick,
+16384 envs per GPU, randomized cube poses (device Philox spawn), random joint-position targets resampled every step,
+per-env masked partial resets every step (Bernoulli p = 1/200) plus resets of finished envs.  A "step" is ONE env.step
+(= one 0.01 s rigid substep) of the whole batch = ONE launch of step_kernel.
+
+Timing: W untimed warm-up steps, then exactly K steps; each step is bracketed by its own CUDA event pair on the
+launching stream and L2 is flushed (256 MiB write) between steps OUTSIDE the event pairs, so every timed launch starts
+from HBM; the K durations are summed and the MAX over ranks is taken.  `e2e` times the same workload through the
+public gymnasium API with the action batch coming from pinned host memory and reward / terminated read back every step.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "env-steps/s, CubePick-v0 Franka 16k envs/GPU"
+N_ENVS_PER_GPU = 16384
+RESET_PROB = 1.0 / 200.0
+ACTION_POOL = 32
+# algorithmic bytes per env-step of step_kernel<7,2> (DESIGN.md "Data layout"):
+#   read : state 46 f32 (184) + action 36 + step_count 4 + episode 4 + done 1            = 229
+#   write: state 184 + step_count 4 + episode 4 + done 1 + agent_pos 36 + environment_state 44 + reward 4 + term 1 + trunc 1 = 279
+BYTES_PER_ENV_STEP = 229 + 279
+
+
+def workload_config(n_envs):
+    return {"workload": "CubePick-v0 Franka state-only, num_envs=%d per GPU, randomized cube poses, random joint targets "
+                        "resampled every step, masked per-env partial resets every step (p=1/200) + auto-reset of finished envs "
+                        "(BASELINE.json configs[2])" % n_envs,
+            "num_envs_per_gpu": n_envs, "dt": 0.01, "substeps_per_step": 1, "solver": "Newton, <=10 iterations, tol 1e-5",
+            "reset_prob": RESET_PROB, "l2": "flushed (256 MiB write) between timed steps"}
+
+
+def measured_peak():
+    try:
+        p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def traffic_per_launch(n_envs):
+    """dram bytes per launch of the step kernel from the committed ncu --set full capture, or None."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        e = t.get("step_kernel_franka", {})
+        if e and int(e.get("n_envs", -1)) == n_envs:
+            return float(e["dram_bytes_per_launch"])
+    except Exception:
+        pass
+    return None
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); smax.append(float(r[2]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port on the host cores (the reference's Genesis CPU backend is not installable here)
+# ------------------------------------------------------------------------------------------------
+def cpu_port_run(n_envs, steps, warmup, threads, seed=0):
+    from gym_genesis_b200.model import franka_cube_pick_model
+    from oracle.binding import Oracle
+    m = franka_cube_pick_model()
+    orc = Oracle(m, np.float32)
+    rng = np.random.RandomState(seed)
+    Q, QD, QA = orc.new_state(n_envs)
+    xy = np.stack([rng.uniform(0.45, 0.8, n_envs), rng.uniform(-0.25, 0.25, n_envs)], 1).astype(np.float32)
+    orc.reset(Q, QD, QA, xy)
+    home = np.tile(m.home_q.astype(np.float32), (n_envs, 1))
+    orc.step(Q, QD, QA, home, iterations=10, tol=1e-6, nthreads=threads)
+    pool = [(home + rng.uniform(-0.3, 0.3, home.shape)).astype(np.float32) for _ in range(8)]
+    for p in pool:
+        p[:, 7:] = rng.uniform(-0.02, 0.04, (n_envs, 2))
+
+    def one(k):
+        mask = rng.random_sample(n_envs) < RESET_PROB
+        tgt = pool[k % len(pool)]
+        if mask.any():                                   # masked reset: spawn + home + settle step instead of the env step
+            xy_ = np.stack([rng.uniform(0.45, 0.8, n_envs), rng.uniform(-0.25, 0.25, n_envs)], 1).astype(np.float32)
+            orc.reset(Q, QD, QA, xy_, mask.astype(np.uint8))
+            tgt = np.where(mask[:, None], home, tgt)
+        orc.step(Q, QD, QA, tgt, iterations=10, tol=1e-6, nthreads=threads)
+        orc.obs(Q)
+
+    for k in range(warmup):
+        one(k)
+    t0 = time.perf_counter()
+    for k in range(steps):
+        one(k)
+    dt = time.perf_counter() - t0
+    return n_envs * steps / dt, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle.binding import build, num_threads
+    build()
+    threads = num_threads()
+    n = 4096
+    steps, warmup = max(1, min(args.steps, 200)), max(1, min(args.warmup, 5))
+    v, dt = cpu_port_run(n, steps, warmup, threads)
+    sample = f"{n} envs x {steps} steps of the same workload (oracle port, fp32 build, {threads} host threads)"
+    out = {"impl": "reference", "metric": METRIC, "value": v, "unit": "env-steps/s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
+           "ms_per_step": dt / steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+           "data": "synthetic", "config": workload_config(n),
+           "cpu_baseline": {"value": v, "unit": "env-steps/s", "cores": threads, "kind": "port", "sample": sample,
+                            "note": "Genesis (the reference's physics dependency) is not installable here; this is the oracle restatement"},
+           "e2e": {"value": v, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out))
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+
+    import __graft_entry__ as ge
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if rank == 0:
+        ge.build_cuda()
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        dist.barrier()
+    from gym_genesis_b200.model import franka_cube_pick_model
+    from gym_genesis_b200.sim import BatchedSim
+
+    n = args.envs
+    m = franka_cube_pick_model()
+    sim = BatchedSim(m, n, device=dev, auto_reset=True, reset_prob=RESET_PROB, seed=args.seed, first_env_id=rank * n)
+    sim.reset(None, None)                                   # device Philox spawn keyed by the GLOBAL env id
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    home = torch.as_tensor(m.home_q, dtype=torch.float32, device=dev)
+    pool = home + 0.6 * (torch.rand((ACTION_POOL, n, 9), generator=g, device=dev) - 0.5)
+    pool[:, :, 7:] = -0.02 + 0.06 * torch.rand((ACTION_POOL, n, 2), generator=g, device=dev)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    stats_all = torch.zeros((world, 8), dtype=torch.float64, device=dev) if world > 1 else None
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for k in range(max(args.warmup, 3)):
+        sim.step(pool[k % ACTION_POOL])
+    barrier()
+    launches0 = BatchedSim.launch_count()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    wall0 = time.perf_counter()
+    for k in range(args.steps):
+        flush.fill_(k & 0xFF)                               # evict L2 (126 MB) between timed launches
+        ev[k][0].record()
+        sim.step(pool[k % ACTION_POOL])
+        ev[k][1].record()
+        if stats_all is not None and (k + 1) % 100 == 0:    # the only collective: episode statistics, off the step path
+            dist.all_gather_into_tensor(stats_all, sim.stats().unsqueeze(0))
+    barrier()
+    wall = time.perf_counter() - wall0
+    launches = BatchedSim.launch_count() - launches0 - (args.steps // 100 if stats_all is not None else 0)
+    clocks = sampler.stop() if rank == 0 else None
+    t_ms = sum(a.elapsed_time(b) for a, b in ev)
+    # L2-warm back-to-back figure (same kernel, no flush) for context
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for k in range(args.steps):
+        sim.step(pool[k % ACTION_POOL])
+    e1.record()
+    barrier()
+    warm_ms = e0.elapsed_time(e1)
+    st = sim.stats().cpu().numpy()
+
+    # ---- end-to-end through the public gymnasium API, host-resident actions ----------------------
+    import gym_genesis  # noqa: F401
+    from gym_genesis_b200.gym_api import gym
+    env = gym.make("gym_genesis/CubePick-v0", robot="franka", num_envs=n, device=dev, auto_reset=True, reset_prob=RESET_PROB,
+                   seed=args.seed, first_env_id=rank * n).unwrapped
+    env.reset(seed=args.seed)
+    host_actions = [pool[k].cpu().pin_memory() for k in range(4)]
+    rew_h = torch.empty(n, dtype=torch.float32).pin_memory()
+    term_h = torch.empty(n, dtype=torch.bool).pin_memory()
+    e2e_steps = min(args.steps, 500)
+    for k in range(5):
+        env.step(host_actions[k % 4])
+    barrier()
+    a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a0.record()
+    for k in range(e2e_steps):
+        obs, reward, terminated, truncated, info = env.step(host_actions[k % 4])       # H2D copy inside step()
+        rew_h.copy_(reward, non_blocking=True)
+        term_h.copy_(terminated, non_blocking=True)
+        torch.cuda.current_stream().synchronize()                                       # host consumes the result every step
+    a1.record()
+    barrier()
+    e2e_ms = a0.elapsed_time(a1)
+
+    times = torch.tensor([t_ms, warm_ms, e2e_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    t_ms, warm_ms, e2e_ms = times.tolist()
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        ms_per_step = t_ms / args.steps
+        value = n * world * args.steps / (t_ms * 1e-3)
+        achieved = BYTES_PER_ENV_STEP * n / (ms_per_step * 1e-3) / 1e9
+        out = {"metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+               "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+               "data": "synthetic", "config": workload_config(n),
+               "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                            "traffic": traffic_per_launch(n), "peak_source": peak_src, "kernel": "step_kernel<7,2,false>",
+                            "algorithmic_bytes_per_launch": BYTES_PER_ENV_STEP * n,
+                            "note": "latency / fp32-issue bound by design: the per-env pipeline is ~1e4 flop per 508 B"},
+               "e2e": {"value": n * world * e2e_steps / (e2e_ms * 1e-3), "unit": "env-steps/s", "h2d_bytes_per_step": n * 9 * 4,
+                       "d2h_bytes_per_step": n * 4 + n, "steps": e2e_steps, "api": "gym.make('gym_genesis/CubePick-v0').unwrapped.step(pinned host action)"},
+               "gpu_launches": int(launches), "clocks": clocks,
+               "l2_warm": {"value": n * world * args.steps / (warm_ms * 1e-3), "unit": "env-steps/s", "note": "back-to-back launches, no L2 flush"},
+               "wall_s_timed_loop": wall,
+               "episode_stats": {"env_steps": st[0], "episodes": st[1], "successes": st[2], "nonfinite_resets": st[5],
+                                 "mean_solver_iters": st[6] / max(st[0], 1), "mean_contacts": st[7] / max(st[0], 1)}}
+        if not args.no_cpu_baseline and world == 1:
+            from oracle.binding import build, num_threads
+            build()
+            threads = num_threads()
+            cn, cs = 4096, 100
+            v, dt = cpu_port_run(cn, cs, 3, threads)
+            out["cpu_baseline"] = {"value": v, "unit": "env-steps/s", "cores": threads, "kind": "port",
+                                   "sample": f"{cn} envs x {cs} steps of the same workload, oracle fp32 build, {threads} host threads ({dt:.1f} s)"}
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=1000)
+    ap.add_argument("--warmup", type=int, default=200)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--envs", type=int, default=N_ENVS_PER_GPU, help="envs per GPU")
+    ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

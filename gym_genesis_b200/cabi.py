@@ -35,6 +35,7 @@ class GgModel(C.Structure):
         ("body_invweight", _f * (1 + GG_MAX_FING)),
         ("pad_body", _i * GG_MAX_PADS),
         ("pad_half", (_f * 3) * GG_MAX_PADS), ("pad_pos", (_f * 3) * GG_MAX_PADS), ("pad_quat", (_f * 4) * GG_MAX_PADS),
+        ("pad_bound", (_f * 4) * (1 + GG_MAX_FING)),
         ("cube_half", _f * 3), ("cube_mass", _f), ("cube_inertia", _f * 3), ("cube_invweight", _f),
         ("dt", _f), ("gravity", _f), ("plane_z", _f), ("friction", _f),
         ("tc", _f), ("dr", _f), ("dmin", _f), ("dmax", _f), ("width", _f), ("mid", _f), ("power", _f), ("minval", _f),
@@ -153,6 +154,24 @@ def compile_gg(sm: "mdl.SceneModel") -> GgModel:
         g.pad_body[k] = code
         k += 1
     g.n_pads = k
+    # conservative bounding sphere of all pads per carrying body (body-level broad phase in the kernel)
+    for b in range(1 + GG_MAX_FING):
+        corners = []
+        for j in range(k):
+            if g.pad_body[j] != b:
+                continue
+            R = mdl.quat_to_mat(list(g.pad_quat[j]))
+            for sx in (-1, 1):
+                for sy in (-1, 1):
+                    for sz in (-1, 1):
+                        corners.append(np.array(list(g.pad_pos[j])) + R @ (np.array(list(g.pad_half[j])) * [sx, sy, sz]))
+        if corners:
+            corners = np.array(corners)
+            ctr = 0.5 * (corners.min(0) + corners.max(0))
+            rad = np.linalg.norm(corners - ctr, axis=1).max() * 1.001 + 1e-6
+            _set(g.pad_bound[b], [*ctr, rad])
+        else:
+            _set(g.pad_bound[b], [0, 0, 0, -1])
     cube = B[sm.cube_body]
     cg = [x for x in sm.geoms if x.group == 1]
     assert len(cg) == 1

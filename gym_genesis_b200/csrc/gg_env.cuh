@@ -286,41 +286,6 @@ GG_HD void imp_aref(const GgModel& M, float pos, float vel, float& imp, float& a
     aref = -Bc * vel - Kc * imp * pos;
 }
 
-// pads + cube narrow phase in the oracle's deterministic order: cube-plane, pads-plane, pads-cube
-template <int NA, int NF>
-GG_HD void collide(const GgModel& M, const RobotDyn<NA, NF>& D, V3 cp, const M3& cR, Contacts& C) {
-    C.count = 0;
-    const int maxc = M.max_contacts < GG_MAX_CONTACTS ? M.max_contacts : GG_MAX_CONTACTS;
-    V3 ch = ld3(M.cube_half);
-    plane_box(M.plane_z, cp, cR, ch, 0, maxc, C);
-    const float rc = sqrtf(dot(ch, ch));
-    bool any = false;
-    for (int g = 0; g < M.n_pads; g++) {       // bounding-sphere broad phase
-        int b = M.pad_body[g];
-        const M3& Rb = b == 0 ? D.lR : D.fR[b - 1 < NF ? (b - 1 < 0 ? 0 : b - 1) : 0];
-        V3 pb = b == 0 ? D.lp : D.fp[b - 1 < NF ? (b - 1 < 0 ? 0 : b - 1) : 0];
-        V3 c = pb + mul(Rb, ld3(M.pad_pos[g]));
-        V3 h = ld3(M.pad_half[g]);
-        float r = sqrtf(dot(h, h));
-        V3 d = c - cp;
-        any = any || (c.z - r <= M.plane_z) || (dot(d, d) <= (r + rc) * (r + rc));
-    }
-    if (!any) return;
-    for (int pass = 0; pass < 2; pass++) {
-        for (int g = 0; g < M.n_pads; g++) {
-            int b = M.pad_body[g];
-            int fi = b - 1 < 0 ? 0 : (b - 1 < NF ? b - 1 : 0);
-            M3 Rb = b == 0 ? D.lR : D.fR[fi];
-            V3 pb = b == 0 ? D.lp : D.fp[fi];
-            V3 c = pb + mul(Rb, ld3(M.pad_pos[g]));
-            M3 R = mmul(Rb, qmat(ldq(M.pad_quat[g])));
-            V3 h = ld3(M.pad_half[g]);
-            if (pass == 0) plane_box(M.plane_z, c, R, h, 1 + b, maxc, C);
-            else box_box(c, R, h, cp, cR, ch, 4 + b, maxc, C);
-        }
-    }
-}
-
 // ---------------------------------------------------------------------------------------------
 // Contact-frame Jacobian rows (normal, tangent 1, tangent 2) of one contact: J (v_b - v_a) at p.
 // ---------------------------------------------------------------------------------------------
@@ -375,12 +340,463 @@ GG_HD float rowval(const float* v3, float mu, int k) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// One substep.  General coupled Newton solve over all NU + 6 dofs (A.4): minimise
-//   1/2 (a - a_s)^T Mt (a - a_s) + sum_active 1/2 D (J a - aref)^2,  exact line search.
+// Solvers for the convex cost of A.4:  1/2 (a - a_s)^T Mt (a - a_s) + sum_active 1/2 D (J a - aref)^2,
+// Newton with exact line search.  Three specialisations of the same algorithm:
+//   solve_robot_limits : robot block, joint-limit rows only (J = +-e_d)          -- registers only
+//   solve_cube_plane   : cube block, <= 4 plane contacts (16 pyramidal rows)      -- registers only
+//   solve_coupled      : all NU + 6 dofs, any contacts (pads touching cube/plane) -- local memory
+// When no pad touches anything the Hessian is block diagonal and the first two give exactly the
+// minimiser of the coupled problem.  An iteration that took the full Newton step (alpha = 1) without
+// any row changing its active state has landed on the exact minimiser of the current quadratic
+// piece, so the loop stops there without re-assembling the gradient.
+// ---------------------------------------------------------------------------------------------
+// Stop criterion shared by the three solvers: largest diagonally-preconditioned gradient component
+// (an estimate of the remaining acceleration error per dof) relative to 1 + |a|_inf.  Unlike a gradient
+// norm scaled by the mean inertia of the whole system it stays meaningful for the cube's rotational dofs,
+// whose inertia (3.4e-6 kg m^2) is six orders below the arm's.
+template <int N> GG_HD float newton_residual(const float* g, const float* H, const float* a) {
+    float r = 0.f, am = 0.f;
+#pragma unroll
+    for (int i = 0; i < N; i++) { r = fmaxf(r, fabsf(g[i]) * gg_rcp(H[GG_TRI(i, i)])); am = fmaxf(am, fabsf(a[i])); }
+    return gg_div(r, 1.f + am);
+}
+
+struct LineSearch {
+    float al, lo, hi, d0, d1, d2;
+    int ls;
+    GG_HD void begin() { al = 0.f; lo = 0.f; hi = -1.f; d0 = 0.f; d1 = 0.f; d2 = 1.f; ls = 0; }
+    // call with phi'(al), phi''(al); returns false when converged
+    GG_HD bool next(float nd1, float nd2) {
+        d1 = nd1; d2 = nd2;
+        if (ls == 0) d0 = d1;
+        else {
+            if (d1 < 0.f) lo = al; else hi = al;
+            if (fabsf(d1) <= fabsf(d0) * 1e-6f) return false;
+        }
+        if (++ls > 12) return false;
+        float nx = al - gg_div(d1, d2);
+        if (hi >= 0.f && (nx <= lo || nx >= hi)) nx = 0.5f * (lo + hi);
+        if (nx <= 0.f) nx = hi >= 0.f ? 0.5f * (lo + hi) : 1e-3f;
+        al = nx;
+        return true;
+    }
+};
+
+template <int NU>
+GG_HD void solve_robot_limits(const float* Mt, const float* as, const float* lsg, const float* laref, const float* lD,
+                              const float* warm, float* a, int iterations, float tol, float scale, int& iters, float& gnorm) {
+    float e[NU], Me[NU];
+    float costw = 0.f, costs = 0.f;
+#pragma unroll
+    for (int i = 0; i < NU; i++) e[i] = warm[i] - as[i];
+    symv_packed<NU>(Mt, e, Me);
+#pragma unroll
+    for (int d = 0; d < NU; d++) {
+        costw += 0.5f * e[d] * Me[d];
+        float jw = lsg[d] * warm[d] - laref[d], js = lsg[d] * as[d] - laref[d];
+        if (lsg[d] != 0.f && jw < 0.f) costw += 0.5f * lD[d] * jw * jw;
+        if (lsg[d] != 0.f && js < 0.f) costs += 0.5f * lD[d] * js * js;
+    }
+    const bool usew = costw < costs;
+#pragma unroll
+    for (int i = 0; i < NU; i++) a[i] = usew ? warm[i] : as[i];
+    int it = 0;
+    for (; it < iterations; it++) {
+        float g[NU], H[NU * (NU + 1) / 2], dinv[NU], sd[NU], Ms[NU];
+#pragma unroll
+        for (int i = 0; i < NU; i++) e[i] = a[i] - as[i];
+        symv_packed<NU>(Mt, e, Me);
+#pragma unroll
+        for (int i = 0; i < NU * (NU + 1) / 2; i++) H[i] = Mt[i];
+#pragma unroll
+        for (int d = 0; d < NU; d++) {
+            float jar = lsg[d] * a[d] - laref[d];
+            bool act = lsg[d] != 0.f && jar < 0.f;
+            g[d] = Me[d] + (act ? lD[d] * jar * lsg[d] : 0.f);
+            H[GG_TRI(d, d)] += act ? lD[d] : 0.f;
+        }
+        gnorm = newton_residual<NU>(g, H, a);
+        if (gnorm < tol) break;
+        chol_packed<NU>(H, dinv);
+#pragma unroll
+        for (int i = 0; i < NU; i++) g[i] = -g[i];
+        chol_solve_packed<NU>(H, dinv, g, sd);
+        symv_packed<NU>(Mt, sd, Ms);
+        const float q1 = dotn<NU>(sd, Me), q2 = dotn<NU>(sd, Ms);
+        LineSearch L; L.begin();
+        for (;;) {
+            float d1 = q1 + L.al * q2, d2 = q2;
+#pragma unroll
+            for (int d = 0; d < NU; d++) {
+                float jv = lsg[d] * sd[d];
+                float x = lsg[d] * a[d] - laref[d] + L.al * jv;
+                if (lsg[d] != 0.f && x < 0.f) { d1 += lD[d] * x * jv; d2 += lD[d] * jv * jv; }
+            }
+            if (!L.next(d1, d2)) break;
+        }
+        int changed = 0;
+#pragma unroll
+        for (int d = 0; d < NU; d++) {
+            float j0 = lsg[d] * a[d] - laref[d];
+            a[d] += L.al * sd[d];
+            float j1 = lsg[d] * a[d] - laref[d];
+            changed += (lsg[d] != 0.f) && ((j0 < 0.f) != (j1 < 0.f));
+        }
+        if (changed == 0 && fabsf(L.al - 1.f) < 1e-3f) { it++; break; }
+    }
+    iters = it;
+}
+
+// cube block against the plane: contacts i < ncp are live, the rest are masked with D = 0
+GG_HD void solve_cube_plane(const GgModel& M, const float* Mc, const float* as, const float* qd, V3 cp, const M3& cR, const V3* p,
+                            const float* depth, int ncp, const float* warm, float* a, int iterations, float tol, float scale,
+                            int& iters, float& gnorm) {
+    const float mu = M.friction;
+    float J[4][3][6], aref[4][4], Dk[4], u[4][3], w[4][3];
+    float costw = 0.f, costs = 0.f;
+#pragma unroll
+    for (int i = 0; i < 6; i++) { float ew = warm[i] - as[i]; costw += 0.5f * Mc[i] * ew * ew; }
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+        // plane normal +z: n = z, t1 = x, t2 = y (= tangent_basis(z)); rows act on [v, w_body]
+        V3 r = p[c] - cp;
+        V3 a0 = cross(cR.c0, r), a1 = cross(cR.c1, r), a2 = cross(cR.c2, r);
+        J[c][0][0] = 0.f; J[c][0][1] = 0.f; J[c][0][2] = 1.f; J[c][0][3] = a0.z; J[c][0][4] = a1.z; J[c][0][5] = a2.z;
+        J[c][1][0] = 1.f; J[c][1][1] = 0.f; J[c][1][2] = 0.f; J[c][1][3] = a0.x; J[c][1][4] = a1.x; J[c][1][5] = a2.x;
+        J[c][2][0] = 0.f; J[c][2][1] = 1.f; J[c][2][2] = 0.f; J[c][2][3] = a0.y; J[c][2][4] = a1.y; J[c][2][5] = a2.y;
+        float vel[3], uw[3], us[3];
+#pragma unroll
+        for (int k = 0; k < 3; k++) { vel[k] = dotn<6>(J[c][k], qd); uw[k] = dotn<6>(J[c][k], warm); us[k] = dotn<6>(J[c][k], as); }
+        const bool live = c < ncp;
+        float imp = 1.f, ar = 0.f;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            imp_aref(M, -depth[c], rowval(vel, mu, k), imp, ar);
+            aref[c][k] = ar;
+        }
+        Dk[c] = live ? gg_rcp(fmaxf(M.minval, 2.f * mu * mu * (1.f - imp) / imp * M.cube_invweight * (1.f + mu * mu))) : 0.f;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            float jw = rowval(uw, mu, k) - aref[c][k], js = rowval(us, mu, k) - aref[c][k];
+            if (jw < 0.f) costw += 0.5f * Dk[c] * jw * jw;
+            if (js < 0.f) costs += 0.5f * Dk[c] * js * js;
+        }
+#pragma unroll
+        for (int k = 0; k < 3; k++) { u[c][k] = uw[k]; w[c][k] = us[k]; }
+    }
+    const bool usew = costw < costs;
+#pragma unroll
+    for (int i = 0; i < 6; i++) a[i] = usew ? warm[i] : as[i];
+#pragma unroll
+    for (int c = 0; c < 4; c++)
+#pragma unroll
+        for (int k = 0; k < 3; k++) u[c][k] = usew ? u[c][k] : w[c][k];
+    int it = 0;
+    for (; it < iterations; it++) {
+        float H[21], g[6], dinv[6], sd[6];
+#pragma unroll
+        for (int i = 0; i < 21; i++) H[i] = 0.f;
+#pragma unroll
+        for (int i = 0; i < 6; i++) { H[GG_TRI(i, i)] = Mc[i]; g[i] = Mc[i] * (a[i] - as[i]); }
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            float Wnn = 0.f, Wn1 = 0.f, W11 = 0.f, Wn2 = 0.f, W22 = 0.f, gn = 0.f, g1 = 0.f, g2 = 0.f;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                float jar = rowval(u[c], mu, k) - aref[c][k];
+                float on = jar < 0.f ? Dk[c] : 0.f;
+                float sm = (k & 1) ? mu : -mu;
+                Wnn += on; gn += on * jar;
+                if (k < 2) { Wn1 += on * sm; W11 += on * mu * mu; g1 += on * jar * sm; }
+                else { Wn2 += on * sm; W22 += on * mu * mu; g2 += on * jar * sm; }
+            }
+            float Pn[6], P1[6], P2[6];
+#pragma unroll
+            for (int i = 0; i < 6; i++) {
+                g[i] += J[c][0][i] * gn + J[c][1][i] * g1 + J[c][2][i] * g2;
+                Pn[i] = Wnn * J[c][0][i] + Wn1 * J[c][1][i] + Wn2 * J[c][2][i];
+                P1[i] = Wn1 * J[c][0][i] + W11 * J[c][1][i];
+                P2[i] = Wn2 * J[c][0][i] + W22 * J[c][2][i];
+            }
+#pragma unroll
+            for (int i = 0; i < 6; i++)
+#pragma unroll
+                for (int j = 0; j <= i; j++) H[GG_TRI(i, j)] += J[c][0][i] * Pn[j] + J[c][1][i] * P1[j] + J[c][2][i] * P2[j];
+        }
+        gnorm = newton_residual<6>(g, H, a);
+        if (gnorm < tol) break;
+        chol_packed<6>(H, dinv);
+#pragma unroll
+        for (int i = 0; i < 6; i++) g[i] = -g[i];
+        chol_solve_packed<6>(H, dinv, g, sd);
+        float q1 = 0.f, q2 = 0.f;
+#pragma unroll
+        for (int i = 0; i < 6; i++) { q1 += Mc[i] * sd[i] * (a[i] - as[i]); q2 += Mc[i] * sd[i] * sd[i]; }
+#pragma unroll
+        for (int c = 0; c < 4; c++)
+#pragma unroll
+            for (int k = 0; k < 3; k++) w[c][k] = dotn<6>(J[c][k], sd);
+        LineSearch L; L.begin();
+        for (;;) {
+            float d1 = q1 + L.al * q2, d2 = q2;
+#pragma unroll
+            for (int c = 0; c < 4; c++)
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    float jv = rowval(w[c], mu, k);
+                    float x = rowval(u[c], mu, k) - aref[c][k] + L.al * jv;
+                    if (x < 0.f) { d1 += Dk[c] * x * jv; d2 += Dk[c] * jv * jv; }
+                }
+            if (!L.next(d1, d2)) break;
+        }
+        int changed = 0;
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            float un[3] = {u[c][0] + L.al * w[c][0], u[c][1] + L.al * w[c][1], u[c][2] + L.al * w[c][2]};
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+                changed += (c < ncp) && ((rowval(u[c], mu, k) - aref[c][k] < 0.f) != (rowval(un, mu, k) - aref[c][k] < 0.f));
+            u[c][0] = un[0]; u[c][1] = un[1]; u[c][2] = un[2];
+        }
+#pragma unroll
+        for (int i = 0; i < 6; i++) a[i] += L.al * sd[i];
+        if (changed == 0 && fabsf(L.al - 1.f) < 1e-3f) { it++; break; }
+    }
+    iters = it;
+}
+
+// general coupled solve over all NV = NU + 6 dofs (pads in contact): Jacobians recomputed per pass
+template <int NA, int NF, bool FH>
+GG_HD void solve_coupled(const GgModel& M, const RobotDyn<NA, NF>& D, const EnvState<NA + NF>& s, const M3& cR, const float* Mc,
+                         const float* as, const float* qdv, const float* lsg, const float* laref, const float* lD,
+                         const Contacts& C, float* a, int iterations, float tol, float scale, int& iters, float& gnorm_out) {
+    constexpr int NU = NA + NF, NV = NU + 6, NH = NV * (NV + 1) / 2;
+    ConRow R;
+    const float mu = M.friction;
+    float costw = 0.f, costs = 0.f;
+    {
+        float e[NV], Me[NU];
+#pragma unroll
+        for (int i = 0; i < NV; i++) e[i] = s.qacc[i] - as[i];
+        symv_packed<NU>(D.Mt, e, Me);
+#pragma unroll
+        for (int i = 0; i < NU; i++) costw += 0.5f * e[i] * Me[i];
+#pragma unroll
+        for (int i = 0; i < 6; i++) costw += 0.5f * Mc[i] * e[NU + i] * e[NU + i];
+#pragma unroll
+        for (int d = 0; d < NU; d++) {
+            float jw = lsg[d] * s.qacc[d] - laref[d], js = lsg[d] * as[d] - laref[d];
+            if (lsg[d] != 0.f && jw < 0.f) costw += 0.5f * lD[d] * jw * jw;
+            if (lsg[d] != 0.f && js < 0.f) costs += 0.5f * lD[d] * js * js;
+        }
+    }
+    for (int c = 0; c < C.count; c++) {
+        float Jn[NV], Jt1[NV], Jt2[NV];
+        V3 t1, t2;
+        tangent_basis(C.n[c], t1, t2);
+        contact_jac<NA, NF, FH>(D, s.cp, cR, C.p[c], C.n[c], t1, t2, C.code[c], Jn, Jt1, Jt2);
+        float vel[3] = {dotn<NV>(Jn, qdv), dotn<NV>(Jt1, qdv), dotn<NV>(Jt2, qdv)};
+        float uw[3] = {dotn<NV>(Jn, s.qacc), dotn<NV>(Jt1, s.qacc), dotn<NV>(Jt2, s.qacc)};
+        float us[3] = {dotn<NV>(Jn, as), dotn<NV>(Jt1, as), dotn<NV>(Jt2, as)};
+        const int code = C.code[c];
+        const int rb = code == 0 ? -1 : (code - 1) % 3;
+        const float wsum = (rb >= 0 ? M.body_invweight[rb] : 0.f) + ((code == 0 || code >= 4) ? M.cube_invweight : 0.f);
+        float imp = 1.f, ar = 0.f;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            imp_aref(M, -C.depth[c], rowval(vel, mu, k), imp, ar);
+            R.aref[c][k] = ar;
+        }
+        const float Dk = gg_rcp(fmaxf(M.minval, 2.f * mu * mu * (1.f - imp) / imp * wsum * (1.f + mu * mu)));
+        R.D[c] = Dk;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            float jw = rowval(uw, mu, k) - R.aref[c][k], js = rowval(us, mu, k) - R.aref[c][k];
+            if (jw < 0.f) costw += 0.5f * Dk * jw * jw;
+            if (js < 0.f) costs += 0.5f * Dk * js * js;
+        }
+        R.u[c][0] = uw[0]; R.u[c][1] = uw[1]; R.u[c][2] = uw[2];
+        R.w[c][0] = us[0]; R.w[c][1] = us[1]; R.w[c][2] = us[2];
+    }
+    const bool warm = costw < costs;
+#pragma unroll
+    for (int i = 0; i < NV; i++) a[i] = warm ? s.qacc[i] : as[i];
+    if (!warm) for (int c = 0; c < C.count; c++) { R.u[c][0] = R.w[c][0]; R.u[c][1] = R.w[c][1]; R.u[c][2] = R.w[c][2]; }
+
+    int it = 0; float gnorm = 0.f;
+    for (; it < iterations; it++) {
+        float H[NH], g[NV], dinv[NV];
+#pragma unroll
+        for (int i = 0; i < NH; i++) H[i] = 0.f;
+#pragma unroll
+        for (int i = 0; i < NU * (NU + 1) / 2; i++) H[i] = D.Mt[i];
+#pragma unroll
+        for (int i = 0; i < 6; i++) H[GG_TRI(NU + i, NU + i)] = Mc[i];
+        {
+            float e[NV];
+#pragma unroll
+            for (int i = 0; i < NV; i++) e[i] = a[i] - as[i];
+            symv_packed<NU>(D.Mt, e, g);
+#pragma unroll
+            for (int i = 0; i < 6; i++) g[NU + i] = Mc[i] * e[NU + i];
+        }
+#pragma unroll
+        for (int d = 0; d < NU; d++) {
+            float jar = lsg[d] * a[d] - laref[d];
+            if (lsg[d] != 0.f && jar < 0.f) { H[GG_TRI(d, d)] += lD[d]; g[d] += lD[d] * jar * lsg[d]; }
+        }
+        for (int c = 0; c < C.count; c++) {
+            float Wnn = 0.f, Wn1 = 0.f, W11 = 0.f, Wn2 = 0.f, W22 = 0.f, gn = 0.f, g1 = 0.f, g2 = 0.f;
+            const float Dk = R.D[c];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                float jar = rowval(R.u[c], mu, k) - R.aref[c][k];
+                if (jar < 0.f) {
+                    float sm = (k & 1) ? mu : -mu;
+                    Wnn += Dk; gn += Dk * jar;
+                    if (k < 2) { Wn1 += Dk * sm; W11 += Dk * mu * mu; g1 += Dk * jar * sm; }
+                    else { Wn2 += Dk * sm; W22 += Dk * mu * mu; g2 += Dk * jar * sm; }
+                }
+            }
+            if (Wnn == 0.f) continue;
+            float Jn[NV], Jt1[NV], Jt2[NV];
+            V3 t1, t2;
+            tangent_basis(C.n[c], t1, t2);
+            const int code = C.code[c];
+            contact_jac<NA, NF, FH>(D, s.cp, cR, C.p[c], C.n[c], t1, t2, code, Jn, Jt1, Jt2);
+            float Pn[NV], P1[NV], P2[NV];
+#pragma unroll
+            for (int i = 0; i < NV; i++) {
+                g[i] += Jn[i] * gn + Jt1[i] * g1 + Jt2[i] * g2;
+                Pn[i] = Wnn * Jn[i] + Wn1 * Jt1[i] + Wn2 * Jt2[i];
+                P1[i] = Wn1 * Jn[i] + W11 * Jt1[i];
+                P2[i] = Wn2 * Jn[i] + W22 * Jt2[i];
+            }
+            if (code == 0) {            // cube block only
+#pragma unroll
+                for (int i = NU; i < NV; i++)
+#pragma unroll
+                    for (int j = NU; j <= i; j++) H[GG_TRI(i, j)] += Jn[i] * Pn[j] + Jt1[i] * P1[j] + Jt2[i] * P2[j];
+            } else if (code < 4) {      // robot block only
+#pragma unroll
+                for (int i = 0; i < NU; i++)
+#pragma unroll
+                    for (int j = 0; j <= i; j++) H[GG_TRI(i, j)] += Jn[i] * Pn[j] + Jt1[i] * P1[j] + Jt2[i] * P2[j];
+            } else {
+#pragma unroll
+                for (int i = 0; i < NV; i++)
+#pragma unroll
+                    for (int j = 0; j <= i; j++) H[GG_TRI(i, j)] += Jn[i] * Pn[j] + Jt1[i] * P1[j] + Jt2[i] * P2[j];
+            }
+        }
+        gnorm = newton_residual<NV>(g, H, a);
+        if (gnorm < tol) break;
+        if (!chol_packed<NV>(H, dinv)) break;
+        float sdir[NV];
+#pragma unroll
+        for (int i = 0; i < NV; i++) g[i] = -g[i];
+        chol_solve_packed<NV>(H, dinv, g, sdir);
+        float q1 = 0.f, q2 = 0.f;
+        {
+            float Ms[NU];
+            symv_packed<NU>(D.Mt, sdir, Ms);
+#pragma unroll
+            for (int i = 0; i < NU; i++) { q1 += Ms[i] * (a[i] - as[i]); q2 += Ms[i] * sdir[i]; }
+        }
+#pragma unroll
+        for (int i = 0; i < 6; i++) { q1 += Mc[i] * sdir[NU + i] * (a[NU + i] - as[NU + i]); q2 += Mc[i] * sdir[NU + i] * sdir[NU + i]; }
+        for (int c = 0; c < C.count; c++) {
+            float Jn[NV], Jt1[NV], Jt2[NV];
+            V3 t1, t2;
+            tangent_basis(C.n[c], t1, t2);
+            contact_jac<NA, NF, FH>(D, s.cp, cR, C.p[c], C.n[c], t1, t2, C.code[c], Jn, Jt1, Jt2);
+            R.w[c][0] = dotn<NV>(Jn, sdir); R.w[c][1] = dotn<NV>(Jt1, sdir); R.w[c][2] = dotn<NV>(Jt2, sdir);
+        }
+        LineSearch L; L.begin();
+        for (;;) {
+            float d1 = q1 + L.al * q2, d2 = q2;
+#pragma unroll
+            for (int d = 0; d < NU; d++) {
+                float jv = lsg[d] * sdir[d];
+                float x = lsg[d] * a[d] - laref[d] + L.al * jv;
+                if (lsg[d] != 0.f && x < 0.f) { d1 += lD[d] * x * jv; d2 += lD[d] * jv * jv; }
+            }
+            for (int c = 0; c < C.count; c++) {
+                const float Dk = R.D[c];
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    float jv = rowval(R.w[c], mu, k);
+                    float x = rowval(R.u[c], mu, k) - R.aref[c][k] + L.al * jv;
+                    if (x < 0.f) { d1 += Dk * x * jv; d2 += Dk * jv * jv; }
+                }
+            }
+            if (!L.next(d1, d2)) break;
+        }
+        const float al = L.al;
+        int changed = 0;
+#pragma unroll
+        for (int d = 0; d < NU; d++) {
+            float j0 = lsg[d] * a[d] - laref[d], j1 = lsg[d] * (a[d] + al * sdir[d]) - laref[d];
+            changed += (lsg[d] != 0.f) && ((j0 < 0.f) != (j1 < 0.f));
+        }
+#pragma unroll
+        for (int i = 0; i < NV; i++) a[i] += al * sdir[i];
+        for (int c = 0; c < C.count; c++) {
+            float un[3] = {R.u[c][0] + al * R.w[c][0], R.u[c][1] + al * R.w[c][1], R.u[c][2] + al * R.w[c][2]};
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+                changed += (rowval(R.u[c], mu, k) - R.aref[c][k] < 0.f) != (rowval(un, mu, k) - R.aref[c][k] < 0.f);
+            R.u[c][0] = un[0]; R.u[c][1] = un[1]; R.u[c][2] = un[2];
+        }
+        if (changed == 0 && fabsf(al - 1.f) < 1e-3f) { it++; break; }
+    }
+    iters = it; gnorm_out = gnorm;
+}
+
+// pads against plane and cube in the oracle's order (after the cube-plane contacts already in C)
+template <int NA, int NF>
+GG_HD void collide_pads(const GgModel& M, const RobotDyn<NA, NF>& D, V3 cp, const M3& cR, Contacts& C) {
+    const int maxc = M.max_contacts < GG_MAX_CONTACTS ? M.max_contacts : GG_MAX_CONTACTS;
+    V3 ch = ld3(M.cube_half);
+    for (int pass = 0; pass < 2; pass++) {
+        for (int g = 0; g < M.n_pads; g++) {
+            int b = M.pad_body[g];
+            int fi = b - 1 < 0 ? 0 : (b - 1 < NF ? b - 1 : 0);
+            M3 Rb = b == 0 ? D.lR : D.fR[fi];
+            V3 pb = b == 0 ? D.lp : D.fp[fi];
+            V3 c = pb + mul(Rb, ld3(M.pad_pos[g]));
+            M3 R = mmul(Rb, qmat(ldq(M.pad_quat[g])));
+            V3 h = ld3(M.pad_half[g]);
+            if (pass == 0) plane_box(M.plane_z, c, R, h, 1 + b, maxc, C);
+            else box_box(c, R, h, cp, cR, ch, 4 + b, maxc, C);
+        }
+    }
+}
+
+// conservative body-level broad phase: does any pad-carrying body's bounding sphere reach the plane or the cube?
+template <int NA, int NF>
+GG_HD bool pads_may_touch(const GgModel& M, const RobotDyn<NA, NF>& D, V3 cp) {
+    V3 ch = ld3(M.cube_half);
+    const float rc = sqrtf(dot(ch, ch));
+    bool any = false;
+#pragma unroll
+    for (int b = 0; b < 1 + NF; b++) {
+        const float r = M.pad_bound[b][3];
+        const M3& Rb = b == 0 ? D.lR : D.fR[b == 0 ? 0 : b - 1];
+        V3 pb = b == 0 ? D.lp : D.fp[b == 0 ? 0 : b - 1];
+        V3 c = pb + mul(Rb, ld3(M.pad_bound[b]));
+        V3 d = c - cp;
+        any = any || (r >= 0.f && ((c.z - r <= M.plane_z) || (dot(d, d) <= (r + rc) * (r + rc))));
+    }
+    return any;
+}
+
+// ---------------------------------------------------------------------------------------------
+// One substep (A.2): dynamics at t, collision, constraint solve, semi-implicit Euler.
 // ---------------------------------------------------------------------------------------------
 template <int NA, int NF, bool FH>
 GG_HD void env_substep(const GgModel& M, EnvState<NA + NF>& s, const float* target, int iterations, float tol, StepInfo& info) {
-    constexpr int NU = NA + NF, NV = NU + 6, NH = NV * (NV + 1) / 2;
+    constexpr int NU = NA + NF, NV = NU + 6;
     RobotDyn<NA, NF> D;
     robot_dynamics<NA, NF, FH>(M, s.q, s.qd, target, D);
     const M3 cR = qmat(s.cq);
@@ -389,22 +805,22 @@ GG_HD void env_substep(const GgModel& M, EnvState<NA + NF>& s, const float* targ
     float Mc[6] = {M.cube_mass, M.cube_mass, M.cube_mass, M.cube_inertia[0], M.cube_inertia[1], M.cube_inertia[2]};
     float as[NV], qdv[NV];
     {
-        float L[NU * (NU + 1) / 2];
+        float L[NU * (NU + 1) / 2], dinv[NU];
 #pragma unroll
         for (int i = 0; i < NU * (NU + 1) / 2; i++) L[i] = D.Mt[i];
-        chol_packed<NU>(L);
-        chol_solve_packed<NU>(L, D.fs, as);
+        chol_packed<NU>(L, dinv);
+        chol_solve_packed<NU>(L, dinv, D.fs, as);
         V3 Iw = mk(Mc[3] * s.cw.x, Mc[4] * s.cw.y, Mc[5] * s.cw.z);
         V3 gyro = cross(s.cw, Iw);
         as[NU + 0] = 0.f; as[NU + 1] = 0.f; as[NU + 2] = -M.gravity;
-        as[NU + 3] = -gyro.x / Mc[3]; as[NU + 4] = -gyro.y / Mc[4]; as[NU + 5] = -gyro.z / Mc[5];
+        as[NU + 3] = -gg_div(gyro.x, Mc[3]); as[NU + 4] = -gg_div(gyro.y, Mc[4]); as[NU + 5] = -gg_div(gyro.z, Mc[5]);
 #pragma unroll
         for (int i = 0; i < NU; i++) qdv[i] = s.qd[i];
         qdv[NU + 0] = s.cv.x; qdv[NU + 1] = s.cv.y; qdv[NU + 2] = s.cv.z;
         qdv[NU + 3] = s.cw.x; qdv[NU + 4] = s.cw.y; qdv[NU + 5] = s.cw.z;
     }
 
-    // ---- constraints: joint limits (one possible row per dof) and contacts
+    // ---- joint-limit rows (at most one per dof)
     float lsg[NU], laref[NU], lD[NU];
     int nlim = 0;
 #pragma unroll
@@ -415,218 +831,70 @@ GG_HD void env_substep(const GgModel& M, EnvState<NA + NF>& s, const float* targ
         float imp, aref;
         imp_aref(M, pos, sg * s.qd[d], imp, aref);
         lsg[d] = sg; laref[d] = aref;
-        lD[d] = 1.f / fmaxf(M.minval, (1.f - imp) / imp * M.dof_invweight[d]);
+        lD[d] = gg_rcp(fmaxf(M.minval, (1.f - imp) / imp * M.dof_invweight[d]));
         nlim += sg != 0.f;
     }
-    Contacts C;
-    collide<NA, NF>(M, D, s.cp, cR, C);
-    info.ncon = C.count;
+
+    float meaninertia = 0.f;
+#pragma unroll
+    for (int i = 0; i < NU; i++) meaninertia += D.Mt[GG_TRI(i, i)];
+#pragma unroll
+    for (int i = 0; i < 6; i++) meaninertia += Mc[i];
+    const float scale = gg_rcp(meaninertia);      // = 1 / (mean inertia * NV)
 
     float a[NV];
-    if (nlim == 0 && C.count == 0) {
+    info.iters = 0; info.grad = 0.f;
+    if (!pads_may_touch<NA, NF>(M, D, s.cp)) {
+        // ---- decoupled fast path: robot block (limits only) and cube block (plane contacts only)
+        if (nlim == 0) {
 #pragma unroll
-        for (int i = 0; i < NV; i++) a[i] = as[i];
-        info.iters = 0; info.grad = 0.f;
-    } else {
-        ConRow R;
-        const float mu = M.friction;
-        // pass 0: aref / D per contact, J a for both warm-start candidates, their costs
-        float costw = 0.f, costs = 0.f;
+            for (int i = 0; i < NU; i++) a[i] = as[i];
+        } else {
+            int it; float gn;
+            solve_robot_limits<NU>(D.Mt, as, lsg, laref, lD, s.qacc, a, iterations, tol, scale, it, gn);
+            info.iters = it; info.grad = gn;
+        }
+        V3 pc[4]; float dc[4]; int ncp = 0;
         {
-            float e[NV];
+            V3 half = ld3(M.cube_half);
 #pragma unroll
-            for (int i = 0; i < NV; i++) e[i] = s.qacc[i] - as[i];
-            // 1/2 e^T Mt e
+            for (int c = 0; c < 4; c++) { pc[c] = s.cp; dc[c] = 0.f; }
 #pragma unroll
-            for (int i = 0; i < NU; i++) {
-                float r = 0.f;
+            for (int i = 0; i < 8; i++) {
+                V3 l = mk((i & 1) ? half.x : -half.x, (i & 2) ? half.y : -half.y, (i & 4) ? half.z : -half.z);
+                V3 w = s.cp + mul(cR, l);
+                float dist = w.z - M.plane_z;
+                if (dist <= 0.f && ncp < 4) {
+                    V3 pp = mk(w.x, w.y, w.z - 0.5f * dist);
 #pragma unroll
-                for (int j = 0; j < NU; j++) r += D.Mt[i >= j ? GG_TRI(i, j) : GG_TRI(j, i)] * e[j];
-                costw += 0.5f * e[i] * r;
-            }
-#pragma unroll
-            for (int i = 0; i < 6; i++) costw += 0.5f * Mc[i] * e[NU + i] * e[NU + i];
-#pragma unroll
-            for (int d = 0; d < NU; d++) {
-                if (lsg[d] != 0.f) {
-                    float jw = lsg[d] * s.qacc[d] - laref[d], js = lsg[d] * as[d] - laref[d];
-                    if (jw < 0.f) costw += 0.5f * lD[d] * jw * jw;
-                    if (js < 0.f) costs += 0.5f * lD[d] * js * js;
+                    for (int c = 0; c < 4; c++) if (c == ncp) { pc[c] = pp; dc[c] = -dist; }
+                    ncp++;
                 }
             }
         }
-        float uw[3], us[3];
-        for (int c = 0; c < C.count; c++) {
-            float Jn[NV], Jt1[NV], Jt2[NV];
-            V3 t1, t2;
-            tangent_basis(C.n[c], t1, t2);
-            contact_jac<NA, NF, FH>(D, s.cp, cR, C.p[c], C.n[c], t1, t2, C.code[c], Jn, Jt1, Jt2);
-            float vel[3] = {dotn<NV>(Jn, qdv), dotn<NV>(Jt1, qdv), dotn<NV>(Jt2, qdv)};
-            uw[0] = dotn<NV>(Jn, s.qacc); uw[1] = dotn<NV>(Jt1, s.qacc); uw[2] = dotn<NV>(Jt2, s.qacc);
-            us[0] = dotn<NV>(Jn, as); us[1] = dotn<NV>(Jt1, as); us[2] = dotn<NV>(Jt2, as);
-            int code = C.code[c];
-            int rb = code == 0 ? -1 : (code - 1) % 3;
-            float wsum = (rb >= 0 ? M.body_invweight[rb] : 0.f) + ((code == 0 || code >= 4) ? M.cube_invweight : 0.f);
-            float imp = 0.f, ar = 0.f;
+        info.ncon = ncp;
+        if (ncp == 0) {
 #pragma unroll
-            for (int k = 0; k < 4; k++) {
-                imp_aref(M, -C.depth[c], rowval(vel, mu, k), imp, ar);
-                R.aref[c][k] = ar;
-                float jw = rowval(uw, mu, k) - ar, js = rowval(us, mu, k) - ar;
-                float Dk = 1.f / fmaxf(M.minval, 2.f * mu * mu * (1.f - imp) / imp * wsum * (1.f + mu * mu));
-                R.D[c] = Dk;
-                if (jw < 0.f) costw += 0.5f * Dk * jw * jw;
-                if (js < 0.f) costs += 0.5f * Dk * js * js;
-            }
-            // provisional: keep both, decide below
-            R.u[c][0] = uw[0]; R.u[c][1] = uw[1]; R.u[c][2] = uw[2];
-            R.w[c][0] = us[0]; R.w[c][1] = us[1]; R.w[c][2] = us[2];
+            for (int i = 0; i < 6; i++) a[NU + i] = as[NU + i];
+        } else {
+            int it; float gn;
+            solve_cube_plane(M, Mc, as + NU, qdv + NU, s.cp, cR, pc, dc, ncp, s.qacc + NU, a + NU, iterations, tol, scale, it, gn);
+            info.iters = it > info.iters ? it : info.iters;
+            info.grad = fmaxf(info.grad, gn);
         }
-        const bool warm = costw < costs;
+    } else {
+        Contacts C;
+        C.count = 0;
+        const int maxc = M.max_contacts < GG_MAX_CONTACTS ? M.max_contacts : GG_MAX_CONTACTS;
+        plane_box(M.plane_z, s.cp, cR, ld3(M.cube_half), 0, maxc, C);
+        collide_pads<NA, NF>(M, D, s.cp, cR, C);
+        info.ncon = C.count;
+        if (nlim == 0 && C.count == 0) {
 #pragma unroll
-        for (int i = 0; i < NV; i++) a[i] = warm ? s.qacc[i] : as[i];
-        if (!warm) for (int c = 0; c < C.count; c++) { R.u[c][0] = R.w[c][0]; R.u[c][1] = R.w[c][1]; R.u[c][2] = R.w[c][2]; }
-
-        float meaninertia = 0.f;
-#pragma unroll
-        for (int i = 0; i < NU; i++) meaninertia += D.Mt[GG_TRI(i, i)];
-#pragma unroll
-        for (int i = 0; i < 6; i++) meaninertia += Mc[i];
-        const float scale = 1.f / meaninertia;      // = 1 / (mean * NV)
-        int it = 0; float gnorm = 0.f;
-        for (; it < iterations; it++) {
-            float H[NH], g[NV];
-            // H = Mt, g = Mt (a - a_s)
-#pragma unroll
-            for (int i = 0; i < NH; i++) H[i] = 0.f;
-#pragma unroll
-            for (int i = 0; i < NU * (NU + 1) / 2; i++) H[i] = D.Mt[i];
-#pragma unroll
-            for (int i = 0; i < 6; i++) H[GG_TRI(NU + i, NU + i)] = Mc[i];
-            {
-                float e[NV];
-#pragma unroll
-                for (int i = 0; i < NV; i++) e[i] = a[i] - as[i];
-#pragma unroll
-                for (int i = 0; i < NU; i++) {
-                    float r = 0.f;
-#pragma unroll
-                    for (int j = 0; j < NU; j++) r += D.Mt[i >= j ? GG_TRI(i, j) : GG_TRI(j, i)] * e[j];
-                    g[i] = r;
-                }
-#pragma unroll
-                for (int i = 0; i < 6; i++) g[NU + i] = Mc[i] * e[NU + i];
-            }
-#pragma unroll
-            for (int d = 0; d < NU; d++) {
-                float jar = lsg[d] * a[d] - laref[d];
-                if (lsg[d] != 0.f && jar < 0.f) { H[GG_TRI(d, d)] += lD[d]; g[d] += lD[d] * jar * lsg[d]; }
-            }
-            for (int c = 0; c < C.count; c++) {
-                float Wnn = 0.f, Wn1 = 0.f, W11 = 0.f, Wn2 = 0.f, W22 = 0.f, gn = 0.f, g1 = 0.f, g2 = 0.f;
-                const float Dk = R.D[c];
-#pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    float jar = rowval(R.u[c], mu, k) - R.aref[c][k];
-                    if (jar < 0.f) {
-                        float sm = (k & 1) ? mu : -mu;
-                        Wnn += Dk; gn += Dk * jar;
-                        if (k < 2) { Wn1 += Dk * sm; W11 += Dk * mu * mu; g1 += Dk * jar * sm; }
-                        else { Wn2 += Dk * sm; W22 += Dk * mu * mu; g2 += Dk * jar * sm; }
-                    }
-                }
-                if (Wnn == 0.f) continue;
-                float Jn[NV], Jt1[NV], Jt2[NV];
-                V3 t1, t2;
-                tangent_basis(C.n[c], t1, t2);
-                const int code = C.code[c];
-                contact_jac<NA, NF, FH>(D, s.cp, cR, C.p[c], C.n[c], t1, t2, code, Jn, Jt1, Jt2);
-                float Pn[NV], P1[NV], P2[NV];
-#pragma unroll
-                for (int i = 0; i < NV; i++) {
-                    g[i] += Jn[i] * gn + Jt1[i] * g1 + Jt2[i] * g2;
-                    Pn[i] = Wnn * Jn[i] + Wn1 * Jt1[i] + Wn2 * Jt2[i];
-                    P1[i] = Wn1 * Jn[i] + W11 * Jt1[i];
-                    P2[i] = Wn2 * Jn[i] + W22 * Jt2[i];
-                }
-                if (code == 0) {            // cube block only
-#pragma unroll
-                    for (int i = NU; i < NV; i++)
-#pragma unroll
-                        for (int j = NU; j <= i; j++) H[GG_TRI(i, j)] += Jn[i] * Pn[j] + Jt1[i] * P1[j] + Jt2[i] * P2[j];
-                } else if (code < 4) {      // robot block only
-#pragma unroll
-                    for (int i = 0; i < NU; i++)
-#pragma unroll
-                        for (int j = 0; j <= i; j++) H[GG_TRI(i, j)] += Jn[i] * Pn[j] + Jt1[i] * P1[j] + Jt2[i] * P2[j];
-                } else {
-#pragma unroll
-                    for (int i = 0; i < NV; i++)
-#pragma unroll
-                        for (int j = 0; j <= i; j++) H[GG_TRI(i, j)] += Jn[i] * Pn[j] + Jt1[i] * P1[j] + Jt2[i] * P2[j];
-                }
-            }
-            gnorm = sqrtf(dotn<NV>(g, g)) * scale;
-            if (gnorm < tol) break;
-            if (!chol_packed<NV>(H)) break;
-            float sdir[NV];
-#pragma unroll
-            for (int i = 0; i < NV; i++) g[i] = -g[i];
-            chol_solve_packed<NV>(H, g, sdir);
-            // line-search quadratic part: q1 = s^T Mt (a - a_s), q2 = s^T Mt s
-            float q1 = 0.f, q2 = 0.f;
-#pragma unroll
-            for (int i = 0; i < NU; i++) {
-                float r = 0.f;
-#pragma unroll
-                for (int j = 0; j < NU; j++) r += D.Mt[i >= j ? GG_TRI(i, j) : GG_TRI(j, i)] * sdir[j];
-                q1 += r * (a[i] - as[i]); q2 += r * sdir[i];
-            }
-#pragma unroll
-            for (int i = 0; i < 6; i++) { q1 += Mc[i] * sdir[NU + i] * (a[NU + i] - as[NU + i]); q2 += Mc[i] * sdir[NU + i] * sdir[NU + i]; }
-            for (int c = 0; c < C.count; c++) {
-                float Jn[NV], Jt1[NV], Jt2[NV];
-                V3 t1, t2;
-                tangent_basis(C.n[c], t1, t2);
-                contact_jac<NA, NF, FH>(D, s.cp, cR, C.p[c], C.n[c], t1, t2, C.code[c], Jn, Jt1, Jt2);
-                R.w[c][0] = dotn<NV>(Jn, sdir); R.w[c][1] = dotn<NV>(Jt1, sdir); R.w[c][2] = dotn<NV>(Jt2, sdir);
-            }
-            // safeguarded Newton on phi'(alpha) (piecewise linear, increasing)
-            float al = 0.f, lo = 0.f, hi = -1.f, d0 = 0.f, d1 = 0.f, d2 = 1.f;
-            for (int ls = 0; ls < 12; ls++) {
-                if (ls > 0) {
-                    float nx = al - d1 / d2;
-                    if (hi >= 0.f && (nx <= lo || nx >= hi)) nx = 0.5f * (lo + hi);
-                    if (nx <= 0.f) nx = hi >= 0.f ? 0.5f * (lo + hi) : 1e-3f;
-                    al = nx;
-                }
-                d1 = q1 + al * q2; d2 = q2;
-#pragma unroll
-                for (int d = 0; d < NU; d++) {
-                    if (lsg[d] != 0.f) {
-                        float jv = lsg[d] * sdir[d];
-                        float x = lsg[d] * a[d] - laref[d] + al * jv;
-                        if (x < 0.f) { d1 += lD[d] * x * jv; d2 += lD[d] * jv * jv; }
-                    }
-                }
-                for (int c = 0; c < C.count; c++) {
-                    const float Dk = R.D[c];
-#pragma unroll
-                    for (int k = 0; k < 4; k++) {
-                        float jv = rowval(R.w[c], mu, k);
-                        float x = rowval(R.u[c], mu, k) - R.aref[c][k] + al * jv;
-                        if (x < 0.f) { d1 += Dk * x * jv; d2 += Dk * jv * jv; }
-                    }
-                }
-                if (ls == 0) { d0 = d1; continue; }
-                if (d1 < 0.f) lo = al; else hi = al;
-                if (fabsf(d1) <= fabsf(d0) * 1e-6f) break;
-            }
-#pragma unroll
-            for (int i = 0; i < NV; i++) a[i] += al * sdir[i];
-            for (int c = 0; c < C.count; c++) { R.u[c][0] += al * R.w[c][0]; R.u[c][1] += al * R.w[c][1]; R.u[c][2] += al * R.w[c][2]; }
+            for (int i = 0; i < NV; i++) a[i] = as[i];
+        } else {
+            solve_coupled<NA, NF, FH>(M, D, s, cR, Mc, as, qdv, lsg, laref, lD, C, a, iterations, tol, scale, info.iters, info.grad);
         }
-        info.iters = it; info.grad = gnorm;
     }
 
     // ---- semi-implicit Euler
@@ -645,11 +913,11 @@ GG_HD void env_substep(const GgModel& M, EnvState<NA + NF>& s, const float* targ
         if (ang > 0.f) {
             float sn, cs;
             gg_sincos(0.5f * ang, &sn, &cs);
-            float k = sn / ang;
+            float k = gg_div(sn, ang);
             dq = mkq(cs, w.x * k, w.y * k, w.z * k);
         }
         Q4 nq = qmul(s.cq, dq);
-        float inv = 1.f / sqrtf(nq.w * nq.w + nq.x * nq.x + nq.y * nq.y + nq.z * nq.z);
+        float inv = gg_rsqrt(nq.w * nq.w + nq.x * nq.x + nq.y * nq.y + nq.z * nq.z);
         s.cq = mkq(nq.w * inv, nq.x * inv, nq.y * inv, nq.z * inv);
     }
 }

@@ -283,7 +283,7 @@ int gg_create(const GgModel* model, int n_envs, int device, GgSim** out) {
     memset(s, 0, sizeof(*s));
     s->model = *model; s->n = n_envs; s->device = device; s->kind = kind;
     s->stride = (n_envs + 31) / 32 * 32;
-    s->cfg.solver_iterations = 10; s->cfg.solver_tolerance = 1e-6f;
+    s->cfg.solver_iterations = 10; s->cfg.solver_tolerance = 1e-5f;
     cudaError_t e1 = cudaMalloc(&s->done, (size_t)s->stride);
     cudaError_t e2 = cudaMalloc(&s->stats, 8 * sizeof(double));
     if (e1 != cudaSuccess || e2 != cudaSuccess) { cudaFree(s->done); cudaFree(s->stats); delete s; return fail("gg_create: cudaMalloc failed%s"); }

@@ -97,8 +97,33 @@ GG_HD void gg_sincos(float a, float* s, float* c) {
 // ---- packed lower-triangular helpers (row-major: idx(i,j) = i(i+1)/2 + j, j <= i) -----------------
 #define GG_TRI(i, j) ((i) * ((i) + 1) / 2 + (j))
 
-// in-place Cholesky A = L L^T on a packed lower matrix; fully unrolled (static indices -> registers)
-template <int N> GG_HD bool chol_packed(float* A) {
+// fast reciprocal / reciprocal square root (device: MUFU-based, <= 2 ulp; host harness: exact)
+GG_HD float gg_rcp(float x) {
+#if defined(__CUDA_ARCH__)
+    return __frcp_rn(x);
+#else
+    return 1.0f / x;
+#endif
+}
+GG_HD float gg_div(float a, float b) {
+#if defined(__CUDA_ARCH__)
+    return __fdividef(a, b);
+#else
+    return a / b;
+#endif
+}
+GG_HD float gg_rsqrt(float x) {
+#if defined(__CUDA_ARCH__)
+    float r = rsqrtf(x);
+    return r * (1.5f - 0.5f * x * r * r);      // one Newton step: ~1 ulp
+#else
+    return 1.0f / sqrtf(x);
+#endif
+}
+
+// in-place Cholesky A = L L^T on a packed lower matrix, fully unrolled (static indices -> registers).
+// dinv receives 1 / L(j,j) so that the triangular solves multiply instead of divide.
+template <int N> GG_HD bool chol_packed(float* A, float* dinv) {
     bool ok = true;
 #pragma unroll
     for (int j = 0; j < N; j++) {
@@ -106,7 +131,8 @@ template <int N> GG_HD bool chol_packed(float* A) {
 #pragma unroll
         for (int k = 0; k < j; k++) s -= A[GG_TRI(j, k)] * A[GG_TRI(j, k)];
         ok = ok && (s > 0.f);
-        float inv = 1.0f / sqrtf(s);
+        float inv = gg_rsqrt(s);
+        dinv[j] = inv;
         A[GG_TRI(j, j)] = s * inv;
 #pragma unroll
         for (int i = j + 1; i < N; i++) {
@@ -119,21 +145,31 @@ template <int N> GG_HD bool chol_packed(float* A) {
     return ok;
 }
 // solve L L^T x = b (x may alias b)
-template <int N> GG_HD void chol_solve_packed(const float* L, const float* b, float* x) {
+template <int N> GG_HD void chol_solve_packed(const float* L, const float* dinv, const float* b, float* x) {
     float y[N];
 #pragma unroll
     for (int i = 0; i < N; i++) {
         float s = b[i];
 #pragma unroll
         for (int k = 0; k < i; k++) s -= L[GG_TRI(i, k)] * y[k];
-        y[i] = s / L[GG_TRI(i, i)];
+        y[i] = s * dinv[i];
     }
 #pragma unroll
     for (int i = N - 1; i >= 0; i--) {
         float s = y[i];
 #pragma unroll
         for (int k = i + 1; k < N; k++) s -= L[GG_TRI(k, i)] * x[k];
-        x[i] = s / L[GG_TRI(i, i)];
+        x[i] = s * dinv[i];
+    }
+}
+// y = A x for a packed symmetric matrix
+template <int N> GG_HD void symv_packed(const float* A, const float* x, float* y) {
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+        float r = 0.f;
+#pragma unroll
+        for (int j = 0; j < N; j++) r += A[i >= j ? GG_TRI(i, j) : GG_TRI(j, i)] * x[j];
+        y[i] = r;
     }
 }
 

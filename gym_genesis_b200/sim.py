@@ -31,7 +31,7 @@ class BatchedSim:
     """
 
     def __init__(self, scene_model: SceneModel, n_envs: int, device="cuda", solver_iterations: int = 10,
-                 solver_tolerance: float = 1e-6, auto_reset: bool = False, time_limit: bool = False, reset_prob: float = 0.0,
+                 solver_tolerance: float = 1e-5, auto_reset: bool = False, time_limit: bool = False, reset_prob: float = 0.0,
                  seed: int = 0, first_env_id: int = 0):
         if not torch.cuda.is_available():
             raise GgError("gym_genesis_b200 needs a CUDA device: the env.step path has no CPU fallback")

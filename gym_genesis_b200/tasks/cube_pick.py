@@ -79,7 +79,7 @@ class CubePickBatch:
 
     def __init__(self, enable_pixels, observation_height, observation_width, num_envs, env_spacing, camera_capture_mode,
                  strip_environment_state, device="cuda", auto_reset=False, time_limit=False, solver_iterations=10,
-                 solver_tolerance=1e-6, seed=0, first_env_id=0, reset_prob=0.0, success_height=None):
+                 solver_tolerance=1e-5, seed=0, first_env_id=0, reset_prob=0.0, success_height=None):
         if enable_pixels:
             raise NotImplementedError("state-only path: rendering (enable_pixels=True) is out of scope (SURVEY.md section 5)")
         if num_envs <= 0:

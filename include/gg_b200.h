@@ -59,6 +59,7 @@ typedef struct GgModel {
     float body_invweight[1 + GG_MAX_FING];        /* last arm link, finger 0, finger 1 */
     int32_t pad_body[GG_MAX_PADS];                /* 0 = last arm link, 1 + f = finger f */
     float pad_half[GG_MAX_PADS][3], pad_pos[GG_MAX_PADS][3], pad_quat[GG_MAX_PADS][4];
+    float pad_bound[1 + GG_MAX_FING][4];          /* per pad-carrying body: bounding sphere (centre xyz, radius; r < 0: no pads) */
     float cube_half[3], cube_mass, cube_inertia[3], cube_invweight;
     float dt, gravity, plane_z, friction;
     float tc, dr, dmin, dmax, width, mid, power, minval;   /* solref / solimp */
@@ -69,7 +70,7 @@ typedef struct GgModel {
 /* Run-time options; defaults (all zero except iterations/tolerance) reproduce the reference. */
 typedef struct GgConfig {
     int32_t solver_iterations;   /* Newton iteration cap per substep (default 10)                  */
-    float solver_tolerance;      /* scaled-gradient stop criterion (default 1e-6)                  */
+    float solver_tolerance;      /* stop when max_i |g_i|/H_ii <= tol * (1 + |a|_inf) (default 1e-5)  */
     int32_t auto_reset;          /* 1: envs that finished (terminated|truncated) reset on next step */
     int32_t time_limit;          /* 1: truncated = step_count >= model.horizon (reference: always 0)*/
     float reset_prob;            /* per-env Bernoulli reset probability per step (benchmark C3)      */

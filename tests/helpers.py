@@ -67,7 +67,7 @@ def _p(a):
     return a.ctypes.data_as(C.c_void_p)
 
 
-def hostsim_step(hs, gg_model, Q, QD, QA, T, iters=10, tol=1e-6):
+def hostsim_step(hs, gg_model, Q, QD, QA, T, iters=10, tol=1e-5):
     q, qd, qa, t = f32(Q).copy(), f32(QD).copy(), f32(QA).copy(), f32(T)
     n = q.shape[0]
     info = np.zeros((n, 3), np.int32)

@@ -1,0 +1,222 @@
+"""GPU tier: the CUDA path, called through the C ABI (BatchedSim -> libgg_b200.so), against the oracle."""
+import numpy as np
+import pytest
+import torch
+
+from gym_genesis_b200 import model as mdl
+from helpers import (ROLLOUT_POS_TOL, TOL_Q_ABS, f32, random_states, scripted_grasp_states, substep_errors)
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def Sim():
+    from gym_genesis_b200.sim import BatchedSim
+    return BatchedSim
+
+
+def _np(t):
+    return t.detach().cpu().numpy().astype(np.float64)
+
+
+def _a_smooth_scale(o, Q, QD, T):
+    return np.array([np.abs(o.dynamics(Q[k], QD[k], T[k])["a_smooth"]).max() * 0.01 for k in range(Q.shape[0])])
+
+
+def _one_substep(sim, Q, QD, QA, T):
+    sim.set_state(Q, QD, QA)
+    sim.step(torch.as_tensor(f32(T)))
+    q, qd, qa = sim.get_state()
+    return _np(q), _np(qd), _np(qa)
+
+
+@pytest.mark.parametrize("on_ground", [True, False])
+def test_single_substep_random_states(Sim, franka_model, oracle64, on_ground):
+    n = 256
+    rng = np.random.default_rng(10 + on_ground)
+    Q, QD, T = random_states(franka_model, rng, n, cube_on_ground=on_ground)
+    QA = np.zeros_like(QD)
+    sim = Sim(franka_model, n)
+    q, qd, qa = _one_substep(sim, Q, QD, QA, T)
+    qo, qdo, qao = Q.copy(), QD.copy(), QA.copy()
+    oracle64.step(qo, qdo, qao, T, iterations=100, tol=1e-12)
+    eq, ev = substep_errors(Q, QD, qo, qdo, q, qd, _a_smooth_scale(oracle64, Q, QD, T))
+    assert eq.max() < TOL_Q_ABS and ev.max() < 1.0, (eq.max(), ev.max())
+    # observations / reward / flags of the step against the oracle on the GPU's own state (bit-exact flags)
+    a, e, r, t = oracle64.obs(q)
+    assert np.abs(_np(sim.obs_agent) - a).max() < 2e-6 and np.abs(_np(sim.obs_env) - e).max() < 2e-6
+    assert (sim.terminated.cpu().numpy().astype(bool) == t).all()
+    assert (sim.reward.cpu().numpy() == r.astype(np.float32)).all()
+    assert not sim.truncated.any()
+
+
+def test_single_substep_scripted_grasp_states(Sim, franka_model, oracle64):
+    """Contact-rich states (pads on the ground, pads on the cube, up to the 64-contact cap)."""
+    states, reward = scripted_grasp_states(franka_model, oracle64, stride=2)
+    assert reward == 1.0
+    Q, QD, QA, T = (np.concatenate([f32(s[k]) for s in states]).astype(np.float64) for k in range(4))
+    sim = Sim(franka_model, Q.shape[0])
+    q, qd, qa = _one_substep(sim, Q, QD, QA, T)
+    qo, qdo, qao = Q.copy(), QD.copy(), QA.copy()
+    info, _ = oracle64.step(qo, qdo, qao, T, iterations=100, tol=1e-12)
+    assert info[:, 0].max() >= 32
+    eq, ev = substep_errors(Q, QD, qo, qdo, q, qd, _a_smooth_scale(oracle64, Q, QD, T))
+    assert eq.max() < TOL_Q_ABS and ev.max() < 1.0, (eq.max(), ev.max())
+
+
+def test_rollout_100_steps(Sim, franka_model, oracle64):
+    """100 control steps, smooth random-walk targets, cube resting: positions stay within the stated bound."""
+    n = 32
+    rng = np.random.default_rng(20)
+    sim = Sim(franka_model, n)
+    xy = np.stack([rng.uniform(0.45, 0.8, n), rng.uniform(-0.25, 0.25, n)], 1).astype(np.float32)
+    sim.reset(None, xy)
+    q, qd, qa = (_np(t) for t in sim.get_state())
+    tgt = np.tile(mdl.FRANKA_HOME, (n, 1))
+    worst = 0.0
+    for k in range(100):
+        tgt = tgt + rng.normal(0, 0.02, tgt.shape)
+        tgt[:, 7:] = np.clip(tgt[:, 7:], -0.02, 0.04)
+        t32 = f32(tgt)
+        sim.step(torch.as_tensor(t32))
+        oracle64.step(q, qd, qa, t32.astype(np.float64), iterations=100, tol=1e-12)
+    qg = _np(sim.get_state()[0])
+    worst = np.abs(qg[:, :12] - q[:, :12]).max()
+    assert worst < ROLLOUT_POS_TOL, worst
+    assert worst < 1e-4          # measured far below the stated bound in free space / resting contact
+
+
+def test_reset_reproduces_reference_sequence(Sim, franka_model, oracle64):
+    """Full reset = spawn at the host RandomState draws, home pose, hold-home target, ONE settle step, obs
+    (franka/cube_pick.py:86-112); the post-reset cube quaternion is the literal (0,0,0,1) of the reference."""
+    n = 128
+    sim = Sim(franka_model, n)
+    r = np.random.RandomState(7)
+    xy = np.stack([r.uniform(0.45, 0.80, n), r.uniform(-0.25, 0.25, n)], 1).astype(np.float32)
+    sim.reset(None, xy)
+    Q, QD, QA = oracle64.new_state(n)
+    oracle64.reset(Q, QD, QA, xy.astype(np.float64))
+    oracle64.step(Q, QD, QA, np.tile(mdl.FRANKA_HOME, (n, 1)))
+    q, qd, _ = (_np(t) for t in sim.get_state())
+    assert np.abs(q - Q).max() < TOL_Q_ABS
+    env = _np(sim.obs_env)
+    assert np.array_equal(env[:, 0:2].astype(np.float32), xy)            # spawn xy untouched by the settle step
+    assert np.abs(env[:, 3:7] - [0, 0, 0, 1]).max() < 1e-6
+    assert (sim.step_count.cpu().numpy() == 0).all() and (sim.episode.cpu().numpy() == 1).all()
+
+
+def test_masked_partial_reset_is_bit_exact_elsewhere(Sim, franka_model, oracle64):
+    n = 512
+    rng = np.random.default_rng(30)
+    sim_a, sim_b = Sim(franka_model, n, seed=123), Sim(franka_model, n, seed=123)
+    xy = np.stack([rng.uniform(0.45, 0.8, n), rng.uniform(-0.25, 0.25, n)], 1).astype(np.float32)
+    act = torch.as_tensor(f32(mdl.FRANKA_HOME + rng.uniform(-0.2, 0.2, (n, 9))), device="cuda")
+    mask = torch.as_tensor(rng.random(n) < 0.25, device="cuda")
+    for s in (sim_a, sim_b):
+        s.reset(None, xy)
+        s.step(act)
+    sim_a.step(act)                       # nobody resets
+    sim_b.step(act, reset_mask=mask)      # 25 % reset instead of stepping
+    qa_, qb_ = sim_a.get_state()[0], sim_b.get_state()[0]
+    keep = ~mask
+    assert torch.equal(qa_[keep], qb_[keep])                                  # untouched envs: bit-identical
+    assert torch.equal(sim_a.obs_env[keep], sim_b.obs_env[keep])
+    # reset envs: spawn xy from the Philox stream (seed, global env id, episode), bit-exact against the oracle
+    idx = torch.nonzero(mask).flatten().cpu().numpy()
+    env = sim_b.obs_env.cpu().numpy()
+    for e in idx[:64]:
+        ref = oracle64.spawn_xy(123, int(e), 1)
+        assert env[e, 0:2].tobytes() == ref.tobytes()
+    assert (sim_b.step_count.cpu().numpy()[idx] == 0).all() and (sim_b.episode.cpu().numpy()[idx] == 2).all()
+    assert (sim_b.step_count.cpu().numpy()[keep.cpu().numpy()] == 2).all()
+
+
+def test_flags_success_and_auto_reset(Sim, franka_model):
+    n = 64
+    sim = Sim(franka_model, n, auto_reset=True, time_limit=True)
+    sim.reset(None, np.tile(np.array([[0.6, 0.0]], np.float32), (n, 1)))
+    q, qd, qa = sim.get_state()
+    q[:16, 11] = 0.5                      # lift 16 cubes above the success height
+    sim.set_state(q, qd, qa)
+    home = torch.as_tensor(np.tile(f32(mdl.FRANKA_HOME), (n, 1)), device="cuda")
+    sim.step(home)
+    term = sim.terminated.cpu().numpy().astype(bool)
+    assert term[:16].all() and not term[16:].any()
+    assert (sim.reward.cpu().numpy() == term.astype(np.float32)).all()
+    sim.step(home)                        # finished envs reset on the next step (episode counter advances)
+    assert (sim.episode.cpu().numpy()[:16] == 2).all() and (sim.episode.cpu().numpy()[16:] == 1).all()
+    assert not sim.terminated.cpu().numpy()[:16].any()
+    st = sim.stats().cpu().numpy()
+    assert st[1] == 16 and st[2] == 16 and st[5] == 0
+    # time limit: truncated exactly at horizon
+    sim2 = Sim(franka_model, 4, time_limit=True)
+    sim2.reset(None, np.tile(np.array([[0.6, 0.0]], np.float32), (4, 1)))
+    h4 = home[:4].contiguous()
+    for k in range(200):
+        sim2.step(h4)
+        assert bool(sim2.truncated.all()) == (k == 199)
+
+
+def test_same_seed_determinism(Sim, franka_model):
+    """The one property the reference author probed (tester.py:11-28): same seed -> same observations (here: bit-identical)."""
+    n = 256
+    outs = []
+    for _ in range(2):
+        sim = Sim(franka_model, n, seed=42, reset_prob=0.02)
+        sim.reset(None, None)
+        g = torch.Generator(device="cpu").manual_seed(0)
+        for k in range(20):
+            act = torch.as_tensor(mdl.FRANKA_HOME, dtype=torch.float32) + 0.3 * (torch.rand((n, 9), generator=g) - 0.5)
+            sim.step(act)
+        outs.append((sim.obs_agent.clone(), sim.obs_env.clone(), sim.episode.clone()))
+    assert all(torch.equal(a, b) for a, b in zip(*outs))
+    assert outs[0][2].max() > 1           # random resets happened
+
+
+def test_full_size_invariants(Sim, franka_model):
+    """BASELINE config sizes (16384 envs, randomized poses, masked resets every step): size-independent properties."""
+    n = 16384
+    sim = Sim(franka_model, n, seed=1, reset_prob=1.0 / 200, auto_reset=True)
+    sim.reset(None, None)
+    g = torch.Generator(device="cuda").manual_seed(0)
+    home = torch.as_tensor(mdl.FRANKA_HOME, dtype=torch.float32, device="cuda")
+    for k in range(50):
+        act = home + 0.6 * (torch.rand((n, 9), generator=g, device="cuda") - 0.5)
+        act[:, 7:] = -0.02 + 0.06 * torch.rand((n, 2), generator=g, device="cuda")
+        sim.step(act)
+    q, qd, qa = sim.get_state()
+    assert torch.isfinite(q).all() and torch.isfinite(qd).all()
+    assert (q[:, 12:16].norm(dim=1) - 1).abs().max() < 1e-5               # unit cube quaternion
+    assert q[:, 11].min() > 0.0195 and q[:, 11].max() < 0.021             # cubes rest on the plane
+    lo = torch.as_tensor(franka_model.dof_table()["lim_lo"][:9], dtype=torch.float32, device="cuda") - 0.01
+    hi = torch.as_tensor(franka_model.dof_table()["lim_hi"][:9], dtype=torch.float32, device="cuda") + 0.01
+    assert ((q[:, :9] > lo) & (q[:, :9] < hi)).all()                      # soft joint limits hold
+    env = sim.obs_env
+    assert torch.allclose(env[:, 10], env[:, 7:10].norm(dim=1), atol=1e-6)
+    st = sim.stats().cpu().numpy()
+    assert st[5] == 0 and st[0] > 0.98 * n * 50 * (1 - 1 / 200.0)
+
+
+def test_gym_surface_end_to_end():
+    import gym_genesis  # noqa: F401
+    from gym_genesis_b200.gym_api import gym
+    env = gym.make("gym_genesis/CubePick-v0", robot="franka", num_envs=8)
+    obs, info = env.reset(seed=3)
+    assert info == {"is_success": [False] * 8}
+    assert obs["agent_pos"].shape == (8, 9) and obs["environment_state"].shape == (8, 11)
+    assert obs["agent_pos"].dtype == torch.float32 and obs["agent_pos"].is_cuda
+    r = np.random.RandomState(3)
+    x = r.uniform(0.45, 0.80, size=(8,)); y = r.uniform(-0.25, 0.25, size=(8,))
+    assert np.array_equal(obs["environment_state"][:, :2].cpu().numpy(), np.stack([x, y], 1).astype(np.float32))
+    base = env.unwrapped
+    act = np.tile(f32(mdl.FRANKA_HOME), (8, 1))
+    obs, reward, terminated, truncated, info = base.step(act)
+    assert reward.shape == (8,) and reward.dtype == torch.float32 and terminated.dtype == torch.bool
+    assert not bool(terminated.any()) and not bool(truncated.any()) and info["is_success"].shape == (8,)
+    base.push()
+    assert base.get_robot().get_dofs_position().shape == (8, 9) and base.get_cube().get_pos().shape == (8, 3)
+    with pytest.raises(ValueError):
+        base.step(np.zeros((8, 7), np.float32))
+    with pytest.raises(NotImplementedError):
+        gym.make("gym_genesis/CubePick-v0", robot="franka", num_envs=2, enable_pixels=True)
+    env.close()
