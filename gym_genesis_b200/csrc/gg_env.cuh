@@ -10,6 +10,16 @@
 #include "gg_b200.h"
 #include "gg_math.cuh"
 
+// The per-link loops of the arm chain stay ROLLED on the device (per-link temporaries then live in local
+// memory): with ~1 warp per scheduler the kernel is instruction-fetch bound (ncu: stall_no_inst 67 % when fully
+// unrolled), so a loop body that is fetched once and re-used from the instruction cache beats straight-line
+// code (measured: 71.5 -> 48.9 us per step at 16384 envs, profiles/r01_notes.md).  -DGG_UNROLL_LINKS restores it.
+#if !defined(GG_UNROLL_LINKS) && defined(__CUDA_ARCH__)
+#define GG_LINK_LOOP _Pragma("unroll 1")
+#else
+#define GG_LINK_LOOP _Pragma("unroll")
+#endif
+
 namespace gg {
 
 template <int NU> struct EnvState {
@@ -43,7 +53,7 @@ GG_HD void robot_dynamics(const GgModel& M, const float* q, const float* qd, con
     M3 Rl = qmat(ql);
     SV V; V.a = mk(0.f, 0.f, 0.f); V.l = mk(0.f, 0.f, 0.f);
     SV A; A.a = mk(0.f, 0.f, 0.f); A.l = mk(0.f, 0.f, M.gravity);   // gravity as base acceleration
-#pragma unroll
+    GG_LINK_LOOP
     for (int l = 0; l < NA; l++) {
         pl = pl + mul(Rl, ld3(M.link_pos[l]));
         float s, c;
@@ -92,11 +102,11 @@ GG_HD void robot_dynamics(const GgModel& M, const float* q, const float* qd, con
         bias[NA + f] = sdot(Sf, Ff);
         Ic = Ic + If; Fc = Fc + Ff;
     }
-#pragma unroll
+    GG_LINK_LOOP
     for (int l = NA - 1; l >= 0; l--) {
         Ic = Ic + I[l]; Fc = Fc + F[l];
         SV G = apply(Ic, S[l]);
-#pragma unroll
+        GG_LINK_LOOP
         for (int i = 0; i <= l; i++) D.Mt[GG_TRI(l, i)] = sdot(S[i], G);
         bias[l] = sdot(S[l], Fc);
     }
@@ -116,7 +126,7 @@ GG_HD void robot_eef(const GgModel& M, const float* q, V3& ep, Q4& eq) {
     Q4 ql = ldq(M.base_quat);
     V3 pl = ld3(M.base_pos);
     M3 Rl = qmat(ql);
-#pragma unroll
+    GG_LINK_LOOP
     for (int l = 0; l < NA; l++) {
         pl = pl + mul(Rl, ld3(M.link_pos[l]));
         float s, c;

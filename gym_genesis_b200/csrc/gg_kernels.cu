@@ -6,6 +6,7 @@
 // ONE kernel launch; nothing is written back to HBM between those stages.
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <atomic>
@@ -82,12 +83,13 @@ template <int NU> __device__ __forceinline__ bool state_finite(const gg::EnvStat
     return isfinite(acc);
 }
 
-constexpr int kBlock = 128;
+constexpr int kBlock = 128;      // default threads per block
+constexpr int kMaxBlock = 1024;
 
 template <int NA, int NF, bool FH>
-__global__ void __launch_bounds__(kBlock) step_kernel(const __grid_constant__ StepArgs A) {
+__global__ void __launch_bounds__(256) step_kernel(const __grid_constant__ StepArgs A) {
     constexpr int NU = NA + NF;
-    const int e = blockIdx.x * kBlock + threadIdx.x;
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
     const bool live = e < A.n;
     float st_steps = 0.f, st_done = 0.f, st_succ = 0.f, st_ret = 0.f, st_len = 0.f, st_nan = 0.f, st_iter = 0.f, st_con = 0.f;
     if (live) {
@@ -155,7 +157,7 @@ __global__ void __launch_bounds__(kBlock) step_kernel(const __grid_constant__ St
     }
     if (A.stats != nullptr && A.mode == 0) {
         float v[8] = {st_steps, st_done, st_succ, st_ret, st_len, st_nan, st_iter, st_con};
-        __shared__ float red[8][kBlock / 32];
+        __shared__ float red[8][kMaxBlock / 32];
 #pragma unroll
         for (int k = 0; k < 8; k++) {
             float x = v[k];
@@ -167,7 +169,7 @@ __global__ void __launch_bounds__(kBlock) step_kernel(const __grid_constant__ St
         if (threadIdx.x < 8) {
             float x = 0.f;
 #pragma unroll
-            for (int w = 0; w < kBlock / 32; w++) x += red[threadIdx.x][w];
+            for (int w = 0; w < (int)(blockDim.x >> 5); w++) x += red[threadIdx.x][w];
             if (x != 0.f) atomicAdd(&A.stats[threadIdx.x], (double)x);
         }
     }
@@ -237,6 +239,7 @@ struct GgSim {
     GgModel model;
     GgConfig cfg;
     int n, device, stride, kind;        // kind: 0 = <7,2,slide>, 1 = <5,1,hinge>
+    int block;                          // threads per block of step_kernel
     float* state; int32_t* step_count; int32_t* episode;
     uint8_t* done; double* stats;       // library-owned (allocated once in gg_create)
     uint32_t step_index;
@@ -250,10 +253,10 @@ static int launch_step(GgSim* sim, StepArgs& A, gg_stream_t stream) {
     A.auto_reset = sim->cfg.auto_reset; A.time_limit = sim->cfg.time_limit; A.reset_prob = sim->cfg.reset_prob;
     A.seed = sim->cfg.seed; A.first_env = sim->cfg.first_env_id; A.step_index = sim->step_index;
     A.stats = sim->stats;
-    const int grid = (sim->n + kBlock - 1) / kBlock;
+    const int grid = (sim->n + sim->block - 1) / sim->block;
     GG_CUDA(cudaSetDevice(sim->device));
-    if (sim->kind == 0) step_kernel<7, 2, false><<<grid, kBlock, 0, (cudaStream_t)stream>>>(A);
-    else step_kernel<5, 1, true><<<grid, kBlock, 0, (cudaStream_t)stream>>>(A);
+    if (sim->kind == 0) step_kernel<7, 2, false><<<grid, sim->block, 0, (cudaStream_t)stream>>>(A);
+    else step_kernel<5, 1, true><<<grid, sim->block, 0, (cudaStream_t)stream>>>(A);
     g_launches.fetch_add(1);
     GG_CUDA(cudaGetLastError());
     return 0;
@@ -283,6 +286,8 @@ int gg_create(const GgModel* model, int n_envs, int device, GgSim** out) {
     memset(s, 0, sizeof(*s));
     s->model = *model; s->n = n_envs; s->device = device; s->kind = kind;
     s->stride = (n_envs + 31) / 32 * 32;
+    s->block = kBlock;
+    if (const char* eb = getenv("GG_BLOCK")) { int b = atoi(eb); if (b >= 32 && b <= 256 && b % 32 == 0) s->block = b; }
     s->cfg.solver_iterations = 10; s->cfg.solver_tolerance = 1e-5f;
     cudaError_t e1 = cudaMalloc(&s->done, (size_t)s->stride);
     cudaError_t e2 = cudaMalloc(&s->stats, 8 * sizeof(double));
