@@ -182,6 +182,7 @@ def run_gpu(args):
         dist.init_process_group("nccl", device_id=dev)
         dist.barrier()
     from gym_genesis_b200.model import franka_cube_pick_model
+    from gym_genesis_b200.shard import gather_stats
     from gym_genesis_b200.sim import BatchedSim
 
     n = args.envs
@@ -215,7 +216,7 @@ def run_gpu(args):
         sim.step(pool[k % ACTION_POOL])
         ev[k][1].record()
         if stats_all is not None and (k + 1) % 100 == 0:    # the only collective: episode statistics, off the step path
-            dist.all_gather_into_tensor(stats_all, sim.stats().unsqueeze(0))
+            stats_all = gather_stats(sim.stats())
     barrier()
     wall = time.perf_counter() - wall0
     launches = BatchedSim.launch_count() - launches0 - (args.steps // 100 if stats_all is not None else 0)

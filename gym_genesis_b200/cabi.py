@@ -71,17 +71,19 @@ def compile_gg(sm: "mdl.SceneModel") -> GgModel:
 
     def rel_transform(child, ancestor):
         """(R, p) of body `child`'s frame (joint at q=0) expressed in body `ancestor`'s frame; ancestor=-1 -> world."""
-        R, p = np.eye(3), np.zeros(3)
+        R, p, qq = np.eye(3), np.zeros(3), np.array([1.0, 0.0, 0.0, 0.0])
         i = child
         while i != ancestor:
             b = B[i]
             Rb = mdl.quat_to_mat(b.quat)
             p = np.asarray(b.pos, dtype=np.float64) + Rb @ p
             R = Rb @ R
+            qq = mdl.quat_mul(mdl.quat_normalize(b.quat), qq)     # quaternion chain keeps the MJCF sign convention
             i = b.parent
             assert i >= -1
             if i != ancestor and i >= 0:
                 assert B[i].jtype == mdl.FIXED, "only fixed bodies may sit between chain links"
+        rel_transform.quat = qq
         return R, p
 
     def owner(i):
@@ -100,7 +102,7 @@ def compile_gg(sm: "mdl.SceneModel") -> GgModel:
     for l, i in enumerate(arm):
         assert np.allclose(B[i].axis, (0, 0, 1)), "arm hinges must rotate about their local z axis"
         R, p = rel_transform(i, prev)
-        _set(g.link_pos[l], p); _set(g.link_quat[l], mdl.mat_to_quat(R))
+        _set(g.link_pos[l], p); _set(g.link_quat[l], rel_transform.quat)
         prev = i
     # merge fixed descendants into their owning arm link / finger
     def merged_inertia(root):
@@ -124,17 +126,18 @@ def compile_gg(sm: "mdl.SceneModel") -> GgModel:
     for f, i in enumerate(fing):
         assert owner(B[i].parent) == last, "gripper dofs must hang off the last arm link"
         R, p = rel_transform(i, last)
-        _set(g.fing_pos[f], p); _set(g.fing_quat[f], mdl.mat_to_quat(R)); _set(g.fing_axis[f], B[i].axis)
+        _set(g.fing_pos[f], p); _set(g.fing_quat[f], rel_transform.quat); _set(g.fing_axis[f], B[i].axis)
         if B[i].jtype == mdl.HINGE:
             assert np.allclose(B[i].axis, (0, 0, 1))
         m, c, I6 = merged_inertia(i)
         g.fing_mass[f] = m; _set(g.fing_com[f], c); _set(g.fing_inertia[f], I6)
     if sm.eef_body == last:
-        Re, pe = np.eye(3), np.zeros(3)
+        pe, qe = np.zeros(3), np.array([1.0, 0.0, 0.0, 0.0])
     else:
         assert owner(sm.eef_body) == last
-        Re, pe = rel_transform(sm.eef_body, last)
-    _set(g.eef_pos, pe); _set(g.eef_quat, mdl.mat_to_quat(Re))
+        _, pe = rel_transform(sm.eef_body, last)
+        qe = rel_transform.quat
+    _set(g.eef_pos, pe); _set(g.eef_quat, qe)
     dt = sm.dof_table()
     body_w, dof_w = sm.invweight0()
     for name in ("armature", "damping", "kp", "kv", "frc_lo", "frc_hi", "lim_lo", "lim_hi"):

@@ -42,3 +42,17 @@ def hostsim():
     d = os.path.join(ROOT, "tests", "hostsim")
     subprocess.check_call(["make", "-s", "-C", d])
     return C.CDLL(os.path.join(d, "libgg_hostsim.so"))
+
+
+@pytest.fixture(scope="session")
+def so101_model():
+    from gym_genesis_b200.model_so101 import ISLAND_TOP_Z, so101_cube_pick_model
+    return so101_cube_pick_model(success_height=ISLAND_TOP_Z + 0.1)
+
+
+@pytest.fixture(scope="session")
+def so101_oracle64(so101_model):
+    import numpy as np
+    from oracle.binding import Oracle, build
+    build()
+    return Oracle(so101_model, np.float64)

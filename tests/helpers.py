@@ -82,30 +82,33 @@ def random_states(m, rng, n, cube_on_ground=True):
     Q = np.zeros((n, nu + 7))
     QD = np.zeros((n, nu + 6))
     Q[:, :nu] = m.home_q + rng.uniform(-0.3, 0.3, (n, nu))
-    Q[:, m.n_arm:nu] = rng.uniform(0.0, 0.04, (n, m.n_fing))
-    Q[:, nu] = rng.uniform(0.45, 0.8, n)
-    Q[:, nu + 1] = rng.uniform(-0.25, 0.25, n)
+    fing_hi = 0.04 if m.name == "franka" else 1.0
+    Q[:, m.n_arm:nu] = rng.uniform(0.0, fing_hi, (n, m.n_fing))
+    Q[:, nu] = rng.uniform(m.spawn_lo[0], m.spawn_hi[0], n)
+    Q[:, nu + 1] = rng.uniform(m.spawn_lo[1], m.spawn_hi[1], n)
     if cube_on_ground:
-        Q[:, nu + 2] = 0.02 - rng.uniform(0, 2e-4, n)
+        Q[:, nu + 2] = m.plane_z + 0.02 - rng.uniform(0, 2e-4, n)
         yaw = rng.uniform(-np.pi, np.pi, n)
         Q[:, nu + 3] = np.cos(yaw / 2)
         Q[:, nu + 6] = np.sin(yaw / 2)
         QD[:, nu:nu + 2] = rng.normal(0, 0.05, (n, 2))
     else:
-        Q[:, nu + 2] = rng.uniform(0.1, 0.4, n)
+        Q[:, nu + 2] = m.plane_z + rng.uniform(0.1, 0.4, n)
         qq = rng.normal(size=(n, 4))
         Q[:, nu + 3:nu + 7] = qq / np.linalg.norm(qq, axis=1, keepdims=True)
         QD[:, nu:] = rng.normal(0, 0.5, (n, 6))
     QD[:, :nu] = rng.normal(0, 0.5, (n, nu))
     T = m.home_q + rng.uniform(-0.3, 0.3, (n, nu))
-    T[:, m.n_arm:] = rng.uniform(-0.02, 0.04, (n, m.n_fing))
+    T[:, m.n_arm:] = rng.uniform(-0.02, fing_hi, (n, m.n_fing))
     return f32(Q).astype(np.float64), f32(QD).astype(np.float64), f32(T).astype(np.float64)
 
 
 def substep_errors(q0, qd0, q_ref, qd_ref, q, qd, a_smooth_scale):
-    """(|q err|_inf, velocity-delta error normalised by TOL: <= 1 passes)."""
+    """(position error, velocity-delta error normalised by its bound: <= 1 passes).
+    The position error is rescaled so that TOL_Q_ABS stays the threshold: positions integrate the new velocity over
+    dt = 0.01 s, so their bound is TOL_Q_ABS + dt * (velocity bound)."""
     eq = np.abs(q - q_ref).max(axis=1)
     d_ref = np.abs(qd_ref - qd0).max(axis=1)
     ev = np.abs(qd - qd_ref).max(axis=1)
     bound = TOL_DQD_REL * np.maximum(d_ref, a_smooth_scale) + TOL_DQD_FLOOR
-    return eq, ev / bound
+    return eq * TOL_Q_ABS / (TOL_Q_ABS + 0.01 * bound), ev / bound

@@ -220,3 +220,38 @@ def test_gym_surface_end_to_end():
     with pytest.raises(NotImplementedError):
         gym.make("gym_genesis/CubePick-v0", robot="franka", num_envs=2, enable_pixels=True)
     env.close()
+
+
+def test_so101_substep_and_full_size(Sim, so101_model, so101_oracle64):
+    """BASELINE config 4: SO-101 articulation (6 hinge dofs), 16384 envs."""
+    m, o = so101_model, so101_oracle64
+    rng = np.random.default_rng(40)
+    n = 256
+    Q, QD, T = random_states(m, rng, n, cube_on_ground=True)
+    QA = np.zeros_like(QD)
+    sim = Sim(m, n)
+    assert sim.agent_dim == 8 and sim.nu == 6
+    q, qd, qa = _one_substep(sim, Q, QD, QA, T)
+    qo, qdo, qao = Q.copy(), QD.copy(), QA.copy()
+    o.step(qo, qdo, qao, T, iterations=100, tol=1e-12)
+    sc = np.array([np.abs(o.dynamics(Q[k], QD[k], T[k])["a_smooth"]).max() * 0.01 for k in range(n)])
+    eq, ev = substep_errors(Q, QD, qo, qdo, q, qd, sc)
+    assert eq.max() < TOL_Q_ABS and ev.max() < 1.0, (eq.max(), ev.max())
+    a, e, r, t = o.obs(q)
+    assert np.abs(_np(sim.obs_agent) - a).max() < 2e-6 and (sim.terminated.cpu().numpy().astype(bool) == t).all()
+    # full size: reset (no settle step for the SO-101 pick task, so101/cube_pick.py:81) then 50 steps with masked resets
+    n = 16384
+    sim = Sim(m, n, seed=2, reset_prob=1.0 / 200, auto_reset=True)
+    sim.reset(None, None)
+    env0 = sim.obs_env.clone()
+    assert (env0[:, 0] >= -0.32).all() and (env0[:, 0] <= -0.28).all() and (env0[:, 1].abs() <= 0.05).all()
+    assert torch.allclose(env0[:, 3:7], torch.tensor([1.0, 0, 0, 0], device="cuda").expand(n, 4))
+    g = torch.Generator(device="cuda").manual_seed(0)
+    home = torch.as_tensor(m.home_q, dtype=torch.float32, device="cuda")
+    for k in range(50):
+        sim.step(home + 0.2 * (torch.rand((n, 6), generator=g, device="cuda") - 0.5))
+    q, qd, _ = sim.get_state()
+    assert torch.isfinite(q).all() and torch.isfinite(qd).all()
+    assert (q[:, 9:13].norm(dim=1) - 1).abs().max() < 1e-5
+    assert (q[:, 8] - (m.plane_z + 0.02)).abs().max() < 2e-3            # cubes dropped 1 mm, now resting on the island plane
+    assert sim.stats().cpu().numpy()[5] == 0

@@ -87,3 +87,46 @@ def test_spawn_draw_bit_exact(hostsim, gg, oracle64):
         ref = oracle64.spawn_xy(seed, gid, epi)
         assert xy.tobytes() == ref.tobytes()
         assert 0.45 <= xy[0] <= 0.80 and -0.25 <= xy[1] <= 0.25
+
+
+def test_so101_substep_random_states(hostsim, so101_model, so101_oracle64):
+    """Second articulation (5 hinges + hinge jaw, scaled, yawed base, plane at the island top, mu = 5)."""
+    gg101 = cabi.compile_gg(so101_model)
+    assert (gg101.n_arm, gg101.n_fing, gg101.fing_hinge, gg101.n_pads) == (5, 1, 1, 2)
+    rng = np.random.default_rng(8)
+    for on_ground in (True, False):
+        Q, QD, T = random_states(so101_model, rng, 48, cube_on_ground=on_ground)
+        QA = np.zeros_like(QD)
+        qo, qdo, qao = Q.copy(), QD.copy(), QA.copy()
+        info, _ = so101_oracle64.step(qo, qdo, qao, T, iterations=100, tol=1e-12)
+        q, qd, qa, hinfo, _ = hostsim_step(hostsim, gg101, Q, QD, QA, T)
+        assert (hinfo[:, 0] == info[:, 0]).all()
+        sc = np.array([np.abs(so101_oracle64.dynamics(Q[k], QD[k], T[k])["a_smooth"]).max() * 0.01 for k in range(Q.shape[0])])
+        eq, ev = substep_errors(Q, QD, qo, qdo, q, qd, sc)
+        assert eq.max() < TOL_Q_ABS and ev.max() < 1.0, (on_ground, eq.max(), ev.max())
+
+
+def test_so101_jaw_contacts_and_observation(hostsim, so101_model, so101_oracle64):
+    """Drive the cube between the jaws so that the box-box manifolds of the jaw boxes are exercised."""
+    m, o = so101_model, so101_oracle64
+    gg101 = cabi.compile_gg(m)
+    q0 = m.full_q(m.home_q)
+    xp, xm = m.fk(q0)
+    # put the cube where the fixed-jaw box is (guaranteed overlap) and a little above the plane
+    g = m.geoms[0]
+    c = xp[g.body] + xm[g.body] @ np.asarray(g.pos)
+    Q = np.tile(q0, (4, 1))
+    Q[:, 6:9] = c + np.array([[0.0, 0, 0], [0.01, 0, 0], [0, 0.01, 0.005], [0.0, -0.01, 0.01]])
+    Q = f32(Q).astype(np.float64)
+    QD = np.zeros((4, 12)); QA = np.zeros((4, 12)); T = np.tile(m.home_q, (4, 1))
+    qo, qdo, qao = Q.copy(), QD.copy(), QA.copy()
+    info, _ = o.step(qo, qdo, qao, T, iterations=200, tol=1e-12)
+    assert info[:, 0].min() >= 1
+    q, qd, qa, hinfo, _ = hostsim_step(hostsim, gg101, Q, QD, QA, T, iters=50)
+    assert (hinfo[:, 0] == info[:, 0]).all()
+    assert np.abs(q - qo).max() < 1e-4 and np.abs(qd - qdo).max() < 2e-2 * max(1.0, np.abs(qdo).max())
+    a, e, r, t = o.obs(qo)
+    agent, envs = np.zeros((4, 8), np.float32), np.zeros((4, 11), np.float32)
+    rew, term = np.zeros(4, np.float32), np.zeros(4, np.uint8)
+    hostsim.hs_observe(C.byref(gg101), 4, _p(f32(qo)), _p(agent), _p(envs), _p(rew), _p(term))
+    assert np.abs(agent - a).max() < 2e-6 and np.abs(envs - e).max() < 2e-6 and (term.astype(bool) == t).all()

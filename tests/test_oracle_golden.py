@@ -149,3 +149,35 @@ def test_newton_reaches_kkt(franka_model, oracle64):
         f = -D * np.minimum(jar, 0)
         g = d["Mt"] @ (a - d["a_smooth"]) - J.T @ f
         assert np.abs(g).max() < 1e-7 * max(1.0, np.abs(d["Mt"] @ d["a_smooth"]).max())
+
+
+def test_so101_fk_known_answers():
+    """SO-101 tree against vectors computed from the reference's own MJCF (tests/golden/make_so101_fk.py)."""
+    from gym_genesis_b200.model import BoxGeom, SceneModel, _cube_body, mat_to_quat
+    from gym_genesis_b200.model_so101 import SO101_STACK_HOME, so101_bodies
+    from oracle.binding import Oracle
+    b = so101_bodies()
+    b.append(_cube_body())
+    sm = SceneModel("so101raw", b, [BoxGeom(7, (0.02,) * 3, group=1)], eef_body=5, cube_body=7, home_q=np.zeros(6), n_arm=5, n_fing=1)
+    orc = Oracle(sm, np.float64)
+    assert abs(sum(x.mass for x in b[:7]) - GOLD["so101_zero"]["total_mass"]) < 1e-6
+    for key, q in (("so101_zero", np.zeros(6)), ("so101_stack_home", SO101_STACK_HOME)):
+        g = GOLD[key]
+        xp, xq = orc.fk(sm.full_q(q))
+        assert np.allclose(xp[5], g["gripper_pos"], atol=2e-6)
+        ref = np.array(g["gripper_quat"])
+        assert min(np.abs(xq[5] - ref).max(), np.abs(xq[5] + ref).max()) < 2e-6
+        if "jaw_pos" in g:
+            assert np.allclose(xp[6], g["jaw_pos"], atol=2e-6)
+        xpn, xmn = sm.fk(sm.full_q(q))
+        assert np.allclose(xpn, xp, atol=1e-6)
+
+
+def test_so101_oracle_matches_numpy_mass_matrix(so101_model, so101_oracle64):
+    rng = np.random.default_rng(5)
+    m = so101_model
+    for _ in range(3):
+        q = m.full_q(m.home_q + rng.uniform(-0.3, 0.3, 6), np.array([-0.3, 0.0, 0.9, 1.0, 0, 0, 0]))
+        M = so101_oracle64.dynamics(q, np.zeros(12), m.home_q)["M"]
+        Mn = m.mass_matrix(q)
+        assert np.abs(M - Mn).max() < 1e-6 * max(1.0, np.abs(Mn).max()) and np.linalg.eigvalsh(M).min() > 0
