@@ -20,6 +20,13 @@
 #define GG_LINK_LOOP _Pragma("unroll")
 #endif
 
+// Same for the per-contact loops of the cube-plane solver (42.9 vs 48.9 us cold at 16384 envs).
+#if !defined(GG_UNROLL_CONTACTS) && defined(__CUDA_ARCH__)
+#define GG_CON_LOOP _Pragma("unroll 1")
+#else
+#define GG_CON_LOOP _Pragma("unroll")
+#endif
+
 namespace gg {
 
 template <int NU> struct EnvState {
@@ -466,7 +473,7 @@ GG_HD void solve_cube_plane(const GgModel& M, const float* Mc, const float* as, 
     float costw = 0.f, costs = 0.f;
 #pragma unroll
     for (int i = 0; i < 6; i++) { float ew = warm[i] - as[i]; costw += 0.5f * Mc[i] * ew * ew; }
-#pragma unroll
+    GG_CON_LOOP
     for (int c = 0; c < 4; c++) {
         // plane normal +z: n = z, t1 = x, t2 = y (= tangent_basis(z)); rows act on [v, w_body]
         V3 r = p[c] - cp;
@@ -497,7 +504,7 @@ GG_HD void solve_cube_plane(const GgModel& M, const float* Mc, const float* as, 
     const bool usew = costw < costs;
 #pragma unroll
     for (int i = 0; i < 6; i++) a[i] = usew ? warm[i] : as[i];
-#pragma unroll
+    GG_CON_LOOP
     for (int c = 0; c < 4; c++)
 #pragma unroll
         for (int k = 0; k < 3; k++) u[c][k] = usew ? u[c][k] : w[c][k];
@@ -508,7 +515,7 @@ GG_HD void solve_cube_plane(const GgModel& M, const float* Mc, const float* as, 
         for (int i = 0; i < 21; i++) H[i] = 0.f;
 #pragma unroll
         for (int i = 0; i < 6; i++) { H[GG_TRI(i, i)] = Mc[i]; g[i] = Mc[i] * (a[i] - as[i]); }
-#pragma unroll
+        GG_CON_LOOP
         for (int c = 0; c < 4; c++) {
             float Wnn = 0.f, Wn1 = 0.f, W11 = 0.f, Wn2 = 0.f, W22 = 0.f, gn = 0.f, g1 = 0.f, g2 = 0.f;
 #pragma unroll
@@ -542,14 +549,14 @@ GG_HD void solve_cube_plane(const GgModel& M, const float* Mc, const float* as, 
         float q1 = 0.f, q2 = 0.f;
 #pragma unroll
         for (int i = 0; i < 6; i++) { q1 += Mc[i] * sd[i] * (a[i] - as[i]); q2 += Mc[i] * sd[i] * sd[i]; }
-#pragma unroll
+        GG_CON_LOOP
         for (int c = 0; c < 4; c++)
 #pragma unroll
             for (int k = 0; k < 3; k++) w[c][k] = dotn<6>(J[c][k], sd);
         LineSearch L; L.begin();
         for (;;) {
             float d1 = q1 + L.al * q2, d2 = q2;
-#pragma unroll
+            GG_CON_LOOP
             for (int c = 0; c < 4; c++)
 #pragma unroll
                 for (int k = 0; k < 4; k++) {
@@ -560,7 +567,7 @@ GG_HD void solve_cube_plane(const GgModel& M, const float* Mc, const float* as, 
             if (!L.next(d1, d2)) break;
         }
         int changed = 0;
-#pragma unroll
+        GG_CON_LOOP
         for (int c = 0; c < 4; c++) {
             float un[3] = {u[c][0] + L.al * w[c][0], u[c][1] + L.al * w[c][1], u[c][2] + L.al * w[c][2]};
 #pragma unroll

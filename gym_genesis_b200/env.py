@@ -52,9 +52,9 @@ class GenesisEnv(gym.Env):
     def step(self, action, reset_mask=None):
         _, reward, _, observation = self._env.step(action, reset_mask)
         sim = self._env.sim
-        is_success = sim.terminated.bool()          # == (reward == 1), computed in-kernel with the strict z > 0.1f test
+        is_success = sim.terminated                 # == (reward == 1), computed in-kernel with the strict z > 0.1f test
         terminated = is_success
-        truncated = sim.truncated.bool()            # all False unless time_limit=True was requested
+        truncated = sim.truncated                   # all False unless time_limit=True was requested
         if self.numpy_flags:
             terminated = terminated.cpu().numpy().astype(bool)
             truncated = truncated.cpu().numpy().astype(bool)

@@ -60,8 +60,9 @@ class BatchedSim:
         self.obs_agent = torch.zeros((self.n_envs, self.agent_dim), dtype=torch.float32, device=dev)
         self.obs_env = torch.zeros((self.n_envs, 11), dtype=torch.float32, device=dev)
         self.reward = torch.zeros(self.n_envs, dtype=torch.float32, device=dev)
-        self.terminated = torch.zeros(self.n_envs, dtype=torch.uint8, device=dev)
-        self.truncated = torch.zeros(self.n_envs, dtype=torch.uint8, device=dev)
+        # torch.bool is one byte holding 0/1: the kernel writes the flags in place, no conversion kernels on the step path
+        self.terminated = torch.zeros(self.n_envs, dtype=torch.bool, device=dev)
+        self.truncated = torch.zeros(self.n_envs, dtype=torch.bool, device=dev)
         self._stats = torch.zeros(8, dtype=torch.float64, device=dev)
         self.cfg = cabi.GgConfig(solver_iterations, solver_tolerance, int(auto_reset), int(time_limit), float(reset_prob),
                                  int(seed) & (2 ** 64 - 1), int(first_env_id))

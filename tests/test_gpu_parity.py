@@ -211,7 +211,7 @@ def test_gym_surface_end_to_end():
     base = env.unwrapped
     act = np.tile(f32(mdl.FRANKA_HOME), (8, 1))
     obs, reward, terminated, truncated, info = base.step(act)
-    assert reward.shape == (8,) and reward.dtype == torch.float32 and terminated.dtype == torch.bool
+    assert reward.shape == (8,) and reward.dtype == torch.float32 and terminated.dtype == torch.bool and truncated.dtype == torch.bool
     assert not bool(terminated.any()) and not bool(truncated.any()) and info["is_success"].shape == (8,)
     base.push()
     assert base.get_robot().get_dofs_position().shape == (8, 9) and base.get_cube().get_pos().shape == (8, 3)
