@@ -257,6 +257,30 @@ def run_gpu(args):
     barrier()
     e2e_ms = a0.elapsed_time(a1)
 
+    # ---- workload B: contact-rich scripted grasp, recorded expert joint targets replayed open-loop ----
+    wb = None
+    gpath = os.path.join(ROOT, "tests", "golden", "grasp_traj.npz")
+    if os.path.exists(gpath) and not args.no_workload_b:
+        d = np.load(gpath)
+        K = d["xy"].shape[0]
+        rep = n // K
+        simb = BatchedSim(m, K * rep, device=dev)
+        acts = torch.as_tensor(np.tile(d["actions"], (rep, 1, 1)), device=dev).transpose(0, 1).contiguous()     # (200, n, 9)
+        xyb = np.tile(d["xy"], (rep, 1))
+        for w in range(2):                                                                                        # episode 0 = warm-up
+            simb.reset(None, xyb)
+            evb = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(200)]
+            for t in range(200):
+                flush.fill_(t & 0xFF)
+                evb[t][0].record(); simb.step(acts[t]); evb[t][1].record()
+            torch.cuda.synchronize(dev)
+        tb = np.array([a.elapsed_time(b) for a, b in evb])
+        stb = simb.stats().cpu().numpy()
+        wb = {"workload": "scripted grasp (hover/stabilize/grasp/grasp/lift x 40 steps), %d recorded expert rollouts tiled over %d envs" % (K, K * rep),
+              "value": K * rep * 200 / (tb.sum() * 1e-3), "unit": "env-steps/s", "ms_per_step_by_stage": [float(tb[i * 40:(i + 1) * 40].mean()) for i in range(5)],
+              "mean_contacts": stb[7] / max(stb[0], 1), "success_rate": float(simb.terminated.float().mean().item()), "nonfinite_resets": stb[5]}
+        simb.close()
+
     times = torch.tensor([t_ms, warm_ms, e2e_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
@@ -277,7 +301,7 @@ def run_gpu(args):
                        "d2h_bytes_per_step": n * 4 + n, "steps": e2e_steps, "api": "gym.make('gym_genesis/CubePick-v0').unwrapped.step(pinned host action)"},
                "gpu_launches": int(launches), "clocks": clocks,
                "l2_warm": {"value": n * world * args.steps / (warm_ms * 1e-3), "unit": "env-steps/s", "note": "back-to-back launches, no L2 flush"},
-               "wall_s_timed_loop": wall,
+               "wall_s_timed_loop": wall, "workload_b": wb,
                "episode_stats": {"env_steps": st[0], "episodes": st[1], "successes": st[2], "nonfinite_resets": st[5],
                                  "mean_solver_iters": st[6] / max(st[0], 1), "mean_contacts": st[7] / max(st[0], 1)}}
         if not args.no_cpu_baseline and world == 1:
@@ -302,6 +326,7 @@ def main():
     ap.add_argument("--envs", type=int, default=N_ENVS_PER_GPU, help="envs per GPU")
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-workload-b", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -264,3 +264,34 @@ def test_so101_substep_and_full_size(Sim, so101_model, so101_oracle64):
     assert ((z[settled] - (m.plane_z + 0.02 - depth)).abs() < 0.1 * depth).float().mean() > 0.99
     assert z.min() > m.plane_z - 0.001 and z.max() < m.plane_z + 0.022
     assert sim.stats().cpu().numpy()[5] == 0
+
+
+def test_scripted_grasp_rollout_open_loop(Sim, franka_model):
+    """Same as the CPU-tier test, on the GPU at scale: 32 recorded expert rollouts tiled over 4096 envs."""
+    import os
+    d = np.load(os.path.join(os.path.dirname(__file__), "golden", "grasp_traj.npz"))
+    K, rep = d["xy"].shape[0], 128
+    n = K * rep
+    sim = Sim(franka_model, n)
+    sim.reset(None, np.tile(d["xy"], (rep, 1)))
+    acts = torch.as_tensor(np.tile(d["actions"], (rep, 1, 1)), device="cuda")
+    succ = torch.zeros(n, dtype=torch.bool, device="cuda")
+    for t in range(200):
+        sim.step(acts[:, t].contiguous())
+        succ |= sim.terminated
+        if t in (79, 99, 199):
+            q = sim.get_state()[0].cpu().numpy()
+            er = np.abs(q[:, :9] - np.tile(d["qrob"][:, t], (rep, 1))).max(1)
+            ec = np.abs(q[:, 9:12] - np.tile(d["cube"][:, t], (rep, 1))).max(1)
+            if t == 79:
+                assert er.max() < 5e-6 and ec.max() < 1e-6, (er.max(), ec.max())
+            if t == 99:
+                assert er.max() < ROLLOUT_POS_TOL and ec.max() < ROLLOUT_POS_TOL and np.median(ec) < 1e-5, (er.max(), ec.max())
+            if t == 199:
+                assert (ec < 5e-3).mean() >= 0.9
+    ref = np.tile(d["reward"].max(1) > 0, rep)
+    s = succ.cpu().numpy()
+    assert (s == ref).mean() >= 0.9
+    assert (s.reshape(rep, K) == s[:K]).all()           # identical inputs in different warps give identical results
+    st = sim.stats().cpu().numpy()
+    assert st[5] == 0 and st[7] / st[0] > 10            # no non-finite envs; contact-rich on average

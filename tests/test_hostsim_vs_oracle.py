@@ -130,3 +130,32 @@ def test_so101_jaw_contacts_and_observation(hostsim, so101_model, so101_oracle64
     rew, term = np.zeros(4, np.float32), np.zeros(4, np.uint8)
     hostsim.hs_observe(C.byref(gg101), 4, _p(f32(qo)), _p(agent), _p(envs), _p(rew), _p(term))
     assert np.abs(agent - a).max() < 2e-6 and np.abs(envs - e).max() < 2e-6 and (term.astype(bool) == t).all()
+
+
+def test_scripted_grasp_rollout_open_loop(hostsim, gg, franka_model, oracle64):
+    """200-step rollouts of the reference expert's stage machine (tests/golden/grasp_traj.npz, recorded closed-loop in
+    the fp64 oracle) replayed open-loop through the device pipeline: contact-free phases stay at fp32 noise, the
+    100-step mark is inside the stated rollout bound, success flags agree."""
+    import os
+    d = np.load(os.path.join(os.path.dirname(__file__), "golden", "grasp_traj.npz"))
+    K = d["xy"].shape[0]
+    Q, QD, QA = oracle64.new_state(K)
+    oracle64.reset(Q, QD, QA, d["xy"].astype(np.float64))
+    q, qd, qa, _, _ = hostsim_step(hostsim, gg, Q, QD, QA, np.tile(f32(mdl.FRANKA_HOME), (K, 1)))
+    succ = np.zeros(K, bool)
+    seen = 0
+    for t in range(200):
+        q, qd, qa, info, _ = hostsim_step(hostsim, gg, q, qd, qa, d["actions"][:, t])
+        succ |= q[:, 11] > np.float32(0.1)
+        seen = max(seen, info[:, 0].max())
+        er = np.abs(q[:, :9] - d["qrob"][:, t]).max(1)
+        ec = np.abs(q[:, 9:12] - d["cube"][:, t]).max(1)
+        if t < 80:
+            assert er.max() < 5e-6 and ec.max() < 1e-6, (t, er.max(), ec.max())
+        if t == 99:
+            assert er.max() < 1e-2 and ec.max() < 1e-2, (er.max(), ec.max())          # stated 100-step bound (helpers.ROLLOUT_POS_TOL)
+            assert np.median(ec) < 1e-5
+    assert seen >= 48
+    assert (ec < 5e-3).mean() >= 0.9                                                   # chaotic contact phases: most still agree at step 200
+    ref = d["reward"].max(1) > 0
+    assert (succ == ref).mean() >= 0.9 and 0.2 < ref.mean() < 0.8
