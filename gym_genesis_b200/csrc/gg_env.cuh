@@ -303,38 +303,6 @@ GG_HD void imp_aref(const GgModel& M, float pos, float vel, float& imp, float& a
     aref = -Bc * vel - Kc * imp * pos;
 }
 
-// ---------------------------------------------------------------------------------------------
-// Contact-frame Jacobian rows (normal, tangent 1, tangent 2) of one contact: J (v_b - v_a) at p.
-// ---------------------------------------------------------------------------------------------
-template <int NA, int NF, bool FH>
-GG_HD void contact_jac(const RobotDyn<NA, NF>& D, V3 cp, const M3& cR, V3 p, V3 n, V3 t1, V3 t2, int code,
-                       float* Jn, float* Jt1, float* Jt2) {
-    constexpr int NU = NA + NF;
-    const int rb = code == 0 ? -1 : (code - 1) % 3;
-    const float sg = code >= 4 ? -1.f : 1.f;
-    const bool cube = code == 0 || code >= 4;
-#pragma unroll
-    for (int i = 0; i < NA; i++) {
-        V3 c = cross(D.jk[i], p - D.jo[i]);
-        bool on = rb >= 0;
-        Jn[i] = on ? sg * dot(n, c) : 0.f; Jt1[i] = on ? sg * dot(t1, c) : 0.f; Jt2[i] = on ? sg * dot(t2, c) : 0.f;
-    }
-#pragma unroll
-    for (int f = 0; f < NF; f++) {
-        V3 c = FH ? cross(D.fk[f], p - D.fo[f]) : D.fk[f];
-        bool on = rb == 1 + f;
-        Jn[NA + f] = on ? sg * dot(n, c) : 0.f; Jt1[NA + f] = on ? sg * dot(t1, c) : 0.f; Jt2[NA + f] = on ? sg * dot(t2, c) : 0.f;
-    }
-    V3 r = p - cp;
-    V3 a0 = cross(cR.c0, r), a1 = cross(cR.c1, r), a2 = cross(cR.c2, r);
-    Jn[NU + 0] = cube ? n.x : 0.f; Jn[NU + 1] = cube ? n.y : 0.f; Jn[NU + 2] = cube ? n.z : 0.f;
-    Jt1[NU + 0] = cube ? t1.x : 0.f; Jt1[NU + 1] = cube ? t1.y : 0.f; Jt1[NU + 2] = cube ? t1.z : 0.f;
-    Jt2[NU + 0] = cube ? t2.x : 0.f; Jt2[NU + 1] = cube ? t2.y : 0.f; Jt2[NU + 2] = cube ? t2.z : 0.f;
-    Jn[NU + 3] = cube ? dot(n, a0) : 0.f; Jn[NU + 4] = cube ? dot(n, a1) : 0.f; Jn[NU + 5] = cube ? dot(n, a2) : 0.f;
-    Jt1[NU + 3] = cube ? dot(t1, a0) : 0.f; Jt1[NU + 4] = cube ? dot(t1, a1) : 0.f; Jt1[NU + 5] = cube ? dot(t1, a2) : 0.f;
-    Jt2[NU + 3] = cube ? dot(t2, a0) : 0.f; Jt2[NU + 4] = cube ? dot(t2, a1) : 0.f; Jt2[NU + 5] = cube ? dot(t2, a2) : 0.f;
-}
-
 template <int N> GG_HD float dotn(const float* a, const float* b) {
     float s = 0.f;
 #pragma unroll
@@ -344,10 +312,9 @@ template <int N> GG_HD float dotn(const float* a, const float* b) {
 
 // per-contact solver scalars kept between passes
 struct ConRow {
-    float aref[GG_MAX_CONTACTS][4];
+    float x[GG_MAX_CONTACTS][4];     // current residual of the 4 pyramidal rows: J a - aref
+    float jv[GG_MAX_CONTACTS][4];    // J s (search direction) of the same rows
     float D[GG_MAX_CONTACTS];
-    float u[GG_MAX_CONTACTS][3];    // Jc a
-    float w[GG_MAX_CONTACTS][3];    // Jc s
 };
 
 // row k of a contact: k = 0: n - mu t1, 1: n + mu t1, 2: n - mu t2, 3: n + mu t2
@@ -378,6 +345,11 @@ template <int N> GG_HD float newton_residual(const float* g, const float* H, con
     return gg_div(r, 1.f + am);
 }
 
+// Line-search accuracy only shapes the path of the outer Newton loop, not its fixed point (the outer loop stops on the
+// residual or on an exact full step).  1e-2 relative on phi' is the upstream ls_tolerance.
+#define GG_LS_TOL 1e-2f
+#define GG_LS_MAX 8
+
 struct LineSearch {
     float al, lo, hi, d0, d1, d2;
     int ls;
@@ -388,9 +360,9 @@ struct LineSearch {
         if (ls == 0) d0 = d1;
         else {
             if (d1 < 0.f) lo = al; else hi = al;
-            if (fabsf(d1) <= fabsf(d0) * 1e-6f) return false;
+            if (fabsf(d1) <= fabsf(d0) * GG_LS_TOL) return false;
         }
-        if (++ls > 12) return false;
+        if (++ls > GG_LS_MAX) return false;
         float nx = al - gg_div(d1, d2);
         if (hi >= 0.f && (nx <= lo || nx >= hi)) nx = 0.5f * (lo + hi);
         if (nx <= 0.f) nx = hi >= 0.f ? 0.5f * (lo + hi) : 1e-3f;
@@ -582,14 +554,71 @@ GG_HD void solve_cube_plane(const GgModel& M, const float* Mc, const float* as, 
     iters = it;
 }
 
-// general coupled solve over all NV = NU + 6 dofs (pads in contact): Jacobians recomputed per pass
+// General coupled solve over all NV = NU + 6 dofs (pads in contact).
+// Every contact row is a unit force d at point p, i.e. the spatial force F = (p x d, d) about a reference point O,
+// and its Jacobian is  J a = F . (T_b(a) - T_a(a))  with T_x(a) = sum_i B_i a_i the spatial acceleration of body
+// x (B_i = twist of dof i about O: the S_i of the dynamics pass re-referenced, plus the cube's six).  All contacts
+// between the same pair of bodies share that twist basis, so the Hessian / gradient of a pair are first
+// accumulated in 6-dim spatial-force space (Phi = sum D F F^T, 21 numbers; gF = sum D jar F) at ~180 instructions per
+// contact and projected onto the dofs ONCE per pair (H += P^T Phi P), instead of building a 3 x 15 Jacobian per
+// contact (~1500 instructions).  Pair index = contact code (0 plane-cube, 1+r plane-robot body r, 4+r body r-cube).
+GG_HD SV sym6_mul(const float* P, const SV& v) {     // packed lower 6x6, order (a.x a.y a.z l.x l.y l.z)
+    const float x[6] = {v.a.x, v.a.y, v.a.z, v.l.x, v.l.y, v.l.z};
+    float y[6];
+#pragma unroll
+    for (int i = 0; i < 6; i++) {
+        float r = 0.f;
+#pragma unroll
+        for (int j = 0; j < 6; j++) r += P[i >= j ? GG_TRI(i, j) : GG_TRI(j, i)] * x[j];
+        y[i] = r;
+    }
+    SV o; o.a = mk(y[0], y[1], y[2]); o.l = mk(y[3], y[4], y[5]);
+    return o;
+}
+
 template <int NA, int NF, bool FH>
 GG_HD void solve_coupled(const GgModel& M, const RobotDyn<NA, NF>& D, const EnvState<NA + NF>& s, const M3& cR, const float* Mc,
                          const float* as, const float* qdv, const float* lsg, const float* laref, const float* lD,
                          const Contacts& C, float* a, int iterations, float tol, float scale, int& iters, float& gnorm_out) {
-    constexpr int NU = NA + NF, NV = NU + 6, NH = NV * (NV + 1) / 2;
+    constexpr int NU = NA + NF, NV = NU + 6, NH = NV * (NV + 1) / 2, NP = 7;
     ConRow R;
     const float mu = M.friction;
+    // ---- twist basis of every dof about the reference point O = cube centre (all contacts are within a few cm of the
+    //      cube or of the fingertips next to it, so lever arms stay small and fp32 cancellation is avoided)
+    const V3 O = s.cp;
+    SV B[NV];
+#pragma unroll
+    for (int i = 0; i < NA; i++) { B[i].a = D.jk[i]; B[i].l = cross(D.jo[i] - O, D.jk[i]); }
+#pragma unroll
+    for (int f = 0; f < NF; f++) {
+        if (FH) { B[NA + f].a = D.fk[f]; B[NA + f].l = cross(D.fo[f] - O, D.fk[f]); }
+        else { B[NA + f].a = mk(0.f, 0.f, 0.f); B[NA + f].l = D.fk[f]; }
+    }
+    B[NU + 0].a = mk(0.f, 0.f, 0.f); B[NU + 0].l = mk(1.f, 0.f, 0.f);
+    B[NU + 1].a = mk(0.f, 0.f, 0.f); B[NU + 1].l = mk(0.f, 1.f, 0.f);
+    B[NU + 2].a = mk(0.f, 0.f, 0.f); B[NU + 2].l = mk(0.f, 0.f, 1.f);
+    B[NU + 3].a = cR.c0; B[NU + 3].l = mk(0.f, 0.f, 0.f);
+    B[NU + 4].a = cR.c1; B[NU + 4].l = mk(0.f, 0.f, 0.f);
+    B[NU + 5].a = cR.c2; B[NU + 5].l = mk(0.f, 0.f, 0.f);
+    // relative spatial acceleration of each pair for a dof vector x
+    auto pair_twists = [&](const float* x, SV* T) {
+        SV arm; arm.a = mk(0.f, 0.f, 0.f); arm.l = mk(0.f, 0.f, 0.f);
+#pragma unroll
+        for (int i = 0; i < NA; i++) arm = arm + B[i] * x[i];
+        SV cube; cube.a = mk(0.f, 0.f, 0.f); cube.l = mk(0.f, 0.f, 0.f);
+#pragma unroll
+        for (int j = 0; j < 6; j++) cube = cube + B[NU + j] * x[NU + j];
+        T[0] = cube; T[1] = arm; T[4] = cube + arm * -1.f;
+#pragma unroll
+        for (int f = 0; f < 2; f++) {
+            SV rb = arm;
+            if (f < NF) rb = arm + B[NA + (f < NF ? f : 0)] * x[NA + (f < NF ? f : 0)];
+            T[2 + f] = rb; T[5 + f] = cube + rb * -1.f;
+        }
+    };
+    SV Tq[NP], Tw[NP], Ts[NP];
+    pair_twists(qdv, Tq); pair_twists(s.qacc, Tw); pair_twists(as, Ts);
+
     float costw = 0.f, costs = 0.f;
     {
         float e[NV], Me[NU];
@@ -607,42 +636,45 @@ GG_HD void solve_coupled(const GgModel& M, const RobotDyn<NA, NF>& D, const EnvS
             if (lsg[d] != 0.f && js < 0.f) costs += 0.5f * lD[d] * js * js;
         }
     }
+    unsigned used = 0u;
     for (int c = 0; c < C.count; c++) {
-        float Jn[NV], Jt1[NV], Jt2[NV];
         V3 t1, t2;
-        tangent_basis(C.n[c], t1, t2);
-        contact_jac<NA, NF, FH>(D, s.cp, cR, C.p[c], C.n[c], t1, t2, C.code[c], Jn, Jt1, Jt2);
-        float vel[3] = {dotn<NV>(Jn, qdv), dotn<NV>(Jt1, qdv), dotn<NV>(Jt2, qdv)};
-        float uw[3] = {dotn<NV>(Jn, s.qacc), dotn<NV>(Jt1, s.qacc), dotn<NV>(Jt2, s.qacc)};
-        float us[3] = {dotn<NV>(Jn, as), dotn<NV>(Jt1, as), dotn<NV>(Jt2, as)};
+        const V3 n = C.n[c], p = C.p[c] - O;
+        tangent_basis(n, t1, t2);
+        SV Fn, F1, F2;
+        Fn.a = cross(p, n); Fn.l = n; F1.a = cross(p, t1); F1.l = t1; F2.a = cross(p, t2); F2.l = t2;
         const int code = C.code[c];
+        used |= 1u << code;
+        float vel[3] = {sdot(Fn, Tq[code]), sdot(F1, Tq[code]), sdot(F2, Tq[code])};
+        float uw[3] = {sdot(Fn, Tw[code]), sdot(F1, Tw[code]), sdot(F2, Tw[code])};
+        float us[3] = {sdot(Fn, Ts[code]), sdot(F1, Ts[code]), sdot(F2, Ts[code])};
         const int rb = code == 0 ? -1 : (code - 1) % 3;
         const float wsum = (rb >= 0 ? M.body_invweight[rb] : 0.f) + ((code == 0 || code >= 4) ? M.cube_invweight : 0.f);
-        float imp = 1.f, ar = 0.f;
+        float imp = 1.f, ar[4];
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
-            imp_aref(M, -C.depth[c], rowval(vel, mu, k), imp, ar);
-            R.aref[c][k] = ar;
-        }
+        for (int k = 0; k < 4; k++) imp_aref(M, -C.depth[c], rowval(vel, mu, k), imp, ar[k]);
         const float Dk = gg_rcp(fmaxf(M.minval, 2.f * mu * mu * (1.f - imp) / imp * wsum * (1.f + mu * mu)));
         R.D[c] = Dk;
 #pragma unroll
         for (int k = 0; k < 4; k++) {
-            float jw = rowval(uw, mu, k) - R.aref[c][k], js = rowval(us, mu, k) - R.aref[c][k];
+            float jw = rowval(uw, mu, k) - ar[k], js = rowval(us, mu, k) - ar[k];
             if (jw < 0.f) costw += 0.5f * Dk * jw * jw;
             if (js < 0.f) costs += 0.5f * Dk * js * js;
+            R.x[c][k] = jw; R.jv[c][k] = js;          // both candidates; the loser is dropped below
         }
-        R.u[c][0] = uw[0]; R.u[c][1] = uw[1]; R.u[c][2] = uw[2];
-        R.w[c][0] = us[0]; R.w[c][1] = us[1]; R.w[c][2] = us[2];
     }
     const bool warm = costw < costs;
 #pragma unroll
     for (int i = 0; i < NV; i++) a[i] = warm ? s.qacc[i] : as[i];
-    if (!warm) for (int c = 0; c < C.count; c++) { R.u[c][0] = R.w[c][0]; R.u[c][1] = R.w[c][1]; R.u[c][2] = R.w[c][2]; }
+    if (!warm) for (int c = 0; c < C.count; c++) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) R.x[c][k] = R.jv[c][k];
+    }
 
     int it = 0; float gnorm = 0.f;
     for (; it < iterations; it++) {
         float H[NH], g[NV], dinv[NV];
+        float Phi[NP][21], gF[NP][6];
 #pragma unroll
         for (int i = 0; i < NH; i++) H[i] = 0.f;
 #pragma unroll
@@ -662,12 +694,17 @@ GG_HD void solve_coupled(const GgModel& M, const RobotDyn<NA, NF>& D, const EnvS
             float jar = lsg[d] * a[d] - laref[d];
             if (lsg[d] != 0.f && jar < 0.f) { H[GG_TRI(d, d)] += lD[d]; g[d] += lD[d] * jar * lsg[d]; }
         }
+        for (int pc = 0; pc < NP; pc++) {
+            for (int i = 0; i < 21; i++) Phi[pc][i] = 0.f;
+            for (int i = 0; i < 6; i++) gF[pc][i] = 0.f;
+        }
+        // ---- accumulate every pair's stiffness / gradient in spatial-force space
         for (int c = 0; c < C.count; c++) {
             float Wnn = 0.f, Wn1 = 0.f, W11 = 0.f, Wn2 = 0.f, W22 = 0.f, gn = 0.f, g1 = 0.f, g2 = 0.f;
             const float Dk = R.D[c];
 #pragma unroll
             for (int k = 0; k < 4; k++) {
-                float jar = rowval(R.u[c], mu, k) - R.aref[c][k];
+                float jar = R.x[c][k];
                 if (jar < 0.f) {
                     float sm = (k & 1) ? mu : -mu;
                     Wnn += Dk; gn += Dk * jar;
@@ -676,34 +713,43 @@ GG_HD void solve_coupled(const GgModel& M, const RobotDyn<NA, NF>& D, const EnvS
                 }
             }
             if (Wnn == 0.f) continue;
-            float Jn[NV], Jt1[NV], Jt2[NV];
             V3 t1, t2;
-            tangent_basis(C.n[c], t1, t2);
+            const V3 n = C.n[c], p = C.p[c] - O;
+            tangent_basis(n, t1, t2);
+            const V3 pn = cross(p, n), p1 = cross(p, t1), p2 = cross(p, t2);
+            const float fn[6] = {pn.x, pn.y, pn.z, n.x, n.y, n.z}, f1[6] = {p1.x, p1.y, p1.z, t1.x, t1.y, t1.z},
+                        f2[6] = {p2.x, p2.y, p2.z, t2.x, t2.y, t2.z};
+            float Pn[6], P1[6], P2[6];
             const int code = C.code[c];
-            contact_jac<NA, NF, FH>(D, s.cp, cR, C.p[c], C.n[c], t1, t2, code, Jn, Jt1, Jt2);
-            float Pn[NV], P1[NV], P2[NV];
 #pragma unroll
-            for (int i = 0; i < NV; i++) {
-                g[i] += Jn[i] * gn + Jt1[i] * g1 + Jt2[i] * g2;
-                Pn[i] = Wnn * Jn[i] + Wn1 * Jt1[i] + Wn2 * Jt2[i];
-                P1[i] = Wn1 * Jn[i] + W11 * Jt1[i];
-                P2[i] = Wn2 * Jn[i] + W22 * Jt2[i];
+            for (int i = 0; i < 6; i++) {
+                gF[code][i] += fn[i] * gn + f1[i] * g1 + f2[i] * g2;
+                Pn[i] = Wnn * fn[i] + Wn1 * f1[i] + Wn2 * f2[i];
+                P1[i] = Wn1 * fn[i] + W11 * f1[i];
+                P2[i] = Wn2 * fn[i] + W22 * f2[i];
             }
-            if (code == 0) {            // cube block only
 #pragma unroll
-                for (int i = NU; i < NV; i++)
+            for (int i = 0; i < 6; i++)
 #pragma unroll
-                    for (int j = NU; j <= i; j++) H[GG_TRI(i, j)] += Jn[i] * Pn[j] + Jt1[i] * P1[j] + Jt2[i] * P2[j];
-            } else if (code < 4) {      // robot block only
-#pragma unroll
-                for (int i = 0; i < NU; i++)
-#pragma unroll
-                    for (int j = 0; j <= i; j++) H[GG_TRI(i, j)] += Jn[i] * Pn[j] + Jt1[i] * P1[j] + Jt2[i] * P2[j];
-            } else {
-#pragma unroll
-                for (int i = 0; i < NV; i++)
-#pragma unroll
-                    for (int j = 0; j <= i; j++) H[GG_TRI(i, j)] += Jn[i] * Pn[j] + Jt1[i] * P1[j] + Jt2[i] * P2[j];
+                for (int j = 0; j <= i; j++) Phi[code][GG_TRI(i, j)] += fn[i] * Pn[j] + f1[i] * P1[j] + f2[i] * P2[j];
+        }
+        // ---- project each used pair onto its dofs: H += P^T Phi P, g += P^T gF
+        for (int pc = 0; pc < NP; pc++) {
+            if (!((used >> pc) & 1u)) continue;
+            const int rb = pc == 0 ? -1 : (pc - 1) % 3;
+            const float sr = pc >= 4 ? -1.f : 1.f;
+            int idx[NV]; float sg[NV]; int nd = 0;
+            if (rb >= 0) {
+                for (int i = 0; i < NA; i++) { idx[nd] = i; sg[nd] = sr; nd++; }
+                if (rb >= 1 && rb - 1 < NF) { idx[nd] = NA + rb - 1; sg[nd] = sr; nd++; }
+            }
+            if (pc == 0 || pc >= 4) for (int j = 0; j < 6; j++) { idx[nd] = NU + j; sg[nd] = 1.f; nd++; }
+            SV gf; gf.a = mk(gF[pc][0], gF[pc][1], gF[pc][2]); gf.l = mk(gF[pc][3], gF[pc][4], gF[pc][5]);
+            for (int jj = 0; jj < nd; jj++) {
+                const int j = idx[jj];
+                const SV y = sym6_mul(Phi[pc], B[j]) * sg[jj];
+                g[j] += sg[jj] * sdot(B[j], gf);
+                for (int ii = jj; ii < nd; ii++) H[GG_TRI(idx[ii], j)] += sg[ii] * sdot(B[idx[ii]], y);
             }
         }
         gnorm = newton_residual<NV>(g, H, a);
@@ -722,12 +768,17 @@ GG_HD void solve_coupled(const GgModel& M, const RobotDyn<NA, NF>& D, const EnvS
         }
 #pragma unroll
         for (int i = 0; i < 6; i++) { q1 += Mc[i] * sdir[NU + i] * (a[NU + i] - as[NU + i]); q2 += Mc[i] * sdir[NU + i] * sdir[NU + i]; }
+        pair_twists(sdir, Ts);
         for (int c = 0; c < C.count; c++) {
-            float Jn[NV], Jt1[NV], Jt2[NV];
             V3 t1, t2;
-            tangent_basis(C.n[c], t1, t2);
-            contact_jac<NA, NF, FH>(D, s.cp, cR, C.p[c], C.n[c], t1, t2, C.code[c], Jn, Jt1, Jt2);
-            R.w[c][0] = dotn<NV>(Jn, sdir); R.w[c][1] = dotn<NV>(Jt1, sdir); R.w[c][2] = dotn<NV>(Jt2, sdir);
+            const V3 n = C.n[c], p = C.p[c] - O;
+            tangent_basis(n, t1, t2);
+            SV Fn, F1, F2;
+            Fn.a = cross(p, n); Fn.l = n; F1.a = cross(p, t1); F1.l = t1; F2.a = cross(p, t2); F2.l = t2;
+            const int code = C.code[c];
+            const float w3[3] = {sdot(Fn, Ts[code]), sdot(F1, Ts[code]), sdot(F2, Ts[code])};
+#pragma unroll
+            for (int k = 0; k < 4; k++) R.jv[c][k] = rowval(w3, mu, k);
         }
         LineSearch L; L.begin();
         for (;;) {
@@ -742,8 +793,8 @@ GG_HD void solve_coupled(const GgModel& M, const RobotDyn<NA, NF>& D, const EnvS
                 const float Dk = R.D[c];
 #pragma unroll
                 for (int k = 0; k < 4; k++) {
-                    float jv = rowval(R.w[c], mu, k);
-                    float x = rowval(R.u[c], mu, k) - R.aref[c][k] + L.al * jv;
+                    const float jv = R.jv[c][k];
+                    const float x = R.x[c][k] + L.al * jv;
                     if (x < 0.f) { d1 += Dk * x * jv; d2 += Dk * jv * jv; }
                 }
             }
@@ -759,11 +810,12 @@ GG_HD void solve_coupled(const GgModel& M, const RobotDyn<NA, NF>& D, const EnvS
 #pragma unroll
         for (int i = 0; i < NV; i++) a[i] += al * sdir[i];
         for (int c = 0; c < C.count; c++) {
-            float un[3] = {R.u[c][0] + al * R.w[c][0], R.u[c][1] + al * R.w[c][1], R.u[c][2] + al * R.w[c][2]};
 #pragma unroll
-            for (int k = 0; k < 4; k++)
-                changed += (rowval(R.u[c], mu, k) - R.aref[c][k] < 0.f) != (rowval(un, mu, k) - R.aref[c][k] < 0.f);
-            R.u[c][0] = un[0]; R.u[c][1] = un[1]; R.u[c][2] = un[2];
+            for (int k = 0; k < 4; k++) {
+                const float x0 = R.x[c][k], x1 = x0 + al * R.jv[c][k];
+                changed += (x0 < 0.f) != (x1 < 0.f);
+                R.x[c][k] = x1;
+            }
         }
         if (changed == 0 && fabsf(al - 1.f) < 1e-3f) { it++; break; }
     }
