@@ -152,6 +152,7 @@ GG_HD void robot_eef(const GgModel& M, const float* q, V3& ep, Q4& eq) {
 struct Contacts {
     V3 p[GG_MAX_CONTACTS];
     V3 n[GG_MAX_CONTACTS];
+    V3 t1[GG_MAX_CONTACTS];       // first tangent (filled by the coupled solver's first pass; t2 = n x t1)
     float depth[GG_MAX_CONTACTS];
     int code[GG_MAX_CONTACTS];
     int count;
@@ -579,7 +580,7 @@ GG_HD SV sym6_mul(const float* P, const SV& v) {     // packed lower 6x6, order 
 template <int NA, int NF, bool FH>
 GG_HD void solve_coupled(const GgModel& M, const RobotDyn<NA, NF>& D, const EnvState<NA + NF>& s, const M3& cR, const float* Mc,
                          const float* as, const float* qdv, const float* lsg, const float* laref, const float* lD,
-                         const Contacts& C, float* a, int iterations, float tol, float scale, int& iters, float& gnorm_out) {
+                         Contacts& C, float* a, int iterations, float tol, float scale, int& iters, float& gnorm_out) {
     constexpr int NU = NA + NF, NV = NU + 6, NH = NV * (NV + 1) / 2, NP = 7;
     ConRow R;
     const float mu = M.friction;
@@ -641,6 +642,7 @@ GG_HD void solve_coupled(const GgModel& M, const RobotDyn<NA, NF>& D, const EnvS
         V3 t1, t2;
         const V3 n = C.n[c], p = C.p[c] - O;
         tangent_basis(n, t1, t2);
+        C.t1[c] = t1;
         SV Fn, F1, F2;
         Fn.a = cross(p, n); Fn.l = n; F1.a = cross(p, t1); F1.l = t1; F2.a = cross(p, t2); F2.l = t2;
         const int code = C.code[c];
@@ -713,9 +715,8 @@ GG_HD void solve_coupled(const GgModel& M, const RobotDyn<NA, NF>& D, const EnvS
                 }
             }
             if (Wnn == 0.f) continue;
-            V3 t1, t2;
             const V3 n = C.n[c], p = C.p[c] - O;
-            tangent_basis(n, t1, t2);
+            const V3 t1 = C.t1[c], t2 = cross(n, t1);
             const V3 pn = cross(p, n), p1 = cross(p, t1), p2 = cross(p, t2);
             const float fn[6] = {pn.x, pn.y, pn.z, n.x, n.y, n.z}, f1[6] = {p1.x, p1.y, p1.z, t1.x, t1.y, t1.z},
                         f2[6] = {p2.x, p2.y, p2.z, t2.x, t2.y, t2.z};
@@ -770,9 +771,8 @@ GG_HD void solve_coupled(const GgModel& M, const RobotDyn<NA, NF>& D, const EnvS
         for (int i = 0; i < 6; i++) { q1 += Mc[i] * sdir[NU + i] * (a[NU + i] - as[NU + i]); q2 += Mc[i] * sdir[NU + i] * sdir[NU + i]; }
         pair_twists(sdir, Ts);
         for (int c = 0; c < C.count; c++) {
-            V3 t1, t2;
             const V3 n = C.n[c], p = C.p[c] - O;
-            tangent_basis(n, t1, t2);
+            const V3 t1 = C.t1[c], t2 = cross(n, t1);
             SV Fn, F1, F2;
             Fn.a = cross(p, n); Fn.l = n; F1.a = cross(p, t1); F1.l = t1; F2.a = cross(p, t2); F2.l = t2;
             const int code = C.code[c];
