@@ -50,16 +50,17 @@ template <int NA, int NF> struct RobotDyn {
     M3 fR[NF > 0 ? NF : 1]; V3 fp[NF > 0 ? NF : 1];   // finger frames
 };
 
+// The dynamics pass is split in two independent halves so that the CUDA kernel can run them in different warps
+// (role specialisation, gg_kernels.cu): both walk the same kinematic chain; robot_crba needs positions only.
+//   robot_crba : frames, composite inertias, Mt = M + armature + dt*(damping + kv)
+//   robot_rnea : velocities / accelerations / link forces, fs = clamp(PD) - damping*qd - bias
 template <int NA, int NF, bool FH>
-GG_HD void robot_dynamics(const GgModel& M, const float* q, const float* qd, const float* target, RobotDyn<NA, NF>& D) {
+GG_HD void robot_crba(const GgModel& M, const float* q, RobotDyn<NA, NF>& D) {
     constexpr int NU = NA + NF;
-    SV S[NA]; SI I[NA]; SV F[NA];
-    float bias[NU];
+    SV S[NA]; SI I[NA];
     Q4 ql = ldq(M.base_quat);
     V3 pl = ld3(M.base_pos);
     M3 Rl = qmat(ql);
-    SV V; V.a = mk(0.f, 0.f, 0.f); V.l = mk(0.f, 0.f, 0.f);
-    SV A; A.a = mk(0.f, 0.f, 0.f); A.l = mk(0.f, 0.f, M.gravity);   // gravity as base acceleration
     GG_LINK_LOOP
     for (int l = 0; l < NA; l++) {
         pl = pl + mul(Rl, ld3(M.link_pos[l]));
@@ -69,14 +70,10 @@ GG_HD void robot_dynamics(const GgModel& M, const float* q, const float* qd, con
         Rl = qmat(ql);
         D.jk[l] = Rl.c2; D.jo[l] = pl;
         S[l].a = Rl.c2; S[l].l = cross(pl, Rl.c2);
-        A = A + crm(V, S[l]) * qd[l];
-        V = V + S[l] * qd[l];
         I[l] = body_inertia(M.link_mass[l], ld3(M.link_com[l]), M.link_inertia[l], Rl, pl);
-        F[l] = apply(I[l], A) + crf(V, apply(I[l], V));
     }
     D.lq = ql; D.lp = pl; D.lR = Rl;
     SI Ic; Ic.m = 0.f; Ic.h = mk(0.f, 0.f, 0.f); Ic.I.xx = Ic.I.yy = Ic.I.zz = Ic.I.xy = Ic.I.xz = Ic.I.yz = 0.f;
-    SV Fc; Fc.a = mk(0.f, 0.f, 0.f); Fc.l = mk(0.f, 0.f, 0.f);
 #pragma unroll
     for (int f = 0; f < NF; f++) {
         Q4 qf = qmul(ql, ldq(M.fing_quat[f]));
@@ -96,34 +93,122 @@ GG_HD void robot_dynamics(const GgModel& M, const float* q, const float* qd, con
             D.fk[f] = a; D.fo[f] = pf;
         }
         D.fR[f] = Rf; D.fp[f] = pf;
-        SV Af = A + crm(V, Sf) * qd[NA + f];
-        SV Vf = V + Sf * qd[NA + f];
         SI If = body_inertia(M.fing_mass[f], ld3(M.fing_com[f]), M.fing_inertia[f], Rf, pf);
-        SV Ff = apply(If, Af) + crf(Vf, apply(If, Vf));
         SV G = apply(If, Sf);
         D.Mt[GG_TRI(NA + f, NA + f)] = sdot(Sf, G);
 #pragma unroll
         for (int i = 0; i < NA; i++) D.Mt[GG_TRI(NA + f, i)] = sdot(S[i], G);
 #pragma unroll
         for (int g = 0; g < f; g++) D.Mt[GG_TRI(NA + f, NA + g)] = 0.f;
-        bias[NA + f] = sdot(Sf, Ff);
-        Ic = Ic + If; Fc = Fc + Ff;
+        Ic = Ic + If;
     }
     GG_LINK_LOOP
     for (int l = NA - 1; l >= 0; l--) {
-        Ic = Ic + I[l]; Fc = Fc + F[l];
+        Ic = Ic + I[l];
         SV G = apply(Ic, S[l]);
         GG_LINK_LOOP
         for (int i = 0; i <= l; i++) D.Mt[GG_TRI(l, i)] = sdot(S[i], G);
+    }
+    // armature; approximate implicit-fast diagonal
+#pragma unroll
+    for (int d = 0; d < NU; d++) D.Mt[GG_TRI(d, d)] += M.armature[d] + M.dt * (M.damping[d] + M.kv[d]);
+}
+
+template <int NA, int NF, bool FH>
+GG_HD void robot_rnea(const GgModel& M, const float* q, const float* qd, const float* target, float* fs) {
+    constexpr int NU = NA + NF;
+    SV S[NA]; SV F[NA];
+    float bias[NU];
+    Q4 ql = ldq(M.base_quat);
+    V3 pl = ld3(M.base_pos);
+    M3 Rl = qmat(ql);
+    SV V; V.a = mk(0.f, 0.f, 0.f); V.l = mk(0.f, 0.f, 0.f);
+    SV A; A.a = mk(0.f, 0.f, 0.f); A.l = mk(0.f, 0.f, M.gravity);   // gravity as base acceleration
+    GG_LINK_LOOP
+    for (int l = 0; l < NA; l++) {
+        pl = pl + mul(Rl, ld3(M.link_pos[l]));
+        float s, c;
+        gg_sincos(0.5f * q[l], &s, &c);
+        ql = qmul_z(qmul(ql, ldq(M.link_quat[l])), c, s);
+        Rl = qmat(ql);
+        S[l].a = Rl.c2; S[l].l = cross(pl, Rl.c2);
+        A = A + crm(V, S[l]) * qd[l];
+        V = V + S[l] * qd[l];
+        SI Il = body_inertia(M.link_mass[l], ld3(M.link_com[l]), M.link_inertia[l], Rl, pl);
+        F[l] = apply(Il, A) + crf(V, apply(Il, V));
+    }
+    SV Fc; Fc.a = mk(0.f, 0.f, 0.f); Fc.l = mk(0.f, 0.f, 0.f);
+#pragma unroll
+    for (int f = 0; f < NF; f++) {
+        Q4 qf = qmul(ql, ldq(M.fing_quat[f]));
+        V3 p0 = pl + mul(Rl, ld3(M.fing_pos[f]));
+        SV Sf; M3 Rf; V3 pf;
+        if (FH) {
+            float s, c;
+            gg_sincos(0.5f * q[NA + f], &s, &c);
+            qf = qmul_z(qf, c, s);
+            Rf = qmat(qf);
+            Sf.a = Rf.c2; Sf.l = cross(p0, Rf.c2); pf = p0;
+        } else {
+            Rf = qmat(qf);
+            V3 a = mul(Rf, ld3(M.fing_axis[f]));
+            Sf.a = mk(0.f, 0.f, 0.f); Sf.l = a; pf = p0 + a * q[NA + f];
+        }
+        SV Af = A + crm(V, Sf) * qd[NA + f];
+        SV Vf = V + Sf * qd[NA + f];
+        SI If = body_inertia(M.fing_mass[f], ld3(M.fing_com[f]), M.fing_inertia[f], Rf, pf);
+        SV Ff = apply(If, Af) + crf(Vf, apply(If, Vf));
+        bias[NA + f] = sdot(Sf, Ff);
+        Fc = Fc + Ff;
+    }
+    GG_LINK_LOOP
+    for (int l = NA - 1; l >= 0; l--) {
+        Fc = Fc + F[l];
         bias[l] = sdot(S[l], Fc);
     }
-    // PD position control with force clamp; passive damping; approximate implicit-fast diagonal
+    // PD position control with force clamp; passive damping
 #pragma unroll
     for (int d = 0; d < NU; d++) {
         float t = M.kp[d] * (target[d] - q[d]) - M.kv[d] * qd[d];
         t = fminf(fmaxf(t, M.frc_lo[d]), M.frc_hi[d]);
-        D.fs[d] = t - M.damping[d] * qd[d] - bias[d];
-        D.Mt[GG_TRI(d, d)] += M.armature[d] + M.dt * (M.damping[d] + M.kv[d]);
+        fs[d] = t - M.damping[d] * qd[d] - bias[d];
+    }
+}
+
+template <int NA, int NF, bool FH>
+GG_HD void robot_dynamics(const GgModel& M, const float* q, const float* qd, const float* target, RobotDyn<NA, NF>& D) {
+    robot_crba<NA, NF, FH>(M, q, D);
+    robot_rnea<NA, NF, FH>(M, q, qd, target, D.fs);
+}
+
+// frames of the pad-carrying bodies only (last arm link + fingers): the cube role's broad phase
+template <int NA, int NF, bool FH>
+GG_HD void robot_pad_frames(const GgModel& M, const float* q, RobotDyn<NA, NF>& D) {
+    Q4 ql = ldq(M.base_quat);
+    V3 pl = ld3(M.base_pos);
+    M3 Rl = qmat(ql);
+    GG_LINK_LOOP
+    for (int l = 0; l < NA; l++) {
+        pl = pl + mul(Rl, ld3(M.link_pos[l]));
+        float s, c;
+        gg_sincos(0.5f * q[l], &s, &c);
+        ql = qmul_z(qmul(ql, ldq(M.link_quat[l])), c, s);
+        Rl = qmat(ql);
+    }
+    D.lq = ql; D.lp = pl; D.lR = Rl;
+#pragma unroll
+    for (int f = 0; f < NF; f++) {
+        Q4 qf = qmul(ql, ldq(M.fing_quat[f]));
+        V3 p0 = pl + mul(Rl, ld3(M.fing_pos[f]));
+        if (FH) {
+            float s, c;
+            gg_sincos(0.5f * q[NA + f], &s, &c);
+            qf = qmul_z(qf, c, s);
+            D.fR[f] = qmat(qf); D.fp[f] = p0;
+        } else {
+            M3 Rf = qmat(qf);
+            D.fR[f] = Rf; D.fp[f] = p0 + mul(Rf, ld3(M.fing_axis[f])) * q[NA + f];
+        }
     }
 }
 
@@ -861,8 +946,133 @@ GG_HD bool pads_may_touch(const GgModel& M, const RobotDyn<NA, NF>& D, V3 cp) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// One substep (A.2): dynamics at t, collision, constraint solve, semi-implicit Euler.
+// Building blocks of one substep (A.2): dynamics at t, collision, constraint solve, semi-implicit Euler.
+// env_substep composes them for one env in one thread (host harness); the CUDA kernel runs them in three
+// role warps per 32 envs (gg_kernels.cu).
 // ---------------------------------------------------------------------------------------------
+// cube block: diagonal inertia, free (unconstrained) acceleration and velocity vector [v_world, w_body]
+GG_HD void cube_free_acc(const GgModel& M, V3 cv, V3 cw, float* Mc, float* as_c, float* qd_c) {
+    Mc[0] = M.cube_mass; Mc[1] = M.cube_mass; Mc[2] = M.cube_mass;
+    Mc[3] = M.cube_inertia[0]; Mc[4] = M.cube_inertia[1]; Mc[5] = M.cube_inertia[2];
+    V3 Iw = mk(Mc[3] * cw.x, Mc[4] * cw.y, Mc[5] * cw.z);
+    V3 gyro = cross(cw, Iw);
+    as_c[0] = 0.f; as_c[1] = 0.f; as_c[2] = -M.gravity;
+    as_c[3] = -gg_div(gyro.x, Mc[3]); as_c[4] = -gg_div(gyro.y, Mc[4]); as_c[5] = -gg_div(gyro.z, Mc[5]);
+    qd_c[0] = cv.x; qd_c[1] = cv.y; qd_c[2] = cv.z; qd_c[3] = cw.x; qd_c[4] = cw.y; qd_c[5] = cw.z;
+}
+
+// joint-limit rows (at most one per dof); returns the number of violated limits
+template <int NU>
+GG_HD int joint_limit_rows(const GgModel& M, const float* q, const float* qd, float* lsg, float* laref, float* lD) {
+    int nlim = 0;
+#pragma unroll
+    for (int d = 0; d < NU; d++) {
+        float plo = q[d] - M.lim_lo[d], phi = M.lim_hi[d] - q[d];
+        float sg = plo < 0.f ? 1.f : (phi < 0.f ? -1.f : 0.f);
+        float pos = plo < 0.f ? plo : phi;
+        float imp, aref;
+        imp_aref(M, pos, sg * qd[d], imp, aref);
+        lsg[d] = sg; laref[d] = aref;
+        lD[d] = gg_rcp(fmaxf(M.minval, (1.f - imp) / imp * M.dof_invweight[d]));
+        nlim += sg != 0.f;
+    }
+    return nlim;
+}
+
+// cube corners touching the plane (first <= 4 in corner-index order, same points as plane_box)
+GG_HD int cube_plane_points(const GgModel& M, V3 cp, const M3& cR, V3* pc, float* dc) {
+    int ncp = 0;
+    V3 half = ld3(M.cube_half);
+#pragma unroll
+    for (int c = 0; c < 4; c++) { pc[c] = cp; dc[c] = 0.f; }
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        V3 l = mk((i & 1) ? half.x : -half.x, (i & 2) ? half.y : -half.y, (i & 4) ? half.z : -half.z);
+        V3 w = cp + mul(cR, l);
+        float dist = w.z - M.plane_z;
+        if (dist <= 0.f && ncp < 4) {
+            V3 pp = mk(w.x, w.y, w.z - 0.5f * dist);
+#pragma unroll
+            for (int c = 0; c < 4; c++) if (c == ncp) { pc[c] = pp; dc[c] = -dist; }
+            ncp++;
+        }
+    }
+    return ncp;
+}
+
+// cube block on the decoupled path: plane contacts only
+GG_HD void cube_block_solve(const GgModel& M, V3 cp, const M3& cR, const float* Mc, const float* as_c, const float* qd_c,
+                            const float* warm_c, float* a_c, int iterations, float tol, StepInfo& info) {
+    V3 pc[4]; float dc[4];
+    const int ncp = cube_plane_points(M, cp, cR, pc, dc);
+    info.ncon = ncp; info.iters = 0; info.grad = 0.f;
+    if (ncp == 0) {
+#pragma unroll
+        for (int i = 0; i < 6; i++) a_c[i] = as_c[i];
+    } else {
+        solve_cube_plane(M, Mc, as_c, qd_c, cp, cR, pc, dc, ncp, warm_c, a_c, iterations, tol, 1.f, info.iters, info.grad);
+    }
+}
+
+// robot block on the decoupled path: joint-limit rows only
+template <int NU>
+GG_HD void robot_block_solve(const float* Mt, const float* as, int nlim, const float* lsg, const float* laref, const float* lD,
+                             const float* warm, float* a, int iterations, float tol, StepInfo& info) {
+    info.ncon = 0; info.iters = 0; info.grad = 0.f;
+    if (nlim == 0) {
+#pragma unroll
+        for (int i = 0; i < NU; i++) a[i] = as[i];
+    } else {
+        solve_robot_limits<NU>(Mt, as, lsg, laref, lD, warm, a, iterations, tol, 1.f, info.iters, info.grad);
+    }
+}
+
+// coupled path: full narrow phase + Newton on all NU + 6 dofs
+template <int NA, int NF, bool FH>
+GG_HD void coupled_block_solve(const GgModel& M, const RobotDyn<NA, NF>& D, const EnvState<NA + NF>& s, const M3& cR, const float* Mc,
+                               const float* as, const float* qdv, int nlim, const float* lsg, const float* laref, const float* lD,
+                               float* a, int iterations, float tol, StepInfo& info) {
+    constexpr int NV = NA + NF + 6;
+    Contacts C;
+    C.count = 0;
+    const int maxc = M.max_contacts < GG_MAX_CONTACTS ? M.max_contacts : GG_MAX_CONTACTS;
+    plane_box(M.plane_z, s.cp, cR, ld3(M.cube_half), 0, maxc, C);
+    collide_pads<NA, NF>(M, D, s.cp, cR, C);
+    info.ncon = C.count; info.iters = 0; info.grad = 0.f;
+    if (nlim == 0 && C.count == 0) {
+#pragma unroll
+        for (int i = 0; i < NV; i++) a[i] = as[i];
+    } else {
+        solve_coupled<NA, NF, FH>(M, D, s, cR, Mc, as, qdv, lsg, laref, lD, C, a, iterations, tol, 1.f, info.iters, info.grad);
+    }
+}
+
+template <int NU> GG_HD void integrate_robot(const GgModel& M, float* q, float* qd, float* qacc, const float* a) {
+#pragma unroll
+    for (int i = 0; i < NU; i++) { qacc[i] = a[i]; qd[i] += a[i] * M.dt; q[i] += qd[i] * M.dt; }
+}
+
+GG_HD void integrate_cube(const GgModel& M, V3& cp, Q4& cq, V3& cv, V3& cw, float* qacc_c, const float* a_c) {
+    const float dt = M.dt;
+#pragma unroll
+    for (int i = 0; i < 6; i++) qacc_c[i] = a_c[i];
+    cv = cv + mk(a_c[0], a_c[1], a_c[2]) * dt;
+    cw = cw + mk(a_c[3], a_c[4], a_c[5]) * dt;
+    cp = cp + cv * dt;
+    V3 w = cw * dt;
+    float ang = sqrtf(dot(w, w));
+    Q4 dq = mkq(1.f, 0.f, 0.f, 0.f);
+    if (ang > 0.f) {
+        float sn, cs;
+        gg_sincos(0.5f * ang, &sn, &cs);
+        float k = gg_div(sn, ang);
+        dq = mkq(cs, w.x * k, w.y * k, w.z * k);
+    }
+    Q4 nq = qmul(cq, dq);
+    float inv = gg_rsqrt(nq.w * nq.w + nq.x * nq.x + nq.y * nq.y + nq.z * nq.z);
+    cq = mkq(nq.w * inv, nq.x * inv, nq.y * inv, nq.z * inv);
+}
+
 template <int NA, int NF, bool FH>
 GG_HD void env_substep(const GgModel& M, EnvState<NA + NF>& s, const float* target, int iterations, float tol, StepInfo& info) {
     constexpr int NU = NA + NF, NV = NU + 6;
@@ -871,124 +1081,36 @@ GG_HD void env_substep(const GgModel& M, EnvState<NA + NF>& s, const float* targ
     const M3 cR = qmat(s.cq);
 
     // ---- smooth (unconstrained) acceleration a_s
-    float Mc[6] = {M.cube_mass, M.cube_mass, M.cube_mass, M.cube_inertia[0], M.cube_inertia[1], M.cube_inertia[2]};
-    float as[NV], qdv[NV];
+    float Mc[6], as[NV], qdv[NV];
     {
         float L[NU * (NU + 1) / 2], dinv[NU];
 #pragma unroll
         for (int i = 0; i < NU * (NU + 1) / 2; i++) L[i] = D.Mt[i];
         chol_packed<NU>(L, dinv);
         chol_solve_packed<NU>(L, dinv, D.fs, as);
-        V3 Iw = mk(Mc[3] * s.cw.x, Mc[4] * s.cw.y, Mc[5] * s.cw.z);
-        V3 gyro = cross(s.cw, Iw);
-        as[NU + 0] = 0.f; as[NU + 1] = 0.f; as[NU + 2] = -M.gravity;
-        as[NU + 3] = -gg_div(gyro.x, Mc[3]); as[NU + 4] = -gg_div(gyro.y, Mc[4]); as[NU + 5] = -gg_div(gyro.z, Mc[5]);
 #pragma unroll
         for (int i = 0; i < NU; i++) qdv[i] = s.qd[i];
-        qdv[NU + 0] = s.cv.x; qdv[NU + 1] = s.cv.y; qdv[NU + 2] = s.cv.z;
-        qdv[NU + 3] = s.cw.x; qdv[NU + 4] = s.cw.y; qdv[NU + 5] = s.cw.z;
+        cube_free_acc(M, s.cv, s.cw, Mc, as + NU, qdv + NU);
     }
-
-    // ---- joint-limit rows (at most one per dof)
     float lsg[NU], laref[NU], lD[NU];
-    int nlim = 0;
-#pragma unroll
-    for (int d = 0; d < NU; d++) {
-        float plo = s.q[d] - M.lim_lo[d], phi = M.lim_hi[d] - s.q[d];
-        float sg = plo < 0.f ? 1.f : (phi < 0.f ? -1.f : 0.f);
-        float pos = plo < 0.f ? plo : phi;
-        float imp, aref;
-        imp_aref(M, pos, sg * s.qd[d], imp, aref);
-        lsg[d] = sg; laref[d] = aref;
-        lD[d] = gg_rcp(fmaxf(M.minval, (1.f - imp) / imp * M.dof_invweight[d]));
-        nlim += sg != 0.f;
-    }
-
-    float meaninertia = 0.f;
-#pragma unroll
-    for (int i = 0; i < NU; i++) meaninertia += D.Mt[GG_TRI(i, i)];
-#pragma unroll
-    for (int i = 0; i < 6; i++) meaninertia += Mc[i];
-    const float scale = gg_rcp(meaninertia);      // = 1 / (mean inertia * NV)
+    const int nlim = joint_limit_rows<NU>(M, s.q, s.qd, lsg, laref, lD);
 
     float a[NV];
-    info.iters = 0; info.grad = 0.f;
     if (!pads_may_touch<NA, NF>(M, D, s.cp)) {
         // ---- decoupled fast path: robot block (limits only) and cube block (plane contacts only)
-        if (nlim == 0) {
-#pragma unroll
-            for (int i = 0; i < NU; i++) a[i] = as[i];
-        } else {
-            int it; float gn;
-            solve_robot_limits<NU>(D.Mt, as, lsg, laref, lD, s.qacc, a, iterations, tol, scale, it, gn);
-            info.iters = it; info.grad = gn;
-        }
-        V3 pc[4]; float dc[4]; int ncp = 0;
-        {
-            V3 half = ld3(M.cube_half);
-#pragma unroll
-            for (int c = 0; c < 4; c++) { pc[c] = s.cp; dc[c] = 0.f; }
-#pragma unroll
-            for (int i = 0; i < 8; i++) {
-                V3 l = mk((i & 1) ? half.x : -half.x, (i & 2) ? half.y : -half.y, (i & 4) ? half.z : -half.z);
-                V3 w = s.cp + mul(cR, l);
-                float dist = w.z - M.plane_z;
-                if (dist <= 0.f && ncp < 4) {
-                    V3 pp = mk(w.x, w.y, w.z - 0.5f * dist);
-#pragma unroll
-                    for (int c = 0; c < 4; c++) if (c == ncp) { pc[c] = pp; dc[c] = -dist; }
-                    ncp++;
-                }
-            }
-        }
-        info.ncon = ncp;
-        if (ncp == 0) {
-#pragma unroll
-            for (int i = 0; i < 6; i++) a[NU + i] = as[NU + i];
-        } else {
-            int it; float gn;
-            solve_cube_plane(M, Mc, as + NU, qdv + NU, s.cp, cR, pc, dc, ncp, s.qacc + NU, a + NU, iterations, tol, scale, it, gn);
-            info.iters = it > info.iters ? it : info.iters;
-            info.grad = fmaxf(info.grad, gn);
-        }
+        StepInfo ir, ic;
+        robot_block_solve<NU>(D.Mt, as, nlim, lsg, laref, lD, s.qacc, a, iterations, tol, ir);
+        cube_block_solve(M, s.cp, cR, Mc, as + NU, qdv + NU, s.qacc + NU, a + NU, iterations, tol, ic);
+        info.ncon = ic.ncon;
+        info.iters = ic.iters > ir.iters ? ic.iters : ir.iters;
+        info.grad = fmaxf(ir.grad, ic.grad);
     } else {
-        Contacts C;
-        C.count = 0;
-        const int maxc = M.max_contacts < GG_MAX_CONTACTS ? M.max_contacts : GG_MAX_CONTACTS;
-        plane_box(M.plane_z, s.cp, cR, ld3(M.cube_half), 0, maxc, C);
-        collide_pads<NA, NF>(M, D, s.cp, cR, C);
-        info.ncon = C.count;
-        if (nlim == 0 && C.count == 0) {
-#pragma unroll
-            for (int i = 0; i < NV; i++) a[i] = as[i];
-        } else {
-            solve_coupled<NA, NF, FH>(M, D, s, cR, Mc, as, qdv, lsg, laref, lD, C, a, iterations, tol, scale, info.iters, info.grad);
-        }
+        coupled_block_solve<NA, NF, FH>(M, D, s, cR, Mc, as, qdv, nlim, lsg, laref, lD, a, iterations, tol, info);
     }
 
     // ---- semi-implicit Euler
-    const float dt = M.dt;
-#pragma unroll
-    for (int i = 0; i < NV; i++) s.qacc[i] = a[i];
-#pragma unroll
-    for (int i = 0; i < NU; i++) { s.qd[i] += a[i] * dt; s.q[i] += s.qd[i] * dt; }
-    s.cv = s.cv + mk(a[NU], a[NU + 1], a[NU + 2]) * dt;
-    s.cw = s.cw + mk(a[NU + 3], a[NU + 4], a[NU + 5]) * dt;
-    s.cp = s.cp + s.cv * dt;
-    {
-        V3 w = s.cw * dt;
-        float ang = sqrtf(dot(w, w));
-        Q4 dq = mkq(1.f, 0.f, 0.f, 0.f);
-        if (ang > 0.f) {
-            float sn, cs;
-            gg_sincos(0.5f * ang, &sn, &cs);
-            float k = gg_div(sn, ang);
-            dq = mkq(cs, w.x * k, w.y * k, w.z * k);
-        }
-        Q4 nq = qmul(s.cq, dq);
-        float inv = gg_rsqrt(nq.w * nq.w + nq.x * nq.x + nq.y * nq.y + nq.z * nq.z);
-        s.cq = mkq(nq.w * inv, nq.x * inv, nq.y * inv, nq.z * inv);
-    }
+    integrate_robot<NU>(M, s.q, s.qd, s.qacc, a);
+    integrate_cube(M, s.cp, s.cq, s.cv, s.cw, s.qacc + NU, a + NU);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -76,102 +76,306 @@ template <int NU> __device__ __forceinline__ void store_state(float* __restrict_
     for (int i = 0; i < NU + 6; i++) a[(size_t)i * stride] = s.qacc[i];
 }
 
-template <int NU> __device__ __forceinline__ bool state_finite(const gg::EnvState<NU>& s) {
-    float acc = s.cp.x + s.cp.y + s.cp.z + s.cq.w + s.cq.x + s.cq.y + s.cq.z + s.cv.x + s.cv.y + s.cv.z + s.cw.x + s.cw.y + s.cw.z;
-#pragma unroll
-    for (int i = 0; i < NU; i++) acc += s.q[i] + s.qd[i];
-    return isfinite(acc);
+// ------------------------------------------------------------------------------------------------
+// step_kernel: ROLE-SPECIALISED warps.  A block owns 32 consecutive envs and runs three warps on them;
+// lane = env, warp = role:
+//   warp 0  MAIN : kinematics + CRBA + Cholesky, smooth acceleration, joint-limit rows, robot-block Newton solve (or the
+//                  coupled solve when a pad can touch something), robot integration, end-effector pose, agent_pos
+//   warp 1  RNEA : velocities / accelerations / link forces of the same chain, PD torque -> fs = tau - bias
+//   warp 2  CUBE : pad broad phase, cube-plane contacts + cube-block Newton solve, cube integration, environment_state,
+//                  reward / terminated / truncated / done, counters, episode statistics
+// The three chains are independent until the points marked by the named barriers below, so the latency of one env.step
+// is the longest role (~5 k instructions) instead of their sum (~14 k), and 16384 envs put 2.6 warps on every scheduler
+// instead of 0.9.  Exchange goes through shared memory ([field][lane], conflict free):
+//   barrier 1 (96 threads): RNEA and CUBE arrive, MAIN waits      -- fs, coupled flag, cube state
+//   barrier 2 (64 threads): MAIN arrives, CUBE waits              -- cube acceleration of coupled envs, solver statistics
+//   barrier 3 (64 threads): MAIN and CUBE wait                    -- end-effector position, non-finite flags
+// ------------------------------------------------------------------------------------------------
+constexpr int kBlockThreads = 96;
+
+#ifndef GG_MINBLOCKS
+#define GG_MINBLOCKS 4
+#endif
+__device__ __forceinline__ void bar_sync(int id, int nthreads) {
+    __syncwarp();
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void bar_arrive(int id, int nthreads) {
+    __threadfence_block();
+    __syncwarp();
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
-constexpr int kBlock = 128;      // default threads per block
-constexpr int kMaxBlock = 1024;
+template <int NU> struct Xchg {
+    float fs[NU][32];         // RNEA -> MAIN
+    float cube[19][32];       // CUBE -> MAIN: cp3 cq4 cv3 cw3 qacc6 (the state a coupled solve starts from)
+    float acube[6][32];       // MAIN -> CUBE: cube acceleration of coupled envs
+    float ep[3][32];          // MAIN -> CUBE: end-effector position after the step
+    int coupled[32];          // CUBE -> MAIN
+    int iters[32], ncon[32];  // MAIN -> CUBE (statistics)
+    int bad[2][32];           // non-finite flags: [0] robot (MAIN), [1] cube (CUBE)
+};
+
+__device__ __forceinline__ bool reset_decision(const StepArgs& A, int e, uint32_t gid) {
+    bool r = false;
+    if (A.mode == 0) {
+        r = (A.reset_mask != nullptr && A.reset_mask[e] != 0) || (A.auto_reset && A.done[e] != 0);
+        if (A.reset_prob > 0.f) {
+            uint32_t o[4];
+            gg::philox4x32_10(gid, A.step_index, 0x52535421u, 0u, (uint32_t)A.seed, (uint32_t)(A.seed >> 32), o);
+            r = r || gg::u01(o[0]) < A.reset_prob;
+        }
+    } else if (A.mode == 1) {
+        r = A.reset_mask == nullptr || A.reset_mask[e] != 0;
+    }
+    return r;
+}
 
 template <int NA, int NF, bool FH>
-__global__ void __launch_bounds__(256) step_kernel(const __grid_constant__ StepArgs A) {
-    constexpr int NU = NA + NF;
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool live = e < A.n;
-    float st_steps = 0.f, st_done = 0.f, st_succ = 0.f, st_ret = 0.f, st_len = 0.f, st_nan = 0.f, st_iter = 0.f, st_con = 0.f;
-    if (live) {
-        gg::EnvState<NU> s;
-        load_state<NU>(A.state, A.stride, e, s);
-        int steps = A.step_count[e], epi = A.episode[e];
-        const uint32_t gid = (uint32_t)(A.first_env + e);
-        bool do_reset = false;
-        if (A.mode == 0) {
-            do_reset = (A.reset_mask != nullptr && A.reset_mask[e] != 0) || (A.auto_reset && A.done[e] != 0);
-            if (A.reset_prob > 0.f) {
-                uint32_t o[4];
-                gg::philox4x32_10(gid, A.step_index, 0x52535421u, 0u, (uint32_t)A.seed, (uint32_t)(A.seed >> 32), o);
-                do_reset = do_reset || gg::u01(o[0]) < A.reset_prob;
-            }
-        } else if (A.mode == 1) {
-            do_reset = A.reset_mask == nullptr || A.reset_mask[e] != 0;
+__global__ void __launch_bounds__(kBlockThreads, GG_MINBLOCKS) step_kernel(const __grid_constant__ StepArgs A) {
+    constexpr int NU = NA + NF, NV = NU + 6;
+    __shared__ Xchg<NU> X;
+    const int lane = threadIdx.x & 31, role = threadIdx.x >> 5;
+    const int e0 = blockIdx.x * 32 + lane;
+    const bool live = e0 < A.n;
+    const int e = live ? e0 : A.n - 1;                    // dead lanes shadow the last env (loads only)
+    const uint32_t gid = (uint32_t)(A.first_env + e);
+    const bool run_sub = A.mode == 0 || (A.mode == 1 && A.M.settle_steps > 0);     // block-uniform
+    bool do_reset = reset_decision(A, e, gid);
+    const bool active = do_reset ? (A.M.settle_steps > 0) : (A.mode == 0);         // this env runs a substep
+        const float* sp = A.state + e;
+    const size_t st = (size_t)A.stride;
+
+    if (role == 1) {
+        // ------------------------------------------------------------------------------ RNEA
+        if (!run_sub) return;
+        float q[NU], qd[NU], tgt[NU], fs[NU];
+#pragma unroll
+        for (int i = 0; i < NU; i++) {
+            const float lq = sp[i * st], lqd = sp[(NU + i) * st];
+            q[i] = do_reset ? A.M.home_q[i] : lq; qd[i] = do_reset ? 0.f : lqd;
         }
-        float tgt[NU];
-        int nsub = 0;
+#pragma unroll
+        for (int i = 0; i < NU; i++) tgt[i] = A.M.home_q[i];
+        if (A.mode == 0 && !do_reset) {
+#pragma unroll
+            for (int i = 0; i < NU; i++) tgt[i] = A.action[(size_t)e * NU + i];
+        }
+        gg::robot_rnea<NA, NF, FH>(A.M, q, qd, tgt, fs);
+#pragma unroll
+        for (int i = 0; i < NU; i++) X.fs[i][lane] = fs[i];
+        bar_arrive(1, 96);
+        return;
+    }
+
+    if (role == 0) {
+        // ------------------------------------------------------------------------------ MAIN
+        float q[NU], qd[NU], qa[NU];
+#pragma unroll
+        for (int i = 0; i < NU; i++) {
+            const float lq = sp[i * st], lqd = sp[(NU + i) * st], lqa = sp[(2 * NU + 13 + i) * st];
+            q[i] = do_reset ? A.M.home_q[i] : lq; qd[i] = do_reset ? 0.f : lqd; qa[i] = do_reset ? 0.f : lqa;
+        }
+        if (run_sub) {
+            gg::RobotDyn<NA, NF> D;
+            gg::robot_crba<NA, NF, FH>(A.M, q, D);
+            float L[NU * (NU + 1) / 2], dinv[NU];
+#pragma unroll
+            for (int i = 0; i < NU * (NU + 1) / 2; i++) L[i] = D.Mt[i];
+            gg::chol_packed<NU>(L, dinv);
+            float lsg[NU], laref[NU], lD[NU];
+            const int nlim = gg::joint_limit_rows<NU>(A.M, q, qd, lsg, laref, lD);
+            bar_sync(1, 96);
+#pragma unroll
+            for (int i = 0; i < NU; i++) D.fs[i] = X.fs[i][lane];
+            float as[NV], a[NV];
+            gg::chol_solve_packed<NU>(L, dinv, D.fs, as);
+            gg::StepInfo info;
+            if (!X.coupled[lane]) {
+                gg::robot_block_solve<NU>(D.Mt, as, nlim, lsg, laref, lD, qa, a, A.iterations, A.tol, info);
+            } else {
+                gg::EnvState<NU> s;
+#pragma unroll
+                for (int i = 0; i < NU; i++) { s.q[i] = q[i]; s.qd[i] = qd[i]; s.qacc[i] = qa[i]; }
+                s.cp = gg::mk(X.cube[0][lane], X.cube[1][lane], X.cube[2][lane]);
+                s.cq = gg::mkq(X.cube[3][lane], X.cube[4][lane], X.cube[5][lane], X.cube[6][lane]);
+                s.cv = gg::mk(X.cube[7][lane], X.cube[8][lane], X.cube[9][lane]);
+                s.cw = gg::mk(X.cube[10][lane], X.cube[11][lane], X.cube[12][lane]);
+#pragma unroll
+                for (int i = 0; i < 6; i++) s.qacc[NU + i] = X.cube[13 + i][lane];
+                const gg::M3 cR = gg::qmat(s.cq);
+                float Mc[6], qdv[NV];
+#pragma unroll
+                for (int i = 0; i < NU; i++) qdv[i] = qd[i];
+                gg::cube_free_acc(A.M, s.cv, s.cw, Mc, as + NU, qdv + NU);
+                gg::coupled_block_solve<NA, NF, FH>(A.M, D, s, cR, Mc, as, qdv, nlim, lsg, laref, lD, a, A.iterations, A.tol, info);
+#pragma unroll
+                for (int i = 0; i < 6; i++) X.acube[i][lane] = a[NU + i];
+                X.ncon[lane] = info.ncon;
+            }
+            X.iters[lane] = info.iters;
+            bar_arrive(2, 64);
+            if (active) gg::integrate_robot<NU>(A.M, q, qd, qa, a);
+        }
+        gg::V3 ep; gg::Q4 eq;
+        gg::robot_eef<NA, NF>(A.M, q, ep, eq);
+        {
+            float acc = 0.f;
+#pragma unroll
+            for (int i = 0; i < NU; i++) acc += q[i] + qd[i];
+            X.bad[0][lane] = (run_sub && active && !isfinite(acc)) ? 1 : 0;
+        }
+        X.ep[0][lane] = ep.x; X.ep[1][lane] = ep.y; X.ep[2][lane] = ep.z;
+        __threadfence_block();
+        bar_sync(3, 64);
+        const bool bad = (X.bad[0][lane] | X.bad[1][lane]) != 0;
+        if (__any_sync(0xffffffffu, bad)) {              // diverged env: re-spawn (rare; both roles take this branch together)
+            // NOTE: the home pose goes into a FRESH array selected element-wise; conditionally overwriting q[] in place
+            // was miscompiled by nvcc 12.9 (stack copy of q[3..6] stored unconditionally), see profiles/r01_notes.md.
+            float qh[NU];
+#pragma unroll
+            for (int i = 0; i < NU; i++) qh[i] = bad ? A.M.home_q[i] : q[i];
+            gg::V3 ep2; gg::Q4 eq2;
+            gg::robot_eef<NA, NF>(A.M, qh, ep2, eq2);
+#pragma unroll
+            for (int i = 0; i < NU; i++) { q[i] = qh[i]; qd[i] = bad ? 0.f : qd[i]; qa[i] = bad ? 0.f : qa[i]; }
+            ep = ep2; eq = eq2;
+            X.ep[0][lane] = ep.x; X.ep[1][lane] = ep.y; X.ep[2][lane] = ep.z;
+            do_reset = do_reset || bad;
+            __threadfence_block();
+            bar_sync(3, 64);
+        }
+        if (live) {
+            float* oa = A.obs_agent + (size_t)e * (7 + NF);
+            oa[0] = ep.x; oa[1] = ep.y; oa[2] = ep.z; oa[3] = eq.w; oa[4] = eq.x; oa[5] = eq.y; oa[6] = eq.z;
+#pragma unroll
+            for (int f = 0; f < NF; f++) oa[7 + f] = q[NA + f];
+            if (A.mode != 2 && (active || do_reset)) {
+                float* wp = A.state + e;
+#pragma unroll
+                for (int i = 0; i < NU; i++) { wp[i * st] = q[i]; wp[(NU + i) * st] = qd[i]; wp[(2 * NU + 13 + i) * st] = qa[i]; }
+            }
+        }
+        return;
+    }
+
+    // ---------------------------------------------------------------------------------- CUBE
+    float st_steps = 0.f, st_done = 0.f, st_succ = 0.f, st_ret = 0.f, st_len = 0.f, st_nan = 0.f, st_iter = 0.f, st_con = 0.f;
+    {
+        const float* cpn = sp + (2 * NU) * st;
+        gg::V3 cp = gg::mk(cpn[0], cpn[st], cpn[2 * st]);
+        gg::Q4 cq = gg::mkq(cpn[3 * st], cpn[4 * st], cpn[5 * st], cpn[6 * st]);
+        gg::V3 cv = gg::mk(cpn[7 * st], cpn[8 * st], cpn[9 * st]);
+        gg::V3 cw = gg::mk(cpn[10 * st], cpn[11 * st], cpn[12 * st]);
+        float qac[6];
+#pragma unroll
+        for (int i = 0; i < 6; i++) qac[i] = sp[(2 * NU + 13 + NU + i) * st];
+        int steps = A.step_count[e], epi = A.episode[e];
         if (do_reset) {
             float x, y;
             if (A.cube_xy != nullptr) { x = A.cube_xy[2 * e]; y = A.cube_xy[2 * e + 1]; }
             else gg::spawn_draw(A.M, A.seed, gid, (uint32_t)epi, x, y);
-            gg::env_reset<NU>(A.M, s, x, y);
+            cp = gg::mk(x, y, A.M.spawn_z); cq = gg::ldq(A.M.spawn_quat);
+            cv = gg::mk(0.f, 0.f, 0.f); cw = gg::mk(0.f, 0.f, 0.f);
+#pragma unroll
+            for (int i = 0; i < 6; i++) qac[i] = 0.f;
             epi += 1; steps = 0;
+        }
+        if (run_sub) {
+            float q[NU];
 #pragma unroll
-            for (int i = 0; i < NU; i++) tgt[i] = A.M.home_q[i];
-            nsub = A.M.settle_steps;
-        } else if (A.mode == 0) {
+            for (int i = 0; i < NU; i++) q[i] = do_reset ? A.M.home_q[i] : sp[i * st];
+            gg::RobotDyn<NA, NF> D;
+            gg::robot_pad_frames<NA, NF, FH>(A.M, q, D);
+            const bool coupled = gg::pads_may_touch<NA, NF>(A.M, D, cp);
+            X.coupled[lane] = coupled ? 1 : 0;
+            X.cube[0][lane] = cp.x; X.cube[1][lane] = cp.y; X.cube[2][lane] = cp.z;
+            X.cube[3][lane] = cq.w; X.cube[4][lane] = cq.x; X.cube[5][lane] = cq.y; X.cube[6][lane] = cq.z;
+            X.cube[7][lane] = cv.x; X.cube[8][lane] = cv.y; X.cube[9][lane] = cv.z;
+            X.cube[10][lane] = cw.x; X.cube[11][lane] = cw.y; X.cube[12][lane] = cw.z;
 #pragma unroll
-            for (int i = 0; i < NU; i++) tgt[i] = A.action[(size_t)e * NU + i];
-            nsub = 1;
+            for (int i = 0; i < 6; i++) X.cube[13 + i][lane] = qac[i];
+            bar_arrive(1, 96);
+            float Mc[6], as_c[6], qd_c[6], a_c[6];
+            gg::cube_free_acc(A.M, cv, cw, Mc, as_c, qd_c);
+            gg::StepInfo ic; ic.ncon = 0; ic.iters = 0; ic.grad = 0.f;
+#pragma unroll
+            for (int i = 0; i < 6; i++) a_c[i] = as_c[i];
+            if (!coupled) gg::cube_block_solve(A.M, cp, gg::qmat(cq), Mc, as_c, qd_c, qac, a_c, A.iterations, A.tol, ic);
+            bar_sync(2, 64);
+            if (coupled) {
+#pragma unroll
+                for (int i = 0; i < 6; i++) a_c[i] = X.acube[i][lane];
+                ic.ncon = X.ncon[lane];
+            }
+            const int it = ic.iters > X.iters[lane] ? ic.iters : X.iters[lane];
+            if (active) {
+                gg::integrate_cube(A.M, cp, cq, cv, cw, qac, a_c);
+                st_iter = (float)it; st_con = (float)ic.ncon;
+            }
         }
-        for (int k = 0; k < nsub; k++) {
-            gg::StepInfo info;
-            gg::env_substep<NA, NF, FH>(A.M, s, tgt, A.iterations, A.tol, info);
-            st_iter += (float)info.iters; st_con += (float)info.ncon;
+        {
+            float acc = cp.x + cp.y + cp.z + cq.w + cq.x + cq.y + cq.z + cv.x + cv.y + cv.z + cw.x + cw.y + cw.z;
+            X.bad[1][lane] = (run_sub && active && !isfinite(acc)) ? 1 : 0;
         }
-        if (nsub > 0 && !state_finite<NU>(s)) {       // diverged env: flag, re-spawn, keep the batch alive
-            float x, y;
-            gg::spawn_draw(A.M, A.seed, gid, (uint32_t)epi, x, y);
-            gg::env_reset<NU>(A.M, s, x, y);
-            epi += 1; steps = 0; st_nan = 1.f;
-            do_reset = true;
+        __threadfence_block();
+        bar_sync(3, 64);
+        const bool bad = (X.bad[0][lane] | X.bad[1][lane]) != 0;
+        if (__any_sync(0xffffffffu, bad)) {
+            if (bad) {
+                float x, y;
+                gg::spawn_draw(A.M, A.seed, gid, (uint32_t)epi, x, y);
+                cp = gg::mk(x, y, A.M.spawn_z); cq = gg::ldq(A.M.spawn_quat);
+                cv = gg::mk(0.f, 0.f, 0.f); cw = gg::mk(0.f, 0.f, 0.f);
+#pragma unroll
+                for (int i = 0; i < 6; i++) qac[i] = 0.f;
+                epi += 1; steps = 0; st_nan = 1.f;
+                do_reset = true;
+            }
+            bar_sync(3, 64);
         }
+        const gg::V3 ep = gg::mk(X.ep[0][lane], X.ep[1][lane], X.ep[2][lane]);
         if (A.mode == 0 && !do_reset) { steps += 1; st_steps = 1.f; }
-        float agent[7 + NF], envs[GG_ENV_STATE_DIM], rew; bool succ;
-        gg::env_observe<NA, NF>(A.M, s, agent, envs, rew, succ);
+        const gg::V3 d = ep - cp;
+        const bool succ = cp.z > A.M.success_z;
+        const float rew = succ ? 1.f : 0.f;
         const bool trunc = A.time_limit && steps >= A.M.horizon;
+        if (live) {
+            float* oe = A.obs_env + (size_t)e * GG_ENV_STATE_DIM;
+            oe[0] = cp.x; oe[1] = cp.y; oe[2] = cp.z; oe[3] = cq.w; oe[4] = cq.x; oe[5] = cq.y; oe[6] = cq.z;
+            oe[7] = d.x; oe[8] = d.y; oe[9] = d.z; oe[10] = sqrtf(gg::dot(d, d));
+            if (A.reward) A.reward[e] = rew;
+            if (A.terminated) A.terminated[e] = succ ? 1 : 0;
+            if (A.truncated) A.truncated[e] = trunc ? 1 : 0;
+            if (A.mode != 2) {
+                A.done[e] = (succ || trunc) ? 1 : 0;
+                if (active || do_reset) {
+                    float* wp = A.state + e + (2 * NU) * st;
+                    wp[0] = cp.x; wp[st] = cp.y; wp[2 * st] = cp.z;
+                    wp[3 * st] = cq.w; wp[4 * st] = cq.x; wp[5 * st] = cq.y; wp[6 * st] = cq.z;
+                    wp[7 * st] = cv.x; wp[8 * st] = cv.y; wp[9 * st] = cv.z;
+                    wp[10 * st] = cw.x; wp[11 * st] = cw.y; wp[12 * st] = cw.z;
 #pragma unroll
-        for (int i = 0; i < 7 + NF; i++) A.obs_agent[(size_t)e * (7 + NF) + i] = agent[i];
-#pragma unroll
-        for (int i = 0; i < GG_ENV_STATE_DIM; i++) A.obs_env[(size_t)e * GG_ENV_STATE_DIM + i] = envs[i];
-        if (A.reward) A.reward[e] = rew;
-        if (A.terminated) A.terminated[e] = succ ? 1 : 0;
-        if (A.truncated) A.truncated[e] = trunc ? 1 : 0;
-        if (A.mode != 2) {
-            A.done[e] = (succ || trunc) ? 1 : 0;
-            if (nsub > 0 || do_reset) store_state<NU>(A.state, A.stride, e, s);
-            A.step_count[e] = steps; A.episode[e] = epi;
-            if (A.mode == 0 && (succ || trunc)) { st_done = 1.f; st_succ = succ ? 1.f : 0.f; st_len = (float)steps; }
-            if (A.mode == 0) st_ret = rew;
+                    for (int i = 0; i < 6; i++) wp[(13 + NU + i) * st] = qac[i];
+                }
+                A.step_count[e] = steps; A.episode[e] = epi;
+                if (A.mode == 0 && (succ || trunc)) { st_done = 1.f; st_succ = succ ? 1.f : 0.f; st_len = (float)steps; }
+                if (A.mode == 0) st_ret = rew;
+            }
         }
+        if (!live) { st_steps = st_done = st_succ = st_ret = st_len = st_nan = st_iter = st_con = 0.f; }
     }
     if (A.stats != nullptr && A.mode == 0) {
         float v[8] = {st_steps, st_done, st_succ, st_ret, st_len, st_nan, st_iter, st_con};
-        __shared__ float red[8][kMaxBlock / 32];
+        float mine = 0.f;
 #pragma unroll
         for (int k = 0; k < 8; k++) {
             float x = v[k];
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
-            if ((threadIdx.x & 31) == 0) red[k][threadIdx.x >> 5] = x;
+            if (lane == k) mine = x;
         }
-        __syncthreads();
-        if (threadIdx.x < 8) {
-            float x = 0.f;
-#pragma unroll
-            for (int w = 0; w < (int)(blockDim.x >> 5); w++) x += red[threadIdx.x][w];
-            if (x != 0.f) atomicAdd(&A.stats[threadIdx.x], (double)x);
-        }
+        if (lane < 8 && mine != 0.f) atomicAdd(&A.stats[lane], (double)mine);
     }
 }
 
@@ -239,7 +443,6 @@ struct GgSim {
     GgModel model;
     GgConfig cfg;
     int n, device, stride, kind;        // kind: 0 = <7,2,slide>, 1 = <5,1,hinge>
-    int block;                          // threads per block of step_kernel
     float* state; int32_t* step_count; int32_t* episode;
     uint8_t* done; double* stats;       // library-owned (allocated once in gg_create)
     uint32_t step_index;
@@ -253,10 +456,10 @@ static int launch_step(GgSim* sim, StepArgs& A, gg_stream_t stream) {
     A.auto_reset = sim->cfg.auto_reset; A.time_limit = sim->cfg.time_limit; A.reset_prob = sim->cfg.reset_prob;
     A.seed = sim->cfg.seed; A.first_env = sim->cfg.first_env_id; A.step_index = sim->step_index;
     A.stats = sim->stats;
-    const int grid = (sim->n + sim->block - 1) / sim->block;
+    const int grid = (sim->n + 31) / 32;                 // 32 envs x 3 role warps per block
     GG_CUDA(cudaSetDevice(sim->device));
-    if (sim->kind == 0) step_kernel<7, 2, false><<<grid, sim->block, 0, (cudaStream_t)stream>>>(A);
-    else step_kernel<5, 1, true><<<grid, sim->block, 0, (cudaStream_t)stream>>>(A);
+    if (sim->kind == 0) step_kernel<7, 2, false><<<grid, kBlockThreads, 0, (cudaStream_t)stream>>>(A);
+    else step_kernel<5, 1, true><<<grid, kBlockThreads, 0, (cudaStream_t)stream>>>(A);
     g_launches.fetch_add(1);
     GG_CUDA(cudaGetLastError());
     return 0;
@@ -286,8 +489,6 @@ int gg_create(const GgModel* model, int n_envs, int device, GgSim** out) {
     memset(s, 0, sizeof(*s));
     s->model = *model; s->n = n_envs; s->device = device; s->kind = kind;
     s->stride = (n_envs + 31) / 32 * 32;
-    s->block = kBlock;
-    if (const char* eb = getenv("GG_BLOCK")) { int b = atoi(eb); if (b >= 32 && b <= 256 && b % 32 == 0) s->block = b; }
     s->cfg.solver_iterations = 10; s->cfg.solver_tolerance = 1e-5f;
     cudaError_t e1 = cudaMalloc(&s->done, (size_t)s->stride);
     cudaError_t e2 = cudaMalloc(&s->stats, 8 * sizeof(double));

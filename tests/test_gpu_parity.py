@@ -295,3 +295,30 @@ def test_scripted_grasp_rollout_open_loop(Sim, franka_model):
     assert (s.reshape(rep, K) == s[:K]).all()           # identical inputs in different warps give identical results
     st = sim.stats().cpu().numpy()
     assert st[5] == 0 and st[7] / st[0] > 10            # no non-finite envs; contact-rich on average
+
+
+def test_nonfinite_env_is_respawned_and_neighbours_untouched(Sim, franka_model, oracle64):
+    """A diverged env (non-finite state after the substep) is flagged, re-spawned at the home pose and counted;
+    every other env of the same warp/block steps exactly as if nothing had happened."""
+    n = 96
+    rng = np.random.default_rng(77)
+    Q, QD, T = random_states(franka_model, rng, n, cube_on_ground=True)
+    QA = np.zeros_like(QD)
+    ref = Sim(franka_model, n)
+    q_ref, qd_ref, _ = _one_substep(ref, Q, QD, QA, T)
+    QDb = QD.copy()
+    QDb[5, 2] = np.nan             # robot joint velocity of env 5
+    QDb[40, 10] = np.inf           # cube linear velocity of env 40
+    sim = Sim(franka_model, n)
+    q, qd, _ = _one_substep(sim, Q, QDb, QA, T)
+    ok = np.ones(n, bool); ok[[5, 40]] = False
+    assert (q[ok] == q_ref[ok]).all() and (qd[ok] == qd_ref[ok]).all()               # bit-exact elsewhere
+    for k in (5, 40):
+        assert np.isfinite(q[k]).all() and np.isfinite(qd[k]).all()
+        assert np.abs(q[k, :9] - franka_model.home_q).max() < 1e-6 and np.abs(qd[k]).max() == 0.0
+        assert abs(q[k, 11] - 0.02) < 1e-6
+    a, e, r, t = oracle64.obs(q)
+    assert np.abs(_np(sim.obs_agent) - a).max() < 2e-6 and np.abs(_np(sim.obs_env) - e).max() < 2e-6
+    st = sim.stats().cpu().numpy()
+    assert st[5] == 2 and st[0] == n - 2
+    assert (sim.episode.cpu().numpy()[[5, 40]] == 1).all() and sim.episode.cpu().numpy()[ok].max() == 0

@@ -19,3 +19,7 @@ print("eq",eq.max(),"ev",ev.max())
 k=int(np.argmax(ev)); print(k, info[k], "qd err", (qd-qdo)[k], "dqd ref", (qdo-QD)[k])
 print("qacc gpu", qa[k]); print("qacc ref", qao[k])
 st=sim.stats().cpu().numpy(); print(st)
+np.set_printoptions(precision=4, suppress=True, linewidth=200)
+print("q err by column", np.abs(q-qo).max(0))
+print("qd err by column", np.abs(qd-qdo).max(0))
+print("rows with big err", np.where(np.abs(q-qo).max(1)>1e-3)[0][:40])

@@ -36,5 +36,5 @@ for k in range(a.steps):
 e1.record(); torch.cuda.synchronize()
 warm = e0.elapsed_time(e1) / a.steps
 st = sim.stats().cpu().numpy()
-print(json.dumps({"tag": a.tag, "block": os.environ.get("GG_BLOCK", "default"), "envs": n, "cold_us": round(cold * 1e3, 2), "warm_us": round(warm * 1e3, 2),
+print(json.dumps({"tag": a.tag, "envs": n, "cold_us": round(cold * 1e3, 2), "warm_us": round(warm * 1e3, 2),
                   "cold_Msteps": round(n / cold / 1e3, 1), "warm_Msteps": round(n / warm / 1e3, 1), "iters": round(st[6] / max(st[0], 1), 3)}))
