@@ -54,10 +54,44 @@ template <int NA, int NF> struct RobotDyn {
 // (role specialisation, gg_kernels.cu): both walk the same kinematic chain; robot_crba needs positions only.
 //   robot_crba : frames, composite inertias, Mt = M + armature + dt*(damping + kv)
 //   robot_rnea : velocities / accelerations / link forces, fs = clamp(PD) - damping*qd - bias
-template <int NA, int NF, bool FH>
-GG_HD void robot_crba(const GgModel& M, const float* q, RobotDyn<NA, NF>& D) {
-    constexpr int NU = NA + NF;
+// Per-link temporaries of the rolled chain loops (motion subspace S_l, spatial inertia I_l).  The host harness and the RNEA
+// warp keep them in a plain local array; the MAIN warp of the CUDA kernel passes a view of shared memory ([element][lane], conflict
+// free) so that the dynamically indexed accesses are LDS / STS instead of L1-cached local memory.
+template <int NA> struct LinkStoreLocal {
     SV S[NA]; SI I[NA];
+    GG_HD SV getS(int l) const { return S[l]; }
+    GG_HD void setS(int l, const SV& v) { S[l] = v; }
+    GG_HD SI getI(int l) const { return I[l]; }
+    GG_HD void setI(int l, const SI& v) { I[l] = v; }
+};
+template <int NA> struct LinkStoreStrided {      // b points at this lane's column; element e lives at b[e * STRIDE]
+    enum { STRIDE = 32, FLOATS = NA * 16 };
+    float* b;
+    GG_HD SV getS(int l) const {
+        const float* p = b + l * 16 * STRIDE;
+        SV v; v.a = mk(p[0], p[STRIDE], p[2 * STRIDE]); v.l = mk(p[3 * STRIDE], p[4 * STRIDE], p[5 * STRIDE]);
+        return v;
+    }
+    GG_HD void setS(int l, const SV& v) {
+        float* p = b + l * 16 * STRIDE;
+        p[0] = v.a.x; p[STRIDE] = v.a.y; p[2 * STRIDE] = v.a.z; p[3 * STRIDE] = v.l.x; p[4 * STRIDE] = v.l.y; p[5 * STRIDE] = v.l.z;
+    }
+    GG_HD SI getI(int l) const {
+        const float* p = b + (l * 16 + 6) * STRIDE;
+        SI v; v.m = p[0]; v.h = mk(p[STRIDE], p[2 * STRIDE], p[3 * STRIDE]);
+        v.I.xx = p[4 * STRIDE]; v.I.yy = p[5 * STRIDE]; v.I.zz = p[6 * STRIDE]; v.I.xy = p[7 * STRIDE]; v.I.xz = p[8 * STRIDE]; v.I.yz = p[9 * STRIDE];
+        return v;
+    }
+    GG_HD void setI(int l, const SI& v) {
+        float* p = b + (l * 16 + 6) * STRIDE;
+        p[0] = v.m; p[STRIDE] = v.h.x; p[2 * STRIDE] = v.h.y; p[3 * STRIDE] = v.h.z;
+        p[4 * STRIDE] = v.I.xx; p[5 * STRIDE] = v.I.yy; p[6 * STRIDE] = v.I.zz; p[7 * STRIDE] = v.I.xy; p[8 * STRIDE] = v.I.xz; p[9 * STRIDE] = v.I.yz;
+    }
+};
+
+template <int NA, int NF, bool FH, class LS>
+GG_HD void robot_crba(const GgModel& M, const float* q, RobotDyn<NA, NF>& D, LS& ls) {
+    constexpr int NU = NA + NF;
     Q4 ql = ldq(M.base_quat);
     V3 pl = ld3(M.base_pos);
     M3 Rl = qmat(ql);
@@ -69,8 +103,9 @@ GG_HD void robot_crba(const GgModel& M, const float* q, RobotDyn<NA, NF>& D) {
         ql = qmul_z(qmul(ql, ldq(M.link_quat[l])), c, s);
         Rl = qmat(ql);
         D.jk[l] = Rl.c2; D.jo[l] = pl;
-        S[l].a = Rl.c2; S[l].l = cross(pl, Rl.c2);
-        I[l] = body_inertia(M.link_mass[l], ld3(M.link_com[l]), M.link_inertia[l], Rl, pl);
+        SV Sl; Sl.a = Rl.c2; Sl.l = cross(pl, Rl.c2);
+        ls.setS(l, Sl);
+        ls.setI(l, body_inertia(M.link_mass[l], ld3(M.link_com[l]), M.link_inertia[l], Rl, pl));
     }
     D.lq = ql; D.lp = pl; D.lR = Rl;
     SI Ic; Ic.m = 0.f; Ic.h = mk(0.f, 0.f, 0.f); Ic.I.xx = Ic.I.yy = Ic.I.zz = Ic.I.xy = Ic.I.xz = Ic.I.yz = 0.f;
@@ -96,18 +131,18 @@ GG_HD void robot_crba(const GgModel& M, const float* q, RobotDyn<NA, NF>& D) {
         SI If = body_inertia(M.fing_mass[f], ld3(M.fing_com[f]), M.fing_inertia[f], Rf, pf);
         SV G = apply(If, Sf);
         D.Mt[GG_TRI(NA + f, NA + f)] = sdot(Sf, G);
-#pragma unroll
-        for (int i = 0; i < NA; i++) D.Mt[GG_TRI(NA + f, i)] = sdot(S[i], G);
+        GG_LINK_LOOP
+        for (int i = 0; i < NA; i++) D.Mt[GG_TRI(NA + f, i)] = sdot(ls.getS(i), G);
 #pragma unroll
         for (int g = 0; g < f; g++) D.Mt[GG_TRI(NA + f, NA + g)] = 0.f;
         Ic = Ic + If;
     }
     GG_LINK_LOOP
     for (int l = NA - 1; l >= 0; l--) {
-        Ic = Ic + I[l];
-        SV G = apply(Ic, S[l]);
+        Ic = Ic + ls.getI(l);
+        SV G = apply(Ic, ls.getS(l));
         GG_LINK_LOOP
-        for (int i = 0; i <= l; i++) D.Mt[GG_TRI(l, i)] = sdot(S[i], G);
+        for (int i = 0; i <= l; i++) D.Mt[GG_TRI(l, i)] = sdot(ls.getS(i), G);
     }
     // armature; approximate implicit-fast diagonal
 #pragma unroll
@@ -177,7 +212,8 @@ GG_HD void robot_rnea(const GgModel& M, const float* q, const float* qd, const f
 
 template <int NA, int NF, bool FH>
 GG_HD void robot_dynamics(const GgModel& M, const float* q, const float* qd, const float* target, RobotDyn<NA, NF>& D) {
-    robot_crba<NA, NF, FH>(M, q, D);
+    LinkStoreLocal<NA> ls;
+    robot_crba<NA, NF, FH>(M, q, D, ls);
     robot_rnea<NA, NF, FH>(M, q, qd, target, D.fs);
 }
 
@@ -234,21 +270,23 @@ GG_HD void robot_eef(const GgModel& M, const float* q, V3& ep, Q4& eq) {
 // Narrow phase.  Contact code: 0 = plane-cube, 1+r = plane-robot body r, 4+r = robot body r-cube
 // (r: 0 = last arm link, 1+f = finger f).  Normal points from the first body to the second.
 // ---------------------------------------------------------------------------------------------
-struct Contacts {
-    V3 p[GG_MAX_CONTACTS];
-    V3 n[GG_MAX_CONTACTS];
-    V3 t1[GG_MAX_CONTACTS];       // first tangent (filled by the coupled solver's first pass; t2 = n x t1)
-    float depth[GG_MAX_CONTACTS];
-    int code[GG_MAX_CONTACTS];
+template <int CAP> struct ContactsT {
+    V3 p[CAP];
+    V3 n[CAP];
+    V3 t1[CAP];                   // first tangent (filled by the coupled solver's first pass; t2 = n x t1)
+    float depth[CAP];
+    int code[CAP];
     int count;
 };
+typedef ContactsT<GG_MAX_CONTACTS> Contacts;
+typedef ContactsT<8> Contacts8;   // one geom pair (the warp-cooperative narrow phase collides one pad per lane)
 
-GG_HD void add_contact(Contacts& C, int maxc, V3 p, V3 n, float depth, int code) {
+template <class CT> GG_HD void add_contact(CT& C, int maxc, V3 p, V3 n, float depth, int code) {
     if (C.count < maxc) { C.p[C.count] = p; C.n[C.count] = n; C.depth[C.count] = depth; C.code[C.count] = code; C.count++; }
 }
 
 // plane z = h against a box: the first <= 4 corners (corner-index order) with signed distance <= 0
-GG_HD void plane_box(float h, V3 c, const M3& R, V3 half, int code, int maxc, Contacts& C) {
+template <class CT> GG_HD void plane_box(float h, V3 c, const M3& R, V3 half, int code, int maxc, CT& C) {
     int cnt = 0;
 #pragma unroll
     for (int i = 0; i < 8; i++) {
@@ -282,7 +320,7 @@ GG_HD int clip_poly(const V3* in, int n, V3* out, int ax, float s, float lim) {
 // box A (robot pad) against box B (cube): SAT over 15 axes; A faces win ties, B faces and edge axes
 // must be better by 5 %.  Face case: incident face clipped to the reference face, contacts at the
 // mid-surface; edge case: midpoint of the closest points of the two supporting edges.
-GG_HD void box_box(V3 cA, const M3& RA, V3 hA3, V3 cB, const M3& RB, V3 hB3, int code, int maxc, Contacts& C) {
+template <class CT> GG_HD void box_box(V3 cA, const M3& RA, V3 hA3, V3 cB, const M3& RB, V3 hB3, int code, int maxc, CT& C) {
     const float FUDGE = 1.05f;
     V3 A[3] = {RA.c0, RA.c1, RA.c2}, B[3] = {RB.c0, RB.c1, RB.c2};
     float hA[3] = {hA3.x, hA3.y, hA3.z}, hB[3] = {hB3.x, hB3.y, hB3.z};
@@ -522,12 +560,27 @@ GG_HD void solve_robot_limits(const float* Mt, const float* as, const float* lsg
     iters = it;
 }
 
+// Per-contact temporaries of the cube-plane solver: 29 floats per contact -- J (3 x 6), aref (4), D, u (3), w (3).
+// Local arrays on the host / shared-memory view in the CUDA kernel's CUBE warp (see LinkStoreStrided).
+struct CubeConLocal {
+    float v[4][29];
+    GG_HD float get(int c, int k) const { return v[c][k]; }
+    GG_HD void set(int c, int k, float x) { v[c][k] = x; }
+};
+struct CubeConStrided {
+    enum { STRIDE = 32, FLOATS = 4 * 29 };
+    float* b;
+    GG_HD float get(int c, int k) const { return b[(c * 29 + k) * STRIDE]; }
+    GG_HD void set(int c, int k, float x) { b[(c * 29 + k) * STRIDE] = x; }
+};
+enum { CC_J = 0, CC_AREF = 18, CC_D = 22, CC_U = 23, CC_W = 26 };
+
 // cube block against the plane: contacts i < ncp are live, the rest are masked with D = 0
+template <class CS>
 GG_HD void solve_cube_plane(const GgModel& M, const float* Mc, const float* as, const float* qd, V3 cp, const M3& cR, const V3* p,
-                            const float* depth, int ncp, const float* warm, float* a, int iterations, float tol, float scale,
+                            const float* depth, int ncp, const float* warm, float* a, int iterations, float tol, CS& cs,
                             int& iters, float& gnorm) {
     const float mu = M.friction;
-    float J[4][3][6], aref[4][4], Dk[4], u[4][3], w[4][3];
     float costw = 0.f, costs = 0.f;
 #pragma unroll
     for (int i = 0; i < 6; i++) { float ew = warm[i] - as[i]; costw += 0.5f * Mc[i] * ew * ew; }
@@ -536,36 +589,43 @@ GG_HD void solve_cube_plane(const GgModel& M, const float* Mc, const float* as, 
         // plane normal +z: n = z, t1 = x, t2 = y (= tangent_basis(z)); rows act on [v, w_body]
         V3 r = p[c] - cp;
         V3 a0 = cross(cR.c0, r), a1 = cross(cR.c1, r), a2 = cross(cR.c2, r);
-        J[c][0][0] = 0.f; J[c][0][1] = 0.f; J[c][0][2] = 1.f; J[c][0][3] = a0.z; J[c][0][4] = a1.z; J[c][0][5] = a2.z;
-        J[c][1][0] = 1.f; J[c][1][1] = 0.f; J[c][1][2] = 0.f; J[c][1][3] = a0.x; J[c][1][4] = a1.x; J[c][1][5] = a2.x;
-        J[c][2][0] = 0.f; J[c][2][1] = 1.f; J[c][2][2] = 0.f; J[c][2][3] = a0.y; J[c][2][4] = a1.y; J[c][2][5] = a2.y;
+        float J[3][6];
+        J[0][0] = 0.f; J[0][1] = 0.f; J[0][2] = 1.f; J[0][3] = a0.z; J[0][4] = a1.z; J[0][5] = a2.z;
+        J[1][0] = 1.f; J[1][1] = 0.f; J[1][2] = 0.f; J[1][3] = a0.x; J[1][4] = a1.x; J[1][5] = a2.x;
+        J[2][0] = 0.f; J[2][1] = 1.f; J[2][2] = 0.f; J[2][3] = a0.y; J[2][4] = a1.y; J[2][5] = a2.y;
         float vel[3], uw[3], us[3];
 #pragma unroll
-        for (int k = 0; k < 3; k++) { vel[k] = dotn<6>(J[c][k], qd); uw[k] = dotn<6>(J[c][k], warm); us[k] = dotn<6>(J[c][k], as); }
+        for (int k = 0; k < 3; k++) { vel[k] = dotn<6>(J[k], qd); uw[k] = dotn<6>(J[k], warm); us[k] = dotn<6>(J[k], as); }
         const bool live = c < ncp;
-        float imp = 1.f, ar = 0.f;
+        float imp = 1.f, ar[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) imp_aref(M, -depth[c], rowval(vel, mu, k), imp, ar[k]);
+        const float Dk = live ? gg_rcp(fmaxf(M.minval, 2.f * mu * mu * (1.f - imp) / imp * M.cube_invweight * (1.f + mu * mu))) : 0.f;
 #pragma unroll
         for (int k = 0; k < 4; k++) {
-            imp_aref(M, -depth[c], rowval(vel, mu, k), imp, ar);
-            aref[c][k] = ar;
-        }
-        Dk[c] = live ? gg_rcp(fmaxf(M.minval, 2.f * mu * mu * (1.f - imp) / imp * M.cube_invweight * (1.f + mu * mu))) : 0.f;
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            float jw = rowval(uw, mu, k) - aref[c][k], js = rowval(us, mu, k) - aref[c][k];
-            if (jw < 0.f) costw += 0.5f * Dk[c] * jw * jw;
-            if (js < 0.f) costs += 0.5f * Dk[c] * js * js;
+            float jw = rowval(uw, mu, k) - ar[k], js = rowval(us, mu, k) - ar[k];
+            if (jw < 0.f) costw += 0.5f * Dk * jw * jw;
+            if (js < 0.f) costs += 0.5f * Dk * js * js;
         }
 #pragma unroll
-        for (int k = 0; k < 3; k++) { u[c][k] = uw[k]; w[c][k] = us[k]; }
+        for (int k = 0; k < 3; k++)
+#pragma unroll
+            for (int i = 0; i < 6; i++) cs.set(c, CC_J + k * 6 + i, J[k][i]);
+#pragma unroll
+        for (int k = 0; k < 4; k++) cs.set(c, CC_AREF + k, ar[k]);
+        cs.set(c, CC_D, Dk);
+#pragma unroll
+        for (int k = 0; k < 3; k++) { cs.set(c, CC_U + k, uw[k]); cs.set(c, CC_W + k, us[k]); }
     }
     const bool usew = costw < costs;
 #pragma unroll
     for (int i = 0; i < 6; i++) a[i] = usew ? warm[i] : as[i];
-    GG_CON_LOOP
-    for (int c = 0; c < 4; c++)
+    if (!usew) {
+        GG_CON_LOOP
+        for (int c = 0; c < 4; c++)
 #pragma unroll
-        for (int k = 0; k < 3; k++) u[c][k] = usew ? u[c][k] : w[c][k];
+            for (int k = 0; k < 3; k++) cs.set(c, CC_U + k, cs.get(c, CC_W + k));
+    }
     int it = 0;
     for (; it < iterations; it++) {
         float H[21], g[6], dinv[6], sd[6];
@@ -575,11 +635,21 @@ GG_HD void solve_cube_plane(const GgModel& M, const float* Mc, const float* as, 
         for (int i = 0; i < 6; i++) { H[GG_TRI(i, i)] = Mc[i]; g[i] = Mc[i] * (a[i] - as[i]); }
         GG_CON_LOOP
         for (int c = 0; c < 4; c++) {
+            float J[3][6], u[3], ar[4];
+#pragma unroll
+            for (int k = 0; k < 3; k++)
+#pragma unroll
+                for (int i = 0; i < 6; i++) J[k][i] = cs.get(c, CC_J + k * 6 + i);
+#pragma unroll
+            for (int k = 0; k < 3; k++) u[k] = cs.get(c, CC_U + k);
+#pragma unroll
+            for (int k = 0; k < 4; k++) ar[k] = cs.get(c, CC_AREF + k);
+            const float Dk = cs.get(c, CC_D);
             float Wnn = 0.f, Wn1 = 0.f, W11 = 0.f, Wn2 = 0.f, W22 = 0.f, gn = 0.f, g1 = 0.f, g2 = 0.f;
 #pragma unroll
             for (int k = 0; k < 4; k++) {
-                float jar = rowval(u[c], mu, k) - aref[c][k];
-                float on = jar < 0.f ? Dk[c] : 0.f;
+                float jar = rowval(u, mu, k) - ar[k];
+                float on = jar < 0.f ? Dk : 0.f;
                 float sm = (k & 1) ? mu : -mu;
                 Wnn += on; gn += on * jar;
                 if (k < 2) { Wn1 += on * sm; W11 += on * mu * mu; g1 += on * jar * sm; }
@@ -588,15 +658,15 @@ GG_HD void solve_cube_plane(const GgModel& M, const float* Mc, const float* as, 
             float Pn[6], P1[6], P2[6];
 #pragma unroll
             for (int i = 0; i < 6; i++) {
-                g[i] += J[c][0][i] * gn + J[c][1][i] * g1 + J[c][2][i] * g2;
-                Pn[i] = Wnn * J[c][0][i] + Wn1 * J[c][1][i] + Wn2 * J[c][2][i];
-                P1[i] = Wn1 * J[c][0][i] + W11 * J[c][1][i];
-                P2[i] = Wn2 * J[c][0][i] + W22 * J[c][2][i];
+                g[i] += J[0][i] * gn + J[1][i] * g1 + J[2][i] * g2;
+                Pn[i] = Wnn * J[0][i] + Wn1 * J[1][i] + Wn2 * J[2][i];
+                P1[i] = Wn1 * J[0][i] + W11 * J[1][i];
+                P2[i] = Wn2 * J[0][i] + W22 * J[2][i];
             }
 #pragma unroll
             for (int i = 0; i < 6; i++)
 #pragma unroll
-                for (int j = 0; j <= i; j++) H[GG_TRI(i, j)] += J[c][0][i] * Pn[j] + J[c][1][i] * P1[j] + J[c][2][i] * P2[j];
+                for (int j = 0; j <= i; j++) H[GG_TRI(i, j)] += J[0][i] * Pn[j] + J[1][i] * P1[j] + J[2][i] * P2[j];
         }
         gnorm = newton_residual<6>(g, H, a);
         if (gnorm < tol) break;
@@ -610,28 +680,40 @@ GG_HD void solve_cube_plane(const GgModel& M, const float* Mc, const float* as, 
         GG_CON_LOOP
         for (int c = 0; c < 4; c++)
 #pragma unroll
-            for (int k = 0; k < 3; k++) w[c][k] = dotn<6>(J[c][k], sd);
+            for (int k = 0; k < 3; k++) {
+                float r = 0.f;
+#pragma unroll
+                for (int i = 0; i < 6; i++) r += cs.get(c, CC_J + k * 6 + i) * sd[i];
+                cs.set(c, CC_W + k, r);
+            }
         LineSearch L; L.begin();
         for (;;) {
             float d1 = q1 + L.al * q2, d2 = q2;
             GG_CON_LOOP
-            for (int c = 0; c < 4; c++)
+            for (int c = 0; c < 4; c++) {
+                const float u[3] = {cs.get(c, CC_U), cs.get(c, CC_U + 1), cs.get(c, CC_U + 2)};
+                const float w[3] = {cs.get(c, CC_W), cs.get(c, CC_W + 1), cs.get(c, CC_W + 2)};
+                const float Dk = cs.get(c, CC_D);
 #pragma unroll
                 for (int k = 0; k < 4; k++) {
-                    float jv = rowval(w[c], mu, k);
-                    float x = rowval(u[c], mu, k) - aref[c][k] + L.al * jv;
-                    if (x < 0.f) { d1 += Dk[c] * x * jv; d2 += Dk[c] * jv * jv; }
+                    float jv = rowval(w, mu, k);
+                    float x = rowval(u, mu, k) - cs.get(c, CC_AREF + k) + L.al * jv;
+                    if (x < 0.f) { d1 += Dk * x * jv; d2 += Dk * jv * jv; }
                 }
+            }
             if (!L.next(d1, d2)) break;
         }
         int changed = 0;
         GG_CON_LOOP
         for (int c = 0; c < 4; c++) {
-            float un[3] = {u[c][0] + L.al * w[c][0], u[c][1] + L.al * w[c][1], u[c][2] + L.al * w[c][2]};
+            const float u[3] = {cs.get(c, CC_U), cs.get(c, CC_U + 1), cs.get(c, CC_U + 2)};
+            float un[3] = {u[0] + L.al * cs.get(c, CC_W), u[1] + L.al * cs.get(c, CC_W + 1), u[2] + L.al * cs.get(c, CC_W + 2)};
 #pragma unroll
-            for (int k = 0; k < 4; k++)
-                changed += (c < ncp) && ((rowval(u[c], mu, k) - aref[c][k] < 0.f) != (rowval(un, mu, k) - aref[c][k] < 0.f));
-            u[c][0] = un[0]; u[c][1] = un[1]; u[c][2] = un[2];
+            for (int k = 0; k < 4; k++) {
+                const float ar = cs.get(c, CC_AREF + k);
+                changed += (c < ncp) && ((rowval(u, mu, k) - ar < 0.f) != (rowval(un, mu, k) - ar < 0.f));
+            }
+            cs.set(c, CC_U, un[0]); cs.set(c, CC_U + 1, un[1]); cs.set(c, CC_U + 2, un[2]);
         }
 #pragma unroll
         for (int i = 0; i < 6; i++) a[i] += L.al * sd[i];
@@ -1001,8 +1083,9 @@ GG_HD int cube_plane_points(const GgModel& M, V3 cp, const M3& cR, V3* pc, float
 }
 
 // cube block on the decoupled path: plane contacts only
+template <class CS>
 GG_HD void cube_block_solve(const GgModel& M, V3 cp, const M3& cR, const float* Mc, const float* as_c, const float* qd_c,
-                            const float* warm_c, float* a_c, int iterations, float tol, StepInfo& info) {
+                            const float* warm_c, float* a_c, int iterations, float tol, CS& cs, StepInfo& info) {
     V3 pc[4]; float dc[4];
     const int ncp = cube_plane_points(M, cp, cR, pc, dc);
     info.ncon = ncp; info.iters = 0; info.grad = 0.f;
@@ -1010,7 +1093,7 @@ GG_HD void cube_block_solve(const GgModel& M, V3 cp, const M3& cR, const float* 
 #pragma unroll
         for (int i = 0; i < 6; i++) a_c[i] = as_c[i];
     } else {
-        solve_cube_plane(M, Mc, as_c, qd_c, cp, cR, pc, dc, ncp, warm_c, a_c, iterations, tol, 1.f, info.iters, info.grad);
+        solve_cube_plane(M, Mc, as_c, qd_c, cp, cR, pc, dc, ncp, warm_c, a_c, iterations, tol, cs, info.iters, info.grad);
     }
 }
 
@@ -1099,8 +1182,9 @@ GG_HD void env_substep(const GgModel& M, EnvState<NA + NF>& s, const float* targ
     if (!pads_may_touch<NA, NF>(M, D, s.cp)) {
         // ---- decoupled fast path: robot block (limits only) and cube block (plane contacts only)
         StepInfo ir, ic;
+        CubeConLocal cs;
         robot_block_solve<NU>(D.Mt, as, nlim, lsg, laref, lD, s.qacc, a, iterations, tol, ir);
-        cube_block_solve(M, s.cp, cR, Mc, as + NU, qdv + NU, s.qacc + NU, a + NU, iterations, tol, ic);
+        cube_block_solve(M, s.cp, cR, Mc, as + NU, qdv + NU, s.qacc + NU, a + NU, iterations, tol, cs, ic);
         info.ncon = ic.ncon;
         info.iters = ic.iters > ir.iters ? ic.iters : ir.iters;
         info.grad = fmaxf(ir.grad, ic.grad);

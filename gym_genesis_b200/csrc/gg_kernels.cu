@@ -14,6 +14,7 @@
 
 #include "gg_b200.h"
 #include "gg_env.cuh"
+#include "gg_coop.cuh"
 
 namespace {
 
@@ -79,17 +80,24 @@ template <int NU> __device__ __forceinline__ void store_state(float* __restrict_
 // ------------------------------------------------------------------------------------------------
 // step_kernel: ROLE-SPECIALISED warps.  A block owns 32 consecutive envs and runs three warps on them;
 // lane = env, warp = role:
-//   warp 0  MAIN : kinematics + CRBA + Cholesky, smooth acceleration, joint-limit rows, robot-block Newton solve (or the
-//                  coupled solve when a pad can touch something), robot integration, end-effector pose, agent_pos
+//   warp 0  MAIN : kinematics + CRBA + Cholesky, smooth acceleration, joint-limit rows, robot-block Newton solve,
+//                  robot integration, end-effector pose, agent_pos
 //   warp 1  RNEA : velocities / accelerations / link forces of the same chain, PD torque -> fs = tau - bias
 //   warp 2  CUBE : pad broad phase, cube-plane contacts + cube-block Newton solve, cube integration, environment_state,
 //                  reward / terminated / truncated / done, counters, episode statistics
 // The three chains are independent until the points marked by the named barriers below, so the latency of one env.step
-// is the longest role (~5 k instructions) instead of their sum (~14 k), and 16384 envs put 2.6 warps on every scheduler
-// instead of 0.9.  Exchange goes through shared memory ([field][lane], conflict free):
-//   barrier 1 (96 threads): RNEA and CUBE arrive, MAIN waits      -- fs, coupled flag, cube state
-//   barrier 2 (64 threads): MAIN arrives, CUBE waits              -- cube acceleration of coupled envs, solver statistics
+// is the longest role instead of their sum, and 16384 envs put 2.6 warps on every scheduler instead of 0.9.
+// Exchange goes through shared memory ([field][lane], conflict free):
+//   barrier 1 (96 threads): CUBE arrives, RNEA and MAIN wait      -- fs, coupled flags, cube state
+//   barrier 2 (64 threads): MAIN arrives, CUBE waits              -- solver statistics of the robot block
 //   barrier 3 (64 threads): MAIN and CUBE wait                    -- end-effector position, non-finite flags
+//
+// Envs whose pads may touch the cube or the plane ("coupled", decided by the CUBE warp's broad phase) leave the
+// thread-per-env mapping: after barrier 1 the three warps of the block become three solver teams and work through the
+// block's coupled envs ONE WARP PER ENV (gg_coop.cuh; 10 KB of shared memory per team), MAIN lanes publishing their env's
+// dynamics through shared memory (barriers 4 / 5 bracket every round of three envs).  Blocks without coupled envs never
+// execute that code.  (Tried and measured, profiles/r01_notes.md: team buffers in a global scratch slice -- 1.5x slower
+// teams; a second, device-launched kernel for the coupled envs (CUDA dynamic parallelism tail launch) -- 2.6x slower.)
 // ------------------------------------------------------------------------------------------------
 constexpr int kBlockThreads = 96;
 
@@ -109,10 +117,10 @@ __device__ __forceinline__ void bar_arrive(int id, int nthreads) {
 template <int NU> struct Xchg {
     float fs[NU][32];         // RNEA -> MAIN
     float cube[19][32];       // CUBE -> MAIN: cp3 cq4 cv3 cw3 qacc6 (the state a coupled solve starts from)
-    float acube[6][32];       // MAIN -> CUBE: cube acceleration of coupled envs
+    float aout[NU + 6][32];   // solver teams -> MAIN / CUBE: acceleration of coupled envs
     float ep[3][32];          // MAIN -> CUBE: end-effector position after the step
     int coupled[32];          // CUBE -> MAIN
-    int iters[32], ncon[32];  // MAIN -> CUBE (statistics)
+    int iters[32], ncon[32];  // MAIN / teams -> CUBE (statistics)
     int bad[2][32];           // non-finite flags: [0] robot (MAIN), [1] cube (CUBE)
 };
 
@@ -131,10 +139,30 @@ __device__ __forceinline__ bool reset_decision(const StepArgs& A, int e, uint32_
     return r;
 }
 
+// one round of the solver-team protocol for the warp `team`: solve the (r0 + team)-th deferred env of the block
+template <int NA, int NF, bool FH, int NU>
+__device__ __forceinline__ void team_round(const StepArgs& A, gg::TeamWork<NA, NF>* TW, gg::TeamBuf<NU + 6>* TB, Xchg<NU>& X, unsigned cm,
+                                           int ncpl, int r0, int team, int lane) {
+    const int k = r0 + team;
+    if (k < ncpl) {
+        const int el = __fns(cm, 0, k + 1);
+        int its, nc;
+        gg::team_solve<NA, NF, FH>(A.M, TW[team], TB[team], A.iterations, A.tol, lane, &X.aout[0][el], 32, its, nc);
+        if (lane == 0) { X.iters[el] = its; X.ncon[el] = nc; }
+    }
+    __threadfence_block();
+}
+
 template <int NA, int NF, bool FH>
 __global__ void __launch_bounds__(kBlockThreads, GG_MINBLOCKS) step_kernel(const __grid_constant__ StepArgs A) {
+    constexpr bool TEAMS = true;
     constexpr int NU = NA + NF, NV = NU + 6;
     __shared__ Xchg<NU> X;
+    __shared__ gg::TeamWork<NA, NF> TW[3];
+    __shared__ gg::TeamBuf<NV> TB[3];
+    // until the first team round the team buffers double as scratch for the rolled loops of MAIN (per-link S, I) and CUBE
+    // (per-contact J, aref, D, u, w)
+    static_assert(sizeof(TB) >= (gg::LinkStoreStrided<NA>::FLOATS + gg::CubeConStrided::FLOATS) * 32 * sizeof(float), "team buffers too small for the scratch views");
     const int lane = threadIdx.x & 31, role = threadIdx.x >> 5;
     const int e0 = blockIdx.x * 32 + lane;
     const bool live = e0 < A.n;
@@ -143,7 +171,7 @@ __global__ void __launch_bounds__(kBlockThreads, GG_MINBLOCKS) step_kernel(const
     const bool run_sub = A.mode == 0 || (A.mode == 1 && A.M.settle_steps > 0);     // block-uniform
     bool do_reset = reset_decision(A, e, gid);
     const bool active = do_reset ? (A.M.settle_steps > 0) : (A.mode == 0);         // this env runs a substep
-        const float* sp = A.state + e;
+    const float* sp = A.state + e;
     const size_t st = (size_t)A.stride;
 
     if (role == 1) {
@@ -164,7 +192,17 @@ __global__ void __launch_bounds__(kBlockThreads, GG_MINBLOCKS) step_kernel(const
         gg::robot_rnea<NA, NF, FH>(A.M, q, qd, tgt, fs);
 #pragma unroll
         for (int i = 0; i < NU; i++) X.fs[i][lane] = fs[i];
-        bar_arrive(1, 96);
+        if (!TEAMS) { bar_arrive(1, 96); return; }
+        __threadfence_block();
+        bar_sync(1, 96);
+        const unsigned cm = __ballot_sync(0xffffffffu, X.coupled[lane] != 0);
+        const int ncpl = __popc(cm);
+#pragma unroll 1
+        for (int r0 = 0; r0 < ncpl; r0 += 3) {            // solver team 1 (see MAIN for the round protocol)
+            bar_sync(4, 96);
+            team_round<NA, NF, FH, NU>(A, TW, TB, X, cm, ncpl, r0, 1, lane);
+            bar_sync(5, 96);
+        }
         return;
     }
 
@@ -176,9 +214,15 @@ __global__ void __launch_bounds__(kBlockThreads, GG_MINBLOCKS) step_kernel(const
             const float lq = sp[i * st], lqd = sp[(NU + i) * st], lqa = sp[(2 * NU + 13 + i) * st];
             q[i] = do_reset ? A.M.home_q[i] : lq; qd[i] = do_reset ? 0.f : lqd; qa[i] = do_reset ? 0.f : lqa;
         }
+        bool commit = live;
         if (run_sub) {
             gg::RobotDyn<NA, NF> D;
-            gg::robot_crba<NA, NF, FH>(A.M, q, D);
+            {
+                // per-link temporaries in the (still idle) team buffers: [element][lane] view of shared memory
+                gg::LinkStoreStrided<NA> ls;
+                ls.b = reinterpret_cast<float*>(TB) + lane;
+                gg::robot_crba<NA, NF, FH>(A.M, q, D, ls);
+            }
             float L[NU * (NU + 1) / 2], dinv[NU];
 #pragma unroll
             for (int i = 0; i < NU * (NU + 1) / 2; i++) L[i] = D.Mt[i];
@@ -188,32 +232,62 @@ __global__ void __launch_bounds__(kBlockThreads, GG_MINBLOCKS) step_kernel(const
             bar_sync(1, 96);
 #pragma unroll
             for (int i = 0; i < NU; i++) D.fs[i] = X.fs[i][lane];
-            float as[NV], a[NV];
+            float as[NU], a[NU];
             gg::chol_solve_packed<NU>(L, dinv, D.fs, as);
             gg::StepInfo info;
-            if (!X.coupled[lane]) {
-                gg::robot_block_solve<NU>(D.Mt, as, nlim, lsg, laref, lD, qa, a, A.iterations, A.tol, info);
-            } else {
-                gg::EnvState<NU> s;
+            info.ncon = 0; info.iters = 0; info.grad = 0.f;
+            const bool coupled = X.coupled[lane] != 0;
 #pragma unroll
-                for (int i = 0; i < NU; i++) { s.q[i] = q[i]; s.qd[i] = qd[i]; s.qacc[i] = qa[i]; }
-                s.cp = gg::mk(X.cube[0][lane], X.cube[1][lane], X.cube[2][lane]);
-                s.cq = gg::mkq(X.cube[3][lane], X.cube[4][lane], X.cube[5][lane], X.cube[6][lane]);
-                s.cv = gg::mk(X.cube[7][lane], X.cube[8][lane], X.cube[9][lane]);
-                s.cw = gg::mk(X.cube[10][lane], X.cube[11][lane], X.cube[12][lane]);
+            for (int i = 0; i < NU; i++) a[i] = as[i];
+            if (commit && !coupled) gg::robot_block_solve<NU>(D.Mt, as, nlim, lsg, laref, lD, qa, a, A.iterations, A.tol, info);
+            if (TEAMS) {
+                const unsigned cm = __ballot_sync(0xffffffffu, coupled);
+                const int ncpl = __popc(cm);
+                const int myrank = __popc(cm & ((1u << lane) - 1u));
+#pragma unroll 1
+                for (int r0 = 0; r0 < ncpl; r0 += 3) {
+                    // round protocol: the MAIN lanes of the next three coupled envs publish their dynamics, barrier 4,
+                    // every warp solves one env (team t = role takes the (r0 + t)-th coupled env), barrier 5
+                    if (coupled && myrank >= r0 && myrank < r0 + 3) {
+                        gg::TeamWork<NA, NF>& W = TW[myrank - r0];
 #pragma unroll
-                for (int i = 0; i < 6; i++) s.qacc[NU + i] = X.cube[13 + i][lane];
-                const gg::M3 cR = gg::qmat(s.cq);
-                float Mc[6], qdv[NV];
+                        for (int i = 0; i < NU * (NU + 1) / 2; i++) W.Mt[i] = D.Mt[i];
 #pragma unroll
-                for (int i = 0; i < NU; i++) qdv[i] = qd[i];
-                gg::cube_free_acc(A.M, s.cv, s.cw, Mc, as + NU, qdv + NU);
-                gg::coupled_block_solve<NA, NF, FH>(A.M, D, s, cR, Mc, as, qdv, nlim, lsg, laref, lD, a, A.iterations, A.tol, info);
+                        for (int i = 0; i < NU; i++) {
+                            W.as[i] = as[i]; W.qd[i] = qd[i]; W.warm[i] = qa[i]; W.lsg[i] = lsg[i]; W.laref[i] = laref[i]; W.lD[i] = lD[i];
+                        }
 #pragma unroll
-                for (int i = 0; i < 6; i++) X.acube[i][lane] = a[NU + i];
-                X.ncon[lane] = info.ncon;
+                        for (int i = 0; i < NA; i++) {
+                            W.jk[i][0] = D.jk[i].x; W.jk[i][1] = D.jk[i].y; W.jk[i][2] = D.jk[i].z;
+                            W.jo[i][0] = D.jo[i].x; W.jo[i][1] = D.jo[i].y; W.jo[i][2] = D.jo[i].z;
+                        }
+#pragma unroll
+                        for (int f = 0; f < NF; f++) {
+                            W.fk[f][0] = D.fk[f].x; W.fk[f][1] = D.fk[f].y; W.fk[f][2] = D.fk[f].z;
+                            W.fo[f][0] = D.fo[f].x; W.fo[f][1] = D.fo[f].y; W.fo[f][2] = D.fo[f].z;
+                            W.fR[f][0] = D.fR[f].c0.x; W.fR[f][1] = D.fR[f].c0.y; W.fR[f][2] = D.fR[f].c0.z;
+                            W.fR[f][3] = D.fR[f].c1.x; W.fR[f][4] = D.fR[f].c1.y; W.fR[f][5] = D.fR[f].c1.z;
+                            W.fR[f][6] = D.fR[f].c2.x; W.fR[f][7] = D.fR[f].c2.y; W.fR[f][8] = D.fR[f].c2.z;
+                            W.fp[f][0] = D.fp[f].x; W.fp[f][1] = D.fp[f].y; W.fp[f][2] = D.fp[f].z;
+                        }
+                        W.lR[0] = D.lR.c0.x; W.lR[1] = D.lR.c0.y; W.lR[2] = D.lR.c0.z;
+                        W.lR[3] = D.lR.c1.x; W.lR[4] = D.lR.c1.y; W.lR[5] = D.lR.c1.z;
+                        W.lR[6] = D.lR.c2.x; W.lR[7] = D.lR.c2.y; W.lR[8] = D.lR.c2.z;
+                        W.lp[0] = D.lp.x; W.lp[1] = D.lp.y; W.lp[2] = D.lp.z;
+#pragma unroll
+                        for (int i = 0; i < 19; i++) W.cube[i] = X.cube[i][lane];
+                    }
+                    __threadfence_block();
+                    bar_sync(4, 96);
+                    team_round<NA, NF, FH, NU>(A, TW, TB, X, cm, ncpl, r0, 0, lane);
+                    bar_sync(5, 96);
+                }
+                if (coupled) {
+#pragma unroll
+                    for (int i = 0; i < NU; i++) a[i] = X.aout[i][lane];
+                }
             }
-            X.iters[lane] = info.iters;
+            if (!(TEAMS && coupled)) X.iters[lane] = info.iters;
             bar_arrive(2, 64);
             if (active) gg::integrate_robot<NU>(A.M, q, qd, qa, a);
         }
@@ -223,7 +297,7 @@ __global__ void __launch_bounds__(kBlockThreads, GG_MINBLOCKS) step_kernel(const
             float acc = 0.f;
 #pragma unroll
             for (int i = 0; i < NU; i++) acc += q[i] + qd[i];
-            X.bad[0][lane] = (run_sub && active && !isfinite(acc)) ? 1 : 0;
+            X.bad[0][lane] = (run_sub && active && commit && !isfinite(acc)) ? 1 : 0;
         }
         X.ep[0][lane] = ep.x; X.ep[1][lane] = ep.y; X.ep[2][lane] = ep.z;
         __threadfence_block();
@@ -245,7 +319,7 @@ __global__ void __launch_bounds__(kBlockThreads, GG_MINBLOCKS) step_kernel(const
             __threadfence_block();
             bar_sync(3, 64);
         }
-        if (live) {
+        if (commit) {
             float* oa = A.obs_agent + (size_t)e * (7 + NF);
             oa[0] = ep.x; oa[1] = ep.y; oa[2] = ep.z; oa[3] = eq.w; oa[4] = eq.x; oa[5] = eq.y; oa[6] = eq.z;
 #pragma unroll
@@ -281,13 +355,17 @@ __global__ void __launch_bounds__(kBlockThreads, GG_MINBLOCKS) step_kernel(const
             for (int i = 0; i < 6; i++) qac[i] = 0.f;
             epi += 1; steps = 0;
         }
+        bool commit = live;
         if (run_sub) {
-            float q[NU];
+            bool coupled;
+            {
+                float q[NU];
 #pragma unroll
-            for (int i = 0; i < NU; i++) q[i] = do_reset ? A.M.home_q[i] : sp[i * st];
-            gg::RobotDyn<NA, NF> D;
-            gg::robot_pad_frames<NA, NF, FH>(A.M, q, D);
-            const bool coupled = gg::pads_may_touch<NA, NF>(A.M, D, cp);
+                for (int i = 0; i < NU; i++) q[i] = do_reset ? A.M.home_q[i] : sp[i * st];
+                gg::RobotDyn<NA, NF> D;
+                gg::robot_pad_frames<NA, NF, FH>(A.M, q, D);
+                coupled = live && gg::pads_may_touch<NA, NF>(A.M, D, cp);
+            }
             X.coupled[lane] = coupled ? 1 : 0;
             X.cube[0][lane] = cp.x; X.cube[1][lane] = cp.y; X.cube[2][lane] = cp.z;
             X.cube[3][lane] = cq.w; X.cube[4][lane] = cq.x; X.cube[5][lane] = cq.y; X.cube[6][lane] = cq.z;
@@ -301,11 +379,25 @@ __global__ void __launch_bounds__(kBlockThreads, GG_MINBLOCKS) step_kernel(const
             gg::StepInfo ic; ic.ncon = 0; ic.iters = 0; ic.grad = 0.f;
 #pragma unroll
             for (int i = 0; i < 6; i++) a_c[i] = as_c[i];
-            if (!coupled) gg::cube_block_solve(A.M, cp, gg::qmat(cq), Mc, as_c, qd_c, qac, a_c, A.iterations, A.tol, ic);
+            if (commit && !coupled) {
+                gg::CubeConStrided cs;                        // per-contact temporaries behind MAIN's slice of the team buffers
+                cs.b = reinterpret_cast<float*>(TB) + gg::LinkStoreStrided<NA>::FLOATS * 32 + lane;
+                gg::cube_block_solve(A.M, cp, gg::qmat(cq), Mc, as_c, qd_c, qac, a_c, A.iterations, A.tol, cs, ic);
+            }
+            if (TEAMS) {
+                const unsigned cm = __ballot_sync(0xffffffffu, coupled);
+                const int ncpl = __popc(cm);
+#pragma unroll 1
+                for (int r0 = 0; r0 < ncpl; r0 += 3) {        // solver team 2 (see MAIN for the round protocol)
+                    bar_sync(4, 96);
+                    team_round<NA, NF, FH, NU>(A, TW, TB, X, cm, ncpl, r0, 2, lane);
+                    bar_sync(5, 96);
+                }
+            }
             bar_sync(2, 64);
-            if (coupled) {
+            if (TEAMS && coupled) {
 #pragma unroll
-                for (int i = 0; i < 6; i++) a_c[i] = X.acube[i][lane];
+                for (int i = 0; i < 6; i++) a_c[i] = X.aout[NU + i][lane];
                 ic.ncon = X.ncon[lane];
             }
             const int it = ic.iters > X.iters[lane] ? ic.iters : X.iters[lane];
@@ -316,7 +408,7 @@ __global__ void __launch_bounds__(kBlockThreads, GG_MINBLOCKS) step_kernel(const
         }
         {
             float acc = cp.x + cp.y + cp.z + cq.w + cq.x + cq.y + cq.z + cv.x + cv.y + cv.z + cw.x + cw.y + cw.z;
-            X.bad[1][lane] = (run_sub && active && !isfinite(acc)) ? 1 : 0;
+            X.bad[1][lane] = (run_sub && active && commit && !isfinite(acc)) ? 1 : 0;
         }
         __threadfence_block();
         bar_sync(3, 64);
@@ -340,7 +432,7 @@ __global__ void __launch_bounds__(kBlockThreads, GG_MINBLOCKS) step_kernel(const
         const bool succ = cp.z > A.M.success_z;
         const float rew = succ ? 1.f : 0.f;
         const bool trunc = A.time_limit && steps >= A.M.horizon;
-        if (live) {
+        if (commit) {
             float* oe = A.obs_env + (size_t)e * GG_ENV_STATE_DIM;
             oe[0] = cp.x; oe[1] = cp.y; oe[2] = cp.z; oe[3] = cq.w; oe[4] = cq.x; oe[5] = cq.y; oe[6] = cq.z;
             oe[7] = d.x; oe[8] = d.y; oe[9] = d.z; oe[10] = sqrtf(gg::dot(d, d));
@@ -363,7 +455,7 @@ __global__ void __launch_bounds__(kBlockThreads, GG_MINBLOCKS) step_kernel(const
                 if (A.mode == 0) st_ret = rew;
             }
         }
-        if (!live) { st_steps = st_done = st_succ = st_ret = st_len = st_nan = st_iter = st_con = 0.f; }
+        if (!commit) { st_steps = st_done = st_succ = st_ret = st_len = st_nan = st_iter = st_con = 0.f; }
     }
     if (A.stats != nullptr && A.mode == 0) {
         float v[8] = {st_steps, st_done, st_succ, st_ret, st_len, st_nan, st_iter, st_con};

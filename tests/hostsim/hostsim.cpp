@@ -64,3 +64,20 @@ void hs_observe(const GgModel* M, int n, const float* q, float* agent, float* en
 }
 void hs_spawn(const GgModel* M, uint64_t seed, uint32_t gid, uint32_t episode, float* xy) { gg::spawn_draw(*M, seed, gid, episode, xy[0], xy[1]); }
 }
+
+// diagnostic: the kernel's body-level broad phase ("coupled" flag) for n env-major states
+extern "C" void hs_pads_may_touch(const GgModel* M, int n, const float* q, uint8_t* out) {
+    for (int e = 0; e < n; e++) {
+        if (M->n_arm == 7) {
+            const float* pq = q + (size_t)e * 16;
+            gg::RobotDyn<7, 2> D;
+            gg::robot_pad_frames<7, 2, false>(*M, pq, D);
+            out[e] = gg::pads_may_touch<7, 2>(*M, D, gg::mk(pq[9], pq[10], pq[11]));
+        } else {
+            const float* pq = q + (size_t)e * 13;
+            gg::RobotDyn<5, 1> D;
+            gg::robot_pad_frames<5, 1, true>(*M, pq, D);
+            out[e] = gg::pads_may_touch<5, 1>(*M, D, gg::mk(pq[6], pq[7], pq[8]));
+        }
+    }
+}
