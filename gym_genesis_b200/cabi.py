@@ -51,6 +51,11 @@ class GgConfig(C.Structure):
     ]
 
 
+class GgHostIO(C.Structure):
+    _fields_ = [("action", C.c_void_p), ("reward", C.c_void_p), ("terminated", C.c_void_p), ("truncated", C.c_void_p),
+                ("wait", _i)]
+
+
 def _set(arr, values):
     values = np.asarray(values, dtype=np.float64).ravel()
     for k, v in enumerate(values):
@@ -195,9 +200,10 @@ def compile_gg(sm: "mdl.SceneModel") -> GgModel:
 # library loading (no fallback)
 # ----------------------------------------------------------------------------------------------
 LIB_NAME = "libgg_b200.so"
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), LIB_NAME)
+# GG_B200_LIB: developer override used by tools/ to time alternative builds of the SAME sources (compile-time variants)
+LIB_PATH = os.environ.get("GG_B200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), LIB_NAME)
 EXPORTS = ["gg_last_error", "gg_version", "gg_create", "gg_destroy", "gg_configure", "gg_state_rows", "gg_state_stride",
-           "gg_bind_state", "gg_step", "gg_reset", "gg_get_state", "gg_set_state", "gg_observe", "gg_stats", "gg_launch_count"]
+           "gg_bind_state", "gg_step", "gg_step_host", "gg_reset", "gg_get_state", "gg_set_state", "gg_observe", "gg_stats", "gg_launch_count"]
 
 _lib = None
 
@@ -222,6 +228,7 @@ def load_library():
     lib.gg_state_stride.argtypes = [vp]
     lib.gg_bind_state.argtypes = [vp, vp, vp, vp]
     lib.gg_step.argtypes = [vp] * 9
+    lib.gg_step_host.argtypes = [vp, C.POINTER(GgHostIO)] + [vp] * 7
     lib.gg_reset.argtypes = [vp] * 6
     lib.gg_get_state.argtypes = [vp] * 5
     lib.gg_set_state.argtypes = [vp] * 5

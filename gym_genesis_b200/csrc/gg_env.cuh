@@ -27,6 +27,13 @@
 #define GG_CON_LOOP _Pragma("unroll")
 #endif
 
+// warp-uniform "does any lane ..." (callers guarantee a converged warp); the host harness runs one env at a time
+#if defined(__CUDA_ARCH__) && !defined(GG_NO_LIMIT_SKIP)
+#define GG_WARP_ANY(x) __any_sync(0xffffffffu, (x))
+#else
+#define GG_WARP_ANY(x) (x)
+#endif
+
 namespace gg {
 
 template <int NU> struct EnvState {
@@ -150,10 +157,8 @@ GG_HD void robot_crba(const GgModel& M, const float* q, RobotDyn<NA, NF>& D, LS&
 }
 
 template <int NA, int NF, bool FH>
-GG_HD void robot_rnea(const GgModel& M, const float* q, const float* qd, const float* target, float* fs) {
-    constexpr int NU = NA + NF;
+GG_HD void robot_bias(const GgModel& M, const float* q, const float* qd, float* bias) {
     SV S[NA]; SV F[NA];
-    float bias[NU];
     Q4 ql = ldq(M.base_quat);
     V3 pl = ld3(M.base_pos);
     M3 Rl = qmat(ql);
@@ -201,13 +206,24 @@ GG_HD void robot_rnea(const GgModel& M, const float* q, const float* qd, const f
         Fc = Fc + F[l];
         bias[l] = sdot(S[l], Fc);
     }
-    // PD position control with force clamp; passive damping
+}
+
+// PD position control with force clamp; passive damping; fs = tau - bias
+template <int NU>
+GG_HD void pd_force(const GgModel& M, const float* q, const float* qd, const float* target, const float* bias, float* fs) {
 #pragma unroll
     for (int d = 0; d < NU; d++) {
         float t = M.kp[d] * (target[d] - q[d]) - M.kv[d] * qd[d];
         t = fminf(fmaxf(t, M.frc_lo[d]), M.frc_hi[d]);
         fs[d] = t - M.damping[d] * qd[d] - bias[d];
     }
+}
+
+template <int NA, int NF, bool FH>
+GG_HD void robot_rnea(const GgModel& M, const float* q, const float* qd, const float* target, float* fs) {
+    float bias[NA + NF];
+    robot_bias<NA, NF, FH>(M, q, qd, bias);
+    pd_force<NA + NF>(M, q, qd, target, bias, fs);
 }
 
 template <int NA, int NF, bool FH>
@@ -264,6 +280,41 @@ GG_HD void robot_eef(const GgModel& M, const float* q, V3& ep, Q4& eq) {
     }
     ep = pl + mul(Rl, ld3(M.eef_pos));
     eq = qmul(ql, ldq(M.eef_quat));
+}
+
+// The end-effector chain is associative, so the post-step refresh is split between two warps: `robot_chain_head` walks
+// links [0, KS) from the base, `robot_chain_tail` walks links [KS, NA) + the end-effector offset relative to frame KS - 1,
+// `compose_eef` joins them (same result as robot_eef up to rounding).
+template <int NA> GG_HD void robot_chain_head(const GgModel& M, const float* q, int ks, Q4& ql, V3& pl, M3& Rl) {
+    ql = ldq(M.base_quat); pl = ld3(M.base_pos); Rl = qmat(ql);
+    GG_LINK_LOOP
+    for (int l = 0; l < ks; l++) {
+        pl = pl + mul(Rl, ld3(M.link_pos[l]));
+        float s, c;
+        gg_sincos(0.5f * q[l], &s, &c);
+        ql = qmul_z(qmul(ql, ldq(M.link_quat[l])), c, s);
+        Rl = qmat(ql);
+    }
+}
+// qt[l - ks] = joint coordinate of link l
+template <int NA> GG_HD void robot_chain_tail(const GgModel& M, const float* qt, int ks, V3& tp, Q4& tq) {
+    Q4 ql = mkq(1.f, 0.f, 0.f, 0.f);
+    V3 pl = mk(0.f, 0.f, 0.f);
+    M3 Rl; Rl.c0 = mk(1.f, 0.f, 0.f); Rl.c1 = mk(0.f, 1.f, 0.f); Rl.c2 = mk(0.f, 0.f, 1.f);
+    GG_LINK_LOOP
+    for (int l = ks; l < NA; l++) {
+        pl = pl + mul(Rl, ld3(M.link_pos[l]));
+        float s, c;
+        gg_sincos(0.5f * qt[l - ks], &s, &c);
+        ql = qmul_z(qmul(ql, ldq(M.link_quat[l])), c, s);
+        Rl = qmat(ql);
+    }
+    tp = pl + mul(Rl, ld3(M.eef_pos));
+    tq = qmul(ql, ldq(M.eef_quat));
+}
+GG_HD void compose_eef(Q4 ql, V3 pl, const M3& Rl, V3 tp, Q4 tq, V3& ep, Q4& eq) {
+    ep = pl + mul(Rl, tp);
+    eq = qmul(ql, tq);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1052,10 +1103,15 @@ GG_HD int joint_limit_rows(const GgModel& M, const float* q, const float* qd, fl
         float plo = q[d] - M.lim_lo[d], phi = M.lim_hi[d] - q[d];
         float sg = plo < 0.f ? 1.f : (phi < 0.f ? -1.f : 0.f);
         float pos = plo < 0.f ? plo : phi;
-        float imp, aref;
-        imp_aref(M, pos, sg * qd[d], imp, aref);
-        lsg[d] = sg; laref[d] = aref;
-        lD[d] = gg_rcp(fmaxf(M.minval, (1.f - imp) / imp * M.dof_invweight[d]));
+        lsg[d] = sg; laref[d] = 0.f; lD[d] = 0.f;
+        // every consumer guards laref / lD with lsg != 0, so dofs that violate no limit in ANY env of the warp skip the
+        // impedance evaluation (warp-uniform branch; typically only the gripper dofs sit on a limit)
+        if (GG_WARP_ANY(sg != 0.f)) {
+            float imp, aref;
+            imp_aref(M, pos, sg * qd[d], imp, aref);
+            laref[d] = aref;
+            lD[d] = gg_rcp(fmaxf(M.minval, (1.f - imp) / imp * M.dof_invweight[d]));
+        }
         nlim += sg != 0.f;
     }
     return nlim;
@@ -1204,7 +1260,13 @@ GG_HD void env_substep(const GgModel& M, EnvState<NA + NF>& s, const float* targ
 template <int NA, int NF>
 GG_HD void env_observe(const GgModel& M, const EnvState<NA + NF>& s, float* agent, float* envs, float& reward, bool& success) {
     V3 ep; Q4 eq;
-    robot_eef<NA, NF>(M, s.q, ep, eq);
+    {
+        constexpr int KS = (NA - 1) / 2;
+        Q4 ql, tq; V3 pl, tp; M3 Rl;
+        robot_chain_head<NA>(M, s.q, KS, ql, pl, Rl);
+        robot_chain_tail<NA>(M, s.q + KS, KS, tp, tq);
+        compose_eef(ql, pl, Rl, tp, tq, ep, eq);
+    }
     agent[0] = ep.x; agent[1] = ep.y; agent[2] = ep.z;
     agent[3] = eq.w; agent[4] = eq.x; agent[5] = eq.y; agent[6] = eq.z;
 #pragma unroll

@@ -38,6 +38,8 @@ struct StepArgs {
     const float* action; float* obs_agent; float* obs_env; float* reward;
     uint8_t* terminated; uint8_t* truncated;
     const uint8_t* reset_mask; const float* cube_xy;
+    float* reward_host; uint8_t* terminated_host; uint8_t* truncated_host;   // nullable pinned-host mirrors (gg_step_host)
+    int stage_action;         // 1: action is 16-byte aligned -> full blocks stage their slab with cp.async
     int mode;                 // 0 = env.step, 1 = reset (+ settle) of masked envs, 2 = observe only
     int iterations; float tol;
     int auto_reset, time_limit; float reset_prob;
@@ -91,6 +93,8 @@ template <int NU> __device__ __forceinline__ void store_state(float* __restrict_
 //   barrier 1 (96 threads): CUBE arrives, RNEA and MAIN wait      -- fs, coupled flags, cube state
 //   barrier 2 (64 threads): MAIN arrives, CUBE waits              -- solver statistics of the robot block
 //   barrier 3 (64 threads): MAIN and CUBE wait                    -- end-effector position, non-finite flags
+//   barrier 6 (64 threads): MAIN and RNEA wait                    -- integrated joint positions for the split end-effector chain
+//   barrier 7 (64 threads): RNEA arrives, MAIN waits              -- tail of the end-effector chain
 //
 // Envs whose pads may touch the cube or the plane ("coupled", decided by the CUBE warp's broad phase) leave the
 // thread-per-env mapping: after barrier 1 the three warps of the block become three solver teams and work through the
@@ -115,10 +119,12 @@ __device__ __forceinline__ void bar_arrive(int id, int nthreads) {
 }
 
 template <int NU> struct Xchg {
+    alignas(16) float act[32 * NU];   // this block's (32, NU) slab of the action batch, staged by the RNEA warp with cp.async
     float fs[NU][32];         // RNEA -> MAIN
     float cube[19][32];       // CUBE -> MAIN: cp3 cq4 cv3 cw3 qacc6 (the state a coupled solve starts from)
     float aout[NU + 6][32];   // solver teams -> MAIN / CUBE: acceleration of coupled envs
     float ep[3][32];          // MAIN -> CUBE: end-effector position after the step
+    float tail[7][32];        // RNEA -> MAIN: end-effector pose relative to arm link KS - 1 after the step (split chain)
     int coupled[32];          // CUBE -> MAIN
     int iters[32], ncon[32];  // MAIN / teams -> CUBE (statistics)
     int bad[2][32];           // non-finite flags: [0] robot (MAIN), [1] cube (CUBE)
@@ -157,6 +163,7 @@ template <int NA, int NF, bool FH>
 __global__ void __launch_bounds__(kBlockThreads, GG_MINBLOCKS) step_kernel(const __grid_constant__ StepArgs A) {
     constexpr bool TEAMS = true;
     constexpr int NU = NA + NF, NV = NU + 6;
+    constexpr int KS = (NA - 1) / 2;      // split point of the end-effector chain (links [0, KS) MAIN, [KS, NA) RNEA)
     __shared__ Xchg<NU> X;
     __shared__ gg::TeamWork<NA, NF> TW[3];
     __shared__ gg::TeamBuf<NV> TB[3];
@@ -177,19 +184,41 @@ __global__ void __launch_bounds__(kBlockThreads, GG_MINBLOCKS) step_kernel(const
     if (role == 1) {
         // ------------------------------------------------------------------------------ RNEA
         if (!run_sub) return;
-        float q[NU], qd[NU], tgt[NU], fs[NU];
+        // The action slab of this block (32 x NU floats, contiguous) is fetched asynchronously into shared memory while the
+        // bias forces are computed: the targets are only needed by the PD law at the very end of this role, so the fetch
+        // latency -- HBM, or PCIe / C2C when the caller passes pinned host memory (gg_step_host, zero-copy) -- is hidden.
+        const bool staged = A.mode == 0 && A.stage_action != 0 && blockIdx.x * 32 + 32 <= A.n;      // block-uniform
+        if (staged) {
+            const float* src = A.action + (size_t)blockIdx.x * 32 * NU;
+            const unsigned dst = (unsigned)__cvta_generic_to_shared(X.act);
+#pragma unroll
+            for (int c = lane; c < 32 * NU / 4; c += 32)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16u * c), "l"(src + 4 * c) : "memory");
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        }
+        float q[NU], qd[NU], tgt[NU], fs[NU], bias[NU];
 #pragma unroll
         for (int i = 0; i < NU; i++) {
             const float lq = sp[i * st], lqd = sp[(NU + i) * st];
             q[i] = do_reset ? A.M.home_q[i] : lq; qd[i] = do_reset ? 0.f : lqd;
         }
+        gg::robot_bias<NA, NF, FH>(A.M, q, qd, bias);
+        if (staged) {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            __syncwarp();
+        }
 #pragma unroll
         for (int i = 0; i < NU; i++) tgt[i] = A.M.home_q[i];
         if (A.mode == 0 && !do_reset) {
+            if (staged) {
 #pragma unroll
-            for (int i = 0; i < NU; i++) tgt[i] = A.action[(size_t)e * NU + i];
+                for (int i = 0; i < NU; i++) tgt[i] = X.act[lane * NU + i];
+            } else {
+#pragma unroll
+                for (int i = 0; i < NU; i++) tgt[i] = A.action[(size_t)e * NU + i];
+            }
         }
-        gg::robot_rnea<NA, NF, FH>(A.M, q, qd, tgt, fs);
+        gg::pd_force<NU>(A.M, q, qd, tgt, bias, fs);
 #pragma unroll
         for (int i = 0; i < NU; i++) X.fs[i][lane] = fs[i];
         if (!TEAMS) { bar_arrive(1, 96); return; }
@@ -203,6 +232,20 @@ __global__ void __launch_bounds__(kBlockThreads, GG_MINBLOCKS) step_kernel(const
             team_round<NA, NF, FH, NU>(A, TW, TB, X, cm, ncpl, r0, 1, lane);
             bar_sync(5, 96);
         }
+#ifndef GG_NO_SPLIT_EEF
+        {
+            // post-step refresh of the end-effector pose, second half of the chain (MAIN walks the first half meanwhile)
+            bar_sync(6, 64);
+            float qt[NA - KS];
+#pragma unroll
+            for (int i = 0; i < NA - KS; i++) qt[i] = X.fs[KS + i][lane];
+            gg::V3 tp; gg::Q4 tq;
+            gg::robot_chain_tail<NA>(A.M, qt, KS, tp, tq);
+            X.tail[0][lane] = tp.x; X.tail[1][lane] = tp.y; X.tail[2][lane] = tp.z;
+            X.tail[3][lane] = tq.w; X.tail[4][lane] = tq.x; X.tail[5][lane] = tq.y; X.tail[6][lane] = tq.z;
+            bar_arrive(7, 64);
+        }
+#endif
         return;
     }
 
@@ -292,6 +335,20 @@ __global__ void __launch_bounds__(kBlockThreads, GG_MINBLOCKS) step_kernel(const
             if (active) gg::integrate_robot<NU>(A.M, q, qd, qa, a);
         }
         gg::V3 ep; gg::Q4 eq;
+#ifndef GG_NO_SPLIT_EEF
+        if (run_sub) {
+            // split chain: the (by now idle) RNEA warp walks links [KS, NA) + the end-effector offset, this warp links [0, KS)
+#pragma unroll
+            for (int i = KS; i < NA; i++) X.fs[i][lane] = q[i];
+            __threadfence_block();
+            bar_sync(6, 64);
+            gg::Q4 ql; gg::V3 pl; gg::M3 Rl;
+            gg::robot_chain_head<NA>(A.M, q, KS, ql, pl, Rl);
+            bar_sync(7, 64);
+            gg::compose_eef(ql, pl, Rl, gg::mk(X.tail[0][lane], X.tail[1][lane], X.tail[2][lane]),
+                            gg::mkq(X.tail[3][lane], X.tail[4][lane], X.tail[5][lane], X.tail[6][lane]), ep, eq);
+        } else
+#endif
         gg::robot_eef<NA, NF>(A.M, q, ep, eq);
         {
             float acc = 0.f;
@@ -439,6 +496,9 @@ __global__ void __launch_bounds__(kBlockThreads, GG_MINBLOCKS) step_kernel(const
             if (A.reward) A.reward[e] = rew;
             if (A.terminated) A.terminated[e] = succ ? 1 : 0;
             if (A.truncated) A.truncated[e] = trunc ? 1 : 0;
+            if (A.reward_host) A.reward_host[e] = rew;
+            if (A.terminated_host) A.terminated_host[e] = succ ? 1 : 0;
+            if (A.truncated_host) A.truncated_host[e] = trunc ? 1 : 0;
             if (A.mode != 2) {
                 A.done[e] = (succ || trunc) ? 1 : 0;
                 if (active || do_reset) {
@@ -538,6 +598,8 @@ struct GgSim {
     float* state; int32_t* step_count; int32_t* episode;
     uint8_t* done; double* stats;       // library-owned (allocated once in gg_create)
     uint32_t step_index;
+    static constexpr int kPinCache = 16;
+    const void* pin_ok[kPinCache]; int pin_next;   // pointers already verified as pinned host memory (gg_step_host)
 };
 
 static int launch_step(GgSim* sim, StepArgs& A, gg_stream_t stream) {
@@ -623,9 +685,42 @@ int gg_step(GgSim* sim, const float* action, float* obs_agent, float* obs_env, f
     memset(&A, 0, sizeof(A));
     A.action = action; A.obs_agent = obs_agent; A.obs_env = obs_env; A.reward = reward;
     A.terminated = terminated; A.truncated = truncated; A.reset_mask = reset_mask; A.cube_xy = nullptr; A.mode = 0;
+    A.stage_action = ((uintptr_t)action & 15u) == 0;
     int rc = launch_step(sim, A, stream);
     sim->step_index++;
     return rc;
+}
+
+// Is `p` page-locked host memory the device can address (cudaHostAlloc / cudaHostRegister)?  The answer is cached per
+// pointer so that the steady-state step pays no driver query.
+static bool pinned_host_ptr(GgSim* sim, const void* p) {
+    for (int i = 0; i < GgSim::kPinCache; i++) if (sim->pin_ok[i] == p) return true;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    if (at.type != cudaMemoryTypeHost && at.type != cudaMemoryTypeManaged) return false;
+    sim->pin_ok[sim->pin_next] = p;
+    sim->pin_next = (sim->pin_next + 1) % GgSim::kPinCache;
+    return true;
+}
+
+int gg_step_host(GgSim* sim, const GgHostIO* io, float* obs_agent, float* obs_env, float* reward, uint8_t* terminated,
+                 uint8_t* truncated, const uint8_t* reset_mask, gg_stream_t stream) {
+    if (!sim || !io || !io->action || !obs_agent || !obs_env) return fail("gg_step_host: null argument%s");
+    if (!pinned_host_ptr(sim, io->action)) return fail("gg_step_host: action must be page-locked (pinned) host memory%s");
+    if (io->reward && !pinned_host_ptr(sim, io->reward)) return fail("gg_step_host: reward mirror must be pinned host memory%s");
+    if (io->terminated && !pinned_host_ptr(sim, io->terminated)) return fail("gg_step_host: terminated mirror must be pinned host memory%s");
+    if (io->truncated && !pinned_host_ptr(sim, io->truncated)) return fail("gg_step_host: truncated mirror must be pinned host memory%s");
+    StepArgs A;
+    memset(&A, 0, sizeof(A));
+    A.action = io->action; A.obs_agent = obs_agent; A.obs_env = obs_env; A.reward = reward;
+    A.terminated = terminated; A.truncated = truncated; A.reset_mask = reset_mask; A.cube_xy = nullptr; A.mode = 0;
+    A.reward_host = io->reward; A.terminated_host = io->terminated; A.truncated_host = io->truncated;
+    A.stage_action = ((uintptr_t)io->action & 15u) == 0;
+    int rc = launch_step(sim, A, stream);
+    sim->step_index++;
+    if (rc != 0) return rc;
+    if (io->wait) GG_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    return 0;
 }
 
 int gg_reset(GgSim* sim, const uint8_t* mask, const float* cube_xy, float* obs_agent, float* obs_env, gg_stream_t stream) {

@@ -2,7 +2,8 @@
 
 Same constructor keywords, same `reset` / `step` / `push` / `get_*` surface.  Differences are the
 ones SURVEY.md Appendix D decides: all five step outputs are torch tensors on the sim device
-(`numpy_flags=True` gives host numpy `terminated` / `truncated` exactly as env.py:64-65 intends),
+(`numpy_flags=True` gives host numpy `terminated` / `truncated` exactly as env.py:64-65 intends;
+`host_io=True` serves a CPU-resident policy: host actions in, host reward / flags out through pinned zero-copy buffers),
 and `get_robot()` / `get_cube()` return the task's handles generically.
 """
 from __future__ import annotations
@@ -19,7 +20,7 @@ class GenesisEnv(gym.Env):
 
     def __init__(self, task, robot="so101", enable_pixels=False, observation_height=480, observation_width=640, num_envs=1,
                  env_spacing=(1.0, 1.0), render_mode=None, camera_capture_mode="per_env", strip_environment_state=True,
-                 numpy_flags=False, **sim_kwargs):
+                 numpy_flags=False, host_io=False, **sim_kwargs):
         super().__init__()
         self.task = task
         self.robot = robot
@@ -32,6 +33,7 @@ class GenesisEnv(gym.Env):
         self.camera_capture_mode = camera_capture_mode
         self.strip_environment_state = strip_environment_state
         self.numpy_flags = numpy_flags
+        self.host_io = host_io
         self._sim_kwargs = sim_kwargs
         self._env = self._make_env_task(self.task)
         self.observation_space = self._env.observation_space
@@ -50,6 +52,13 @@ class GenesisEnv(gym.Env):
         self._env.scene.step()
 
     def step(self, action, reset_mask=None):
+        if self.host_io:
+            # host-resident policy loop (the reference's numpy convention): zero-copy action read, reward / flags land in
+            # pinned host memory, one stream synchronisation per step; observations stay on the device
+            reward, terminated, truncated = self._env.step_host(action, reset_mask)
+            if self.numpy_flags:
+                terminated, truncated = terminated.numpy(), truncated.numpy()
+            return self._env.get_obs(), reward, terminated, truncated, {"is_success": terminated}
         _, reward, _, observation = self._env.step(action, reset_mask)
         sim = self._env.sim
         is_success = sim.terminated                 # == (reward == 1), computed in-kernel with the strict z > 0.1f test

@@ -122,6 +122,44 @@ class BatchedSim:
         self._check(self.lib.gg_step(self._h, _ptr(a), _ptr(self.obs_agent), _ptr(self.obs_env), _ptr(self.reward),
                                      _ptr(self.terminated), _ptr(self.truncated), _ptr(m), self._stream()))
 
+    def _host_buffers(self):
+        if getattr(self, "_host", None) is None:
+            n = self.n_envs
+            self._host = {
+                "action": torch.empty((n, self.nu), dtype=torch.float32).pin_memory(),      # staging for unpinned callers
+                "reward": torch.zeros(n, dtype=torch.float32).pin_memory(),
+                "terminated": torch.zeros(n, dtype=torch.bool).pin_memory(),
+                "truncated": torch.zeros(n, dtype=torch.bool).pin_memory(),
+            }
+            self._hio = cabi.GgHostIO(0, self._host["reward"].data_ptr(), self._host["terminated"].data_ptr(),
+                                      self._host["truncated"].data_ptr(), 1)
+            self._hio_ref = C.byref(self._hio)
+            self._out_ptrs = tuple(_ptr(t) for t in (self.obs_agent, self.obs_env, self.reward, self.terminated, self.truncated))
+        return self._host
+
+    def step_host(self, action, reset_mask=None, wait=True):
+        """env.step for a HOST-resident caller (the reference's numpy convention): `action` is a CPU float32 (n_envs, n_dof)
+        array; a pinned torch tensor is read in place by the kernel over PCIe (zero-copy), anything else is first copied into
+        a pinned staging buffer.  Returns pinned CPU tensors (reward, terminated, truncated) the kernel has written directly;
+        with wait=True (default) they are valid on return.  Observations stay on the device (obs_agent / obs_env)."""
+        h = self._host_buffers()
+        if tuple(getattr(action, "shape", ())) != (self.n_envs, self.nu):
+            raise ValueError(f"action must have shape ({self.n_envs}, {self.nu}), got {tuple(getattr(action, 'shape', ()))}")
+        if isinstance(action, torch.Tensor) and action.device.type == "cpu" and action.dtype == torch.float32 \
+                and action.is_contiguous() and action.is_pinned():
+            a = action
+        else:
+            a = h["action"]
+            a.copy_(torch.as_tensor(np.asarray(action) if not isinstance(action, torch.Tensor) else action, dtype=torch.float32))
+        m = self._as_mask(reset_mask)
+        self._last_action = a
+        self._hio.action = a.data_ptr()
+        self._hio.wait = 1 if wait else 0
+        rc = self.lib.gg_step_host(self._h, self._hio_ref, *self._out_ptrs, _ptr(m), self._stream())
+        if rc != 0:
+            self._check(rc)
+        return h["reward"], h["terminated"], h["truncated"]
+
     def reset(self, mask=None, cube_xy=None):
         m = self._as_mask(mask)
         xy = None

@@ -155,6 +155,14 @@ class CubePickBatch:
         self._physics_step(a, reset_mask)
         return None, self.compute_reward(), None, self.get_obs()
 
+    def step_host(self, action, reset_mask=None):
+        """`step` for a host-resident policy (numpy / CPU-tensor actions, the reference's README convention): the kernel
+        reads a pinned action batch in place and writes reward / terminated / truncated straight into pinned host arrays.
+        Returns (reward, terminated, truncated) as CPU tensors valid on return; observations stay on the device."""
+        out = self.sim.step_host(action, reset_mask)
+        self._targets = self.sim._last_action
+        return out
+
     def compute_reward(self):
         return self.sim.reward
 

@@ -14,6 +14,8 @@
  *   gg_get_state /
  *   gg_set_state     <- entity.get_qpos / get_dofs_velocity / set_qpos / set_dofs_velocity (state injection,
  *                       used by the parity harness)
+ *   gg_step_host     <- the same calls with host numpy arrays as the reference passes / receives them
+ *                       (README.md:34 numpy action; cube_pick.py:130-135 numpy reward; env.py:63-65 numpy flags)
  *   gg_stats         <- (new) per-shard episode statistics for the optional NCCL all-gather
  *
  * Conventions: plain pointers and sizes only; every pointer argument of gg_step / gg_reset is a
@@ -97,6 +99,22 @@ int gg_bind_state(GgSim* sim, float* state, int32_t* step_count, int32_t* episod
  * draw + home pose + settle step) instead of stepped. */
 int gg_step(GgSim* sim, const float* action, float* obs_agent, float* obs_env, float* reward,
             uint8_t* terminated, uint8_t* truncated, const uint8_t* reset_mask, gg_stream_t stream);
+
+/* Host-resident I/O for callers whose policy lives on the CPU -- the reference's own calling convention: numpy actions in
+ * (README.md:34), numpy reward / terminated / truncated out (cube_pick.py:130-135, env.py:63-65).  ZERO-COPY: `action` is
+ * (n_envs, n_dof) in page-locked host memory and is read by the step kernel itself (cp.async over PCIe / C2C, overlapped
+ * with the bias-force computation); the nullable mirrors are page-locked host arrays the kernel writes next to the device
+ * outputs.  No copy-engine transfer and no second launch is involved.  wait != 0: the call returns after the stream has
+ * drained, i.e. when the mirrors are readable (the only entry point that may synchronise). */
+typedef struct GgHostIO {
+    const float* action;
+    float* reward;
+    uint8_t* terminated;
+    uint8_t* truncated;
+    int32_t wait;
+} GgHostIO;
+int gg_step_host(GgSim* sim, const GgHostIO* io, float* obs_agent, float* obs_env, float* reward, uint8_t* terminated,
+                 uint8_t* truncated, const uint8_t* reset_mask, gg_stream_t stream);
 
 /* Reset envs selected by mask (NULL = all).  cube_xy (nullable): (n_envs, 2) explicit spawn
  * positions (the host RandomState stream of the reference); NULL -> device Philox draw keyed by

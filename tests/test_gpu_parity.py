@@ -322,3 +322,44 @@ def test_nonfinite_env_is_respawned_and_neighbours_untouched(Sim, franka_model, 
     st = sim.stats().cpu().numpy()
     assert st[5] == 2 and st[0] == n - 2
     assert (sim.episode.cpu().numpy()[[5, 40]] == 1).all() and sim.episode.cpu().numpy()[ok].max() == 0
+
+
+@pytest.mark.parametrize("n", [1000, 1024])
+def test_step_host_zero_copy_is_bit_identical_to_device_step(Sim, franka_model, n):
+    """gg_step_host (pinned host action read in place by the kernel, reward / flags mirrored into pinned host memory) against
+    gg_step with a device-resident action: bit-identical state, observations and flags; n = 1000 exercises the partial tail
+    block (scalar action loads) next to full blocks (cp.async staged slab)."""
+    rng = np.random.default_rng(77)
+    a = Sim(franka_model, n, seed=3, auto_reset=True, reset_prob=0.02, time_limit=True)
+    b = Sim(franka_model, n, seed=3, auto_reset=True, reset_prob=0.02, time_limit=True)
+    a.reset(None, None); b.reset(None, None)
+    for k in range(12):
+        act = f32(np.tile(mdl.FRANKA_HOME, (n, 1)) + rng.uniform(-0.3, 0.3, (n, 9)))
+        a.step(torch.as_tensor(act, device=a.device))
+        pinned = torch.as_tensor(act).pin_memory() if k % 2 == 0 else act          # pinned: zero-copy; numpy: staged copy
+        rew, term, trunc = b.step_host(pinned)
+        assert torch.equal(rew, a.reward.cpu()) and torch.equal(term, a.terminated.cpu()) and torch.equal(trunc, a.truncated.cpu())
+        assert torch.equal(a.obs_agent, b.obs_agent) and torch.equal(a.obs_env, b.obs_env)
+    for x, y in zip(a.get_state(), b.get_state()):
+        assert torch.equal(x, y)
+    import ctypes as C
+    from gym_genesis_b200 import cabi
+    from gym_genesis_b200.sim import GgError
+    bad = torch.zeros((n, 9), dtype=torch.float32)                                   # pageable host memory must be rejected
+    io = cabi.GgHostIO(bad.data_ptr(), 0, 0, 0, 1)
+    with pytest.raises(GgError, match="pinned"):
+        b._check(b.lib.gg_step_host(b._h, C.byref(io), b.obs_agent.data_ptr(), b.obs_env.data_ptr(), None, None, None, None, b._stream()))
+
+
+def test_gym_surface_host_io():
+    import gym_genesis  # noqa: F401
+    from gym_genesis_b200.gym_api import gym
+    n = 64
+    env = gym.make("gym_genesis/CubePick-v0", robot="franka", num_envs=n, host_io=True).unwrapped
+    obs, info = env.reset(seed=0)
+    act = np.tile(mdl.FRANKA_HOME.astype(np.float32), (n, 1))
+    obs, reward, terminated, truncated, info = env.step(act)                           # numpy action, as in the reference README
+    assert reward.device.type == "cpu" and reward.shape == (n,) and reward.dtype == torch.float32
+    assert terminated.dtype == torch.bool and not terminated.any() and not truncated.any()
+    assert obs["agent_pos"].is_cuda and obs["environment_state"].shape == (n, 11)
+    assert torch.equal(reward, env._env.sim.reward.cpu())
