@@ -156,8 +156,21 @@ GG_HD void robot_crba(const GgModel& M, const float* q, RobotDyn<NA, NF>& D, LS&
     for (int d = 0; d < NU; d++) D.Mt[GG_TRI(d, d)] += M.armature[d] + M.dt * (M.damping[d] + M.kv[d]);
 }
 
-template <int NA, int NF, bool FH>
-GG_HD void robot_bias(const GgModel& M, const float* q, const float* qd, float* bias) {
+// The targets are only needed by the PD law at the very end of the pass, so they come through a functor: `tf.ready()` is called
+// once right before the first `tf(d)` (the CUDA kernel waits there for its asynchronously staged action slab).
+// NOTE: bias[] must stay a local of this function -- hoisting it into the caller (a separate bias pass + PD pass) was
+// miscompiled by nvcc 12.9 (dynamically indexed stores of the rolled loop and the static reads of the PD loop ended up at
+// different stack offsets; caught by the GPU parity tests).
+struct TargetPtr {
+    const float* t;
+    GG_HD void ready() {}
+    GG_HD float operator()(int d) const { return t[d]; }
+};
+
+template <int NA, int NF, bool FH, class TF>
+GG_HD void robot_rnea_t(const GgModel& M, const float* q, const float* qd, TF& tf, float* fs) {
+    constexpr int NU = NA + NF;
+    float bias[NU];
     SV S[NA]; SV F[NA];
     Q4 ql = ldq(M.base_quat);
     V3 pl = ld3(M.base_pos);
@@ -206,14 +219,11 @@ GG_HD void robot_bias(const GgModel& M, const float* q, const float* qd, float* 
         Fc = Fc + F[l];
         bias[l] = sdot(S[l], Fc);
     }
-}
-
-// PD position control with force clamp; passive damping; fs = tau - bias
-template <int NU>
-GG_HD void pd_force(const GgModel& M, const float* q, const float* qd, const float* target, const float* bias, float* fs) {
+    // PD position control with force clamp; passive damping
+    tf.ready();
 #pragma unroll
     for (int d = 0; d < NU; d++) {
-        float t = M.kp[d] * (target[d] - q[d]) - M.kv[d] * qd[d];
+        float t = M.kp[d] * (tf(d) - q[d]) - M.kv[d] * qd[d];
         t = fminf(fmaxf(t, M.frc_lo[d]), M.frc_hi[d]);
         fs[d] = t - M.damping[d] * qd[d] - bias[d];
     }
@@ -221,9 +231,8 @@ GG_HD void pd_force(const GgModel& M, const float* q, const float* qd, const flo
 
 template <int NA, int NF, bool FH>
 GG_HD void robot_rnea(const GgModel& M, const float* q, const float* qd, const float* target, float* fs) {
-    float bias[NA + NF];
-    robot_bias<NA, NF, FH>(M, q, qd, bias);
-    pd_force<NA + NF>(M, q, qd, target, bias, fs);
+    TargetPtr tf; tf.t = target;
+    robot_rnea_t<NA, NF, FH>(M, q, qd, tf, fs);
 }
 
 template <int NA, int NF, bool FH>

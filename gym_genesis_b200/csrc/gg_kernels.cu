@@ -130,6 +130,23 @@ template <int NU> struct Xchg {
     int bad[2][32];           // non-finite flags: [0] robot (MAIN), [1] cube (CUBE)
 };
 
+// PD targets of one env for robot_rnea_t: the staged slab in shared memory (after the cp.async group has landed), the action
+// row in global memory (partial tail block / unaligned batch), or the home pose (envs being reset, settle steps).
+template <int NU> struct ActionFetch {
+    const float* home; const float* slab; const float* global;
+    bool staged, use_action;
+    __device__ __forceinline__ void ready() {
+        if (staged) {                                   // block-uniform
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            __syncwarp();
+        }
+    }
+    __device__ __forceinline__ float operator()(int d) const {
+        const float a = staged ? slab[d] : (use_action ? global[d] : 0.f);
+        return use_action ? a : home[d];
+    }
+};
+
 __device__ __forceinline__ bool reset_decision(const StepArgs& A, int e, uint32_t gid) {
     bool r = false;
     if (A.mode == 0) {
@@ -187,7 +204,11 @@ __global__ void __launch_bounds__(kBlockThreads, GG_MINBLOCKS) step_kernel(const
         // The action slab of this block (32 x NU floats, contiguous) is fetched asynchronously into shared memory while the
         // bias forces are computed: the targets are only needed by the PD law at the very end of this role, so the fetch
         // latency -- HBM, or PCIe / C2C when the caller passes pinned host memory (gg_step_host, zero-copy) -- is hidden.
+#ifndef GG_NO_STAGE
         const bool staged = A.mode == 0 && A.stage_action != 0 && blockIdx.x * 32 + 32 <= A.n;      // block-uniform
+#else
+        const bool staged = false;
+#endif
         if (staged) {
             const float* src = A.action + (size_t)blockIdx.x * 32 * NU;
             const unsigned dst = (unsigned)__cvta_generic_to_shared(X.act);
@@ -196,29 +217,16 @@ __global__ void __launch_bounds__(kBlockThreads, GG_MINBLOCKS) step_kernel(const
                 asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16u * c), "l"(src + 4 * c) : "memory");
             asm volatile("cp.async.commit_group;" ::: "memory");
         }
-        float q[NU], qd[NU], tgt[NU], fs[NU], bias[NU];
+        float q[NU], qd[NU], fs[NU];
 #pragma unroll
         for (int i = 0; i < NU; i++) {
             const float lq = sp[i * st], lqd = sp[(NU + i) * st];
             q[i] = do_reset ? A.M.home_q[i] : lq; qd[i] = do_reset ? 0.f : lqd;
         }
-        gg::robot_bias<NA, NF, FH>(A.M, q, qd, bias);
-        if (staged) {
-            asm volatile("cp.async.wait_group 0;" ::: "memory");
-            __syncwarp();
-        }
-#pragma unroll
-        for (int i = 0; i < NU; i++) tgt[i] = A.M.home_q[i];
-        if (A.mode == 0 && !do_reset) {
-            if (staged) {
-#pragma unroll
-                for (int i = 0; i < NU; i++) tgt[i] = X.act[lane * NU + i];
-            } else {
-#pragma unroll
-                for (int i = 0; i < NU; i++) tgt[i] = A.action[(size_t)e * NU + i];
-            }
-        }
-        gg::pd_force<NU>(A.M, q, qd, tgt, bias, fs);
+        ActionFetch<NU> tf;
+        tf.home = A.M.home_q; tf.slab = X.act + lane * NU; tf.global = A.action + (size_t)e * NU;
+        tf.staged = staged; tf.use_action = A.mode == 0 && !do_reset;
+        gg::robot_rnea_t<NA, NF, FH>(A.M, q, qd, tf, fs);
 #pragma unroll
         for (int i = 0; i < NU; i++) X.fs[i][lane] = fs[i];
         if (!TEAMS) { bar_arrive(1, 96); return; }
