@@ -156,7 +156,7 @@ def run_reference(args):
     sample = f"{n} envs x {steps} steps of the same workload (oracle port, fp32 build, {threads} host threads)"
     out = {"impl": "reference", "metric": METRIC, "value": v, "unit": "env-steps/s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
            "ms_per_step": dt / steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-           "data": "synthetic", "config": workload_config(n),
+           "data": "synthetic", "config": dict(workload_config(N_ENVS_PER_GPU), cpu_sample_envs=n),
            "cpu_baseline": {"value": v, "unit": "env-steps/s", "cores": threads, "kind": "port", "sample": sample,
                             "note": "Genesis (the reference's physics dependency) is not installable here; this is the oracle restatement"},
            "e2e": {"value": v, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -304,6 +304,41 @@ def run_gpu(args):
               "mean_contacts": stb[7] / max(stb[0], 1), "success_rate": float(simb.terminated.float().mean().item()), "nonfinite_resets": stb[5]}
         simb.close()
 
+    # ---- workload C: the reference expert CLOSED-LOOP on the GPU -- batched IK (gg_ik) + env.step ----
+    wc = None
+    if not args.no_workload_c:
+        envc = gym.make("gym_genesis/CubePick-v0", robot="franka", num_envs=n, device=dev, seed=args.seed, first_env_id=rank * n).unwrapped
+        robot = envc.get_robot()
+        eef = robot.get_link("hand")
+        quat = torch.tensor([0.0, 1.0, 0.0, 0.0], device=dev).expand(n, -1)
+        idx = torch.arange(n, device=dev)
+        for w in range(2):                                                                                        # episode 0 = warm-up
+            obs, _ = envc.reset(seed=args.seed + w)
+            succ = torch.zeros(n, dtype=torch.bool, device=dev)
+            evc = [tuple(torch.cuda.Event(enable_timing=True) for _ in range(3)) for _ in range(200)]
+            t = 0
+            for dz, grip in [(0.115, 0.04), (0.115, 0.04), (0.03, -0.02), (0.03, -0.02), (0.25, -0.02)]:
+                off = torch.tensor([0.0, 0.0, dz], device=dev)
+                gr = torch.full((n, 2), grip, device=dev)
+                for _ in range(40):
+                    flush.fill_(t & 0xFF)
+                    evc[t][0].record()
+                    qpos = robot.inverse_kinematics(link=eef, pos=obs["environment_state"][:, :3] + off, quat=quat, envs_idx=idx)
+                    evc[t][1].record()
+                    obs, reward, terminated, truncated, info = envc.step(torch.cat([qpos[:, :-2], gr], dim=1))
+                    evc[t][2].record()
+                    succ |= terminated
+                    t += 1
+            torch.cuda.synchronize(dev)
+        tik = np.array([a.elapsed_time(b) for a, b, c in evc])
+        tall = np.array([a.elapsed_time(c) for a, b, c in evc])
+        wc = {"workload": "reference expert closed loop (examples/franka/pick_cube_state.py: hover/stabilize/grasp/grasp/lift x 40 steps), "
+                          "robot.inverse_kinematics + env.step on the device, %d envs" % n,
+              "value": n * 200 / (tall.sum() * 1e-3), "unit": "env-steps/s", "ik_ms_per_launch": float(tik.mean()),
+              "ik_solves_per_s": n * 200 / (tik.sum() * 1e-3), "ik_ms_by_stage": [float(tik[i * 40:(i + 1) * 40].mean()) for i in range(5)],
+              "success_rate": float(succ.float().mean().item())}
+        envc.close()
+
     times = torch.tensor([t_ms, warm_ms, e2e_ms, e2e_copy_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
@@ -329,7 +364,7 @@ def run_gpu(args):
                        "copy_engine_note": "same loop with cudaMemcpyAsync H2D of the action and D2H of reward / terminated / truncated"},
                "gpu_launches": int(launches), "clocks": clocks,
                "l2_warm": {"value": n * world * args.steps / (warm_ms * 1e-3), "unit": "env-steps/s", "note": "back-to-back launches, no L2 flush"},
-               "wall_s_timed_loop": wall, "workload_b": wb,
+               "wall_s_timed_loop": wall, "workload_b": wb, "workload_c": wc,
                "episode_stats": {"env_steps": st[0], "episodes": st[1], "successes": st[2], "nonfinite_resets": st[5],
                                  "mean_solver_iters": st[6] / max(st[0], 1), "mean_contacts": st[7] / max(st[0], 1)}}
         if not args.no_cpu_baseline and world == 1:
@@ -355,6 +390,7 @@ def main():
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-workload-b", action="store_true")
+    ap.add_argument("--no-workload-c", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -56,6 +56,11 @@ class GgHostIO(C.Structure):
                 ("wait", _i)]
 
 
+class GgIkConfig(C.Structure):
+    _fields_ = [("max_iters", _i), ("damping", _f), ("pos_tol", _f), ("rot_tol", _f), ("max_step", _f), ("respect_limits", _i),
+                ("pos_mask", _f * 3), ("rot_mask", _f * 3)]
+
+
 def _set(arr, values):
     values = np.asarray(values, dtype=np.float64).ravel()
     for k, v in enumerate(values):
@@ -203,7 +208,8 @@ LIB_NAME = "libgg_b200.so"
 # GG_B200_LIB: developer override used by tools/ to time alternative builds of the SAME sources (compile-time variants)
 LIB_PATH = os.environ.get("GG_B200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), LIB_NAME)
 EXPORTS = ["gg_last_error", "gg_version", "gg_create", "gg_destroy", "gg_configure", "gg_state_rows", "gg_state_stride",
-           "gg_bind_state", "gg_step", "gg_step_host", "gg_reset", "gg_get_state", "gg_set_state", "gg_observe", "gg_stats", "gg_launch_count"]
+           "gg_bind_state", "gg_step", "gg_step_host", "gg_reset", "gg_get_state", "gg_set_state", "gg_observe", "gg_stats", "gg_launch_count",
+           "gg_ik", "gg_ik_defaults"]
 
 _lib = None
 
@@ -234,6 +240,9 @@ def load_library():
     lib.gg_set_state.argtypes = [vp] * 5
     lib.gg_observe.argtypes = [vp] * 6
     lib.gg_stats.argtypes = [vp, vp, C.c_int, vp]
+    lib.gg_ik_defaults.argtypes = [C.POINTER(GgIkConfig)]
+    lib.gg_ik_defaults.restype = None
+    lib.gg_ik.argtypes = [vp, C.c_int, vp, vp, vp, vp, vp, vp, vp, C.POINTER(GgIkConfig), vp]
     for name in EXPORTS:
         getattr(lib, name)
     _lib = lib

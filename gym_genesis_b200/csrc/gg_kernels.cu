@@ -15,6 +15,7 @@
 #include "gg_b200.h"
 #include "gg_env.cuh"
 #include "gg_coop.cuh"
+#include "gg_ik.cuh"
 
 namespace {
 
@@ -592,6 +593,47 @@ __global__ void state_copy_kernel(float* state, int stride, int n, float* q, flo
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// ik_kernel: one thread = one IK problem (row).  The chain walk and the 6x6 solve live in registers / a 168-byte local array;
+// rows of a warp run in lock step until every row of the warp has converged (gg_ik.cuh).  Per row: read 36 B (q) + 28 B (target),
+// write 36 B + 12 B -- latency bound like the step kernel.
+// ------------------------------------------------------------------------------------------------
+struct IkArgs {
+    GgModel M; GgIkConfig K;
+    int n_rows, stride;
+    const float* state; const int32_t* envs_idx;
+    const float* tpos; const float* tquat; const float* init_q;
+    float* q_out; float* err_out; int32_t* iters_out;
+};
+
+template <int NA, int NF>
+__global__ void __launch_bounds__(64) ik_kernel(const __grid_constant__ IkArgs A) {
+    constexpr int NU = NA + NF;
+    const int r0 = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = r0 < A.n_rows;
+    const int r = live ? r0 : A.n_rows - 1;              // dead lanes shadow the last row (the warp stays converged)
+    const int e = A.envs_idx ? A.envs_idx[r] : r;
+    float q[NU];
+    if (A.init_q) {
+#pragma unroll
+        for (int i = 0; i < NU; i++) q[i] = A.init_q[(size_t)r * NU + i];
+    } else {
+#pragma unroll
+        for (int i = 0; i < NU; i++) q[i] = A.state[(size_t)i * A.stride + e];
+    }
+    gg::V3 tp = gg::mk(0.f, 0.f, 0.f);
+    gg::Q4 tq = gg::mkq(1.f, 0.f, 0.f, 0.f);
+    if (A.tpos) tp = gg::ld3(A.tpos + (size_t)r * 3);
+    if (A.tquat) tq = gg::ldq(A.tquat + (size_t)r * 4);
+    float perr, rerr;
+    const int it = gg::env_ik<NA>(A.M, A.K, q, tp, tq, perr, rerr);
+    if (!live) return;
+#pragma unroll
+    for (int i = 0; i < NU; i++) A.q_out[(size_t)r * NU + i] = q[i];
+    if (A.err_out) { A.err_out[2 * r] = perr; A.err_out[2 * r + 1] = rerr; }
+    if (A.iters_out) A.iters_out[r] = it;
+}
+
 __global__ void stats_kernel(double* stats, double* out, int clear) {
     int i = threadIdx.x;
     if (i < 8) { out[i] = stats[i]; if (clear) stats[i] = 0.0; }
@@ -760,6 +802,39 @@ static int state_copy(GgSim* sim, float* q, float* qd, float* qacc, int to_soa, 
 int gg_get_state(GgSim* sim, float* q, float* qd, float* qacc, gg_stream_t stream) { return state_copy(sim, q, qd, qacc, 0, stream); }
 int gg_set_state(GgSim* sim, const float* q, const float* qd, const float* qacc, gg_stream_t stream) {
     return state_copy(sim, (float*)q, (float*)qd, (float*)qacc, 1, stream);
+}
+
+void gg_ik_defaults(GgIkConfig* cfg) {
+    if (!cfg) return;
+    cfg->max_iters = 20; cfg->damping = 0.01f; cfg->pos_tol = 5e-4f; cfg->rot_tol = 5e-3f; cfg->max_step = 0.5f;
+    cfg->respect_limits = 1;
+    for (int i = 0; i < 3; i++) { cfg->pos_mask[i] = 1.f; cfg->rot_mask[i] = 1.f; }
+}
+
+int gg_ik(GgSim* sim, int n_rows, const int32_t* envs_idx, const float* target_pos, const float* target_quat,
+          const float* init_q, float* q_out, float* err_out, int32_t* iters_out, const GgIkConfig* cfg, gg_stream_t stream) {
+    if (!sim || !q_out) return fail("gg_ik: null argument%s");
+    if (!target_pos && !target_quat) return fail("gg_ik: at least one of target_pos / target_quat is required%s");
+    if (n_rows <= 0) return fail("gg_ik: n_rows must be positive%s");
+    if (!envs_idx && !init_q && n_rows > sim->n) return fail("gg_ik: n_rows exceeds n_envs (pass envs_idx or init_q)%s");
+    if (!init_q && sim->state == nullptr) return fail("gg_ik: state not bound and no init_q given%s");
+    IkArgs A;
+    memset(&A, 0, sizeof(A));
+    A.M = sim->model;
+    if (cfg) A.K = *cfg; else gg_ik_defaults(&A.K);
+    if (A.K.max_iters < 0 || A.K.max_iters > 10000) return fail("gg_ik: max_iters out of range%s");
+    if (!(A.K.damping > 0.f)) return fail("gg_ik: damping must be positive%s");
+    if (!target_pos) A.K.pos_mask[0] = A.K.pos_mask[1] = A.K.pos_mask[2] = 0.f;
+    if (!target_quat) A.K.rot_mask[0] = A.K.rot_mask[1] = A.K.rot_mask[2] = 0.f;
+    A.n_rows = n_rows; A.stride = sim->stride; A.state = sim->state; A.envs_idx = envs_idx;
+    A.tpos = target_pos; A.tquat = target_quat; A.init_q = init_q; A.q_out = q_out; A.err_out = err_out; A.iters_out = iters_out;
+    GG_CUDA(cudaSetDevice(sim->device));
+    const int grid = (n_rows + 63) / 64;
+    if (sim->kind == 0) ik_kernel<7, 2><<<grid, 64, 0, (cudaStream_t)stream>>>(A);
+    else ik_kernel<5, 1><<<grid, 64, 0, (cudaStream_t)stream>>>(A);
+    g_launches.fetch_add(1);
+    GG_CUDA(cudaGetLastError());
+    return 0;
 }
 
 int gg_stats(GgSim* sim, double* out8, int clear, gg_stream_t stream) {

@@ -44,6 +44,14 @@ GENESIS_COMPAT_SELF_COLLISION = False    # pad-pad / pad-link pairs skipped (sam
 GENESIS_COMPAT_MAX_PLANE_CONTACTS = 4    # mjc_PlaneBox keeps the first 4 penetrating corners
 GENESIS_COMPAT_MAX_BOXBOX_CONTACTS = 8
 GENESIS_COMPAT_MAX_CONTACTS = 64         # per-env cap (Genesis: max_collision_pairs), deterministic order
+# robot.inverse_kinematics defaults (RigidEntity.inverse_kinematics keyword defaults, [UPSTREAM-RECALL, medium])
+GENESIS_COMPAT_IK_MAX_ITERS = 20         # max_solver_iters
+GENESIS_COMPAT_IK_DAMPING = 0.01         # dq = J^T (J J^T + damping^2 I)^-1 e
+GENESIS_COMPAT_IK_POS_TOL = 5e-4         # m
+GENESIS_COMPAT_IK_ROT_TOL = 5e-3         # rad
+GENESIS_COMPAT_IK_MAX_STEP = 0.5         # max_step_size per dof and update
+GENESIS_COMPAT_IK_RESAMPLE = False       # Genesis retries from random qpos (max_samples=50, host RNG) when the first
+                                         # sample fails; not restated -- only the first sample (init = current qpos) runs
 
 
 # ----------------------------------------------------------------------------------------------

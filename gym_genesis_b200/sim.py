@@ -193,6 +193,53 @@ class BatchedSim:
         q, qd, qacc = prep(q, self.nq), prep(qd, self.nv), prep(qacc, self.nv)
         self._check(self.lib.gg_set_state(self._h, _ptr(q), _ptr(qd), _ptr(qacc), self._stream()))
 
+    def inverse_kinematics(self, pos=None, quat=None, init_qpos=None, envs_idx=None, respect_joint_limit=True,
+                           max_solver_iters=20, damping=0.01, pos_tol=5e-4, rot_tol=5e-3, pos_mask=(True, True, True),
+                           rot_mask=(True, True, True), max_step_size=0.5, return_error=False, return_iters=False):
+        """Batched IK of the observed end-effector link: one CUDA launch (`gg_ik`), no host sync.  Mirrors the keywords of
+        Genesis' `RigidEntity.inverse_kinematics` as the reference's experts call it (examples/franka/pick_cube_state.py:46-51).
+        pos (B, 3) / quat (B, 4) wxyz; init_qpos (B, n_dof) or None = the envs' current joint positions; envs_idx (B,) or None =
+        envs 0..B-1.  Returns qpos (B, n_dof) [, err (B, 2) = |e_pos|, |e_rot|] [, iters (B,)]."""
+        if pos is None and quat is None:
+            raise ValueError("inverse_kinematics needs pos and/or quat")
+        dev = self.device
+
+        def prep(t, k):
+            if t is None:
+                return None
+            t = torch.as_tensor(t, dtype=torch.float32).to(dev)
+            if t.dim() == 1:
+                t = t[None]
+            if t.shape[-1] != k or t.dim() != 2:
+                raise ValueError(f"expected shape (B, {k}), got {tuple(t.shape)}")
+            return t.contiguous()
+        pos, quat, init_qpos = prep(pos, 3), prep(quat, 4), prep(init_qpos, self.nu)
+        idx = None
+        if envs_idx is not None:
+            idx = torch.as_tensor(envs_idx).to(device=dev, dtype=torch.int32).reshape(-1).contiguous()
+        rows = {t.shape[0] for t in (pos, quat, init_qpos) if t is not None}
+        if idx is not None:
+            rows.add(idx.shape[0])
+        if len(rows) != 1:
+            raise ValueError(f"pos / quat / init_qpos / envs_idx disagree on the batch size: {sorted(rows)}")
+        B = rows.pop()
+        if idx is None and init_qpos is None and B > self.n_envs:
+            raise ValueError(f"batch of {B} rows exceeds num_envs={self.n_envs}")
+        k = cabi.GgIkConfig()
+        self.lib.gg_ik_defaults(C.byref(k))
+        k.max_iters, k.damping, k.pos_tol, k.rot_tol, k.max_step = int(max_solver_iters), float(damping), float(pos_tol), float(rot_tol), float(max_step_size)
+        k.respect_limits = int(bool(respect_joint_limit))
+        for i in range(3):
+            k.pos_mask[i] = 1.0 if pos_mask[i] else 0.0
+            k.rot_mask[i] = 1.0 if rot_mask[i] else 0.0
+        q_out = torch.empty((B, self.nu), dtype=torch.float32, device=dev)
+        err = torch.empty((B, 2), dtype=torch.float32, device=dev) if return_error else None
+        iters = torch.empty(B, dtype=torch.int32, device=dev) if return_iters else None
+        self._check(self.lib.gg_ik(self._h, B, _ptr(idx), _ptr(pos), _ptr(quat), _ptr(init_qpos), _ptr(q_out), _ptr(err), _ptr(iters),
+                                   C.byref(k), self._stream()))
+        out = (q_out,) + ((err,) if return_error else ()) + ((iters,) if return_iters else ())
+        return out[0] if len(out) == 1 else out
+
     def stats(self, clear=False) -> torch.Tensor:
         """[env-steps, episodes finished, successes, return sum, length sum, non-finite resets, solver iterations, contacts]."""
         self._check(self.lib.gg_stats(self._h, _ptr(self._stats), int(clear), self._stream()))

@@ -58,6 +58,21 @@ class _Robot:
     def get_dofs_velocity(self):
         return self._task.sim.get_state()[1][:, : self._task.sim.nu]
 
+    def inverse_kinematics(self, link=None, pos=None, quat=None, init_qpos=None, respect_joint_limit=True, max_samples=50,
+                           max_solver_iters=20, damping=0.01, pos_tol=5e-4, rot_tol=5e-3, pos_mask=(True, True, True),
+                           rot_mask=(True, True, True), max_step_size=0.5, dofs_idx_local=None, return_error=False, envs_idx=None):
+        """Genesis' `robot.inverse_kinematics(link=eef, pos=, quat=, envs_idx=)` as the reference experts call it
+        (examples/franka/pick_cube_state.py:46-51): batched damped least squares on the GPU, returns qpos (B, n_dof).
+        Only the end-effector link is supported; `max_samples` is accepted and ignored (first sample only, see gg_ik.cuh)."""
+        if link is not None and link is not self._task.eef:
+            raise NotImplementedError("inverse_kinematics: only the end-effector link (get_link('hand')) is supported")
+        if dofs_idx_local is not None:
+            raise NotImplementedError("inverse_kinematics: dofs_idx_local is not supported")
+        return self._task.sim.inverse_kinematics(pos=pos, quat=quat, init_qpos=init_qpos, envs_idx=envs_idx,
+                                                 respect_joint_limit=respect_joint_limit, max_solver_iters=max_solver_iters,
+                                                 damping=damping, pos_tol=pos_tol, rot_tol=rot_tol, pos_mask=pos_mask,
+                                                 rot_mask=rot_mask, max_step_size=max_step_size, return_error=return_error)
+
     def control_dofs_position(self, position, dofs_idx_local=None):
         idx = slice(None) if dofs_idx_local is None else torch.as_tensor(np.asarray(dofs_idx_local), device=self._task.sim.device)
         self._task._targets[:, idx] = torch.as_tensor(position, dtype=torch.float32, device=self._task.sim.device)

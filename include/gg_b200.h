@@ -17,6 +17,9 @@
  *   gg_step_host     <- the same calls with host numpy arrays as the reference passes / receives them
  *                       (README.md:34 numpy action; cube_pick.py:130-135 numpy reward; env.py:63-65 numpy flags)
  *   gg_stats         <- (new) per-shard episode statistics for the optional NCCL all-gather
+ *   gg_ik            <- robot.inverse_kinematics(link=eef, pos=, quat=, envs_idx=)   examples/franka/pick_cube_state.py:46-51,
+ *                       examples/franka/stack_cube_state.py:78-83, examples/so_101/collect_task_stack_cube_batch.py:88-94
+ *                       (the caller-side step of every expert policy)
  *
  * Conventions: plain pointers and sizes only; every pointer argument of gg_step / gg_reset is a
  * DEVICE pointer into caller-owned (torch) memory unless stated otherwise; all work is enqueued
@@ -134,6 +137,28 @@ int gg_observe(GgSim* sim, float* obs_agent, float* obs_env, float* reward, uint
  * [0] env-steps, [1] episodes finished, [2] successes, [3] return sum, [4] length sum,
  * [5] non-finite envs auto-reset, [6] solver iterations sum, [7] contacts sum. */
 int gg_stats(GgSim* sim, double* out8, int clear, gg_stream_t stream);
+
+/* Batched inverse kinematics of the observed end-effector link (damped least squares, Genesis'
+ * `RigidEntity.inverse_kinematics` defaults below; first sample only, see csrc/gg_ik.cuh).
+ * Zero-initialise and call gg_ik_defaults() to get: max_iters 20, damping 0.01, pos_tol 5e-4, rot_tol 5e-3,
+ * max_step 0.5, respect_limits 1, masks all 1. */
+typedef struct GgIkConfig {
+    int32_t max_iters;        /* max_solver_iters: DLS updates per env                                  */
+    float damping;            /* J^T (J J^T + damping^2 I)^-1                                            */
+    float pos_tol, rot_tol;   /* solved when |e_pos| < pos_tol and |e_rot| < rot_tol (m, rad)            */
+    float max_step;           /* max_step_size: per-dof clamp of one update (rad)                        */
+    int32_t respect_limits;   /* respect_joint_limit: clip to [lim_lo, lim_hi] after every update        */
+    float pos_mask[3], rot_mask[3]; /* pos_mask / rot_mask: 1 = constrain this world axis, 0 = free      */
+} GgIkConfig;
+void gg_ik_defaults(GgIkConfig* cfg);
+
+/* n_rows IK problems.  Row r belongs to env envs_idx[r] (NULL: env r; then n_rows <= n_envs).
+ * target_pos (n_rows, 3) / target_quat (n_rows, 4, wxyz): DEVICE pointers; either may be NULL (that half of the pose is
+ * left free).  init_q (n_rows, n_dof) nullable: start from the env's current joint positions (Genesis init_qpos=None).
+ * q_out (n_rows, n_dof): solution, gripper dofs copied from the start configuration.  err_out (n_rows, 2) nullable:
+ * final |e_pos|, |e_rot|.  iters_out (n_rows) nullable: DLS updates applied.  The simulation state is not modified. */
+int gg_ik(GgSim* sim, int n_rows, const int32_t* envs_idx, const float* target_pos, const float* target_quat,
+          const float* init_q, float* q_out, float* err_out, int32_t* iters_out, const GgIkConfig* cfg, gg_stream_t stream);
 
 /* Number of kernels this library has launched since load (for bench.py's gpu_launches). */
 int64_t gg_launch_count(void);

@@ -163,6 +163,23 @@ class Oracle:
         m = None if mask is None else np.ascontiguousarray(mask, dtype=np.uint8)
         self._fn("reset")(self.h, C.c_int(n), _p(q), _p(qd), _p(qacc), _p(m) if m is not None else None, _p(xy))
 
+    def ik(self, q_init, target_pos=None, target_quat=None, max_iters=20, damping=0.01, pos_tol=5e-4, rot_tol=5e-3,
+           max_step=0.5, respect_limits=True, mask6=None):
+        """Batched damped-least-squares IK of the eef body (restates robot.inverse_kinematics, reference
+        examples/franka/pick_cube_state.py:46-51).  q_init (n, nu) -> (q (n, nu), err (n, 2), iters (n))."""
+        q_init = self._a(q_init)
+        n = q_init.shape[0]
+        tp = None if target_pos is None else self._a(target_pos, (n, 3))
+        tq = None if target_quat is None else self._a(target_quat, (n, 4))
+        mk = np.ascontiguousarray(np.ones(6) if mask6 is None else mask6, dtype=np.float64)
+        q_out = np.zeros((n, self.nu), self.dtype)
+        err = np.zeros((n, 2), self.dtype)
+        iters = np.zeros(n, np.int32)
+        self._fn("ik")(self.h, C.c_int(n), _p(q_init), _p(tp) if tp is not None else None, _p(tq) if tq is not None else None,
+                       C.c_int(max_iters), C.c_double(damping), C.c_double(pos_tol), C.c_double(rot_tol), C.c_double(max_step),
+                       C.c_int(int(respect_limits)), _p(mk), _p(q_out), _p(err), _p(iters))
+        return q_out, err, iters
+
     def new_state(self, n):
         return (np.zeros((n, self.nq), self.dtype), np.zeros((n, self.nv), self.dtype), np.zeros((n, self.nv), self.dtype))
 

@@ -741,6 +741,68 @@ template <class T> static void observe(const Model<T>& m, const T* q, T* agent, 
     *term = succ ? 1 : 0;
 }
 
+// ------------------------------------------------------------------------------------ inverse kinematics
+// Restates robot.inverse_kinematics(link=eef, pos=, quat=) as the reference's expert policies call it
+// (examples/franka/pick_cube_state.py:46-51): Genesis' damped-least-squares iteration [UPSTREAM-RECALL]
+//     e = [target_pos - pos ; rotvec(target_quat * conj(quat))] (masked),  solved: |e_pos| < pos_tol and |e_rot| < rot_tol
+//     dq = J^T (J J^T + damping^2 I)^-1 e over the dofs that move the link, clamp(|dq_i| <= max_step), clip to joint limits
+// first sample only (init = given q).  Dense Jacobian columns + dense 6x6 Cholesky: deliberately NOT the shifted
+// Gram-matrix formulation the CUDA kernel uses (gym_genesis_b200/csrc/gg_ik.cuh).
+template <class T> static int inverse_kinematics(const Model<T>& m, T* qfull, const T* tpos, const T* tquat, int max_iters, T damping,
+                                                 T pos_tol, T rot_tol, T max_step, int respect_limits, const T* mask6, T* err2) {
+    Kin<T> k;
+    int used = 0;
+    const int b = m.eef_body;
+    for (int it = 0;; it++) {
+        forward_kinematics(m, qfull, k);
+        const T* xp = &k.xpos[b * 3]; const T* xq = &k.xquat[b * 4];
+        T e[6] = {0, 0, 0, 0, 0, 0};
+        if (tpos) for (int c = 0; c < 3; c++) e[c] = (tpos[c] - xp[c]) * mask6[c];
+        if (tquat) {
+            T inv[4] = {xq[0], -xq[1], -xq[2], -xq[3]}, qe[4];
+            quat_mul(tquat, inv, qe);
+            T sg = qe[0] < 0 ? (T)-1 : (T)1;
+            T s = std::sqrt(qe[1] * qe[1] + qe[2] * qe[2] + qe[3] * qe[3]);
+            T kk = 2 * sg;
+            if (s > (T)1e-9) kk = sg * 2 * std::atan2(s, std::fabs(qe[0])) / s;
+            for (int c = 0; c < 3; c++) e[3 + c] = qe[1 + c] * kk * mask6[3 + c];
+        }
+        err2[0] = std::sqrt(e[0] * e[0] + e[1] * e[1] + e[2] * e[2]);
+        err2[1] = std::sqrt(e[3] * e[3] + e[4] * e[4] + e[5] * e[5]);
+        if ((err2[0] < pos_tol && err2[1] < rot_tol) || it >= max_iters) break;
+        used++;
+        std::vector<int> dofs;
+        for (int d = 0; d < m.nu; d++) if (m.affects[b * m.nv + d]) dofs.push_back(d);
+        const int nd = (int)dofs.size();
+        std::vector<T> J(6 * nd);
+        for (int j = 0; j < nd; j++) {
+            T jv[3], jw[3];
+            jac_col(m, k, b, dofs[j], xp, jv, jw);
+            for (int c = 0; c < 3; c++) { J[c * nd + j] = jv[c]; J[(3 + c) * nd + j] = jw[c]; }
+        }
+        std::vector<T> A(36, 0);
+        for (int r = 0; r < 6; r++)
+            for (int c = 0; c < 6; c++) {
+                T s = r == c ? damping * damping : (T)0;
+                for (int j = 0; j < nd; j++) s += J[r * nd + j] * J[c * nd + j];
+                A[r * 6 + c] = s;
+            }
+        T y[6];
+        chol(A, 6);
+        chol_solve(A, 6, e, y);
+        for (int j = 0; j < nd; j++) {
+            T dq = 0;
+            for (int r = 0; r < 6; r++) dq += J[r * nd + j] * y[r];
+            dq = std::min(std::max(dq, -max_step), max_step);
+            const int d = dofs[j];
+            T nq = qfull[d] + dq;                               // robot dofs: qadr == dofadr (hinge / slide only)
+            if (respect_limits && m.limited[d]) nq = std::min(std::max(nq, m.lim_lo[d]), m.lim_hi[d]);
+            qfull[d] = nq;
+        }
+    }
+    return used;
+}
+
 // ------------------------------------------------------------------------------------ Philox4x32-10
 static inline void philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
     uint32_t c0 = ctr[0], c1 = ctr[1], c2 = ctr[2], c3 = ctr[3], k0 = key[0], k1 = key[1];
@@ -852,6 +914,25 @@ void orc_spawn_xy(const void* hv, uint64_t seed, uint32_t env_id, uint32_t episo
             qq[m.nu] = xy[e * 2]; qq[m.nu + 1] = xy[e * 2 + 1]; qq[m.nu + 2] = m.opt[OPT_SPAWN_Z];                   \
             for (int i = 0; i < 4; i++) qq[m.nu + 3 + i] = m.spawn_quat[i];                                          \
             for (int i = 0; i < m.nv; i++) { qd[(size_t)e * m.nv + i] = 0; qacc[(size_t)e * m.nv + i] = 0; }         \
+        }                                                                                                            \
+    }                                                                                                                \
+    /* batched IK of the eef body: q_init / q_out (n, nu); tpos (n,3) / tquat (n,4) nullable; err (n,2); iters (n) */   \
+    void orc_ik_##SUF(const void* hv, int n, const T* q_init, const T* tpos, const T* tquat, int max_iters, double damping, \
+                      double pos_tol, double rot_tol, double max_step, int respect_limits, const double* mask6, T* q_out, \
+                      T* err, int32_t* iters) {                                                                      \
+        const Model<T>& m = Pick<T>::get((const Handle*)hv);                                                         \
+        T mk[6]; for (int i = 0; i < 6; i++) mk[i] = (T)mask6[i];                                                    \
+        for (int e = 0; e < n; e++) {                                                                                \
+            std::vector<T> qf(m.nq, 0);                                                                              \
+            for (int i = 0; i < m.nu; i++) qf[i] = q_init[(size_t)e * m.nu + i];                                     \
+            qf[m.nu + 3] = 1;                                                                                        \
+            T e2[2];                                                                                                 \
+            int it = inverse_kinematics(m, qf.data(), tpos ? tpos + (size_t)e * 3 : (const T*)nullptr,               \
+                                        tquat ? tquat + (size_t)e * 4 : (const T*)nullptr, max_iters, (T)damping,   \
+                                        (T)pos_tol, (T)rot_tol, (T)max_step, respect_limits, mk, e2);                \
+            for (int i = 0; i < m.nu; i++) q_out[(size_t)e * m.nu + i] = qf[i];                                      \
+            if (err) { err[e * 2] = e2[0]; err[e * 2 + 1] = e2[1]; }                                                 \
+            if (iters) iters[e] = it;                                                                                \
         }                                                                                                            \
     }                                                                                                                \
     /* inverse weights recomputed from scratch at q0 (robot dofs) -- independent of the host model compiler */       \

@@ -4,6 +4,7 @@
 #include <stdint.h>
 #include <string.h>
 #include "gg_env.cuh"
+#include "gg_ik.cuh"
 
 template <int NA, int NF, bool FH>
 static void run(const GgModel* M, int n, float* q, float* qd, float* qacc, const float* target, int iterations, float tol,
@@ -79,5 +80,24 @@ extern "C" void hs_pads_may_touch(const GgModel* M, int n, const float* q, uint8
             gg::robot_pad_frames<5, 1, true>(*M, pq, D);
             out[e] = gg::pads_may_touch<5, 1>(*M, D, gg::mk(pq[6], pq[7], pq[8]));
         }
+    }
+}
+
+// batched IK through the device header (gg_ik.cuh), one row at a time
+extern "C" void hs_ik(const GgModel* M, const GgIkConfig* K, int n, const float* q_init, const float* tpos, const float* tquat,
+                      float* q_out, float* err, int32_t* iters) {
+    const int nu = M->n_arm + M->n_fing;
+    for (int e = 0; e < n; e++) {
+        float q[GG_MAX_DOF];
+        for (int i = 0; i < nu; i++) q[i] = q_init[(size_t)e * nu + i];
+        GgIkConfig k = *K;
+        gg::V3 tp = gg::mk(0.f, 0.f, 0.f); gg::Q4 tq = gg::mkq(1.f, 0.f, 0.f, 0.f);
+        if (tpos) tp = gg::ld3(tpos + (size_t)e * 3); else k.pos_mask[0] = k.pos_mask[1] = k.pos_mask[2] = 0.f;
+        if (tquat) tq = gg::ldq(tquat + (size_t)e * 4); else k.rot_mask[0] = k.rot_mask[1] = k.rot_mask[2] = 0.f;
+        float pe, re;
+        int it = M->n_arm == 7 ? gg::env_ik<7>(*M, k, q, tp, tq, pe, re) : gg::env_ik<5>(*M, k, q, tp, tq, pe, re);
+        for (int i = 0; i < nu; i++) q_out[(size_t)e * nu + i] = q[i];
+        if (err) { err[2 * e] = pe; err[2 * e + 1] = re; }
+        if (iters) iters[e] = it;
     }
 }
