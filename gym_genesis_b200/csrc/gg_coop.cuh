@@ -34,7 +34,8 @@ template <int NA, int NF> struct TeamWork {          // published by the MAIN la
 template <int NV> struct TeamBuf {
     static constexpr int NH = NV * (NV + 1) / 2;
     float F[GG_TEAM_CAP][18];     // spatial forces (moment about O, direction) of n, t1, t2; first p, n while colliding
-    float Wc[GG_TEAM_CAP][8];     // per-iteration weights Wnn Wn1 W11 Wn2 W22 gn g1 g2
+    float Wc[8][GG_TEAM_CAP];     // per-iteration weights Wnn Wn1 W11 Wn2 W22 gn g1 g2, component-major: the writer is lane = contact
+                                  // (a [contact][8] layout is an 8-way bank conflict), the readers broadcast one contact
     float depth[GG_MAX_CONTACTS];
     int code[GG_MAX_CONTACTS];
     float TB[NV][6];                  // twist of every dof about O (angular, linear)
@@ -316,8 +317,8 @@ __device__ __noinline__ void team_solve(const GgModel& M, const TeamWork<NA, NF>
                         else { Wn2 += Dk[s] * sm; W22 += Dk[s] * mu * mu; g2 += Dk[s] * jar * sm; }
                     }
                 }
-                float* w = B.Wc[c];
-                w[0] = Wnn; w[1] = Wn1; w[2] = W11; w[3] = Wn2; w[4] = W22; w[5] = gn; w[6] = g1; w[7] = g2;
+                B.Wc[0][c] = Wnn; B.Wc[1][c] = Wn1; B.Wc[2][c] = W11; B.Wc[3][c] = Wn2; B.Wc[4][c] = W22;
+                B.Wc[5][c] = gn; B.Wc[6][c] = g1; B.Wc[7][c] = g2;
             }
         }
         __syncwarp();
@@ -332,8 +333,8 @@ __device__ __noinline__ void team_solve(const GgModel& M, const TeamWork<NA, NF>
             int cur = -1;
 #pragma unroll 1
             for (int c = 0; c < ncon; c++) {
-                const float* w = B.Wc[c];
-                if (w[0] == 0.f) continue;                      // no active row (uniform across the warp)
+                if (B.Wc[0][c] == 0.f) continue;                // no active row (uniform across the warp)
+                const float w[8] = {B.Wc[0][c], B.Wc[1][c], B.Wc[2][c], B.Wc[3][c], B.Wc[4][c], B.Wc[5][c], B.Wc[6][c], B.Wc[7][c]};
                 const int code = B.code[c];
                 if (code != cur) {
                     if (cur >= 0) { if (lane < 21) B.Phi[cur][lane] += acc; else if (lane < 27) B.gF[cur][lane - 21] += acc; }

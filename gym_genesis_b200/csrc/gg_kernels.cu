@@ -46,6 +46,7 @@ struct StepArgs {
     int auto_reset, time_limit; float reset_prob;
     uint64_t seed; int64_t first_env; uint32_t step_index;
     double* stats;
+    float* team_scratch;      // n_envs x sizeof(TeamWork) / 4 floats: dynamics of coupled envs, published by their MAIN lane
 };
 
 template <int NU> __device__ __forceinline__ void load_state(const float* __restrict__ st, int stride, int e, gg::EnvState<NU>& s) {
@@ -99,9 +100,10 @@ template <int NU> __device__ __forceinline__ void store_state(float* __restrict_
 //
 // Envs whose pads may touch the cube or the plane ("coupled", decided by the CUBE warp's broad phase) leave the
 // thread-per-env mapping: after barrier 1 the three warps of the block become three solver teams and work through the
-// block's coupled envs ONE WARP PER ENV (gg_coop.cuh; 10 KB of shared memory per team), MAIN lanes publishing their env's
-// dynamics through shared memory (barriers 4 / 5 bracket every round of three envs).  Blocks without coupled envs never
-// execute that code.  (Tried and measured, profiles/r01_notes.md: team buffers in a global scratch slice -- 1.5x slower
+// block's coupled envs ONE WARP PER ENV (gg_coop.cuh; 10 KB of shared memory per team).  The MAIN lane of a coupled env
+// publishes its dynamics to the env's slot of a global scratch slab (832 B, L2 resident); after barrier 4 the teams pop
+// envs from a block-local queue (team_queue) until it is empty, barrier 5.  Blocks without coupled envs never execute
+// that code.  (Tried and measured, profiles/r01_notes.md: team buffers in a global scratch slice -- 1.5x slower
 // teams; a second, device-launched kernel for the coupled envs (CUDA dynamic parallelism tail launch) -- 2.6x slower.)
 // ------------------------------------------------------------------------------------------------
 constexpr int kBlockThreads = 96;
@@ -129,6 +131,7 @@ template <int NU> struct Xchg {
     int coupled[32];          // CUBE -> MAIN
     int iters[32], ncon[32];  // MAIN / teams -> CUBE (statistics)
     int bad[2][32];           // non-finite flags: [0] robot (MAIN), [1] cube (CUBE)
+    int next;                 // head of the block's queue of coupled envs (solver teams pop with atomicAdd)
 };
 
 // PD targets of one env for robot_rnea_t: the staged slab in shared memory (after the cp.async group has landed), the action
@@ -163,16 +166,30 @@ __device__ __forceinline__ bool reset_decision(const StepArgs& A, int e, uint32_
     return r;
 }
 
-// one round of the solver-team protocol for the warp `team`: solve the (r0 + team)-th deferred env of the block
+// Solver-team work queue: the three warps of the block pop the block's coupled envs one at a time (X.next), pull the env's
+// published dynamics from the global scratch slab into their shared-memory TeamWork (7 coalesced 128-byte lines) and solve it
+// warp-cooperatively.  No barrier between envs: a team that drew a cheap env (few contacts, warm start already optimal) moves
+// straight on to the next one instead of waiting for the slowest of three (the lock-step rounds this replaces spent 27 % of
+// their stall samples in bar.sync, profiles/r01_v7_grasp_*).
 template <int NA, int NF, bool FH, int NU>
-__device__ __forceinline__ void team_round(const StepArgs& A, gg::TeamWork<NA, NF>* TW, gg::TeamBuf<NU + 6>* TB, Xchg<NU>& X, unsigned cm,
-                                           int ncpl, int r0, int team, int lane) {
-    const int k = r0 + team;
-    if (k < ncpl) {
+__device__ __forceinline__ void team_queue(const StepArgs& A, gg::TeamWork<NA, NF>* TW, gg::TeamBuf<NU + 6>* TB, Xchg<NU>& X, unsigned cm,
+                                           int ncpl, int team, int lane) {
+    constexpr int TWF = sizeof(gg::TeamWork<NA, NF>) / sizeof(float);
+    for (;;) {
+        int k = 0;
+        if (lane == 0) k = atomicAdd(&X.next, 1);
+        k = __shfl_sync(0xffffffffu, k, 0);
+        if (k >= ncpl) break;
         const int el = __fns(cm, 0, k + 1);
+        const float* src = A.team_scratch + (size_t)(blockIdx.x * 32 + el) * TWF;
+        float* dst = reinterpret_cast<float*>(&TW[team]);
+#pragma unroll 1
+        for (int i = lane; i < TWF; i += 32) dst[i] = __ldcg(src + i);
+        __syncwarp();
         int its, nc;
         gg::team_solve<NA, NF, FH>(A.M, TW[team], TB[team], A.iterations, A.tol, lane, &X.aout[0][el], 32, its, nc);
         if (lane == 0) { X.iters[el] = its; X.ncon[el] = nc; }
+        __syncwarp();
     }
     __threadfence_block();
 }
@@ -189,6 +206,7 @@ __global__ void __launch_bounds__(kBlockThreads, GG_MINBLOCKS) step_kernel(const
     // (per-contact J, aref, D, u, w)
     static_assert(sizeof(TB) >= (gg::LinkStoreStrided<NA>::FLOATS + gg::CubeConStrided::FLOATS) * 32 * sizeof(float), "team buffers too small for the scratch views");
     const int lane = threadIdx.x & 31, role = threadIdx.x >> 5;
+    if (threadIdx.x == 64) X.next = 0;                    // CUBE lane 0: ordered before every pop by barrier 1 (arrive) and barrier 4
     const int e0 = blockIdx.x * 32 + lane;
     const bool live = e0 < A.n;
     const int e = live ? e0 : A.n - 1;                    // dead lanes shadow the last env (loads only)
@@ -235,10 +253,9 @@ __global__ void __launch_bounds__(kBlockThreads, GG_MINBLOCKS) step_kernel(const
         bar_sync(1, 96);
         const unsigned cm = __ballot_sync(0xffffffffu, X.coupled[lane] != 0);
         const int ncpl = __popc(cm);
-#pragma unroll 1
-        for (int r0 = 0; r0 < ncpl; r0 += 3) {            // solver team 1 (see MAIN for the round protocol)
+        if (ncpl > 0) {                                   // solver team 1 (see MAIN for the protocol)
             bar_sync(4, 96);
-            team_round<NA, NF, FH, NU>(A, TW, TB, X, cm, ncpl, r0, 1, lane);
+            team_queue<NA, NF, FH, NU>(A, TW, TB, X, cm, ncpl, 1, lane);
             bar_sync(5, 96);
         }
 #ifndef GG_NO_SPLIT_EEF
@@ -295,13 +312,13 @@ __global__ void __launch_bounds__(kBlockThreads, GG_MINBLOCKS) step_kernel(const
             if (TEAMS) {
                 const unsigned cm = __ballot_sync(0xffffffffu, coupled);
                 const int ncpl = __popc(cm);
-                const int myrank = __popc(cm & ((1u << lane) - 1u));
-#pragma unroll 1
-                for (int r0 = 0; r0 < ncpl; r0 += 3) {
-                    // round protocol: the MAIN lanes of the next three coupled envs publish their dynamics, barrier 4,
-                    // every warp solves one env (team t = role takes the (r0 + t)-th coupled env), barrier 5
-                    if (coupled && myrank >= r0 && myrank < r0 + 3) {
-                        gg::TeamWork<NA, NF>& W = TW[myrank - r0];
+                if (ncpl > 0) {
+                    // protocol: the MAIN lane of every coupled env publishes its dynamics to the env's slot of the global scratch
+                    // slab (L2 resident), barrier 4 (the team buffers are free of MAIN's / CUBE's scratch views from here on),
+                    // the three warps drain the block's queue of coupled envs, barrier 5 (accelerations are in X.aout)
+                    if (coupled) {
+                        constexpr int TWF = sizeof(gg::TeamWork<NA, NF>) / sizeof(float);
+                        gg::TeamWork<NA, NF>& W = *reinterpret_cast<gg::TeamWork<NA, NF>*>(A.team_scratch + (size_t)e0 * TWF);
 #pragma unroll
                         for (int i = 0; i < NU * (NU + 1) / 2; i++) W.Mt[i] = D.Mt[i];
 #pragma unroll
@@ -331,7 +348,7 @@ __global__ void __launch_bounds__(kBlockThreads, GG_MINBLOCKS) step_kernel(const
                     }
                     __threadfence_block();
                     bar_sync(4, 96);
-                    team_round<NA, NF, FH, NU>(A, TW, TB, X, cm, ncpl, r0, 0, lane);
+                    team_queue<NA, NF, FH, NU>(A, TW, TB, X, cm, ncpl, 0, lane);
                     bar_sync(5, 96);
                 }
                 if (coupled) {
@@ -453,10 +470,9 @@ __global__ void __launch_bounds__(kBlockThreads, GG_MINBLOCKS) step_kernel(const
             if (TEAMS) {
                 const unsigned cm = __ballot_sync(0xffffffffu, coupled);
                 const int ncpl = __popc(cm);
-#pragma unroll 1
-                for (int r0 = 0; r0 < ncpl; r0 += 3) {        // solver team 2 (see MAIN for the round protocol)
+                if (ncpl > 0) {                               // solver team 2 (see MAIN for the protocol)
                     bar_sync(4, 96);
-                    team_round<NA, NF, FH, NU>(A, TW, TB, X, cm, ncpl, r0, 2, lane);
+                    team_queue<NA, NF, FH, NU>(A, TW, TB, X, cm, ncpl, 2, lane);
                     bar_sync(5, 96);
                 }
             }
@@ -647,6 +663,7 @@ struct GgSim {
     int n, device, stride, kind;        // kind: 0 = <7,2,slide>, 1 = <5,1,hinge>
     float* state; int32_t* step_count; int32_t* episode;
     uint8_t* done; double* stats;       // library-owned (allocated once in gg_create)
+    float* team_scratch;                // library-owned: published dynamics of coupled envs (step_kernel solver teams)
     uint32_t step_index;
     static constexpr int kPinCache = 16;
     const void* pin_ok[kPinCache]; int pin_next;   // pointers already verified as pinned host memory (gg_step_host)
@@ -659,7 +676,7 @@ static int launch_step(GgSim* sim, StepArgs& A, gg_stream_t stream) {
     A.iterations = sim->cfg.solver_iterations; A.tol = sim->cfg.solver_tolerance;
     A.auto_reset = sim->cfg.auto_reset; A.time_limit = sim->cfg.time_limit; A.reset_prob = sim->cfg.reset_prob;
     A.seed = sim->cfg.seed; A.first_env = sim->cfg.first_env_id; A.step_index = sim->step_index;
-    A.stats = sim->stats;
+    A.stats = sim->stats; A.team_scratch = sim->team_scratch;
     const int grid = (sim->n + 31) / 32;                 // 32 envs x 3 role warps per block
     GG_CUDA(cudaSetDevice(sim->device));
     if (sim->kind == 0) step_kernel<7, 2, false><<<grid, kBlockThreads, 0, (cudaStream_t)stream>>>(A);
@@ -696,7 +713,12 @@ int gg_create(const GgModel* model, int n_envs, int device, GgSim** out) {
     s->cfg.solver_iterations = 10; s->cfg.solver_tolerance = 1e-5f;
     cudaError_t e1 = cudaMalloc(&s->done, (size_t)s->stride);
     cudaError_t e2 = cudaMalloc(&s->stats, 8 * sizeof(double));
-    if (e1 != cudaSuccess || e2 != cudaSuccess) { cudaFree(s->done); cudaFree(s->stats); delete s; return fail("gg_create: cudaMalloc failed%s"); }
+    const size_t twf = kind == 0 ? sizeof(gg::TeamWork<7, 2>) : sizeof(gg::TeamWork<5, 1>);
+    cudaError_t e3 = cudaMalloc(&s->team_scratch, (size_t)s->stride * twf);
+    if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) {
+        cudaFree(s->done); cudaFree(s->stats); cudaFree(s->team_scratch); delete s;
+        return fail("gg_create: cudaMalloc failed%s");
+    }
     cudaMemset(s->done, 0, (size_t)s->stride);
     cudaMemset(s->stats, 0, 8 * sizeof(double));
     *out = s;
@@ -706,7 +728,7 @@ int gg_create(const GgModel* model, int n_envs, int device, GgSim** out) {
 int gg_destroy(GgSim* sim) {
     if (!sim) return 0;
     cudaSetDevice(sim->device);
-    cudaFree(sim->done); cudaFree(sim->stats);
+    cudaFree(sim->done); cudaFree(sim->stats); cudaFree(sim->team_scratch);
     delete sim;
     return 0;
 }
