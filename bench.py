@@ -160,7 +160,7 @@ def run_reference(args):
            "cpu_baseline": {"value": v, "unit": "env-steps/s", "cores": threads, "kind": "port", "sample": sample,
                             "note": "Genesis (the reference's physics dependency) is not installable here; this is the oracle restatement"},
            "e2e": {"value": v, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(out))
+    args.out.emit(out)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -312,10 +312,13 @@ def run_gpu(args):
         eef = robot.get_link("hand")
         quat = torch.tensor([0.0, 1.0, 0.0, 0.0], device=dev).expand(n, -1)
         idx = torch.arange(n, device=dev)
+        from gym_genesis_b200.recorder import TrajectoryRecorder
+        rec = TrajectoryRecorder(envc._env.sim, 200)
         for w in range(2):                                                                                        # episode 0 = warm-up
             obs, _ = envc.reset(seed=args.seed + w)
+            rec.begin_episode()
             succ = torch.zeros(n, dtype=torch.bool, device=dev)
-            evc = [tuple(torch.cuda.Event(enable_timing=True) for _ in range(3)) for _ in range(200)]
+            evc = [tuple(torch.cuda.Event(enable_timing=True) for _ in range(4)) for _ in range(200)]
             t = 0
             for dz, grip in [(0.115, 0.04), (0.115, 0.04), (0.03, -0.02), (0.03, -0.02), (0.25, -0.02)]:
                 off = torch.tensor([0.0, 0.0, dz], device=dev)
@@ -325,18 +328,32 @@ def run_gpu(args):
                     evc[t][0].record()
                     qpos = robot.inverse_kinematics(link=eef, pos=obs["environment_state"][:, :3] + off, quat=quat, envs_idx=idx)
                     evc[t][1].record()
-                    obs, reward, terminated, truncated, info = envc.step(torch.cat([qpos[:, :-2], gr], dim=1))
+                    action = torch.cat([qpos[:, :-2], gr], dim=1)
+                    obs, reward, terminated, truncated, info = envc.step(action)
                     evc[t][2].record()
+                    rec.record(t, action)
+                    evc[t][3].record()
                     succ |= terminated
                     t += 1
+            x0, x1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            flush.fill_(1)
+            x0.record()
+            frames, env_ids = rec.export_successful()                                                         # compaction + ONE D2H copy
+            x1.record()
             torch.cuda.synchronize(dev)
-        tik = np.array([a.elapsed_time(b) for a, b, c in evc])
-        tall = np.array([a.elapsed_time(c) for a, b, c in evc])
+        tik = np.array([e[0].elapsed_time(e[1]) for e in evc])
+        tall = np.array([e[0].elapsed_time(e[3]) for e in evc])
+        trec = np.array([e[2].elapsed_time(e[3]) for e in evc])
+        fbytes = n * rec.frame_dim * 4
         wc = {"workload": "reference expert closed loop (examples/franka/pick_cube_state.py: hover/stabilize/grasp/grasp/lift x 40 steps), "
-                          "robot.inverse_kinematics + env.step on the device, %d envs" % n,
+                          "robot.inverse_kinematics + env.step + device-side frame recording, %d envs" % n,
               "value": n * 200 / (tall.sum() * 1e-3), "unit": "env-steps/s", "ik_ms_per_launch": float(tik.mean()),
               "ik_solves_per_s": n * 200 / (tik.sum() * 1e-3), "ik_ms_by_stage": [float(tik[i * 40:(i + 1) * 40].mean()) for i in range(5)],
-              "success_rate": float(succ.float().mean().item())}
+              "success_rate": float(succ.float().mean().item()),
+              "record": {"us_per_step": float(trec.mean() * 1e3), "algorithmic_GBps": 2 * fbytes / (trec.mean() * 1e-3) / 1e9,
+                         "bytes_per_step": 2 * fbytes, "note": "gg_record: one copy kernel per step, frames stay on the device"},
+              "export": {"ms_per_episode": float(x0.elapsed_time(x1)), "episodes": int(frames.shape[0]),
+                         "bytes_to_host": int(frames.numel() * 4), "note": "gg_export_successful (select + gather) + one D2H copy of the successful envs"}}
         envc.close()
 
     times = torch.tensor([t_ms, warm_ms, e2e_ms, e2e_copy_ms], dtype=torch.float64, device=dev)
@@ -375,9 +392,23 @@ def run_gpu(args):
             v, dt = cpu_port_run(cn, cs, 3, threads)
             out["cpu_baseline"] = {"value": v, "unit": "env-steps/s", "cores": threads, "kind": "port",
                                    "sample": f"{cn} envs x {cs} steps of the same workload, oracle fp32 build, {threads} host threads ({dt:.1f} s)"}
-        print(json.dumps(out))
+        args.out.emit(out)
     if world > 1:
         dist.destroy_process_group()
+
+
+class JsonStdout:
+    """Keeps stdout to the ONE JSON line of the contract: native libraries (NCCL prints its version banner on stdout under
+    torchrun) and anything else write to stderr while the benchmark runs."""
+
+    def __init__(self):
+        sys.stdout.flush()
+        self._fd = os.dup(1)
+        os.dup2(2, 1)
+
+    def emit(self, obj):
+        sys.stdout.flush()
+        os.write(self._fd, (json.dumps(obj) + "\n").encode())
 
 
 def main():
@@ -392,6 +423,7 @@ def main():
     ap.add_argument("--no-workload-b", action="store_true")
     ap.add_argument("--no-workload-c", action="store_true")
     args = ap.parse_args()
+    args.out = JsonStdout()
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -209,7 +209,7 @@ LIB_NAME = "libgg_b200.so"
 LIB_PATH = os.environ.get("GG_B200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), LIB_NAME)
 EXPORTS = ["gg_last_error", "gg_version", "gg_create", "gg_destroy", "gg_configure", "gg_state_rows", "gg_state_stride",
            "gg_bind_state", "gg_step", "gg_step_host", "gg_reset", "gg_get_state", "gg_set_state", "gg_observe", "gg_stats", "gg_launch_count",
-           "gg_ik", "gg_ik_defaults"]
+           "gg_ik", "gg_ik_defaults", "gg_frame_dim", "gg_record", "gg_export_successful"]
 
 _lib = None
 
@@ -240,6 +240,9 @@ def load_library():
     lib.gg_set_state.argtypes = [vp] * 5
     lib.gg_observe.argtypes = [vp] * 6
     lib.gg_stats.argtypes = [vp, vp, C.c_int, vp]
+    lib.gg_frame_dim.argtypes = [vp]
+    lib.gg_record.argtypes = [vp, vp, vp, C.c_int, C.c_int, vp, vp, vp, vp, vp]
+    lib.gg_export_successful.argtypes = [vp, vp, vp, C.c_int, vp, vp, vp, vp]
     lib.gg_ik_defaults.argtypes = [C.POINTER(GgIkConfig)]
     lib.gg_ik_defaults.restype = None
     lib.gg_ik.argtypes = [vp, C.c_int, vp, vp, vp, vp, vp, vp, vp, C.POINTER(GgIkConfig), vp]

@@ -650,6 +650,63 @@ __global__ void __launch_bounds__(64) ik_kernel(const __grid_constant__ IkArgs A
     if (A.iters_out) A.iters_out[r] = it;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Trajectory store.  Pure data movement, HBM bound:
+//   record_kernel : frame t <- [agent_pos | environment_state | action | reward]; one thread per float, 4 B read + 4 B written,
+//                   consecutive threads write consecutive addresses (the (n, F) frame slab is contiguous)
+//   select_kernel : one block; ordered compaction of the envs whose reward was ever > 0 (block-wide exclusive scan per 1024 envs)
+//   export_kernel : out[slot][t][:] <- traj[t][env][:]; block (x, env) copies a run of (t, c) pairs: reads are F-float runs,
+//                   writes are fully contiguous
+// ------------------------------------------------------------------------------------------------
+__global__ void record_kernel(float* __restrict__ frame, int32_t* __restrict__ ever, int n, int AD, int NU, const float* __restrict__ agent,
+                              const float* __restrict__ envs, const float* __restrict__ action, const float* __restrict__ reward) {
+    const int F = AD + GG_ENV_STATE_DIM + NU + 1;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * F) return;
+    const int e = i / F, c = i - e * F;
+    float v;
+    if (c < AD) v = agent[(size_t)e * AD + c];
+    else if (c < AD + GG_ENV_STATE_DIM) v = envs[(size_t)e * GG_ENV_STATE_DIM + (c - AD)];
+    else if (c < F - 1) v = action[(size_t)e * NU + (c - AD - GG_ENV_STATE_DIM)];
+    else { v = reward[e]; if (v > 0.f) ever[e] = 1; }
+    frame[i] = v;
+}
+
+__global__ void __launch_bounds__(1024) select_kernel(const int32_t* __restrict__ ever, int n, int32_t* __restrict__ slot,
+                                                      int32_t* __restrict__ env_ids, int32_t* __restrict__ count) {
+    __shared__ int wsum[32];
+    __shared__ int base_s;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (threadIdx.x == 0) base_s = 0;
+    __syncthreads();
+    for (int e0 = 0; e0 < n; e0 += 1024) {
+        const int e = e0 + threadIdx.x;
+        const int f = (e < n && ever[e] != 0) ? 1 : 0;
+        const unsigned m = __ballot_sync(0xffffffffu, f);
+        if (lane == 0) wsum[w] = __popc(m);
+        __syncthreads();
+        int off = base_s;
+        for (int k = 0; k < w; k++) off += wsum[k];
+        const int pos = off + __popc(m & ((1u << lane) - 1u));
+        if (e < n) slot[e] = f ? pos : -1;
+        if (f) env_ids[pos] = e;
+        __syncthreads();
+        if (threadIdx.x == 0) { int t = 0; for (int k = 0; k < 32; k++) t += wsum[k]; base_s += t; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *count = base_s;
+}
+
+__global__ void export_kernel(const float* __restrict__ traj, const int32_t* __restrict__ slot, int T, int n, int F, float* __restrict__ out) {
+    const int e = blockIdx.y;
+    const int s = slot[e];
+    if (s < 0) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= T * F) return;
+    const int t = i / F, c = i - t * F;
+    out[(size_t)s * T * F + i] = traj[((size_t)t * n + e) * F + c];
+}
+
 __global__ void stats_kernel(double* stats, double* out, int clear) {
     int i = threadIdx.x;
     if (i < 8) { out[i] = stats[i]; if (clear) stats[i] = 0.0; }
@@ -664,6 +721,7 @@ struct GgSim {
     float* state; int32_t* step_count; int32_t* episode;
     uint8_t* done; double* stats;       // library-owned (allocated once in gg_create)
     float* team_scratch;                // library-owned: published dynamics of coupled envs (step_kernel solver teams)
+    int32_t* slot;                      // library-owned, allocated on first gg_export_successful: env -> compacted episode slot
     uint32_t step_index;
     static constexpr int kPinCache = 16;
     const void* pin_ok[kPinCache]; int pin_next;   // pointers already verified as pinned host memory (gg_step_host)
@@ -728,7 +786,7 @@ int gg_create(const GgModel* model, int n_envs, int device, GgSim** out) {
 int gg_destroy(GgSim* sim) {
     if (!sim) return 0;
     cudaSetDevice(sim->device);
-    cudaFree(sim->done); cudaFree(sim->stats); cudaFree(sim->team_scratch);
+    cudaFree(sim->done); cudaFree(sim->stats); cudaFree(sim->team_scratch); cudaFree(sim->slot);
     delete sim;
     return 0;
 }
@@ -855,6 +913,37 @@ int gg_ik(GgSim* sim, int n_rows, const int32_t* envs_idx, const float* target_p
     if (sim->kind == 0) ik_kernel<7, 2><<<grid, 64, 0, (cudaStream_t)stream>>>(A);
     else ik_kernel<5, 1><<<grid, 64, 0, (cudaStream_t)stream>>>(A);
     g_launches.fetch_add(1);
+    GG_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int gg_frame_dim(const GgSim* sim) { return sim ? (7 + sim->model.n_fing) + GG_ENV_STATE_DIM + (sim->model.n_arm + sim->model.n_fing) + 1 : -1; }
+
+int gg_record(GgSim* sim, float* traj, int32_t* ever, int t, int horizon, const float* action, const float* obs_agent,
+              const float* obs_env, const float* reward, gg_stream_t stream) {
+    if (!sim || !traj || !ever || !action || !obs_agent || !obs_env || !reward) return fail("gg_record: null argument%s");
+    if (t < 0 || t >= horizon) return fail("gg_record: frame index outside the horizon%s");
+    const int F = gg_frame_dim(sim), n = sim->n;
+    GG_CUDA(cudaSetDevice(sim->device));
+    const int total = n * F;
+    record_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(traj + (size_t)t * n * F, ever, n, 7 + sim->model.n_fing,
+                                                                         sim->model.n_arm + sim->model.n_fing, obs_agent, obs_env, action, reward);
+    g_launches.fetch_add(1);
+    GG_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int gg_export_successful(GgSim* sim, const float* traj, const int32_t* ever, int horizon, float* out, int32_t* out_env_ids,
+                         int32_t* out_count, gg_stream_t stream) {
+    if (!sim || !traj || !ever || !out || !out_env_ids || !out_count) return fail("gg_export_successful: null argument%s");
+    if (horizon <= 0) return fail("gg_export_successful: horizon must be positive%s");
+    const int F = gg_frame_dim(sim), n = sim->n;
+    GG_CUDA(cudaSetDevice(sim->device));
+    if (!sim->slot) GG_CUDA(cudaMalloc(&sim->slot, (size_t)sim->stride * sizeof(int32_t)));   // first use only
+    select_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(ever, n, sim->slot, out_env_ids, out_count);
+    dim3 grid((horizon * F + 255) / 256, n);
+    export_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(traj, sim->slot, horizon, n, F, out);
+    g_launches.fetch_add(2);
     GG_CUDA(cudaGetLastError());
     return 0;
 }

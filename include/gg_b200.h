@@ -20,6 +20,10 @@
  *   gg_ik            <- robot.inverse_kinematics(link=eef, pos=, quat=, envs_idx=)   examples/franka/pick_cube_state.py:46-51,
  *                       examples/franka/stack_cube_state.py:78-83, examples/so_101/collect_task_stack_cube_batch.py:88-94
  *                       (the caller-side step of every expert policy)
+ *   gg_record /
+ *   gg_export_successful <- the collectors' per-step `.detach().cpu().numpy()` appends and the "save envs whose reward was ever
+ *                       > 0" loop                                          examples/franka/pick_cube_state.py:86-113
+ *                       (frames stay on the device; one compacted copy per episode)
  *
  * Conventions: plain pointers and sizes only; every pointer argument of gg_step / gg_reset is a
  * DEVICE pointer into caller-owned (torch) memory unless stated otherwise; all work is enqueued
@@ -159,6 +163,22 @@ void gg_ik_defaults(GgIkConfig* cfg);
  * final |e_pos|, |e_rot|.  iters_out (n_rows) nullable: DLS updates applied.  The simulation state is not modified. */
 int gg_ik(GgSim* sim, int n_rows, const int32_t* envs_idx, const float* target_pos, const float* target_quat,
           const float* init_q, float* q_out, float* err_out, int32_t* iters_out, const GgIkConfig* cfg, gg_stream_t stream);
+
+/* Device-side trajectory store for the data collectors (examples/franka/pick_cube_state.py:86-113).
+ * traj: caller-owned DEVICE buffer of (horizon, n_envs, F) float32 frames, F = gg_frame_dim() =
+ * (7 + n_fing) + 11 + n_dof + 1, frame = [agent_pos | environment_state | action | reward].
+ * ever: caller-owned DEVICE int32[n_envs]; gg_record sets ever[e] = 1 when env e's reward is > 0 (the collector's
+ * `np.any(rewards[:, b] > 0)`); the caller zeroes it at episode start.
+ * gg_record(t): frame t of every env <- the given observation / action / reward arrays (the outputs of the gg_step that
+ * consumed `action`, as the reference appends them after env.step).
+ * gg_export_successful: compacts the envs with ever[e] != 0, in env order, into out (n_selected, horizon, F) -- episode-major,
+ * the order LeRobotDataset.add_frame / save_episode receive them -- and writes their env ids and the count (DEVICE int32).
+ * out / out_env_ids must have room for n_envs episodes / ids. */
+int gg_frame_dim(const GgSim* sim);
+int gg_record(GgSim* sim, float* traj, int32_t* ever, int t, int horizon, const float* action, const float* obs_agent,
+              const float* obs_env, const float* reward, gg_stream_t stream);
+int gg_export_successful(GgSim* sim, const float* traj, const int32_t* ever, int horizon, float* out, int32_t* out_env_ids,
+                         int32_t* out_count, gg_stream_t stream);
 
 /* Number of kernels this library has launched since load (for bench.py's gpu_launches). */
 int64_t gg_launch_count(void);
