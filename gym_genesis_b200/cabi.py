@@ -14,6 +14,7 @@ import numpy as np
 from . import model as mdl
 
 GG_MAX_ARM, GG_MAX_FING, GG_MAX_DOF, GG_MAX_PADS, GG_MAX_CONTACTS = 7, 2, 9, 12, 64
+GG_MAX_OBJ, GG_STACK_MAX_CONTACTS, GG_STACK_ENV_STATE_DIM = 5, 96, 14
 
 _f = C.c_float
 _i = C.c_int32
@@ -42,6 +43,12 @@ class GgModel(C.Structure):
         ("home_q", _f * GG_MAX_DOF),
         ("spawn_lo", _f * 2), ("spawn_hi", _f * 2), ("spawn_z", _f), ("spawn_quat", _f * 4), ("success_z", _f),
     ]
+
+
+class GgStackTask(C.Structure):
+    _fields_ = [("n_obj", _i), ("max_contacts", _i),
+                ("spawn_lo", (_f * 2) * GG_MAX_OBJ), ("spawn_hi", (_f * 2) * GG_MAX_OBJ),
+                ("stack_xy", _f), ("stack_z", _f)]
 
 
 class GgConfig(C.Structure):
@@ -187,7 +194,10 @@ def compile_gg(sm: "mdl.SceneModel") -> GgModel:
             _set(g.pad_bound[b], [0, 0, 0, -1])
     cube = B[sm.cube_body]
     cg = [x for x in sm.geoms if x.group == 1]
-    assert len(cg) == 1
+    assert len(cg) == sm.n_obj and [x.body for x in cg] == list(sm.obj_bodies)
+    for x, b in zip(cg, sm.obj_bodies):      # every object is the same box (franka/cube_stack.py:54-77: five 0.04 m cubes)
+        assert np.allclose(x.half, cg[0].half) and np.allclose(x.pos, 0) and B[b].mass == cube.mass
+        assert np.allclose(B[b].inertia, cube.inertia) and abs(body_w[b] - body_w[sm.cube_body]) < 1e-9 * body_w[b]
     _set(g.cube_half, cg[0].half)
     g.cube_mass = cube.mass
     _set(g.cube_inertia, cube.inertia[:3])
@@ -201,6 +211,17 @@ def compile_gg(sm: "mdl.SceneModel") -> GgModel:
     return g
 
 
+def compile_stack_task(sm: "mdl.SceneModel") -> GgStackTask:
+    """Task constants of a multi-object scene (`franka/cube_stack.py:119-196`): spawn ranges and stacking thresholds."""
+    assert sm.task == "stack" and 2 <= sm.n_obj <= GG_MAX_OBJ
+    t = GgStackTask()
+    t.n_obj, t.max_contacts = sm.n_obj, min(sm.max_contacts, GG_STACK_MAX_CONTACTS)
+    for k, (xlo, xhi, ylo, yhi) in enumerate(sm.obj_spawn):
+        _set(t.spawn_lo[k], [xlo, ylo]); _set(t.spawn_hi[k], [xhi, yhi])
+    t.stack_xy, t.stack_z = sm.stack_xy, sm.stack_z
+    return t
+
+
 # ----------------------------------------------------------------------------------------------
 # library loading (no fallback)
 # ----------------------------------------------------------------------------------------------
@@ -209,7 +230,10 @@ LIB_NAME = "libgg_b200.so"
 LIB_PATH = os.environ.get("GG_B200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), LIB_NAME)
 EXPORTS = ["gg_last_error", "gg_version", "gg_create", "gg_destroy", "gg_configure", "gg_state_rows", "gg_state_stride",
            "gg_bind_state", "gg_step", "gg_step_host", "gg_reset", "gg_get_state", "gg_set_state", "gg_observe", "gg_stats", "gg_launch_count",
-           "gg_ik", "gg_ik_defaults", "gg_frame_dim", "gg_record", "gg_export_successful"]
+           "gg_ik", "gg_ik_defaults", "gg_frame_dim", "gg_record", "gg_export_successful",
+           "gg_stack_create", "gg_stack_destroy", "gg_stack_configure", "gg_stack_state_rows", "gg_stack_state_stride",
+           "gg_stack_bind_state", "gg_stack_step", "gg_stack_reset", "gg_stack_get_state", "gg_stack_set_state", "gg_stack_observe",
+           "gg_stack_stats", "gg_stack_info"]
 
 _lib = None
 
@@ -246,6 +270,19 @@ def load_library():
     lib.gg_ik_defaults.argtypes = [C.POINTER(GgIkConfig)]
     lib.gg_ik_defaults.restype = None
     lib.gg_ik.argtypes = [vp, C.c_int, vp, vp, vp, vp, vp, vp, vp, C.POINTER(GgIkConfig), vp]
+    lib.gg_stack_create.argtypes = [C.POINTER(GgModel), C.POINTER(GgStackTask), C.c_int, C.c_int, C.POINTER(vp)]
+    lib.gg_stack_destroy.argtypes = [vp]
+    lib.gg_stack_configure.argtypes = [vp, C.POINTER(GgConfig)]
+    lib.gg_stack_state_rows.argtypes = [vp]
+    lib.gg_stack_state_stride.argtypes = [vp]
+    lib.gg_stack_bind_state.argtypes = [vp, vp, vp, vp]
+    lib.gg_stack_step.argtypes = [vp] * 9
+    lib.gg_stack_reset.argtypes = [vp] * 6
+    lib.gg_stack_get_state.argtypes = [vp] * 5
+    lib.gg_stack_set_state.argtypes = [vp] * 5
+    lib.gg_stack_observe.argtypes = [vp] * 6
+    lib.gg_stack_stats.argtypes = [vp, vp, C.c_int, vp]
+    lib.gg_stack_info.argtypes = [vp, vp, vp, vp]
     for name in EXPORTS:
         getattr(lib, name)
     _lib = lib

@@ -727,6 +727,10 @@ struct GgSim {
     const void* pin_ok[kPinCache]; int pin_next;   // pointers already verified as pinned host memory (gg_step_host)
 };
 
+// hooks for the other translation units of the library (gg_stack.cu): shared error string and launch counter
+int gg_internal_fail(const char* fmt, const char* detail) { return fail(fmt, detail); }
+void gg_internal_count_launches(int k) { g_launches.fetch_add(k); }
+
 static int launch_step(GgSim* sim, StepArgs& A, gg_stream_t stream) {
     if (sim->state == nullptr) return fail("gg_bind_state has not been called%s");
     A.M = sim->model; A.n = sim->n; A.stride = sim->stride;

@@ -1,0 +1,524 @@
+// CUDA kernels (sm_100a) and C ABI of the multi-object (CubeStack) step path: include/gg_b200.h, gg_stack_*.
+// Replaces, for gym_genesis/tasks/franka/cube_stack.py:119-216, the Genesis calls of reset / step / compute_reward / get_obs.
+//
+// One env.step = three launches on the caller's stream (per-env pipeline in gg_stack.cuh):
+//   stack_prep_kernel    thread per env, 32 envs per block.  Masked reset, robot dynamics, pad broad phase, decoupled robot solve.
+//                        The StackIn record of each env (robot dynamics + object states, 297 floats) is transposed through shared
+//                        memory and written env-major, so that both this kernel's stores and the solver's loads are coalesced.
+//   stack_solve_kernel   WARP per env, 4 envs per block, ~23 KB of dynamic shared memory per warp (contact table, pair stiffness,
+//                        39 x 39 packed Hessian).  Accelerations go to a [dof][env] slab.
+//   stack_finish_kernel  thread per env.  Integration, observations, reward / flags, counters, statistics.
+// The records and the slab (22 MB at 16384 envs) stay L2 resident between the three kernels.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <new>
+
+#include "gg_b200.h"
+#include "gg_stack.cuh"
+
+int gg_internal_fail(const char* fmt, const char* detail);
+void gg_internal_count_launches(int k);
+
+namespace {
+
+#define SK_CUDA(call)                                                                              \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) return gg_internal_fail("CUDA error: %s", cudaGetErrorString(e_)); \
+    } while (0)
+
+constexpr unsigned kFullMask = 0xffffffffu;
+
+struct WarpDev {
+    int lane;
+    __device__ __forceinline__ void sync() const { __syncwarp(); }
+    __device__ __forceinline__ float shfl(float v, int src) const { return __shfl_sync(kFullMask, v, src); }
+    __device__ __forceinline__ int shfli(int v, int src) const { return __shfl_sync(kFullMask, v, src); }
+    __device__ __forceinline__ float sum(float v) const {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFullMask, v, o);
+        return v;
+    }
+    __device__ __forceinline__ float max(float v) const {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(kFullMask, v, o));
+        return v;
+    }
+    __device__ __forceinline__ bool any(bool p) const { return __any_sync(kFullMask, p) != 0; }
+    __device__ __forceinline__ int scan_incl(int v) const {
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int u = __shfl_up_sync(kFullMask, v, o);
+            if (lane >= o) v += u;
+        }
+        return v;
+    }
+};
+
+struct StackArgs {
+    GgModel M;
+    GgStackTask T;
+    int n, stride;
+    float* state; int32_t* step_count; int32_t* episode; uint8_t* done;
+    const float* action; float* obs_agent; float* obs_env; float* reward;
+    uint8_t* terminated; uint8_t* truncated;
+    const uint8_t* reset_mask; const float* obj_xy;
+    int mode;                 // 0 = env.step, 1 = reset (+ settle) of masked envs, 2 = observe only
+    int iterations; float tol;
+    int auto_reset, time_limit; float reset_prob;
+    uint64_t seed; int64_t first_env; uint32_t step_index;
+    double* stats;
+    float* work;              // n x sizeof(StackIn) / 4 floats, env-major
+    float* acc;               // NV x stride accelerations, [dof][env]
+    int32_t* ncon; int32_t* iters;
+    uint8_t* flags;           // per env: bit 0 reset applied by this call, bit 1 a substep runs
+};
+
+// state rows: q [0, NU) | qd [NU, 2NU) | objects 13 K | warm start NU + 6 K
+template <int NU, int K> struct Rows {
+    static constexpr int Q = 0, QD = NU, OBJ = 2 * NU, WARM = 2 * NU + 13 * K;
+};
+
+__device__ __forceinline__ bool stack_reset_decision(const StackArgs& A, int e, uint32_t gid) {
+    bool r = false;
+    if (A.mode == 0) {
+        r = (A.reset_mask != nullptr && A.reset_mask[e] != 0) || (A.auto_reset && A.done[e] != 0);
+        if (A.reset_prob > 0.f) {
+            uint32_t o[4];
+            gg::philox4x32_10(gid, A.step_index, 0x52535421u, 0u, (uint32_t)A.seed, (uint32_t)(A.seed >> 32), o);
+            r = r || gg::u01(o[0]) < A.reset_prob;
+        }
+    } else if (A.mode == 1) {
+        r = A.reset_mask == nullptr || A.reset_mask[e] != 0;
+    }
+    return r;
+}
+
+template <int K>
+__device__ __forceinline__ void spawn_objects(const StackArgs& A, int e, uint32_t gid, uint32_t epi, bool use_xy, gg::ObjState<K>& O) {
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+        float x, y;
+        if (use_xy && A.obj_xy != nullptr) { x = A.obj_xy[((size_t)e * K + k) * 2]; y = A.obj_xy[((size_t)e * K + k) * 2 + 1]; }
+        else gg::stack_spawn_draw(A.T, A.seed, gid, epi, k, x, y);
+        O.p[k] = gg::mk(x, y, A.M.spawn_z); O.q[k] = gg::ldq(A.M.spawn_quat);
+        O.v[k] = gg::mk(0.f, 0.f, 0.f); O.w[k] = gg::mk(0.f, 0.f, 0.f);
+    }
+}
+
+template <int NU, int K>
+__device__ __forceinline__ void load_objects(const float* sp, size_t st, gg::ObjState<K>& O) {
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+        const float* c = sp + (Rows<NU, K>::OBJ + 13 * k) * st;
+        O.p[k] = gg::mk(c[0], c[st], c[2 * st]);
+        O.q[k] = gg::mkq(c[3 * st], c[4 * st], c[5 * st], c[6 * st]);
+        O.v[k] = gg::mk(c[7 * st], c[8 * st], c[9 * st]);
+        O.w[k] = gg::mk(c[10 * st], c[11 * st], c[12 * st]);
+    }
+}
+template <int NU, int K>
+__device__ __forceinline__ void store_objects(float* sp, size_t st, const gg::ObjState<K>& O) {
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+        float* c = sp + (Rows<NU, K>::OBJ + 13 * k) * st;
+        c[0] = O.p[k].x; c[st] = O.p[k].y; c[2 * st] = O.p[k].z;
+        c[3 * st] = O.q[k].w; c[4 * st] = O.q[k].x; c[5 * st] = O.q[k].y; c[6 * st] = O.q[k].z;
+        c[7 * st] = O.v[k].x; c[8 * st] = O.v[k].y; c[9 * st] = O.v[k].z;
+        c[10 * st] = O.w[k].x; c[11 * st] = O.w[k].y; c[12 * st] = O.w[k].z;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------ prep
+template <int NA, int NF, bool FH, int K>
+__global__ void __launch_bounds__(32) stack_prep_kernel(const __grid_constant__ StackArgs A) {
+    constexpr int NU = NA + NF, NV = NU + 6 * K;
+    typedef gg::StackIn<NA, NF, K> InT;
+    typedef Rows<NU, K> R;
+    constexpr int WF = sizeof(InT) / sizeof(float);
+    constexpr int WFP = WF | 1;                                   // odd row stride: lane = env writes are conflict free
+    __shared__ float sm[32 * WFP];
+    const int lane = threadIdx.x;
+    const int e0 = blockIdx.x * 32 + lane;
+    const bool live = e0 < A.n;
+    const int e = live ? e0 : A.n - 1;
+    const uint32_t gid = (uint32_t)(A.first_env + e);
+    const size_t st = (size_t)A.stride;
+    float* sp = A.state + e;
+    const bool do_reset = stack_reset_decision(A, e, gid);
+    const bool active = do_reset ? (A.M.settle_steps > 0) : (A.mode == 0);
+    if (live) A.flags[e] = (do_reset ? 1 : 0) | (active ? 2 : 0);
+
+    float q[NU], qd[NU], warm[NU], target[NU];
+    gg::ObjState<K> O;
+    float* rec = sm + lane * WFP;
+    InT& In = *reinterpret_cast<InT*>(rec);                       // row of the transposition buffer
+    if (do_reset) {
+#pragma unroll
+        for (int i = 0; i < NU; i++) { q[i] = A.M.home_q[i]; qd[i] = 0.f; warm[i] = 0.f; }
+        spawn_objects<K>(A, e, gid, (uint32_t)A.episode[e], true, O);
+#pragma unroll
+        for (int k = 0; k < K; k++)
+#pragma unroll
+            for (int i = 0; i < 6; i++) In.warm_obj[k][i] = 0.f;
+        if (live) {
+#pragma unroll
+            for (int i = 0; i < NU; i++) { sp[(R::Q + i) * st] = q[i]; sp[(R::QD + i) * st] = 0.f; }
+            store_objects<NU, K>(sp, st, O);
+#pragma unroll
+            for (int i = 0; i < NV; i++) sp[(R::WARM + i) * st] = 0.f;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < NU; i++) { q[i] = sp[(R::Q + i) * st]; qd[i] = sp[(R::QD + i) * st]; warm[i] = sp[(R::WARM + i) * st]; }
+        load_objects<NU, K>(sp, st, O);
+#pragma unroll
+        for (int k = 0; k < K; k++)
+#pragma unroll
+            for (int i = 0; i < 6; i++) In.warm_obj[k][i] = sp[(R::WARM + NU + 6 * k + i) * st];
+    }
+    const bool use_action = A.mode == 0 && !do_reset;
+#pragma unroll
+    for (int i = 0; i < NU; i++) target[i] = use_action ? A.action[(size_t)e * NU + i] : A.M.home_q[i];
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+        float* o = In.obj[k];
+        o[0] = O.p[k].x; o[1] = O.p[k].y; o[2] = O.p[k].z; o[3] = O.q[k].w; o[4] = O.q[k].x; o[5] = O.q[k].y; o[6] = O.q[k].z;
+        o[7] = O.v[k].x; o[8] = O.v[k].y; o[9] = O.v[k].z; o[10] = O.w[k].x; o[11] = O.w[k].y; o[12] = O.w[k].z;
+    }
+    gg::stack_prep<NA, NF, FH, K>(A.M, q, qd, warm, target, O, A.iterations, A.tol, active && live, In.W);
+    __syncwarp();
+    // coalesced env-major copy of the block's records
+    const int nlive = min(32, A.n - blockIdx.x * 32);
+    float* dst = A.work + (size_t)blockIdx.x * 32 * WF;
+    for (int r = 0; r < nlive; r++)
+        for (int i = lane; i < WF; i += 32) dst[(size_t)r * WF + i] = sm[r * WFP + i];
+}
+
+// ----------------------------------------------------------------------------------------------------------------- solve
+constexpr int kSolveWarps = 4;
+
+template <int NA, int NF, bool FH, int K>
+__global__ void __launch_bounds__(32 * kSolveWarps) stack_solve_kernel(const __grid_constant__ StackArgs A) {
+    constexpr int NU = NA + NF;
+    typedef gg::StackIn<NA, NF, K> InT;
+    typedef gg::StackBuf<NU, K> BufT;
+    constexpr int WF = sizeof(InT) / sizeof(float);
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int e = blockIdx.x * kSolveWarps + warp;
+    if (e >= A.n) return;
+    if (!(A.flags[e] & 2)) return;                                // warp-uniform: this env runs no substep
+    unsigned char* base = smem + (size_t)warp * (sizeof(InT) + sizeof(BufT));
+    InT& In = *reinterpret_cast<InT*>(base);
+    BufT& B = *reinterpret_cast<BufT*>(base + sizeof(InT));
+    {
+        const float* src = A.work + (size_t)e * WF;
+        float* dst = reinterpret_cast<float*>(&In);
+        for (int i = lane; i < WF; i += 32) dst[i] = __ldcg(src + i);
+    }
+    __syncwarp();
+    WarpDev wc{lane};
+    int its = 0, nc = 0;
+    gg::stack_solve<NA, NF, FH, K>(A.M, A.T.max_contacts, In, B, A.iterations, A.tol, wc, A.acc + e, A.stride, its, nc);
+    if (lane == 0) {
+        const int ri = (int)In.W.rob_iters;
+        A.ncon[e] = nc; A.iters[e] = its > ri ? its : ri;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------- finish
+template <int NA, int NF, bool FH, int K>
+__global__ void __launch_bounds__(128) stack_finish_kernel(const __grid_constant__ StackArgs A) {
+    constexpr int NU = NA + NF, NV = NU + 6 * K;
+    typedef Rows<NU, K> R;
+    const int lane = threadIdx.x & 31;
+    const int e0 = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = e0 < A.n;
+    const int e = live ? e0 : A.n - 1;
+    const uint32_t gid = (uint32_t)(A.first_env + e);
+    const size_t st = (size_t)A.stride;
+    float* sp = A.state + e;
+    const int fl = A.mode == 2 ? 0 : A.flags[e];
+    bool do_reset = (fl & 1) != 0;
+    const bool active = (fl & 2) != 0;
+    float st_steps = 0.f, st_done = 0.f, st_succ = 0.f, st_ret = 0.f, st_len = 0.f, st_nan = 0.f, st_iter = 0.f, st_con = 0.f;
+
+    float q[NU], qd[NU], qa[NV];
+    gg::ObjState<K> O;
+#pragma unroll
+    for (int i = 0; i < NU; i++) { q[i] = sp[(R::Q + i) * st]; qd[i] = sp[(R::QD + i) * st]; }
+    load_objects<NU, K>(sp, st, O);
+    int steps = A.step_count[e], epi = A.episode[e];
+    if (do_reset) { epi += 1; steps = 0; }
+    if (active) {
+        float a[NV];
+#pragma unroll
+        for (int i = 0; i < NV; i++) a[i] = A.acc[(size_t)i * st + e];
+        gg::integrate_robot<NU>(A.M, q, qd, qa, a);
+#pragma unroll
+        for (int k = 0; k < K; k++) gg::integrate_cube(A.M, O.p[k], O.q[k], O.v[k], O.w[k], qa + NU + 6 * k, a + NU + 6 * k);
+        st_iter = (float)A.iters[e]; st_con = (float)A.ncon[e];
+        float chk = 0.f;
+#pragma unroll
+        for (int i = 0; i < NU; i++) chk += q[i] + qd[i];
+#pragma unroll
+        for (int k = 0; k < K; k++)
+            chk += O.p[k].x + O.p[k].y + O.p[k].z + O.q[k].w + O.q[k].x + O.q[k].y + O.q[k].z + O.v[k].x + O.v[k].y + O.v[k].z + O.w[k].x +
+                   O.w[k].y + O.w[k].z;
+        if (!isfinite(chk)) {
+            // non-finite env: re-spawn without a substep (counted in the statistics, never thrown from the hot path)
+#pragma unroll
+            for (int i = 0; i < NU; i++) { q[i] = A.M.home_q[i]; qd[i] = 0.f; }
+#pragma unroll
+            for (int i = 0; i < NV; i++) qa[i] = 0.f;
+            spawn_objects<K>(A, e, gid, (uint32_t)epi, false, O);
+            epi += 1; steps = 0; st_nan = 1.f; do_reset = true;
+        }
+    }
+    if (A.mode == 0 && !do_reset) { steps += 1; st_steps = 1.f; }
+    float agent[7 + NF], envs[GG_STACK_ENV_STATE_DIM], rew;
+    bool succ;
+    gg::stack_observe<NA, NF, K>(A.M, A.T, q, O, agent, envs, rew, succ);
+    const bool trunc = A.time_limit && steps >= A.M.horizon;
+    if (live) {
+        float* oa = A.obs_agent + (size_t)e * (7 + NF);
+#pragma unroll
+        for (int i = 0; i < 7 + NF; i++) oa[i] = agent[i];
+        float* oe = A.obs_env + (size_t)e * GG_STACK_ENV_STATE_DIM;
+#pragma unroll
+        for (int i = 0; i < GG_STACK_ENV_STATE_DIM; i++) oe[i] = envs[i];
+        if (A.reward) A.reward[e] = rew;
+        if (A.terminated) A.terminated[e] = succ ? 1 : 0;
+        if (A.truncated) A.truncated[e] = trunc ? 1 : 0;
+        if (A.mode != 2) {
+            A.done[e] = (succ || trunc) ? 1 : 0;
+            if (active) {
+#pragma unroll
+                for (int i = 0; i < NU; i++) { sp[(R::Q + i) * st] = q[i]; sp[(R::QD + i) * st] = qd[i]; }
+                store_objects<NU, K>(sp, st, O);
+#pragma unroll
+                for (int i = 0; i < NV; i++) sp[(R::WARM + i) * st] = qa[i];
+            }
+            A.step_count[e] = steps; A.episode[e] = epi;
+            if (A.mode == 0 && (succ || trunc)) { st_done = 1.f; st_succ = succ ? 1.f : 0.f; st_len = (float)steps; }
+            if (A.mode == 0) st_ret = rew;
+        }
+    } else {
+        st_steps = st_done = st_succ = st_ret = st_len = st_nan = st_iter = st_con = 0.f;
+    }
+    if (A.stats != nullptr && A.mode == 0) {
+        float v[8] = {st_steps, st_done, st_succ, st_ret, st_len, st_nan, st_iter, st_con};
+        float mine = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            float x = v[k];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(kFullMask, x, o);
+            if (lane == k) mine = x;
+        }
+        if (lane < 8 && mine != 0.f) atomicAdd(&A.stats[lane], (double)mine);
+    }
+}
+
+// env-major <-> struct-of-arrays copies (state injection / inspection)
+__global__ void stack_state_copy_kernel(float* state, int stride, int n, int NU, int K, float* q, float* qd, float* qacc, int to_soa) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    const size_t st = (size_t)stride;
+    float* sp = state + e;
+    const int NQ = NU + 7 * K, NV = NU + 6 * K, OBJ = 2 * NU, WARM = 2 * NU + 13 * K;
+    for (int i = 0; i < NU; i++) {
+        if (q) { float* a = q + (size_t)e * NQ + i; float* b = sp + i * st; if (to_soa) *b = *a; else *a = *b; }
+        if (qd) { float* a = qd + (size_t)e * NV + i; float* b = sp + (NU + i) * st; if (to_soa) *b = *a; else *a = *b; }
+    }
+    for (int k = 0; k < K; k++) {
+        for (int i = 0; i < 7; i++)
+            if (q) { float* a = q + (size_t)e * NQ + NU + 7 * k + i; float* b = sp + (OBJ + 13 * k + i) * st; if (to_soa) *b = *a; else *a = *b; }
+        for (int i = 0; i < 6; i++)
+            if (qd) { float* a = qd + (size_t)e * NV + NU + 6 * k + i; float* b = sp + (OBJ + 13 * k + 7 + i) * st; if (to_soa) *b = *a; else *a = *b; }
+    }
+    for (int i = 0; i < NV; i++)
+        if (qacc) { float* a = qacc + (size_t)e * NV + i; float* b = sp + (WARM + i) * st; if (to_soa) *b = *a; else *a = *b; }
+}
+
+__global__ void stack_stats_kernel(double* stats, double* out, int clear) {
+    const int i = threadIdx.x;
+    if (i < 8) { out[i] = stats[i]; if (clear) stats[i] = 0.0; }
+}
+
+}  // namespace
+
+struct GgStackSim {
+    GgModel model;
+    GgStackTask task;
+    GgConfig cfg;
+    int n, device, stride, nu, nv;
+    float* state; int32_t* step_count; int32_t* episode;     // caller-owned
+    uint8_t* done; uint8_t* flags; double* stats;            // library-owned
+    float* work; float* acc; int32_t* ncon; int32_t* iters;
+    uint32_t step_index;
+    size_t solve_smem;
+};
+
+typedef gg::StackIn<7, 2, 5> FrankaIn;
+typedef gg::StackBuf<9, 5> FrankaBuf;
+
+static int stack_launch(GgStackSim* sim, StackArgs& A, gg_stream_t stream) {
+    if (sim->state == nullptr) return gg_internal_fail("gg_stack_bind_state has not been called%s", "");
+    A.M = sim->model; A.T = sim->task; A.n = sim->n; A.stride = sim->stride;
+    A.state = sim->state; A.step_count = sim->step_count; A.episode = sim->episode; A.done = sim->done;
+    A.iterations = sim->cfg.solver_iterations; A.tol = sim->cfg.solver_tolerance;
+    A.auto_reset = sim->cfg.auto_reset; A.time_limit = sim->cfg.time_limit; A.reset_prob = sim->cfg.reset_prob;
+    A.seed = sim->cfg.seed; A.first_env = sim->cfg.first_env_id; A.step_index = sim->step_index;
+    A.stats = sim->stats; A.work = sim->work; A.acc = sim->acc; A.ncon = sim->ncon; A.iters = sim->iters; A.flags = sim->flags;
+    cudaStream_t s = (cudaStream_t)stream;
+    SK_CUDA(cudaSetDevice(sim->device));
+    int launches = 1;
+    if (A.mode != 2) {
+        stack_prep_kernel<7, 2, false, 5><<<(sim->n + 31) / 32, 32, 0, s>>>(A);
+        stack_solve_kernel<7, 2, false, 5><<<(sim->n + kSolveWarps - 1) / kSolveWarps, 32 * kSolveWarps, sim->solve_smem, s>>>(A);
+        launches = 3;
+    }
+    stack_finish_kernel<7, 2, false, 5><<<(sim->n + 127) / 128, 128, 0, s>>>(A);
+    gg_internal_count_launches(launches);
+    SK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" {
+
+int gg_stack_create(const GgModel* model, const GgStackTask* task, int n_envs, int device, GgStackSim** out) {
+    if (!model || !task || !out) return gg_internal_fail("gg_stack_create: null argument%s", "");
+    if (n_envs <= 0) return gg_internal_fail("gg_stack_create: n_envs must be positive%s", "");
+    if (!(model->n_arm == 7 && model->n_fing == 2 && !model->fing_hinge))
+        return gg_internal_fail("gg_stack_create: unsupported articulation (need 7 hinges + 2 slides)%s", "");
+    if (task->n_obj != 5) return gg_internal_fail("gg_stack_create: the stacking scene has 5 cubes (cube_1, cube_2, 3 distractors)%s", "");
+    if (task->max_contacts < 1 || task->max_contacts > GG_STACK_MAX_CONTACTS) return gg_internal_fail("gg_stack_create: max_contacts out of range%s", "");
+    if (model->n_pads < 0 || model->n_pads > GG_MAX_PADS) return gg_internal_fail("gg_stack_create: too many pads%s", "");
+    if (model->power != 2.0f) return gg_internal_fail("gg_stack_create: solimp power must be 2%s", "");
+    if (model->settle_steps < 0 || model->settle_steps > 1) return gg_internal_fail("gg_stack_create: settle_steps must be 0 or 1%s", "");
+    int ndev = 0;
+    SK_CUDA(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return gg_internal_fail("gg_stack_create: bad device index%s", "");
+    SK_CUDA(cudaSetDevice(device));
+    GgStackSim* s = new (std::nothrow) GgStackSim();
+    if (!s) return gg_internal_fail("gg_stack_create: out of host memory%s", "");
+    memset(s, 0, sizeof(*s));
+    s->model = *model; s->task = *task; s->n = n_envs; s->device = device;
+    s->nu = model->n_arm + model->n_fing; s->nv = s->nu + 6 * task->n_obj;
+    s->stride = (n_envs + 31) / 32 * 32;
+    s->cfg.solver_iterations = 10; s->cfg.solver_tolerance = 1e-5f;
+    s->solve_smem = kSolveWarps * (sizeof(FrankaIn) + sizeof(FrankaBuf));
+    cudaError_t e[7];
+    e[0] = cudaMalloc(&s->done, (size_t)s->stride);
+    e[1] = cudaMalloc(&s->flags, (size_t)s->stride);
+    e[2] = cudaMalloc(&s->stats, 8 * sizeof(double));
+    e[3] = cudaMalloc(&s->work, (size_t)s->stride * sizeof(FrankaIn));
+    e[4] = cudaMalloc(&s->acc, (size_t)s->stride * s->nv * sizeof(float));
+    e[5] = cudaMalloc(&s->ncon, (size_t)s->stride * sizeof(int32_t));
+    e[6] = cudaMalloc(&s->iters, (size_t)s->stride * sizeof(int32_t));
+    bool ok = true;
+    for (int i = 0; i < 7; i++) ok = ok && e[i] == cudaSuccess;
+    if (ok) ok = cudaFuncSetAttribute(stack_solve_kernel<7, 2, false, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->solve_smem) == cudaSuccess;
+    if (!ok) {
+        cudaFree(s->done); cudaFree(s->flags); cudaFree(s->stats); cudaFree(s->work); cudaFree(s->acc); cudaFree(s->ncon); cudaFree(s->iters);
+        delete s;
+        return gg_internal_fail("gg_stack_create: device allocation failed%s", "");
+    }
+    cudaMemset(s->done, 0, (size_t)s->stride);
+    cudaMemset(s->flags, 0, (size_t)s->stride);
+    cudaMemset(s->stats, 0, 8 * sizeof(double));
+    cudaMemset(s->ncon, 0, (size_t)s->stride * sizeof(int32_t));
+    cudaMemset(s->iters, 0, (size_t)s->stride * sizeof(int32_t));
+    *out = s;
+    return 0;
+}
+
+int gg_stack_destroy(GgStackSim* s) {
+    if (!s) return 0;
+    cudaSetDevice(s->device);
+    cudaFree(s->done); cudaFree(s->flags); cudaFree(s->stats); cudaFree(s->work); cudaFree(s->acc); cudaFree(s->ncon); cudaFree(s->iters);
+    delete s;
+    return 0;
+}
+
+int gg_stack_configure(GgStackSim* sim, const GgConfig* cfg) {
+    if (!sim || !cfg) return gg_internal_fail("gg_stack_configure: null argument%s", "");
+    if (cfg->solver_iterations < 1 || cfg->solver_iterations > 1000) return gg_internal_fail("gg_stack_configure: solver_iterations out of range%s", "");
+    if (!(cfg->reset_prob >= 0.f && cfg->reset_prob <= 1.f)) return gg_internal_fail("gg_stack_configure: reset_prob out of range%s", "");
+    sim->cfg = *cfg;
+    return 0;
+}
+
+int gg_stack_state_rows(const GgStackSim* sim) { return sim ? 3 * sim->nu + 19 * sim->task.n_obj : -1; }
+int gg_stack_state_stride(const GgStackSim* sim) { return sim ? sim->stride : -1; }
+
+int gg_stack_bind_state(GgStackSim* sim, float* state, int32_t* step_count, int32_t* episode) {
+    if (!sim || !state || !step_count || !episode) return gg_internal_fail("gg_stack_bind_state: null argument%s", "");
+    sim->state = state; sim->step_count = step_count; sim->episode = episode;
+    return 0;
+}
+
+int gg_stack_step(GgStackSim* sim, const float* action, float* obs_agent, float* obs_env, float* reward, uint8_t* terminated,
+                  uint8_t* truncated, const uint8_t* reset_mask, gg_stream_t stream) {
+    if (!sim || !action || !obs_agent || !obs_env) return gg_internal_fail("gg_stack_step: null argument%s", "");
+    StackArgs A;
+    memset(&A, 0, sizeof(A));
+    A.action = action; A.obs_agent = obs_agent; A.obs_env = obs_env; A.reward = reward; A.terminated = terminated;
+    A.truncated = truncated; A.reset_mask = reset_mask; A.mode = 0;
+    const int rc = stack_launch(sim, A, stream);
+    sim->step_index++;
+    return rc;
+}
+
+int gg_stack_reset(GgStackSim* sim, const uint8_t* mask, const float* obj_xy, float* obs_agent, float* obs_env, gg_stream_t stream) {
+    if (!sim || !obs_agent || !obs_env) return gg_internal_fail("gg_stack_reset: null argument%s", "");
+    StackArgs A;
+    memset(&A, 0, sizeof(A));
+    A.obs_agent = obs_agent; A.obs_env = obs_env; A.reset_mask = mask; A.obj_xy = obj_xy; A.mode = 1;
+    return stack_launch(sim, A, stream);
+}
+
+int gg_stack_observe(GgStackSim* sim, float* obs_agent, float* obs_env, float* reward, uint8_t* terminated, gg_stream_t stream) {
+    if (!sim || !obs_agent || !obs_env) return gg_internal_fail("gg_stack_observe: null argument%s", "");
+    StackArgs A;
+    memset(&A, 0, sizeof(A));
+    A.obs_agent = obs_agent; A.obs_env = obs_env; A.reward = reward; A.terminated = terminated; A.mode = 2;
+    return stack_launch(sim, A, stream);
+}
+
+static int stack_state_copy(GgStackSim* sim, float* q, float* qd, float* qacc, int to_soa, gg_stream_t stream) {
+    if (!sim || sim->state == nullptr) return gg_internal_fail("stack state copy: state not bound%s", "");
+    SK_CUDA(cudaSetDevice(sim->device));
+    stack_state_copy_kernel<<<(sim->n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(sim->state, sim->stride, sim->n, sim->nu, sim->task.n_obj, q, qd,
+                                                                                   qacc, to_soa);
+    gg_internal_count_launches(1);
+    SK_CUDA(cudaGetLastError());
+    return 0;
+}
+int gg_stack_get_state(GgStackSim* sim, float* q, float* qd, float* qacc, gg_stream_t stream) { return stack_state_copy(sim, q, qd, qacc, 0, stream); }
+int gg_stack_set_state(GgStackSim* sim, const float* q, const float* qd, const float* qacc, gg_stream_t stream) {
+    return stack_state_copy(sim, (float*)q, (float*)qd, (float*)qacc, 1, stream);
+}
+
+int gg_stack_stats(GgStackSim* sim, double* out8, int clear, gg_stream_t stream) {
+    if (!sim || !out8) return gg_internal_fail("gg_stack_stats: null argument%s", "");
+    SK_CUDA(cudaSetDevice(sim->device));
+    stack_stats_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(sim->stats, out8, clear);
+    gg_internal_count_launches(1);
+    SK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int gg_stack_info(GgStackSim* sim, int32_t* ncon, int32_t* iters, gg_stream_t stream) {
+    if (!sim) return gg_internal_fail("gg_stack_info: null argument%s", "");
+    SK_CUDA(cudaSetDevice(sim->device));
+    if (ncon) SK_CUDA(cudaMemcpyAsync(ncon, sim->ncon, (size_t)sim->n * sizeof(int32_t), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    if (iters) SK_CUDA(cudaMemcpyAsync(iters, sim->iters, (size_t)sim->n * sizeof(int32_t), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return 0;
+}
+
+}  // extern "C"

@@ -12,7 +12,7 @@ import numpy as np
 import torch
 
 from .gym_api import gym
-from .tasks import FrankaCubePickBatch, So101CubePickBatch
+from .tasks import FrankaCubePickBatch, FrankaCubeStackEmptyBatch, So101CubePickBatch
 
 
 class GenesisEnv(gym.Env):
@@ -96,10 +96,13 @@ class GenesisEnv(gym.Env):
                              observation_width=self.observation_width, num_envs=self.num_envs, env_spacing=self.env_spacing,
                              camera_capture_mode=self.camera_capture_mode, strip_environment_state=self.strip_environment_state)
         common_kwargs.update(self._sim_kwargs)
-        # the reference map (env.py:111-118) also lists cube_stack variants: those are "next" rows
+        # the reference map (env.py:111-118) sends ("franka", "cube_stack") to the kitchen-scene variant of the same task;
+        # its physics (Panda + five free cubes on a flat support) is FrankaCubeStackEmptyBatch, built here.
+        # The SO-101 stack variants remain a "next" row (8f-3).
         task_map = {
             ("franka", "cube_pick", True): FrankaCubePickBatch,
             ("so101", "cube_pick", True): So101CubePickBatch,
+            ("franka", "cube_stack", True): FrankaCubeStackEmptyBatch,
         }
         key = (self.robot, task_name, self.num_envs > 0)
         if key not in task_map:

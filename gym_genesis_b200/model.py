@@ -44,6 +44,7 @@ GENESIS_COMPAT_SELF_COLLISION = False    # pad-pad / pad-link pairs skipped (sam
 GENESIS_COMPAT_MAX_PLANE_CONTACTS = 4    # mjc_PlaneBox keeps the first 4 penetrating corners
 GENESIS_COMPAT_MAX_BOXBOX_CONTACTS = 8
 GENESIS_COMPAT_MAX_CONTACTS = 64         # per-env cap (Genesis: max_collision_pairs), deterministic order
+GENESIS_COMPAT_MAX_CONTACTS_STACK = 96   # same cap for the five-cube CubeStack scene (20 cube-plane points alone)
 # robot.inverse_kinematics defaults (RigidEntity.inverse_kinematics keyword defaults, [UPSTREAM-RECALL, medium])
 GENESIS_COMPAT_IK_MAX_ITERS = 20         # max_solver_iters
 GENESIS_COMPAT_IK_DAMPING = 0.01         # dq = J^T (J J^T + damping^2 I)^-1 e
@@ -172,6 +173,13 @@ class SceneModel:
     settle_steps: int = 1
     horizon: int = 200
     qpos0: Optional[np.ndarray] = None   # configuration at which invweight0 is evaluated (MJCF qpos0 = 0)
+    # multi-object scenes (reference: franka/cube_stack.py:27-240): free boxes in dof order, cube_body = obj_bodies[0]
+    obj_bodies: Optional[List[int]] = None
+    obj_spawn: Optional[Sequence[Sequence[float]]] = None   # per object (x_lo, x_hi, y_lo, y_hi); draw order x then y per object
+    task: str = "pick"               # "pick": reward = cube z > success_z; "stack": xy_dist < stack_xy and z_diff > stack_z
+    stack_xy: float = 0.05           # franka/cube_stack.py:195
+    stack_z: float = 0.03            # franka/cube_stack.py:195
+    max_contacts: int = GENESIS_COMPAT_MAX_CONTACTS
 
     # ---- derived sizes -----------------------------------------------------------------------
     def __post_init__(self):
@@ -193,6 +201,15 @@ class SceneModel:
         assert self.dofadr[self.cube_body] == self.nu, "robot dofs must precede the cube's free joint"
         if self.qpos0 is None:
             self.qpos0 = np.zeros(self.nu)
+        if self.obj_bodies is None:
+            self.obj_bodies = [self.cube_body]
+        if self.obj_spawn is None:
+            self.obj_spawn = [(self.spawn_lo[0], self.spawn_hi[0], self.spawn_lo[1], self.spawn_hi[1])] * len(self.obj_bodies)
+        self.n_obj = len(self.obj_bodies)
+        assert self.obj_bodies[0] == self.cube_body and len(self.obj_spawn) == self.n_obj
+        for k, b in enumerate(self.obj_bodies):
+            assert self.bodies[b].jtype == FREE and self.dofadr[b] == self.nu + 6 * k, "objects must follow the robot in dof order"
+        assert self.nv == self.nu + 6 * self.n_obj
 
     # ---- per-dof tables ----------------------------------------------------------------------
     def dof_table(self):
@@ -213,7 +230,9 @@ class SceneModel:
 
     # ---- fp64 numpy kinematics / dynamics (host logic; used for invweight0 and golden vectors) -
     def default_cube_q(self):
-        return np.array([0.65, 0.0, self.plane_z + 0.02, 1.0, 0.0, 0.0, 0.0])
+        if self.n_obj == 1:
+            return np.array([0.65, 0.0, self.plane_z + 0.02, 1.0, 0.0, 0.0, 0.0])
+        return np.concatenate([[*self.bodies[b].pos, 1.0, 0.0, 0.0, 0.0] for b in self.obj_bodies]).astype(np.float64)
 
     def full_q(self, q_robot, cube_q=None):
         q = np.zeros(self.nq)
@@ -311,6 +330,9 @@ class SceneModel:
         out = dict(
             nb=self.nb, nv=self.nv, nq=self.nq, nu=self.nu, ngeom=len(self.geoms),
             eef_body=self.eef_body, cube_body=self.cube_body,
+            n_obj=self.n_obj, task={"pick": 0, "stack": 1}[self.task],
+            obj_body=np.array(self.obj_bodies, dtype=np.int32),
+            obj_spawn=f32(self.obj_spawn).ravel(), task_opt=f32([self.stack_xy, self.stack_z]),
             parent=np.array([b.parent for b in B], dtype=np.int32),
             jtype=np.array([b.jtype for b in B], dtype=np.int32),
             dofadr=self.dofadr.copy(), qadr=self.qadr.copy(),
@@ -336,7 +358,7 @@ class SceneModel:
                      GENESIS_COMPAT_MINVAL, self.success_z, self.spawn_lo[0], self.spawn_hi[0],
                      self.spawn_lo[1], self.spawn_hi[1], self.spawn_z]),
             spawn_quat=f32(self.spawn_quat), home_q=f32(self.home_q),
-            max_contacts=GENESIS_COMPAT_MAX_CONTACTS,
+            max_contacts=self.max_contacts,
         )
         return out
 
@@ -409,7 +431,36 @@ def franka_cube_pick_model() -> SceneModel:
     return SceneModel("franka", bodies, geoms, eef_body=8, cube_body=11, home_q=FRANKA_HOME.copy(), n_arm=7, n_fing=2)
 
 
-def get_model(robot: str) -> SceneModel:
+# cube_1 (picked), cube_2 (target), three distractors: body positions of franka/cube_stack.py:54-77 (the distractors'
+# build-time positions are unseeded np.random draws there, overwritten by every reset; fixed representative values here)
+_STACK_CUBE_POS = [(0.6, -0.1, 0.02), (0.45, 0.15, 0.02), (0.35, -0.25, 0.02), (0.55, 0.25, 0.02), (0.65, 0.05, 0.02)]
+# spawn ranges (x_lo, x_hi, y_lo, y_hi): cube_1 franka/cube_stack.py:125-126, cube_2 :132-133, distractors :141-142
+_STACK_SPAWN = [(0.45, 0.75, -0.2, 0.2), (0.3, 0.7, -0.3, 0.3), (0.3, 0.7, -0.3, 0.3), (0.3, 0.7, -0.3, 0.3), (0.3, 0.7, -0.3, 0.3)]
+
+
+def franka_cube_stack_model(n_distractors: int = 3) -> SceneModel:
+    """Plane + Panda + cube_1 + cube_2 + 3 distractor cubes, all free 4 cm boxes: `franka/cube_stack.py:42-96`
+    (`FrankaCubeStackEmptyBatch`).  Gains are the explicit ones of `:156-161` (already the Panda table here)."""
+    base = franka_cube_pick_model()
+    bodies = base.bodies[:-1]
+    geoms = [g for g in base.geoms if g.group == 0]
+    n_obj = 2 + n_distractors
+    obj = []
+    for k in range(n_obj):
+        b = _cube_body()
+        b.name = ("cube_1", "cube_2")[k] if k < 2 else f"distractor_{k - 2}"
+        b.pos = _STACK_CUBE_POS[k]
+        obj.append(len(bodies))
+        bodies.append(b)
+        geoms.append(BoxGeom(obj[-1], (CUBE_SIZE / 2,) * 3, group=1))
+    return SceneModel("franka_stack", bodies, geoms, eef_body=8, cube_body=obj[0], home_q=FRANKA_HOME.copy(), n_arm=7, n_fing=2,
+                      obj_bodies=obj, obj_spawn=_STACK_SPAWN[:n_obj], task="stack",
+                      max_contacts=GENESIS_COMPAT_MAX_CONTACTS_STACK)
+
+
+def get_model(robot: str, task: str = "cube_pick") -> SceneModel:
+    if robot == "franka" and task == "cube_stack":
+        return franka_cube_stack_model()
     if robot == "franka":
         return franka_cube_pick_model()
     if robot == "so101":

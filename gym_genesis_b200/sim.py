@@ -248,3 +248,136 @@ class BatchedSim:
     @staticmethod
     def launch_count() -> int:
         return int(cabi.load_library().gg_launch_count())
+
+
+class BatchedStackSim(BatchedSim):
+    """N independent worlds of the stacking scene (arm + gripper + five free cubes + plane), `gg_stack_*` entry points.
+
+    Replaces the Genesis `Scene` of `gym_genesis/tasks/franka/cube_stack.py:42-96`.  One env.step = three launches
+    (thread-per-env dynamics, warp-per-env contact solve, thread-per-env integration / observation); see
+    `csrc/gg_stack.cu`.  `inverse_kinematics` runs the same `gg_ik` kernel as the pick scene on this sim's joint state.
+    """
+
+    def __init__(self, scene_model: SceneModel, n_envs: int, device="cuda", solver_iterations: int = 10,
+                 solver_tolerance: float = 1e-5, auto_reset: bool = False, time_limit: bool = False, reset_prob: float = 0.0,
+                 seed: int = 0, first_env_id: int = 0):
+        if not torch.cuda.is_available():
+            raise GgError("gym_genesis_b200 needs a CUDA device: the env.step path has no CPU fallback")
+        self.lib = cabi.load_library()
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise ValueError(f"device must be a CUDA device, got {device}")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        self.scene_model = scene_model
+        self.gg_model = cabi.compile_gg(scene_model)
+        self.gg_task = cabi.compile_stack_task(scene_model)
+        self.n_envs = int(n_envs)
+        self.nu = scene_model.nu
+        self.n_obj = scene_model.n_obj
+        self.nq, self.nv = self.nu + 7 * self.n_obj, self.nu + 6 * self.n_obj
+        self.agent_dim = 7 + scene_model.n_fing
+        self.env_dim = cabi.GG_STACK_ENV_STATE_DIM
+        h = C.c_void_p()
+        self._check(self.lib.gg_stack_create(C.byref(self.gg_model), C.byref(self.gg_task), self.n_envs, self.device.index, C.byref(h)))
+        self._h = h
+        rows, stride = self.lib.gg_stack_state_rows(h), self.lib.gg_stack_state_stride(h)
+        dev = self.device
+        self.state = torch.zeros((rows, stride), dtype=torch.float32, device=dev)
+        self.step_count = torch.zeros(self.n_envs, dtype=torch.int32, device=dev)
+        self.episode = torch.zeros(self.n_envs, dtype=torch.int32, device=dev)
+        self._check(self.lib.gg_stack_bind_state(h, _ptr(self.state), _ptr(self.step_count), _ptr(self.episode)))
+        self.obs_agent = torch.zeros((self.n_envs, self.agent_dim), dtype=torch.float32, device=dev)
+        self.obs_env = torch.zeros((self.n_envs, self.env_dim), dtype=torch.float32, device=dev)
+        self.reward = torch.zeros(self.n_envs, dtype=torch.float32, device=dev)
+        self.terminated = torch.zeros(self.n_envs, dtype=torch.bool, device=dev)
+        self.truncated = torch.zeros(self.n_envs, dtype=torch.bool, device=dev)
+        self._stats = torch.zeros(8, dtype=torch.float64, device=dev)
+        self.cfg = cabi.GgConfig(solver_iterations, solver_tolerance, int(auto_reset), int(time_limit), float(reset_prob),
+                                 int(seed) & (2 ** 64 - 1), int(first_env_id))
+        self._check(self.lib.gg_stack_configure(h, C.byref(self.cfg)))
+        self._ik_h = None
+
+    def configure(self, **kw):
+        for k, v in kw.items():
+            if not hasattr(self.cfg, k):
+                raise AttributeError(k)
+            setattr(self.cfg, k, v)
+        self._check(self.lib.gg_stack_configure(self._h, C.byref(self.cfg)))
+
+    def close(self):
+        if getattr(self, "_ik_h", None) is not None:
+            self.lib.gg_destroy(self._ik_h)
+            self._ik_h = None
+        if getattr(self, "_h", None) is not None:
+            self.lib.gg_stack_destroy(self._h)
+            self._h = None
+
+    def step(self, action, reset_mask=None):
+        a = self._as_action(action)
+        m = self._as_mask(reset_mask)
+        self._last_action = a
+        self._check(self.lib.gg_stack_step(self._h, _ptr(a), _ptr(self.obs_agent), _ptr(self.obs_env), _ptr(self.reward),
+                                           _ptr(self.terminated), _ptr(self.truncated), _ptr(m), self._stream()))
+
+    def step_host(self, action, reset_mask=None, wait=True):
+        raise NotImplementedError("host_io (zero-copy host actions) is implemented for the CubePick path only")
+
+    def reset(self, mask=None, obj_xy=None):
+        m = self._as_mask(mask)
+        xy = None
+        if obj_xy is not None:
+            xy = torch.as_tensor(np.asarray(obj_xy, dtype=np.float32) if not isinstance(obj_xy, torch.Tensor) else obj_xy)
+            if xy.shape != (self.n_envs, self.n_obj, 2):
+                raise ValueError(f"obj_xy must have shape ({self.n_envs}, {self.n_obj}, 2)")
+            xy = xy.to(device=self.device, dtype=torch.float32).contiguous()
+        self._last_action = None
+        self._check(self.lib.gg_stack_reset(self._h, _ptr(m), _ptr(xy), _ptr(self.obs_agent), _ptr(self.obs_env), self._stream()))
+
+    def observe(self):
+        self._check(self.lib.gg_stack_observe(self._h, _ptr(self.obs_agent), _ptr(self.obs_env), _ptr(self.reward),
+                                              _ptr(self.terminated), self._stream()))
+
+    def get_state(self):
+        q = torch.empty((self.n_envs, self.nq), dtype=torch.float32, device=self.device)
+        qd = torch.empty((self.n_envs, self.nv), dtype=torch.float32, device=self.device)
+        qacc = torch.empty((self.n_envs, self.nv), dtype=torch.float32, device=self.device)
+        self._check(self.lib.gg_stack_get_state(self._h, _ptr(q), _ptr(qd), _ptr(qacc), self._stream()))
+        return q, qd, qacc
+
+    def set_state(self, q=None, qd=None, qacc=None):
+        def prep(t, k):
+            if t is None:
+                return None
+            t = torch.as_tensor(t, dtype=torch.float32).to(self.device).contiguous()
+            if t.shape != (self.n_envs, k):
+                raise ValueError(f"expected shape ({self.n_envs}, {k}), got {tuple(t.shape)}")
+            return t
+        q, qd, qacc = prep(q, self.nq), prep(qd, self.nv), prep(qacc, self.nv)
+        self._check(self.lib.gg_stack_set_state(self._h, _ptr(q), _ptr(qd), _ptr(qacc), self._stream()))
+
+    def step_info(self):
+        """(contacts, Newton iterations) of the last step per env, int32 device tensors."""
+        nc = torch.empty(self.n_envs, dtype=torch.int32, device=self.device)
+        it = torch.empty(self.n_envs, dtype=torch.int32, device=self.device)
+        self._check(self.lib.gg_stack_info(self._h, _ptr(nc), _ptr(it), self._stream()))
+        return nc, it
+
+    def inverse_kinematics(self, *args, **kw):
+        # the IK kernel reads joint positions from state rows [0, n_dof) with the env index fastest: the stacking layout
+        # starts with the same rows, so a CubePick handle bound to this sim's buffers serves it unchanged
+        if self._ik_h is None:
+            h = C.c_void_p()
+            self._check(self.lib.gg_create(C.byref(self.gg_model), self.n_envs, self.device.index, C.byref(h)))
+            assert self.lib.gg_state_stride(h) == self.state.shape[1]
+            self._check(self.lib.gg_bind_state(h, _ptr(self.state), _ptr(self.step_count), _ptr(self.episode)))
+            self._ik_h = h
+        stack_h, self._h = self._h, self._ik_h
+        try:
+            return BatchedSim.inverse_kinematics(self, *args, **kw)
+        finally:
+            self._h = stack_h
+
+    def stats(self, clear=False) -> torch.Tensor:
+        self._check(self.lib.gg_stack_stats(self._h, _ptr(self._stats), int(clear), self._stream()))
+        return self._stats

@@ -1,0 +1,99 @@
+"""Batched CubeStack task on the B200 simulator.
+
+Mirrors `FrankaCubeStackEmptyBatch` (`gym_genesis/tasks/franka/cube_stack.py:27-240`): Panda + cube_1 (picked) + cube_2
+(target) + three distractor cubes on the ground plane; observation `agent_pos` (9) and `environment_state` (14) =
+[cube_1 pos, cube_1 quat, eef - cube_1, |.|, cube_2 pos] (`:198-216`); reward = (|xy_1 - xy_2| < 0.05) & (z_1 - z_2 > 0.03)
+(`:188-196`); reset draws, per cube, all x then all y from the host RandomState (`:123-145`), sets the home pose, holds it and
+runs one settle step (`:147-163`).  The reference maps `CubeStack-v0` + franka to a kitchen-scene variant whose extra
+geometry is visual / static (env.py:115); the physics of that task is this scene.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from ..gym_api import spaces
+from ..model import get_model
+from ..sim import BatchedStackSim
+from .cube_pick import CubePickBatch, _Link, _Robot, _Scene
+
+AGENT_DIM = 9       # franka/cube_stack.py:18
+ENV_DIM = 14        # franka/cube_stack.py:19
+
+
+class _StackCube:
+    """Handle of object k (`cube_1`, `cube_2`, `distractor_cubes[i]` of the reference): poses read from the SoA state."""
+
+    def __init__(self, task, k):
+        self._task, self._k = task, k
+
+    def _rows(self, a, b):
+        sim = self._task.sim
+        r0 = 2 * sim.nu + 13 * self._k
+        return sim.state[r0 + a:r0 + b, : sim.n_envs].t().contiguous()
+
+    def get_pos(self):
+        return self._rows(0, 3)
+
+    def get_quat(self):
+        return self._rows(3, 7)
+
+    def get_vel(self):
+        return self._rows(7, 10)
+
+
+class FrankaCubeStackEmptyBatch(CubePickBatch):
+    robot_name = "franka"
+
+    def __init__(self, enable_pixels, observation_height, observation_width, num_envs, env_spacing, camera_capture_mode,
+                 strip_environment_state, device="cuda", auto_reset=False, time_limit=False, solver_iterations=10,
+                 solver_tolerance=1e-5, seed=0, first_env_id=0, reset_prob=0.0):
+        if enable_pixels:
+            raise NotImplementedError("state-only path: rendering (enable_pixels=True) is out of scope (SURVEY.md section 5)")
+        if num_envs <= 0:
+            raise ValueError("num_envs must be positive for the batched task")
+        self.enable_pixels = enable_pixels
+        self.observation_height = observation_height
+        self.observation_width = observation_width
+        self.num_envs = num_envs
+        self.camera_capture_mode = camera_capture_mode
+        self.strip_environment_state = strip_environment_state
+        self._random = np.random.RandomState()
+        self.model = get_model(self.robot_name, "cube_stack")
+        self.sim = BatchedStackSim(self.model, num_envs, device=device, solver_iterations=solver_iterations,
+                                   solver_tolerance=solver_tolerance, auto_reset=auto_reset, time_limit=time_limit,
+                                   reset_prob=reset_prob, seed=seed, first_env_id=first_env_id)
+        self.agent_dim = self.sim.agent_dim
+        self.observation_space = spaces.Dict({
+            "agent_pos": spaces.Box(low=-np.inf, high=np.inf, shape=(AGENT_DIM,), dtype=np.float32),
+            "environment_state": spaces.Box(low=-np.inf, high=np.inf, shape=(ENV_DIM,), dtype=np.float32),
+        })
+        self.action_space = spaces.Box(low=-1.0, high=1.0, shape=(AGENT_DIM,), dtype=np.float32)
+        self._home = torch.tensor(self.model.home_q, dtype=torch.float32, device=self.sim.device).repeat(num_envs, 1)
+        self._targets = self._home.clone()
+        self.scene = _Scene(self)
+        self.eef = _Link(self)
+        self.robot = _Robot(self)
+        self.cube_1 = _StackCube(self, 0)
+        self.cube_2 = _StackCube(self, 1)
+        self.distractor_cubes = [_StackCube(self, k) for k in range(2, self.model.n_obj)]
+        self.cube = self.cube_1
+        self.motors_dof = np.arange(self.model.n_arm)
+        self.fingers_dof = np.arange(self.model.n_arm, self.model.nu)
+
+    @property
+    def franka(self):
+        return self.robot
+
+    def _spawn_xy(self):
+        """Host RandomState stream of the reference (cube_stack.py:123-145): for cube_1, cube_2, then each distractor,
+        all x draws followed by all y draws."""
+        B = self.num_envs
+        out = np.zeros((B, self.model.n_obj, 2), dtype=np.float32)
+        for k, (xlo, xhi, ylo, yhi) in enumerate(self.model.obj_spawn):
+            out[:, k, 0] = self._random.uniform(xlo, xhi, size=(B,))
+            out[:, k, 1] = self._random.uniform(ylo, yhi, size=(B,))
+        return out
+
+    def step_host(self, action, reset_mask=None):
+        raise NotImplementedError("host_io is implemented for the CubePick path only")

@@ -24,6 +24,10 @@
  *   gg_export_successful <- the collectors' per-step `.detach().cpu().numpy()` appends and the "save envs whose reward was ever
  *                       > 0" loop                                          examples/franka/pick_cube_state.py:86-113
  *                       (frames stay on the device; one compacted copy per episode)
+ *   gg_stack_*      <- the same calls of the five-cube stacking task:
+ *                       gym_genesis/tasks/franka/cube_stack.py:42-96 (scene: cube_1, cube_2, 3 distractors, Panda),
+ *                       :119-170 (reset: per-cube spawn ranges, home pose, explicit gains, one settle step),
+ *                       :180-186 (step), :188-196 (reward xy_dist < 0.05 & z_diff > 0.03), :198-216 (obs 9 + 14)
  *
  * Conventions: plain pointers and sizes only; every pointer argument of gg_step / gg_reset is a
  * DEVICE pointer into caller-owned (torch) memory unless stated otherwise; all work is enqueued
@@ -179,6 +183,51 @@ int gg_record(GgSim* sim, float* traj, int32_t* ever, int t, int horizon, const 
               const float* obs_env, const float* reward, gg_stream_t stream);
 int gg_export_successful(GgSim* sim, const float* traj, const int32_t* ever, int horizon, float* out, int32_t* out_env_ids,
                          int32_t* out_count, gg_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Multi-object scenes: `FrankaCubeStackEmptyBatch` (gym_genesis/tasks/franka/cube_stack.py:27-240).  The robot, the box
+ * geometry / inertia shared by all cubes and the solver constants come from GgModel; GgStackTask adds the object count,
+ * the per-object spawn ranges and the stacking thresholds.  Object 0 = cube_1 (picked), object 1 = cube_2 (target), the
+ * rest are distractors.  Cube-cube box-box contacts are generated (RigidOptions(box_box_detection=True), :46).
+ *
+ * State buffer (caller-owned, float32, gg_stack_state_rows() x gg_stack_state_stride(), env index fastest):
+ *   rows [0, nu) q | [nu, 2nu) qd | 13 rows per object (pos3 quat4 linvel3 angvel3) | nu + 6 n_obj rows warm start.
+ * One gg_stack_step = three launches on `stream`: stack_prep_kernel (thread per env: masked reset, PD, CRBA, Cholesky,
+ * RNEA, joint-limit rows, pad broad phase, robot-block solve when no pad can touch anything), stack_solve_kernel (warp per
+ * env: narrow phase incl. cube-cube, Newton on the coupled dofs), stack_finish_kernel (thread per env: integration,
+ * observations, reward / flags, counters, statistics).
+ * ------------------------------------------------------------------------------------------------------------------ */
+#define GG_MAX_OBJ 5
+#define GG_STACK_MAX_CONTACTS 96
+#define GG_STACK_ENV_STATE_DIM 14 /* cube1 pos3 + quat4 + (eef - cube1)3 + |.|1 + cube2 pos3   cube_stack.py:209 */
+
+typedef struct GgStackTask {
+    int32_t n_obj, max_contacts;
+    float spawn_lo[GG_MAX_OBJ][2], spawn_hi[GG_MAX_OBJ][2];   /* per-object uniform xy ranges   cube_stack.py:125-142 */
+    float stack_xy, stack_z;                                  /* reward thresholds              cube_stack.py:195     */
+} GgStackTask;
+
+typedef struct GgStackSim GgStackSim;
+
+int gg_stack_create(const GgModel* model, const GgStackTask* task, int n_envs, int device, GgStackSim** out);
+int gg_stack_destroy(GgStackSim* sim);
+int gg_stack_configure(GgStackSim* sim, const GgConfig* cfg);
+int gg_stack_state_rows(const GgStackSim* sim);
+int gg_stack_state_stride(const GgStackSim* sim);
+int gg_stack_bind_state(GgStackSim* sim, float* state, int32_t* step_count, int32_t* episode);
+/* action (n_envs, n_dof); obs_agent (n_envs, 7 + n_fing); obs_env (n_envs, 14); reward / flags (n_envs); reset_mask nullable. */
+int gg_stack_step(GgStackSim* sim, const float* action, float* obs_agent, float* obs_env, float* reward, uint8_t* terminated,
+                  uint8_t* truncated, const uint8_t* reset_mask, gg_stream_t stream);
+/* obj_xy (nullable): (n_envs, n_obj, 2) explicit spawn positions (the reference's host RandomState stream, drawn per object:
+ * all x then all y); NULL -> device Philox draw keyed by (cfg.seed, global env id, episode, object). */
+int gg_stack_reset(GgStackSim* sim, const uint8_t* mask, const float* obj_xy, float* obs_agent, float* obs_env, gg_stream_t stream);
+/* env-major copies: q (n_envs, n_dof + 7 n_obj), qd and qacc (n_envs, n_dof + 6 n_obj). */
+int gg_stack_get_state(GgStackSim* sim, float* q, float* qd, float* qacc, gg_stream_t stream);
+int gg_stack_set_state(GgStackSim* sim, const float* q, const float* qd, const float* qacc, gg_stream_t stream);
+int gg_stack_observe(GgStackSim* sim, float* obs_agent, float* obs_env, float* reward, uint8_t* terminated, gg_stream_t stream);
+int gg_stack_stats(GgStackSim* sim, double* out8, int clear, gg_stream_t stream);
+/* per-env diagnostics of the last step (DEVICE int32[n_envs] each, nullable): contacts, Newton iterations */
+int gg_stack_info(GgStackSim* sim, int32_t* ncon, int32_t* iters, gg_stream_t stream);
 
 /* Number of kernels this library has launched since load (for bench.py's gpu_launches). */
 int64_t gg_launch_count(void);

@@ -14,11 +14,11 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "liboracle.so")
 
-_INT_FIELDS = ["parent", "jtype", "dofadr", "qadr", "limited", "ctrl", "geom_body", "geom_group"]
+_INT_FIELDS = ["parent", "jtype", "dofadr", "qadr", "limited", "ctrl", "geom_body", "geom_group", "obj_body"]
 _DBL_FIELDS = ["pos", "quat", "axis", "mass", "com", "inertia", "body_invweight", "dof_invweight",
                "armature", "damping", "kp", "kv", "frc_lo", "frc_hi", "lim_lo", "lim_hi",
-               "geom_half", "geom_pos", "geom_quat", "opt", "spawn_quat", "home_q"]
-_SCALARS = ["nb", "nv", "nq", "nu", "ngeom", "eef_body", "cube_body", "max_contacts"]
+               "geom_half", "geom_pos", "geom_quat", "opt", "spawn_quat", "home_q", "obj_spawn", "task_opt"]
+_SCALARS = ["nb", "nv", "nq", "nu", "ngeom", "eef_body", "cube_body", "max_contacts", "n_obj", "task"]
 
 
 class _OrcModel(C.Structure):
@@ -79,6 +79,8 @@ class Oracle:
         for k in ("nb", "nv", "nq", "nu"):
             setattr(self, k, int(self.flat[k]))
         self.agent_dim = 7 + scene_model.n_fing
+        self.n_obj = int(self.flat["n_obj"])
+        self.env_dim = 14 if scene_model.task == "stack" else 11
 
     def __del__(self):
         try:
@@ -151,7 +153,7 @@ class Oracle:
         q = self._a(q)
         n = q.shape[0]
         agent = np.zeros((n, self.agent_dim), self.dtype)
-        envs = np.zeros((n, 11), self.dtype)
+        envs = np.zeros((n, self.env_dim), self.dtype)
         reward = np.zeros(n, self.dtype)
         term = np.zeros(n, np.uint8)
         self._fn("obs")(self.h, C.c_int(n), _p(q), _p(agent), C.c_int(self.agent_dim), _p(envs), _p(reward), _p(term))
@@ -159,7 +161,7 @@ class Oracle:
 
     def reset(self, q, qd, qacc, xy, mask=None):
         n = q.shape[0]
-        xy = self._a(xy, (n, 2))
+        xy = self._a(xy, (n, self.n_obj, 2))
         m = None if mask is None else np.ascontiguousarray(mask, dtype=np.uint8)
         self._fn("reset")(self.h, C.c_int(n), _p(q), _p(qd), _p(qacc), _p(m) if m is not None else None, _p(xy))
 
@@ -187,6 +189,15 @@ class Oracle:
         out = np.zeros(2, np.float32)
         lib().orc_spawn_xy(self.h, C.c_uint64(seed), C.c_uint32(env_id), C.c_uint32(episode), _p(out))
         return out
+
+
+def _spawn_obj(self, seed, env_id, episode, k):
+    out = np.zeros(2, np.float32)
+    lib().orc_spawn_obj(self.h, C.c_uint64(seed), C.c_uint32(env_id), C.c_uint32(episode), C.c_uint32(k), _p(out))
+    return out
+
+
+Oracle.spawn_obj = _spawn_obj
 
 
 def philox(ctr, key):

@@ -44,11 +44,11 @@
 
 extern "C" {
 typedef struct {
-    int32_t nb, nv, nq, nu, ngeom, eef_body, cube_body, max_contacts;
-    const int32_t *parent, *jtype, *dofadr, *qadr, *limited, *ctrl, *geom_body, *geom_group;
+    int32_t nb, nv, nq, nu, ngeom, eef_body, cube_body, max_contacts, n_obj, task;
+    const int32_t *parent, *jtype, *dofadr, *qadr, *limited, *ctrl, *geom_body, *geom_group, *obj_body;
     const double *pos, *quat, *axis, *mass, *com, *inertia, *body_invweight, *dof_invweight;
     const double *armature, *damping, *kp, *kv, *frc_lo, *frc_hi, *lim_lo, *lim_hi;
-    const double *geom_half, *geom_pos, *geom_quat, *opt, *spawn_quat, *home_q;
+    const double *geom_half, *geom_pos, *geom_quat, *opt, *spawn_quat, *home_q, *obj_spawn, *task_opt;
 } OrcModel;
 }
 
@@ -100,9 +100,12 @@ template <class T> inline void quat_to_mat(const T* q, T* R) {
 // ------------------------------------------------------------------------------------ model
 template <class T> struct Model {
     int nb, nv, nq, nu, ngeom, eef_body, cube_body, max_contacts;
-    std::vector<int> parent, jtype, dofadr, qadr, limited, ctrl, geom_body, geom_group;
+    int n_obj, task;                      // task 0: pick (franka/cube_pick.py), 1: stack (franka/cube_stack.py)
+    std::vector<int> parent, jtype, dofadr, qadr, limited, ctrl, geom_body, geom_group, obj_body;
     std::vector<T> pos, quat, axis, mass, com, inertia, body_w, dof_w, armature, damping, kp, kv, frc_lo, frc_hi,
         lim_lo, lim_hi, geom_half, geom_pos, geom_quat, opt, spawn_quat, home_q;
+    std::vector<T> obj_spawn;             // per object: x_lo, x_hi, y_lo, y_hi
+    std::vector<T> task_opt;              // stack: xy threshold, z threshold (franka/cube_stack.py:195)
     std::vector<int> dof_body;            // body owning each dof
     std::vector<char> affects;            // affects[body*nv + dof]
 };
@@ -117,6 +120,8 @@ static std::vector<int> cvti(const int32_t* p, int n) { return std::vector<int>(
 template <class T> static void build(Model<T>& m, const OrcModel* c) {
     m.nb = c->nb; m.nv = c->nv; m.nq = c->nq; m.nu = c->nu; m.ngeom = c->ngeom;
     m.eef_body = c->eef_body; m.cube_body = c->cube_body; m.max_contacts = c->max_contacts;
+    m.n_obj = c->n_obj; m.task = c->task;
+    m.obj_body = cvti(c->obj_body, m.n_obj); m.obj_spawn = cvt<T>(c->obj_spawn, m.n_obj * 4); m.task_opt = cvt<T>(c->task_opt, 2);
     m.parent = cvti(c->parent, m.nb); m.jtype = cvti(c->jtype, m.nb);
     m.dofadr = cvti(c->dofadr, m.nb); m.qadr = cvti(c->qadr, m.nb);
     m.limited = cvti(c->limited, m.nv); m.ctrl = cvti(c->ctrl, m.nv);
@@ -506,7 +511,9 @@ template <class T> static void geom_pose(const Model<T>& m, const Kin<T>& k, int
     for (int i = 0; i < 3; i++) c[i] = k.xpos[b * 3 + i] + off[i];
 }
 
-// Order (deterministic): object-plane, pads-plane in geom order, pad-object in geom order; capped at max_contacts.
+// Order (deterministic): objects-plane, pads-plane in geom order, pad-object (pad-major, object-minor), object-object
+// pairs (i < j, row-major) -- the cube-cube box-box pairs of franka/cube_stack.py (RigidOptions(box_box_detection=True),
+// :46); capped at max_contacts.
 template <class T> static void collide(const Model<T>& m, const Kin<T>& k, std::vector<Contact<T>>& out) {
     out.clear();
     const T h = m.opt[OPT_PLANE_Z];
@@ -522,6 +529,15 @@ template <class T> static void collide(const Model<T>& m, const Kin<T>& k, std::
         geom_pose(m, k, g, c, R);
         for (int o = 0; o < m.ngeom; o++) {
             if (m.geom_group[o] != 1) continue;
+            geom_pose(m, k, o, c2, R2);
+            box_box(c, R, &m.geom_half[g * 3], m.geom_body[g], c2, R2, &m.geom_half[o * 3], m.geom_body[o], m.max_contacts, out);
+        }
+    }
+    for (int g = 0; g < m.ngeom; g++) {
+        if (m.geom_group[g] != 1) continue;
+        geom_pose(m, k, g, c, R);
+        for (int o = g + 1; o < m.ngeom; o++) {
+            if (m.geom_group[o] != 1 || m.geom_body[o] == m.geom_body[g]) continue;
             geom_pose(m, k, o, c2, R2);
             box_box(c, R, &m.geom_half[g * 3], m.geom_body[g], c2, R2, &m.geom_half[o * 3], m.geom_body[o], m.max_contacts, out);
         }
@@ -737,6 +753,17 @@ template <class T> static void observe(const Model<T>& m, const T* q, T* agent, 
     envs[10] = std::sqrt(dot3(dd, dd));
     // reference compares a float32 z with 0.1 under NumPy weak-scalar promotion => z > 0.1f
     bool succ = (float)cp[2] > (float)m.opt[OPT_SUCCESS_Z];
+    if (m.task == 1) {
+        // franka/cube_stack.py:188-216: environment_state = [cube1 pos, cube1 quat, eef - cube1, |.|, cube2 pos] (14);
+        // reward = (|xy1 - xy2| < 0.05) & (z1 - z2 > 0.03) evaluated on float32 device tensors (torch weak-scalar promotion
+        // keeps float32).  The 2-norm is restated as sqrtf(fmaf(dx, dx, dy * dy)); the CUDA path uses the same expression.
+        const T* c2 = &k.xpos[m.obj_body[1] * 3];
+        for (int c = 0; c < 3; c++) envs[11 + c] = c2[c];
+        const float dx = (float)cp[0] - (float)c2[0], dy = (float)cp[1] - (float)c2[1];
+        const float xy = std::sqrt(std::fmaf(dx, dx, dy * dy));
+        const float dz = (float)cp[2] - (float)c2[2];
+        succ = xy < (float)m.task_opt[0] && dz > (float)m.task_opt[1];
+    }
     *reward = succ ? 1 : 0;
     *term = succ ? 1 : 0;
 }
@@ -843,6 +870,19 @@ void orc_destroy(void* h) { delete (Handle*)h; }
 void orc_philox(const uint32_t* ctr, const uint32_t* key, uint32_t* out) { philox4x32_10(ctr, key, out); }
 
 // device-reset spawn draw: counter (env_id, episode, 0, 0), key = seed; u = (x>>8)*2^-24; x = fma(u, hi-lo, lo)
+int orc_env_dim(const void* hv) { return ((const Handle*)hv)->f.task == 1 ? 14 : 11; }
+
+// object k of a multi-object scene: counter (env_id, episode, k, 0); object 0 of a one-object scene = orc_spawn_xy
+void orc_spawn_obj(const void* hv, uint64_t seed, uint32_t env_id, uint32_t episode, uint32_t k, float* xy) {
+    const Model<float>& m = ((const Handle*)hv)->f;
+    uint32_t ctr[4] = {env_id, episode, k, 0}, key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)}, o[4];
+    philox4x32_10(ctr, key, o);
+    float u0 = (float)(o[0] >> 8) * 5.9604644775390625e-8f, u1 = (float)(o[1] >> 8) * 5.9604644775390625e-8f;
+    const float* r = &m.obj_spawn[k * 4];
+    xy[0] = std::fmaf(u0, r[1] - r[0], r[0]);
+    xy[1] = std::fmaf(u1, r[3] - r[2], r[2]);
+}
+
 void orc_spawn_xy(const void* hv, uint64_t seed, uint32_t env_id, uint32_t episode, float* xy) {
     const Model<float>& m = ((const Handle*)hv)->f;
     uint32_t ctr[4] = {env_id, episode, 0, 0}, key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)}, o[4];
@@ -901,18 +941,22 @@ void orc_spawn_xy(const void* hv, uint64_t seed, uint32_t env_id, uint32_t episo
     }                                                                                                                \
     void orc_obs_##SUF(const void* hv, int n, const T* q, T* agent, int agent_dim, T* envs, T* reward, uint8_t* term) { \
         const Model<T>& m = Pick<T>::get((const Handle*)hv);                                                         \
+        const int ed = m.task == 1 ? 14 : 11;                                                                        \
         for (int e = 0; e < n; e++)                                                                                  \
-            observe(m, q + (size_t)e * m.nq, agent + (size_t)e * agent_dim, agent_dim, envs + (size_t)e * 11, reward + e, term + e); \
+            observe(m, q + (size_t)e * m.nq, agent + (size_t)e * agent_dim, agent_dim, envs + (size_t)e * ed, reward + e, term + e); \
     }                                                                                                                \
-    /* masked reset of the state (no settle step here): cube at (xy, spawn_z, spawn_quat), robot home, zero vel/qacc */ \
+    /* masked reset of the state (no settle step here): object k at (xy[e][k], spawn_z, spawn_quat), robot home, zero vel/qacc */ \
     void orc_reset_##SUF(const void* hv, int n, T* q, T* qd, T* qacc, const uint8_t* mask, const T* xy) {             \
         const Model<T>& m = Pick<T>::get((const Handle*)hv);                                                         \
         for (int e = 0; e < n; e++) {                                                                                \
             if (mask && !mask[e]) continue;                                                                          \
             T* qq = q + (size_t)e * m.nq;                                                                            \
             for (int i = 0; i < m.nu; i++) qq[i] = m.home_q[i];                                                      \
-            qq[m.nu] = xy[e * 2]; qq[m.nu + 1] = xy[e * 2 + 1]; qq[m.nu + 2] = m.opt[OPT_SPAWN_Z];                   \
-            for (int i = 0; i < 4; i++) qq[m.nu + 3 + i] = m.spawn_quat[i];                                          \
+            for (int k = 0; k < m.n_obj; k++) {                                                                      \
+                T* o = qq + m.nu + 7 * k;                                                                            \
+                o[0] = xy[((size_t)e * m.n_obj + k) * 2]; o[1] = xy[((size_t)e * m.n_obj + k) * 2 + 1]; o[2] = m.opt[OPT_SPAWN_Z]; \
+                for (int i = 0; i < 4; i++) o[3 + i] = m.spawn_quat[i];                                              \
+            }                                                                                                        \
             for (int i = 0; i < m.nv; i++) { qd[(size_t)e * m.nv + i] = 0; qacc[(size_t)e * m.nv + i] = 0; }         \
         }                                                                                                            \
     }                                                                                                                \

@@ -112,3 +112,62 @@ def substep_errors(q0, qd0, q_ref, qd_ref, q, qd, a_smooth_scale):
     ev = np.abs(qd - qd_ref).max(axis=1)
     bound = TOL_DQD_REL * np.maximum(d_ref, a_smooth_scale) + TOL_DQD_FLOOR
     return eq * TOL_Q_ABS / (TOL_Q_ABS + 0.01 * bound), ev / bound
+
+
+# ---- multi-object (CubeStack) scene ---------------------------------------------------------------------------------
+def hostsim_stack_step(hs, gg_model, task, Q, QD, QA, T, iters=10, tol=1e-5):
+    """One substep of the multi-object pipeline (gg_stack.cuh) on the host harness; the warp-cooperative solve runs on 32
+    host threads per emulated warp."""
+    q, qd, qa, t = f32(Q).copy(), f32(QD).copy(), f32(QA).copy(), f32(T)
+    n = q.shape[0]
+    info = np.zeros((n, 4), np.int32)
+    rc = hs.hs_stack_step(C.byref(gg_model), C.byref(task), n, _p(q), _p(qd), _p(qa), _p(t), iters, C.c_float(tol), _p(info))
+    assert rc == 0
+    return q, qd, qa, info
+
+
+def stack_random_states(m, rng, n):
+    """Reset-like states of the stacking scene: cubes on the plane at random spawn positions (with yaw and a small planar
+    velocity), env 1 with an overlapping pair, env 2 with cube_1 resting on cube_2, env 3 with cube_1 in free flight;
+    robot near home with random joint velocities."""
+    nu, K = m.nu, m.n_obj
+    Q = np.zeros((n, nu + 7 * K))
+    QD = np.zeros((n, nu + 6 * K))
+    Q[:, :nu] = m.home_q + rng.uniform(-0.25, 0.25, (n, nu))
+    Q[:, m.n_arm:nu] = rng.uniform(0.0, 0.04, (n, m.n_fing))
+    QD[:, :nu] = rng.normal(0, 0.4, (n, nu))
+    for k, (xlo, xhi, ylo, yhi) in enumerate(m.obj_spawn):
+        o = nu + 7 * k
+        Q[:, o] = rng.uniform(xlo, xhi, n)
+        Q[:, o + 1] = rng.uniform(ylo, yhi, n)
+        Q[:, o + 2] = m.plane_z + 0.02 - rng.uniform(0, 2e-4, n)
+        yaw = rng.uniform(-np.pi, np.pi, n)
+        Q[:, o + 3] = np.cos(yaw / 2)
+        Q[:, o + 6] = np.sin(yaw / 2)
+        QD[:, nu + 6 * k:nu + 6 * k + 2] = rng.normal(0, 0.05, (n, 2))
+    if n > 1:
+        Q[1, nu + 7:nu + 9] = Q[1, nu:nu + 2] + [0.021, 0.012]                 # cube_2 overlaps cube_1
+    if n > 2:
+        Q[2, nu + 7:nu + 14] = [Q[2, nu], Q[2, nu + 1], 0.0199, 1, 0, 0, 0]    # cube_1 on top of cube_2
+        Q[2, nu + 2:nu + 7] = [0.0597, 1, 0, 0, 0]
+        QD[2, nu:nu + 12] = 0
+    if n > 3:
+        Q[3, nu + 2] = 0.3
+        QD[3, nu:nu + 6] = rng.normal(0, 0.5, 6)
+    T = m.home_q + rng.uniform(-0.3, 0.3, (n, nu))
+    T[:, m.n_arm:] = rng.uniform(-0.02, 0.04, (n, m.n_fing))
+    return f32(Q).astype(np.float64), f32(QD).astype(np.float64), f32(T).astype(np.float64)
+
+
+# Contact-rich states of the stacking scene reach 60-96 contacts (pads on cube_1, cube_1 on cube_2, 16-20 cube-plane points),
+# twice the row count the pick scene's floor was sized for; the fp32 build of the oracle differs from its fp64 build by up
+# to 1.5e-5 rad/s on the golden trajectory (tools/make_stack_traj.py prints the spread).
+TOL_DQD_FLOOR_STACK = 6e-5
+
+
+def stack_substep_errors(q0, qd0, q_ref, qd_ref, q, qd, a_smooth_scale):
+    eq = np.abs(q - q_ref).max(axis=1)
+    d_ref = np.abs(qd_ref - qd0).max(axis=1)
+    ev = np.abs(qd - qd_ref).max(axis=1)
+    bound = TOL_DQD_REL * np.maximum(d_ref, a_smooth_scale) + TOL_DQD_FLOOR_STACK
+    return eq * TOL_Q_ABS / (TOL_Q_ABS + 0.01 * bound), ev / bound

@@ -1,0 +1,113 @@
+// TEST HARNESS ONLY: runs the multi-object step pipeline of gym_genesis_b200/csrc/gg_stack.cuh on the host so that the
+// kernel math -- including the WARP-COOPERATIVE solve, emulated with 32 host threads per warp and a barrier behind every
+// warp collective -- can be checked against the oracle in the CPU-only test tier.  The product never loads this library.
+#include <pthread.h>
+#include <stdint.h>
+#include <string.h>
+
+#include <thread>
+#include <vector>
+
+#include "gg_stack.cuh"
+
+namespace {
+
+struct HostWarp {
+    pthread_barrier_t bar;
+    float f[32];
+    int i[32];
+    HostWarp() { pthread_barrier_init(&bar, nullptr, 32); }
+    ~HostWarp() { pthread_barrier_destroy(&bar); }
+};
+
+struct WarpHost {
+    int lane;
+    HostWarp* w;
+    void sync() { pthread_barrier_wait(&w->bar); }
+    float shfl(float v, int src) { w->f[lane] = v; sync(); float r = w->f[src]; sync(); return r; }
+    int shfli(int v, int src) { w->i[lane] = v; sync(); int r = w->i[src]; sync(); return r; }
+    float sum(float v) { w->f[lane] = v; sync(); float r = 0.f; for (int l = 0; l < 32; l++) r += w->f[l]; sync(); return r; }
+    float max(float v) { w->f[lane] = v; sync(); float r = w->f[0]; for (int l = 1; l < 32; l++) r = fmaxf(r, w->f[l]); sync(); return r; }
+    bool any(bool p) { w->i[lane] = p ? 1 : 0; sync(); int r = 0; for (int l = 0; l < 32; l++) r |= w->i[l]; sync(); return r != 0; }
+    int scan_incl(int v) { w->i[lane] = v; sync(); int r = 0; for (int l = 0; l <= lane; l++) r += w->i[l]; sync(); return r; }
+};
+
+template <int NA, int NF, bool FH, int K>
+void run(const GgModel* M, const GgStackTask* T, int n, float* q, float* qd, float* qacc, const float* target, int iterations, float tol,
+         int32_t* info) {
+    constexpr int NU = NA + NF, NQ = NU + 7 * K, NV = NU + 6 * K;
+    auto* In = new gg::StackIn<NA, NF, K>;
+    auto* B = new gg::StackBuf<NU, K>;
+    HostWarp hw;
+    for (int e = 0; e < n; e++) {
+        float* pq = q + (size_t)e * NQ; float* pv = qd + (size_t)e * NV; float* pa = qacc + (size_t)e * NV;
+        gg::ObjState<K> O;
+        for (int k = 0; k < K; k++) {
+            const float* o = pq + NU + 7 * k; const float* v = pv + NU + 6 * k;
+            O.p[k] = gg::mk(o[0], o[1], o[2]); O.q[k] = gg::mkq(o[3], o[4], o[5], o[6]);
+            O.v[k] = gg::mk(v[0], v[1], v[2]); O.w[k] = gg::mk(v[3], v[4], v[5]);
+            float* d = In->obj[k];
+            for (int i = 0; i < 7; i++) d[i] = o[i];
+            for (int i = 0; i < 6; i++) { d[7 + i] = v[i]; In->warm_obj[k][i] = pa[NU + 6 * k + i]; }
+        }
+        gg::stack_prep<NA, NF, FH, K>(*M, pq, pv, pa, target + (size_t)e * NU, O, iterations, tol, true, In->W);
+        float a[NV];
+        int its[32], nc[32];
+        std::vector<std::thread> th;
+        for (int l = 0; l < 32; l++)
+            th.emplace_back([&, l]() {
+                WarpHost wc{l, &hw};
+                gg::stack_solve<NA, NF, FH, K>(*M, T->max_contacts, *In, *B, iterations, tol, wc, a, 1, its[l], nc[l]);
+            });
+        for (auto& t : th) t.join();
+        gg::integrate_robot<NU>(*M, pq, pv, pa, a);
+        for (int k = 0; k < K; k++) {
+            gg::integrate_cube(*M, O.p[k], O.q[k], O.v[k], O.w[k], pa + NU + 6 * k, a + NU + 6 * k);
+            float* o = pq + NU + 7 * k; float* v = pv + NU + 6 * k;
+            o[0] = O.p[k].x; o[1] = O.p[k].y; o[2] = O.p[k].z; o[3] = O.q[k].w; o[4] = O.q[k].x; o[5] = O.q[k].y; o[6] = O.q[k].z;
+            v[0] = O.v[k].x; v[1] = O.v[k].y; v[2] = O.v[k].z; v[3] = O.w[k].x; v[4] = O.w[k].y; v[5] = O.w[k].z;
+        }
+        if (info) {
+            const int ri = (int)In->W.rob_iters;
+            info[e * 4] = nc[0]; info[e * 4 + 1] = its[0] > ri ? its[0] : ri; info[e * 4 + 2] = In->W.coupled != 0.f; info[e * 4 + 3] = 0;
+        }
+    }
+    delete In;
+    delete B;
+}
+
+template <int NA, int NF, int K>
+void obs(const GgModel* M, const GgStackTask* T, int n, const float* q, float* agent, float* envs, float* reward, uint8_t* term) {
+    constexpr int NU = NA + NF, NQ = NU + 7 * K;
+    for (int e = 0; e < n; e++) {
+        const float* pq = q + (size_t)e * NQ;
+        gg::ObjState<K> O;
+        for (int k = 0; k < K; k++) {
+            const float* o = pq + NU + 7 * k;
+            O.p[k] = gg::mk(o[0], o[1], o[2]); O.q[k] = gg::mkq(o[3], o[4], o[5], o[6]);
+        }
+        bool ok;
+        gg::stack_observe<NA, NF, K>(*M, *T, pq, O, agent + (size_t)e * (7 + NF), envs + (size_t)e * GG_STACK_ENV_STATE_DIM, reward[e], ok);
+        term[e] = ok;
+    }
+}
+
+}  // namespace
+
+extern "C" {
+int hs_sizeof_stack_task(void) { return (int)sizeof(GgStackTask); }
+int hs_stack_step(const GgModel* M, const GgStackTask* T, int n, float* q, float* qd, float* qacc, const float* target, int iterations,
+                  float tol, int32_t* info) {
+    if (M->n_arm == 7 && M->n_fing == 2 && T->n_obj == 5) run<7, 2, false, 5>(M, T, n, q, qd, qacc, target, iterations, tol, info);
+    else return -1;
+    return 0;
+}
+int hs_stack_observe(const GgModel* M, const GgStackTask* T, int n, const float* q, float* agent, float* envs, float* reward, uint8_t* term) {
+    if (M->n_arm == 7 && M->n_fing == 2 && T->n_obj == 5) obs<7, 2, 5>(M, T, n, q, agent, envs, reward, term);
+    else return -1;
+    return 0;
+}
+void hs_stack_spawn(const GgStackTask* T, uint64_t seed, uint32_t gid, uint32_t episode, int k, float* xy) {
+    gg::stack_spawn_draw(*T, seed, gid, episode, k, xy[0], xy[1]);
+}
+}

@@ -1,0 +1,268 @@
+"""GPU tier of the multi-object (CubeStack) path, SURVEY.md 8f-1: the CUDA kernels called through the C ABI
+(BatchedStackSim -> gg_stack_* in libgg_b200.so) against the oracle and the committed golden trajectory."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from gym_genesis_b200.model import FRANKA_HOME, franka_cube_stack_model
+from helpers import (ROLLOUT_POS_TOL, TOL_Q_ABS, f32, stack_random_states, stack_substep_errors)
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "stack_traj.npz")
+
+
+@pytest.fixture(scope="module")
+def sm():
+    return franka_cube_stack_model()
+
+
+@pytest.fixture(scope="module")
+def orc(sm):
+    from oracle.binding import Oracle, build
+    build()
+    return Oracle(sm, np.float64)
+
+
+@pytest.fixture(scope="module")
+def Sim():
+    from gym_genesis_b200.sim import BatchedStackSim
+    return BatchedStackSim
+
+
+def _np(t):
+    return t.detach().cpu().numpy().astype(np.float64)
+
+
+def _asm(o, Q, QD, T):
+    return np.array([np.abs(o.dynamics(Q[k], QD[k], T[k])["a_smooth"]).max() * 0.01 for k in range(Q.shape[0])])
+
+
+def _one_substep(sim, Q, QD, QA, T):
+    sim.set_state(Q, QD, QA)
+    sim.step(torch.as_tensor(f32(T)))
+    q, qd, qa = sim.get_state()
+    return _np(q), _np(qd), _np(qa)
+
+
+def test_state_roundtrip_and_layout(Sim, sm):
+    n = 37
+    sim = Sim(sm, n)
+    assert sim.state.shape == (3 * 9 + 19 * 5, 64)
+    rng = np.random.default_rng(0)
+    Q, QD, QA = f32(rng.normal(size=(n, 44))), f32(rng.normal(size=(n, 39))), f32(rng.normal(size=(n, 39)))
+    sim.set_state(Q, QD, QA)
+    q, qd, qa = sim.get_state()
+    assert (q.cpu().numpy() == Q).all() and (qd.cpu().numpy() == QD).all() and (qa.cpu().numpy() == QA).all()
+    st = sim.state.cpu().numpy()
+    assert (st[0:9, :n].T == Q[:, :9]).all() and (st[18 + 13:18 + 13 + 7, :n].T == Q[:, 16:23]).all()
+
+
+def test_single_substep_random_states(Sim, sm, orc):
+    n = 192
+    rng = np.random.default_rng(31)
+    Q, QD, T = stack_random_states(sm, rng, n)
+    QA = np.zeros_like(QD)
+    sim = Sim(sm, n)
+    q, qd, qa = _one_substep(sim, Q, QD, QA, T)
+    qo, qdo, qao = Q.copy(), QD.copy(), QA.copy()
+    info, _ = orc.step(qo, qdo, qao, T, iterations=100, tol=1e-12)
+    nc, it = sim.step_info()
+    assert (nc.cpu().numpy() == info[:, 0]).all()             # identical contact counts, cube-cube pairs included
+    eq, ev = stack_substep_errors(Q, QD, qo, qdo, q, qd, _asm(orc, Q, QD, T))
+    assert eq.max() < TOL_Q_ABS and ev.max() < 1.0, (eq.max(), ev.max(), int(np.argmax(ev)))
+    # observations / reward / flags against the oracle on the GPU's own state: flags bit-exact
+    a, e, r, t = orc.obs(q)
+    assert np.abs(_np(sim.obs_agent) - a).max() < 2e-6 and np.abs(_np(sim.obs_env) - e).max() < 2e-6
+    assert (sim.terminated.cpu().numpy().astype(bool) == t).all() and t[2]
+    assert (sim.reward.cpu().numpy() == r.astype(np.float32)).all()
+    assert not sim.truncated.any()
+
+
+def test_single_substep_golden_stack_trajectory(Sim, sm):
+    """Every sample of the committed pick-and-stack rollout (free space, grasp with 36-52 contacts, carry, cube_1 lowered onto
+    cube_2, release) against the oracle's stored next state."""
+    g = np.load(GOLDEN)
+    Q, QD, QA, T = g["q"], g["qd"], g["qacc"], g["act"]
+    sim = Sim(sm, Q.shape[0])
+    q, qd, qa = _one_substep(sim, Q, QD, QA, T)
+    nc, it = sim.step_info()
+    assert (nc.cpu().numpy() == g["ncon"]).all()
+    eq, ev = stack_substep_errors(Q, QD, g["qn"], g["qdn"], q, qd, g["asm"])
+    assert eq.max() < TOL_Q_ABS and ev.max() < 1.0, (eq.max(), ev.max(), int(np.argmax(ev)))
+    assert it.max().item() <= 10
+
+
+def test_reset_matches_reference_semantics(Sim, sm, orc):
+    """reset = per-cube spawn (host stream), home pose, hold-home targets, ONE settle step, obs (cube_stack.py:119-170)."""
+    n = 64
+    rng = np.random.RandomState(5)
+    xy = np.zeros((n, 5, 2), np.float32)
+    for k, (xlo, xhi, ylo, yhi) in enumerate(sm.obj_spawn):
+        xy[:, k, 0] = rng.uniform(xlo, xhi, n)
+        xy[:, k, 1] = rng.uniform(ylo, yhi, n)
+    sim = Sim(sm, n)
+    sim.reset(None, xy)
+    q, qd, qa = (_np(t) for t in sim.get_state())
+    qo, qdo, qao = orc.new_state(n)
+    orc.reset(qo, qdo, qao, xy.astype(np.float64))
+    q0, qd0 = qo.copy(), qdo.copy()
+    tgt = np.tile(FRANKA_HOME, (n, 1))
+    orc.step(qo, qdo, qao, tgt, iterations=100, tol=1e-12)
+    eq, ev = stack_substep_errors(q0, qd0, qo, qdo, q, qd, _asm(orc, q0, qd0, tgt))
+    assert eq.max() < TOL_Q_ABS and ev.max() < 1.0, (eq.max(), ev.max())
+    a, e, r, t = orc.obs(q)
+    assert np.abs(_np(sim.obs_agent) - a).max() < 2e-6 and np.abs(_np(sim.obs_env) - e).max() < 2e-6
+    assert (sim.episode.cpu().numpy() == 1).all() and (sim.step_count.cpu().numpy() == 0).all()
+
+
+def test_masked_reset_counters_and_philox_spawn_bit_exact(Sim, sm, orc):
+    n = 96
+    seed = 1234
+    sim = Sim(sm, n, seed=seed, first_env_id=1000)
+    sim.reset(None, None)                                     # device Philox draws for every env, episode 0
+    q0 = sim.get_state()[0].cpu().numpy()
+    sim.configure(solver_iterations=10)
+    tgt = torch.as_tensor(f32(np.tile(FRANKA_HOME, (n, 1))))
+    for _ in range(3):
+        sim.step(tgt)
+    assert (sim.step_count.cpu().numpy() == 3).all()
+    mask = np.zeros(n, bool)
+    mask[::3] = True
+    before = sim.get_state()[0].cpu().numpy()
+    sim.step(tgt, reset_mask=mask)
+    q1 = sim.get_state()[0].cpu().numpy()
+    sc, ep = sim.step_count.cpu().numpy(), sim.episode.cpu().numpy()
+    assert (sc[mask] == 0).all() and (sc[~mask] == 4).all() and (ep[mask] == 2).all() and (ep[~mask] == 1).all()
+    # spawn xy of reset envs: bit-exact Philox draws keyed by (seed, GLOBAL env id, episode, object); z / quat settle by < 1e-3
+    for e in np.nonzero(mask)[0][:12]:
+        for k in range(5):
+            ref = orc.spawn_obj(seed, 1000 + int(e), 1, k)
+            got = q1[e, 9 + 7 * k: 9 + 7 * k + 2]
+            assert np.abs(got - ref).max() < 2e-4             # one settle step may nudge overlapping cubes
+    e = int(np.nonzero(mask)[0][0])
+    first = np.array([orc.spawn_obj(seed, 1000 + e, 0, k) for k in range(5)])
+    far = np.min([np.abs(first[i] - first[j]).max() for i in range(5) for j in range(i)]) > 0.045
+    if far:
+        assert np.abs(q0[e, 9:44].reshape(5, 7)[:, :2] - first).max() < 1e-6
+    # envs outside the mask were stepped, not touched by the reset
+    assert np.abs(q1[~mask, 9:] - before[~mask, 9:]).max() < 1e-3
+
+
+def test_rollout_100_steps(Sim, sm, orc):
+    """100 control steps, smooth random-walk targets, cubes resting (some pushed apart from overlapping spawns)."""
+    n = 24
+    rng = np.random.default_rng(21)
+    sim = Sim(sm, n)
+    xy = np.zeros((n, 5, 2), np.float32)
+    for k, (xlo, xhi, ylo, yhi) in enumerate(sm.obj_spawn):
+        xy[:, k, 0] = rng.uniform(xlo, xhi, n)
+        xy[:, k, 1] = rng.uniform(ylo, yhi, n)
+    sim.reset(None, xy)
+    q, qd, qa = (_np(t) for t in sim.get_state())
+    tgt = np.tile(FRANKA_HOME, (n, 1))
+    for _ in range(100):
+        tgt = tgt + rng.normal(0, 0.02, tgt.shape)
+        tgt[:, 7:] = np.clip(tgt[:, 7:], -0.02, 0.04)
+        t32 = f32(tgt)
+        sim.step(torch.as_tensor(t32))
+        orc.step(q, qd, qa, t32.astype(np.float64), iterations=100, tol=1e-10)
+    qg = _np(sim.get_state()[0])
+    pos_cols = list(range(9)) + [9 + 7 * k + c for k in range(5) for c in range(3)]
+    err = np.abs(qg[:, pos_cols] - q[:, pos_cols]).max()
+    assert err < ROLLOUT_POS_TOL, err
+
+
+def test_full_size_invariants(Sim, sm):
+    """16384 envs, 40 steps with random targets, Bernoulli resets and auto-reset: finite state, unit quaternions, cubes on or
+    above the plane, joints inside their (soft) limits, counters consistent with the statistics."""
+    n = 16384
+    sim = Sim(sm, n, auto_reset=True, reset_prob=0.01, seed=3)
+    sim.reset(None, None)
+    g = torch.Generator(device="cuda").manual_seed(0)
+    home = torch.as_tensor(f32(FRANKA_HOME), device="cuda")
+    sim.stats(clear=True)
+    for _ in range(40):
+        a = home + (torch.rand((n, 9), device="cuda", generator=g) - 0.5) * 0.6
+        a[:, 7:] = torch.rand((n, 2), device="cuda", generator=g) * 0.06 - 0.02
+        sim.step(a)
+    q, qd, qa = sim.get_state()
+    assert torch.isfinite(q).all() and torch.isfinite(qd).all() and torch.isfinite(qa).all()
+    cubes = q[:, 9:].reshape(n, 5, 7)
+    assert (cubes[:, :, 3:].norm(dim=2) - 1).abs().max() < 1e-5
+    assert cubes[:, :, 2].min() > 0.015 and cubes[:, :, 2].max() < 0.2
+    lo = torch.as_tensor(list(sim.gg_model.lim_lo), device="cuda")
+    hi = torch.as_tensor(list(sim.gg_model.lim_hi), device="cuda")
+    assert (q[:, :9] > lo - 0.05).all() and (q[:, :9] < hi + 0.05).all()
+    st = sim.stats().cpu().numpy()
+    assert st[5] == 0 and 0.97 * 40 * n < st[0] <= 40 * n and st[7] / st[0] >= 19.0     # >= 5 x 4 plane contacts per env-step
+
+
+def test_gym_surface_cube_stack(sm):
+    import gym_genesis  # noqa: F401  (registers the ids on the B200 backend)
+    from gym_genesis_b200.gym_api import gym
+    n = 48
+    env = gym.make("gym_genesis/CubeStack-v0", robot="franka", num_envs=n)
+    u = env.unwrapped
+    assert u.observation_space["agent_pos"].shape == (9,) and u.observation_space["environment_state"].shape == (14,)
+    obs, info = env.reset(seed=3)
+    assert obs["agent_pos"].shape == (n, 9) and obs["environment_state"].shape == (n, 14) and obs["agent_pos"].is_cuda
+    first = obs["environment_state"].clone()
+    a = torch.as_tensor(f32(np.tile(FRANKA_HOME, (n, 1))), device="cuda")
+    obs, reward, terminated, truncated, info = u.step(a)
+    assert reward.shape == (n,) and terminated.dtype == torch.bool and truncated.dtype == torch.bool and not truncated.any()
+    assert (terminated == (reward == 1)).all() and (info["is_success"] == terminated).all()
+    assert torch.allclose(u.get_cube().get_pos(), obs["environment_state"][:, 0:3])
+    assert torch.allclose(u._env.cube_2.get_pos(), obs["environment_state"][:, 11:14])
+    # same seed -> bit-identical observations (the property tester.py:11-28 probes)
+    obs2, _ = env.reset(seed=3)
+    assert (obs2["environment_state"] == first).all()
+    # the reference's host RandomState stream: cube_1 x draws first, then cube_1 y, cube_2 x, ... (cube_stack.py:123-145)
+    rs = np.random.RandomState(3)
+    x1 = rs.uniform(0.45, 0.75, size=(n,)); y1 = rs.uniform(-0.2, 0.2, size=(n,))
+    x2 = rs.uniform(0.3, 0.7, size=(n,)); y2 = rs.uniform(-0.3, 0.3, size=(n,))
+    es = obs2["environment_state"].cpu().numpy()
+    d12 = np.maximum(np.abs(x1 - x2), np.abs(y1 - y2))
+    ok = d12 > 0.3                                            # cubes that certainly did not touch anything in the settle step
+    assert np.abs(es[ok, 11] - x2[ok]).max() < 1e-3 and np.abs(es[ok, 12] - y2[ok]).max() < 1e-3
+    assert np.abs(es[:, 0] - x1).max() < 5e-3 and np.abs(es[:, 1] - y1).max() < 5e-3
+    env.close()
+
+
+def test_expert_closed_loop_stacks_on_device(Sim, sm):
+    """The collectors' stage machine (hover, descend, grasp, lift, carry, lower, release, retreat) with robot.inverse_kinematics
+    and env.step both on the device: a clear majority of well-separated envs ends with cube_1 resting on cube_2."""
+    from gym_genesis_b200.tasks import FrankaCubeStackEmptyBatch
+    n = 256
+    task = FrankaCubeStackEmptyBatch(False, 480, 640, n, (1.0, 1.0), "global", True)
+    task.seed(1)
+    task.reset()
+    dev = task.sim.device
+    down = torch.tensor([0.0, 1.0, 0.0, 0.0], device=dev).repeat(n, 1)
+    plan = [("c1", 0.2, 0.04, 40), ("c1", 0.105, 0.04, 40), ("c1", 0.105, -0.02, 30), ("lift", 0.25, -0.02, 50),
+            ("c2", 0.23, -0.02, 70), ("c2", 0.148, -0.02, 60), ("c2", 0.148, 0.04, 30), ("c2", 0.3, 0.04, 30)]
+    c1_0, c2_0 = task.cube_1.get_pos(), task.cube_2.get_pos()
+    others = torch.stack([c.get_pos() for c in task.distractor_cubes], 1)
+    sep = (c1_0 - c2_0)[:, :2].norm(dim=1) > 0.12
+    for o in range(others.shape[1]):
+        sep &= ((others[:, o] - c1_0)[:, :2].norm(dim=1) > 0.12) & ((others[:, o] - c2_0)[:, :2].norm(dim=1) > 0.12)
+    hold = None
+    for name, dz, grip, steps in plan:
+        for _ in range(steps):
+            c1, c2 = task.cube_1.get_pos(), task.cube_2.get_pos()
+            if name == "c1":
+                tp = c1 + torch.tensor([0.0, 0.0, dz], device=dev); hold = c1.clone()
+            elif name == "lift":
+                tp = hold + torch.tensor([0.0, 0.0, dz], device=dev)
+            else:
+                tp = torch.stack([c2[:, 0], c2[:, 1], torch.full((n,), 0.02 + dz, device=dev)], 1)
+            qt = task.robot.inverse_kinematics(link=task.eef, pos=tp, quat=down)
+            act = qt.clone()
+            act[:, 7:] = grip
+            task.step(act)
+    rew = task.compute_reward()
+    assert sep.sum().item() >= 40
+    rate = rew[sep].mean().item()
+    assert rate > 0.5, (rate, int(sep.sum()))
+    assert torch.isfinite(task.sim.get_state()[0]).all()

@@ -1,0 +1,184 @@
+"""CPU tier of the multi-object (CubeStack) path, SURVEY.md 8f-1: the oracle's stacking scene against closed forms and
+conservation laws, the golden trajectory against the oracle that generated it, and the DEVICE pipeline of gg_stack.cuh --
+including the warp-cooperative solve, emulated with 32 host threads per warp -- against the oracle."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from gym_genesis_b200 import cabi
+from gym_genesis_b200.model import franka_cube_stack_model
+from helpers import (TOL_Q_ABS, _p, f32, hostsim_stack_step, stack_random_states, stack_substep_errors)
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "stack_traj.npz")
+
+
+@pytest.fixture(scope="module")
+def sm():
+    return franka_cube_stack_model()
+
+
+@pytest.fixture(scope="module")
+def orc(sm):
+    from oracle.binding import Oracle, build
+    build()
+    return Oracle(sm, np.float64)
+
+
+@pytest.fixture(scope="module")
+def gg(sm):
+    return cabi.compile_gg(sm), cabi.compile_stack_task(sm)
+
+
+def _rest_state(orc, sm, xy):
+    q, qd, qa = orc.new_state(1)
+    orc.reset(q, qd, qa, np.asarray(xy, dtype=np.float64)[None])
+    return q, qd, qa
+
+
+SPREAD = [[0.55, 0.05], [0.5, -0.15], [0.35, 0.25], [0.65, 0.25], [0.4, -0.25]]
+
+
+# ---- the oracle's stacking scene -----------------------------------------------------------------------------------
+def test_model_sizes_and_reference_constants(sm):
+    assert (sm.nu, sm.n_obj, sm.nv, sm.nq) == (9, 5, 39, 44)
+    # franka/cube_stack.py:125-126, 132-133, 141-142
+    assert sm.obj_spawn[0] == (0.45, 0.75, -0.2, 0.2) and all(s == (0.3, 0.7, -0.3, 0.3) for s in sm.obj_spawn[1:])
+    t = sm.dof_table()
+    assert list(t["kp"][:9]) == [4500, 4500, 3500, 3500, 2000, 2000, 2000, 100, 100]       # :156
+    assert list(t["kv"][:9]) == [450, 450, 350, 350, 200, 200, 200, 10, 10]                # :157
+    assert list(t["frc_hi"][:9]) == [87] * 7 + [100, 100]                                  # :158-161
+    assert (sm.stack_xy, sm.stack_z) == (0.05, 0.03)                                       # :195
+
+
+def test_stacked_cube_rests_and_scores(orc, sm):
+    xy = [list(x) for x in SPREAD]
+    xy[0] = xy[1]
+    q, qd, qa = _rest_state(orc, sm, xy)
+    q[0, 9 + 2] = 0.06
+    tgt = sm.home_q[None].copy()
+    for _ in range(150):
+        info, _ = orc.step(q, qd, qa, tgt)
+    assert info[0, 0] == 20                                   # 4 x 4 cube-plane corners + 4 face contacts cube_1 on cube_2
+    assert np.abs(qd[0, 9:21]).max() < 1e-6
+    # closed form of the soft contact at rest: 4 corners share m g, each through 4 pyramidal rows with
+    # D = 1 / (2 mu^2 (1 + mu^2) (1 - imp) / imp w), imp = dmax beyond the 1 mm width; top cube rests deeper on its support
+    z1, z2 = q[0, 11], q[0, 18]
+    assert 0.0195 < z2 < 0.02 and 0.039 < z1 - z2 < 0.04
+    _, envs, rew, term = orc.obs(q)
+    assert rew[0] == 1.0 and term[0]
+    assert np.allclose(envs[0, 11:14], q[0, 16:19]) and np.allclose(envs[0, 0:3], q[0, 9:12])
+
+
+def test_overlapping_spawn_is_pushed_apart(orc, sm):
+    xy = [list(x) for x in SPREAD]
+    xy[1] = [xy[0][0] + 0.02, xy[0][1] + 0.01]
+    q, qd, qa = _rest_state(orc, sm, xy)
+    assert len(orc.contacts(q[0])) > 20                       # cube-cube box-box contacts exist (box_box_detection=True)
+    tgt = sm.home_q[None].copy()
+    for _ in range(200):
+        orc.step(q, qd, qa, tgt)
+    d = q[0, 9:11] - q[0, 16:18]
+    assert max(abs(d[0]), abs(d[1])) > 0.0399                 # separated along a face normal
+    assert len(orc.contacts(q[0])) == 20 and np.all(np.isfinite(q))
+
+
+def test_cube_cube_contact_forces_are_internal(orc, sm):
+    """Two cubes colliding in free flight: the contact rows enter with J_b - J_a, so the pair's total linear momentum
+    changes by gravity alone."""
+    q, qd, qa = _rest_state(orc, sm, SPREAD)
+    q[0, 9:12] = [0.5, 0.0, 0.5]
+    q[0, 16:19] = [0.5, 0.036, 0.51]
+    qd[0, 9:15] = [0, 0.4, 0, 0.3, -0.2, 0.1]
+    qd[0, 15:21] = [0, -0.3, 0, 0, 0.5, 0]
+    p0 = qd[0, 9:12] + qd[0, 15:18]
+    info, _ = orc.step(q, qd, qa, sm.home_q[None].copy())
+    assert info[0, 0] > 12                                    # 3 resting distractors x 4 corners + the cube-cube points
+    p1 = qd[0, 9:12] + qd[0, 15:18]
+    assert np.allclose(p1 - p0, [0, 0, -2 * 9.81 * 0.01], atol=1e-9)
+    assert abs(qd[0, 10] - 0.4) > 1e-3                        # and the contact did act
+
+
+def test_reward_thresholds_are_float32_strict(orc, sm):
+    q, _, _ = _rest_state(orc, sm, SPREAD)
+    Q = np.repeat(q, 6, axis=0)
+    Q[:, 16:19] = [0.5, 0.0, 0.02]
+    c = np.float32
+    cases = [(c(0.5) + c(0.04), 0.0, 0.06, True), (0.5, 0.0, c(0.02) + c(0.03), False),     # z diff == 0.03f: not >
+             (0.5, 0.0, np.nextafter(c(0.02) + c(0.03), c(1)), True), (0.55, 0.0, 0.06, False),   # xy == 0.05: not <
+             (0.5, 0.0499, 0.06, True), (0.5, 0.0, 0.04, False)]
+    for i, (x, y, z, _) in enumerate(cases):
+        Q[i, 9:12] = [x, y, z]
+    _, _, rew, term = orc.obs(f32(Q).astype(np.float64))
+    assert [bool(r) for r in rew] == [e for *_, e in cases] and list(term) == [e for *_, e in cases]
+
+
+def test_golden_trajectory_is_the_oracles(orc):
+    g = np.load(GOLDEN)
+    assert g["final_reward"][0] == 1.0 and g["ncon"].max() >= 48 and g["ncon"].min() == 16
+    idx = np.arange(0, len(g["q"]), 7)
+    q, qd, qa = g["q"][idx].copy(), g["qd"][idx].copy(), g["qacc"][idx].copy()
+    info, _ = orc.step(q, qd, qa, g["act"][idx], iterations=100, tol=1e-12)
+    assert np.abs(q - g["qn"][idx]).max() < 1e-12 and np.abs(qd - g["qdn"][idx]).max() < 1e-10
+    assert (info[:, 0] == g["ncon"][idx]).all()
+
+
+# ---- device pipeline on the host harness ---------------------------------------------------------------------------
+def test_struct_layout_matches_header(hostsim):
+    assert hostsim.hs_sizeof_stack_task() == C.sizeof(cabi.GgStackTask)
+
+
+def _asm(o, Q, QD, T):
+    return np.array([np.abs(o.dynamics(Q[k], QD[k], T[k])["a_smooth"]).max() * 0.01 for k in range(Q.shape[0])])
+
+
+def test_substep_random_states(hostsim, gg, sm, orc):
+    rng = np.random.default_rng(11)
+    Q, QD, T = stack_random_states(sm, rng, 16)
+    QA = np.zeros_like(QD)
+    qo, qdo, qao = Q.copy(), QD.copy(), QA.copy()
+    info, _ = orc.step(qo, qdo, qao, T, iterations=100, tol=1e-12)
+    q, qd, qa, hinfo = hostsim_stack_step(hostsim, gg[0], gg[1], Q, QD, QA, T)
+    assert (hinfo[:, 0] == info[:, 0]).all()                  # identical contact counts (incl. cube-cube pairs)
+    assert info[1, 0] > 20 and info[2, 0] == 20 and info[3, 0] == 16
+    eq, ev = stack_substep_errors(Q, QD, qo, qdo, q, qd, _asm(orc, Q, QD, T))
+    assert eq.max() < TOL_Q_ABS and ev.max() < 1.0, (eq.max(), ev.max())
+    # warm start from the converged accelerations: same answer, at most as many iterations
+    q2, qd2, _, hinfo2 = hostsim_stack_step(hostsim, gg[0], gg[1], Q, QD, qao, T)
+    eq2, ev2 = stack_substep_errors(Q, QD, qo, qdo, q2, qd2, _asm(orc, Q, QD, T))
+    assert ev2.max() < 1.0 and (hinfo2[:, 1] <= np.maximum(hinfo[:, 1], 1)).all()
+
+
+def test_substep_along_golden_stack_trajectory(hostsim, gg, orc):
+    g = np.load(GOLDEN)
+    idx = np.arange(0, len(g["q"]), 4)
+    Q, QD, QA, T = g["q"][idx], g["qd"][idx], g["qacc"][idx], g["act"][idx]
+    q, qd, qa, hinfo = hostsim_stack_step(hostsim, gg[0], gg[1], Q, QD, QA, T)
+    assert (hinfo[:, 0] == g["ncon"][idx]).all()
+    assert hinfo[:, 2].min() == 0 and hinfo[:, 2].max() == 1  # both the decoupled and the coupled path are exercised
+    eq, ev = stack_substep_errors(Q, QD, g["qn"][idx], g["qdn"][idx], q, qd, g["asm"][idx])
+    assert eq.max() < TOL_Q_ABS and ev.max() < 1.0, (eq.max(), ev.max(), int(np.argmax(ev)))
+
+
+def test_observation_and_flags_bit_exact(hostsim, gg, sm, orc):
+    g = np.load(GOLDEN)
+    Q = f32(np.concatenate([g["q"][::5], g["final_q"]]))
+    n = Q.shape[0]
+    agent, envs = np.zeros((n, 9), np.float32), np.zeros((n, 14), np.float32)
+    rew, term = np.zeros(n, np.float32), np.zeros(n, np.uint8)
+    assert hostsim.hs_stack_observe(C.byref(gg[0]), C.byref(gg[1]), n, _p(Q), _p(agent), _p(envs), _p(rew), _p(term)) == 0
+    a, e, r, t = orc.obs(Q.astype(np.float64))
+    assert np.abs(agent - a).max() < 2e-6 and np.abs(envs - e).max() < 2e-6
+    assert (rew == r).all() and (term.astype(bool) == t).all() and t.any() and not t.all()
+
+
+def test_spawn_draws_bit_exact(hostsim, gg, orc):
+    for seed, gid, epi in [(0, 0, 0), (7, 123456, 3), (2 ** 40 + 5, 16383, 17)]:
+        for k in range(5):
+            xy = np.zeros(2, np.float32)
+            hostsim.hs_stack_spawn(C.byref(gg[1]), C.c_uint64(seed), C.c_uint32(gid), C.c_uint32(epi), k, _p(xy))
+            ref = orc.spawn_obj(seed, gid, epi, k)
+            assert xy.tobytes() == ref.tobytes()
+            lo, hi = gg[1].spawn_lo[k], gg[1].spawn_hi[k]
+            assert lo[0] <= xy[0] <= hi[0] and lo[1] <= xy[1] <= hi[1]
