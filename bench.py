@@ -356,6 +356,51 @@ def run_gpu(args):
                          "bytes_to_host": int(frames.numel() * 4), "note": "gg_export_successful (select + gather) + one D2H copy of the successful envs"}}
         envc.close()
 
+    # ---- workload D: CubeStack scene, five free cubes, cube-cube contacts (gg_stack_*: 3 launches / step) ----
+    wd = None
+    spath = os.path.join(ROOT, "tests", "golden", "stack_traj.npz")
+    if not args.no_workload_d and os.path.exists(spath):
+        from gym_genesis_b200.model import franka_cube_stack_model
+        from gym_genesis_b200.sim import BatchedStackSim
+        sm = franka_cube_stack_model()
+
+        def timed_steps(sim, batches):
+            ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in batches]
+            for k, b in enumerate(batches):
+                flush.fill_(k & 0xFF)
+                ev[k][0].record(); sim.step(b); ev[k][1].record()
+            torch.cuda.synchronize(dev)
+            return np.array([a.elapsed_time(b) for a, b in ev])
+
+        sims = BatchedStackSim(sm, n, device=dev, auto_reset=True, reset_prob=1.0 / 200, seed=args.seed, first_env_id=rank * n)
+        sims.reset(None, None)
+        gd = torch.Generator(device=dev).manual_seed(args.seed + 17)
+        home9 = torch.as_tensor(sm.home_q.astype(np.float32), device=dev)
+        nd = 220
+        ad = home9 + (torch.rand((nd, n, 9), device=dev, generator=gd) - 0.5) * 0.6
+        ad[:, :, 7:] = torch.rand((nd, n, 2), device=dev, generator=gd) * 0.06 - 0.02
+        timed_steps(sims, [ad[k] for k in range(20)])
+        sims.stats(clear=True)
+        l0 = BatchedSim.launch_count()
+        td = timed_steps(sims, [ad[k] for k in range(20, nd)])
+        ld = BatchedSim.launch_count() - l0
+        sd = sims.stats().cpu().numpy()
+        sims.close()
+        gs_ = np.load(spath)
+        simr = BatchedStackSim(sm, n, device=dev)
+        simr.reset(None, np.repeat(gs_["spawn"], n, axis=0))
+        af = torch.as_tensor(gs_["act_full"], device=dev)
+        tr = timed_steps(simr, [af[k].repeat(n, 1).contiguous() for k in range(af.shape[0])])
+        sr = simr.stats().cpu().numpy()
+        wd = {"workload": "CubeStack scene (Panda + cube_1 + cube_2 + 3 distractors, franka/cube_stack.py), %d envs: random joint targets, "
+                          "Bernoulli(1/200) resets + auto-reset" % n,
+              "value": n / (td.mean() * 1e-3), "unit": "env-steps/s", "ms_per_step": float(td.mean()), "launches_per_step": ld / len(td),
+              "mean_contacts": sd[7] / max(sd[0], 1), "mean_solver_iters": sd[6] / max(sd[0], 1), "nonfinite_resets": sd[5],
+              "replay": {"workload": "golden pick-and-stack rollout (tests/golden/stack_traj.npz) replayed open-loop in every env",
+                         "value": n / (tr.mean() * 1e-3), "unit": "env-steps/s", "ms_per_step": float(tr.mean()),
+                         "mean_contacts": sr[7] / max(sr[0], 1), "success_rate": float(simr.reward.mean().item())}}
+        simr.close()
+
     times = torch.tensor([t_ms, warm_ms, e2e_ms, e2e_copy_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
@@ -381,7 +426,7 @@ def run_gpu(args):
                        "copy_engine_note": "same loop with cudaMemcpyAsync H2D of the action and D2H of reward / terminated / truncated"},
                "gpu_launches": int(launches), "clocks": clocks,
                "l2_warm": {"value": n * world * args.steps / (warm_ms * 1e-3), "unit": "env-steps/s", "note": "back-to-back launches, no L2 flush"},
-               "wall_s_timed_loop": wall, "workload_b": wb, "workload_c": wc,
+               "wall_s_timed_loop": wall, "workload_b": wb, "workload_c": wc, "workload_d": wd,
                "episode_stats": {"env_steps": st[0], "episodes": st[1], "successes": st[2], "nonfinite_resets": st[5],
                                  "mean_solver_iters": st[6] / max(st[0], 1), "mean_contacts": st[7] / max(st[0], 1)}}
         if not args.no_cpu_baseline and world == 1:
@@ -422,6 +467,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-workload-b", action="store_true")
     ap.add_argument("--no-workload-c", action="store_true")
+    ap.add_argument("--no-workload-d", action="store_true")
     args = ap.parse_args()
     args.out = JsonStdout()
     if args.impl == "reference":

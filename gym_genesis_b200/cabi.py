@@ -48,7 +48,7 @@ class GgModel(C.Structure):
 class GgStackTask(C.Structure):
     _fields_ = [("n_obj", _i), ("max_contacts", _i),
                 ("spawn_lo", (_f * 2) * GG_MAX_OBJ), ("spawn_hi", (_f * 2) * GG_MAX_OBJ),
-                ("stack_xy", _f), ("stack_z", _f)]
+                ("stack_xy", _f), ("stack_z", _f), ("min_dist", _f), ("agent_qpos", _i)]
 
 
 class GgConfig(C.Structure):
@@ -219,6 +219,7 @@ def compile_stack_task(sm: "mdl.SceneModel") -> GgStackTask:
     for k, (xlo, xhi, ylo, yhi) in enumerate(sm.obj_spawn):
         _set(t.spawn_lo[k], [xlo, ylo]); _set(t.spawn_hi[k], [xhi, yhi])
     t.stack_xy, t.stack_z = sm.stack_xy, sm.stack_z
+    t.min_dist, t.agent_qpos = sm.stack_min_dist, int(sm.agent_mode == "qpos")
     return t
 
 
@@ -233,7 +234,7 @@ EXPORTS = ["gg_last_error", "gg_version", "gg_create", "gg_destroy", "gg_configu
            "gg_ik", "gg_ik_defaults", "gg_frame_dim", "gg_record", "gg_export_successful",
            "gg_stack_create", "gg_stack_destroy", "gg_stack_configure", "gg_stack_state_rows", "gg_stack_state_stride",
            "gg_stack_bind_state", "gg_stack_step", "gg_stack_reset", "gg_stack_get_state", "gg_stack_set_state", "gg_stack_observe",
-           "gg_stack_stats", "gg_stack_info"]
+           "gg_stack_stats", "gg_stack_info", "gg_stack_agent_dim"]
 
 _lib = None
 
@@ -283,6 +284,7 @@ def load_library():
     lib.gg_stack_observe.argtypes = [vp] * 6
     lib.gg_stack_stats.argtypes = [vp, vp, C.c_int, vp]
     lib.gg_stack_info.argtypes = [vp, vp, vp, vp]
+    lib.gg_stack_agent_dim.argtypes = [vp]
     for name in EXPORTS:
         getattr(lib, name)
     _lib = lib

@@ -2,11 +2,14 @@
 // Replaces, for gym_genesis/tasks/franka/cube_stack.py:119-216, the Genesis calls of reset / step / compute_reward / get_obs.
 //
 // One env.step = three launches on the caller's stream (per-env pipeline in gg_stack.cuh):
-//   stack_prep_kernel    thread per env, 32 envs per block.  Masked reset, robot dynamics, pad broad phase, decoupled robot solve.
-//                        The StackIn record of each env (robot dynamics + object states, 297 floats) is transposed through shared
-//                        memory and written env-major, so that both this kernel's stores and the solver's loads are coalesced.
-//   stack_solve_kernel   WARP per env, 4 envs per block, ~23 KB of dynamic shared memory per warp (contact table, pair stiffness,
-//                        39 x 39 packed Hessian).  Accelerations go to a [dof][env] slab.
+//   stack_prep_kernel    thread per env, 32 envs per block.  Masked reset, robot dynamics, body-level broad phase (pads vs plane /
+//                        cubes, cube vs cube); every body that can touch nothing but the plane is solved HERE in registers
+//                        (robot block with joint-limit rows, 6 x 6 cube blocks with <= 4 plane contacts).  The StackIn record of
+//                        each env (robot dynamics + object states) is transposed through shared memory and written env-major, so
+//                        that both this kernel's stores and the solver's loads are coalesced.
+//   stack_solve_kernel   WARP per env that has bodies in reach of each other, 4 envs per block, ~23 KB of dynamic shared memory
+//                        per warp (contact table, pair stiffness, packed Hessian of the active dofs).  Accelerations go to a
+//                        [dof][env] slab.
 //   stack_finish_kernel  thread per env.  Integration, observations, reward / flags, counters, statistics.
 // The records and the slab (22 MB at 16384 envs) stay L2 resident between the three kernels.
 #include <cuda_runtime.h>
@@ -73,7 +76,10 @@ struct StackArgs {
     float* work;              // n x sizeof(StackIn) / 4 floats, env-major
     float* acc;               // NV x stride accelerations, [dof][env]
     int32_t* ncon; int32_t* iters;
-    uint8_t* flags;           // per env: bit 0 reset applied by this call, bit 1 a substep runs
+    uint8_t* flags;           // per env: bit 0 reset applied by this call, bit 1 a substep runs, bit 2 some bodies need the
+                              // cooperative solve (otherwise stack_prep's register solves are the whole answer)
+    int32_t* coop_list;       // envs that need the cooperative solve, appended by stack_prep_kernel (order irrelevant: envs are independent)
+    int32_t* coop_ctr;        // [0] list length, [1] pop cursor of the persistent solver warps; cleared by stack_finish_kernel
 };
 
 // state rows: q [0, NU) | qd [NU, 2NU) | objects 13 K | warm start NU + 6 K
@@ -98,11 +104,16 @@ __device__ __forceinline__ bool stack_reset_decision(const StackArgs& A, int e, 
 
 template <int K>
 __device__ __forceinline__ void spawn_objects(const StackArgs& A, int e, uint32_t gid, uint32_t epi, bool use_xy, gg::ObjState<K>& O) {
+    float xy[K][2];
+    if (use_xy && A.obj_xy != nullptr) {
+#pragma unroll
+        for (int k = 0; k < K; k++) { xy[k][0] = A.obj_xy[((size_t)e * K + k) * 2]; xy[k][1] = A.obj_xy[((size_t)e * K + k) * 2 + 1]; }
+    } else {
+        gg::stack_spawn_all(A.T, A.seed, gid, epi, K, xy);
+    }
 #pragma unroll
     for (int k = 0; k < K; k++) {
-        float x, y;
-        if (use_xy && A.obj_xy != nullptr) { x = A.obj_xy[((size_t)e * K + k) * 2]; y = A.obj_xy[((size_t)e * K + k) * 2 + 1]; }
-        else gg::stack_spawn_draw(A.T, A.seed, gid, epi, k, x, y);
+        const float x = xy[k][0], y = xy[k][1];
         O.p[k] = gg::mk(x, y, A.M.spawn_z); O.q[k] = gg::ldq(A.M.spawn_quat);
         O.v[k] = gg::mk(0.f, 0.f, 0.f); O.w[k] = gg::mk(0.f, 0.f, 0.f);
     }
@@ -149,7 +160,6 @@ __global__ void __launch_bounds__(32) stack_prep_kernel(const __grid_constant__ 
     float* sp = A.state + e;
     const bool do_reset = stack_reset_decision(A, e, gid);
     const bool active = do_reset ? (A.M.settle_steps > 0) : (A.mode == 0);
-    if (live) A.flags[e] = (do_reset ? 1 : 0) | (active ? 2 : 0);
 
     float q[NU], qd[NU], warm[NU], target[NU];
     gg::ObjState<K> O;
@@ -188,7 +198,23 @@ __global__ void __launch_bounds__(32) stack_prep_kernel(const __grid_constant__ 
         o[0] = O.p[k].x; o[1] = O.p[k].y; o[2] = O.p[k].z; o[3] = O.q[k].w; o[4] = O.q[k].x; o[5] = O.q[k].y; o[6] = O.q[k].z;
         o[7] = O.v[k].x; o[8] = O.v[k].y; o[9] = O.v[k].z; o[10] = O.w[k].x; o[11] = O.w[k].y; o[12] = O.w[k].z;
     }
-    gg::stack_prep<NA, NF, FH, K>(A.M, q, qd, warm, target, O, A.iterations, A.tol, active && live, In.W);
+    gg::stack_prep<NA, NF, FH, K>(A.M, q, qd, warm, target, O, A.iterations, A.tol, active && live, In);
+    if (live) {
+        const bool coop = active && In.W.amask != 0.f;
+        A.flags[e] = (do_reset ? 1 : 0) | (active ? 2 : 0) | (coop ? 4 : 0);
+        if (active) {
+            // accelerations of everything solved in registers; the cooperative solve overwrites its own dofs
+            float* ap = A.acc + e;
+#pragma unroll
+            for (int i = 0; i < NU; i++) ap[(size_t)i * st] = In.W.arob[i];
+#pragma unroll
+            for (int k = 0; k < K; k++)
+#pragma unroll
+                for (int i = 0; i < 6; i++) ap[(size_t)(NU + 6 * k + i) * st] = In.aobj[k][i];
+            if (!coop) { A.ncon[e] = (int)In.W.iso_ncon; A.iters[e] = (int)In.W.iso_iters; }
+            else A.coop_list[atomicAdd(&A.coop_ctr[0], 1)] = e;
+        }
+    }
     __syncwarp();
     // coalesced env-major copy of the block's records
     const int nlive = min(32, A.n - blockIdx.x * 32);
@@ -200,6 +226,9 @@ __global__ void __launch_bounds__(32) stack_prep_kernel(const __grid_constant__ 
 // ----------------------------------------------------------------------------------------------------------------- solve
 constexpr int kSolveWarps = 4;
 
+// PERSISTENT warps: every warp pops env ids from the list stack_prep_kernel compacted (envs whose bodies can touch each other)
+// until it is empty.  A block-per-4-envs launch left 60 % of the warp slots idle -- warps of envs with nothing to solve exit at
+// once but their block keeps its 92 KB of shared memory until its slowest warp is done (profiles/r01_v10_stack_*).
 template <int NA, int NF, bool FH, int K>
 __global__ void __launch_bounds__(32 * kSolveWarps) stack_solve_kernel(const __grid_constant__ StackArgs A) {
     constexpr int NU = NA + NF;
@@ -208,24 +237,30 @@ __global__ void __launch_bounds__(32 * kSolveWarps) stack_solve_kernel(const __g
     constexpr int WF = sizeof(InT) / sizeof(float);
     extern __shared__ __align__(16) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int e = blockIdx.x * kSolveWarps + warp;
-    if (e >= A.n) return;
-    if (!(A.flags[e] & 2)) return;                                // warp-uniform: this env runs no substep
     unsigned char* base = smem + (size_t)warp * (sizeof(InT) + sizeof(BufT));
     InT& In = *reinterpret_cast<InT*>(base);
     BufT& B = *reinterpret_cast<BufT*>(base + sizeof(InT));
-    {
-        const float* src = A.work + (size_t)e * WF;
-        float* dst = reinterpret_cast<float*>(&In);
-        for (int i = lane; i < WF; i += 32) dst[i] = __ldcg(src + i);
-    }
-    __syncwarp();
+    const int count = A.coop_ctr[0];
     WarpDev wc{lane};
-    int its = 0, nc = 0;
-    gg::stack_solve<NA, NF, FH, K>(A.M, A.T.max_contacts, In, B, A.iterations, A.tol, wc, A.acc + e, A.stride, its, nc);
-    if (lane == 0) {
-        const int ri = (int)In.W.rob_iters;
-        A.ncon[e] = nc; A.iters[e] = its > ri ? its : ri;
+    for (;;) {
+        int k = 0;
+        if (lane == 0) k = atomicAdd(&A.coop_ctr[1], 1);
+        k = __shfl_sync(kFullMask, k, 0);
+        if (k >= count) break;
+        const int e = A.coop_list[k];
+        {
+            const float* src = A.work + (size_t)e * WF;
+            float* dst = reinterpret_cast<float*>(&In);
+            for (int i = lane; i < WF; i += 32) dst[i] = __ldcg(src + i);
+        }
+        __syncwarp();
+        int its = 0, nc = 0;
+        gg::stack_solve<NA, NF, FH, K>(A.M, A.T.max_contacts, In, B, A.iterations, A.tol, wc, A.acc + e, A.stride, its, nc);
+        if (lane == 0) {
+            const int ri = (int)In.W.iso_iters;
+            A.ncon[e] = nc; A.iters[e] = its > ri ? its : ri;
+        }
+        __syncwarp();
     }
 }
 
@@ -284,9 +319,10 @@ __global__ void __launch_bounds__(128) stack_finish_kernel(const __grid_constant
     gg::stack_observe<NA, NF, K>(A.M, A.T, q, O, agent, envs, rew, succ);
     const bool trunc = A.time_limit && steps >= A.M.horizon;
     if (live) {
-        float* oa = A.obs_agent + (size_t)e * (7 + NF);
+        const int adim = A.T.agent_qpos ? NU : 7 + NF;
+        float* oa = A.obs_agent + (size_t)e * adim;
 #pragma unroll
-        for (int i = 0; i < 7 + NF; i++) oa[i] = agent[i];
+        for (int i = 0; i < 7 + NF; i++) if (i < adim) oa[i] = agent[i];
         float* oe = A.obs_env + (size_t)e * GG_STACK_ENV_STATE_DIM;
 #pragma unroll
         for (int i = 0; i < GG_STACK_ENV_STATE_DIM; i++) oe[i] = envs[i];
@@ -309,6 +345,7 @@ __global__ void __launch_bounds__(128) stack_finish_kernel(const __grid_constant
     } else {
         st_steps = st_done = st_succ = st_ret = st_len = st_nan = st_iter = st_con = 0.f;
     }
+    if (blockIdx.x == 0 && threadIdx.x == 0) { A.coop_ctr[0] = 0; A.coop_ctr[1] = 0; }      // ready for the next step's prep
     if (A.stats != nullptr && A.mode == 0) {
         float v[8] = {st_steps, st_done, st_succ, st_ret, st_len, st_nan, st_iter, st_con};
         float mine = 0.f;
@@ -355,16 +392,23 @@ struct GgStackSim {
     GgModel model;
     GgStackTask task;
     GgConfig cfg;
-    int n, device, stride, nu, nv;
+    int n, device, stride, nu, nv, kind;                     // kind: 0 = <7,2,slide> Panda, 1 = <5,1,hinge> SO-101
     float* state; int32_t* step_count; int32_t* episode;     // caller-owned
     uint8_t* done; uint8_t* flags; double* stats;            // library-owned
     float* work; float* acc; int32_t* ncon; int32_t* iters;
+    int32_t* coop_list; int32_t* coop_ctr;
     uint32_t step_index;
     size_t solve_smem;
+    int solve_blocks;                                         // persistent grid of the cooperative solver
 };
 
 typedef gg::StackIn<7, 2, 5> FrankaIn;
 typedef gg::StackBuf<9, 5> FrankaBuf;
+typedef gg::StackIn<5, 1, 5> So101In;
+typedef gg::StackBuf<6, 5> So101Buf;
+
+template <int NA, int NF, bool FH, int K>
+static void stack_launch_t(GgStackSim* sim, const StackArgs& A, cudaStream_t s);
 
 static int stack_launch(GgStackSim* sim, StackArgs& A, gg_stream_t stream) {
     if (sim->state == nullptr) return gg_internal_fail("gg_stack_bind_state has not been called%s", "");
@@ -374,18 +418,24 @@ static int stack_launch(GgStackSim* sim, StackArgs& A, gg_stream_t stream) {
     A.auto_reset = sim->cfg.auto_reset; A.time_limit = sim->cfg.time_limit; A.reset_prob = sim->cfg.reset_prob;
     A.seed = sim->cfg.seed; A.first_env = sim->cfg.first_env_id; A.step_index = sim->step_index;
     A.stats = sim->stats; A.work = sim->work; A.acc = sim->acc; A.ncon = sim->ncon; A.iters = sim->iters; A.flags = sim->flags;
+    A.coop_list = sim->coop_list; A.coop_ctr = sim->coop_ctr;
     cudaStream_t s = (cudaStream_t)stream;
     SK_CUDA(cudaSetDevice(sim->device));
-    int launches = 1;
-    if (A.mode != 2) {
-        stack_prep_kernel<7, 2, false, 5><<<(sim->n + 31) / 32, 32, 0, s>>>(A);
-        stack_solve_kernel<7, 2, false, 5><<<(sim->n + kSolveWarps - 1) / kSolveWarps, 32 * kSolveWarps, sim->solve_smem, s>>>(A);
-        launches = 3;
-    }
-    stack_finish_kernel<7, 2, false, 5><<<(sim->n + 127) / 128, 128, 0, s>>>(A);
-    gg_internal_count_launches(launches);
+    if (sim->kind == 0) stack_launch_t<7, 2, false, 5>(sim, A, s);
+    else stack_launch_t<5, 1, true, 5>(sim, A, s);
+    gg_internal_count_launches(A.mode != 2 ? 3 : 1);
     SK_CUDA(cudaGetLastError());
     return 0;
+}
+
+template <int NA, int NF, bool FH, int K>
+static void stack_launch_t(GgStackSim* sim, const StackArgs& A, cudaStream_t s) {
+    if (A.mode != 2) {
+        stack_prep_kernel<NA, NF, FH, K><<<(sim->n + 31) / 32, 32, 0, s>>>(A);
+        const int need = (sim->n + kSolveWarps - 1) / kSolveWarps;
+        stack_solve_kernel<NA, NF, FH, K><<<need < sim->solve_blocks ? need : sim->solve_blocks, 32 * kSolveWarps, sim->solve_smem, s>>>(A);
+    }
+    stack_finish_kernel<NA, NF, FH, K><<<(sim->n + 127) / 128, 128, 0, s>>>(A);
 }
 
 extern "C" {
@@ -393,8 +443,10 @@ extern "C" {
 int gg_stack_create(const GgModel* model, const GgStackTask* task, int n_envs, int device, GgStackSim** out) {
     if (!model || !task || !out) return gg_internal_fail("gg_stack_create: null argument%s", "");
     if (n_envs <= 0) return gg_internal_fail("gg_stack_create: n_envs must be positive%s", "");
-    if (!(model->n_arm == 7 && model->n_fing == 2 && !model->fing_hinge))
-        return gg_internal_fail("gg_stack_create: unsupported articulation (need 7 hinges + 2 slides)%s", "");
+    int kind = -1;
+    if (model->n_arm == 7 && model->n_fing == 2 && !model->fing_hinge) kind = 0;
+    else if (model->n_arm == 5 && model->n_fing == 1 && model->fing_hinge) kind = 1;
+    if (kind < 0) return gg_internal_fail("gg_stack_create: unsupported articulation (need 7 hinges + 2 slides or 5 hinges + 1 hinge)%s", "");
     if (task->n_obj != 5) return gg_internal_fail("gg_stack_create: the stacking scene has 5 cubes (cube_1, cube_2, 3 distractors)%s", "");
     if (task->max_contacts < 1 || task->max_contacts > GG_STACK_MAX_CONTACTS) return gg_internal_fail("gg_stack_create: max_contacts out of range%s", "");
     if (model->n_pads < 0 || model->n_pads > GG_MAX_PADS) return gg_internal_fail("gg_stack_create: too many pads%s", "");
@@ -407,24 +459,40 @@ int gg_stack_create(const GgModel* model, const GgStackTask* task, int n_envs, i
     GgStackSim* s = new (std::nothrow) GgStackSim();
     if (!s) return gg_internal_fail("gg_stack_create: out of host memory%s", "");
     memset(s, 0, sizeof(*s));
-    s->model = *model; s->task = *task; s->n = n_envs; s->device = device;
+    s->model = *model; s->task = *task; s->n = n_envs; s->device = device; s->kind = kind;
     s->nu = model->n_arm + model->n_fing; s->nv = s->nu + 6 * task->n_obj;
     s->stride = (n_envs + 31) / 32 * 32;
     s->cfg.solver_iterations = 10; s->cfg.solver_tolerance = 1e-5f;
-    s->solve_smem = kSolveWarps * (sizeof(FrankaIn) + sizeof(FrankaBuf));
-    cudaError_t e[7];
+    s->solve_smem = kSolveWarps * (kind == 0 ? sizeof(FrankaIn) + sizeof(FrankaBuf) : sizeof(So101In) + sizeof(So101Buf));
+    cudaError_t e[9];
     e[0] = cudaMalloc(&s->done, (size_t)s->stride);
     e[1] = cudaMalloc(&s->flags, (size_t)s->stride);
     e[2] = cudaMalloc(&s->stats, 8 * sizeof(double));
-    e[3] = cudaMalloc(&s->work, (size_t)s->stride * sizeof(FrankaIn));
+    e[3] = cudaMalloc(&s->work, (size_t)s->stride * (kind == 0 ? sizeof(FrankaIn) : sizeof(So101In)));
     e[4] = cudaMalloc(&s->acc, (size_t)s->stride * s->nv * sizeof(float));
     e[5] = cudaMalloc(&s->ncon, (size_t)s->stride * sizeof(int32_t));
     e[6] = cudaMalloc(&s->iters, (size_t)s->stride * sizeof(int32_t));
+    e[7] = cudaMalloc(&s->coop_list, (size_t)s->stride * sizeof(int32_t));
+    e[8] = cudaMalloc(&s->coop_ctr, 2 * sizeof(int32_t));
     bool ok = true;
-    for (int i = 0; i < 7; i++) ok = ok && e[i] == cudaSuccess;
-    if (ok) ok = cudaFuncSetAttribute(stack_solve_kernel<7, 2, false, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->solve_smem) == cudaSuccess;
+    for (int i = 0; i < 9; i++) ok = ok && e[i] == cudaSuccess;
+    {
+        // persistent solver grid: as many blocks as fit at once (shared-memory bound), one wave on every SM
+        cudaDeviceProp prop;
+        int per_sm = 0;
+        if (ok && cudaGetDeviceProperties(&prop, device) == cudaSuccess) {
+            per_sm = (int)(prop.sharedMemPerMultiprocessor / (s->solve_smem + 1024));
+            if (per_sm < 1) per_sm = 1;
+            s->solve_blocks = prop.multiProcessorCount * per_sm;
+        } else {
+            s->solve_blocks = 148 * 2;
+        }
+    }
+    if (ok && kind == 0) ok = cudaFuncSetAttribute(stack_solve_kernel<7, 2, false, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->solve_smem) == cudaSuccess;
+    if (ok && kind == 1) ok = cudaFuncSetAttribute(stack_solve_kernel<5, 1, true, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->solve_smem) == cudaSuccess;
     if (!ok) {
         cudaFree(s->done); cudaFree(s->flags); cudaFree(s->stats); cudaFree(s->work); cudaFree(s->acc); cudaFree(s->ncon); cudaFree(s->iters);
+        cudaFree(s->coop_list); cudaFree(s->coop_ctr);
         delete s;
         return gg_internal_fail("gg_stack_create: device allocation failed%s", "");
     }
@@ -433,6 +501,7 @@ int gg_stack_create(const GgModel* model, const GgStackTask* task, int n_envs, i
     cudaMemset(s->stats, 0, 8 * sizeof(double));
     cudaMemset(s->ncon, 0, (size_t)s->stride * sizeof(int32_t));
     cudaMemset(s->iters, 0, (size_t)s->stride * sizeof(int32_t));
+    cudaMemset(s->coop_ctr, 0, 2 * sizeof(int32_t));
     *out = s;
     return 0;
 }
@@ -441,6 +510,7 @@ int gg_stack_destroy(GgStackSim* s) {
     if (!s) return 0;
     cudaSetDevice(s->device);
     cudaFree(s->done); cudaFree(s->flags); cudaFree(s->stats); cudaFree(s->work); cudaFree(s->acc); cudaFree(s->ncon); cudaFree(s->iters);
+    cudaFree(s->coop_list); cudaFree(s->coop_ctr);
     delete s;
     return 0;
 }
@@ -453,6 +523,7 @@ int gg_stack_configure(GgStackSim* sim, const GgConfig* cfg) {
     return 0;
 }
 
+int gg_stack_agent_dim(const GgStackSim* sim) { return sim ? (sim->task.agent_qpos ? sim->nu : 7 + sim->model.n_fing) : -1; }
 int gg_stack_state_rows(const GgStackSim* sim) { return sim ? 3 * sim->nu + 19 * sim->task.n_obj : -1; }
 int gg_stack_state_stride(const GgStackSim* sim) { return sim ? sim->stride : -1; }
 

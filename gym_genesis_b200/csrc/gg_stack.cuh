@@ -43,15 +43,18 @@ template <int NA, int NF> struct StackWork {
     float fk[NFX][3], fo[NFX][3];
     float lR[9], lp[3];
     float fR[NFX][9], fp[NFX][3];
-    float coupled;       // 1: a pad may touch a cube or the plane -> the robot dofs join the cooperative solve
+    float amask;         // bodies of the cooperative solve: bit 0 robot (a pad may touch a cube or the plane), bit 1 + k cube k
+                         // (within reach of a pad or of another cube); everything else was solved in registers by stack_prep
     float active;        // 1: this env runs a substep
-    float rob_iters, pad0;
+    float iso_iters;     // largest Newton iteration count of the register solves
+    float iso_ncon;      // plane contacts of the cubes solved in registers
 };
 
 template <int NA, int NF, int K> struct StackIn {
     StackWork<NA, NF> W;
     float obj[K][13];     // pos3 quat4 linvel3 angvel3 (body frame)
     float warm_obj[K][6];
+    float aobj[K][6];     // acceleration of the cubes solved in registers (isolated: 6 x 6 block with <= 4 plane contacts)
 };
 
 template <int NU, int K> struct StackBuf {
@@ -66,7 +69,8 @@ template <int NU, int K> struct StackBuf {
     int pairAB[NPAIR];        // -1: pair has no contact
     float Y[NV][6];
     float H[NH];
-    float dinv[NV], vx[NV], vs[NV];
+    float dinv[NV], vx[NV];
+    int gl[NV];               // local (compacted) index -> dof
 };
 
 // ---- body / pair bookkeeping ------------------------------------------------------------------------------------------
@@ -106,10 +110,32 @@ GG_HD float sk_dot6(const float* a, const float* b) {
 // ---------------------------------------------------------------------------------------------------------------------
 // stage 1: thread per env
 // ---------------------------------------------------------------------------------------------------------------------
+// conservative body-level broad phase: does any pad-carrying body's bounding sphere reach the plane / cube k?
+template <int NA, int NF>
+GG_HD void stack_pad_reach(const GgModel& M, const RobotDyn<NA, NF>& D, int K, const V3* cp, bool& plane, unsigned& cubes) {
+    const V3 ch = ld3(M.cube_half);
+    const float rc = sqrtf(dot(ch, ch));
+    plane = false; cubes = 0u;
+#pragma unroll
+    for (int b = 0; b < 1 + NF; b++) {
+        const float r = M.pad_bound[b][3];
+        if (r < 0.f) continue;
+        const M3& Rb = b == 0 ? D.lR : D.fR[b == 0 ? 0 : b - 1];
+        const V3 pb = b == 0 ? D.lp : D.fp[b == 0 ? 0 : b - 1];
+        const V3 c = pb + mul(Rb, ld3(M.pad_bound[b]));
+        plane = plane || (c.z - r <= M.plane_z);
+        for (int k = 0; k < K; k++) {
+            const V3 d = c - cp[k];
+            if (dot(d, d) <= (r + rc) * (r + rc)) cubes |= 1u << k;
+        }
+    }
+}
+
 template <int NA, int NF, bool FH, int K>
 GG_HD void stack_prep(const GgModel& M, const float* q, const float* qd, const float* warm, const float* target, const ObjState<K>& O,
-                      int iterations, float tol, bool active, StackWork<NA, NF>& W) {
+                      int iterations, float tol, bool active, StackIn<NA, NF, K>& In) {
     constexpr int NU = NA + NF;
+    StackWork<NA, NF>& W = In.W;
     RobotDyn<NA, NF> D;
     robot_dynamics<NA, NF, FH>(M, q, qd, target, D);
     float as[NU];
@@ -122,13 +148,43 @@ GG_HD void stack_prep(const GgModel& M, const float* q, const float* qd, const f
     }
     float lsg[NU], laref[NU], lD[NU], a[NU];
     const int nlim = joint_limit_rows<NU>(M, q, qd, lsg, laref, lD);
-    bool coupled = false;
+    // ---- who can touch whom: pads vs plane / cubes, cube vs cube (bounding spheres)
+    bool pad_plane; unsigned pad_cubes;
+    stack_pad_reach<NA, NF>(M, D, K, O.p, pad_plane, pad_cubes);
+    unsigned amask = (pad_plane || pad_cubes != 0u) ? 1u : 0u;
+    amask |= pad_cubes << 1;
+    {
+        const V3 ch = ld3(M.cube_half);
+        const float r2 = 4.f * dot(ch, ch);
 #pragma unroll
-    for (int k = 0; k < K; k++) coupled = coupled || pads_may_touch<NA, NF>(M, D, O.p[k]);
+        for (int i = 0; i < K; i++)
+#pragma unroll
+            for (int j = i + 1; j < K; j++) {
+                const V3 d = O.p[i] - O.p[j];
+                if (dot(d, d) <= r2) amask |= (2u << i) | (2u << j);
+            }
+    }
+    // ---- register solves of everything that cannot touch anything but the plane
     StepInfo ir; ir.ncon = 0; ir.iters = 0; ir.grad = 0.f;
 #pragma unroll
     for (int i = 0; i < NU; i++) a[i] = as[i];
-    if (active && !coupled) robot_block_solve<NU>(D.Mt, as, nlim, lsg, laref, lD, warm, a, iterations, tol, ir);
+    if (active && !(amask & 1u)) robot_block_solve<NU>(D.Mt, as, nlim, lsg, laref, lD, warm, a, iterations, tol, ir);
+    int iso_iters = ir.iters, iso_ncon = 0;
+    for (int k = 0; k < K; k++) {
+        float Mc[6], as_c[6], qd_c[6], a_c[6], w_c[6];
+        cube_free_acc(M, O.v[k], O.w[k], Mc, as_c, qd_c);
+#pragma unroll
+        for (int i = 0; i < 6; i++) { a_c[i] = as_c[i]; w_c[i] = In.warm_obj[k][i]; }
+        if (active && !((amask >> (1 + k)) & 1u)) {
+            StepInfo ic;
+            CubeConLocal cs;
+            cube_block_solve(M, O.p[k], qmat(O.q[k]), Mc, as_c, qd_c, w_c, a_c, iterations, tol, cs, ic);
+            iso_ncon += ic.ncon;
+            iso_iters = ic.iters > iso_iters ? ic.iters : iso_iters;
+        }
+#pragma unroll
+        for (int i = 0; i < 6; i++) In.aobj[k][i] = a_c[i];
+    }
 #pragma unroll
     for (int i = 0; i < NU * (NU + 1) / 2; i++) W.Mt[i] = D.Mt[i];
 #pragma unroll
@@ -152,7 +208,7 @@ GG_HD void stack_prep(const GgModel& M, const float* q, const float* qd, const f
     W.lR[0] = D.lR.c0.x; W.lR[1] = D.lR.c0.y; W.lR[2] = D.lR.c0.z; W.lR[3] = D.lR.c1.x; W.lR[4] = D.lR.c1.y; W.lR[5] = D.lR.c1.z;
     W.lR[6] = D.lR.c2.x; W.lR[7] = D.lR.c2.y; W.lR[8] = D.lR.c2.z;
     W.lp[0] = D.lp.x; W.lp[1] = D.lp.y; W.lp[2] = D.lp.z;
-    W.coupled = coupled ? 1.f : 0.f; W.active = active ? 1.f : 0.f; W.rob_iters = (float)ir.iters; W.pad0 = 0.f;
+    W.amask = (float)amask; W.active = active ? 1.f : 0.f; W.iso_iters = (float)iso_iters; W.iso_ncon = (float)iso_ncon;
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -166,12 +222,12 @@ GG_HD M3 sk_mat9(const float* r) {
 // narrow phase, one geom pair per lane and round; contacts come out in the serial order
 // (cubes-plane, pads-plane, pad-major pad-cube, row-major cube-cube) -- oracle.cpp: collide
 template <int NA, int NF, int K, class WC>
-GG_WD int stack_collide(const GgModel& M, int max_contacts, const StackIn<NA, NF, K>& In, bool cpl, StackBuf<NA + NF, K>& B, WC& wc) {
+GG_WD int stack_collide(const GgModel& M, int max_contacts, const StackIn<NA, NF, K>& In, unsigned amask, StackBuf<NA + NF, K>& B, WC& wc) {
     const int lane = wc.lane;
     const int maxc = max_contacts < SK_CAP ? max_contacts : SK_CAP;
     const V3 ch = ld3(M.cube_half);
     const float rc = sqrtf(dot(ch, ch));
-    const int np = cpl ? M.n_pads : 0;
+    const int np = (amask & 1u) ? M.n_pads : 0;             // bodies outside the cooperative solve were handled by stack_prep
     const int nT = K + np + np * K + K * (K - 1) / 2;
     int total = 0;
     for (int t0 = 0; t0 < nT; t0 += 32) {
@@ -181,7 +237,7 @@ GG_WD int stack_collide(const GgModel& M, int max_contacts, const StackIn<NA, NF
         if (t < nT) {
             if (t < K) {
                 const float* o = In.obj[t];
-                plane_box(M.plane_z, mk(o[0], o[1], o[2]), qmat(mkq(o[3], o[4], o[5], o[6])), ch, sk_code(sk_pair_id<K>(0, 4 + t), 0, 4 + t), 8, C);
+                if ((amask >> (1 + t)) & 1u) plane_box(M.plane_z, mk(o[0], o[1], o[2]), qmat(mkq(o[3], o[4], o[5], o[6])), ch, sk_code(sk_pair_id<K>(0, 4 + t), 0, 4 + t), 8, C);
             } else if (t < K + np + np * K) {
                 t -= K;
                 const bool plane = t < np;
@@ -201,7 +257,7 @@ GG_WD int stack_collide(const GgModel& M, int max_contacts, const StackIn<NA, NF
                     const V3 cp = mk(o[0], o[1], o[2]);
                     const V3 dd = c - cp;
                     const float rr = sqrtf(dot(h, h)) + rc;
-                    if (dot(dd, dd) <= rr * rr)
+                    if (((amask >> (1 + k)) & 1u) && dot(dd, dd) <= rr * rr)
                         box_box(c, mmul(Rb, qmat(ldq(M.pad_quat[g]))), h, cp, qmat(mkq(o[3], o[4], o[5], o[6])), ch,
                                 sk_code(sk_pair_id<K>(1 + b, 4 + k), 1 + b, 4 + k), 8, C);
                 }
@@ -214,7 +270,7 @@ GG_WD int stack_collide(const GgModel& M, int max_contacts, const StackIn<NA, NF
                 const float* oj = In.obj[j];
                 const V3 ci = mk(oi[0], oi[1], oi[2]), cj = mk(oj[0], oj[1], oj[2]);
                 const V3 dd = ci - cj;
-                if (dot(dd, dd) <= 4.f * rc * rc)
+                if (((amask >> (1 + i)) & (amask >> (1 + j)) & 1u) && dot(dd, dd) <= 4.f * rc * rc)
                     box_box(ci, qmat(mkq(oi[3], oi[4], oi[5], oi[6])), ch, cj, qmat(mkq(oj[3], oj[4], oj[5], oj[6])), ch,
                             sk_code(sk_pair_id<K>(4 + i, 4 + j), 4 + i, 4 + j), 8, C);
             }
@@ -236,7 +292,8 @@ GG_WD int stack_collide(const GgModel& M, int max_contacts, const StackIn<NA, NF
     return total;
 }
 
-// the solve.  a_out[d * a_stride] receives the acceleration of every dof (robot dofs: W.arob when decoupled).
+// the solve over the ACTIVE bodies (W.amask != 0).  a_out[d * a_stride] receives the acceleration of the active dofs; the others
+// keep the result of stack_prep's register solves (W.arob, In.aobj), which the caller has already stored there.
 template <int NA, int NF, bool FH, int K, class WC>
 GG_WD void stack_solve(const GgModel& M, int max_contacts, const StackIn<NA, NF, K>& In, StackBuf<NA + NF, K>& B, int iterations, float tol,
                        WC& wc, float* a_out, int a_stride, int& iters_out, int& ncon_out) {
@@ -245,14 +302,29 @@ GG_WD void stack_solve(const GgModel& M, int max_contacts, const StackIn<NA, NF,
     const StackWork<NA, NF>& W = In.W;
     const int lane = wc.lane;
     const float mu = M.friction;
-    const bool cpl = W.coupled != 0.f;
-    const int d0 = cpl ? 0 : NU;                      // first dof of the cooperative solve
-    const int n = NV - d0;
-    const V3 O = mk(In.obj[0][0], In.obj[0][1], In.obj[0][2]);
+    const unsigned amask = (unsigned)W.amask;
+    const bool cpl = (amask & 1u) != 0u;
+    // compacted (local) index of dof d: robot dofs first, then the active cubes in order
+    auto loc = [&](int d) -> int {
+        if (d < NU) return d;
+        const int kb = (d - NU) / 6;
+        int below = 0;
+#pragma unroll
+        for (int k = 0; k < K; k++) below += (k < kb && ((amask >> (1 + k)) & 1u)) ? 1 : 0;
+        return (cpl ? NU : 0) + 6 * below + (d - NU - 6 * kb);
+    };
+    int n = cpl ? NU : 0;
+#pragma unroll
+    for (int k = 0; k < K; k++) n += ((amask >> (1 + k)) & 1u) ? 6 : 0;
+    // reference point of the spatial vectors: the first active cube (contacts of interest are near it), else cube 0
+    int kref = 0;
+#pragma unroll
+    for (int k = K - 1; k >= 0; k--) if ((amask >> (1 + k)) & 1u) kref = k;
+    const V3 O = mk(In.obj[kref][0], In.obj[kref][1], In.obj[kref][2]);
 
     // ---- contacts
-    const int ncon = stack_collide<NA, NF, K>(M, max_contacts, In, cpl, B, wc);
-    ncon_out = ncon;
+    const int ncon = stack_collide<NA, NF, K>(M, max_contacts, In, amask, B, wc);
+    ncon_out = ncon + (int)W.iso_ncon;
     for (int i = lane; i < BufT::NPAIR; i += 32) B.pairAB[i] = -1;
     wc.sync();
 #pragma unroll
@@ -275,6 +347,7 @@ GG_WD void stack_solve(const GgModel& M, int max_contacts, const StackIn<NA, NF,
     // ---- per-dof data: lane owns dofs lane, lane + 32
     float Bd[ND][6], as_d[ND], qd_d[ND], warm_d[ND], Mc_d[ND];
     bool val[ND];                                      // dof takes part in the cooperative solve
+    int ld[ND];                                        // its local index
     float lsg_d = 0.f, laref_d = 0.f, lD_d = 0.f;
     float Mrow[NU];
 #pragma unroll
@@ -285,7 +358,9 @@ GG_WD void stack_solve(const GgModel& M, int max_contacts, const StackIn<NA, NF,
 #pragma unroll
         for (int k = 0; k < 6; k++) Bd[s][k] = 0.f;
         as_d[s] = 0.f; qd_d[s] = 0.f; warm_d[s] = 0.f; Mc_d[s] = 0.f;
-        val[s] = d >= d0 && d < NV;
+        val[s] = d < NV && (d < NU ? cpl : (((amask >> (1 + (d - NU) / 6)) & 1u) != 0u));
+        ld[s] = val[s] ? loc(d) : 0;
+        if (val[s]) B.gl[ld[s]] = d;
         if (d < NA) {
             const V3 k = ld3(W.jk[d]), o = ld3(W.jo[d]);
             const V3 l = cross(o - O, k);
@@ -507,7 +582,7 @@ GG_WD void stack_solve(const GgModel& M, int max_contacts, const StackIn<NA, NF,
 #pragma unroll
         for (int s = 0; s < ND; s++) {
             const int d = lane + 32 * s;
-            if (val[s] && d >= NU) B.H[GG_TRI(d - d0, d - d0)] = Mc_d[s];
+            if (val[s] && d >= NU) B.H[GG_TRI(ld[s], ld[s])] = Mc_d[s];
         }
         wc.sync();
         // ---- ... + sum over the body pairs in contact of P^T Phi P;  g += P^T gF
@@ -540,7 +615,7 @@ GG_WD void stack_solve(const GgModel& M, int max_contacts, const StackIn<NA, NF,
                 const int i = li < nA ? sk_dof<NA, NF>(A, li) : sk_dof<NA, NF>(Bb, li - nA);
                 const int j = lj < nA ? sk_dof<NA, NF>(A, lj) : sk_dof<NA, NF>(Bb, lj - nA);
                 const float si = sk_sign<NA, NF>(A, Bb, i);
-                B.H[GG_TRI(i - d0, j - d0)] += si * sk_dot6(B.TB[i], B.Y[j]);
+                B.H[GG_TRI(loc(i), loc(j))] += si * sk_dot6(B.TB[i], B.Y[j]);
             }
             wc.sync();
         }
@@ -552,7 +627,7 @@ GG_WD void stack_solve(const GgModel& M, int max_contacts, const StackIn<NA, NF,
 #pragma unroll
             for (int s = 0; s < ND; s++) {
                 const int d = lane + 32 * s;
-                if (val[s]) { r = fmaxf(r, fabsf(g_d[s]) * gg_rcp(B.H[GG_TRI(d - d0, d - d0)])); am = fmaxf(am, fabsf(a_d[s])); }
+                if (val[s]) { r = fmaxf(r, fabsf(g_d[s]) * gg_rcp(B.H[GG_TRI(ld[s], ld[s])])); am = fmaxf(am, fabsf(a_d[s])); }
             }
             r = wc.max(r); am = wc.max(am);
             if (gg_div(r, 1.f + am) < tol) break;
@@ -589,30 +664,32 @@ GG_WD void stack_solve(const GgModel& M, int max_contacts, const StackIn<NA, NF,
         float s_d[ND];
 #pragma unroll
         for (int s = 0; s < ND; s++) s_d[s] = val[s] ? -g_d[s] : 0.f;
-        for (int dk = d0; dk < NV; dk++) {
-            const int k = dk - d0;
+        for (int k = 0; k < n; k++) {
+            const int dk = B.gl[k];
             float cand = s_d[0];
 #pragma unroll
             for (int s = 1; s < ND; s++) if ((dk >> 5) == s) cand = s_d[s];
             const float yk = wc.shfl(cand, dk & 31) * B.dinv[k];
 #pragma unroll
             for (int s = 0; s < ND; s++) {
-                const int d = lane + 32 * s;
-                if (d == dk) s_d[s] = yk;
-                else if (d > dk && d < NV) s_d[s] -= B.H[GG_TRI(d - d0, k)] * yk;
+                if (val[s]) {
+                    if (ld[s] == k) s_d[s] = yk;
+                    else if (ld[s] > k) s_d[s] -= B.H[GG_TRI(ld[s], k)] * yk;
+                }
             }
         }
-        for (int dk = NV - 1; dk >= d0; dk--) {
-            const int k = dk - d0;
+        for (int k = n - 1; k >= 0; k--) {
+            const int dk = B.gl[k];
             float cand = s_d[0];
 #pragma unroll
             for (int s = 1; s < ND; s++) if ((dk >> 5) == s) cand = s_d[s];
             const float xk = wc.shfl(cand, dk & 31) * B.dinv[k];
 #pragma unroll
             for (int s = 0; s < ND; s++) {
-                const int d = lane + 32 * s;
-                if (d == dk) s_d[s] = xk;
-                else if (d < dk && val[s]) s_d[s] -= B.H[GG_TRI(k, d - d0)] * xk;
+                if (val[s]) {
+                    if (ld[s] == k) s_d[s] = xk;
+                    else if (ld[s] < k) s_d[s] -= B.H[GG_TRI(k, ld[s])] * xk;
+                }
             }
         }
         // ---- exact line search along s
@@ -671,7 +748,7 @@ GG_WD void stack_solve(const GgModel& M, int max_contacts, const StackIn<NA, NF,
 #pragma unroll
     for (int s = 0; s < ND; s++) {
         const int d = lane + 32 * s;
-        if (d < NV) a_out[(size_t)d * a_stride] = val[s] ? a_d[s] : W.arob[d < NU ? d : 0];
+        if (val[s]) a_out[(size_t)d * a_stride] = a_d[s];
     }
     wc.sync();
 }
@@ -679,7 +756,8 @@ GG_WD void stack_solve(const GgModel& M, int max_contacts, const StackIn<NA, NF,
 // ---------------------------------------------------------------------------------------------------------------------
 // stage 3: thread per env
 // ---------------------------------------------------------------------------------------------------------------------
-// Observation / reward / success of the stacking task (franka/cube_stack.py:188-216): agent 7 + NF floats, envs 14 floats.
+// Observation / reward / success of the stacking task (franka/cube_stack.py:188-216): agent 7 + NF floats (or the n_dof joint
+// positions, T.agent_qpos), envs 14 floats.
 // The reward compares float32 device tensors: sqrt(dx^2 + dy^2) < 0.05f and z1 - z2 > 0.03f; the 2-norm is evaluated as
 // sqrtf(fmaf(dx, dx, dy * dy)) here and in the oracle so that the flags are bit-exact given matched states.
 template <int NA, int NF, int K>
@@ -687,10 +765,16 @@ GG_HD void stack_observe(const GgModel& M, const GgStackTask& T, const float* q,
                          float& reward, bool& success) {
     V3 ep; Q4 eq;
     robot_eef<NA, NF>(M, q, ep, eq);
-    agent[0] = ep.x; agent[1] = ep.y; agent[2] = ep.z;
-    agent[3] = eq.w; agent[4] = eq.x; agent[5] = eq.y; agent[6] = eq.z;
+    if (T.agent_qpos) {
+        // so101/cube_stack_batch.py:176: agent_pos = so_101.get_qpos()  (n_dof floats; the buffer holds 7 + NF >= n_dof)
 #pragma unroll
-    for (int f = 0; f < NF; f++) agent[7 + f] = q[NA + f];
+        for (int i = 0; i < NA + NF; i++) agent[i] = q[i];
+    } else {
+        agent[0] = ep.x; agent[1] = ep.y; agent[2] = ep.z;
+        agent[3] = eq.w; agent[4] = eq.x; agent[5] = eq.y; agent[6] = eq.z;
+#pragma unroll
+        for (int f = 0; f < NF; f++) agent[7 + f] = q[NA + f];
+    }
     const V3 c1 = O.p[0], c2 = O.p[K > 1 ? 1 : 0];
     envs[0] = c1.x; envs[1] = c1.y; envs[2] = c1.z;
     envs[3] = O.q[0].w; envs[4] = O.q[0].x; envs[5] = O.q[0].y; envs[6] = O.q[0].z;
@@ -709,12 +793,30 @@ GG_HD void stack_observe(const GgModel& M, const GgStackTask& T, const float* q,
     reward = success ? 1.f : 0.f;
 }
 
-// device-side spawn draw of object k: Philox counter (global env id, episode, k, 0), key = seed
-GG_HD void stack_spawn_draw(const GgStackTask& T, uint64_t seed, uint32_t gid, uint32_t episode, int k, float& x, float& y) {
+// device-side spawn draw of object k: Philox counter (global env id, episode, k, attempt), key = seed
+GG_HD void stack_spawn_draw(const GgStackTask& T, uint64_t seed, uint32_t gid, uint32_t episode, int k, uint32_t attempt, float& x, float& y) {
     uint32_t o[4];
-    philox4x32_10(gid, episode, (uint32_t)k, 0u, (uint32_t)seed, (uint32_t)(seed >> 32), o);
+    philox4x32_10(gid, episode, (uint32_t)k, attempt, (uint32_t)seed, (uint32_t)(seed >> 32), o);
     x = fmaf(u01(o[0]), T.spawn_hi[k][0] - T.spawn_lo[k][0], T.spawn_lo[k][0]);
     y = fmaf(u01(o[1]), T.spawn_hi[k][1] - T.spawn_lo[k][1], T.spawn_lo[k][1]);
+}
+// all objects of one env.  With T.min_dist > 0 objects 0 and 1 are re-drawn TOGETHER (attempt 0, 1, ... <= 15) until
+// fmaf(dx, dx, dy * dy) >= min_dist^2 -- the rejection loop of so101/cube_stack_batch.py:70-86 on the device stream.
+GG_HD void stack_spawn_all(const GgStackTask& T, uint64_t seed, uint32_t gid, uint32_t episode, int K, float (*xy)[2]) {
+    for (int k = 0; k < K; k++) stack_spawn_draw(T, seed, gid, episode, k, 0u, xy[k][0], xy[k][1]);
+    if (T.min_dist > 0.f && K > 1) {
+        for (uint32_t a = 1; a < 16; a++) {
+            const float dx = xy[1][0] - xy[0][0], dy = xy[1][1] - xy[0][1];
+#if defined(__CUDA_ARCH__)
+            const float d2 = fmaf(dx, dx, __fmul_rn(dy, dy));
+#else
+            const float d2 = fmaf(dx, dx, dy * dy);
+#endif
+            if (d2 >= T.min_dist * T.min_dist) break;
+            stack_spawn_draw(T, seed, gid, episode, 0, a, xy[0][0], xy[0][1]);
+            stack_spawn_draw(T, seed, gid, episode, 1, a, xy[1][0], xy[1][1]);
+        }
+    }
 }
 
 }  // namespace gg

@@ -12,7 +12,7 @@ import numpy as np
 import torch
 
 from .gym_api import gym
-from .tasks import FrankaCubePickBatch, FrankaCubeStackEmptyBatch, So101CubePickBatch
+from .tasks import FrankaCubePickBatch, FrankaCubeStackEmptyBatch, So101CubePickBatch, So101CubeStackBatch
 
 
 class GenesisEnv(gym.Env):
@@ -98,11 +98,12 @@ class GenesisEnv(gym.Env):
         common_kwargs.update(self._sim_kwargs)
         # the reference map (env.py:111-118) sends ("franka", "cube_stack") to the kitchen-scene variant of the same task;
         # its physics (Panda + five free cubes on a flat support) is FrankaCubeStackEmptyBatch, built here.
-        # The SO-101 stack variants remain a "next" row (8f-3).
+        # ("so101", "cube_stack") is the reference's CubeStackBatch (so101/cube_stack_batch.py).
         task_map = {
             ("franka", "cube_pick", True): FrankaCubePickBatch,
             ("so101", "cube_pick", True): So101CubePickBatch,
             ("franka", "cube_stack", True): FrankaCubeStackEmptyBatch,
+            ("so101", "cube_stack", True): So101CubeStackBatch,
         }
         key = (self.robot, task_name, self.num_envs > 0)
         if key not in task_map:

@@ -179,6 +179,8 @@ class SceneModel:
     task: str = "pick"               # "pick": reward = cube z > success_z; "stack": xy_dist < stack_xy and z_diff > stack_z
     stack_xy: float = 0.05           # franka/cube_stack.py:195
     stack_z: float = 0.03            # franka/cube_stack.py:195
+    stack_min_dist: float = 0.0      # so101/cube_stack_batch.py:70 (0.06): cube_1 / cube_2 re-drawn until this far apart
+    agent_mode: str = "eef"          # "eef": eef pose + gripper dofs; "qpos": joint positions (so101/cube_stack_batch.py:176)
     max_contacts: int = GENESIS_COMPAT_MAX_CONTACTS
 
     # ---- derived sizes -----------------------------------------------------------------------
@@ -332,7 +334,8 @@ class SceneModel:
             eef_body=self.eef_body, cube_body=self.cube_body,
             n_obj=self.n_obj, task={"pick": 0, "stack": 1}[self.task],
             obj_body=np.array(self.obj_bodies, dtype=np.int32),
-            obj_spawn=f32(self.obj_spawn).ravel(), task_opt=f32([self.stack_xy, self.stack_z]),
+            obj_spawn=f32(self.obj_spawn).ravel(),
+            task_opt=f32([self.stack_xy, self.stack_z, self.stack_min_dist, float(self.agent_mode == "qpos")]),
             parent=np.array([b.parent for b in B], dtype=np.int32),
             jtype=np.array([b.jtype for b in B], dtype=np.int32),
             dofadr=self.dofadr.copy(), qadr=self.qadr.copy(),
@@ -463,6 +466,9 @@ def get_model(robot: str, task: str = "cube_pick") -> SceneModel:
         return franka_cube_stack_model()
     if robot == "franka":
         return franka_cube_pick_model()
+    if robot == "so101" and task == "cube_stack":
+        from .model_so101 import so101_cube_stack_model
+        return so101_cube_stack_model()
     if robot == "so101":
         from .model_so101 import so101_cube_pick_model
         return so101_cube_pick_model()

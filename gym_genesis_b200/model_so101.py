@@ -55,7 +55,7 @@ _FIXED_JAW_BOX = ((0.0105, 0.008, 0.0327), (-0.0195, -0.000218214, -0.07175))   
 _MOVING_JAW_BOX = ((0.0075, 0.0285, 0.0075), (-0.003, -0.0535, 0.0189))            # on body `moving_jaw_so101_v1` (geom :114)
 
 
-def so101_bodies(scale=1.0, base_pos=(0.0, 0.0, 0.0), base_yaw_deg=0.0, friction_gains=True):
+def so101_bodies(scale=1.0, base_pos=(0.0, 0.0, 0.0), base_yaw_deg=0.0, friction_gains=True, arm_gains=(_ARM_KP, _ARM_KV)):
     s = float(scale)
     yaw = np.deg2rad(base_yaw_deg)
     base_quat = (np.cos(yaw / 2), 0.0, 0.0, np.sin(yaw / 2))
@@ -67,7 +67,7 @@ def so101_bodies(scale=1.0, base_pos=(0.0, 0.0, 0.0), base_yaw_deg=0.0, friction
             continue
         arm = k <= 5
         bodies.append(Body(name, parent, tuple(p * s for p in pos), quat, jtype=HINGE, axis=(0, 0, 1), range=rng, limited=True,
-                           armature=_ARMATURE, damping=_DAMPING, kp=_ARM_KP if arm else _JAW_KP, kv=_ARM_KV if arm else _JAW_KV,
+                           armature=_ARMATURE, damping=_DAMPING, kp=arm_gains[0] if arm else _JAW_KP, kv=arm_gains[1] if arm else _JAW_KV,
                            frc=(-_FRC, _FRC), **kw))
     return bodies
 
@@ -93,3 +93,34 @@ def so101_cube_pick_model(placement="stack", success_height=None) -> SceneModel:
                     success_z=0.1 if success_height is None else float(success_height),    # so101/cube_pick.py:112 (literal; see D11)
                     settle_steps=0)                                                        # so101/cube_pick.py:81 (commented out)
     return sm
+
+
+# so101/cube_stack_batch.py:72-75 (cube_1, cube_2) and :93-94 (distractors): x_lo, x_hi, y_lo, y_hi
+_SO101_STACK_SPAWN = [(-0.3, -0.1, -0.1, 0.1), (-0.3, -0.1, -0.1, 0.1), (-0.35, 0.0, -0.2, 0.2), (-0.35, 0.0, -0.2, 0.2), (-0.35, 0.0, -0.2, 0.2)]
+# build-time positions, overwritten by every reset (tasks/utils.py:756-790: cube_1, cube_2 literal; distractors unseeded draws)
+_SO101_STACK_POS = [(0.1, 0.0), (-0.1, 0.05), (-0.2, -0.15), (0.15, 0.2), (-0.3, 0.15)]
+
+
+def so101_cube_stack_model() -> SceneModel:
+    """SO-101 `CubeStackBatch` (`so101/cube_stack_batch.py:25-226`, scene `tasks/utils.py:593-794`): robot at (-0.5, 0, 0.7),
+    yaw 90 deg, scale 1.3 (`utils.py:733-744`), five free 4 cm cubes on the island top (modelled as a plane at ISLAND_TOP_Z),
+    MJCF actuator gains (kp 17.8, kv 0: the task's set_dofs_kp / set_friction calls are commented out, `:46-49`), default
+    friction, one settle step in reset (`:111`), agent_pos = joint positions (`:176`)."""
+    scale = 1.3
+    bodies = so101_bodies(scale, (-0.5, 0.0, 0.7), 90.0, arm_gains=(_JAW_KP, _JAW_KV))
+    geoms = [BoxGeom(5, tuple(h * scale for h in _FIXED_JAW_BOX[0]), tuple(p * scale for p in _FIXED_JAW_BOX[1]), group=0),
+             BoxGeom(6, tuple(h * scale for h in _MOVING_JAW_BOX[0]), tuple(p * scale for p in _MOVING_JAW_BOX[1]), group=0)]
+    z = ISLAND_TOP_Z + 0.02 + 0.001                                               # utils.py:752, cube_stack_batch.py:67
+    obj = []
+    for k in range(5):
+        b = _cube_body()
+        b.name = ("cube_1", "cube_2")[k] if k < 2 else f"distractor_{k - 2}"
+        b.pos = (*_SO101_STACK_POS[k], z)
+        obj.append(len(bodies))
+        bodies.append(b)
+        geoms.append(BoxGeom(obj[-1], (CUBE_SIZE / 2,) * 3, group=1))
+    from .model import GENESIS_COMPAT_MAX_CONTACTS_STACK
+    return SceneModel("so101_stack", bodies, geoms, eef_body=5, cube_body=obj[0], home_q=SO101_STACK_HOME.copy(), n_arm=5, n_fing=1,
+                      plane_z=ISLAND_TOP_Z, spawn_z=z, spawn_quat=(0.0, 0.0, 0.0, 1.0),   # cube_stack_batch.py:66
+                      settle_steps=1, obj_bodies=obj, obj_spawn=_SO101_STACK_SPAWN, task="stack", stack_min_dist=0.06,
+                      agent_mode="qpos", max_contacts=GENESIS_COMPAT_MAX_CONTACTS_STACK)

@@ -276,11 +276,11 @@ class BatchedStackSim(BatchedSim):
         self.nu = scene_model.nu
         self.n_obj = scene_model.n_obj
         self.nq, self.nv = self.nu + 7 * self.n_obj, self.nu + 6 * self.n_obj
-        self.agent_dim = 7 + scene_model.n_fing
         self.env_dim = cabi.GG_STACK_ENV_STATE_DIM
         h = C.c_void_p()
         self._check(self.lib.gg_stack_create(C.byref(self.gg_model), C.byref(self.gg_task), self.n_envs, self.device.index, C.byref(h)))
         self._h = h
+        self.agent_dim = self.lib.gg_stack_agent_dim(h)       # 7 + n_fing (eef pose + gripper) or n_dof (joint positions)
         rows, stride = self.lib.gg_stack_state_rows(h), self.lib.gg_stack_state_stride(h)
         dev = self.device
         self.state = torch.zeros((rows, stride), dtype=torch.float32, device=dev)

@@ -42,6 +42,18 @@ class _StackCube:
         return self._rows(7, 10)
 
 
+class _EefLink(_Link):
+    """End-effector handle of a task whose agent_pos is NOT the eef pose (SO-101 stack): pose from environment_state's
+    eef - cube_1 difference and the cube_1 position."""
+
+    def get_pos(self):
+        es = self._task.sim.obs_env
+        return es[:, 0:3] + es[:, 7:10]
+
+    def get_quat(self):
+        raise NotImplementedError("eef orientation is not part of this task's observations")
+
+
 class FrankaCubeStackEmptyBatch(CubePickBatch):
     robot_name = "franka"
 
@@ -65,14 +77,14 @@ class FrankaCubeStackEmptyBatch(CubePickBatch):
                                    reset_prob=reset_prob, seed=seed, first_env_id=first_env_id)
         self.agent_dim = self.sim.agent_dim
         self.observation_space = spaces.Dict({
-            "agent_pos": spaces.Box(low=-np.inf, high=np.inf, shape=(AGENT_DIM,), dtype=np.float32),
+            "agent_pos": spaces.Box(low=-np.inf, high=np.inf, shape=(self.agent_dim,), dtype=np.float32),
             "environment_state": spaces.Box(low=-np.inf, high=np.inf, shape=(ENV_DIM,), dtype=np.float32),
         })
-        self.action_space = spaces.Box(low=-1.0, high=1.0, shape=(AGENT_DIM,), dtype=np.float32)
+        self.action_space = spaces.Box(low=-1.0, high=1.0, shape=(self.model.nu,), dtype=np.float32)
         self._home = torch.tensor(self.model.home_q, dtype=torch.float32, device=self.sim.device).repeat(num_envs, 1)
         self._targets = self._home.clone()
         self.scene = _Scene(self)
-        self.eef = _Link(self)
+        self.eef = _Link(self) if self.model.agent_mode == "eef" else _EefLink(self)
         self.robot = _Robot(self)
         self.cube_1 = _StackCube(self, 0)
         self.cube_2 = _StackCube(self, 1)
@@ -97,3 +109,33 @@ class FrankaCubeStackEmptyBatch(CubePickBatch):
 
     def step_host(self, action, reset_mask=None):
         raise NotImplementedError("host_io is implemented for the CubePick path only")
+
+
+class So101CubeStackBatch(FrankaCubeStackEmptyBatch):
+    """SO-101 `CubeStackBatch` (`gym_genesis/tasks/so101/cube_stack_batch.py:25-226`): agent_pos = the six joint
+    positions (`:176`), environment_state (14) as in the Franka task (the reference declares ENV_DIM = 10 at `:17` but returns
+    14 values, `:181`; the space here states what is returned), reward `:150-160`."""
+    robot_name = "so101"
+
+    @property
+    def so_101(self):
+        return self.robot
+
+    def _spawn_xy(self):
+        """Host RandomState stream of `cube_stack_batch.py:70-97`: per env, scalar draws x1, y1, x2, y2 repeated until the two
+        cubes are >= 0.06 apart; then, per distractor, all x draws followed by all y draws."""
+        B = self.num_envs
+        out = np.zeros((B, self.model.n_obj, 2), dtype=np.float32)
+        (x1lo, x1hi, y1lo, y1hi), (x2lo, x2hi, y2lo, y2hi) = self.model.obj_spawn[0], self.model.obj_spawn[1]
+        for b in range(B):
+            while True:
+                x1 = self._random.uniform(x1lo, x1hi); y1 = self._random.uniform(y1lo, y1hi)
+                x2 = self._random.uniform(x2lo, x2hi); y2 = self._random.uniform(y2lo, y2hi)
+                if ((x2 - x1) ** 2 + (y2 - y1) ** 2) ** 0.5 >= self.model.stack_min_dist:
+                    out[b, 0], out[b, 1] = (x1, y1), (x2, y2)
+                    break
+        for k in range(2, self.model.n_obj):
+            xlo, xhi, ylo, yhi = self.model.obj_spawn[k]
+            out[:, k, 0] = self._random.uniform(xlo, xhi, size=(B,))
+            out[:, k, 1] = self._random.uniform(ylo, yhi, size=(B,))
+        return out

@@ -185,7 +185,8 @@ int gg_export_successful(GgSim* sim, const float* traj, const int32_t* ever, int
                          int32_t* out_count, gg_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
- * Multi-object scenes: `FrankaCubeStackEmptyBatch` (gym_genesis/tasks/franka/cube_stack.py:27-240).  The robot, the box
+ * Multi-object scenes: `FrankaCubeStackEmptyBatch` (gym_genesis/tasks/franka/cube_stack.py:27-240) and the SO-101
+ * `CubeStackBatch` (gym_genesis/tasks/so101/cube_stack_batch.py:25-226, scene tasks/utils.py:593-794).  The robot, the box
  * geometry / inertia shared by all cubes and the solver constants come from GgModel; GgStackTask adds the object count,
  * the per-object spawn ranges and the stacking thresholds.  Object 0 = cube_1 (picked), object 1 = cube_2 (target), the
  * rest are distractors.  Cube-cube box-box contacts are generated (RigidOptions(box_box_detection=True), :46).
@@ -205,6 +206,9 @@ typedef struct GgStackTask {
     int32_t n_obj, max_contacts;
     float spawn_lo[GG_MAX_OBJ][2], spawn_hi[GG_MAX_OBJ][2];   /* per-object uniform xy ranges   cube_stack.py:125-142 */
     float stack_xy, stack_z;                                  /* reward thresholds              cube_stack.py:195     */
+    float min_dist;      /* > 0: objects 0 and 1 are re-drawn until at least this far apart (so101/cube_stack_batch.py:70-86) */
+    int32_t agent_qpos;  /* 0: agent_pos = eef pos3 + quat4 + gripper dofs (franka/cube_stack.py:211);
+                            1: agent_pos = joint positions, n_dof floats (so101/cube_stack_batch.py:176)                    */
 } GgStackTask;
 
 typedef struct GgStackSim GgStackSim;
@@ -215,7 +219,8 @@ int gg_stack_configure(GgStackSim* sim, const GgConfig* cfg);
 int gg_stack_state_rows(const GgStackSim* sim);
 int gg_stack_state_stride(const GgStackSim* sim);
 int gg_stack_bind_state(GgStackSim* sim, float* state, int32_t* step_count, int32_t* episode);
-/* action (n_envs, n_dof); obs_agent (n_envs, 7 + n_fing); obs_env (n_envs, 14); reward / flags (n_envs); reset_mask nullable. */
+/* action (n_envs, n_dof); obs_agent (n_envs, gg_stack_agent_dim()); obs_env (n_envs, 14); reward / flags (n_envs); reset_mask nullable. */
+int gg_stack_agent_dim(const GgStackSim* sim);
 int gg_stack_step(GgStackSim* sim, const float* action, float* obs_agent, float* obs_env, float* reward, uint8_t* terminated,
                   uint8_t* truncated, const uint8_t* reset_mask, gg_stream_t stream);
 /* obj_xy (nullable): (n_envs, n_obj, 2) explicit spawn positions (the reference's host RandomState stream, drawn per object:

@@ -78,7 +78,7 @@ class Oracle:
         self.h = C.c_void_p(lib().orc_create(C.byref(cm)))
         for k in ("nb", "nv", "nq", "nu"):
             setattr(self, k, int(self.flat[k]))
-        self.agent_dim = 7 + scene_model.n_fing
+        self.agent_dim = scene_model.nu if getattr(scene_model, "agent_mode", "eef") == "qpos" else 7 + scene_model.n_fing
         self.n_obj = int(self.flat["n_obj"])
         self.env_dim = 14 if scene_model.task == "stack" else 11
 

@@ -105,7 +105,8 @@ template <class T> struct Model {
     std::vector<T> pos, quat, axis, mass, com, inertia, body_w, dof_w, armature, damping, kp, kv, frc_lo, frc_hi,
         lim_lo, lim_hi, geom_half, geom_pos, geom_quat, opt, spawn_quat, home_q;
     std::vector<T> obj_spawn;             // per object: x_lo, x_hi, y_lo, y_hi
-    std::vector<T> task_opt;              // stack: xy threshold, z threshold (franka/cube_stack.py:195)
+    std::vector<T> task_opt;              // stack: xy threshold, z threshold (franka/cube_stack.py:195), min spawn distance
+                                          // (so101/cube_stack_batch.py:70), agent_pos = joint positions flag (:176)
     std::vector<int> dof_body;            // body owning each dof
     std::vector<char> affects;            // affects[body*nv + dof]
 };
@@ -121,7 +122,7 @@ template <class T> static void build(Model<T>& m, const OrcModel* c) {
     m.nb = c->nb; m.nv = c->nv; m.nq = c->nq; m.nu = c->nu; m.ngeom = c->ngeom;
     m.eef_body = c->eef_body; m.cube_body = c->cube_body; m.max_contacts = c->max_contacts;
     m.n_obj = c->n_obj; m.task = c->task;
-    m.obj_body = cvti(c->obj_body, m.n_obj); m.obj_spawn = cvt<T>(c->obj_spawn, m.n_obj * 4); m.task_opt = cvt<T>(c->task_opt, 2);
+    m.obj_body = cvti(c->obj_body, m.n_obj); m.obj_spawn = cvt<T>(c->obj_spawn, m.n_obj * 4); m.task_opt = cvt<T>(c->task_opt, 4);
     m.parent = cvti(c->parent, m.nb); m.jtype = cvti(c->jtype, m.nb);
     m.dofadr = cvti(c->dofadr, m.nb); m.qadr = cvti(c->qadr, m.nb);
     m.limited = cvti(c->limited, m.nv); m.ctrl = cvti(c->ctrl, m.nv);
@@ -743,9 +744,13 @@ template <class T> static void observe(const Model<T>& m, const T* q, T* agent, 
     const int e = m.eef_body, cb = m.cube_body, nf = agent_dim - 7;
     const T* ep = &k.xpos[e * 3]; const T* eq = &k.xquat[e * 4];
     const T* cp = &k.xpos[cb * 3]; const T* cq = &k.xquat[cb * 4];
-    for (int c = 0; c < 3; c++) agent[c] = ep[c];
-    for (int c = 0; c < 4; c++) agent[3 + c] = eq[c];
-    for (int c = 0; c < nf; c++) agent[7 + c] = q[m.nu - nf + c];
+    if (m.task == 1 && m.task_opt[3] != 0) {
+        for (int c = 0; c < m.nu; c++) agent[c] = q[c];          // so101/cube_stack_batch.py:176: agent_pos = get_qpos()
+    } else {
+        for (int c = 0; c < 3; c++) agent[c] = ep[c];
+        for (int c = 0; c < 4; c++) agent[3 + c] = eq[c];
+        for (int c = 0; c < nf; c++) agent[7 + c] = q[m.nu - nf + c];
+    }
     for (int c = 0; c < 3; c++) envs[c] = cp[c];
     for (int c = 0; c < 4; c++) envs[3 + c] = cq[c];
     T dd[3] = {ep[0] - cp[0], ep[1] - cp[1], ep[2] - cp[2]};
@@ -872,15 +877,35 @@ void orc_philox(const uint32_t* ctr, const uint32_t* key, uint32_t* out) { philo
 // device-reset spawn draw: counter (env_id, episode, 0, 0), key = seed; u = (x>>8)*2^-24; x = fma(u, hi-lo, lo)
 int orc_env_dim(const void* hv) { return ((const Handle*)hv)->f.task == 1 ? 14 : 11; }
 
-// object k of a multi-object scene: counter (env_id, episode, k, 0); object 0 of a one-object scene = orc_spawn_xy
-void orc_spawn_obj(const void* hv, uint64_t seed, uint32_t env_id, uint32_t episode, uint32_t k, float* xy) {
-    const Model<float>& m = ((const Handle*)hv)->f;
-    uint32_t ctr[4] = {env_id, episode, k, 0}, key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)}, o[4];
+// object k of a multi-object scene: counter (env_id, episode, k, attempt); object 0 of a one-object scene = orc_spawn_xy
+static void spawn_obj_draw(const Model<float>& m, uint64_t seed, uint32_t env_id, uint32_t episode, uint32_t k, uint32_t attempt, float* xy) {
+    uint32_t ctr[4] = {env_id, episode, k, attempt}, key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)}, o[4];
     philox4x32_10(ctr, key, o);
     float u0 = (float)(o[0] >> 8) * 5.9604644775390625e-8f, u1 = (float)(o[1] >> 8) * 5.9604644775390625e-8f;
     const float* r = &m.obj_spawn[k * 4];
     xy[0] = std::fmaf(u0, r[1] - r[0], r[0]);
     xy[1] = std::fmaf(u1, r[3] - r[2], r[2]);
+}
+// all objects of one env (xy: n_obj x 2).  With min_dist > 0 (so101/cube_stack_batch.py:70-86) objects 0 and 1 are re-drawn
+// together, attempt 1, 2, ... <= 15, until fmaf(dx, dx, dy * dy) >= min_dist^2 in float32.
+void orc_spawn_all(const void* hv, uint64_t seed, uint32_t env_id, uint32_t episode, float* xy) {
+    const Model<float>& m = ((const Handle*)hv)->f;
+    for (int k = 0; k < m.n_obj; k++) spawn_obj_draw(m, seed, env_id, episode, k, 0, xy + 2 * k);
+    const float md = m.task_opt[2];
+    if (md > 0 && m.n_obj > 1)
+        for (uint32_t a = 1; a < 16; a++) {
+            const float dx = xy[2] - xy[0], dy = xy[3] - xy[1];
+            if (std::fmaf(dx, dx, dy * dy) >= md * md) break;
+            spawn_obj_draw(m, seed, env_id, episode, 0, a, xy);
+            spawn_obj_draw(m, seed, env_id, episode, 1, a, xy + 2);
+        }
+}
+void orc_spawn_obj(const void* hv, uint64_t seed, uint32_t env_id, uint32_t episode, uint32_t k, float* xy) {
+    const Model<float>& m = ((const Handle*)hv)->f;
+    float all[2 * 16];
+    orc_spawn_all(hv, seed, env_id, episode, all);
+    xy[0] = all[2 * k]; xy[1] = all[2 * k + 1];
+    (void)m;
 }
 
 void orc_spawn_xy(const void* hv, uint64_t seed, uint32_t env_id, uint32_t episode, float* xy) {

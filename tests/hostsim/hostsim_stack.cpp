@@ -50,16 +50,22 @@ void run(const GgModel* M, const GgStackTask* T, int n, float* q, float* qd, flo
             for (int i = 0; i < 7; i++) d[i] = o[i];
             for (int i = 0; i < 6; i++) { d[7 + i] = v[i]; In->warm_obj[k][i] = pa[NU + 6 * k + i]; }
         }
-        gg::stack_prep<NA, NF, FH, K>(*M, pq, pv, pa, target + (size_t)e * NU, O, iterations, tol, true, In->W);
+        gg::stack_prep<NA, NF, FH, K>(*M, pq, pv, pa, target + (size_t)e * NU, O, iterations, tol, true, *In);
         float a[NV];
+        for (int i = 0; i < NU; i++) a[i] = In->W.arob[i];
+        for (int k = 0; k < K; k++)
+            for (int i = 0; i < 6; i++) a[NU + 6 * k + i] = In->aobj[k][i];
         int its[32], nc[32];
-        std::vector<std::thread> th;
-        for (int l = 0; l < 32; l++)
-            th.emplace_back([&, l]() {
-                WarpHost wc{l, &hw};
-                gg::stack_solve<NA, NF, FH, K>(*M, T->max_contacts, *In, *B, iterations, tol, wc, a, 1, its[l], nc[l]);
-            });
-        for (auto& t : th) t.join();
+        its[0] = 0; nc[0] = (int)In->W.iso_ncon;
+        if (In->W.amask != 0.f) {
+            std::vector<std::thread> th;
+            for (int l = 0; l < 32; l++)
+                th.emplace_back([&, l]() {
+                    WarpHost wc{l, &hw};
+                    gg::stack_solve<NA, NF, FH, K>(*M, T->max_contacts, *In, *B, iterations, tol, wc, a, 1, its[l], nc[l]);
+                });
+            for (auto& t : th) t.join();
+        }
         gg::integrate_robot<NU>(*M, pq, pv, pa, a);
         for (int k = 0; k < K; k++) {
             gg::integrate_cube(*M, O.p[k], O.q[k], O.v[k], O.w[k], pa + NU + 6 * k, a + NU + 6 * k);
@@ -68,8 +74,8 @@ void run(const GgModel* M, const GgStackTask* T, int n, float* q, float* qd, flo
             v[0] = O.v[k].x; v[1] = O.v[k].y; v[2] = O.v[k].z; v[3] = O.w[k].x; v[4] = O.w[k].y; v[5] = O.w[k].z;
         }
         if (info) {
-            const int ri = (int)In->W.rob_iters;
-            info[e * 4] = nc[0]; info[e * 4 + 1] = its[0] > ri ? its[0] : ri; info[e * 4 + 2] = In->W.coupled != 0.f; info[e * 4 + 3] = 0;
+            const int ri = (int)In->W.iso_iters;
+            info[e * 4] = nc[0]; info[e * 4 + 1] = its[0] > ri ? its[0] : ri; info[e * 4 + 2] = ((int)In->W.amask) & 1; info[e * 4 + 3] = (int)In->W.amask;
         }
     }
     delete In;
@@ -99,15 +105,17 @@ int hs_sizeof_stack_task(void) { return (int)sizeof(GgStackTask); }
 int hs_stack_step(const GgModel* M, const GgStackTask* T, int n, float* q, float* qd, float* qacc, const float* target, int iterations,
                   float tol, int32_t* info) {
     if (M->n_arm == 7 && M->n_fing == 2 && T->n_obj == 5) run<7, 2, false, 5>(M, T, n, q, qd, qacc, target, iterations, tol, info);
+    else if (M->n_arm == 5 && M->n_fing == 1 && T->n_obj == 5) run<5, 1, true, 5>(M, T, n, q, qd, qacc, target, iterations, tol, info);
     else return -1;
     return 0;
 }
 int hs_stack_observe(const GgModel* M, const GgStackTask* T, int n, const float* q, float* agent, float* envs, float* reward, uint8_t* term) {
     if (M->n_arm == 7 && M->n_fing == 2 && T->n_obj == 5) obs<7, 2, 5>(M, T, n, q, agent, envs, reward, term);
+    else if (M->n_arm == 5 && M->n_fing == 1 && T->n_obj == 5) obs<5, 1, 5>(M, T, n, q, agent, envs, reward, term);
     else return -1;
     return 0;
 }
-void hs_stack_spawn(const GgStackTask* T, uint64_t seed, uint32_t gid, uint32_t episode, int k, float* xy) {
-    gg::stack_spawn_draw(*T, seed, gid, episode, k, xy[0], xy[1]);
+void hs_stack_spawn(const GgStackTask* T, uint64_t seed, uint32_t gid, uint32_t episode, float* xy) {
+    gg::stack_spawn_all(*T, seed, gid, episode, T->n_obj, reinterpret_cast<float(*)[2]>(xy));
 }
 }

@@ -135,19 +135,24 @@ def test_masked_reset_counters_and_philox_spawn_bit_exact(Sim, sm, orc):
     q1 = sim.get_state()[0].cpu().numpy()
     sc, ep = sim.step_count.cpu().numpy(), sim.episode.cpu().numpy()
     assert (sc[mask] == 0).all() and (sc[~mask] == 4).all() and (ep[mask] == 2).all() and (ep[~mask] == 1).all()
-    # spawn xy of reset envs: bit-exact Philox draws keyed by (seed, GLOBAL env id, episode, object); z / quat settle by < 1e-3
-    for e in np.nonzero(mask)[0][:12]:
+    # spawn xy of reset envs: Philox draws keyed by (seed, GLOBAL env id, episode, object), bit-exact for every cube that
+    # lands clear of the others (an overlapping spawn is pushed apart by the settle step)
+    checked = 0
+    for e in np.nonzero(mask)[0]:
+        ref = np.array([orc.spawn_obj(seed, 1000 + int(e), 1, k) for k in range(5)])
         for k in range(5):
-            ref = orc.spawn_obj(seed, 1000 + int(e), 1, k)
-            got = q1[e, 9 + 7 * k: 9 + 7 * k + 2]
-            assert np.abs(got - ref).max() < 2e-4             # one settle step may nudge overlapping cubes
+            clear = all(np.abs(ref[k] - ref[j]).max() > 0.08 for j in range(5) if j != k)
+            if clear:
+                assert (q1[e, 9 + 7 * k: 9 + 7 * k + 2] == ref[k]).all()
+                checked += 1
+    assert checked > 50
     e = int(np.nonzero(mask)[0][0])
     first = np.array([orc.spawn_obj(seed, 1000 + e, 0, k) for k in range(5)])
-    far = np.min([np.abs(first[i] - first[j]).max() for i in range(5) for j in range(i)]) > 0.045
-    if far:
-        assert np.abs(q0[e, 9:44].reshape(5, 7)[:, :2] - first).max() < 1e-6
+    for k in range(5):
+        if all(np.abs(first[k] - first[j]).max() > 0.08 for j in range(5) if j != k):
+            assert (q0[e, 9 + 7 * k: 9 + 7 * k + 2] == first[k]).all()
     # envs outside the mask were stepped, not touched by the reset
-    assert np.abs(q1[~mask, 9:] - before[~mask, 9:]).max() < 1e-3
+    assert np.abs(q1[~mask, 9:] - before[~mask, 9:]).max() < 2e-2    # one 0.01 s step (overlapping spawns still separating)
 
 
 def test_rollout_100_steps(Sim, sm, orc):
@@ -266,3 +271,69 @@ def test_expert_closed_loop_stacks_on_device(Sim, sm):
     rate = rew[sep].mean().item()
     assert rate > 0.5, (rate, int(sep.sum()))
     assert torch.isfinite(task.sim.get_state()[0]).all()
+
+
+# ---- SO-101 CubeStackBatch ----------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def so():
+    from gym_genesis_b200.model_so101 import so101_cube_stack_model
+    from oracle.binding import Oracle
+    m = so101_cube_stack_model()
+    return m, Oracle(m, np.float64)
+
+
+def test_so101_stack_single_substep(Sim, so):
+    from test_stack_cpu import _so101_states
+    m, orc = so
+    n = 128
+    rng = np.random.default_rng(41)
+    Q, QD, T = _so101_states(m, rng, n)
+    QA = np.zeros_like(QD)
+    sim = Sim(m, n)
+    assert sim.agent_dim == 6 and sim.state.shape[0] == 3 * 6 + 19 * 5
+    q, qd, qa = _one_substep(sim, Q, QD, QA, T)
+    qo, qdo, qao = Q.copy(), QD.copy(), QA.copy()
+    info, _ = orc.step(qo, qdo, qao, T, iterations=100, tol=1e-12)
+    nc, it = sim.step_info()
+    assert (nc.cpu().numpy() == info[:, 0]).all()
+    eq, ev = stack_substep_errors(Q, QD, qo, qdo, q, qd, _asm(orc, Q, QD, T))
+    assert eq.max() < TOL_Q_ABS and ev.max() < 1.0, (eq.max(), ev.max(), int(np.argmax(ev)))
+    a, e, r, t = orc.obs(q)
+    assert (sim.obs_agent.cpu().numpy() == f32(q[:, :6])).all()                      # agent_pos = joint positions, bit-exact
+    assert np.abs(_np(sim.obs_env) - e).max() < 2e-6
+    assert (sim.terminated.cpu().numpy().astype(bool) == t).all() and t[2]
+
+
+def test_so101_stack_gym_surface_and_reset_stream(so):
+    import gym_genesis  # noqa: F401
+    from gym_genesis_b200.gym_api import gym
+    m, orc = so
+    n = 40
+    env = gym.make("gym_genesis/CubeStack-v0", robot="so101", num_envs=n)
+    u = env.unwrapped
+    obs, _ = env.reset(seed=11)
+    assert obs["agent_pos"].shape == (n, 6) and obs["environment_state"].shape == (n, 14)
+    # the reference's host stream (cube_stack_batch.py:70-97): per-env rejection loop, then vector draws per distractor
+    rs = np.random.RandomState(11)
+    xy = np.zeros((n, 5, 2))
+    for b in range(n):
+        while True:
+            x1, y1, x2, y2 = rs.uniform(-0.3, -0.1), rs.uniform(-0.1, 0.1), rs.uniform(-0.3, -0.1), rs.uniform(-0.1, 0.1)
+            if ((x2 - x1) ** 2 + (y2 - y1) ** 2) ** 0.5 >= 0.06:
+                xy[b, 0], xy[b, 1] = (x1, y1), (x2, y2)
+                break
+    for k in range(2, 5):
+        xy[:, k, 0] = rs.uniform(-0.35, 0.0, size=(n,)); xy[:, k, 1] = rs.uniform(-0.2, 0.2, size=(n,))
+    # oracle: reset + one settle step holding the home pose
+    qo, qdo, qao = orc.new_state(n)
+    orc.reset(qo, qdo, qao, f32(xy).astype(np.float64))
+    orc.step(qo, qdo, qao, np.tile(m.home_q, (n, 1)), iterations=100, tol=1e-12)
+    q = _np(u._env.sim.get_state()[0])
+    assert np.abs(q - qo).max() < 5e-5, np.abs(q - qo).max()
+    a, e, r, t = orc.obs(q)
+    assert np.abs(_np(obs["environment_state"]) - e).max() < 2e-6
+    act = torch.as_tensor(f32(np.tile(m.home_q, (n, 1))), device="cuda")
+    obs, reward, terminated, truncated, info = u.step(act)
+    assert reward.shape == (n,) and (terminated == (reward == 1)).all() and not truncated.any()
+    assert torch.isfinite(obs["environment_state"]).all()
+    env.close()

@@ -175,10 +175,84 @@ def test_observation_and_flags_bit_exact(hostsim, gg, sm, orc):
 
 def test_spawn_draws_bit_exact(hostsim, gg, orc):
     for seed, gid, epi in [(0, 0, 0), (7, 123456, 3), (2 ** 40 + 5, 16383, 17)]:
+        xy = np.zeros((5, 2), np.float32)
+        hostsim.hs_stack_spawn(C.byref(gg[1]), C.c_uint64(seed), C.c_uint32(gid), C.c_uint32(epi), _p(xy))
         for k in range(5):
-            xy = np.zeros(2, np.float32)
-            hostsim.hs_stack_spawn(C.byref(gg[1]), C.c_uint64(seed), C.c_uint32(gid), C.c_uint32(epi), k, _p(xy))
             ref = orc.spawn_obj(seed, gid, epi, k)
-            assert xy.tobytes() == ref.tobytes()
+            assert xy[k].tobytes() == ref.tobytes()
             lo, hi = gg[1].spawn_lo[k], gg[1].spawn_hi[k]
-            assert lo[0] <= xy[0] <= hi[0] and lo[1] <= xy[1] <= hi[1]
+            assert lo[0] <= xy[k, 0] <= hi[0] and lo[1] <= xy[k, 1] <= hi[1]
+
+
+# ---- SO-101 CubeStackBatch ----------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def so():
+    from gym_genesis_b200.model_so101 import so101_cube_stack_model
+    from oracle.binding import Oracle
+    m = so101_cube_stack_model()
+    return m, Oracle(m, np.float64), cabi.compile_gg(m), cabi.compile_stack_task(m)
+
+
+def test_so101_stack_model_reference_constants(so):
+    m = so[0]
+    assert (m.nu, m.n_obj, m.nv, m.nq) == (6, 5, 36, 41)
+    assert m.obj_spawn[0] == (-0.3, -0.1, -0.1, 0.1) and m.obj_spawn[2] == (-0.35, 0.0, -0.2, 0.2)    # cube_stack_batch.py:72-75, 93-94
+    assert m.stack_min_dist == 0.06 and m.agent_mode == "qpos" and m.settle_steps == 1                # :70, :176, :111
+    assert abs(m.spawn_z - (0.7000312834978104 + 0.021)) < 1e-12 and tuple(m.spawn_quat) == (0, 0, 0, 1)   # :66-67
+    assert np.allclose(m.home_q, np.deg2rad([0, -177, 165, 72, -83, 0]))                              # :106
+    assert set(m.dof_table()["kp"][:6]) == {17.8}                                                     # so101_old_calib.xml:23
+
+
+def _so101_states(m, rng, n):
+    nu, K = m.nu, m.n_obj
+    Q = np.zeros((n, nu + 7 * K)); QD = np.zeros((n, nu + 6 * K))
+    Q[:, :nu] = m.home_q + rng.uniform(-0.15, 0.15, (n, nu))
+    QD[:, :nu] = rng.normal(0, 0.3, (n, nu))
+    for k, (xlo, xhi, ylo, yhi) in enumerate(m.obj_spawn):
+        o = nu + 7 * k
+        Q[:, o] = rng.uniform(xlo, xhi, n); Q[:, o + 1] = rng.uniform(ylo, yhi, n)
+        Q[:, o + 2] = m.plane_z + 0.02 - rng.uniform(0, 2e-4, n)
+        yaw = rng.uniform(-np.pi, np.pi, n)
+        Q[:, o + 3] = np.cos(yaw / 2); Q[:, o + 6] = np.sin(yaw / 2)
+    Q[1, nu + 7:nu + 9] = Q[1, nu:nu + 2] + [0.02, 0.011]
+    Q[2, nu + 7:nu + 14] = [Q[2, nu], Q[2, nu + 1], m.plane_z + 0.0199, 1, 0, 0, 0]
+    Q[2, nu + 2:nu + 7] = [m.plane_z + 0.0597, 1, 0, 0, 0]
+    T = m.home_q + rng.uniform(-0.2, 0.2, (n, nu))
+    return f32(Q).astype(np.float64), f32(QD).astype(np.float64), f32(T).astype(np.float64)
+
+
+def test_so101_substep_and_observation(hostsim, so):
+    m, orc, ggm, task = so
+    rng = np.random.default_rng(5)
+    Q, QD, T = _so101_states(m, rng, 12)
+    QA = np.zeros_like(QD)
+    qo, qdo, qao = Q.copy(), QD.copy(), QA.copy()
+    info, _ = orc.step(qo, qdo, qao, T, iterations=100, tol=1e-12)
+    q, qd, qa, hinfo = hostsim_stack_step(hostsim, ggm, task, Q, QD, QA, T)
+    assert (hinfo[:, 0] == info[:, 0]).all() and info[1, 0] > 20
+    eq, ev = stack_substep_errors(Q, QD, qo, qdo, q, qd, _asm(orc, Q, QD, T))
+    assert eq.max() < TOL_Q_ABS and ev.max() < 1.0, (eq.max(), ev.max())
+    n = Q.shape[0]
+    agent, envs = np.zeros((n, 8), np.float32), np.zeros((n, 14), np.float32)
+    rew, term = np.zeros(n, np.float32), np.zeros(n, np.uint8)
+    assert hostsim.hs_stack_observe(C.byref(ggm), C.byref(task), n, _p(f32(q)), _p(agent), _p(envs), _p(rew), _p(term)) == 0
+    a, e, r, t = orc.obs(q.astype(np.float64))
+    assert a.shape == (n, 6) and (agent[:, :6] == f32(q)[:, :6]).all() and np.abs(a - q[:, :6]).max() == 0    # agent_pos = qpos
+    assert np.abs(envs - e).max() < 2e-6 and (rew == r).all() and (term.astype(bool) == t).all() and t[2]
+
+
+def test_so101_spawn_rejection_bit_exact(hostsim, so):
+    m, orc, ggm, task = so
+    redrawn = 0
+    for gid in range(400):
+        xy = np.zeros((5, 2), np.float32)
+        hostsim.hs_stack_spawn(C.byref(task), C.c_uint64(9), C.c_uint32(gid), C.c_uint32(2), _p(xy))
+        ref = np.array([orc.spawn_obj(9, gid, 2, k) for k in range(5)])
+        assert xy.tobytes() == ref.tobytes()
+        assert np.hypot(*(xy[0] - xy[1])) >= 0.06 - 1e-6                                  # cube_stack_batch.py:70-86
+        first = np.zeros((5, 2), np.float32)
+        t0 = cabi.GgStackTask.from_buffer_copy(task); t0.min_dist = 0.0
+        hostsim.hs_stack_spawn(C.byref(t0), C.c_uint64(9), C.c_uint32(gid), C.c_uint32(2), _p(first))
+        redrawn += int((first[:2] != xy[:2]).any())
+        assert (first[2:] == xy[2:]).all()
+    assert 5 < redrawn < 120            # P(|d| < 0.06) on a 0.2 x 0.2 square is ~ 0.24

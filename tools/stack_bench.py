@@ -19,7 +19,7 @@ from gym_genesis_b200.sim import BatchedStackSim  # noqa: E402
 def timed(fn, steps, flush):
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
     for k in range(steps):
-        flush.fill_(k)
+        flush.fill_(k & 0xFF)
         ev[k][0].record()
         fn(k)
         ev[k][1].record()
