@@ -224,7 +224,10 @@ __global__ void __launch_bounds__(32) stack_prep_kernel(const __grid_constant__ 
 }
 
 // ----------------------------------------------------------------------------------------------------------------- solve
-constexpr int kSolveWarps = 4;
+#ifndef GG_SOLVE_WARPS
+#define GG_SOLVE_WARPS 4
+#endif
+constexpr int kSolveWarps = GG_SOLVE_WARPS;
 
 // PERSISTENT warps: every warp pops env ids from the list stack_prep_kernel compacted (envs whose bodies can touch each other)
 // until it is empty.  A block-per-4-envs launch left 60 % of the warp slots idle -- warps of envs with nothing to solve exit at

@@ -233,11 +233,19 @@ GG_WD int stack_collide(const GgModel& M, int max_contacts, const StackIn<NA, NF
     for (int t0 = 0; t0 < nT; t0 += 32) {
         Contacts8 C;
         C.count = 0;
+        // decode the lane's geom pair, then ONE plane_box / box_box call site (the two routines are ~3 k instructions when
+        // inlined; the solver is instruction-supply bound, see profiles/r01_notes.md)
         int t = t0 + lane;
+        int kind = 0, code = 0;                                   // 0 none, 1 plane-box, 2 box-box
+        V3 cA = mk(0.f, 0.f, 0.f), hA = ch, cB = cA;
+        M3 RA = sk_mat9(In.W.lR), RB = RA;
         if (t < nT) {
             if (t < K) {
                 const float* o = In.obj[t];
-                if ((amask >> (1 + t)) & 1u) plane_box(M.plane_z, mk(o[0], o[1], o[2]), qmat(mkq(o[3], o[4], o[5], o[6])), ch, sk_code(sk_pair_id<K>(0, 4 + t), 0, 4 + t), 8, C);
+                if ((amask >> (1 + t)) & 1u) {
+                    kind = 1; cA = mk(o[0], o[1], o[2]); RA = qmat(mkq(o[3], o[4], o[5], o[6]));
+                    code = sk_code(sk_pair_id<K>(0, 4 + t), 0, 4 + t);
+                }
             } else if (t < K + np + np * K) {
                 t -= K;
                 const bool plane = t < np;
@@ -247,19 +255,19 @@ GG_WD int stack_collide(const GgModel& M, int max_contacts, const StackIn<NA, NF
                 const int fi = b - 1 < 0 ? 0 : (b - 1 < NF ? b - 1 : 0);
                 const M3 Rb = b == 0 ? sk_mat9(In.W.lR) : sk_mat9(In.W.fR[fi]);
                 const V3 pb = b == 0 ? ld3(In.W.lp) : ld3(In.W.fp[fi]);
-                const V3 c = pb + mul(Rb, ld3(M.pad_pos[g]));
-                const V3 h = ld3(M.pad_half[g]);
+                cA = pb + mul(Rb, ld3(M.pad_pos[g]));
+                hA = ld3(M.pad_half[g]);
+                const float rp = sqrtf(dot(hA, hA));
                 if (plane) {
-                    if (c.z - sqrtf(dot(h, h)) <= M.plane_z)
-                        plane_box(M.plane_z, c, mmul(Rb, qmat(ldq(M.pad_quat[g]))), h, sk_code(sk_pair_id<K>(0, 1 + b), 0, 1 + b), 8, C);
+                    if (cA.z - rp <= M.plane_z) { kind = 1; RA = mmul(Rb, qmat(ldq(M.pad_quat[g]))); code = sk_code(sk_pair_id<K>(0, 1 + b), 0, 1 + b); }
                 } else {
                     const float* o = In.obj[k];
-                    const V3 cp = mk(o[0], o[1], o[2]);
-                    const V3 dd = c - cp;
-                    const float rr = sqrtf(dot(h, h)) + rc;
-                    if (((amask >> (1 + k)) & 1u) && dot(dd, dd) <= rr * rr)
-                        box_box(c, mmul(Rb, qmat(ldq(M.pad_quat[g]))), h, cp, qmat(mkq(o[3], o[4], o[5], o[6])), ch,
-                                sk_code(sk_pair_id<K>(1 + b, 4 + k), 1 + b, 4 + k), 8, C);
+                    cB = mk(o[0], o[1], o[2]);
+                    const V3 dd = cA - cB;
+                    if (((amask >> (1 + k)) & 1u) && dot(dd, dd) <= (rp + rc) * (rp + rc)) {
+                        kind = 2; RA = mmul(Rb, qmat(ldq(M.pad_quat[g]))); RB = qmat(mkq(o[3], o[4], o[5], o[6]));
+                        code = sk_code(sk_pair_id<K>(1 + b, 4 + k), 1 + b, 4 + k);
+                    }
                 }
             } else {
                 t -= K + np + np * K;
@@ -268,13 +276,16 @@ GG_WD int stack_collide(const GgModel& M, int max_contacts, const StackIn<NA, NF
                 const int j = i + 1 + t;
                 const float* oi = In.obj[i];
                 const float* oj = In.obj[j];
-                const V3 ci = mk(oi[0], oi[1], oi[2]), cj = mk(oj[0], oj[1], oj[2]);
-                const V3 dd = ci - cj;
-                if (((amask >> (1 + i)) & (amask >> (1 + j)) & 1u) && dot(dd, dd) <= 4.f * rc * rc)
-                    box_box(ci, qmat(mkq(oi[3], oi[4], oi[5], oi[6])), ch, cj, qmat(mkq(oj[3], oj[4], oj[5], oj[6])), ch,
-                            sk_code(sk_pair_id<K>(4 + i, 4 + j), 4 + i, 4 + j), 8, C);
+                cA = mk(oi[0], oi[1], oi[2]); cB = mk(oj[0], oj[1], oj[2]);
+                const V3 dd = cA - cB;
+                if (((amask >> (1 + i)) & (amask >> (1 + j)) & 1u) && dot(dd, dd) <= 4.f * rc * rc) {
+                    kind = 2; RA = qmat(mkq(oi[3], oi[4], oi[5], oi[6])); RB = qmat(mkq(oj[3], oj[4], oj[5], oj[6]));
+                    code = sk_code(sk_pair_id<K>(4 + i, 4 + j), 4 + i, 4 + j);
+                }
             }
         }
+        if (kind == 1) plane_box(M.plane_z, cA, RA, hA, code, 8, C);
+        if (wc.any(kind == 2)) { if (kind == 2) box_box(cA, RA, hA, cB, RB, ch, code, 8, C); }
         const int incl = wc.scan_incl(C.count);
         const int base = total + incl - C.count;
         for (int k = 0; k < C.count; k++) {
