@@ -186,6 +186,8 @@ def run_gpu(args):
     from gym_genesis_b200.sim import BatchedSim
 
     n = args.envs
+    if args.total_envs:                                    # BASELINE.json configs[4]: a fixed total sharded over the ranks
+        n = args.total_envs // int(os.environ.get("WORLD_SIZE", "1"))
     m = franka_cube_pick_model()
     sim = BatchedSim(m, n, device=dev, auto_reset=True, reset_prob=RESET_PROB, seed=args.seed, first_env_id=rank * n)
     sim.reset(None, None)                                   # device Philox spawn keyed by the GLOBAL env id
@@ -401,6 +403,29 @@ def run_gpu(args):
                          "mean_contacts": sr[7] / max(sr[0], 1), "success_rate": float(simr.reward.mean().item())}}
         simr.close()
 
+    # ---- BASELINE.json configs[3]: SO-101 cube pick (6 hinge dofs), same shape of workload ----
+    c4 = None
+    if not args.no_config4:
+        from gym_genesis_b200.model_so101 import ISLAND_TOP_Z, so101_cube_pick_model
+        m4 = so101_cube_pick_model(success_height=ISLAND_TOP_Z + 0.1)
+        sim4 = BatchedSim(m4, n, device=dev, auto_reset=True, reset_prob=RESET_PROB, seed=args.seed, first_env_id=rank * n)
+        sim4.reset(None, None)
+        g4 = torch.Generator(device=dev).manual_seed(args.seed + 4)
+        home4 = torch.as_tensor(m4.home_q.astype(np.float32), device=dev)
+        a4 = home4 + (torch.rand((8, n, 6), device=dev, generator=g4) - 0.5) * 0.6
+        for k in range(20):
+            sim4.step(a4[k % 8])
+        ev4 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(200)]
+        for k in range(200):
+            flush.fill_(k & 0xFF)
+            ev4[k][0].record(); sim4.step(a4[k % 8]); ev4[k][1].record()
+        torch.cuda.synchronize(dev)
+        t4 = np.array([a.elapsed_time(b) for a, b in ev4])
+        c4 = {"workload": "SO-101 cube pick (stack placement, BASELINE.json configs[3]), %d envs, random joint targets + Bernoulli(1/200) resets" % n,
+              "value": n / (t4.mean() * 1e-3), "unit": "env-steps/s", "ms_per_step": float(t4.mean()),
+              "roofline_frac_hbm": 411 * n / (t4.mean() * 1e-3) / 1e9 / measured_peak()[0], "algorithmic_bytes_per_env_step": 411}
+        sim4.close()
+
     times = torch.tensor([t_ms, warm_ms, e2e_ms, e2e_copy_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
@@ -411,7 +436,7 @@ def run_gpu(args):
         value = n * world * args.steps / (t_ms * 1e-3)
         achieved = BYTES_PER_ENV_STEP * n / (ms_per_step * 1e-3) / 1e9
         out = {"metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-               "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+               "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if args.total_envs else "weak", "vs_baseline": None, "dtype": "f32",
                "data": "synthetic", "config": workload_config(n),
                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                             "traffic": traffic_per_launch(n), "peak_source": peak_src, "kernel": "step_kernel<7,2,false>",
@@ -426,7 +451,7 @@ def run_gpu(args):
                        "copy_engine_note": "same loop with cudaMemcpyAsync H2D of the action and D2H of reward / terminated / truncated"},
                "gpu_launches": int(launches), "clocks": clocks,
                "l2_warm": {"value": n * world * args.steps / (warm_ms * 1e-3), "unit": "env-steps/s", "note": "back-to-back launches, no L2 flush"},
-               "wall_s_timed_loop": wall, "workload_b": wb, "workload_c": wc, "workload_d": wd,
+               "wall_s_timed_loop": wall, "workload_b": wb, "workload_c": wc, "workload_d": wd, "config4_so101": c4,
                "episode_stats": {"env_steps": st[0], "episodes": st[1], "successes": st[2], "nonfinite_resets": st[5],
                                  "mean_solver_iters": st[6] / max(st[0], 1), "mean_contacts": st[7] / max(st[0], 1)}}
         if not args.no_cpu_baseline and world == 1:
@@ -435,8 +460,11 @@ def run_gpu(args):
             threads = num_threads()
             cn, cs = 4096, 2000                             # ~10-20 s of host work
             v, dt = cpu_port_run(cn, cs, 3, threads)
+            v1, dt1 = cpu_port_run(1, 20000, 100, 1)       # BASELINE.json configs[0]: num_envs = 1 on one host thread
             out["cpu_baseline"] = {"value": v, "unit": "env-steps/s", "cores": threads, "kind": "port",
-                                   "sample": f"{cn} envs x {cs} steps of the same workload, oracle fp32 build, {threads} host threads ({dt:.1f} s)"}
+                                   "sample": f"{cn} envs x {cs} steps of the same workload, oracle fp32 build, {threads} host threads ({dt:.1f} s)",
+                                   "single_env_single_thread": {"value": v1, "unit": "env-steps/s", "cores": 1,
+                                                                "sample": f"num_envs=1 x 20000 steps (BASELINE.json configs[0]), {dt1:.1f} s"}}
         args.out.emit(out)
     if world > 1:
         dist.destroy_process_group()
@@ -463,6 +491,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=200)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--envs", type=int, default=N_ENVS_PER_GPU, help="envs per GPU")
+    ap.add_argument("--total-envs", type=int, default=0, help="fixed total env count sharded over the ranks (BASELINE configs[4]: 131072); "
+                                                              "overrides --envs and reports scaling = strong")
+    ap.add_argument("--no-config4", action="store_true")
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-workload-b", action="store_true")

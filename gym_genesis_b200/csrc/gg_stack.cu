@@ -2,7 +2,7 @@
 // Replaces, for gym_genesis/tasks/franka/cube_stack.py:119-216, the Genesis calls of reset / step / compute_reward / get_obs.
 //
 // One env.step = three launches on the caller's stream (per-env pipeline in gg_stack.cuh):
-//   stack_prep_kernel    thread per env, 32 envs per block.  Masked reset, robot dynamics, body-level broad phase (pads vs plane /
+//   stack_prep_kernel    thread per env, 32 envs and two role warps per block.  Masked reset, robot dynamics, body-level broad phase (pads vs plane /
 //                        cubes, cube vs cube); every body that can touch nothing but the plane is solved HERE in registers
 //                        (robot block with joint-limit rows, 6 x 6 cube blocks with <= 4 plane contacts).  The StackIn record of
 //                        each env (robot dynamics + object states) is transposed through shared memory and written env-major, so
@@ -143,15 +143,21 @@ __device__ __forceinline__ void store_objects(float* sp, size_t st, const gg::Ob
 }
 
 // ------------------------------------------------------------------------------------------------------------------ prep
+// Two role warps per 32 envs (lane = env): warp 0 ROBOT runs the robot half (dynamics, limit rows, robot-block solve), warp 1
+// CUBES the cube half (pad reach from its own walk of the pad-body chain, cube-cube reach, register solves of the isolated
+// cubes, reset spawn).  The halves are independent until the amask words are merged after one __syncthreads; running them side
+// by side halves the dependent chain of this latency-bound kernel and doubles its warps per SM.
 template <int NA, int NF, bool FH, int K>
-__global__ void __launch_bounds__(32) stack_prep_kernel(const __grid_constant__ StackArgs A) {
+__global__ void __launch_bounds__(64) stack_prep_kernel(const __grid_constant__ StackArgs A) {
     constexpr int NU = NA + NF, NV = NU + 6 * K;
     typedef gg::StackIn<NA, NF, K> InT;
     typedef Rows<NU, K> R;
     constexpr int WF = sizeof(InT) / sizeof(float);
     constexpr int WFP = WF | 1;                                   // odd row stride: lane = env writes are conflict free
     __shared__ float sm[32 * WFP];
-    const int lane = threadIdx.x;
+    __shared__ unsigned s_rmask[32], s_cmask[32];
+    __shared__ int s_rit[32], s_cit[32], s_cnc[32];
+    const int lane = threadIdx.x & 31, role = threadIdx.x >> 5;
     const int e0 = blockIdx.x * 32 + lane;
     const bool live = e0 < A.n;
     const int e = live ? e0 : A.n - 1;
@@ -160,66 +166,97 @@ __global__ void __launch_bounds__(32) stack_prep_kernel(const __grid_constant__ 
     float* sp = A.state + e;
     const bool do_reset = stack_reset_decision(A, e, gid);
     const bool active = do_reset ? (A.M.settle_steps > 0) : (A.mode == 0);
-
-    float q[NU], qd[NU], warm[NU], target[NU];
-    gg::ObjState<K> O;
     float* rec = sm + lane * WFP;
     InT& In = *reinterpret_cast<InT*>(rec);                       // row of the transposition buffer
-    if (do_reset) {
+
+    // object states: both roles need the positions; CUBES owns the reset writes and the record fields
+    gg::ObjState<K> O;
+    if (do_reset) spawn_objects<K>(A, e, gid, (uint32_t)A.episode[e], true, O);
+    else load_objects<NU, K>(sp, st, O);
+
+    if (role == 0) {
+        // ---------------------------------------------------------------------------------------------------------- ROBOT
+        float q[NU], qd[NU], warm[NU], target[NU];
 #pragma unroll
-        for (int i = 0; i < NU; i++) { q[i] = A.M.home_q[i]; qd[i] = 0.f; warm[i] = 0.f; }
-        spawn_objects<K>(A, e, gid, (uint32_t)A.episode[e], true, O);
-#pragma unroll
-        for (int k = 0; k < K; k++)
-#pragma unroll
-            for (int i = 0; i < 6; i++) In.warm_obj[k][i] = 0.f;
-        if (live) {
-#pragma unroll
-            for (int i = 0; i < NU; i++) { sp[(R::Q + i) * st] = q[i]; sp[(R::QD + i) * st] = 0.f; }
-            store_objects<NU, K>(sp, st, O);
-#pragma unroll
-            for (int i = 0; i < NV; i++) sp[(R::WARM + i) * st] = 0.f;
+        for (int i = 0; i < NU; i++) {
+            const float lq = sp[(R::Q + i) * st], lqd = sp[(R::QD + i) * st], lw = sp[(R::WARM + i) * st];
+            q[i] = do_reset ? A.M.home_q[i] : lq; qd[i] = do_reset ? 0.f : lqd; warm[i] = do_reset ? 0.f : lw;
         }
+        if (do_reset && live) {
+#pragma unroll
+            for (int i = 0; i < NU; i++) { sp[(R::Q + i) * st] = q[i]; sp[(R::QD + i) * st] = 0.f; sp[(R::WARM + i) * st] = 0.f; }
+        }
+        const bool use_action = A.mode == 0 && !do_reset;
+#pragma unroll
+        for (int i = 0; i < NU; i++) target[i] = use_action ? A.action[(size_t)e * NU + i] : A.M.home_q[i];
+        int rit = 0;
+        s_rmask[lane] = gg::stack_prep_robot<NA, NF, FH, K>(A.M, q, qd, warm, target, O.p, A.iterations, A.tol, active && live, In.W, rit);
+        s_rit[lane] = rit;
     } else {
-#pragma unroll
-        for (int i = 0; i < NU; i++) { q[i] = sp[(R::Q + i) * st]; qd[i] = sp[(R::QD + i) * st]; warm[i] = sp[(R::WARM + i) * st]; }
-        load_objects<NU, K>(sp, st, O);
-#pragma unroll
-        for (int k = 0; k < K; k++)
-#pragma unroll
-            for (int i = 0; i < 6; i++) In.warm_obj[k][i] = sp[(R::WARM + NU + 6 * k + i) * st];
-    }
-    const bool use_action = A.mode == 0 && !do_reset;
-#pragma unroll
-    for (int i = 0; i < NU; i++) target[i] = use_action ? A.action[(size_t)e * NU + i] : A.M.home_q[i];
-#pragma unroll
-    for (int k = 0; k < K; k++) {
-        float* o = In.obj[k];
-        o[0] = O.p[k].x; o[1] = O.p[k].y; o[2] = O.p[k].z; o[3] = O.q[k].w; o[4] = O.q[k].x; o[5] = O.q[k].y; o[6] = O.q[k].z;
-        o[7] = O.v[k].x; o[8] = O.v[k].y; o[9] = O.v[k].z; o[10] = O.w[k].x; o[11] = O.w[k].y; o[12] = O.w[k].z;
-    }
-    gg::stack_prep<NA, NF, FH, K>(A.M, q, qd, warm, target, O, A.iterations, A.tol, active && live, In);
-    if (live) {
-        const bool coop = active && In.W.amask != 0.f;
-        A.flags[e] = (do_reset ? 1 : 0) | (active ? 2 : 0) | (coop ? 4 : 0);
-        if (active) {
-            // accelerations of everything solved in registers; the cooperative solve overwrites its own dofs
-            float* ap = A.acc + e;
-#pragma unroll
-            for (int i = 0; i < NU; i++) ap[(size_t)i * st] = In.W.arob[i];
+        // ---------------------------------------------------------------------------------------------------------- CUBES
+        if (do_reset) {
 #pragma unroll
             for (int k = 0; k < K; k++)
 #pragma unroll
-                for (int i = 0; i < 6; i++) ap[(size_t)(NU + 6 * k + i) * st] = In.aobj[k][i];
-            if (!coop) { A.ncon[e] = (int)In.W.iso_ncon; A.iters[e] = (int)In.W.iso_iters; }
-            else A.coop_list[atomicAdd(&A.coop_ctr[0], 1)] = e;
+                for (int i = 0; i < 6; i++) In.warm_obj[k][i] = 0.f;
+            if (live) {
+                store_objects<NU, K>(sp, st, O);
+#pragma unroll
+                for (int i = 0; i < 6 * K; i++) sp[(R::WARM + NU + i) * st] = 0.f;
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < K; k++)
+#pragma unroll
+                for (int i = 0; i < 6; i++) In.warm_obj[k][i] = sp[(R::WARM + NU + 6 * k + i) * st];
+        }
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+            float* o = In.obj[k];
+            o[0] = O.p[k].x; o[1] = O.p[k].y; o[2] = O.p[k].z; o[3] = O.q[k].w; o[4] = O.q[k].x; o[5] = O.q[k].y; o[6] = O.q[k].z;
+            o[7] = O.v[k].x; o[8] = O.v[k].y; o[9] = O.v[k].z; o[10] = O.w[k].x; o[11] = O.w[k].y; o[12] = O.w[k].z;
+        }
+        unsigned pad_cubes;
+        {
+            float q[NU];
+#pragma unroll
+            for (int i = 0; i < NU; i++) { const float lq = sp[(R::Q + i) * st]; q[i] = do_reset ? A.M.home_q[i] : lq; }
+            gg::RobotDyn<NA, NF> D;
+            gg::robot_pad_frames<NA, NF, FH>(A.M, q, D);
+            bool pad_plane;
+            gg::stack_pad_reach<NA, NF>(A.M, D, K, O.p, pad_plane, pad_cubes);
+        }
+        int cit = 0, cnc = 0;
+        s_cmask[lane] = gg::stack_prep_cubes<K>(A.M, O, In.warm_obj, pad_cubes, A.iterations, A.tol, active && live, In.aobj, cit, cnc);
+        s_cit[lane] = cit; s_cnc[lane] = cnc;
+    }
+    __syncthreads();
+    if (role == 0) {
+        const unsigned amask = s_rmask[lane] | s_cmask[lane];
+        const int iso_iters = s_rit[lane] > s_cit[lane] ? s_rit[lane] : s_cit[lane];
+        In.W.amask = (float)amask; In.W.iso_iters = (float)iso_iters; In.W.iso_ncon = (float)s_cnc[lane];
+        if (live) {
+            const bool coop = active && amask != 0u;
+            A.flags[e] = (do_reset ? 1 : 0) | (active ? 2 : 0) | (coop ? 4 : 0);
+            if (active) {
+                // accelerations of everything solved in registers; the cooperative solve overwrites its own dofs
+                float* ap = A.acc + e;
+#pragma unroll
+                for (int i = 0; i < NU; i++) ap[(size_t)i * st] = In.W.arob[i];
+#pragma unroll
+                for (int k = 0; k < K; k++)
+#pragma unroll
+                    for (int i = 0; i < 6; i++) ap[(size_t)(NU + 6 * k + i) * st] = In.aobj[k][i];
+                if (!coop) { A.ncon[e] = s_cnc[lane]; A.iters[e] = iso_iters; }
+                else A.coop_list[atomicAdd(&A.coop_ctr[0], 1)] = e;
+            }
         }
     }
-    __syncwarp();
-    // coalesced env-major copy of the block's records
+    __syncthreads();
+    // coalesced env-major copy of the block's records (both warps)
     const int nlive = min(32, A.n - blockIdx.x * 32);
     float* dst = A.work + (size_t)blockIdx.x * 32 * WF;
-    for (int r = 0; r < nlive; r++)
+    for (int r = role; r < nlive; r += 2)
         for (int i = lane; i < WF; i += 32) dst[(size_t)r * WF + i] = sm[r * WFP + i];
 }
 
@@ -434,7 +471,7 @@ static int stack_launch(GgStackSim* sim, StackArgs& A, gg_stream_t stream) {
 template <int NA, int NF, bool FH, int K>
 static void stack_launch_t(GgStackSim* sim, const StackArgs& A, cudaStream_t s) {
     if (A.mode != 2) {
-        stack_prep_kernel<NA, NF, FH, K><<<(sim->n + 31) / 32, 32, 0, s>>>(A);
+        stack_prep_kernel<NA, NF, FH, K><<<(sim->n + 31) / 32, 64, 0, s>>>(A);
         const int need = (sim->n + kSolveWarps - 1) / kSolveWarps;
         stack_solve_kernel<NA, NF, FH, K><<<need < sim->solve_blocks ? need : sim->solve_blocks, 32 * kSolveWarps, sim->solve_smem, s>>>(A);
     }

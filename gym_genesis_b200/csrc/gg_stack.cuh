@@ -131,11 +131,15 @@ GG_HD void stack_pad_reach(const GgModel& M, const RobotDyn<NA, NF>& D, int K, c
     }
 }
 
+// The prep stage is two independent halves (the CUDA kernel runs them in two warps of the same block, lane = env):
+//   stack_prep_robot : robot dynamics, limit rows, pad reach, robot-block solve when no pad can touch anything -> In.W (all but the
+//                      amask / iso_* words), returns the robot's amask bits (bit 0 robot, bit 1 + k cube k within reach of a pad)
+//   stack_prep_cubes : cube-cube reach, register solves of the isolated cubes -> In.aobj, returns the cube bits and statistics
+// The pad reach is needed by both; the cube half recomputes it from the pad-body frames (robot_pad_frames, one chain walk).
 template <int NA, int NF, bool FH, int K>
-GG_HD void stack_prep(const GgModel& M, const float* q, const float* qd, const float* warm, const float* target, const ObjState<K>& O,
-                      int iterations, float tol, bool active, StackIn<NA, NF, K>& In) {
+GG_HD unsigned stack_prep_robot(const GgModel& M, const float* q, const float* qd, const float* warm, const float* target, const V3* cube_pos,
+                                int iterations, float tol, bool active, StackWork<NA, NF>& W, int& rob_iters) {
     constexpr int NU = NA + NF;
-    StackWork<NA, NF>& W = In.W;
     RobotDyn<NA, NF> D;
     robot_dynamics<NA, NF, FH>(M, q, qd, target, D);
     float as[NU];
@@ -148,43 +152,14 @@ GG_HD void stack_prep(const GgModel& M, const float* q, const float* qd, const f
     }
     float lsg[NU], laref[NU], lD[NU], a[NU];
     const int nlim = joint_limit_rows<NU>(M, q, qd, lsg, laref, lD);
-    // ---- who can touch whom: pads vs plane / cubes, cube vs cube (bounding spheres)
     bool pad_plane; unsigned pad_cubes;
-    stack_pad_reach<NA, NF>(M, D, K, O.p, pad_plane, pad_cubes);
-    unsigned amask = (pad_plane || pad_cubes != 0u) ? 1u : 0u;
-    amask |= pad_cubes << 1;
-    {
-        const V3 ch = ld3(M.cube_half);
-        const float r2 = 4.f * dot(ch, ch);
-#pragma unroll
-        for (int i = 0; i < K; i++)
-#pragma unroll
-            for (int j = i + 1; j < K; j++) {
-                const V3 d = O.p[i] - O.p[j];
-                if (dot(d, d) <= r2) amask |= (2u << i) | (2u << j);
-            }
-    }
-    // ---- register solves of everything that cannot touch anything but the plane
+    stack_pad_reach<NA, NF>(M, D, K, cube_pos, pad_plane, pad_cubes);
+    const unsigned rmask = ((pad_plane || pad_cubes != 0u) ? 1u : 0u) | (pad_cubes << 1);
     StepInfo ir; ir.ncon = 0; ir.iters = 0; ir.grad = 0.f;
 #pragma unroll
     for (int i = 0; i < NU; i++) a[i] = as[i];
-    if (active && !(amask & 1u)) robot_block_solve<NU>(D.Mt, as, nlim, lsg, laref, lD, warm, a, iterations, tol, ir);
-    int iso_iters = ir.iters, iso_ncon = 0;
-    for (int k = 0; k < K; k++) {
-        float Mc[6], as_c[6], qd_c[6], a_c[6], w_c[6];
-        cube_free_acc(M, O.v[k], O.w[k], Mc, as_c, qd_c);
-#pragma unroll
-        for (int i = 0; i < 6; i++) { a_c[i] = as_c[i]; w_c[i] = In.warm_obj[k][i]; }
-        if (active && !((amask >> (1 + k)) & 1u)) {
-            StepInfo ic;
-            CubeConLocal cs;
-            cube_block_solve(M, O.p[k], qmat(O.q[k]), Mc, as_c, qd_c, w_c, a_c, iterations, tol, cs, ic);
-            iso_ncon += ic.ncon;
-            iso_iters = ic.iters > iso_iters ? ic.iters : iso_iters;
-        }
-#pragma unroll
-        for (int i = 0; i < 6; i++) In.aobj[k][i] = a_c[i];
-    }
+    if (active && !(rmask & 1u)) robot_block_solve<NU>(D.Mt, as, nlim, lsg, laref, lD, warm, a, iterations, tol, ir);
+    rob_iters = ir.iters;
 #pragma unroll
     for (int i = 0; i < NU * (NU + 1) / 2; i++) W.Mt[i] = D.Mt[i];
 #pragma unroll
@@ -208,7 +183,55 @@ GG_HD void stack_prep(const GgModel& M, const float* q, const float* qd, const f
     W.lR[0] = D.lR.c0.x; W.lR[1] = D.lR.c0.y; W.lR[2] = D.lR.c0.z; W.lR[3] = D.lR.c1.x; W.lR[4] = D.lR.c1.y; W.lR[5] = D.lR.c1.z;
     W.lR[6] = D.lR.c2.x; W.lR[7] = D.lR.c2.y; W.lR[8] = D.lR.c2.z;
     W.lp[0] = D.lp.x; W.lp[1] = D.lp.y; W.lp[2] = D.lp.z;
-    W.amask = (float)amask; W.active = active ? 1.f : 0.f; W.iso_iters = (float)iso_iters; W.iso_ncon = (float)iso_ncon;
+    W.active = active ? 1.f : 0.f;
+    return rmask;
+}
+
+// pad_cubes: bit k = cube k within reach of a pad.  Returns the cube bits of amask (bit 1 + k).
+template <int K>
+GG_HD unsigned stack_prep_cubes(const GgModel& M, const ObjState<K>& O, const float (*warm_obj)[6], unsigned pad_cubes, int iterations,
+                                float tol, bool active, float (*aobj)[6], int& iso_iters, int& iso_ncon) {
+    unsigned cmask = pad_cubes << 1;
+    {
+        const V3 ch = ld3(M.cube_half);
+        const float r2 = 4.f * dot(ch, ch);
+#pragma unroll
+        for (int i = 0; i < K; i++)
+#pragma unroll
+            for (int j = i + 1; j < K; j++) {
+                const V3 d = O.p[i] - O.p[j];
+                if (dot(d, d) <= r2) cmask |= (2u << i) | (2u << j);
+            }
+    }
+    iso_iters = 0; iso_ncon = 0;
+    for (int k = 0; k < K; k++) {
+        float Mc[6], as_c[6], qd_c[6], a_c[6], w_c[6];
+        cube_free_acc(M, O.v[k], O.w[k], Mc, as_c, qd_c);
+#pragma unroll
+        for (int i = 0; i < 6; i++) { a_c[i] = as_c[i]; w_c[i] = warm_obj[k][i]; }
+        if (active && !((cmask >> (1 + k)) & 1u)) {
+            StepInfo ic;
+            CubeConLocal cs;
+            cube_block_solve(M, O.p[k], qmat(O.q[k]), Mc, as_c, qd_c, w_c, a_c, iterations, tol, cs, ic);
+            iso_ncon += ic.ncon;
+            iso_iters = ic.iters > iso_iters ? ic.iters : iso_iters;
+        }
+#pragma unroll
+        for (int i = 0; i < 6; i++) aobj[k][i] = a_c[i];
+    }
+    return cmask;
+}
+
+// both halves in one thread (host harness)
+template <int NA, int NF, bool FH, int K>
+GG_HD void stack_prep(const GgModel& M, const float* q, const float* qd, const float* warm, const float* target, const ObjState<K>& O,
+                      int iterations, float tol, bool active, StackIn<NA, NF, K>& In) {
+    int rob_iters, iso_iters, iso_ncon;
+    const unsigned rmask = stack_prep_robot<NA, NF, FH, K>(M, q, qd, warm, target, O.p, iterations, tol, active, In.W, rob_iters);
+    const unsigned cmask = stack_prep_cubes<K>(M, O, In.warm_obj, rmask >> 1, iterations, tol, active, In.aobj, iso_iters, iso_ncon);
+    In.W.amask = (float)(rmask | cmask);
+    In.W.iso_iters = (float)(rob_iters > iso_iters ? rob_iters : iso_iters);
+    In.W.iso_ncon = (float)iso_ncon;
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
