@@ -70,7 +70,8 @@ template <int NU, int K> struct StackBuf {
     float Y[NV][6];
     float H[NH];
     float dinv[NV], vx[NV];
-    int gl[NV];               // local (compacted) index -> dof
+    int gl[NV], lo[NV];       // local (compacted) index -> dof and back
+    int plist[NPAIR];         // ids of the body pairs in contact
 };
 
 // ---- body / pair bookkeeping ------------------------------------------------------------------------------------------
@@ -328,6 +329,8 @@ GG_WD int stack_collide(const GgModel& M, int max_contacts, const StackIn<NA, NF
 
 // the solve over the ACTIVE bodies (W.amask != 0).  a_out[d * a_stride] receives the acceleration of the active dofs; the others
 // keep the result of stack_prep's register solves (W.arob, In.aobj), which the caller has already stored there.
+// Ownership: lane l (and l + 32 when more than 32 dofs are active -- a warp-uniform rarity) owns the l-th ACTIVE dof, i.e. row l of
+// the packed Hessian; B.gl / B.lo translate between that compacted index and the dof number.
 template <int NA, int NF, bool FH, int K, class WC>
 GG_WD void stack_solve(const GgModel& M, int max_contacts, const StackIn<NA, NF, K>& In, StackBuf<NA + NF, K>& B, int iterations, float tol,
                        WC& wc, float* a_out, int a_stride, int& iters_out, int& ncon_out) {
@@ -338,18 +341,11 @@ GG_WD void stack_solve(const GgModel& M, int max_contacts, const StackIn<NA, NF,
     const float mu = M.friction;
     const unsigned amask = (unsigned)W.amask;
     const bool cpl = (amask & 1u) != 0u;
-    // compacted (local) index of dof d: robot dofs first, then the active cubes in order
-    auto loc = [&](int d) -> int {
-        if (d < NU) return d;
-        const int kb = (d - NU) / 6;
-        int below = 0;
-#pragma unroll
-        for (int k = 0; k < K; k++) below += (k < kb && ((amask >> (1 + k)) & 1u)) ? 1 : 0;
-        return (cpl ? NU : 0) + 6 * below + (d - NU - 6 * kb);
-    };
-    int n = cpl ? NU : 0;
+    const int nrob = cpl ? NU : 0;
+    int n = nrob;
 #pragma unroll
     for (int k = 0; k < K; k++) n += ((amask >> (1 + k)) & 1u) ? 6 : 0;
+    const bool wide = n > 32;                          // slot 1 of the per-lane arrays is in use
     // reference point of the spatial vectors: the first active cube (contacts of interest are near it), else cube 0
     int kref = 0;
 #pragma unroll
@@ -378,37 +374,52 @@ GG_WD void stack_solve(const GgModel& M, int max_contacts, const StackIn<NA, NF,
         }
     }
 
-    // ---- per-dof data: lane owns dofs lane, lane + 32
+    // ---- per-dof data: lane owns active dofs number lane, lane + 32
     float Bd[ND][6], as_d[ND], qd_d[ND], warm_d[ND], Mc_d[ND];
-    bool val[ND];                                      // dof takes part in the cooperative solve
-    int ld[ND];                                        // its local index
+    bool val[ND];
+    int dd[ND];                                        // dof number of the owned row (0 when none)
     float lsg_d = 0.f, laref_d = 0.f, lD_d = 0.f;
     float Mrow[NU];
 #pragma unroll
     for (int j = 0; j < NU; j++) Mrow[j] = 0.f;
 #pragma unroll
     for (int s = 0; s < ND; s++) {
-        const int d = lane + 32 * s;
+        const int l = lane + 32 * s;
 #pragma unroll
         for (int k = 0; k < 6; k++) Bd[s][k] = 0.f;
         as_d[s] = 0.f; qd_d[s] = 0.f; warm_d[s] = 0.f; Mc_d[s] = 0.f;
-        val[s] = d < NV && (d < NU ? cpl : (((amask >> (1 + (d - NU) / 6)) & 1u) != 0u));
-        ld[s] = val[s] ? loc(d) : 0;
-        if (val[s]) B.gl[ld[s]] = d;
+        val[s] = l < n; dd[s] = 0;
+        if (s > 0 && !wide) continue;
+        if (!val[s]) continue;
+        int d;
+        if (l < nrob) d = l;
+        else {
+            const int r = (l - nrob) / 6, j = (l - nrob) - 6 * r;
+            int kb = 0, seen = 0;
+#pragma unroll
+            for (int k = 0; k < K; k++) {
+                const bool on = ((amask >> (1 + k)) & 1u) != 0u;
+                if (on && seen == r) kb = k;
+                seen += on ? 1 : 0;
+            }
+            d = NU + 6 * kb + j;
+        }
+        dd[s] = d;
+        B.gl[l] = d; B.lo[d] = l;
         if (d < NA) {
             const V3 k = ld3(W.jk[d]), o = ld3(W.jo[d]);
-            const V3 l = cross(o - O, k);
-            Bd[s][0] = k.x; Bd[s][1] = k.y; Bd[s][2] = k.z; Bd[s][3] = l.x; Bd[s][4] = l.y; Bd[s][5] = l.z;
+            const V3 lv = cross(o - O, k);
+            Bd[s][0] = k.x; Bd[s][1] = k.y; Bd[s][2] = k.z; Bd[s][3] = lv.x; Bd[s][4] = lv.y; Bd[s][5] = lv.z;
         } else if (d < NU) {
             const int f = d - NA;
             const V3 k = ld3(W.fk[f]), o = ld3(W.fo[f]);
             if (FH) {
-                const V3 l = cross(o - O, k);
-                Bd[s][0] = k.x; Bd[s][1] = k.y; Bd[s][2] = k.z; Bd[s][3] = l.x; Bd[s][4] = l.y; Bd[s][5] = l.z;
+                const V3 lv = cross(o - O, k);
+                Bd[s][0] = k.x; Bd[s][1] = k.y; Bd[s][2] = k.z; Bd[s][3] = lv.x; Bd[s][4] = lv.y; Bd[s][5] = lv.z;
             } else {
                 Bd[s][3] = k.x; Bd[s][4] = k.y; Bd[s][5] = k.z;
             }
-        } else if (d < NV) {
+        } else {
             const int kb = (d - NU) / 6, j = (d - NU) % 6;
             const float* o = In.obj[kb];
             float Mc[6], asc[6], qdc[6];
@@ -417,53 +428,60 @@ GG_WD void stack_solve(const GgModel& M, int max_contacts, const StackIn<NA, NF,
             else {
                 const M3 R = qmat(mkq(o[3], o[4], o[5], o[6]));
                 const V3 ax = j == 3 ? R.c0 : (j == 4 ? R.c1 : R.c2);
-                const V3 l = cross(mk(o[0], o[1], o[2]) - O, ax);
-                Bd[s][0] = ax.x; Bd[s][1] = ax.y; Bd[s][2] = ax.z; Bd[s][3] = l.x; Bd[s][4] = l.y; Bd[s][5] = l.z;
+                const V3 lv = cross(mk(o[0], o[1], o[2]) - O, ax);
+                Bd[s][0] = ax.x; Bd[s][1] = ax.y; Bd[s][2] = ax.z; Bd[s][3] = lv.x; Bd[s][4] = lv.y; Bd[s][5] = lv.z;
             }
 #pragma unroll
             for (int k = 0; k < 6; k++) if (k == j) { as_d[s] = asc[k]; qd_d[s] = qdc[k]; Mc_d[s] = Mc[k]; }
             warm_d[s] = In.warm_obj[kb][j];
         }
-        if (d < NU) {
+        if (d < NU) {                                   // only reached with the robot active, in slot 0
             as_d[s] = W.as[d]; qd_d[s] = W.qd[d]; warm_d[s] = W.warm[d];
-            if (cpl) { lsg_d = W.lsg[d]; laref_d = W.laref[d]; lD_d = W.lD[d]; }
+            lsg_d = W.lsg[d]; laref_d = W.laref[d]; lD_d = W.lD[d];
 #pragma unroll
             for (int j = 0; j < NU; j++) Mrow[j] = W.Mt[d >= j ? GG_TRI(d, j) : GG_TRI(j, d)];
         }
-        if (d < NV) {
 #pragma unroll
-            for (int k = 0; k < 6; k++) B.TB[d][k] = Bd[s][k];
-        }
+        for (int k = 0; k < 6; k++) B.TB[d][k] = Bd[s][k];
+    }
+    // compact list of the body pairs in contact
+    int npair = 0;
+    wc.sync();
+    for (int p0 = 0; p0 < BufT::NPAIR; p0 += 32) {
+        const int pid = p0 + lane;
+        const int flag = (pid < BufT::NPAIR && B.pairAB[pid] >= 0) ? 1 : 0;
+        const int incl = wc.scan_incl(flag);
+        if (flag) B.plist[npair + incl - 1] = pid;
+        npair += wc.shfli(incl, 31);
     }
     wc.sync();
 
-    // (Mt + Mc) x for a vector held one component per (lane, slot); frozen dofs contribute nothing
+    // (Mt + Mc) x for a vector held one component per owned row
     auto mass_mul = [&](const float* x, float* r) {
-        wc.sync();
-#pragma unroll
-        for (int s = 0; s < ND; s++) { const int d = lane + 32 * s; if (d < NV) B.vx[d] = val[s] ? x[s] : 0.f; }
-        wc.sync();
+        if (cpl) {
+            wc.sync();
+            if (lane < NU) B.vx[lane] = x[0];              // robot rows are local rows 0..NU-1 of slot 0
+            wc.sync();
+        }
 #pragma unroll
         for (int s = 0; s < ND; s++) {
-            const int d = lane + 32 * s;
             float v = Mc_d[s] * x[s];
-            if (s == 0 && d < NU) {
+            if (s == 0 && cpl && lane < NU) {
 #pragma unroll
                 for (int j = 0; j < NU; j++) v += Mrow[j] * B.vx[j];
             }
             r[s] = val[s] ? v : 0.f;
         }
     };
-    // body twists of the dof vector x into T[slot]
+    // body twists of the dof vector x into T[slot] (inactive bodies: zero twist, they carry no contact)
     auto body_twists = [&](const float* x, int slot) {
         wc.sync();
 #pragma unroll
         for (int s = 0; s < ND; s++) {
-            const int d = lane + 32 * s;
-            if (d < NV) {
-                const float xv = val[s] ? x[s] : 0.f;
+            if (s > 0 && !wide) continue;
+            if (val[s]) {
 #pragma unroll
-                for (int k = 0; k < 6; k++) B.Y[d][k] = Bd[s][k] * xv;
+                for (int k = 0; k < 6; k++) B.Y[dd[s]][k] = Bd[s][k] * x[s];
             }
         }
         wc.sync();
@@ -471,9 +489,11 @@ GG_WD void stack_solve(const GgModel& M, int max_contacts, const StackIn<NA, NF,
             const int b = t / 6, k = t % 6;
             float v = 0.f;
             if (b >= 1 && b < 4) {
-                for (int d = 0; d < NA; d++) v += B.Y[d][k];
-                if (b >= 2 && b - 2 < NF) v += B.Y[NA + b - 2][k];
-            } else if (b >= 4) {
+                if (cpl) {
+                    for (int d = 0; d < NA; d++) v += B.Y[d][k];
+                    if (b >= 2 && b - 2 < NF) v += B.Y[NA + b - 2][k];
+                }
+            } else if (b >= 4 && ((amask >> (1 + b - 4)) & 1u)) {
                 for (int j = 0; j < 6; j++) v += B.Y[NU + 6 * (b - 4) + j][k];
             }
             B.T[slot][b][k] = v;
@@ -559,9 +579,11 @@ GG_WD void stack_solve(const GgModel& M, int max_contacts, const StackIn<NA, NF,
             const float jar = lsg_d * a_d[0] - laref_d;
             if (lsg_d != 0.f && jar < 0.f) { hlim = lD_d; g_d[0] += lD_d * jar * lsg_d; }
         }
-        // ---- per-contact weights, clear the accumulators
-        for (int i = lane; i < BufT::NPAIR * 21; i += 32) (&B.Phi[0][0])[i] = 0.f;
-        for (int i = lane; i < BufT::NPAIR * 6; i += 32) (&B.gF[0][0])[i] = 0.f;
+        // ---- per-contact weights, clear the accumulators of the pairs in contact
+        for (int u = 0; u < npair; u++) {
+            const int pid = B.plist[u];
+            if (lane < 21) B.Phi[pid][lane] = 0.f; else if (lane < 27) B.gF[pid][lane - 21] = 0.f;
+        }
         for (int i = lane; i < n * (n + 1) / 2; i += 32) B.H[i] = 0.f;
 #pragma unroll
         for (int s = 0; s < SK_CPL; s++) {
@@ -615,19 +637,20 @@ GG_WD void stack_solve(const GgModel& M, int max_contacts, const StackIn<NA, NF,
         if (cpl) for (int e = lane; e < NU * (NU + 1) / 2; e += 32) B.H[e] = W.Mt[e];
 #pragma unroll
         for (int s = 0; s < ND; s++) {
-            const int d = lane + 32 * s;
-            if (val[s] && d >= NU) B.H[GG_TRI(ld[s], ld[s])] = Mc_d[s];
+            const int l = lane + 32 * s;
+            if (val[s] && dd[s] >= NU) B.H[GG_TRI(l, l)] = Mc_d[s];
         }
         wc.sync();
         // ---- ... + sum over the body pairs in contact of P^T Phi P;  g += P^T gF
-        for (int pid = 0; pid < BufT::NPAIR; pid++) {
+        for (int u = 0; u < npair; u++) {
+            const int pid = B.plist[u];
             const int ab = B.pairAB[pid];
-            if (ab < 0) continue;                                // uniform
             const int A = ab & 0xff, Bb = ab >> 8;
 #pragma unroll
             for (int s = 0; s < ND; s++) {
-                const int d = lane + 32 * s;
+                if (s > 0 && !wide) continue;
                 if (val[s]) {
+                    const int d = dd[s];
                     const float sj = sk_sign<NA, NF>(A, Bb, d);
                     if (sj != 0.f) {
                         const float* P = B.Phi[pid];
@@ -649,7 +672,7 @@ GG_WD void stack_solve(const GgModel& M, int max_contacts, const StackIn<NA, NF,
                 const int i = li < nA ? sk_dof<NA, NF>(A, li) : sk_dof<NA, NF>(Bb, li - nA);
                 const int j = lj < nA ? sk_dof<NA, NF>(A, lj) : sk_dof<NA, NF>(Bb, lj - nA);
                 const float si = sk_sign<NA, NF>(A, Bb, i);
-                B.H[GG_TRI(loc(i), loc(j))] += si * sk_dot6(B.TB[i], B.Y[j]);
+                B.H[GG_TRI(B.lo[i], B.lo[j])] += si * sk_dot6(B.TB[i], B.Y[j]);
             }
             wc.sync();
         }
@@ -660,8 +683,8 @@ GG_WD void stack_solve(const GgModel& M, int max_contacts, const StackIn<NA, NF,
             float r = 0.f, am = 0.f;
 #pragma unroll
             for (int s = 0; s < ND; s++) {
-                const int d = lane + 32 * s;
-                if (val[s]) { r = fmaxf(r, fabsf(g_d[s]) * gg_rcp(B.H[GG_TRI(ld[s], ld[s])])); am = fmaxf(am, fabsf(a_d[s])); }
+                const int l = lane + 32 * s;
+                if (val[s]) { r = fmaxf(r, fabsf(g_d[s]) * gg_rcp(B.H[GG_TRI(l, l)])); am = fmaxf(am, fabsf(a_d[s])); }
             }
             r = wc.max(r); am = wc.max(am);
             if (gg_div(r, 1.f + am) < tol) break;
@@ -674,6 +697,7 @@ GG_WD void stack_solve(const GgModel& M, int max_contacts, const StackIn<NA, NF,
             for (int s = 0; s < ND; s++) {
                 const int i = j + lane + 32 * s;
                 t[s] = 0.f;
+                if (s > 0 && n - j <= 32) continue;
                 if (i < n) {
                     const float* ri = &B.H[GG_TRI(i, 0)];
                     const float* rj = &B.H[GG_TRI(j, 0)];
@@ -694,36 +718,32 @@ GG_WD void stack_solve(const GgModel& M, int max_contacts, const StackIn<NA, NF,
             wc.sync();
         }
         if (!ok) break;
-        // ---- solve L L^T s = -g: the right-hand side stays in registers (lane owns its dofs), one shuffle per column
+        // ---- solve L L^T s = -g: the right-hand side stays in registers (lane owns its rows), one shuffle per column
         float s_d[ND];
 #pragma unroll
         for (int s = 0; s < ND; s++) s_d[s] = val[s] ? -g_d[s] : 0.f;
         for (int k = 0; k < n; k++) {
-            const int dk = B.gl[k];
             float cand = s_d[0];
 #pragma unroll
-            for (int s = 1; s < ND; s++) if ((dk >> 5) == s) cand = s_d[s];
-            const float yk = wc.shfl(cand, dk & 31) * B.dinv[k];
+            for (int s = 1; s < ND; s++) if ((k >> 5) == s) cand = s_d[s];
+            const float yk = wc.shfl(cand, k & 31) * B.dinv[k];
 #pragma unroll
             for (int s = 0; s < ND; s++) {
-                if (val[s]) {
-                    if (ld[s] == k) s_d[s] = yk;
-                    else if (ld[s] > k) s_d[s] -= B.H[GG_TRI(ld[s], k)] * yk;
-                }
+                const int l = lane + 32 * s;
+                if (l == k) s_d[s] = yk;
+                else if (l > k && l < n) s_d[s] -= B.H[GG_TRI(l, k)] * yk;
             }
         }
         for (int k = n - 1; k >= 0; k--) {
-            const int dk = B.gl[k];
             float cand = s_d[0];
 #pragma unroll
-            for (int s = 1; s < ND; s++) if ((dk >> 5) == s) cand = s_d[s];
-            const float xk = wc.shfl(cand, dk & 31) * B.dinv[k];
+            for (int s = 1; s < ND; s++) if ((k >> 5) == s) cand = s_d[s];
+            const float xk = wc.shfl(cand, k & 31) * B.dinv[k];
 #pragma unroll
             for (int s = 0; s < ND; s++) {
-                if (val[s]) {
-                    if (ld[s] == k) s_d[s] = xk;
-                    else if (ld[s] < k) s_d[s] -= B.H[GG_TRI(k, ld[s])] * xk;
-                }
+                const int l = lane + 32 * s;
+                if (l == k) s_d[s] = xk;
+                else if (l < k) s_d[s] -= B.H[GG_TRI(k, l)] * xk;
             }
         }
         // ---- exact line search along s
@@ -780,10 +800,8 @@ GG_WD void stack_solve(const GgModel& M, int max_contacts, const StackIn<NA, NF,
     }
     iters_out = it;
 #pragma unroll
-    for (int s = 0; s < ND; s++) {
-        const int d = lane + 32 * s;
-        if (val[s]) a_out[(size_t)d * a_stride] = a_d[s];
-    }
+    for (int s = 0; s < ND; s++)
+        if (val[s]) a_out[(size_t)dd[s] * a_stride] = a_d[s];
     wc.sync();
 }
 

@@ -171,3 +171,17 @@ def stack_substep_errors(q0, qd0, q_ref, qd_ref, q, qd, a_smooth_scale):
     ev = np.abs(qd - qd_ref).max(axis=1)
     bound = TOL_DQD_REL * np.maximum(d_ref, a_smooth_scale) + TOL_DQD_FLOOR_STACK
     return eq * TOL_Q_ABS / (TOL_Q_ABS + 0.01 * bound), ev / bound
+
+
+def stack_cluster_states(g, idx=(30, 36, 60, 80)):
+    """Golden grasp / carry samples with the four other cubes lined up next to cube_1 (0.045 m pitch): every body is within
+    reach of another one, so the cooperative solve runs on all 39 dofs (its two-rows-per-lane path)."""
+    idx = list(idx)
+    Q, QD, QA, T = (g[k][idx].copy() for k in ("q", "qd", "qacc", "act"))
+    for r in range(len(idx)):
+        c1 = Q[r, 9:12].copy()
+        for k, off in zip(range(1, 5), (0.045, -0.045, 0.09, -0.09)):
+            Q[r, 9 + 7 * k: 9 + 7 * k + 7] = [c1[0] + off, c1[1], 0.0199 if r < len(idx) - 1 else c1[2], 1, 0, 0, 0]
+        QD[r, 9:] = 0
+        QA[r] = 0
+    return tuple(f32(x).astype(np.float64) for x in (Q, QD, QA, T))
