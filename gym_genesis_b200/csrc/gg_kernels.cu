@@ -658,16 +658,16 @@ __global__ void __launch_bounds__(64) ik_kernel(const __grid_constant__ IkArgs A
 //   export_kernel : out[slot][t][:] <- traj[t][env][:]; block (x, env) copies a run of (t, c) pairs: reads are F-float runs,
 //                   writes are fully contiguous
 // ------------------------------------------------------------------------------------------------
-__global__ void record_kernel(float* __restrict__ frame, int32_t* __restrict__ ever, int n, int AD, int NU, const float* __restrict__ agent,
+__global__ void record_kernel(float* __restrict__ frame, int32_t* __restrict__ ever, int n, int AD, int ED, int NU, const float* __restrict__ agent,
                               const float* __restrict__ envs, const float* __restrict__ action, const float* __restrict__ reward) {
-    const int F = AD + GG_ENV_STATE_DIM + NU + 1;
+    const int F = AD + ED + NU + 1;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n * F) return;
     const int e = i / F, c = i - e * F;
     float v;
     if (c < AD) v = agent[(size_t)e * AD + c];
-    else if (c < AD + GG_ENV_STATE_DIM) v = envs[(size_t)e * GG_ENV_STATE_DIM + (c - AD)];
-    else if (c < F - 1) v = action[(size_t)e * NU + (c - AD - GG_ENV_STATE_DIM)];
+    else if (c < AD + ED) v = envs[(size_t)e * ED + (c - AD)];
+    else if (c < F - 1) v = action[(size_t)e * NU + (c - AD - ED)];
     else { v = reward[e]; if (v > 0.f) ever[e] = 1; }
     frame[i] = v;
 }
@@ -730,6 +730,33 @@ struct GgSim {
 // hooks for the other translation units of the library (gg_stack.cu): shared error string and launch counter
 int gg_internal_fail(const char* fmt, const char* detail) { return fail(fmt, detail); }
 void gg_internal_count_launches(int k) { g_launches.fetch_add(k); }
+
+// trajectory store shared by the pick and the stacking scenes (frame = [agent_pos | environment_state | action | reward])
+int gg_internal_record(int device, int n, int AD, int ED, int NU, float* traj, int32_t* ever, int t, int horizon, const float* action,
+                       const float* obs_agent, const float* obs_env, const float* reward, gg_stream_t stream) {
+    if (!traj || !ever || !action || !obs_agent || !obs_env || !reward) return fail("gg_record: null argument%s");
+    if (t < 0 || t >= horizon) return fail("gg_record: frame index outside the horizon%s");
+    const int F = AD + ED + NU + 1;
+    GG_CUDA(cudaSetDevice(device));
+    const int total = n * F;
+    record_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(traj + (size_t)t * n * F, ever, n, AD, ED, NU, obs_agent, obs_env, action, reward);
+    g_launches.fetch_add(1);
+    GG_CUDA(cudaGetLastError());
+    return 0;
+}
+int gg_internal_export(int device, int n, int stride, int F, int32_t** slot, const float* traj, const int32_t* ever, int horizon, float* out,
+                       int32_t* out_env_ids, int32_t* out_count, gg_stream_t stream) {
+    if (!traj || !ever || !out || !out_env_ids || !out_count) return fail("gg_export_successful: null argument%s");
+    if (horizon <= 0) return fail("gg_export_successful: horizon must be positive%s");
+    GG_CUDA(cudaSetDevice(device));
+    if (!*slot) GG_CUDA(cudaMalloc(slot, (size_t)stride * sizeof(int32_t)));   // first use only
+    select_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(ever, n, *slot, out_env_ids, out_count);
+    dim3 grid((horizon * F + 255) / 256, n);
+    export_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(traj, *slot, horizon, n, F, out);
+    g_launches.fetch_add(2);
+    GG_CUDA(cudaGetLastError());
+    return 0;
+}
 
 static int launch_step(GgSim* sim, StepArgs& A, gg_stream_t stream) {
     if (sim->state == nullptr) return fail("gg_bind_state has not been called%s");
@@ -925,31 +952,15 @@ int gg_frame_dim(const GgSim* sim) { return sim ? (7 + sim->model.n_fing) + GG_E
 
 int gg_record(GgSim* sim, float* traj, int32_t* ever, int t, int horizon, const float* action, const float* obs_agent,
               const float* obs_env, const float* reward, gg_stream_t stream) {
-    if (!sim || !traj || !ever || !action || !obs_agent || !obs_env || !reward) return fail("gg_record: null argument%s");
-    if (t < 0 || t >= horizon) return fail("gg_record: frame index outside the horizon%s");
-    const int F = gg_frame_dim(sim), n = sim->n;
-    GG_CUDA(cudaSetDevice(sim->device));
-    const int total = n * F;
-    record_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(traj + (size_t)t * n * F, ever, n, 7 + sim->model.n_fing,
-                                                                         sim->model.n_arm + sim->model.n_fing, obs_agent, obs_env, action, reward);
-    g_launches.fetch_add(1);
-    GG_CUDA(cudaGetLastError());
-    return 0;
+    if (!sim) return fail("gg_record: null argument%s");
+    return gg_internal_record(sim->device, sim->n, 7 + sim->model.n_fing, GG_ENV_STATE_DIM, sim->model.n_arm + sim->model.n_fing, traj, ever, t,
+                              horizon, action, obs_agent, obs_env, reward, stream);
 }
 
 int gg_export_successful(GgSim* sim, const float* traj, const int32_t* ever, int horizon, float* out, int32_t* out_env_ids,
                          int32_t* out_count, gg_stream_t stream) {
-    if (!sim || !traj || !ever || !out || !out_env_ids || !out_count) return fail("gg_export_successful: null argument%s");
-    if (horizon <= 0) return fail("gg_export_successful: horizon must be positive%s");
-    const int F = gg_frame_dim(sim), n = sim->n;
-    GG_CUDA(cudaSetDevice(sim->device));
-    if (!sim->slot) GG_CUDA(cudaMalloc(&sim->slot, (size_t)sim->stride * sizeof(int32_t)));   // first use only
-    select_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(ever, n, sim->slot, out_env_ids, out_count);
-    dim3 grid((horizon * F + 255) / 256, n);
-    export_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(traj, sim->slot, horizon, n, F, out);
-    g_launches.fetch_add(2);
-    GG_CUDA(cudaGetLastError());
-    return 0;
+    if (!sim) return fail("gg_export_successful: null argument%s");
+    return gg_internal_export(sim->device, sim->n, sim->stride, gg_frame_dim(sim), &sim->slot, traj, ever, horizon, out, out_env_ids, out_count, stream);
 }
 
 int gg_stats(GgSim* sim, double* out8, int clear, gg_stream_t stream) {

@@ -23,6 +23,10 @@
 
 int gg_internal_fail(const char* fmt, const char* detail);
 void gg_internal_count_launches(int k);
+int gg_internal_record(int device, int n, int AD, int ED, int NU, float* traj, int32_t* ever, int t, int horizon, const float* action,
+                       const float* obs_agent, const float* obs_env, const float* reward, gg_stream_t stream);
+int gg_internal_export(int device, int n, int stride, int F, int32_t** slot, const float* traj, const int32_t* ever, int horizon, float* out,
+                       int32_t* out_env_ids, int32_t* out_count, gg_stream_t stream);
 
 namespace {
 
@@ -282,11 +286,25 @@ __global__ void __launch_bounds__(32 * kSolveWarps) stack_solve_kernel(const __g
     BufT& B = *reinterpret_cast<BufT*>(base + sizeof(InT));
     const int count = A.coop_ctr[0];
     WarpDev wc{lane};
+#ifdef GG_SOLVE_LOCKSTEP
+    __shared__ int s_base;
+#endif
     for (;;) {
         int k = 0;
+#ifdef GG_SOLVE_LOCKSTEP
+        // the warps of a block start their envs together: the solver is one long instruction stream executed about once per env,
+        // so warps in the same phase share the instruction cache lines they pull in
+        __syncthreads();
+        if (threadIdx.x == 0) s_base = atomicAdd(&A.coop_ctr[1], kSolveWarps);
+        __syncthreads();
+        if (s_base >= count) break;                               // block-uniform
+        k = s_base + warp;
+        if (k >= count) continue;
+#else
         if (lane == 0) k = atomicAdd(&A.coop_ctr[1], 1);
         k = __shfl_sync(kFullMask, k, 0);
         if (k >= count) break;
+#endif
         const int e = A.coop_list[k];
         {
             const float* src = A.work + (size_t)e * WF;
@@ -437,6 +455,7 @@ struct GgStackSim {
     uint8_t* done; uint8_t* flags; double* stats;            // library-owned
     float* work; float* acc; int32_t* ncon; int32_t* iters;
     int32_t* coop_list; int32_t* coop_ctr;
+    int32_t* slot;                                            // allocated on first gg_stack_export_successful
     uint32_t step_index;
     size_t solve_smem;
     int solve_blocks;                                         // persistent grid of the cooperative solver
@@ -550,7 +569,7 @@ int gg_stack_destroy(GgStackSim* s) {
     if (!s) return 0;
     cudaSetDevice(s->device);
     cudaFree(s->done); cudaFree(s->flags); cudaFree(s->stats); cudaFree(s->work); cudaFree(s->acc); cudaFree(s->ncon); cudaFree(s->iters);
-    cudaFree(s->coop_list); cudaFree(s->coop_ctr);
+    cudaFree(s->coop_list); cudaFree(s->coop_ctr); cudaFree(s->slot);
     delete s;
     return 0;
 }
@@ -622,6 +641,22 @@ int gg_stack_stats(GgStackSim* sim, double* out8, int clear, gg_stream_t stream)
     gg_internal_count_launches(1);
     SK_CUDA(cudaGetLastError());
     return 0;
+}
+
+int gg_stack_frame_dim(const GgStackSim* sim) { return sim ? gg_stack_agent_dim(sim) + GG_STACK_ENV_STATE_DIM + sim->nu + 1 : -1; }
+
+int gg_stack_record(GgStackSim* sim, float* traj, int32_t* ever, int t, int horizon, const float* action, const float* obs_agent,
+                    const float* obs_env, const float* reward, gg_stream_t stream) {
+    if (!sim) return gg_internal_fail("gg_stack_record: null argument%s", "");
+    return gg_internal_record(sim->device, sim->n, gg_stack_agent_dim(sim), GG_STACK_ENV_STATE_DIM, sim->nu, traj, ever, t, horizon, action,
+                              obs_agent, obs_env, reward, stream);
+}
+
+int gg_stack_export_successful(GgStackSim* sim, const float* traj, const int32_t* ever, int horizon, float* out, int32_t* out_env_ids,
+                               int32_t* out_count, gg_stream_t stream) {
+    if (!sim) return gg_internal_fail("gg_stack_export_successful: null argument%s", "");
+    return gg_internal_export(sim->device, sim->n, sim->stride, gg_stack_frame_dim(sim), &sim->slot, traj, ever, horizon, out, out_env_ids,
+                              out_count, stream);
 }
 
 int gg_stack_info(GgStackSim* sim, int32_t* ncon, int32_t* iters, gg_stream_t stream) {

@@ -31,13 +31,17 @@ class TrajectoryRecorder:
         if horizon <= 0:
             raise ValueError("horizon must be positive")
         self.sim, self.horizon = sim, int(horizon)
-        self.frame_dim = int(sim.lib.gg_frame_dim(sim._h))
+        # the stacking scenes (BatchedStackSim) have their own entry points and a 14-value environment_state
+        stack = hasattr(sim, "n_obj")
+        self._f_dim, self._f_rec, self._f_exp = ((sim.lib.gg_stack_frame_dim, sim.lib.gg_stack_record, sim.lib.gg_stack_export_successful)
+                                                 if stack else (sim.lib.gg_frame_dim, sim.lib.gg_record, sim.lib.gg_export_successful))
+        self.frame_dim = int(self._f_dim(sim._h))
         dev = sim.device
         self.traj = torch.zeros((self.horizon, sim.n_envs, self.frame_dim), dtype=torch.float32, device=dev)
         self.ever = torch.zeros(sim.n_envs, dtype=torch.int32, device=dev)
         self._out = None
         self._host = None
-        a, e, u = sim.agent_dim, 11, sim.nu
+        a, e, u = sim.agent_dim, (sim.env_dim if stack else 11), sim.nu
         self.slices = {"agent_pos": slice(0, a), "environment_state": slice(a, a + e), "action": slice(a + e, a + e + u),
                        "reward": slice(a + e + u, a + e + u + 1)}
 
@@ -48,7 +52,7 @@ class TrajectoryRecorder:
         """Store frame t: the simulator's current observation / reward buffers (the outputs of the step that consumed `action`)."""
         a = self.sim._as_action(action)
         s = self.sim
-        s._check(s.lib.gg_record(s._h, _ptr(self.traj), _ptr(self.ever), int(t), self.horizon, _ptr(a), _ptr(s.obs_agent), _ptr(s.obs_env),
+        s._check(self._f_rec(s._h, _ptr(self.traj), _ptr(self.ever), int(t), self.horizon, _ptr(a), _ptr(s.obs_agent), _ptr(s.obs_env),
                                  _ptr(s.reward), s._stream()))
 
     def export_successful(self):
@@ -60,7 +64,7 @@ class TrajectoryRecorder:
             self._out = (torch.empty((s.n_envs, self.horizon, self.frame_dim), dtype=torch.float32, device=s.device),
                          torch.empty(s.n_envs, dtype=torch.int32, device=s.device), torch.zeros(1, dtype=torch.int32, device=s.device))
         out, ids, cnt = self._out
-        s._check(s.lib.gg_export_successful(s._h, _ptr(self.traj), _ptr(self.ever), self.horizon, _ptr(out), _ptr(ids), _ptr(cnt), s._stream()))
+        s._check(self._f_exp(s._h, _ptr(self.traj), _ptr(self.ever), self.horizon, _ptr(out), _ptr(ids), _ptr(cnt), s._stream()))
         k = int(cnt.item())                       # the one host sync of the episode
         if self._host is None or self._host.shape[0] < k:
             # pinned landing buffer, grown geometrically and re-used across episodes (page-locking 100s of MB costs ~100 ms)

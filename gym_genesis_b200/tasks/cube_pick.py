@@ -36,11 +36,13 @@ class _Link:
     def __init__(self, task):
         self._task = task
 
-    def get_pos(self):
-        return self._task.sim.obs_agent[:, 0:3].clone()
+    def get_pos(self, envs_idx=None):
+        p = self._task.sim.obs_agent[:, 0:3]
+        return p.clone() if envs_idx is None else p[torch.as_tensor(envs_idx, device=p.device).long()]
 
-    def get_quat(self):
-        return self._task.sim.obs_agent[:, 3:7].clone()
+    def get_quat(self, envs_idx=None):
+        q = self._task.sim.obs_agent[:, 3:7]
+        return q.clone() if envs_idx is None else q[torch.as_tensor(envs_idx, device=q.device).long()]
 
 
 class _Robot:
@@ -50,8 +52,9 @@ class _Robot:
     def get_link(self, name):
         return self._task.eef
 
-    def get_dofs_position(self):
-        return self._task.sim.get_state()[0][:, : self._task.sim.nu]
+    def get_dofs_position(self, envs_idx=None):
+        q = self._task.sim.get_state()[0][:, : self._task.sim.nu]
+        return q if envs_idx is None else q[torch.as_tensor(envs_idx, device=q.device).long()]
 
     get_qpos = get_dofs_position
 

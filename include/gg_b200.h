@@ -231,6 +231,13 @@ int gg_stack_get_state(GgStackSim* sim, float* q, float* qd, float* qacc, gg_str
 int gg_stack_set_state(GgStackSim* sim, const float* q, const float* qd, const float* qacc, gg_stream_t stream);
 int gg_stack_observe(GgStackSim* sim, float* obs_agent, float* obs_env, float* reward, uint8_t* terminated, gg_stream_t stream);
 int gg_stack_stats(GgStackSim* sim, double* out8, int clear, gg_stream_t stream);
+/* trajectory store of the stacking collectors (examples/franka/stack_cube_state.py, examples/so_101/collect_task_stack_cube_batch.py):
+ * same contract as gg_record / gg_export_successful with F = gg_stack_frame_dim() = agent_dim + 14 + n_dof + 1 */
+int gg_stack_frame_dim(const GgStackSim* sim);
+int gg_stack_record(GgStackSim* sim, float* traj, int32_t* ever, int t, int horizon, const float* action, const float* obs_agent,
+                    const float* obs_env, const float* reward, gg_stream_t stream);
+int gg_stack_export_successful(GgStackSim* sim, const float* traj, const int32_t* ever, int horizon, float* out, int32_t* out_env_ids,
+                               int32_t* out_count, gg_stream_t stream);
 /* per-env diagnostics of the last step (DEVICE int32[n_envs] each, nullable): contacts, Newton iterations */
 int gg_stack_info(GgStackSim* sim, int32_t* ncon, int32_t* iters, gg_stream_t stream);
 

@@ -110,3 +110,39 @@ def test_device_recorder_matches_reference_collector(robot, n, lift):
     with pytest.raises(Exception):
         rec.record(T, home.repeat(n, 1))
     sim.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("robot", ["franka", "so101"])
+def test_device_recorder_stacking_scenes(robot):
+    """The same store for the stacking tasks (gg_stack_record / gg_stack_export_successful): 14-value environment_state, agent_pos of
+    9 (Franka: eef pose + fingers) or 6 (SO-101: joint positions) values."""
+    from gym_genesis_b200.model import get_model
+    from gym_genesis_b200.recorder import TrajectoryRecorder
+    from gym_genesis_b200.sim import BatchedStackSim
+    m = get_model(robot, "cube_stack")
+    n, T = 300, 8
+    sim = BatchedStackSim(m, n, seed=2)
+    rec = TrajectoryRecorder(sim, T)
+    assert rec.frame_dim == sim.agent_dim + 14 + sim.nu + 1 and sim.agent_dim == (9 if robot == "franka" else 6)
+    sim.reset(None, None)
+    q, qd, qa = sim.get_state()
+    rng = np.random.RandomState(1)
+    up = torch.as_tensor(rng.rand(n) < 0.25).to(sim.device)            # put cube_1 on top of cube_2 in a quarter of the envs
+    nu = sim.nu
+    q[up, nu:nu + 3] = q[up, nu + 7:nu + 10] + torch.tensor([0.0, 0.0, 0.0402], device=sim.device)
+    sim.set_state(q, qd, qa)
+    rec.begin_episode()
+    ag, en, ac, rw = [], [], [], []
+    home = torch.as_tensor(m.home_q, dtype=torch.float32, device=sim.device)
+    for t in range(T):
+        action = (home + 0.05 * torch.randn((n, nu), device=sim.device)).contiguous()
+        sim.step(action)
+        rec.record(t, action)
+        ag.append(sim.obs_agent.cpu().numpy()); en.append(sim.obs_env.cpu().numpy()); ac.append(action.cpu().numpy()); rw.append(sim.reward.cpu().numpy())
+    eps_ref, ids_ref = reference_collect(ag, en, ac, rw)
+    frames, env_ids = rec.export_successful()
+    assert np.array_equal(env_ids.numpy(), ids_ref) and 0 < len(ids_ref) < n
+    assert frames.shape == eps_ref.shape and np.array_equal(frames.numpy(), eps_ref)
+    assert set(ids_ref.tolist()) >= set(np.nonzero(up.cpu().numpy())[0].tolist()[:5])
+    sim.close()
