@@ -23,6 +23,9 @@ from gym_genesis_b200.recorder import LeRobotWriter, TrajectoryRecorder, write_l
 
 STAGES = ["hover", "grasp", "lift", "place", "release"]
 GRIP_OPEN, GRIP_CLOSED = 0.04, -0.02
+# way-points per stage (8 for the straight moves, 4 + 4 + 3 via the hover point) -> 80 // (n - 1) actions per segment (:84-91)
+N_WP = {"hover": 8, "grasp": 8, "lift": 8, "place": 11, "release": 11}
+HORIZON = sum((80 // (N_WP[s] - 1)) * (N_WP[s] - 1) for s in STAGES)
 
 
 def expert_policy(robot, obs, stage):
@@ -83,7 +86,7 @@ def main():
     args = ap.parse_args()
     env = gym.make("gym_genesis/CubeStack-v0", enable_pixels=False, robot="franka", num_envs=args.num_envs).unwrapped
     sim = env._env.sim
-    rec = None
+    rec = TrajectoryRecorder(sim, horizon=HORIZON)
     writer = LeRobotWriter(args.out, fps=60, robot_type="franka")
     for ep in range(args.episodes):
         t0 = time.perf_counter()
@@ -91,8 +94,6 @@ def main():
         t = 0
         for stage in STAGES:
             path = expert_policy(env.get_robot(), obs, stage)
-            if rec is None:
-                rec = TrajectoryRecorder(sim, horizon=len(path) * len(STAGES))
             if t == 0:
                 rec.begin_episode()
             for action in path:
