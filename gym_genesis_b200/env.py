@@ -12,7 +12,7 @@ import numpy as np
 import torch
 
 from .gym_api import gym
-from .tasks import FrankaCubePickBatch, FrankaCubeStackEmptyBatch, So101CubePickBatch, So101CubeStackBatch
+from .tasks import FrankaCubePickBatch, FrankaCubeStackEmptyBatch, So101CubePickBatch, So101CubeStackBatch, So101CubeStackOne
 
 
 class GenesisEnv(gym.Env):
@@ -104,6 +104,7 @@ class GenesisEnv(gym.Env):
             ("so101", "cube_pick", True): So101CubePickBatch,
             ("franka", "cube_stack", True): FrankaCubeStackEmptyBatch,
             ("so101", "cube_stack", True): So101CubeStackBatch,
+            ("so101", "cube_stack", False): So101CubeStackOne,       # num_envs = 0: unbatched shapes (env.py:114)
         }
         key = (self.robot, task_name, self.num_envs > 0)
         if key not in task_map:

@@ -139,3 +139,45 @@ class So101CubeStackBatch(FrankaCubeStackEmptyBatch):
             out[:, k, 0] = self._random.uniform(xlo, xhi, size=(B,))
             out[:, k, 1] = self._random.uniform(ylo, yhi, size=(B,))
         return out
+
+
+class So101CubeStackOne:
+    """Unbatched SO-101 stacking task (`gym_genesis/tasks/so101/cube_stack.py`, selected by `num_envs=0`, env.py:114,120): the same
+    scene, reset stream (scalar draws: one x / y per cube, `:66-93` -- identical to the batched stream at B = 1), reward and
+    observations with the env dimension dropped: agent_pos (6,), environment_state (14,), scalar reward."""
+
+    def __init__(self, enable_pixels, observation_height, observation_width, num_envs, env_spacing, camera_capture_mode,
+                 strip_environment_state, **sim_kwargs):
+        self._b = So101CubeStackBatch(enable_pixels, observation_height, observation_width, 1, env_spacing, camera_capture_mode,
+                                      strip_environment_state, **sim_kwargs)
+        self.num_envs = 0
+        for name in ("observation_space", "action_space", "scene", "sim", "model", "robot", "eef", "cube", "cube_1", "cube_2",
+                     "distractor_cubes", "motors_dof", "fingers_dof", "enable_pixels"):
+            setattr(self, name, getattr(self._b, name))
+
+    @property
+    def so_101(self):
+        return self._b.robot
+
+    def seed(self, seed):
+        self._b.seed(seed)
+
+    def _squeeze(self, obs):
+        return {k: v[0] for k, v in obs.items()}
+
+    def reset(self, mask=None):
+        return self._squeeze(self._b.reset(None))
+
+    def step(self, action, reset_mask=None):
+        a = torch.as_tensor(action, dtype=torch.float32).reshape(1, -1)
+        _, reward, _, obs = self._b.step(a)
+        return None, reward[0], None, self._squeeze(obs)
+
+    def compute_reward(self):
+        return self._b.compute_reward()[0]
+
+    def get_obs(self):
+        return self._squeeze(self._b.get_obs())
+
+    def get_cams(self):
+        return self._b.get_cams()
