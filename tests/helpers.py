@@ -185,3 +185,28 @@ def stack_cluster_states(g, idx=(30, 36, 60, 80)):
         QD[r, 9:] = 0
         QA[r] = 0
     return tuple(f32(x).astype(np.float64) for x in (Q, QD, QA, T))
+
+
+def stack_pile_states(m, orc, n=12, steps=90, every=15, seed=7):
+    """Tumbling piles: the five cubes are dropped from 5-25 cm above one spot with random orientations and spins and the oracle
+    rolls the scene forward; the sampled states contain edge-edge and vertex-face cube-cube contacts, cubes resting on two others,
+    and cubes bouncing off the plane on one corner.  Returns float32-rounded (Q, QD, QA, T) stacked over the sample times."""
+    rng = np.random.default_rng(seed)
+    nu, K = m.nu, m.n_obj
+    Q, QD, QA = orc.new_state(n)
+    Q[:, :nu] = m.home_q
+    for k in range(K):
+        o = nu + 7 * k
+        Q[:, o:o + 2] = np.array([0.55, 0.0]) + rng.uniform(-0.03, 0.03, (n, 2))
+        Q[:, o + 2] = m.plane_z + 0.05 + 0.05 * k + rng.uniform(0, 0.01, n)
+        qq = rng.normal(size=(n, 4))
+        Q[:, o + 3:o + 7] = qq / np.linalg.norm(qq, axis=1, keepdims=True)
+        QD[:, nu + 6 * k:nu + 6 * k + 3] = rng.normal(0, 0.2, (n, 3))
+        QD[:, nu + 6 * k + 3:nu + 6 * k + 6] = rng.normal(0, 3.0, (n, 3))
+    T = np.tile(m.home_q, (n, 1))
+    out = []
+    for s in range(steps):
+        if s % every == every - 1:
+            out.append((f32(Q).astype(np.float64), f32(QD).astype(np.float64), f32(QA).astype(np.float64), T.copy()))
+        orc.step(Q, QD, QA, T, iterations=100, tol=1e-10)
+    return tuple(np.concatenate([o[i] for o in out]) for i in range(4))
