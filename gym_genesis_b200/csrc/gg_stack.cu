@@ -2,7 +2,7 @@
 // Replaces, for gym_genesis/tasks/franka/cube_stack.py:119-216, the Genesis calls of reset / step / compute_reward / get_obs.
 //
 // One env.step = three launches on the caller's stream (per-env pipeline in gg_stack.cuh):
-//   stack_prep_kernel    thread per env, 32 envs and two role warps per block.  Masked reset, robot dynamics, body-level broad phase (pads vs plane /
+//   stack_prep_kernel    thread per env, 32 envs and three role warps per block.  Masked reset, robot dynamics, body-level broad phase (pads vs plane /
 //                        cubes, cube vs cube); every body that can touch nothing but the plane is solved HERE in registers
 //                        (robot block with joint-limit rows, 6 x 6 cube blocks with <= 4 plane contacts).  The StackIn record of
 //                        each env (robot dynamics + object states) is transposed through shared memory and written env-major, so
@@ -147,18 +147,38 @@ __device__ __forceinline__ void store_objects(float* sp, size_t st, const gg::Ob
 }
 
 // ------------------------------------------------------------------------------------------------------------------ prep
-// Two role warps per 32 envs (lane = env): warp 0 ROBOT runs the robot half (dynamics, limit rows, robot-block solve), warp 1
-// CUBES the cube half (pad reach from its own walk of the pad-body chain, cube-cube reach, register solves of the isolated
-// cubes, reset spawn).  The halves are independent until the amask words are merged after one __syncthreads; running them side
-// by side halves the dependent chain of this latency-bound kernel and doubles its warps per SM.
+// Three role warps per 32 envs (lane = env), as in the CubePick step kernel: warp 0 ROBOT (CRBA, Cholesky, limit rows, robot-block
+// solve), warp 1 RNEA (bias forces + PD torque of the same chain, handed over through shared memory and named barrier 1), warp 2
+// CUBES (pad reach from its own walk of the pad-body chain, cube-cube reach, register solves of the isolated cubes, reset
+// spawn).  The pieces are independent until the amask words are merged after one __syncthreads; running them side by side cuts
+// the dependent chain of this latency-bound kernel and triples its warps per SM.
+__device__ __forceinline__ void sk_bar_sync(int id, int nthreads) {
+    __syncwarp();
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void sk_bar_arrive(int id, int nthreads) {
+    __threadfence_block();
+    __syncwarp();
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+template <int NU> struct FsShared {                               // ROBOT warp: wait for the RNEA warp, then read this lane's column
+    const float* col;                                             // fs[i] at col[i * 32]
+    __device__ __forceinline__ void operator()(float* fs) const {
+        sk_bar_sync(1, 64);
+#pragma unroll
+        for (int i = 0; i < NU; i++) fs[i] = col[i * 32];
+    }
+};
+
 template <int NA, int NF, bool FH, int K>
-__global__ void __launch_bounds__(64) stack_prep_kernel(const __grid_constant__ StackArgs A) {
-    constexpr int NU = NA + NF, NV = NU + 6 * K;
+__global__ void __launch_bounds__(96, 4) stack_prep_kernel(const __grid_constant__ StackArgs A) {
+    constexpr int NU = NA + NF;
     typedef gg::StackIn<NA, NF, K> InT;
     typedef Rows<NU, K> R;
     constexpr int WF = sizeof(InT) / sizeof(float);
     constexpr int WFP = WF | 1;                                   // odd row stride: lane = env writes are conflict free
     __shared__ float sm[32 * WFP];
+    __shared__ float s_fs[NU * 32];
     __shared__ unsigned s_rmask[32], s_cmask[32];
     __shared__ int s_rit[32], s_cit[32], s_cnc[32];
     const int lane = threadIdx.x & 31, role = threadIdx.x >> 5;
@@ -173,41 +193,56 @@ __global__ void __launch_bounds__(64) stack_prep_kernel(const __grid_constant__ 
     float* rec = sm + lane * WFP;
     InT& In = *reinterpret_cast<InT*>(rec);                       // row of the transposition buffer
 
-    // object states: both roles need the positions; CUBES owns the reset writes and the record fields
-    gg::ObjState<K> O;
-    if (do_reset) spawn_objects<K>(A, e, gid, (uint32_t)A.episode[e], true, O);
-    else load_objects<NU, K>(sp, st, O);
-
-    if (role == 0) {
+    if (role == 1) {
+        // ----------------------------------------------------------------------------------------------------------- RNEA
+        float q[NU], qd[NU], target[NU], fs[NU];
+#pragma unroll
+        for (int i = 0; i < NU; i++) {
+            const float lq = sp[(R::Q + i) * st], lqd = sp[(R::QD + i) * st];
+            q[i] = do_reset ? A.M.home_q[i] : lq; qd[i] = do_reset ? 0.f : lqd;
+        }
+        const bool use_action = A.mode == 0 && !do_reset;
+#pragma unroll
+        for (int i = 0; i < NU; i++) target[i] = use_action ? A.action[(size_t)e * NU + i] : A.M.home_q[i];
+        gg::robot_rnea<NA, NF, FH>(A.M, q, qd, target, fs);
+#pragma unroll
+        for (int i = 0; i < NU; i++) s_fs[i * 32 + lane] = fs[i];
+        sk_bar_arrive(1, 64);
+    } else if (role == 0) {
         // ---------------------------------------------------------------------------------------------------------- ROBOT
-        float q[NU], qd[NU], warm[NU], target[NU];
+        float q[NU], qd[NU], warm[NU];
 #pragma unroll
         for (int i = 0; i < NU; i++) {
             const float lq = sp[(R::Q + i) * st], lqd = sp[(R::QD + i) * st], lw = sp[(R::WARM + i) * st];
             q[i] = do_reset ? A.M.home_q[i] : lq; qd[i] = do_reset ? 0.f : lqd; warm[i] = do_reset ? 0.f : lw;
         }
-        if (do_reset && live) {
+        gg::V3 cpos[K];
+        if (do_reset) {
+            gg::ObjState<K> O;
+            spawn_objects<K>(A, e, gid, (uint32_t)A.episode[e], true, O);
 #pragma unroll
-            for (int i = 0; i < NU; i++) { sp[(R::Q + i) * st] = q[i]; sp[(R::QD + i) * st] = 0.f; sp[(R::WARM + i) * st] = 0.f; }
+            for (int k = 0; k < K; k++) cpos[k] = O.p[k];
+        } else {
+#pragma unroll
+            for (int k = 0; k < K; k++) {
+                const float* c = sp + (R::OBJ + 13 * k) * st;
+                cpos[k] = gg::mk(c[0], c[st], c[2 * st]);
+            }
         }
-        const bool use_action = A.mode == 0 && !do_reset;
-#pragma unroll
-        for (int i = 0; i < NU; i++) target[i] = use_action ? A.action[(size_t)e * NU + i] : A.M.home_q[i];
         int rit = 0;
-        s_rmask[lane] = gg::stack_prep_robot<NA, NF, FH, K>(A.M, q, qd, warm, target, O.p, A.iterations, A.tol, active && live, In.W, rit);
+        FsShared<NU> fsp{s_fs + lane};
+        s_rmask[lane] = gg::stack_prep_robot<NA, NF, FH, K>(A.M, q, qd, warm, cpos, A.iterations, A.tol, active && live, In.W, rit, fsp);
         s_rit[lane] = rit;
     } else {
         // ---------------------------------------------------------------------------------------------------------- CUBES
+        gg::ObjState<K> O;
+        if (do_reset) spawn_objects<K>(A, e, gid, (uint32_t)A.episode[e], true, O);
+        else load_objects<NU, K>(sp, st, O);
         if (do_reset) {
 #pragma unroll
             for (int k = 0; k < K; k++)
 #pragma unroll
                 for (int i = 0; i < 6; i++) In.warm_obj[k][i] = 0.f;
-            if (live) {
-                store_objects<NU, K>(sp, st, O);
-#pragma unroll
-                for (int i = 0; i < 6 * K; i++) sp[(R::WARM + NU + i) * st] = 0.f;
-            }
         } else {
 #pragma unroll
             for (int k = 0; k < K; k++)
@@ -233,9 +268,19 @@ __global__ void __launch_bounds__(64) stack_prep_kernel(const __grid_constant__ 
         int cit = 0, cnc = 0;
         s_cmask[lane] = gg::stack_prep_cubes<K>(A.M, O, In.warm_obj, pad_cubes, A.iterations, A.tol, active && live, In.aobj, cit, cnc);
         s_cit[lane] = cit; s_cnc[lane] = cnc;
+        if (do_reset && live) {
+            // the state of a reset env is rewritten only after every role has read what it needs (joint rows: below, by ROBOT)
+            store_objects<NU, K>(sp, st, O);
+#pragma unroll
+            for (int i = 0; i < 6 * K; i++) sp[(R::WARM + NU + i) * st] = 0.f;
+        }
     }
     __syncthreads();
     if (role == 0) {
+        if (do_reset && live) {
+#pragma unroll
+            for (int i = 0; i < NU; i++) { sp[(R::Q + i) * st] = A.M.home_q[i]; sp[(R::QD + i) * st] = 0.f; sp[(R::WARM + i) * st] = 0.f; }
+        }
         const unsigned amask = s_rmask[lane] | s_cmask[lane];
         const int iso_iters = s_rit[lane] > s_cit[lane] ? s_rit[lane] : s_cit[lane];
         In.W.amask = (float)amask; In.W.iso_iters = (float)iso_iters; In.W.iso_ncon = (float)s_cnc[lane];
@@ -257,10 +302,10 @@ __global__ void __launch_bounds__(64) stack_prep_kernel(const __grid_constant__ 
         }
     }
     __syncthreads();
-    // coalesced env-major copy of the block's records (both warps)
+    // coalesced env-major copy of the block's records (all three warps)
     const int nlive = min(32, A.n - blockIdx.x * 32);
     float* dst = A.work + (size_t)blockIdx.x * 32 * WF;
-    for (int r = role; r < nlive; r += 2)
+    for (int r = role; r < nlive; r += 3)
         for (int i = lane; i < WF; i += 32) dst[(size_t)r * WF + i] = sm[r * WFP + i];
 }
 
@@ -490,7 +535,7 @@ static int stack_launch(GgStackSim* sim, StackArgs& A, gg_stream_t stream) {
 template <int NA, int NF, bool FH, int K>
 static void stack_launch_t(GgStackSim* sim, const StackArgs& A, cudaStream_t s) {
     if (A.mode != 2) {
-        stack_prep_kernel<NA, NF, FH, K><<<(sim->n + 31) / 32, 64, 0, s>>>(A);
+        stack_prep_kernel<NA, NF, FH, K><<<(sim->n + 31) / 32, 96, 0, s>>>(A);
         const int need = (sim->n + kSolveWarps - 1) / kSolveWarps;
         stack_solve_kernel<NA, NF, FH, K><<<need < sim->solve_blocks ? need : sim->solve_blocks, 32 * kSolveWarps, sim->solve_smem, s>>>(A);
     }

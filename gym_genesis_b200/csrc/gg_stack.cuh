@@ -132,30 +132,40 @@ GG_HD void stack_pad_reach(const GgModel& M, const RobotDyn<NA, NF>& D, int K, c
     }
 }
 
-// The prep stage is two independent halves (the CUDA kernel runs them in two warps of the same block, lane = env):
-//   stack_prep_robot : robot dynamics, limit rows, pad reach, robot-block solve when no pad can touch anything -> In.W (all but the
-//                      amask / iso_* words), returns the robot's amask bits (bit 0 robot, bit 1 + k cube k within reach of a pad)
+// The prep stage is independent pieces (the CUDA kernel runs them in three role warps of the same block, lane = env):
+//   stack_prep_robot : CRBA, Cholesky, limit rows, pad reach, robot-block solve when no pad can touch anything -> In.W (all but the
+//                      amask / iso_* words), returns the robot's amask bits (bit 0 robot, bit 1 + k cube k within reach of a pad);
+//                      the bias / PD half of the dynamics pass (robot_rnea) arrives through the FSP functor
 //   stack_prep_cubes : cube-cube reach, register solves of the isolated cubes -> In.aobj, returns the cube bits and statistics
 // The pad reach is needed by both; the cube half recomputes it from the pad-body frames (robot_pad_frames, one chain walk).
-template <int NA, int NF, bool FH, int K>
-GG_HD unsigned stack_prep_robot(const GgModel& M, const float* q, const float* qd, const float* warm, const float* target, const V3* cube_pos,
-                                int iterations, float tol, bool active, StackWork<NA, NF>& W, int& rob_iters) {
+// FSP: provider of fs = clamp(PD) - damping qd - bias.  The host harness computes it in place (robot_rnea); the CUDA kernel's ROBOT
+// warp receives it from the RNEA warp, which walks the same chain concurrently (the two halves of the dynamics pass are independent).
+template <int NA, int NF, bool FH> struct FsInline {
+    const GgModel* M; const float* q; const float* qd; const float* target;
+    GG_HD void operator()(float* fs) const { robot_rnea<NA, NF, FH>(*M, q, qd, target, fs); }
+};
+
+template <int NA, int NF, bool FH, int K, class FSP>
+GG_HD unsigned stack_prep_robot(const GgModel& M, const float* q, const float* qd, const float* warm, const V3* cube_pos,
+                                int iterations, float tol, bool active, StackWork<NA, NF>& W, int& rob_iters, FSP& fsp) {
     constexpr int NU = NA + NF;
     RobotDyn<NA, NF> D;
-    robot_dynamics<NA, NF, FH>(M, q, qd, target, D);
-    float as[NU];
     {
-        float L[NU * (NU + 1) / 2], dinv[NU];
-#pragma unroll
-        for (int i = 0; i < NU * (NU + 1) / 2; i++) L[i] = D.Mt[i];
-        chol_packed<NU>(L, dinv);
-        chol_solve_packed<NU>(L, dinv, D.fs, as);
+        LinkStoreLocal<NA> ls;
+        robot_crba<NA, NF, FH>(M, q, D, ls);
     }
+    float L[NU * (NU + 1) / 2], dinv[NU];
+#pragma unroll
+    for (int i = 0; i < NU * (NU + 1) / 2; i++) L[i] = D.Mt[i];
+    chol_packed<NU>(L, dinv);
     float lsg[NU], laref[NU], lD[NU], a[NU];
     const int nlim = joint_limit_rows<NU>(M, q, qd, lsg, laref, lD);
     bool pad_plane; unsigned pad_cubes;
     stack_pad_reach<NA, NF>(M, D, K, cube_pos, pad_plane, pad_cubes);
     const unsigned rmask = ((pad_plane || pad_cubes != 0u) ? 1u : 0u) | (pad_cubes << 1);
+    float as[NU];
+    fsp(D.fs);
+    chol_solve_packed<NU>(L, dinv, D.fs, as);
     StepInfo ir; ir.ncon = 0; ir.iters = 0; ir.grad = 0.f;
 #pragma unroll
     for (int i = 0; i < NU; i++) a[i] = as[i];
@@ -228,7 +238,8 @@ template <int NA, int NF, bool FH, int K>
 GG_HD void stack_prep(const GgModel& M, const float* q, const float* qd, const float* warm, const float* target, const ObjState<K>& O,
                       int iterations, float tol, bool active, StackIn<NA, NF, K>& In) {
     int rob_iters, iso_iters, iso_ncon;
-    const unsigned rmask = stack_prep_robot<NA, NF, FH, K>(M, q, qd, warm, target, O.p, iterations, tol, active, In.W, rob_iters);
+    FsInline<NA, NF, FH> fsp{&M, q, qd, target};
+    const unsigned rmask = stack_prep_robot<NA, NF, FH, K>(M, q, qd, warm, O.p, iterations, tol, active, In.W, rob_iters, fsp);
     const unsigned cmask = stack_prep_cubes<K>(M, O, In.warm_obj, rmask >> 1, iterations, tol, active, In.aobj, iso_iters, iso_ncon);
     In.W.amask = (float)(rmask | cmask);
     In.W.iso_iters = (float)(rob_iters > iso_iters ? rob_iters : iso_iters);
