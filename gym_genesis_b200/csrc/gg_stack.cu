@@ -7,9 +7,9 @@
 //                        (robot block with joint-limit rows, 6 x 6 cube blocks with <= 4 plane contacts).  The StackIn record of
 //                        each env (robot dynamics + object states) is transposed through shared memory and written env-major, so
 //                        that both this kernel's stores and the solver's loads are coalesced.
-//   stack_solve_kernel   WARP per env that has bodies in reach of each other, 4 envs per block, ~23 KB of dynamic shared memory
-//                        per warp (contact table, pair stiffness, packed Hessian of the active dofs).  Accelerations go to a
-//                        [dof][env] slab.
+//   stack_solve_kernel   persistent warps drain the compacted list of envs that have bodies in reach of each other; one WARP per
+//                        env, 4 warps per block, ~23 KB of dynamic shared memory per warp (contact table, pair stiffness, packed
+//                        Hessian of the active dofs).  Accelerations go to a [dof][env] slab.
 //   stack_finish_kernel  thread per env.  Integration, observations, reward / flags, counters, statistics.
 // The records and the slab (22 MB at 16384 envs) stay L2 resident between the three kernels.
 #include <cuda_runtime.h>
