@@ -387,3 +387,50 @@ def test_so101_stack_unbatched_variant(so):
     o2, reward, terminated, truncated, info = env.unwrapped.step(a)
     assert o2["agent_pos"].shape == (6,) and reward.dim() == 0
     env.close(); ref.close()
+
+
+def test_sharding_invariance(Sim, sm):
+    """Rank r of G owns global envs [r n, (r + 1) n) (`first_env_id`): spawn draws and Bernoulli resets are keyed by the GLOBAL env
+    id, so two shards of n envs reproduce one simulator of 2 n envs bit for bit (no collective on the step path)."""
+    n = 96
+    kw = dict(auto_reset=True, reset_prob=0.05, seed=77)
+    whole = Sim(sm, 2 * n, **kw)
+    parts = [Sim(sm, n, first_env_id=r * n, **kw) for r in range(2)]
+    g = torch.Generator(device="cuda").manual_seed(1)
+    home = torch.as_tensor(f32(FRANKA_HOME), device="cuda")
+    for s in [whole] + parts:
+        s.reset(None, None)
+    for _ in range(12):
+        a = home + (torch.rand((2 * n, 9), device="cuda", generator=g) - 0.5) * 0.5
+        whole.step(a)
+        for r in range(2):
+            parts[r].step(a[r * n:(r + 1) * n].contiguous())
+    qw, qdw, _ = whole.get_state()
+    for r in range(2):
+        q, qd, _ = parts[r].get_state()
+        assert torch.equal(q, qw[r * n:(r + 1) * n]) and torch.equal(qd, qdw[r * n:(r + 1) * n])
+        assert torch.equal(parts[r].episode, whole.episode[r * n:(r + 1) * n])
+        assert torch.equal(parts[r].obs_env, whole.obs_env[r * n:(r + 1) * n])
+    assert whole.episode.max().item() > 1                     # Bernoulli resets did happen
+
+
+def test_so101_stack_rollout(Sim, so):
+    m, orc = so
+    n = 16
+    rng = np.random.default_rng(9)
+    xy = np.zeros((n, 5, 2), np.float32)
+    for k, (xlo, xhi, ylo, yhi) in enumerate(m.obj_spawn):
+        xy[:, k, 0] = rng.uniform(xlo, xhi, n); xy[:, k, 1] = rng.uniform(ylo, yhi, n)
+    sim = Sim(m, n)
+    sim.reset(None, xy)
+    q, qd, qa = (_np(t) for t in sim.get_state())
+    tgt = np.tile(m.home_q, (n, 1))
+    for _ in range(60):
+        tgt = tgt + rng.normal(0, 0.01, tgt.shape)
+        t32 = f32(tgt)
+        sim.step(torch.as_tensor(t32))
+        orc.step(q, qd, qa, t32.astype(np.float64), iterations=100, tol=1e-10)
+    qg = _np(sim.get_state()[0])
+    pos_cols = list(range(6)) + [6 + 7 * k + c for k in range(5) for c in range(3)]
+    err = np.abs(qg[:, pos_cols] - q[:, pos_cols]).max()
+    assert err < ROLLOUT_POS_TOL, err
