@@ -135,6 +135,7 @@ class BatchedSim:
                                       self._host["truncated"].data_ptr(), 1)
             self._hio_ref = C.byref(self._hio)
             self._out_ptrs = tuple(_ptr(t) for t in (self.obs_agent, self.obs_env, self.reward, self.terminated, self.truncated))
+            self._pinned_ok = {}
         return self._host
 
     def step_host(self, action, reset_mask=None, wait=True):
@@ -143,15 +144,22 @@ class BatchedSim:
         a pinned staging buffer.  Returns pinned CPU tensors (reward, terminated, truncated) the kernel has written directly;
         with wait=True (default) they are valid on return.  Observations stay on the device (obs_agent / obs_env)."""
         h = self._host_buffers()
-        if tuple(getattr(action, "shape", ())) != (self.n_envs, self.nu):
-            raise ValueError(f"action must have shape ({self.n_envs}, {self.nu}), got {tuple(getattr(action, 'shape', ()))}")
-        if isinstance(action, torch.Tensor) and action.device.type == "cpu" and action.dtype == torch.float32 \
-                and action.is_contiguous() and action.is_pinned():
+        # tensors that passed the checks once are recognised by (object id, data pointer): `is_pinned()` is a driver query
+        key = (id(action), action.data_ptr()) if isinstance(action, torch.Tensor) else None
+        if key is not None and key in self._pinned_ok:
             a = action
         else:
-            a = h["action"]
-            a.copy_(torch.as_tensor(np.asarray(action) if not isinstance(action, torch.Tensor) else action, dtype=torch.float32))
-        m = self._as_mask(reset_mask)
+            if tuple(getattr(action, "shape", ())) != (self.n_envs, self.nu):
+                raise ValueError(f"action must have shape ({self.n_envs}, {self.nu}), got {tuple(getattr(action, 'shape', ()))}")
+            if isinstance(action, torch.Tensor) and action.device.type == "cpu" and action.dtype == torch.float32 \
+                    and action.is_contiguous() and action.is_pinned():
+                a = action
+                if len(self._pinned_ok) < 64:
+                    self._pinned_ok[key] = action          # keeps the tensor alive, so the id cannot be recycled
+            else:
+                a = h["action"]
+                a.copy_(torch.as_tensor(np.asarray(action) if not isinstance(action, torch.Tensor) else action, dtype=torch.float32))
+        m = None if reset_mask is None else self._as_mask(reset_mask)
         self._last_action = a
         self._hio.action = a.data_ptr()
         self._hio.wait = 1 if wait else 0
