@@ -402,6 +402,24 @@ def run_gpu(args):
                          "value": n / (tr.mean() * 1e-3), "unit": "env-steps/s", "ms_per_step": float(tr.mean()),
                          "mean_contacts": sr[7] / max(sr[0], 1), "success_rate": float(simr.reward.mean().item())}}
         simr.close()
+        # end to end through the gymnasium surface with a host-resident policy (zero-copy pinned actions in, reward / flags out)
+        envd = gym.make("gym_genesis/CubeStack-v0", robot="franka", num_envs=n, device=dev, auto_reset=True, reset_prob=1.0 / 200,
+                        seed=args.seed, first_env_id=rank * n, host_io=True).unwrapped
+        envd.reset(seed=args.seed)
+        hd = [ad[k].cpu().pin_memory() for k in range(4)]
+        for k in range(5):
+            envd.step(hd[k % 4])
+        d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        chk = 0.0
+        d0.record()
+        for k in range(200):
+            obs, reward, terminated, truncated, info = envd.step(hd[k % 4])
+            chk += float(reward[0]) + float(terminated[-1])
+        d1.record()
+        torch.cuda.synchronize(dev)
+        wd["e2e"] = {"value": n * 200 / (d0.elapsed_time(d1) * 1e-3), "unit": "env-steps/s", "h2d_bytes_per_step": n * 9 * 4,
+                     "d2h_bytes_per_step": n * 4 + 2 * n, "api": "gym.make('gym_genesis/CubeStack-v0', robot='franka', host_io=True).unwrapped.step(pinned host action)"}
+        envd.close()
 
     # ---- BASELINE.json configs[3]: SO-101 cube pick (6 hinge dofs), same shape of workload ----
     c4 = None

@@ -234,7 +234,8 @@ EXPORTS = ["gg_last_error", "gg_version", "gg_create", "gg_destroy", "gg_configu
            "gg_ik", "gg_ik_defaults", "gg_frame_dim", "gg_record", "gg_export_successful",
            "gg_stack_create", "gg_stack_destroy", "gg_stack_configure", "gg_stack_state_rows", "gg_stack_state_stride",
            "gg_stack_bind_state", "gg_stack_step", "gg_stack_reset", "gg_stack_get_state", "gg_stack_set_state", "gg_stack_observe",
-           "gg_stack_stats", "gg_stack_info", "gg_stack_agent_dim", "gg_stack_frame_dim", "gg_stack_record", "gg_stack_export_successful"]
+           "gg_stack_stats", "gg_stack_info", "gg_stack_agent_dim", "gg_stack_frame_dim", "gg_stack_record", "gg_stack_export_successful",
+           "gg_stack_step_host"]
 
 _lib = None
 
@@ -285,6 +286,7 @@ def load_library():
     lib.gg_stack_stats.argtypes = [vp, vp, C.c_int, vp]
     lib.gg_stack_info.argtypes = [vp, vp, vp, vp]
     lib.gg_stack_agent_dim.argtypes = [vp]
+    lib.gg_stack_step_host.argtypes = [vp, C.POINTER(GgHostIO)] + [vp] * 7
     lib.gg_stack_frame_dim.argtypes = [vp]
     lib.gg_stack_record.argtypes = [vp, vp, vp, C.c_int, C.c_int, vp, vp, vp, vp, vp]
     lib.gg_stack_export_successful.argtypes = [vp, vp, vp, C.c_int, vp, vp, vp, vp]

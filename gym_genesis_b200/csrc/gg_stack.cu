@@ -72,6 +72,7 @@ struct StackArgs {
     const float* action; float* obs_agent; float* obs_env; float* reward;
     uint8_t* terminated; uint8_t* truncated;
     const uint8_t* reset_mask; const float* obj_xy;
+    float* reward_host; uint8_t* terminated_host; uint8_t* truncated_host;   // nullable pinned-host mirrors (gg_stack_step_host)
     int mode;                 // 0 = env.step, 1 = reset (+ settle) of masked envs, 2 = observe only
     int iterations; float tol;
     int auto_reset, time_limit; float reset_prob;
@@ -432,6 +433,9 @@ __global__ void __launch_bounds__(128) stack_finish_kernel(const __grid_constant
         if (A.reward) A.reward[e] = rew;
         if (A.terminated) A.terminated[e] = succ ? 1 : 0;
         if (A.truncated) A.truncated[e] = trunc ? 1 : 0;
+        if (A.reward_host) A.reward_host[e] = rew;
+        if (A.terminated_host) A.terminated_host[e] = succ ? 1 : 0;
+        if (A.truncated_host) A.truncated_host[e] = trunc ? 1 : 0;
         if (A.mode != 2) {
             A.done[e] = (succ || trunc) ? 1 : 0;
             if (active) {
@@ -502,6 +506,8 @@ struct GgStackSim {
     int32_t* coop_list; int32_t* coop_ctr;
     int32_t* slot;                                            // allocated on first gg_stack_export_successful
     uint32_t step_index;
+    static constexpr int kPinCache = 16;
+    const void* pin_ok[kPinCache]; int pin_next;             // pointers already verified as pinned host memory
     size_t solve_smem;
     int solve_blocks;                                         // persistent grid of the cooperative solver
 };
@@ -647,6 +653,39 @@ int gg_stack_step(GgStackSim* sim, const float* action, float* obs_agent, float*
     const int rc = stack_launch(sim, A, stream);
     sim->step_index++;
     return rc;
+}
+
+static bool stack_host_ptr(const void* p) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeManaged;
+}
+
+int gg_stack_step_host(GgStackSim* sim, const GgHostIO* io, float* obs_agent, float* obs_env, float* reward, uint8_t* terminated,
+                       uint8_t* truncated, const uint8_t* reset_mask, gg_stream_t stream) {
+    if (!sim || !io || !io->action || !obs_agent || !obs_env) return gg_internal_fail("gg_stack_step_host: null argument%s", "");
+    // the answer of the driver query is cached per pointer so that the steady-state step pays none
+    const void* ptrs[4] = {io->action, io->reward, io->terminated, io->truncated};
+    for (int k = 0; k < 4; k++) {
+        if (!ptrs[k]) continue;
+        bool known = false;
+        for (int i = 0; i < GgStackSim::kPinCache; i++) known = known || sim->pin_ok[i] == ptrs[k];
+        if (!known) {
+            if (!stack_host_ptr(ptrs[k])) return gg_internal_fail("gg_stack_step_host: action / mirrors must be page-locked (pinned) host memory%s", "");
+            sim->pin_ok[sim->pin_next] = ptrs[k];
+            sim->pin_next = (sim->pin_next + 1) % GgStackSim::kPinCache;
+        }
+    }
+    StackArgs A;
+    memset(&A, 0, sizeof(A));
+    A.action = io->action; A.obs_agent = obs_agent; A.obs_env = obs_env; A.reward = reward; A.terminated = terminated;
+    A.truncated = truncated; A.reset_mask = reset_mask; A.mode = 0;
+    A.reward_host = io->reward; A.terminated_host = io->terminated; A.truncated_host = io->truncated;
+    const int rc = stack_launch(sim, A, stream);
+    sim->step_index++;
+    if (rc != 0) return rc;
+    if (io->wait) SK_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    return 0;
 }
 
 int gg_stack_reset(GgStackSim* sim, const uint8_t* mask, const float* obj_xy, float* obs_agent, float* obs_env, gg_stream_t stream) {

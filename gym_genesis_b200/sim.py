@@ -163,10 +163,13 @@ class BatchedSim:
         self._last_action = a
         self._hio.action = a.data_ptr()
         self._hio.wait = 1 if wait else 0
-        rc = self.lib.gg_step_host(self._h, self._hio_ref, *self._out_ptrs, _ptr(m), self._stream())
+        rc = self._step_host_fn()(self._h, self._hio_ref, *self._out_ptrs, _ptr(m), self._stream())
         if rc != 0:
             self._check(rc)
         return h["reward"], h["terminated"], h["truncated"]
+
+    def _step_host_fn(self):
+        return self.lib.gg_step_host
 
     def reset(self, mask=None, cube_xy=None):
         m = self._as_mask(mask)
@@ -328,8 +331,8 @@ class BatchedStackSim(BatchedSim):
         self._check(self.lib.gg_stack_step(self._h, _ptr(a), _ptr(self.obs_agent), _ptr(self.obs_env), _ptr(self.reward),
                                            _ptr(self.terminated), _ptr(self.truncated), _ptr(m), self._stream()))
 
-    def step_host(self, action, reset_mask=None, wait=True):
-        raise NotImplementedError("host_io (zero-copy host actions) is implemented for the CubePick path only")
+    def _step_host_fn(self):
+        return self.lib.gg_stack_step_host
 
     def reset(self, mask=None, obj_xy=None):
         m = self._as_mask(mask)

@@ -107,8 +107,6 @@ class FrankaCubeStackEmptyBatch(CubePickBatch):
             out[:, k, 1] = self._random.uniform(ylo, yhi, size=(B,))
         return out
 
-    def step_host(self, action, reset_mask=None):
-        raise NotImplementedError("host_io is implemented for the CubePick path only")
 
 
 class So101CubeStackBatch(FrankaCubeStackEmptyBatch):

@@ -223,6 +223,10 @@ int gg_stack_bind_state(GgStackSim* sim, float* state, int32_t* step_count, int3
 int gg_stack_agent_dim(const GgStackSim* sim);
 int gg_stack_step(GgStackSim* sim, const float* action, float* obs_agent, float* obs_env, float* reward, uint8_t* terminated,
                   uint8_t* truncated, const uint8_t* reset_mask, gg_stream_t stream);
+/* Host-resident I/O, same contract as gg_step_host: the prep kernel reads the pinned (n_envs, n_dof) action batch in place over
+ * PCIe / C2C, the finish kernel writes reward / terminated / truncated into the nullable pinned mirrors; wait != 0 drains the stream. */
+int gg_stack_step_host(GgStackSim* sim, const GgHostIO* io, float* obs_agent, float* obs_env, float* reward, uint8_t* terminated,
+                       uint8_t* truncated, const uint8_t* reset_mask, gg_stream_t stream);
 /* obj_xy (nullable): (n_envs, n_obj, 2) explicit spawn positions (the reference's host RandomState stream, drawn per object:
  * all x then all y); NULL -> device Philox draw keyed by (cfg.seed, global env id, episode, object). */
 int gg_stack_reset(GgStackSim* sim, const uint8_t* mask, const float* obj_xy, float* obs_agent, float* obs_env, gg_stream_t stream);

@@ -434,3 +434,46 @@ def test_so101_stack_rollout(Sim, so):
     pos_cols = list(range(6)) + [6 + 7 * k + c for k in range(5) for c in range(3)]
     err = np.abs(qg[:, pos_cols] - q[:, pos_cols]).max()
     assert err < ROLLOUT_POS_TOL, err
+
+
+@pytest.mark.parametrize("robot", ["franka", "so101"])
+def test_step_host_zero_copy_is_bit_identical_to_device_step(Sim, robot):
+    """gg_stack_step_host (pinned host action read in place by the prep kernel, reward / flags mirrored into pinned host memory by
+    the finish kernel) against gg_stack_step with a device-resident action: bit-identical state, observations and flags."""
+    from gym_genesis_b200.model import get_model
+    m = get_model(robot, "cube_stack")
+    n = 1000
+    rng = np.random.default_rng(78)
+    a = Sim(m, n, seed=3, auto_reset=True, reset_prob=0.02, time_limit=True)
+    b = Sim(m, n, seed=3, auto_reset=True, reset_prob=0.02, time_limit=True)
+    a.reset(None, None); b.reset(None, None)
+    for k in range(10):
+        act = f32(np.tile(m.home_q, (n, 1)) + rng.uniform(-0.2, 0.2, (n, m.nu)))
+        a.step(torch.as_tensor(act, device=a.device))
+        pinned = torch.as_tensor(act).pin_memory() if k % 2 == 0 else act          # pinned: zero-copy; numpy: staged copy
+        rew, term, trunc = b.step_host(pinned)
+        assert torch.equal(rew, a.reward.cpu()) and torch.equal(term, a.terminated.cpu()) and torch.equal(trunc, a.truncated.cpu())
+        assert torch.equal(a.obs_agent, b.obs_agent) and torch.equal(a.obs_env, b.obs_env)
+    for x, y in zip(a.get_state(), b.get_state()):
+        assert torch.equal(x, y)
+    import ctypes as C
+    from gym_genesis_b200 import cabi
+    from gym_genesis_b200.sim import GgError
+    bad = torch.zeros((n, m.nu), dtype=torch.float32)                               # pageable host memory must be rejected
+    io = cabi.GgHostIO(bad.data_ptr(), 0, 0, 0, 1)
+    with pytest.raises(GgError, match="pinned"):
+        b._check(b.lib.gg_stack_step_host(b._h, C.byref(io), b.obs_agent.data_ptr(), b.obs_env.data_ptr(), None, None, None, None, b._stream()))
+
+
+def test_gym_surface_host_io_cube_stack():
+    import gym_genesis  # noqa: F401
+    from gym_genesis_b200.gym_api import gym
+    n = 64
+    env = gym.make("gym_genesis/CubeStack-v0", robot="franka", num_envs=n, host_io=True).unwrapped
+    obs, info = env.reset(seed=0)
+    act = np.tile(FRANKA_HOME.astype(np.float32), (n, 1))
+    obs, reward, terminated, truncated, info = env.step(act)                           # numpy action, as in the reference README
+    assert reward.device.type == "cpu" and reward.shape == (n,) and terminated.dtype == torch.bool and not truncated.any()
+    assert obs["agent_pos"].is_cuda and obs["environment_state"].shape == (n, 14)
+    assert torch.equal(reward, env._env.sim.reward.cpu())
+    env.close()
