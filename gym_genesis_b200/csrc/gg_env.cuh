@@ -1069,9 +1069,56 @@ GG_HD void collide_pads(const GgModel& M, const RobotDyn<NA, NF>& D, V3 cp, cons
     }
 }
 
+// exact box-plane reach of the pads of body b (lowest point of an oriented box: c.z - sum_i |R_zi| h_i), with a 1e-5 m margin so
+// that it stays conservative against the corner-by-corner arithmetic of plane_box.  Only evaluated when the body's bounding
+// sphere already reaches the plane: long pads (the SO-101 jaws) make that sphere test fire ten times more often than contact.
+GG_HD bool pads_reach_plane(const GgModel& M, int b, const M3& Rb, V3 pb) {
+    bool hit = false;
+    for (int g = 0; g < M.n_pads; g++) {
+        if (M.pad_body[g] != b) continue;
+        const V3 c = pb + mul(Rb, ld3(M.pad_pos[g]));
+        const M3 R = mmul(Rb, qmat(ldq(M.pad_quat[g])));
+        const V3 h = ld3(M.pad_half[g]);
+        const float ext = fabsf(R.c0.z) * h.x + fabsf(R.c1.z) * h.y + fabsf(R.c2.z) * h.z;
+        hit = hit || (c.z - ext <= M.plane_z + 1e-5f);
+    }
+    return hit;
+}
+
+// pads of body b against the cube, two conservative refinements of the sphere-sphere test:
+//   (1) distance from the cube centre to the pad box (closest point of an oriented box) against the cube's bounding-sphere radius
+//   (2) the six face axes of the separating-axis test (the nine edge-edge axes are skipped: a miss on any axis proves separation,
+//       so testing fewer axes only errs towards "may touch"); 1e-5 m margin against the narrow phase's own arithmetic
+GG_HD bool pads_reach_cube(const GgModel& M, int b, const M3& Rb, V3 pb, V3 cp, const M3& cR, V3 ch) {
+    const float rc = sqrtf(dot(ch, ch)) + 1e-5f;
+    bool hit = false;
+    for (int g = 0; g < M.n_pads; g++) {
+        if (M.pad_body[g] != b) continue;
+        const V3 c = pb + mul(Rb, ld3(M.pad_pos[g]));
+        const M3 R = mmul(Rb, qmat(ldq(M.pad_quat[g])));
+        const V3 h = ld3(M.pad_half[g]);
+        const V3 t = cp - c;
+        const V3 l = mulT(R, t);
+        const V3 e = mk(fmaxf(fabsf(l.x) - h.x, 0.f), fmaxf(fabsf(l.y) - h.y, 0.f), fmaxf(fabsf(l.z) - h.z, 0.f));
+        if (dot(e, e) > rc * rc) continue;
+        bool sep = false;
+#pragma unroll
+        for (int ax = 0; ax < 3; ax++) {
+            const V3 ua = col(R, ax), ub = col(cR, ax);
+            // pad face axis: extent of the pad = h[ax], extent of the cube = sum_j |ua . cR_j| ch_j
+            const float ra = comp(h, ax) + fabsf(dot(ua, cR.c0)) * ch.x + fabsf(dot(ua, cR.c1)) * ch.y + fabsf(dot(ua, cR.c2)) * ch.z;
+            sep = sep || (fabsf(dot(t, ua)) > ra + 1e-5f);
+            const float rb = comp(ch, ax) + fabsf(dot(ub, R.c0)) * h.x + fabsf(dot(ub, R.c1)) * h.y + fabsf(dot(ub, R.c2)) * h.z;
+            sep = sep || (fabsf(dot(t, ub)) > rb + 1e-5f);
+        }
+        hit = hit || !sep;
+    }
+    return hit;
+}
+
 // conservative body-level broad phase: does any pad-carrying body's bounding sphere reach the plane or the cube?
 template <int NA, int NF>
-GG_HD bool pads_may_touch(const GgModel& M, const RobotDyn<NA, NF>& D, V3 cp) {
+GG_HD bool pads_may_touch(const GgModel& M, const RobotDyn<NA, NF>& D, V3 cp, Q4 cq) {
     V3 ch = ld3(M.cube_half);
     const float rc = sqrtf(dot(ch, ch));
     bool any = false;
@@ -1082,7 +1129,10 @@ GG_HD bool pads_may_touch(const GgModel& M, const RobotDyn<NA, NF>& D, V3 cp) {
         V3 pb = b == 0 ? D.lp : D.fp[b == 0 ? 0 : b - 1];
         V3 c = pb + mul(Rb, ld3(M.pad_bound[b]));
         V3 d = c - cp;
-        any = any || (r >= 0.f && ((c.z - r <= M.plane_z) || (dot(d, d) <= (r + rc) * (r + rc))));
+        bool hit = false;
+        if (r >= 0.f && dot(d, d) <= (r + rc) * (r + rc)) hit = pads_reach_cube(M, b, Rb, pb, cp, qmat(cq), ch);   // rare: refine the sphere tests
+        if (r >= 0.f && !hit && c.z - r <= M.plane_z) hit = pads_reach_plane(M, b, Rb, pb);
+        any = any || hit;
     }
     return any;
 }
@@ -1244,7 +1294,7 @@ GG_HD void env_substep(const GgModel& M, EnvState<NA + NF>& s, const float* targ
     const int nlim = joint_limit_rows<NU>(M, s.q, s.qd, lsg, laref, lD);
 
     float a[NV];
-    if (!pads_may_touch<NA, NF>(M, D, s.cp)) {
+    if (!pads_may_touch<NA, NF>(M, D, s.cp, s.cq)) {
         // ---- decoupled fast path: robot block (limits only) and cube block (plane contacts only)
         StepInfo ir, ic;
         CubeConLocal cs;

@@ -447,7 +447,7 @@ __global__ void __launch_bounds__(kBlockThreads, GG_MINBLOCKS) step_kernel(const
                 for (int i = 0; i < NU; i++) q[i] = do_reset ? A.M.home_q[i] : sp[i * st];
                 gg::RobotDyn<NA, NF> D;
                 gg::robot_pad_frames<NA, NF, FH>(A.M, q, D);
-                coupled = live && gg::pads_may_touch<NA, NF>(A.M, D, cp);
+                coupled = live && gg::pads_may_touch<NA, NF>(A.M, D, cp, cq);
             }
             X.coupled[lane] = coupled ? 1 : 0;
             X.cube[0][lane] = cp.x; X.cube[1][lane] = cp.y; X.cube[2][lane] = cp.z;

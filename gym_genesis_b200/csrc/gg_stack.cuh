@@ -113,7 +113,7 @@ GG_HD float sk_dot6(const float* a, const float* b) {
 // ---------------------------------------------------------------------------------------------------------------------
 // conservative body-level broad phase: does any pad-carrying body's bounding sphere reach the plane / cube k?
 template <int NA, int NF>
-GG_HD void stack_pad_reach(const GgModel& M, const RobotDyn<NA, NF>& D, int K, const V3* cp, bool& plane, unsigned& cubes) {
+GG_HD void stack_pad_reach(const GgModel& M, const RobotDyn<NA, NF>& D, int K, const V3* cp, const Q4* cq, bool& plane, unsigned& cubes) {
     const V3 ch = ld3(M.cube_half);
     const float rc = sqrtf(dot(ch, ch));
     plane = false; cubes = 0u;
@@ -124,10 +124,10 @@ GG_HD void stack_pad_reach(const GgModel& M, const RobotDyn<NA, NF>& D, int K, c
         const M3& Rb = b == 0 ? D.lR : D.fR[b == 0 ? 0 : b - 1];
         const V3 pb = b == 0 ? D.lp : D.fp[b == 0 ? 0 : b - 1];
         const V3 c = pb + mul(Rb, ld3(M.pad_bound[b]));
-        plane = plane || (c.z - r <= M.plane_z);
+        if (!plane && c.z - r <= M.plane_z) plane = pads_reach_plane(M, b, Rb, pb);     // refine the sphere test (gg_env.cuh)
         for (int k = 0; k < K; k++) {
             const V3 d = c - cp[k];
-            if (dot(d, d) <= (r + rc) * (r + rc)) cubes |= 1u << k;
+            if (!((cubes >> k) & 1u) && dot(d, d) <= (r + rc) * (r + rc) && pads_reach_cube(M, b, Rb, pb, cp[k], qmat(cq[k]), ch)) cubes |= 1u << k;
         }
     }
 }
@@ -146,7 +146,7 @@ template <int NA, int NF, bool FH> struct FsInline {
 };
 
 template <int NA, int NF, bool FH, int K, class FSP>
-GG_HD unsigned stack_prep_robot(const GgModel& M, const float* q, const float* qd, const float* warm, const V3* cube_pos,
+GG_HD unsigned stack_prep_robot(const GgModel& M, const float* q, const float* qd, const float* warm, const V3* cube_pos, const Q4* cube_quat,
                                 int iterations, float tol, bool active, StackWork<NA, NF>& W, int& rob_iters, FSP& fsp) {
     constexpr int NU = NA + NF;
     RobotDyn<NA, NF> D;
@@ -161,7 +161,7 @@ GG_HD unsigned stack_prep_robot(const GgModel& M, const float* q, const float* q
     float lsg[NU], laref[NU], lD[NU], a[NU];
     const int nlim = joint_limit_rows<NU>(M, q, qd, lsg, laref, lD);
     bool pad_plane; unsigned pad_cubes;
-    stack_pad_reach<NA, NF>(M, D, K, cube_pos, pad_plane, pad_cubes);
+    stack_pad_reach<NA, NF>(M, D, K, cube_pos, cube_quat, pad_plane, pad_cubes);
     const unsigned rmask = ((pad_plane || pad_cubes != 0u) ? 1u : 0u) | (pad_cubes << 1);
     float as[NU];
     fsp(D.fs);
@@ -239,7 +239,7 @@ GG_HD void stack_prep(const GgModel& M, const float* q, const float* qd, const f
                       int iterations, float tol, bool active, StackIn<NA, NF, K>& In) {
     int rob_iters, iso_iters, iso_ncon;
     FsInline<NA, NF, FH> fsp{&M, q, qd, target};
-    const unsigned rmask = stack_prep_robot<NA, NF, FH, K>(M, q, qd, warm, O.p, iterations, tol, active, In.W, rob_iters, fsp);
+    const unsigned rmask = stack_prep_robot<NA, NF, FH, K>(M, q, qd, warm, O.p, O.q, iterations, tol, active, In.W, rob_iters, fsp);
     const unsigned cmask = stack_prep_cubes<K>(M, O, In.warm_obj, rmask >> 1, iterations, tol, active, In.aobj, iso_iters, iso_ncon);
     In.W.amask = (float)(rmask | cmask);
     In.W.iso_iters = (float)(rob_iters > iso_iters ? rob_iters : iso_iters);

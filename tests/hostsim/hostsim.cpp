@@ -73,12 +73,12 @@ extern "C" void hs_pads_may_touch(const GgModel* M, int n, const float* q, uint8
             const float* pq = q + (size_t)e * 16;
             gg::RobotDyn<7, 2> D;
             gg::robot_pad_frames<7, 2, false>(*M, pq, D);
-            out[e] = gg::pads_may_touch<7, 2>(*M, D, gg::mk(pq[9], pq[10], pq[11]));
+            out[e] = gg::pads_may_touch<7, 2>(*M, D, gg::mk(pq[9], pq[10], pq[11]), gg::mkq(pq[12], pq[13], pq[14], pq[15]));
         } else {
             const float* pq = q + (size_t)e * 13;
             gg::RobotDyn<5, 1> D;
             gg::robot_pad_frames<5, 1, true>(*M, pq, D);
-            out[e] = gg::pads_may_touch<5, 1>(*M, D, gg::mk(pq[6], pq[7], pq[8]));
+            out[e] = gg::pads_may_touch<5, 1>(*M, D, gg::mk(pq[6], pq[7], pq[8]), gg::mkq(pq[9], pq[10], pq[11], pq[12]));
         }
     }
 }

@@ -159,3 +159,40 @@ def test_scripted_grasp_rollout_open_loop(hostsim, gg, franka_model, oracle64):
     assert (ec < 5e-3).mean() >= 0.9                                                   # chaotic contact phases: most still agree at step 200
     ref = d["reward"].max(1) > 0
     assert (succ == ref).mean() >= 0.9 and 0.2 < ref.mean() < 0.8
+
+
+@pytest.mark.parametrize("robot", ["franka", "so101"])
+def test_pad_broad_phase_is_conservative(hostsim, robot, franka_model, so101_model, oracle64, so101_oracle64):
+    """The body-level broad phase (bounding spheres refined by sphere-vs-box, six face axes of the SAT and the exact box-plane reach)
+    may only err towards "may touch": whenever the oracle's narrow phase finds a pad contact, the flag is set.  Cubes are placed at
+    random poses within a few centimetres of the gripper, where the refinements actually decide."""
+    m, orc = (franka_model, oracle64) if robot == "franka" else (so101_model, so101_oracle64)
+    gg = cabi.compile_gg(m)
+    rng = np.random.default_rng(12)
+    n, nu = 3000, m.nu
+    Q = np.zeros((n, nu + 7))
+    Q[:, :nu] = m.home_q + rng.uniform(-0.5, 0.5, (n, nu))
+    lo, hi = np.array(list(gg.lim_lo)[:nu]), np.array(list(gg.lim_hi)[:nu])
+    Q[:, :nu] = np.clip(Q[:, :nu], lo, hi)
+    pad_geoms = [g for g in m.geoms if g.group == 0]
+    for k in range(n):
+        xp, xm = m.fk(m.full_q(Q[k, :nu]))
+        g = pad_geoms[rng.integers(len(pad_geoms))]
+        tip = xp[g.body] + xm[g.body] @ np.asarray(g.pos)
+        Q[k, nu:nu + 3] = tip + rng.uniform(-0.045, 0.045, 3)
+        if k % 3 == 0:
+            Q[k, nu + 2] = max(Q[k, nu + 2], m.plane_z + 0.0199)          # resting height: pad-plane and pad-cube both in play
+        qq = rng.normal(size=4)
+        Q[k, nu + 3:nu + 7] = qq / np.linalg.norm(qq)
+    Q = f32(Q).astype(np.float64)
+    flag = np.zeros(n, np.uint8)
+    hostsim.hs_pads_may_touch(C.byref(gg), n, _p(f32(Q)), _p(flag))
+    pad_bodies = {g.body for g in pad_geoms}
+    touching = np.zeros(n, bool)
+    for k in range(n):
+        c = orc.contacts(Q[k])
+        touching[k] = any(int(r[7]) in pad_bodies or int(r[8]) in pad_bodies for r in c)
+    assert touching.sum() > 100 and (~touching).sum() > 100
+    assert flag[touching].all(), int((~flag[touching].astype(bool)).sum())
+    # and it is a useful filter: a good share of the near misses is rejected
+    assert flag[~touching].mean() < 0.8
