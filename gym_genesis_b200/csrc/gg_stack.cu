@@ -171,6 +171,14 @@ template <int NU> struct FsShared {                               // ROBOT warp:
     }
 };
 
+template <int NA, int NF> struct RmaskShared {                    // ROBOT warp: the CUBES warp evaluated the pad reach for both roles
+    const unsigned* p;
+    __device__ __forceinline__ unsigned operator()(const gg::RobotDyn<NA, NF>&) const {
+        sk_bar_sync(2, 64);
+        return *p;
+    }
+};
+
 template <int NA, int NF, bool FH, int K>
 __global__ void __launch_bounds__(96, 4) stack_prep_kernel(const __grid_constant__ StackArgs A) {
     constexpr int NU = NA + NF;
@@ -217,24 +225,10 @@ __global__ void __launch_bounds__(96, 4) stack_prep_kernel(const __grid_constant
             const float lq = sp[(R::Q + i) * st], lqd = sp[(R::QD + i) * st], lw = sp[(R::WARM + i) * st];
             q[i] = do_reset ? A.M.home_q[i] : lq; qd[i] = do_reset ? 0.f : lqd; warm[i] = do_reset ? 0.f : lw;
         }
-        gg::V3 cpos[K];
-        gg::Q4 cquat[K];
-        if (do_reset) {
-            gg::ObjState<K> O;
-            spawn_objects<K>(A, e, gid, (uint32_t)A.episode[e], true, O);
-#pragma unroll
-            for (int k = 0; k < K; k++) { cpos[k] = O.p[k]; cquat[k] = O.q[k]; }
-        } else {
-#pragma unroll
-            for (int k = 0; k < K; k++) {
-                const float* c = sp + (R::OBJ + 13 * k) * st;
-                cpos[k] = gg::mk(c[0], c[st], c[2 * st]);
-                cquat[k] = gg::mkq(c[3 * st], c[4 * st], c[5 * st], c[6 * st]);
-            }
-        }
         int rit = 0;
         FsShared<NU> fsp{s_fs + lane};
-        s_rmask[lane] = gg::stack_prep_robot<NA, NF, FH, K>(A.M, q, qd, warm, cpos, cquat, A.iterations, A.tol, active && live, In.W, rit, fsp);
+        RmaskShared<NA, NF> rmp{s_rmask + lane};
+        gg::stack_prep_robot<NA, NF, FH, K>(A.M, q, qd, warm, A.iterations, A.tol, active && live, In.W, rit, fsp, rmp);
         s_rit[lane] = rit;
     } else {
         // ---------------------------------------------------------------------------------------------------------- CUBES
@@ -266,7 +260,9 @@ __global__ void __launch_bounds__(96, 4) stack_prep_kernel(const __grid_constant
             gg::RobotDyn<NA, NF> D;
             gg::robot_pad_frames<NA, NF, FH>(A.M, q, D);
             bool pad_plane;
-            gg::stack_pad_reach<NA, NF>(A.M, D, K, O.p, O.q, pad_plane, pad_cubes);
+            gg::stack_pad_reach<NA, NF, K>(A.M, D, O.p, O.q, pad_plane, pad_cubes);
+            s_rmask[lane] = ((pad_plane || pad_cubes != 0u) ? 1u : 0u) | (pad_cubes << 1);
+            sk_bar_arrive(2, 64);                                 // ROBOT picks the robot's amask bits up after its Cholesky
         }
         int cit = 0, cnc = 0;
         s_cmask[lane] = gg::stack_prep_cubes<K>(A.M, O, In.warm_obj, pad_cubes, A.iterations, A.tol, active && live, In.aobj, cit, cnc);

@@ -112,8 +112,8 @@ GG_HD float sk_dot6(const float* a, const float* b) {
 // stage 1: thread per env
 // ---------------------------------------------------------------------------------------------------------------------
 // conservative body-level broad phase: does any pad-carrying body's bounding sphere reach the plane / cube k?
-template <int NA, int NF>
-GG_HD void stack_pad_reach(const GgModel& M, const RobotDyn<NA, NF>& D, int K, const V3* cp, const Q4* cq, bool& plane, unsigned& cubes) {
+template <int NA, int NF, int K>
+GG_HD void stack_pad_reach(const GgModel& M, const RobotDyn<NA, NF>& D, const V3* cp, const Q4* cq, bool& plane, unsigned& cubes) {
     const V3 ch = ld3(M.cube_half);
     const float rc = sqrtf(dot(ch, ch));
     plane = false; cubes = 0u;
@@ -125,6 +125,7 @@ GG_HD void stack_pad_reach(const GgModel& M, const RobotDyn<NA, NF>& D, int K, c
         const V3 pb = b == 0 ? D.lp : D.fp[b == 0 ? 0 : b - 1];
         const V3 c = pb + mul(Rb, ld3(M.pad_bound[b]));
         if (!plane && c.z - r <= M.plane_z) plane = pads_reach_plane(M, b, Rb, pb);     // refine the sphere test (gg_env.cuh)
+#pragma unroll
         for (int k = 0; k < K; k++) {
             const V3 d = c - cp[k];
             if (!((cubes >> k) & 1u) && dot(d, d) <= (r + rc) * (r + rc) && pads_reach_cube(M, b, Rb, pb, cp[k], qmat(cq[k]), ch)) cubes |= 1u << k;
@@ -145,9 +146,21 @@ template <int NA, int NF, bool FH> struct FsInline {
     GG_HD void operator()(float* fs) const { robot_rnea<NA, NF, FH>(*M, q, qd, target, fs); }
 };
 
-template <int NA, int NF, bool FH, int K, class FSP>
-GG_HD unsigned stack_prep_robot(const GgModel& M, const float* q, const float* qd, const float* warm, const V3* cube_pos, const Q4* cube_quat,
-                                int iterations, float tol, bool active, StackWork<NA, NF>& W, int& rob_iters, FSP& fsp) {
+// RMP: provider of the robot's amask bits (bit 0: a pad may touch the plane or a cube, bit 1 + k: cube k within reach of a pad).
+// The host harness evaluates the pad reach in place from the frames of this pass; the CUBES warp of the CUDA kernel evaluates it
+// once for both roles (one source of truth: the two roles can never disagree about who is coupled) and hands it over.
+template <int NA, int NF, int K> struct RmaskInline {
+    const GgModel* M; const V3* cube_pos; const Q4* cube_quat;
+    GG_HD unsigned operator()(const RobotDyn<NA, NF>& D) const {
+        bool pad_plane; unsigned pad_cubes;
+        stack_pad_reach<NA, NF, K>(*M, D, cube_pos, cube_quat, pad_plane, pad_cubes);
+        return ((pad_plane || pad_cubes != 0u) ? 1u : 0u) | (pad_cubes << 1);
+    }
+};
+
+template <int NA, int NF, bool FH, int K, class FSP, class RMP>
+GG_HD unsigned stack_prep_robot(const GgModel& M, const float* q, const float* qd, const float* warm, int iterations, float tol, bool active,
+                                StackWork<NA, NF>& W, int& rob_iters, FSP& fsp, RMP& rmp) {
     constexpr int NU = NA + NF;
     RobotDyn<NA, NF> D;
     {
@@ -160,11 +173,9 @@ GG_HD unsigned stack_prep_robot(const GgModel& M, const float* q, const float* q
     chol_packed<NU>(L, dinv);
     float lsg[NU], laref[NU], lD[NU], a[NU];
     const int nlim = joint_limit_rows<NU>(M, q, qd, lsg, laref, lD);
-    bool pad_plane; unsigned pad_cubes;
-    stack_pad_reach<NA, NF>(M, D, K, cube_pos, cube_quat, pad_plane, pad_cubes);
-    const unsigned rmask = ((pad_plane || pad_cubes != 0u) ? 1u : 0u) | (pad_cubes << 1);
     float as[NU];
     fsp(D.fs);
+    const unsigned rmask = rmp(D);
     chol_solve_packed<NU>(L, dinv, D.fs, as);
     StepInfo ir; ir.ncon = 0; ir.iters = 0; ir.grad = 0.f;
 #pragma unroll
@@ -239,7 +250,8 @@ GG_HD void stack_prep(const GgModel& M, const float* q, const float* qd, const f
                       int iterations, float tol, bool active, StackIn<NA, NF, K>& In) {
     int rob_iters, iso_iters, iso_ncon;
     FsInline<NA, NF, FH> fsp{&M, q, qd, target};
-    const unsigned rmask = stack_prep_robot<NA, NF, FH, K>(M, q, qd, warm, O.p, O.q, iterations, tol, active, In.W, rob_iters, fsp);
+    RmaskInline<NA, NF, K> rmp{&M, O.p, O.q};
+    const unsigned rmask = stack_prep_robot<NA, NF, FH, K>(M, q, qd, warm, iterations, tol, active, In.W, rob_iters, fsp, rmp);
     const unsigned cmask = stack_prep_cubes<K>(M, O, In.warm_obj, rmask >> 1, iterations, tol, active, In.aobj, iso_iters, iso_ncon);
     In.W.amask = (float)(rmask | cmask);
     In.W.iso_iters = (float)(rob_iters > iso_iters ? rob_iters : iso_iters);
