@@ -14,7 +14,8 @@ from gym_genesis_b200.sim import BatchedSim  # noqa: E402
 dev = torch.device("cuda", 0)
 n = 16384
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-for amp, mu, reset_prob in ((0.3, 5.0, 1 / 200.), (0.3, 5.0, 0.0), (0.1, 5.0, 1 / 200.), (0.3, 1.0, 1 / 200.)):
+CASES = ((0.3, 5.0, 1 / 200.), (0.3, 5.0, 0.0), (0.1, 5.0, 1 / 200.), (0.3, 1.0, 1 / 200.))
+for amp, mu, reset_prob in (CASES[:1] if "--one" in sys.argv else CASES):
     m = so101_cube_pick_model(success_height=ISLAND_TOP_Z + 0.1)
     m.friction = mu
     sim = BatchedSim(m, n, device=dev, auto_reset=True, reset_prob=reset_prob, seed=0)
