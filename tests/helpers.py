@@ -210,3 +210,30 @@ def stack_pile_states(m, orc, n=12, steps=90, every=15, seed=7):
             out.append((f32(Q).astype(np.float64), f32(QD).astype(np.float64), f32(QA).astype(np.float64), T.copy()))
         orc.step(Q, QD, QA, T, iterations=100, tol=1e-10)
     return tuple(np.concatenate([o[i] for o in out]) for i in range(4))
+
+
+def stack_clutter_states(m, gg_model, rng, n):
+    """Cubes dropped around a random pad of the gripper at random poses (overlapping the fingers, each other and the plane, up to
+    ~75 contacts) with random velocities: every kind of body pair of the stacking scene in one state."""
+    nu, K = m.nu, m.n_obj
+    Q = np.zeros((n, nu + 7 * K)); QD = np.zeros((n, nu + 6 * K))
+    Q[:, :nu] = m.home_q + rng.uniform(-0.6, 0.6, (n, nu))
+    Q[:, m.n_arm:nu] = rng.uniform(0, 0.04, (n, m.n_fing))
+    Q[:, :nu] = np.clip(Q[:, :nu], np.array(list(gg_model.lim_lo)[:nu]), np.array(list(gg_model.lim_hi)[:nu]))
+    pads = [g for g in m.geoms if g.group == 0]
+    for k in range(n):
+        xp, xm = m.fk(np.concatenate([Q[k, :nu], m.default_cube_q()]))
+        g = pads[rng.integers(len(pads))]
+        tip = xp[g.body] + xm[g.body] @ np.asarray(g.pos)
+        for c in range(K):
+            o = nu + 7 * c
+            Q[k, o:o + 3] = tip + rng.uniform(-0.05, 0.05, 3) if (c < 2 or rng.random() < 0.5) else \
+                [rng.uniform(0.3, 0.7), rng.uniform(-0.3, 0.3), m.plane_z + 0.0199]
+            Q[k, o + 2] = max(Q[k, o + 2], m.plane_z + 0.0199)
+            qq = rng.normal(size=4)
+            Q[k, o + 3:o + 7] = qq / np.linalg.norm(qq)
+            QD[k, nu + 6 * c:nu + 6 * c + 6] = rng.normal(0, 0.3, 6)
+    QD[:, :nu] = rng.normal(0, 0.5, (n, nu))
+    T = m.home_q + rng.uniform(-0.5, 0.5, (n, nu))
+    T[:, m.n_arm:] = rng.uniform(-0.02, 0.04, (n, m.n_fing))
+    return tuple(f32(x).astype(np.float64) for x in (Q, QD, T))

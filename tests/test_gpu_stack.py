@@ -7,8 +7,8 @@ import pytest
 import torch
 
 from gym_genesis_b200.model import FRANKA_HOME, franka_cube_stack_model
-from helpers import (ROLLOUT_POS_TOL, TOL_Q_ABS, f32, stack_cluster_states, stack_pile_states, stack_random_states,
-                     stack_substep_errors)
+from helpers import (ROLLOUT_POS_TOL, TOL_Q_ABS, f32, stack_cluster_states, stack_clutter_states, stack_pile_states,
+                     stack_random_states, stack_substep_errors)
 
 pytestmark = pytest.mark.gpu
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "stack_traj.npz")
@@ -117,6 +117,19 @@ def test_tumbling_pile_states(Sim, sm, orc):
     qo, qdo, qao = Q.copy(), QD.copy(), QA.copy()
     info, _ = orc.step(qo, qdo, qao, T, iterations=200, tol=1e-12)
     assert (sim.step_info()[0].cpu().numpy() == info[:, 0]).all() and info[:, 0].max() >= 16
+    eq, ev = stack_substep_errors(Q, QD, qo, qdo, q, qd, _asm(orc, Q, QD, T))
+    assert eq.max() < TOL_Q_ABS and ev.max() < 1.0, (eq.max(), ev.max(), int(np.argmax(ev)))
+
+
+def test_gripper_cube_clutter_states(Sim, sm, orc):
+    """512 states with cubes overlapping the fingers, each other and the plane at random poses (up to ~75 contacts)."""
+    Q, QD, T = stack_clutter_states(sm, Sim(sm, 1).gg_model, np.random.default_rng(321), 512)
+    QA = np.zeros_like(QD)
+    sim = Sim(sm, Q.shape[0])
+    q, qd, qa = _one_substep(sim, Q, QD, QA, T)
+    qo, qdo, qao = Q.copy(), QD.copy(), QA.copy()
+    info, _ = orc.step(qo, qdo, qao, T, iterations=300, tol=1e-12)
+    assert (sim.step_info()[0].cpu().numpy() == info[:, 0]).all() and info[:, 0].max() >= 60
     eq, ev = stack_substep_errors(Q, QD, qo, qdo, q, qd, _asm(orc, Q, QD, T))
     assert eq.max() < TOL_Q_ABS and ev.max() < 1.0, (eq.max(), ev.max(), int(np.argmax(ev)))
 

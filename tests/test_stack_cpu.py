@@ -9,8 +9,8 @@ import pytest
 
 from gym_genesis_b200 import cabi
 from gym_genesis_b200.model import franka_cube_stack_model
-from helpers import (TOL_Q_ABS, _p, f32, hostsim_stack_step, stack_cluster_states, stack_pile_states, stack_random_states,
-                     stack_substep_errors)
+from helpers import (TOL_Q_ABS, _p, f32, hostsim_stack_step, stack_cluster_states, stack_clutter_states, stack_pile_states,
+                     stack_random_states, stack_substep_errors)
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "stack_traj.npz")
 
@@ -180,6 +180,18 @@ def test_tumbling_pile_states(hostsim, gg, sm, orc):
     info, _ = orc.step(qo, qdo, qao, T, iterations=200, tol=1e-12)
     q, qd, qa, hinfo = hostsim_stack_step(hostsim, gg[0], gg[1], Q, QD, QA, T)
     assert (hinfo[:, 0] == info[:, 0]).all() and info[:, 0].max() >= 10
+    eq, ev = stack_substep_errors(Q, QD, qo, qdo, q, qd, _asm(orc, Q, QD, T))
+    assert eq.max() < TOL_Q_ABS and ev.max() < 1.0, (eq.max(), ev.max(), int(np.argmax(ev)))
+
+
+def test_gripper_cube_clutter_states(hostsim, gg, sm, orc):
+    """Cubes overlapping the fingers, each other and the plane at random poses (up to ~75 contacts)."""
+    Q, QD, T = stack_clutter_states(sm, gg[0], np.random.default_rng(123), 40)
+    QA = np.zeros_like(QD)
+    qo, qdo, qao = Q.copy(), QD.copy(), QA.copy()
+    info, _ = orc.step(qo, qdo, qao, T, iterations=300, tol=1e-12)
+    q, qd, qa, hinfo = hostsim_stack_step(hostsim, gg[0], gg[1], Q, QD, QA, T)
+    assert (hinfo[:, 0] == info[:, 0]).all() and info[:, 0].max() >= 40
     eq, ev = stack_substep_errors(Q, QD, qo, qdo, q, qd, _asm(orc, Q, QD, T))
     assert eq.max() < TOL_Q_ABS and ev.max() < 1.0, (eq.max(), ev.max(), int(np.argmax(ev)))
 
