@@ -237,3 +237,28 @@ def stack_clutter_states(m, gg_model, rng, n):
     T = m.home_q + rng.uniform(-0.5, 0.5, (n, nu))
     T[:, m.n_arm:] = rng.uniform(-0.02, 0.04, (n, m.n_fing))
     return tuple(f32(x).astype(np.float64) for x in (Q, QD, T))
+
+
+def pick_clutter_states(m, gg_model, rng, n):
+    """CubePick scene with the cube dropped around a random pad of the gripper at a random pose (overlapping the fingers and / or the
+    plane) and random velocities: the coupled path of the step kernel (warp-per-env solver teams) on states the scripted grasp never
+    visits."""
+    nu = m.nu
+    Q = np.zeros((n, nu + 7)); QD = np.zeros((n, nu + 6))
+    Q[:, :nu] = m.home_q + rng.uniform(-0.6, 0.6, (n, nu))
+    if m.name == "franka":
+        Q[:, m.n_arm:nu] = rng.uniform(0, 0.04, (n, m.n_fing))
+    Q[:, :nu] = np.clip(Q[:, :nu], np.array(list(gg_model.lim_lo)[:nu]), np.array(list(gg_model.lim_hi)[:nu]))
+    pads = [g for g in m.geoms if g.group == 0]
+    for k in range(n):
+        xp, xm = m.fk(m.full_q(Q[k, :nu]))
+        g = pads[rng.integers(len(pads))]
+        tip = xp[g.body] + xm[g.body] @ np.asarray(g.pos)
+        Q[k, nu:nu + 3] = tip + rng.uniform(-0.04, 0.04, 3)
+        Q[k, nu + 2] = max(Q[k, nu + 2], m.plane_z + 0.0199)
+        qq = rng.normal(size=4)
+        Q[k, nu + 3:nu + 7] = qq / np.linalg.norm(qq)
+    QD[:, :nu] = rng.normal(0, 0.5, (n, nu))
+    QD[:, nu:] = rng.normal(0, 0.3, (n, 6))
+    T = m.home_q + rng.uniform(-0.5, 0.5, (n, nu))
+    return tuple(f32(x).astype(np.float64) for x in (Q, QD, T))

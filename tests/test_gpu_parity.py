@@ -4,7 +4,7 @@ import pytest
 import torch
 
 from gym_genesis_b200 import model as mdl
-from helpers import (ROLLOUT_POS_TOL, TOL_Q_ABS, f32, random_states, scripted_grasp_states, substep_errors)
+from helpers import (ROLLOUT_POS_TOL, TOL_Q_ABS, f32, pick_clutter_states, random_states, scripted_grasp_states, substep_errors)
 
 pytestmark = pytest.mark.gpu
 
@@ -62,6 +62,20 @@ def test_single_substep_scripted_grasp_states(Sim, franka_model, oracle64):
     assert info[:, 0].max() >= 32
     eq, ev = substep_errors(Q, QD, qo, qdo, q, qd, _a_smooth_scale(oracle64, Q, QD, T))
     assert eq.max() < TOL_Q_ABS and ev.max() < 1.0, (eq.max(), ev.max())
+
+
+def test_single_substep_gripper_cube_clutter(Sim, franka_model, oracle64):
+    """1024 states with the cube at random poses around the fingers (overlapping pads and / or plane): the warp-per-env solver teams
+    next to the register-resident path inside the same blocks."""
+    sim = Sim(franka_model, 1024)
+    Q, QD, T = pick_clutter_states(franka_model, sim.gg_model, np.random.default_rng(56), 1024)
+    QA = np.zeros_like(QD)
+    q, qd, qa = _one_substep(sim, Q, QD, QA, T)
+    qo, qdo, qao = Q.copy(), QD.copy(), QA.copy()
+    info, _ = oracle64.step(qo, qdo, qao, T, iterations=300, tol=1e-12)
+    assert (info[:, 0] > 4).sum() > 200
+    eq, ev = substep_errors(Q, QD, qo, qdo, q, qd, _a_smooth_scale(oracle64, Q, QD, T))
+    assert eq.max() < TOL_Q_ABS and ev.max() < 1.0, (eq.max(), ev.max(), int(np.argmax(ev)))
 
 
 def test_rollout_100_steps(Sim, franka_model, oracle64):

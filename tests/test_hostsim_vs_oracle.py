@@ -7,7 +7,7 @@ import pytest
 
 from gym_genesis_b200 import cabi
 from gym_genesis_b200 import model as mdl
-from helpers import (TOL_Q_ABS, _p, f32, hostsim_step, random_states, scripted_grasp_states, substep_errors)
+from helpers import (TOL_Q_ABS, _p, f32, hostsim_step, pick_clutter_states, random_states, scripted_grasp_states, substep_errors)
 
 
 @pytest.fixture(scope="module")
@@ -196,3 +196,15 @@ def test_pad_broad_phase_is_conservative(hostsim, robot, franka_model, so101_mod
     assert flag[touching].all(), int((~flag[touching].astype(bool)).sum())
     # and it is a useful filter: a good share of the near misses is rejected
     assert flag[~touching].mean() < 0.8
+
+
+def test_substep_gripper_cube_clutter(hostsim, gg, franka_model, oracle64):
+    """The cube at random poses around the fingers (overlapping pads and / or plane): contact counts and the substep against the oracle."""
+    Q, QD, T = pick_clutter_states(franka_model, gg, np.random.default_rng(55), 300)
+    QA = np.zeros_like(QD)
+    qo, qdo, qao = Q.copy(), QD.copy(), QA.copy()
+    info, _ = oracle64.step(qo, qdo, qao, T, iterations=300, tol=1e-12)
+    q, qd, qa, hinfo, _ = hostsim_step(hostsim, gg, Q, QD, QA, T)
+    assert (hinfo[:, 0] == info[:, 0]).all() and (info[:, 0] > 4).sum() > 50
+    eq, ev = substep_errors(Q, QD, qo, qdo, q, qd, _a_smooth_scale(oracle64, Q, QD, T))
+    assert eq.max() < TOL_Q_ABS and ev.max() < 1.0, (eq.max(), ev.max(), int(np.argmax(ev)))
