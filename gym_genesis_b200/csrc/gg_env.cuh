@@ -1085,10 +1085,25 @@ GG_HD bool pads_reach_plane(const GgModel& M, int b, const M3& Rb, V3 pb) {
     return hit;
 }
 
+// Two oriented boxes: the six face axes of the separating-axis test (the nine edge-edge axes are skipped: a miss on any axis
+// proves separation, so testing fewer axes only errs towards "may touch"); 1e-5 m margin against the narrow phase's own arithmetic.
+GG_HD bool boxes_may_touch(V3 cA, const M3& RA, V3 hA, V3 cB, const M3& RB, V3 hB) {
+    const V3 t = cB - cA;
+    bool sep = false;
+#pragma unroll
+    for (int ax = 0; ax < 3; ax++) {
+        const V3 ua = col(RA, ax), ub = col(RB, ax);
+        const float ra = comp(hA, ax) + fabsf(dot(ua, RB.c0)) * hB.x + fabsf(dot(ua, RB.c1)) * hB.y + fabsf(dot(ua, RB.c2)) * hB.z;
+        sep = sep || (fabsf(dot(t, ua)) > ra + 1e-5f);
+        const float rb = comp(hB, ax) + fabsf(dot(ub, RA.c0)) * hA.x + fabsf(dot(ub, RA.c1)) * hA.y + fabsf(dot(ub, RA.c2)) * hA.z;
+        sep = sep || (fabsf(dot(t, ub)) > rb + 1e-5f);
+    }
+    return !sep;
+}
+
 // pads of body b against the cube, two conservative refinements of the sphere-sphere test:
 //   (1) distance from the cube centre to the pad box (closest point of an oriented box) against the cube's bounding-sphere radius
-//   (2) the six face axes of the separating-axis test (the nine edge-edge axes are skipped: a miss on any axis proves separation,
-//       so testing fewer axes only errs towards "may touch"); 1e-5 m margin against the narrow phase's own arithmetic
+//   (2) boxes_may_touch
 GG_HD bool pads_reach_cube(const GgModel& M, int b, const M3& Rb, V3 pb, V3 cp, const M3& cR, V3 ch) {
     const float rc = sqrtf(dot(ch, ch)) + 1e-5f;
     bool hit = false;
@@ -1097,21 +1112,10 @@ GG_HD bool pads_reach_cube(const GgModel& M, int b, const M3& Rb, V3 pb, V3 cp, 
         const V3 c = pb + mul(Rb, ld3(M.pad_pos[g]));
         const M3 R = mmul(Rb, qmat(ldq(M.pad_quat[g])));
         const V3 h = ld3(M.pad_half[g]);
-        const V3 t = cp - c;
-        const V3 l = mulT(R, t);
+        const V3 l = mulT(R, cp - c);
         const V3 e = mk(fmaxf(fabsf(l.x) - h.x, 0.f), fmaxf(fabsf(l.y) - h.y, 0.f), fmaxf(fabsf(l.z) - h.z, 0.f));
         if (dot(e, e) > rc * rc) continue;
-        bool sep = false;
-#pragma unroll
-        for (int ax = 0; ax < 3; ax++) {
-            const V3 ua = col(R, ax), ub = col(cR, ax);
-            // pad face axis: extent of the pad = h[ax], extent of the cube = sum_j |ua . cR_j| ch_j
-            const float ra = comp(h, ax) + fabsf(dot(ua, cR.c0)) * ch.x + fabsf(dot(ua, cR.c1)) * ch.y + fabsf(dot(ua, cR.c2)) * ch.z;
-            sep = sep || (fabsf(dot(t, ua)) > ra + 1e-5f);
-            const float rb = comp(ch, ax) + fabsf(dot(ub, R.c0)) * h.x + fabsf(dot(ub, R.c1)) * h.y + fabsf(dot(ub, R.c2)) * h.z;
-            sep = sep || (fabsf(dot(t, ub)) > rb + 1e-5f);
-        }
-        hit = hit || !sep;
+        hit = hit || boxes_may_touch(c, R, h, cp, cR, ch);
     }
     return hit;
 }

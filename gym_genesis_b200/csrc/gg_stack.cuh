@@ -222,7 +222,9 @@ GG_HD unsigned stack_prep_cubes(const GgModel& M, const ObjState<K>& O, const fl
 #pragma unroll
             for (int j = i + 1; j < K; j++) {
                 const V3 d = O.p[i] - O.p[j];
-                if (dot(d, d) <= r2) cmask |= (2u << i) | (2u << j);
+                // bounding spheres first; where they fire (resting neighbours sit one cube width apart, well inside 2 r), the six
+                // face axes of the SAT decide: cubes that were pushed apart and now rest a hair from each other stay decoupled
+                if (dot(d, d) <= r2 && boxes_may_touch(O.p[i], qmat(O.q[i]), ch, O.p[j], qmat(O.q[j]), ch)) cmask |= (2u << i) | (2u << j);
             }
     }
     iso_iters = 0; iso_ncon = 0;

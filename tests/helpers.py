@@ -174,13 +174,13 @@ def stack_substep_errors(q0, qd0, q_ref, qd_ref, q, qd, a_smooth_scale):
 
 
 def stack_cluster_states(g, idx=(30, 36, 60, 80)):
-    """Golden grasp / carry samples with the four other cubes lined up next to cube_1 (0.045 m pitch): every body is within
-    reach of another one, so the cooperative solve runs on all 39 dofs (its two-rows-per-lane path)."""
+    """Golden grasp / carry samples with the four other cubes lined up against cube_1 (0.0398 m pitch: 0.2 mm of overlap between
+    neighbours): every body touches another one, so the cooperative solve runs on all 39 dofs (its two-rows-per-lane path)."""
     idx = list(idx)
     Q, QD, QA, T = (g[k][idx].copy() for k in ("q", "qd", "qacc", "act"))
     for r in range(len(idx)):
         c1 = Q[r, 9:12].copy()
-        for k, off in zip(range(1, 5), (0.045, -0.045, 0.09, -0.09)):
+        for k, off in zip(range(1, 5), (0.0398, -0.0398, 0.0796, -0.0796)):
             Q[r, 9 + 7 * k: 9 + 7 * k + 7] = [c1[0] + off, c1[1], 0.0199 if r < len(idx) - 1 else c1[2], 1, 0, 0, 0]
         QD[r, 9:] = 0
         QA[r] = 0
