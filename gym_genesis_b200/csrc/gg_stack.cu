@@ -1,12 +1,14 @@
 // CUDA kernels (sm_100a) and C ABI of the multi-object (CubeStack) step path: include/gg_b200.h, gg_stack_*.
 // Replaces, for gym_genesis/tasks/franka/cube_stack.py:119-216, the Genesis calls of reset / step / compute_reward / get_obs.
 //
-// One env.step = three launches on the caller's stream (per-env pipeline in gg_stack.cuh):
+// One env.step = four launches on the caller's stream (per-env pipeline in gg_stack.cuh):
 //   stack_prep_kernel    thread per env, 32 envs and three role warps per block.  Masked reset, robot dynamics, body-level broad phase (pads vs plane /
-//                        cubes, cube vs cube); every body that can touch nothing but the plane is solved HERE in registers
-//                        (robot block with joint-limit rows, 6 x 6 cube blocks with <= 4 plane contacts).  The StackIn record of
+//                        cubes, cube vs cube); a robot whose pads can touch nothing is solved HERE in registers (robot block with
+//                        joint-limit rows).  The StackIn record of
 //                        each env (robot dynamics + object states) is transposed through shared memory and written env-major, so
 //                        that both this kernel's stores and the solver's loads are coalesced.
+//   stack_cubes_kernel   thread per (cube, env): the cubes that can touch nothing but the plane are solved in registers (6 x 6
+//                        block, <= 4 plane contacts).
 //   stack_solve_kernel   persistent warps drain the compacted list of envs that have bodies in reach of each other; one WARP per
 //                        env, 4 warps per block, ~23 KB of dynamic shared memory per warp (contact table, pair stiffness, packed
 //                        Hessian of the active dofs).  Accelerations go to a [dof][env] slab.
@@ -83,6 +85,10 @@ struct StackArgs {
     int32_t* ncon; int32_t* iters;
     uint8_t* flags;           // per env: bit 0 reset applied by this call, bit 1 a substep runs, bit 2 some bodies need the
                               // cooperative solve (otherwise stack_prep's register solves are the whole answer)
+    int32_t* amask;           // per env: bodies of the cooperative solve (bit 0 robot, bit 1 + k cube k), written by stack_prep_kernel
+    uint8_t* rob_it;          // per env: Newton iterations of the robot block's register solve
+    uint8_t* iso_nc;          // [cube][env]: plane contacts / Newton iterations of the cubes solved in registers (stack_cubes_kernel)
+    uint8_t* iso_it;
     int32_t* coop_list;       // envs that need the cooperative solve, appended by stack_prep_kernel (order irrelevant: envs are independent)
     int32_t* coop_ctr;        // [0] list length, [1] pop cursor of the persistent solver warps; cleared by stack_finish_kernel
 };
@@ -189,7 +195,7 @@ __global__ void __launch_bounds__(96, 4) stack_prep_kernel(const __grid_constant
     __shared__ float sm[32 * WFP];
     __shared__ float s_fs[NU * 32];
     __shared__ unsigned s_rmask[32], s_cmask[32];
-    __shared__ int s_rit[32], s_cit[32], s_cnc[32];
+    __shared__ int s_rit[32];
     const int lane = threadIdx.x & 31, role = threadIdx.x >> 5;
     const int e0 = blockIdx.x * 32 + lane;
     const bool live = e0 < A.n;
@@ -264,9 +270,7 @@ __global__ void __launch_bounds__(96, 4) stack_prep_kernel(const __grid_constant
             s_rmask[lane] = ((pad_plane || pad_cubes != 0u) ? 1u : 0u) | (pad_cubes << 1);
             sk_bar_arrive(2, 64);                                 // ROBOT picks the robot's amask bits up after its Cholesky
         }
-        int cit = 0, cnc = 0;
-        s_cmask[lane] = gg::stack_prep_cubes<K>(A.M, O, In.warm_obj, pad_cubes, A.iterations, A.tol, active && live, In.aobj, cit, cnc);
-        s_cit[lane] = cit; s_cnc[lane] = cnc;
+        s_cmask[lane] = gg::stack_cube_reach<K>(A.M, O, pad_cubes);   // the isolated cubes are solved by stack_cubes_kernel
         if (do_reset && live) {
             // the state of a reset env is rewritten only after every role has read what it needs (joint rows: below, by ROBOT)
             store_objects<NU, K>(sp, st, O);
@@ -281,22 +285,18 @@ __global__ void __launch_bounds__(96, 4) stack_prep_kernel(const __grid_constant
             for (int i = 0; i < NU; i++) { sp[(R::Q + i) * st] = A.M.home_q[i]; sp[(R::QD + i) * st] = 0.f; sp[(R::WARM + i) * st] = 0.f; }
         }
         const unsigned amask = s_rmask[lane] | s_cmask[lane];
-        const int iso_iters = s_rit[lane] > s_cit[lane] ? s_rit[lane] : s_cit[lane];
-        In.W.amask = (float)amask; In.W.iso_iters = (float)iso_iters; In.W.iso_ncon = (float)s_cnc[lane];
+        In.W.amask = (float)amask; In.W.iso_iters = (float)s_rit[lane]; In.W.iso_ncon = 0.f;
         if (live) {
             const bool coop = active && amask != 0u;
             A.flags[e] = (do_reset ? 1 : 0) | (active ? 2 : 0) | (coop ? 4 : 0);
+            A.amask[e] = (int32_t)amask;
+            A.rob_it[e] = (uint8_t)s_rit[lane];
             if (active) {
-                // accelerations of everything solved in registers; the cooperative solve overwrites its own dofs
+                // acceleration of the robot block's register solve; the cooperative solve overwrites it when the robot is active
                 float* ap = A.acc + e;
 #pragma unroll
                 for (int i = 0; i < NU; i++) ap[(size_t)i * st] = In.W.arob[i];
-#pragma unroll
-                for (int k = 0; k < K; k++)
-#pragma unroll
-                    for (int i = 0; i < 6; i++) ap[(size_t)(NU + 6 * k + i) * st] = In.aobj[k][i];
-                if (!coop) { A.ncon[e] = s_cnc[lane]; A.iters[e] = iso_iters; }
-                else A.coop_list[atomicAdd(&A.coop_ctr[0], 1)] = e;
+                if (coop) A.coop_list[atomicAdd(&A.coop_ctr[0], 1)] = e;
             }
         }
     }
@@ -306,6 +306,36 @@ __global__ void __launch_bounds__(96, 4) stack_prep_kernel(const __grid_constant
     float* dst = A.work + (size_t)blockIdx.x * 32 * WF;
     for (int r = role; r < nlive; r += 3)
         for (int i = lane; i < WF; i += 32) dst[(size_t)r * WF + i] = sm[r * WFP + i];
+}
+
+// ----------------------------------------------------------------------------------------------------------------- cubes
+// One thread per (cube, env): the cubes that can touch nothing but the plane -- the large majority -- are solved here in registers
+// (6 x 6 block, <= 4 plane contacts), K times more threads than a thread-per-env pass and none of its serial chain.  Lanes of a warp
+// share the cube index and walk consecutive envs, so every state row is one coalesced line.
+template <int NU, int K>
+__global__ void __launch_bounds__(128) stack_cubes_kernel(const __grid_constant__ StackArgs A) {
+    typedef Rows<NU, K> R;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int k = t / A.stride, e = t - k * A.stride;
+    if (k >= K || e >= A.n) return;
+    const size_t st = (size_t)A.stride;
+    const bool solve = (A.flags[e] & 2) && !((A.amask[e] >> (1 + k)) & 1);
+    int nc = 0, it = 0;
+    if (solve) {
+        const float* c = A.state + e + (R::OBJ + 13 * k) * st;
+        const gg::V3 p = gg::mk(c[0], c[st], c[2 * st]);
+        const gg::Q4 q = gg::mkq(c[3 * st], c[4 * st], c[5 * st], c[6 * st]);
+        const gg::V3 v = gg::mk(c[7 * st], c[8 * st], c[9 * st]);
+        const gg::V3 w = gg::mk(c[10 * st], c[11 * st], c[12 * st]);
+        float warm[6], a_c[6];
+#pragma unroll
+        for (int i = 0; i < 6; i++) warm[i] = A.state[e + (R::WARM + NU + 6 * k + i) * st];
+        gg::stack_cube_isolated(A.M, p, q, v, w, warm, A.iterations, A.tol, true, a_c, nc, it);
+#pragma unroll
+        for (int i = 0; i < 6; i++) A.acc[(size_t)(NU + 6 * k + i) * st + e] = a_c[i];
+    }
+    A.iso_nc[(size_t)k * st + e] = (uint8_t)nc;
+    A.iso_it[(size_t)k * st + e] = (uint8_t)it;
 }
 
 // ----------------------------------------------------------------------------------------------------------------- solve
@@ -359,8 +389,7 @@ __global__ void __launch_bounds__(32 * kSolveWarps) stack_solve_kernel(const __g
         int its = 0, nc = 0;
         gg::stack_solve<NA, NF, FH, K>(A.M, A.T.max_contacts, In, B, A.iterations, A.tol, wc, A.acc + e, A.stride, its, nc);
         if (lane == 0) {
-            const int ri = (int)In.W.iso_iters;
-            A.ncon[e] = nc; A.iters[e] = its > ri ? its : ri;
+            A.ncon[e] = nc; A.iters[e] = its;
         }
         __syncwarp();
     }
@@ -397,7 +426,20 @@ __global__ void __launch_bounds__(128) stack_finish_kernel(const __grid_constant
         gg::integrate_robot<NU>(A.M, q, qd, qa, a);
 #pragma unroll
         for (int k = 0; k < K; k++) gg::integrate_cube(A.M, O.p[k], O.q[k], O.v[k], O.w[k], qa + NU + 6 * k, a + NU + 6 * k);
-        st_iter = (float)A.iters[e]; st_con = (float)A.ncon[e];
+        {
+            // contacts / Newton iterations of the step: the cooperative solve (if any) + the register solves of robot and cubes
+            int nc = (fl & 4) ? A.ncon[e] : 0, it = (fl & 4) ? A.iters[e] : 0;
+            const int ri = A.rob_it[e];
+            it = it > ri ? it : ri;
+#pragma unroll
+            for (int k = 0; k < K; k++) {
+                nc += A.iso_nc[(size_t)k * st + e];
+                const int ci = A.iso_it[(size_t)k * st + e];
+                it = it > ci ? it : ci;
+            }
+            if (live) { A.ncon[e] = nc; A.iters[e] = it; }
+            st_iter = (float)it; st_con = (float)nc;
+        }
         float chk = 0.f;
 #pragma unroll
         for (int i = 0; i < NU; i++) chk += q[i] + qd[i];
@@ -502,6 +544,7 @@ struct GgStackSim {
     uint8_t* done; uint8_t* flags; double* stats;            // library-owned
     float* work; float* acc; int32_t* ncon; int32_t* iters;
     int32_t* coop_list; int32_t* coop_ctr;
+    int32_t* amask; uint8_t* rob_it; uint8_t* iso_nc; uint8_t* iso_it;
     int32_t* slot;                                            // allocated on first gg_stack_export_successful
     uint32_t step_index;
     static constexpr int kPinCache = 16;
@@ -527,11 +570,12 @@ static int stack_launch(GgStackSim* sim, StackArgs& A, gg_stream_t stream) {
     A.seed = sim->cfg.seed; A.first_env = sim->cfg.first_env_id; A.step_index = sim->step_index;
     A.stats = sim->stats; A.work = sim->work; A.acc = sim->acc; A.ncon = sim->ncon; A.iters = sim->iters; A.flags = sim->flags;
     A.coop_list = sim->coop_list; A.coop_ctr = sim->coop_ctr;
+    A.amask = sim->amask; A.rob_it = sim->rob_it; A.iso_nc = sim->iso_nc; A.iso_it = sim->iso_it;
     cudaStream_t s = (cudaStream_t)stream;
     SK_CUDA(cudaSetDevice(sim->device));
     if (sim->kind == 0) stack_launch_t<7, 2, false, 5>(sim, A, s);
     else stack_launch_t<5, 1, true, 5>(sim, A, s);
-    gg_internal_count_launches(A.mode != 2 ? 3 : 1);
+    gg_internal_count_launches(A.mode != 2 ? 4 : 1);
     SK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -540,6 +584,7 @@ template <int NA, int NF, bool FH, int K>
 static void stack_launch_t(GgStackSim* sim, const StackArgs& A, cudaStream_t s) {
     if (A.mode != 2) {
         stack_prep_kernel<NA, NF, FH, K><<<(sim->n + 31) / 32, 96, 0, s>>>(A);
+        stack_cubes_kernel<NA + NF, K><<<(K * sim->stride + 127) / 128, 128, 0, s>>>(A);
         const int need = (sim->n + kSolveWarps - 1) / kSolveWarps;
         stack_solve_kernel<NA, NF, FH, K><<<need < sim->solve_blocks ? need : sim->solve_blocks, 32 * kSolveWarps, sim->solve_smem, s>>>(A);
     }
@@ -572,7 +617,7 @@ int gg_stack_create(const GgModel* model, const GgStackTask* task, int n_envs, i
     s->stride = (n_envs + 31) / 32 * 32;
     s->cfg.solver_iterations = 10; s->cfg.solver_tolerance = 1e-5f;
     s->solve_smem = kSolveWarps * (kind == 0 ? sizeof(FrankaIn) + sizeof(FrankaBuf) : sizeof(So101In) + sizeof(So101Buf));
-    cudaError_t e[9];
+    cudaError_t e[13];
     e[0] = cudaMalloc(&s->done, (size_t)s->stride);
     e[1] = cudaMalloc(&s->flags, (size_t)s->stride);
     e[2] = cudaMalloc(&s->stats, 8 * sizeof(double));
@@ -582,8 +627,12 @@ int gg_stack_create(const GgModel* model, const GgStackTask* task, int n_envs, i
     e[6] = cudaMalloc(&s->iters, (size_t)s->stride * sizeof(int32_t));
     e[7] = cudaMalloc(&s->coop_list, (size_t)s->stride * sizeof(int32_t));
     e[8] = cudaMalloc(&s->coop_ctr, 2 * sizeof(int32_t));
+    e[9] = cudaMalloc(&s->amask, (size_t)s->stride * sizeof(int32_t));
+    e[10] = cudaMalloc(&s->rob_it, (size_t)s->stride);
+    e[11] = cudaMalloc(&s->iso_nc, (size_t)s->stride * task->n_obj);
+    e[12] = cudaMalloc(&s->iso_it, (size_t)s->stride * task->n_obj);
     bool ok = true;
-    for (int i = 0; i < 9; i++) ok = ok && e[i] == cudaSuccess;
+    for (int i = 0; i < 13; i++) ok = ok && e[i] == cudaSuccess;
     {
         // persistent solver grid: as many blocks as fit at once (shared-memory bound), one wave on every SM
         cudaDeviceProp prop;
@@ -600,7 +649,7 @@ int gg_stack_create(const GgModel* model, const GgStackTask* task, int n_envs, i
     if (ok && kind == 1) ok = cudaFuncSetAttribute(stack_solve_kernel<5, 1, true, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->solve_smem) == cudaSuccess;
     if (!ok) {
         cudaFree(s->done); cudaFree(s->flags); cudaFree(s->stats); cudaFree(s->work); cudaFree(s->acc); cudaFree(s->ncon); cudaFree(s->iters);
-        cudaFree(s->coop_list); cudaFree(s->coop_ctr);
+        cudaFree(s->coop_list); cudaFree(s->coop_ctr); cudaFree(s->amask); cudaFree(s->rob_it); cudaFree(s->iso_nc); cudaFree(s->iso_it);
         delete s;
         return gg_internal_fail("gg_stack_create: device allocation failed%s", "");
     }
@@ -610,6 +659,10 @@ int gg_stack_create(const GgModel* model, const GgStackTask* task, int n_envs, i
     cudaMemset(s->ncon, 0, (size_t)s->stride * sizeof(int32_t));
     cudaMemset(s->iters, 0, (size_t)s->stride * sizeof(int32_t));
     cudaMemset(s->coop_ctr, 0, 2 * sizeof(int32_t));
+    cudaMemset(s->amask, 0, (size_t)s->stride * sizeof(int32_t));
+    cudaMemset(s->rob_it, 0, (size_t)s->stride);
+    cudaMemset(s->iso_nc, 0, (size_t)s->stride * task->n_obj);
+    cudaMemset(s->iso_it, 0, (size_t)s->stride * task->n_obj);
     *out = s;
     return 0;
 }
@@ -619,6 +672,7 @@ int gg_stack_destroy(GgStackSim* s) {
     cudaSetDevice(s->device);
     cudaFree(s->done); cudaFree(s->flags); cudaFree(s->stats); cudaFree(s->work); cudaFree(s->acc); cudaFree(s->ncon); cudaFree(s->iters);
     cudaFree(s->coop_list); cudaFree(s->coop_ctr); cudaFree(s->slot);
+    cudaFree(s->amask); cudaFree(s->rob_it); cudaFree(s->iso_nc); cudaFree(s->iso_it);
     delete s;
     return 0;
 }

@@ -209,39 +209,51 @@ GG_HD unsigned stack_prep_robot(const GgModel& M, const float* q, const float* q
     return rmask;
 }
 
-// pad_cubes: bit k = cube k within reach of a pad.  Returns the cube bits of amask (bit 1 + k).
+// pad_cubes: bit k = cube k within reach of a pad.  Returns the cube bits of amask (bit 1 + k): cubes within reach of a pad or of
+// another cube.
+template <int K>
+GG_HD unsigned stack_cube_reach(const GgModel& M, const ObjState<K>& O, unsigned pad_cubes) {
+    unsigned cmask = pad_cubes << 1;
+    const V3 ch = ld3(M.cube_half);
+    const float r2 = 4.f * dot(ch, ch);
+#pragma unroll
+    for (int i = 0; i < K; i++)
+#pragma unroll
+        for (int j = i + 1; j < K; j++) {
+            const V3 d = O.p[i] - O.p[j];
+            // bounding spheres first; where they fire (resting neighbours sit one cube width apart, well inside 2 r), the six
+            // face axes of the SAT decide: cubes that were pushed apart and now rest a hair from each other stay decoupled
+            if (dot(d, d) <= r2 && boxes_may_touch(O.p[i], qmat(O.q[i]), ch, O.p[j], qmat(O.q[j]), ch)) cmask |= (2u << i) | (2u << j);
+        }
+    return cmask;
+}
+
+// register solve of ONE isolated cube (6 x 6 block, <= 4 plane contacts): a_c, contacts, Newton iterations
+GG_HD void stack_cube_isolated(const GgModel& M, V3 p, Q4 q, V3 v, V3 w, const float* warm_c, int iterations, float tol, bool solve,
+                               float* a_c, int& ncon, int& iters) {
+    float Mc[6], as_c[6], qd_c[6], w_c[6];
+    cube_free_acc(M, v, w, Mc, as_c, qd_c);
+#pragma unroll
+    for (int i = 0; i < 6; i++) { a_c[i] = as_c[i]; w_c[i] = warm_c[i]; }
+    ncon = 0; iters = 0;
+    if (solve) {
+        StepInfo ic;
+        CubeConLocal cs;
+        cube_block_solve(M, p, qmat(q), Mc, as_c, qd_c, w_c, a_c, iterations, tol, cs, ic);
+        ncon = ic.ncon; iters = ic.iters;
+    }
+}
+
 template <int K>
 GG_HD unsigned stack_prep_cubes(const GgModel& M, const ObjState<K>& O, const float (*warm_obj)[6], unsigned pad_cubes, int iterations,
                                 float tol, bool active, float (*aobj)[6], int& iso_iters, int& iso_ncon) {
-    unsigned cmask = pad_cubes << 1;
-    {
-        const V3 ch = ld3(M.cube_half);
-        const float r2 = 4.f * dot(ch, ch);
-#pragma unroll
-        for (int i = 0; i < K; i++)
-#pragma unroll
-            for (int j = i + 1; j < K; j++) {
-                const V3 d = O.p[i] - O.p[j];
-                // bounding spheres first; where they fire (resting neighbours sit one cube width apart, well inside 2 r), the six
-                // face axes of the SAT decide: cubes that were pushed apart and now rest a hair from each other stay decoupled
-                if (dot(d, d) <= r2 && boxes_may_touch(O.p[i], qmat(O.q[i]), ch, O.p[j], qmat(O.q[j]), ch)) cmask |= (2u << i) | (2u << j);
-            }
-    }
+    const unsigned cmask = stack_cube_reach<K>(M, O, pad_cubes);
     iso_iters = 0; iso_ncon = 0;
     for (int k = 0; k < K; k++) {
-        float Mc[6], as_c[6], qd_c[6], a_c[6], w_c[6];
-        cube_free_acc(M, O.v[k], O.w[k], Mc, as_c, qd_c);
-#pragma unroll
-        for (int i = 0; i < 6; i++) { a_c[i] = as_c[i]; w_c[i] = warm_obj[k][i]; }
-        if (active && !((cmask >> (1 + k)) & 1u)) {
-            StepInfo ic;
-            CubeConLocal cs;
-            cube_block_solve(M, O.p[k], qmat(O.q[k]), Mc, as_c, qd_c, w_c, a_c, iterations, tol, cs, ic);
-            iso_ncon += ic.ncon;
-            iso_iters = ic.iters > iso_iters ? ic.iters : iso_iters;
-        }
-#pragma unroll
-        for (int i = 0; i < 6; i++) aobj[k][i] = a_c[i];
+        int nc, it;
+        stack_cube_isolated(M, O.p[k], O.q[k], O.v[k], O.w[k], warm_obj[k], iterations, tol, active && !((cmask >> (1 + k)) & 1u), aobj[k], nc, it);
+        iso_ncon += nc;
+        iso_iters = it > iso_iters ? it : iso_iters;
     }
     return cmask;
 }
