@@ -193,10 +193,11 @@ int gg_export_successful(GgSim* sim, const float* traj, const int32_t* ever, int
  *
  * State buffer (caller-owned, float32, gg_stack_state_rows() x gg_stack_state_stride(), env index fastest):
  *   rows [0, nu) q | [nu, 2nu) qd | 13 rows per object (pos3 quat4 linvel3 angvel3) | nu + 6 n_obj rows warm start.
- * One gg_stack_step = three launches on `stream`: stack_prep_kernel (thread per env: masked reset, PD, CRBA, Cholesky,
- * RNEA, joint-limit rows, pad broad phase, robot-block solve when no pad can touch anything), stack_solve_kernel (warp per
- * env: narrow phase incl. cube-cube, Newton on the coupled dofs), stack_finish_kernel (thread per env: integration,
- * observations, reward / flags, counters, statistics).
+ * One gg_stack_step = four launches on `stream`: stack_prep_kernel (thread per env: masked reset, PD, CRBA, Cholesky,
+ * RNEA, joint-limit rows, body-level broad phase, robot-block solve when no pad can touch anything), stack_cubes_kernel
+ * (thread per (cube, env): register solves of the cubes that can touch nothing but the plane), stack_solve_kernel (warp per
+ * env with bodies in reach of each other: narrow phase incl. cube-cube, Newton on the coupled dofs), stack_finish_kernel
+ * (thread per env: integration, observations, reward / flags, counters, statistics).
  * ------------------------------------------------------------------------------------------------------------------ */
 #define GG_MAX_OBJ 5
 #define GG_STACK_MAX_CONTACTS 96
