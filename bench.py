@@ -358,7 +358,7 @@ def run_gpu(args):
                          "bytes_to_host": int(frames.numel() * 4), "note": "gg_export_successful (select + gather) + one D2H copy of the successful envs"}}
         envc.close()
 
-    # ---- workload D: CubeStack scene, five free cubes, cube-cube contacts (gg_stack_*: 3 launches / step) ----
+    # ---- workload D: CubeStack scene, five free cubes, cube-cube contacts (gg_stack_*: 4 launches / step) ----
     wd = None
     spath = os.path.join(ROOT, "tests", "golden", "stack_traj.npz")
     if not args.no_workload_d and os.path.exists(spath):

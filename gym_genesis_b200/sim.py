@@ -264,8 +264,8 @@ class BatchedSim:
 class BatchedStackSim(BatchedSim):
     """N independent worlds of the stacking scene (arm + gripper + five free cubes + plane), `gg_stack_*` entry points.
 
-    Replaces the Genesis `Scene` of `gym_genesis/tasks/franka/cube_stack.py:42-96`.  One env.step = three launches
-    (thread-per-env dynamics, warp-per-env contact solve, thread-per-env integration / observation); see
+    Replaces the Genesis `Scene` of `gym_genesis/tasks/franka/cube_stack.py:42-96`.  One env.step = four launches
+    (thread-per-env dynamics, thread-per-cube register solves, warp-per-env contact solve, thread-per-env integration / observation); see
     `csrc/gg_stack.cu`.  `inverse_kinematics` runs the same `gg_ik` kernel as the pick scene on this sim's joint state.
     """
 
