@@ -90,7 +90,8 @@ struct StackArgs {
     uint8_t* iso_nc;          // [cube][env]: plane contacts / Newton iterations of the cubes solved in registers (stack_cubes_kernel)
     uint8_t* iso_it;
     int32_t* coop_list;       // envs that need the cooperative solve, appended by stack_prep_kernel (order irrelevant: envs are independent)
-    int32_t* coop_ctr;        // [0] list length, [1] pop cursor of the persistent solver warps; cleared by stack_finish_kernel
+    int32_t* coop_ctr;        // [0] heavy-list length, [1] pop cursor of the persistent solver warps, [2] light-list length (the
+                              // light list starts at coop_list + stride); cleared by stack_finish_kernel
 };
 
 // state rows: q [0, NU) | qd [NU, 2NU) | objects 13 K | warm start NU + 6 K
@@ -296,7 +297,13 @@ __global__ void __launch_bounds__(96, 4) stack_prep_kernel(const __grid_constant
                 float* ap = A.acc + e;
 #pragma unroll
                 for (int i = 0; i < NU; i++) ap[(size_t)i * st] = In.W.arob[i];
-                if (coop) A.coop_list[atomicAdd(&A.coop_ctr[0], 1)] = e;
+                if (coop) {
+                    // two lists, drained heavy first (longest-processing-time order shortens the tail of the persistent grid):
+                    // heavy = the robot or at least three cubes take part (15+ dofs, pad contacts), light = a pair of cubes
+                    const bool heavy = (amask & 1u) || __popc(amask >> 1) >= 3;
+                    if (heavy) A.coop_list[atomicAdd(&A.coop_ctr[0], 1)] = e;
+                    else A.coop_list[A.stride + atomicAdd(&A.coop_ctr[2], 1)] = e;
+                }
             }
         }
     }
@@ -358,7 +365,8 @@ __global__ void __launch_bounds__(32 * kSolveWarps) stack_solve_kernel(const __g
     unsigned char* base = smem + (size_t)warp * (sizeof(InT) + sizeof(BufT));
     InT& In = *reinterpret_cast<InT*>(base);
     BufT& B = *reinterpret_cast<BufT*>(base + sizeof(InT));
-    const int count = A.coop_ctr[0];
+    const int n_heavy = A.coop_ctr[0];
+    const int count = n_heavy + A.coop_ctr[2];                       // heavy list first, then the light one
     WarpDev wc{lane};
 #ifdef GG_SOLVE_LOCKSTEP
     __shared__ int s_base;
@@ -379,7 +387,7 @@ __global__ void __launch_bounds__(32 * kSolveWarps) stack_solve_kernel(const __g
         k = __shfl_sync(kFullMask, k, 0);
         if (k >= count) break;
 #endif
-        const int e = A.coop_list[k];
+        const int e = k < n_heavy ? A.coop_list[k] : A.coop_list[A.stride + k - n_heavy];
         {
             const float* src = A.work + (size_t)e * WF;
             float* dst = reinterpret_cast<float*>(&In);
@@ -492,7 +500,7 @@ __global__ void __launch_bounds__(128) stack_finish_kernel(const __grid_constant
     } else {
         st_steps = st_done = st_succ = st_ret = st_len = st_nan = st_iter = st_con = 0.f;
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0) { A.coop_ctr[0] = 0; A.coop_ctr[1] = 0; }      // ready for the next step's prep
+    if (blockIdx.x == 0 && threadIdx.x == 0) { A.coop_ctr[0] = 0; A.coop_ctr[1] = 0; A.coop_ctr[2] = 0; }      // ready for the next step's prep
     if (A.stats != nullptr && A.mode == 0) {
         float v[8] = {st_steps, st_done, st_succ, st_ret, st_len, st_nan, st_iter, st_con};
         float mine = 0.f;
@@ -625,8 +633,8 @@ int gg_stack_create(const GgModel* model, const GgStackTask* task, int n_envs, i
     e[4] = cudaMalloc(&s->acc, (size_t)s->stride * s->nv * sizeof(float));
     e[5] = cudaMalloc(&s->ncon, (size_t)s->stride * sizeof(int32_t));
     e[6] = cudaMalloc(&s->iters, (size_t)s->stride * sizeof(int32_t));
-    e[7] = cudaMalloc(&s->coop_list, (size_t)s->stride * sizeof(int32_t));
-    e[8] = cudaMalloc(&s->coop_ctr, 2 * sizeof(int32_t));
+    e[7] = cudaMalloc(&s->coop_list, 2 * (size_t)s->stride * sizeof(int32_t));
+    e[8] = cudaMalloc(&s->coop_ctr, 4 * sizeof(int32_t));
     e[9] = cudaMalloc(&s->amask, (size_t)s->stride * sizeof(int32_t));
     e[10] = cudaMalloc(&s->rob_it, (size_t)s->stride);
     e[11] = cudaMalloc(&s->iso_nc, (size_t)s->stride * task->n_obj);
@@ -658,7 +666,7 @@ int gg_stack_create(const GgModel* model, const GgStackTask* task, int n_envs, i
     cudaMemset(s->stats, 0, 8 * sizeof(double));
     cudaMemset(s->ncon, 0, (size_t)s->stride * sizeof(int32_t));
     cudaMemset(s->iters, 0, (size_t)s->stride * sizeof(int32_t));
-    cudaMemset(s->coop_ctr, 0, 2 * sizeof(int32_t));
+    cudaMemset(s->coop_ctr, 0, 4 * sizeof(int32_t));
     cudaMemset(s->amask, 0, (size_t)s->stride * sizeof(int32_t));
     cudaMemset(s->rob_it, 0, (size_t)s->stride);
     cudaMemset(s->iso_nc, 0, (size_t)s->stride * task->n_obj);
