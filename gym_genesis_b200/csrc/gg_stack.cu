@@ -559,6 +559,8 @@ struct GgStackSim {
     const void* pin_ok[kPinCache]; int pin_next;             // pointers already verified as pinned host memory
     size_t solve_smem;
     int solve_blocks;                                         // persistent grid of the cooperative solver
+    cudaStream_t side;                                        // the cubes kernel runs beside the cooperative solve (fork / join per step)
+    cudaEvent_t ev_fork, ev_join;
 };
 
 typedef gg::StackIn<7, 2, 5> FrankaIn;
@@ -592,9 +594,16 @@ template <int NA, int NF, bool FH, int K>
 static void stack_launch_t(GgStackSim* sim, const StackArgs& A, cudaStream_t s) {
     if (A.mode != 2) {
         stack_prep_kernel<NA, NF, FH, K><<<(sim->n + 31) / 32, 96, 0, s>>>(A);
-        stack_cubes_kernel<NA + NF, K><<<(K * sim->stride + 127) / 128, 128, 0, s>>>(A);
+        // the register solves of the isolated cubes and the cooperative solve touch disjoint dofs: fork the former onto a side
+        // stream so that they share the SMs (the solver is shared-memory bound at 8 warps / SM and leaves registers and warp slots
+        // free), join before the finish kernel.  Event fork / join is capturable, so the step still records into a CUDA graph.
+        cudaEventRecord(sim->ev_fork, s);
+        cudaStreamWaitEvent(sim->side, sim->ev_fork, 0);
+        stack_cubes_kernel<NA + NF, K><<<(K * sim->stride + 127) / 128, 128, 0, sim->side>>>(A);
+        cudaEventRecord(sim->ev_join, sim->side);
         const int need = (sim->n + kSolveWarps - 1) / kSolveWarps;
         stack_solve_kernel<NA, NF, FH, K><<<need < sim->solve_blocks ? need : sim->solve_blocks, 32 * kSolveWarps, sim->solve_smem, s>>>(A);
+        cudaStreamWaitEvent(s, sim->ev_join, 0);
     }
     stack_finish_kernel<NA, NF, FH, K><<<(sim->n + 127) / 128, 128, 0, s>>>(A);
 }
@@ -666,6 +675,10 @@ int gg_stack_create(const GgModel* model, const GgStackTask* task, int n_envs, i
     cudaMemset(s->stats, 0, 8 * sizeof(double));
     cudaMemset(s->ncon, 0, (size_t)s->stride * sizeof(int32_t));
     cudaMemset(s->iters, 0, (size_t)s->stride * sizeof(int32_t));
+    ok = cudaStreamCreateWithFlags(&s->side, cudaStreamNonBlocking) == cudaSuccess &&
+         cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming) == cudaSuccess &&
+         cudaEventCreateWithFlags(&s->ev_join, cudaEventDisableTiming) == cudaSuccess;
+    if (!ok) { gg_stack_destroy(s); return gg_internal_fail("gg_stack_create: stream / event creation failed%s", ""); }
     cudaMemset(s->coop_ctr, 0, 4 * sizeof(int32_t));
     cudaMemset(s->amask, 0, (size_t)s->stride * sizeof(int32_t));
     cudaMemset(s->rob_it, 0, (size_t)s->stride);
@@ -678,6 +691,9 @@ int gg_stack_create(const GgModel* model, const GgStackTask* task, int n_envs, i
 int gg_stack_destroy(GgStackSim* s) {
     if (!s) return 0;
     cudaSetDevice(s->device);
+    if (s->side) { cudaStreamSynchronize(s->side); cudaStreamDestroy(s->side); }
+    if (s->ev_fork) cudaEventDestroy(s->ev_fork);
+    if (s->ev_join) cudaEventDestroy(s->ev_join);
     cudaFree(s->done); cudaFree(s->flags); cudaFree(s->stats); cudaFree(s->work); cudaFree(s->acc); cudaFree(s->ncon); cudaFree(s->iters);
     cudaFree(s->coop_list); cudaFree(s->coop_ctr); cudaFree(s->slot);
     cudaFree(s->amask); cudaFree(s->rob_it); cudaFree(s->iso_nc); cudaFree(s->iso_it);
