@@ -404,7 +404,7 @@ def run_gpu(args):
         simr.close()
         # end to end through the gymnasium surface with a host-resident policy (zero-copy pinned actions in, reward / flags out)
         envd = gym.make("gym_genesis/CubeStack-v0", robot="franka", num_envs=n, device=dev, auto_reset=True, reset_prob=1.0 / 200,
-                        seed=args.seed, first_env_id=rank * n, host_io=True).unwrapped
+                        seed=args.seed, first_env_id=rank * n, host_io=True, scene="empty").unwrapped
         envd.reset(seed=args.seed)
         hd = [ad[k].cpu().pin_memory() for k in range(4)]
         for k in range(5):
@@ -418,7 +418,7 @@ def run_gpu(args):
         d1.record()
         torch.cuda.synchronize(dev)
         wd["e2e"] = {"value": n * 200 / (d0.elapsed_time(d1) * 1e-3), "unit": "env-steps/s", "h2d_bytes_per_step": n * 9 * 4,
-                     "d2h_bytes_per_step": n * 4 + 2 * n, "api": "gym.make('gym_genesis/CubeStack-v0', robot='franka', host_io=True).unwrapped.step(pinned host action)"}
+                     "d2h_bytes_per_step": n * 4 + 2 * n, "api": "gym.make('gym_genesis/CubeStack-v0', robot='franka', scene='empty', host_io=True).unwrapped.step(pinned host action)"}
         envd.close()
 
     # ---- BASELINE.json configs[3]: SO-101 cube pick (6 hinge dofs), same shape of workload ----

@@ -4,8 +4,10 @@ Same program as the reference's `examples/franka/stack_cube_state.py` -- gym.mak
 (Cartesian way-points -> `robot.inverse_kinematics` -> joint-space interpolation, 80 actions per stage), save the envs whose reward
 was ever > 0 as LeRobot episodes -- with the host round trips removed: IK runs on the GPU (`gg_ik`), frames are recorded on the
 GPU (`gg_stack_record`) and the successful envs come back with one copy per episode (`gg_stack_export_successful`).
-The way-point heights are the reference's (`:33-49`) shifted by the Panda's hand-to-pad distance where the literal value would
-put the pads below the table (grasp: hand 0.105 above the cube centre; place / release: 0.148 above the table + cube_2).
+`--scene kitchen` (default) is what the reference's `CubeStack-v0` + franka builds -- the Panda at morph scale 0.6 next to the kitchen
+island -- and uses the reference's way-point heights literally (`:33-49`: hover 0.25, grasp 0.045, lift 0.28, place / release 0.18
+above the cube centres, tuned for that 0.6-scale gripper); `--scene empty` is the full-size Panda on the ground plane
+(`FrankaCubeStackEmptyBatch`) with the heights shifted by its hand-to-pad distance (grasp 0.105, place / release 0.148).
 
     python examples/franka/stack_cube_state.py --num-envs 1024 --episodes 1 --out data/stack_cube
 """
@@ -28,7 +30,11 @@ N_WP = {"hover": 8, "grasp": 8, "lift": 8, "place": 11, "release": 11}
 HORIZON = sum((80 // (N_WP[s] - 1)) * (N_WP[s] - 1) for s in STAGES)
 
 
-def expert_policy(robot, obs, stage):
+# hand height above the cube centre per stage: (hover, grasp, lift, carry, place / release)
+HEIGHTS = {"kitchen": (0.25, 0.045, 0.28, 0.25, 0.18), "empty": (0.25, 0.105, 0.28, 0.25, 0.148)}
+
+
+def expert_policy(robot, obs, stage, heights=HEIGHTS["empty"], grip_open=GRIP_OPEN):
     """Reference `expert_policy` (stack_cube_state.py:18-109): returns a list of (B, 9) joint-target tensors for one stage."""
     es = obs["environment_state"]
     B, dev = es.shape[0], es.device
@@ -37,16 +43,17 @@ def expert_policy(robot, obs, stage):
     cube1, cube2 = es[:, :3], es[:, 11:14]
     off = lambda z, y=0.0: torch.tensor([0.0, y, z], device=dev)
     hover_pos = None
+    h_hover, h_grasp, h_lift, h_carry, h_place = heights
     if stage == "hover":
-        target, grip = cube1 + off(0.25), GRIP_OPEN
+        target, grip = cube1 + off(h_hover), grip_open
     elif stage == "grasp":
-        target, grip = cube1 + off(0.105), GRIP_CLOSED
+        target, grip = cube1 + off(h_grasp), GRIP_CLOSED
     elif stage == "lift":
-        target, grip = cube1 + off(0.28), GRIP_CLOSED
+        target, grip = cube1 + off(h_lift), GRIP_CLOSED
     elif stage == "place":
-        hover_pos, target, grip = cube2 + off(0.25), cube2 + off(0.148), GRIP_CLOSED
+        hover_pos, target, grip = cube2 + off(h_carry), cube2 + off(h_place, 0.004), GRIP_CLOSED      # :44: 4 mm y offset
     elif stage == "release":
-        hover_pos, target, grip = cube2 + off(0.25), cube2 + off(0.148), GRIP_OPEN
+        hover_pos, target, grip = cube2 + off(h_carry), cube2 + off(h_place), grip_open
     else:
         raise ValueError(f"Unknown stage: {stage}")
     current = eef.get_pos(envs_idx=torch.arange(B, device=dev))
@@ -71,7 +78,7 @@ def expert_policy(robot, obs, stage):
     if stage == "grasp":                                       # close over the last five actions (:96-103)
         for i, q in enumerate(path):
             k = i - (len(path) - 5)
-            q[:, -2:] = GRIP_OPEN if k < 0 else (1 - k / 5) * GRIP_OPEN + (k / 5) * GRIP_CLOSED
+            q[:, -2:] = grip_open if k < 0 else (1 - k / 5) * grip_open + (k / 5) * GRIP_CLOSED
     else:
         for q in path:
             q[:, -2:] = grip
@@ -83,8 +90,9 @@ def main():
     ap.add_argument("--num-envs", type=int, default=1024)
     ap.add_argument("--episodes", type=int, default=1)
     ap.add_argument("--out", default="data/stack_cube")
+    ap.add_argument("--scene", default="kitchen", choices=["kitchen", "empty"])
     args = ap.parse_args()
-    env = gym.make("gym_genesis/CubeStack-v0", enable_pixels=False, robot="franka", num_envs=args.num_envs).unwrapped
+    env = gym.make("gym_genesis/CubeStack-v0", enable_pixels=False, robot="franka", num_envs=args.num_envs, scene=args.scene).unwrapped
     sim = env._env.sim
     rec = TrajectoryRecorder(sim, horizon=HORIZON)
     writer = LeRobotWriter(args.out, fps=60, robot_type="franka")
@@ -93,7 +101,7 @@ def main():
         obs, _ = env.reset()
         t = 0
         for stage in STAGES:
-            path = expert_policy(env.get_robot(), obs, stage)
+            path = expert_policy(env.get_robot(), obs, stage, HEIGHTS[args.scene])
             if t == 0:
                 rec.begin_episode()
             for action in path:

@@ -12,7 +12,8 @@ import numpy as np
 import torch
 
 from .gym_api import gym
-from .tasks import FrankaCubePickBatch, FrankaCubeStackEmptyBatch, So101CubePickBatch, So101CubeStackBatch, So101CubeStackOne
+from .tasks import (FrankaCubePickBatch, FrankaCubeStackEmptyBatch, FrankaCubeStackKitchenBatch, So101CubePickBatch, So101CubeStackBatch,
+                    So101CubeStackOne)
 
 
 class GenesisEnv(gym.Env):
@@ -96,13 +97,16 @@ class GenesisEnv(gym.Env):
                              observation_width=self.observation_width, num_envs=self.num_envs, env_spacing=self.env_spacing,
                              camera_capture_mode=self.camera_capture_mode, strip_environment_state=self.strip_environment_state)
         common_kwargs.update(self._sim_kwargs)
-        # the reference map (env.py:111-118) sends ("franka", "cube_stack") to the kitchen-scene variant of the same task;
-        # its physics (Panda + five free cubes on a flat support) is FrankaCubeStackEmptyBatch, built here.
-        # ("so101", "cube_stack") is the reference's CubeStackBatch (so101/cube_stack_batch.py).
+        # the reference map (env.py:111-118): ("franka", "cube_stack") is the kitchen-island variant (scaled Panda, cubes on the
+        # island top); `scene="empty"` selects FrankaCubeStackEmptyBatch, the plane variant the reference ships but does not wire
+        # (SURVEY.md 8f-1).  ("so101", "cube_stack") is CubeStackBatch (8f-3), num_envs = 0 its unbatched form.
+        scene = common_kwargs.pop("scene", "kitchen")
+        if scene not in ("kitchen", "empty"):
+            raise ValueError(f"scene must be 'kitchen' or 'empty', got {scene!r}")
         task_map = {
             ("franka", "cube_pick", True): FrankaCubePickBatch,
             ("so101", "cube_pick", True): So101CubePickBatch,
-            ("franka", "cube_stack", True): FrankaCubeStackEmptyBatch,
+            ("franka", "cube_stack", True): FrankaCubeStackKitchenBatch if scene == "kitchen" else FrankaCubeStackEmptyBatch,
             ("so101", "cube_stack", True): So101CubeStackBatch,
             ("so101", "cube_stack", False): So101CubeStackOne,       # num_envs = 0: unbatched shapes (env.py:114)
         }

@@ -410,26 +410,36 @@ def _cube_body(size=CUBE_SIZE, density=GENESIS_COMPAT_RIGID_DENSITY):
     return Body("cube", -1, (0.65, 0.0, size / 2), (1, 0, 0, 0), jtype=FREE, mass=m, inertia=(i, i, i, 0, 0, 0))
 
 
-def franka_cube_pick_model() -> SceneModel:
-    """Plane + Panda (9 dofs) + free 4 cm cube: the scene of `franka/cube_pick.py:50-54`."""
-    bodies = [Body("link0", -1, (0, 0, 0), (1, 0, 0, 0), mass=0.629769, com=(-0.041018, -0.00014, 0.049974),
-                   inertia=(0.00315, 0.00388, 0.004285, 8.2904e-7, 0.00015, 8.2299e-6))]
+def franka_bodies(scale: float = 1.0, base_pos=(0.0, 0.0, 0.0)):
+    """Panda body table (link0 .. link7, hand, two fingers) and its pad geoms.  `scale` is the MJCF morph scale of the kitchen
+    scenes (`tasks/utils.py:369-376`: scale 0.6 at (-0.5, 0, 0.7)): lengths x s, masses x s^3, inertias x s^5; joint ranges, armature,
+    damping and the task's explicit gains are kept ([UPSTREAM-RECALL]: Genesis scales geometry and inertial data of a morph)."""
+    s = float(scale)
+    sc = lambda v: tuple(float(x) * s for x in v)
+    bodies = [Body("link0", -1, tuple(float(x) for x in base_pos), (1, 0, 0, 0), mass=0.629769 * s ** 3, com=sc((-0.041018, -0.00014, 0.049974)),
+                   inertia=tuple(i * s ** 5 for i in (0.00315, 0.00388, 0.004285, 8.2904e-7, 0.00015, 8.2299e-6)))]
     for j, (name, parent, pos, quat, rng, mass, com, inertia) in enumerate(_PANDA_LINKS):
-        bodies.append(Body(name, parent, pos, quat, jtype=HINGE, axis=(0, 0, 1), range=rng, limited=True,
+        bodies.append(Body(name, parent, sc(pos), quat, jtype=HINGE, axis=(0, 0, 1), range=rng, limited=True,
                            armature=0.1, damping=1.0, kp=_PANDA_KP[j], kv=_PANDA_KV[j],
-                           frc=(-_PANDA_FRC[j], _PANDA_FRC[j]), mass=mass, com=com, inertia=inertia))
-    bodies.append(Body("hand", 7, (0, 0, 0.107), (0.9238795, 0, 0, -0.3826834), mass=0.73, com=(-0.01, 0, 0.03),
-                       inertia=(0.001, 0.0025, 0.0017, 0, 0, 0)))
+                           frc=(-_PANDA_FRC[j], _PANDA_FRC[j]), mass=mass * s ** 3, com=sc(com), inertia=tuple(i * s ** 5 for i in inertia)))
+    bodies.append(Body("hand", 7, sc((0, 0, 0.107)), (0.9238795, 0, 0, -0.3826834), mass=0.73 * s ** 3, com=sc((-0.01, 0, 0.03)),
+                       inertia=tuple(i * s ** 5 for i in (0.001, 0.0025, 0.0017, 0, 0, 0))))
     for f, (name, quat) in enumerate((("left_finger", (1, 0, 0, 0)), ("right_finger", (0, 0, 0, 1)))):
-        bodies.append(Body(name, 8, (0, 0, 0.0584), quat, jtype=SLIDE, axis=(0, 1, 0), range=(0.0, 0.04), limited=True,
+        bodies.append(Body(name, 8, sc((0, 0, 0.0584)), quat, jtype=SLIDE, axis=(0, 1, 0), range=(0.0, 0.04 * s), limited=True,
                            armature=0.1, damping=1.0, kp=_PANDA_KP[7 + f], kv=_PANDA_KV[7 + f],
-                           frc=(-_PANDA_FRC[7 + f], _PANDA_FRC[7 + f]), mass=0.015,
-                           inertia=(2.375e-6, 2.375e-6, 7.5e-7, 0, 0, 0)))
-    bodies.append(_cube_body())
+                           frc=(-_PANDA_FRC[7 + f], _PANDA_FRC[7 + f]), mass=0.015 * s ** 3,
+                           inertia=tuple(i * s ** 5 for i in (2.375e-6, 2.375e-6, 7.5e-7, 0, 0, 0))))
     geoms = []
     for fb in (9, 10):
         for half, pos in _PANDA_PADS:
-            geoms.append(BoxGeom(fb, half, pos, group=0))
+            geoms.append(BoxGeom(fb, sc(half), sc(pos), group=0))
+    return bodies, geoms
+
+
+def franka_cube_pick_model() -> SceneModel:
+    """Plane + Panda (9 dofs) + free 4 cm cube: the scene of `franka/cube_pick.py:50-54`."""
+    bodies, geoms = franka_bodies()
+    bodies.append(_cube_body())
     geoms.append(BoxGeom(11, (CUBE_SIZE / 2,) * 3, group=1))
     return SceneModel("franka", bodies, geoms, eef_body=8, cube_body=11, home_q=FRANKA_HOME.copy(), n_arm=7, n_fing=2)
 
@@ -461,9 +471,37 @@ def franka_cube_stack_model(n_distractors: int = 3) -> SceneModel:
                       max_contacts=GENESIS_COMPAT_MAX_CONTACTS_STACK)
 
 
-def get_model(robot: str, task: str = "cube_pick") -> SceneModel:
+KITCHEN_ISLAND_TOP_Z = 0.7000312834978104     # tasks/utils.py:378-384 (= -0.2003899186849594 + GLB bounding-box top)
+# cube_1, cube_2 (franka/cube_stack_kitchen_batch.py:71-72, 78-79), distractors (:87-88): x_lo, x_hi, y_lo, y_hi
+_KITCHEN_SPAWN = [(-0.3, -0.1, -0.15, 0.15), (-0.3, -0.1, -0.15, 0.15), (-0.35, 0.0, -0.2, 0.2), (-0.35, 0.0, -0.2, 0.2), (-0.35, 0.0, -0.2, 0.2)]
+_KITCHEN_POS = [(0.1, 0.0), (-0.1, 0.05), (-0.2, -0.15), (0.15, 0.2), (-0.25, 0.1)]       # utils.py:386-425 (distractors: unseeded draws)
+
+
+def franka_cube_stack_kitchen_model() -> SceneModel:
+    """`FrankaCubeStackKitchenBatch` (`franka/cube_stack_kitchen_batch.py:26-150`, scene `tasks/utils.py:239-427`): what the
+    reference wires to `CubeStack-v0` + franka (`env.py:115`).  Panda at (-0.5, 0, 0.7) with morph scale 0.6, five free 4 cm cubes
+    on the kitchen island (its top modelled as a plane, as for the SO-101 scenes; the rest of the kitchen has `collision=False`),
+    same gains, observation and reward as the plane variant."""
+    bodies, geoms = franka_bodies(0.6, (-0.5, 0.0, 0.7))
+    z = KITCHEN_ISLAND_TOP_Z + 0.02 + 0.001                                      # cube_stack_kitchen_batch.py:67
+    obj = []
+    for k in range(5):
+        b = _cube_body()
+        b.name = ("cube_1", "cube_2")[k] if k < 2 else f"distractor_{k - 2}"
+        b.pos = (*_KITCHEN_POS[k], z)
+        obj.append(len(bodies))
+        bodies.append(b)
+        geoms.append(BoxGeom(obj[-1], (CUBE_SIZE / 2,) * 3, group=1))
+    # reset writes the literal finger opening 0.04 (:94), beyond the scaled finger range (0.024): the joint-limit rows push it
+    # back within a few steps, as they would upstream
+    return SceneModel("franka_stack_kitchen", bodies, geoms, eef_body=8, cube_body=obj[0], home_q=FRANKA_HOME.copy(), n_arm=7, n_fing=2,
+                      plane_z=KITCHEN_ISLAND_TOP_Z, spawn_z=z, obj_bodies=obj, obj_spawn=_KITCHEN_SPAWN, task="stack",
+                      max_contacts=GENESIS_COMPAT_MAX_CONTACTS_STACK)
+
+
+def get_model(robot: str, task: str = "cube_pick", scene: str = "kitchen") -> SceneModel:
     if robot == "franka" and task == "cube_stack":
-        return franka_cube_stack_model()
+        return franka_cube_stack_kitchen_model() if scene == "kitchen" else franka_cube_stack_model()
     if robot == "franka":
         return franka_cube_pick_model()
     if robot == "so101" and task == "cube_stack":

@@ -56,6 +56,7 @@ class _EefLink(_Link):
 
 class FrankaCubeStackEmptyBatch(CubePickBatch):
     robot_name = "franka"
+    scene_name = "empty"
 
     def __init__(self, enable_pixels, observation_height, observation_width, num_envs, env_spacing, camera_capture_mode,
                  strip_environment_state, device="cuda", auto_reset=False, time_limit=False, solver_iterations=10,
@@ -71,7 +72,7 @@ class FrankaCubeStackEmptyBatch(CubePickBatch):
         self.camera_capture_mode = camera_capture_mode
         self.strip_environment_state = strip_environment_state
         self._random = np.random.RandomState()
-        self.model = get_model(self.robot_name, "cube_stack")
+        self.model = get_model(self.robot_name, "cube_stack", self.scene_name)
         self.sim = BatchedStackSim(self.model, num_envs, device=device, solver_iterations=solver_iterations,
                                    solver_tolerance=solver_tolerance, auto_reset=auto_reset, time_limit=time_limit,
                                    reset_prob=reset_prob, seed=seed, first_env_id=first_env_id)
@@ -107,6 +108,13 @@ class FrankaCubeStackEmptyBatch(CubePickBatch):
             out[:, k, 1] = self._random.uniform(ylo, yhi, size=(B,))
         return out
 
+
+
+class FrankaCubeStackKitchenBatch(FrankaCubeStackEmptyBatch):
+    """`FrankaCubeStackKitchenBatch` (`gym_genesis/tasks/franka/cube_stack_kitchen_batch.py:26-150`): the variant the reference wires
+    to `CubeStack-v0` + franka (`env.py:115`) -- Panda at (-0.5, 0, 0.7) with morph scale 0.6, cubes on the kitchen island
+    (`tasks/utils.py:369-427`), spawn ranges `:71-88`; same protocol, observation and reward as the plane variant."""
+    scene_name = "kitchen"
 
 
 class So101CubeStackBatch(FrankaCubeStackEmptyBatch):

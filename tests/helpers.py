@@ -148,11 +148,11 @@ def stack_random_states(m, rng, n):
     if n > 1:
         Q[1, nu + 7:nu + 9] = Q[1, nu:nu + 2] + [0.021, 0.012]                 # cube_2 overlaps cube_1
     if n > 2:
-        Q[2, nu + 7:nu + 14] = [Q[2, nu], Q[2, nu + 1], 0.0199, 1, 0, 0, 0]    # cube_1 on top of cube_2
-        Q[2, nu + 2:nu + 7] = [0.0597, 1, 0, 0, 0]
+        Q[2, nu + 7:nu + 14] = [Q[2, nu], Q[2, nu + 1], m.plane_z + 0.0199, 1, 0, 0, 0]    # cube_1 on top of cube_2
+        Q[2, nu + 2:nu + 7] = [m.plane_z + 0.0597, 1, 0, 0, 0]
         QD[2, nu:nu + 12] = 0
     if n > 3:
-        Q[3, nu + 2] = 0.3
+        Q[3, nu + 2] = m.plane_z + 0.3
         QD[3, nu:nu + 6] = rng.normal(0, 0.5, 6)
     T = m.home_q + rng.uniform(-0.3, 0.3, (n, nu))
     T[:, m.n_arm:] = rng.uniform(-0.02, 0.04, (n, m.n_fing))

@@ -248,7 +248,7 @@ def test_gym_surface_cube_stack(sm):
     import gym_genesis  # noqa: F401  (registers the ids on the B200 backend)
     from gym_genesis_b200.gym_api import gym
     n = 48
-    env = gym.make("gym_genesis/CubeStack-v0", robot="franka", num_envs=n)
+    env = gym.make("gym_genesis/CubeStack-v0", robot="franka", num_envs=n, scene="empty")
     u = env.unwrapped
     assert u.observation_space["agent_pos"].shape == (9,) and u.observation_space["environment_state"].shape == (14,)
     obs, info = env.reset(seed=3)
@@ -482,11 +482,42 @@ def test_gym_surface_host_io_cube_stack():
     import gym_genesis  # noqa: F401
     from gym_genesis_b200.gym_api import gym
     n = 64
-    env = gym.make("gym_genesis/CubeStack-v0", robot="franka", num_envs=n, host_io=True).unwrapped
+    env = gym.make("gym_genesis/CubeStack-v0", robot="franka", num_envs=n, host_io=True, scene="empty").unwrapped
     obs, info = env.reset(seed=0)
     act = np.tile(FRANKA_HOME.astype(np.float32), (n, 1))
     obs, reward, terminated, truncated, info = env.step(act)                           # numpy action, as in the reference README
     assert reward.device.type == "cpu" and reward.shape == (n,) and terminated.dtype == torch.bool and not truncated.any()
     assert obs["agent_pos"].is_cuda and obs["environment_state"].shape == (n, 14)
     assert torch.equal(reward, env._env.sim.reward.cpu())
+    env.close()
+
+
+# ---- FrankaCubeStackKitchenBatch: what the reference wires to CubeStack-v0 + franka (scaled Panda on the kitchen island) ----------
+def test_kitchen_variant_substep_and_surface(Sim):
+    from gym_genesis_b200.model import franka_cube_stack_kitchen_model
+    from oracle.binding import Oracle
+    m = franka_cube_stack_kitchen_model()
+    orc = Oracle(m, np.float64)
+    n = 96
+    rng = np.random.default_rng(61)
+    sim = Sim(m, n)
+    Q, QD, T = stack_clutter_states(m, sim.gg_model, rng, n)
+    Q2, QD2, T2 = stack_random_states(m, rng, n)
+    Q2[:, :9] = np.clip(Q2[:, :9], np.array(list(sim.gg_model.lim_lo)), np.array(list(sim.gg_model.lim_hi)))
+    for (q0, qd0, t0) in ((Q, QD, T), (f32(Q2).astype(np.float64), QD2, T2)):
+        qa0 = np.zeros_like(qd0)
+        q, qd, qa = _one_substep(sim, q0, qd0, qa0, t0)
+        qo, qdo, qao = q0.copy(), qd0.copy(), qa0.copy()
+        info, _ = orc.step(qo, qdo, qao, t0, iterations=300, tol=1e-12)
+        assert (sim.step_info()[0].cpu().numpy() == info[:, 0]).all()
+        eq, ev = stack_substep_errors(q0, qd0, qo, qdo, q, qd, _asm(orc, q0, qd0, t0))
+        assert eq.max() < TOL_Q_ABS and ev.max() < 1.0, (eq.max(), ev.max(), int(np.argmax(ev)))
+    import gym_genesis  # noqa: F401
+    from gym_genesis_b200.gym_api import gym
+    env = gym.make("gym_genesis/CubeStack-v0", robot="franka", num_envs=32)            # the reference's mapping: kitchen variant
+    obs, _ = env.reset(seed=4)
+    es = obs["environment_state"].cpu().numpy()
+    assert obs["agent_pos"].shape == (32, 9) and es.shape == (32, 14)
+    assert (es[:, 0] > -0.31).all() and (es[:, 0] < -0.09).all() and np.abs(es[:, 2] - (m.plane_z + 0.02)).max() < 2e-3   # :71, :67
+    assert np.abs(obs["agent_pos"][:, 2].cpu().numpy() - 1.037).max() < 5e-3                                            # scaled arm at home
     env.close()
