@@ -12,8 +12,8 @@ import numpy as np
 import torch
 
 from .gym_api import gym
-from .tasks import (FrankaCubePickBatch, FrankaCubeStackEmptyBatch, FrankaCubeStackKitchenBatch, So101CubePickBatch, So101CubeStackBatch,
-                    So101CubeStackOne)
+from .tasks import (FrankaCubePickBatch, FrankaCubeStackEmptyBatch, FrankaCubeStackKitchenBatch, FrankaCubeStackOne, So101CubePickBatch,
+                    So101CubeStackBatch, So101CubeStackOne)
 
 
 class GenesisEnv(gym.Env):
@@ -109,6 +109,7 @@ class GenesisEnv(gym.Env):
             ("franka", "cube_stack", True): FrankaCubeStackKitchenBatch if scene == "kitchen" else FrankaCubeStackEmptyBatch,
             ("so101", "cube_stack", True): So101CubeStackBatch,
             ("so101", "cube_stack", False): So101CubeStackOne,       # num_envs = 0: unbatched shapes (env.py:114)
+            ("franka", "cube_stack", False): FrankaCubeStackOne,     # env.py:116
         }
         key = (self.robot, task_name, self.num_envs > 0)
         if key not in task_map:

@@ -147,23 +147,20 @@ class So101CubeStackBatch(FrankaCubeStackEmptyBatch):
         return out
 
 
-class So101CubeStackOne:
-    """Unbatched SO-101 stacking task (`gym_genesis/tasks/so101/cube_stack.py`, selected by `num_envs=0`, env.py:114,120): the same
-    scene, reset stream (scalar draws: one x / y per cube, `:66-93` -- identical to the batched stream at B = 1), reward and
-    observations with the env dimension dropped: agent_pos (6,), environment_state (14,), scalar reward."""
+class _UnbatchedStack:
+    """Unbatched stacking task (selected by `num_envs=0`, reference env.py:114-120): the batched class at B = 1 with the env
+    dimension dropped from observations and reward.  The reference's unbatched resets draw one scalar x / y per cube, which
+    consumes the host RandomState exactly like the batched vector draws at B = 1."""
+    batch_cls = None
 
     def __init__(self, enable_pixels, observation_height, observation_width, num_envs, env_spacing, camera_capture_mode,
                  strip_environment_state, **sim_kwargs):
-        self._b = So101CubeStackBatch(enable_pixels, observation_height, observation_width, 1, env_spacing, camera_capture_mode,
-                                      strip_environment_state, **sim_kwargs)
+        self._b = self.batch_cls(enable_pixels, observation_height, observation_width, 1, env_spacing, camera_capture_mode,
+                                 strip_environment_state, **sim_kwargs)
         self.num_envs = 0
         for name in ("observation_space", "action_space", "scene", "sim", "model", "robot", "eef", "cube", "cube_1", "cube_2",
                      "distractor_cubes", "motors_dof", "fingers_dof", "enable_pixels"):
             setattr(self, name, getattr(self._b, name))
-
-    @property
-    def so_101(self):
-        return self._b.robot
 
     def seed(self, seed):
         self._b.seed(seed)
@@ -187,3 +184,24 @@ class So101CubeStackOne:
 
     def get_cams(self):
         return self._b.get_cams()
+
+
+class FrankaCubeStackOne(_UnbatchedStack):
+    """`gym_genesis/tasks/franka/cube_stack_one.py`: the unbatched kitchen-island variant (same spawn ranges `:68-85`, home pose and
+    gains as `FrankaCubeStackKitchenBatch`)."""
+    batch_cls = FrankaCubeStackKitchenBatch
+
+    @property
+    def franka(self):
+        return self._b.robot
+
+
+class So101CubeStackOne(_UnbatchedStack):
+    """Unbatched SO-101 stacking task (`gym_genesis/tasks/so101/cube_stack.py`, selected by `num_envs=0`, env.py:114,120): the same
+    scene, reset stream (scalar draws: one x / y per cube, `:66-93` -- identical to the batched stream at B = 1), reward and
+    observations with the env dimension dropped: agent_pos (6,), environment_state (14,), scalar reward."""
+    batch_cls = So101CubeStackBatch
+
+    @property
+    def so_101(self):
+        return self._b.robot

@@ -385,20 +385,20 @@ def test_so101_stack_gym_surface_and_reset_stream(so):
     env.close()
 
 
-def test_so101_stack_unbatched_variant(so):
-    """num_envs = 0 selects the unbatched task (reference env.py:114,120): same physics, env dimension dropped."""
+@pytest.mark.parametrize("robot,adim", [("so101", 6), ("franka", 9)])
+def test_stack_unbatched_variants(robot, adim):
+    """num_envs = 0 selects the unbatched task (reference env.py:114-120): same physics, env dimension dropped."""
     import gym_genesis  # noqa: F401
     from gym_genesis_b200.gym_api import gym
-    m, orc = so
-    env = gym.make("gym_genesis/CubeStack-v0", robot="so101", num_envs=0)
+    env = gym.make("gym_genesis/CubeStack-v0", robot=robot, num_envs=0)
     obs, _ = env.reset(seed=11)
-    assert obs["agent_pos"].shape == (6,) and obs["environment_state"].shape == (14,)
-    ref = gym.make("gym_genesis/CubeStack-v0", robot="so101", num_envs=1)
+    assert obs["agent_pos"].shape == (adim,) and obs["environment_state"].shape == (14,)
+    ref = gym.make("gym_genesis/CubeStack-v0", robot=robot, num_envs=1)
     obs1, _ = ref.reset(seed=11)
     assert torch.equal(obs1["environment_state"][0], obs["environment_state"])      # identical reset stream at B = 1
-    a = torch.as_tensor(f32(m.home_q), device="cuda")
+    a = torch.as_tensor(f32(env.unwrapped._env.model.home_q), device="cuda")
     o2, reward, terminated, truncated, info = env.unwrapped.step(a)
-    assert o2["agent_pos"].shape == (6,) and reward.dim() == 0
+    assert o2["agent_pos"].shape == (adim,) and reward.dim() == 0
     env.close(); ref.close()
 
 
