@@ -739,6 +739,7 @@ GG_WD void stack_solve(const GgModel& M, int max_contacts, const StackIn<NA, NF,
                     const float* ri = &B.H[GG_TRI(i, 0)];
                     const float* rj = &B.H[GG_TRI(j, 0)];
                     float v = ri[j];
+#pragma unroll 4
                     for (int k = 0; k < j; k++) v -= ri[k] * rj[k];
                     t[s] = v;
                 }
