@@ -72,6 +72,7 @@ template <int NU, int K> struct StackBuf {
     float dinv[NV], vx[NV];
     int gl[NV], lo[NV];       // local (compacted) index -> dof and back
     int plist[NPAIR];         // ids of the body pairs in contact
+    int tlist[SK_CAP];        // geom pairs that survive the narrow phase's cull, in task order (<= 5 + 12 + 60 + 10 tasks)
 };
 
 // ---- body / pair bookkeeping ------------------------------------------------------------------------------------------
@@ -280,73 +281,101 @@ GG_HD M3 sk_mat9(const float* r) {
     return R;
 }
 
-// narrow phase, one geom pair per lane and round; contacts come out in the serial order
-// (cubes-plane, pads-plane, pad-major pad-cube, row-major cube-cube) -- oracle.cpp: collide
+// narrow phase; contacts come out in the serial order (cubes-plane, pads-plane, pad-major pad-cube, row-major cube-cube) --
+// oracle.cpp: collide.  Three steps so that the expensive routine runs on full lanes only:
+//   (1) every geom pair ("task") is decoded and CULLED by one lane: bounding spheres, then the six face axes of the SAT
+//       (boxes_may_touch) / the exact box-plane reach -- cheap, ~100 instructions;
+//   (2) the surviving task ids are compacted in task order into B.tlist;
+//   (3) lane i re-decodes survivor i and runs plane_box / box_box: one round for up to 32 survivors (a grasp has ~12) instead of
+//       one round per 32 TASKS (a grasp has 75), each of which paid the full 2 k-instruction box_box for its few live lanes.
+// plane_box and box_box have ONE call site each (they are ~3 k instructions inlined; the solver is instruction-supply bound).
+template <int NA, int NF, int K>
+struct SkPair { int kind, code; V3 cA, hA, cB; M3 RA, RB; };      // kind: 0 none, 1 plane-box, 2 box-box
+
+template <int NA, int NF, int K>
+GG_HD SkPair<NA, NF, K> sk_decode(const GgModel& M, const StackIn<NA, NF, K>& In, unsigned amask, int np, int t) {
+    SkPair<NA, NF, K> P;
+    const V3 ch = ld3(M.cube_half);
+    const float rc = sqrtf(dot(ch, ch));
+    P.kind = 0; P.code = 0; P.cA = mk(0.f, 0.f, 0.f); P.hA = ch; P.cB = P.cA; P.RA = sk_mat9(In.W.lR); P.RB = P.RA;
+    if (t < K) {
+        const float* o = In.obj[t];
+        if ((amask >> (1 + t)) & 1u) {
+            P.kind = 1; P.cA = mk(o[0], o[1], o[2]); P.RA = qmat(mkq(o[3], o[4], o[5], o[6]));
+            P.code = sk_code(sk_pair_id<K>(0, 4 + t), 0, 4 + t);
+        }
+    } else if (t < K + np + np * K) {
+        t -= K;
+        const bool plane = t < np;
+        const int g = plane ? t : (t - np) / K;
+        const int k = plane ? 0 : (t - np) % K;
+        const int b = M.pad_body[g];
+        const int fi = b - 1 < 0 ? 0 : (b - 1 < NF ? b - 1 : 0);
+        const M3 Rb = b == 0 ? sk_mat9(In.W.lR) : sk_mat9(In.W.fR[fi]);
+        const V3 pb = b == 0 ? ld3(In.W.lp) : ld3(In.W.fp[fi]);
+        P.cA = pb + mul(Rb, ld3(M.pad_pos[g]));
+        P.hA = ld3(M.pad_half[g]);
+        const float rp = sqrtf(dot(P.hA, P.hA));
+        if (plane) {
+            if (P.cA.z - rp <= M.plane_z) {
+                P.RA = mmul(Rb, qmat(ldq(M.pad_quat[g])));
+                const float ext = fabsf(P.RA.c0.z) * P.hA.x + fabsf(P.RA.c1.z) * P.hA.y + fabsf(P.RA.c2.z) * P.hA.z;
+                if (P.cA.z - ext <= M.plane_z + 1e-5f) { P.kind = 1; P.code = sk_code(sk_pair_id<K>(0, 1 + b), 0, 1 + b); }
+            }
+        } else {
+            const float* o = In.obj[k];
+            P.cB = mk(o[0], o[1], o[2]);
+            const V3 dd = P.cA - P.cB;
+            if (((amask >> (1 + k)) & 1u) && dot(dd, dd) <= (rp + rc) * (rp + rc)) {
+                P.RA = mmul(Rb, qmat(ldq(M.pad_quat[g]))); P.RB = qmat(mkq(o[3], o[4], o[5], o[6]));
+                if (boxes_may_touch(P.cA, P.RA, P.hA, P.cB, P.RB, ch)) { P.kind = 2; P.code = sk_code(sk_pair_id<K>(1 + b, 4 + k), 1 + b, 4 + k); }
+            }
+        }
+    } else {
+        t -= K + np + np * K;
+        int i = 0;
+        while (t >= K - 1 - i) { t -= K - 1 - i; i++; }
+        const int j = i + 1 + t;
+        const float* oi = In.obj[i];
+        const float* oj = In.obj[j];
+        P.cA = mk(oi[0], oi[1], oi[2]); P.cB = mk(oj[0], oj[1], oj[2]);
+        const V3 dd = P.cA - P.cB;
+        if (((amask >> (1 + i)) & (amask >> (1 + j)) & 1u) && dot(dd, dd) <= 4.f * rc * rc) {
+            P.RA = qmat(mkq(oi[3], oi[4], oi[5], oi[6])); P.RB = qmat(mkq(oj[3], oj[4], oj[5], oj[6]));
+            if (boxes_may_touch(P.cA, P.RA, ch, P.cB, P.RB, ch)) { P.kind = 2; P.code = sk_code(sk_pair_id<K>(4 + i, 4 + j), 4 + i, 4 + j); }
+        }
+    }
+    return P;
+}
+
 template <int NA, int NF, int K, class WC>
 GG_WD int stack_collide(const GgModel& M, int max_contacts, const StackIn<NA, NF, K>& In, unsigned amask, StackBuf<NA + NF, K>& B, WC& wc) {
     const int lane = wc.lane;
     const int maxc = max_contacts < SK_CAP ? max_contacts : SK_CAP;
     const V3 ch = ld3(M.cube_half);
-    const float rc = sqrtf(dot(ch, ch));
     const int np = (amask & 1u) ? M.n_pads : 0;             // bodies outside the cooperative solve were handled by stack_prep
     const int nT = K + np + np * K + K * (K - 1) / 2;
-    int total = 0;
+    // (1) + (2): cull every task, compact the survivors in task order
+    int nsurv = 0;
     for (int t0 = 0; t0 < nT; t0 += 32) {
+        const int t = t0 + lane;
+        int keep = 0;
+        if (t < nT) keep = sk_decode<NA, NF, K>(M, In, amask, np, t).kind != 0 ? 1 : 0;
+        const int incl = wc.scan_incl(keep);
+        if (keep) B.tlist[nsurv + incl - 1] = t;
+        nsurv += wc.shfli(incl, 31);
+    }
+    wc.sync();
+    // (3): the narrow-phase routines on full lanes
+    int total = 0;
+    for (int s0 = 0; s0 < nsurv; s0 += 32) {
         Contacts8 C;
         C.count = 0;
-        // decode the lane's geom pair, then ONE plane_box / box_box call site (the two routines are ~3 k instructions when
-        // inlined; the solver is instruction-supply bound, see profiles/r01_notes.md)
-        int t = t0 + lane;
-        int kind = 0, code = 0;                                   // 0 none, 1 plane-box, 2 box-box
-        V3 cA = mk(0.f, 0.f, 0.f), hA = ch, cB = cA;
-        M3 RA = sk_mat9(In.W.lR), RB = RA;
-        if (t < nT) {
-            if (t < K) {
-                const float* o = In.obj[t];
-                if ((amask >> (1 + t)) & 1u) {
-                    kind = 1; cA = mk(o[0], o[1], o[2]); RA = qmat(mkq(o[3], o[4], o[5], o[6]));
-                    code = sk_code(sk_pair_id<K>(0, 4 + t), 0, 4 + t);
-                }
-            } else if (t < K + np + np * K) {
-                t -= K;
-                const bool plane = t < np;
-                const int g = plane ? t : (t - np) / K;
-                const int k = plane ? 0 : (t - np) % K;
-                const int b = M.pad_body[g];
-                const int fi = b - 1 < 0 ? 0 : (b - 1 < NF ? b - 1 : 0);
-                const M3 Rb = b == 0 ? sk_mat9(In.W.lR) : sk_mat9(In.W.fR[fi]);
-                const V3 pb = b == 0 ? ld3(In.W.lp) : ld3(In.W.fp[fi]);
-                cA = pb + mul(Rb, ld3(M.pad_pos[g]));
-                hA = ld3(M.pad_half[g]);
-                const float rp = sqrtf(dot(hA, hA));
-                if (plane) {
-                    if (cA.z - rp <= M.plane_z) { kind = 1; RA = mmul(Rb, qmat(ldq(M.pad_quat[g]))); code = sk_code(sk_pair_id<K>(0, 1 + b), 0, 1 + b); }
-                } else {
-                    const float* o = In.obj[k];
-                    cB = mk(o[0], o[1], o[2]);
-                    const V3 dd = cA - cB;
-                    if (((amask >> (1 + k)) & 1u) && dot(dd, dd) <= (rp + rc) * (rp + rc)) {
-                        kind = 2; RA = mmul(Rb, qmat(ldq(M.pad_quat[g]))); RB = qmat(mkq(o[3], o[4], o[5], o[6]));
-                        code = sk_code(sk_pair_id<K>(1 + b, 4 + k), 1 + b, 4 + k);
-                    }
-                }
-            } else {
-                t -= K + np + np * K;
-                int i = 0;
-                while (t >= K - 1 - i) { t -= K - 1 - i; i++; }
-                const int j = i + 1 + t;
-                const float* oi = In.obj[i];
-                const float* oj = In.obj[j];
-                cA = mk(oi[0], oi[1], oi[2]); cB = mk(oj[0], oj[1], oj[2]);
-                const V3 dd = cA - cB;
-                if (((amask >> (1 + i)) & (amask >> (1 + j)) & 1u) && dot(dd, dd) <= 4.f * rc * rc) {
-                    kind = 2; RA = qmat(mkq(oi[3], oi[4], oi[5], oi[6])); RB = qmat(mkq(oj[3], oj[4], oj[5], oj[6]));
-                    code = sk_code(sk_pair_id<K>(4 + i, 4 + j), 4 + i, 4 + j);
-                }
-            }
-        }
-        if (kind == 1) plane_box(M.plane_z, cA, RA, hA, code, 8, C);
-        if (wc.any(kind == 2)) { if (kind == 2) box_box(cA, RA, hA, cB, RB, ch, code, 8, C); }
+        SkPair<NA, NF, K> P;
+        P.kind = 0;
+        if (s0 + lane < nsurv) P = sk_decode<NA, NF, K>(M, In, amask, np, B.tlist[s0 + lane]);
+        if (wc.any(P.kind == 1)) { if (P.kind == 1) plane_box(M.plane_z, P.cA, P.RA, P.hA, P.code, 8, C); }
+        if (wc.any(P.kind == 2)) { if (P.kind == 2) box_box(P.cA, P.RA, P.hA, P.cB, P.RB, ch, P.code, 8, C); }
         const int incl = wc.scan_incl(C.count);
         const int base = total + incl - C.count;
         for (int k = 0; k < C.count; k++) {
