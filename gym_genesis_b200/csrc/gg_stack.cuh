@@ -70,7 +70,7 @@ template <int NU, int K> struct StackBuf {
     float Y[NV][6];
     float H[NH];
     float dinv[NV], vx[NV];
-    int gl[NV], lo[NV];       // local (compacted) index -> dof and back
+    int lo[NV];               // dof -> local (compacted) row index of the active dofs
     int plist[NPAIR];         // ids of the body pairs in contact
     int tlist[SK_CAP];        // geom pairs that survive the narrow phase's cull, in task order (<= 5 + 12 + 60 + 10 tasks)
 };
@@ -396,7 +396,7 @@ GG_WD int stack_collide(const GgModel& M, int max_contacts, const StackIn<NA, NF
 // the solve over the ACTIVE bodies (W.amask != 0).  a_out[d * a_stride] receives the acceleration of the active dofs; the others
 // keep the result of stack_prep's register solves (W.arob, In.aobj), which the caller has already stored there.
 // Ownership: lane l (and l + 32 when more than 32 dofs are active -- a warp-uniform rarity) owns the l-th ACTIVE dof, i.e. row l of
-// the packed Hessian; B.gl / B.lo translate between that compacted index and the dof number.
+// the packed Hessian; dd[] (registers) and B.lo translate between that compacted index and the dof number.
 template <int NA, int NF, bool FH, int K, class WC>
 GG_WD void stack_solve(const GgModel& M, int max_contacts, const StackIn<NA, NF, K>& In, StackBuf<NA + NF, K>& B, int iterations, float tol,
                        WC& wc, float* a_out, int a_stride, int& iters_out, int& ncon_out) {
@@ -471,7 +471,7 @@ GG_WD void stack_solve(const GgModel& M, int max_contacts, const StackIn<NA, NF,
             d = NU + 6 * kb + j;
         }
         dd[s] = d;
-        B.gl[l] = d; B.lo[d] = l;
+        B.lo[d] = l;
         if (d < NA) {
             const V3 k = ld3(W.jk[d]), o = ld3(W.jo[d]);
             const V3 lv = cross(o - O, k);
