@@ -249,14 +249,18 @@ def run_gpu(args):
                    seed=args.seed, first_env_id=rank * n, host_io=True).unwrapped
     env.reset(seed=args.seed)
     for k in range(5):
-        env.step(host_actions[k % 4])
+        obs, reward, terminated, truncated, info = env.step(host_actions[k % 4])
+    # the step returns the SAME pinned host tensors every time (the kernel writes into them): numpy views taken once let the host
+    # read the fresh values each step without paying torch's per-element indexing (~4 us per float(tensor[i]))
+    rew_np, term_np = reward.numpy(), terminated.numpy()
     barrier()
     chk = 0.0
     a0.record()
     for k in range(e2e_steps):
         obs, reward, terminated, truncated, info = env.step(host_actions[k % 4])       # returns after the stream drained
-        chk += float(reward[0]) + float(terminated[-1])                                 # host consumes the result every step
+        chk += rew_np[0] + term_np[-1] + rew_np[n // 2]                                 # host consumes the result every step
     a1.record()
+    assert reward.data_ptr() == rew_np.ctypes.data and terminated.data_ptr() == term_np.ctypes.data
     barrier()
     e2e_ms = a0.elapsed_time(a1)
     env.close()
