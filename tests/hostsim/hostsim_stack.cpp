@@ -119,3 +119,15 @@ void hs_stack_spawn(const GgStackTask* T, uint64_t seed, uint32_t gid, uint32_t 
     gg::stack_spawn_all(*T, seed, gid, episode, T->n_obj, reinterpret_cast<float(*)[2]>(xy));
 }
 }
+
+// diagnostic: the cube-cube broad phase (bounding spheres, then the six face axes of the SAT) for n pairs of cube poses (7 floats each)
+extern "C" void hs_cubes_may_touch(const GgModel* M, int n, const float* a, const float* b, uint8_t* out) {
+    const gg::V3 ch = gg::ld3(M->cube_half);
+    for (int i = 0; i < n; i++) {
+        const float* p = a + 7 * i; const float* q = b + 7 * i;
+        const gg::V3 ca = gg::mk(p[0], p[1], p[2]), cb = gg::mk(q[0], q[1], q[2]);
+        const gg::V3 d = ca - cb;
+        out[i] = gg::dot(d, d) <= 4.f * gg::dot(ch, ch) &&
+                 gg::boxes_may_touch(ca, gg::qmat(gg::mkq(p[3], p[4], p[5], p[6])), ch, cb, gg::qmat(gg::mkq(q[3], q[4], q[5], q[6])), ch);
+    }
+}

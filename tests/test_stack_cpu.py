@@ -291,3 +291,32 @@ def test_so101_spawn_rejection_bit_exact(hostsim, so):
         redrawn += int((first[:2] != xy[:2]).any())
         assert (first[2:] == xy[2:]).all()
     assert 5 < redrawn < 120            # P(|d| < 0.06) on a 0.2 x 0.2 square is ~ 0.24
+
+
+def test_cube_cube_broad_phase_is_conservative(hostsim, gg, sm, orc):
+    """boxes_may_touch (bounding spheres + the six face axes of the SAT) may only err towards "may touch": whenever the oracle's
+    box-box narrow phase finds a contact between two cubes, the flag is set; and it rejects most near misses."""
+    rng = np.random.default_rng(8)
+    n = 6000
+    A = np.zeros((n, 7)); B = np.zeros((n, 7))
+    A[:, :3] = [0.5, 0.4, 0.5]                                            # in the air, away from the gripper
+    d = rng.normal(size=(n, 3)); d /= np.linalg.norm(d, axis=1, keepdims=True)
+    B[:, :3] = A[:, :3] + d * rng.uniform(0.030, 0.072, (n, 1))          # centre distance from deep overlap to beyond the spheres
+    for X in (A, B):
+        q = rng.normal(size=(n, 4)); X[:, 3:] = q / np.linalg.norm(q, axis=1, keepdims=True)
+    A[::4, 3:] = [1, 0, 0, 0]; B[::4, 3:] = [1, 0, 0, 0]                  # axis-aligned pairs: resting neighbours
+    A, B = f32(A), f32(B)
+    flag = np.zeros(n, np.uint8)
+    hostsim.hs_cubes_may_touch(C.byref(gg[0]), n, _p(A), _p(B), _p(flag))
+    q0, _, _ = orc.new_state(1)
+    q0[0, :9] = sm.home_q
+    for k in range(2, 5):
+        q0[0, 9 + 7 * k: 9 + 7 * k + 7] = [2.0 + k, 0, 0.5, 1, 0, 0, 0]   # the other cubes far away, in the air
+    touching = np.zeros(n, bool)
+    for i in range(n):
+        q0[0, 9:16] = A[i]; q0[0, 16:23] = B[i]
+        c = orc.contacts(q0[0])
+        touching[i] = any({int(r[7]), int(r[8])} == {sm.obj_bodies[0], sm.obj_bodies[1]} for r in c)
+    assert touching.sum() > 1000 and (~touching).sum() > 1000
+    assert flag[touching].all(), int((~flag[touching].astype(bool)).sum())
+    assert flag[~touching].mean() < 0.5                                   # the nine edge-edge axes are all it leaves on the table
