@@ -320,3 +320,33 @@ def test_cube_cube_broad_phase_is_conservative(hostsim, gg, sm, orc):
     assert touching.sum() > 1000 and (~touching).sum() > 1000
     assert flag[touching].all(), int((~flag[touching].astype(bool)).sum())
     assert flag[~touching].mean() < 0.5                                   # the nine edge-edge axes are all it leaves on the table
+
+
+def test_kitchen_model_reference_constants_and_substep(hostsim):
+    """FrankaCubeStackKitchenBatch: Panda at morph scale 0.6 at (-0.5, 0, 0.7) (tasks/utils.py:369-376), cubes on the island top,
+    spawn ranges of cube_stack_kitchen_batch.py:71-88; the host build of the device pipeline against the oracle on its states."""
+    from gym_genesis_b200.model import KITCHEN_ISLAND_TOP_Z, franka_cube_pick_model, franka_cube_stack_kitchen_model
+    from helpers import stack_clutter_states
+    from oracle.binding import Oracle
+    k, full = franka_cube_stack_kitchen_model(), franka_cube_pick_model()
+    assert k.obj_spawn[0] == (-0.3, -0.1, -0.15, 0.15) and k.obj_spawn[2] == (-0.35, 0.0, -0.2, 0.2)
+    assert abs(k.plane_z - 0.7000312834978104) < 1e-12 and abs(k.spawn_z - (KITCHEN_ISLAND_TOP_Z + 0.021)) < 1e-12
+    assert tuple(k.bodies[0].pos) == (-0.5, 0.0, 0.7)
+    for b6, b1 in zip(k.bodies[:11], full.bodies[:11]):
+        assert np.allclose(b6.mass, b1.mass * 0.6 ** 3) and np.allclose(b6.inertia, np.asarray(b1.inertia) * 0.6 ** 5)
+        if b6.name != "link0":
+            assert np.allclose(b6.pos, np.asarray(b1.pos) * 0.6)
+    assert list(k.dof_table()["kp"][:9]) == [4500, 4500, 3500, 3500, 2000, 2000, 2000, 100, 100]      # :101
+    xp, _ = k.fk(np.concatenate([k.home_q, k.default_cube_q()]))
+    xf, _ = full.fk(full.full_q(full.home_q))
+    assert np.allclose(xp[8] - [-0.5, 0.0, 0.7], 0.6 * xf[8], atol=1e-9)                                # the scaled arm, same pose
+    gm, task = cabi.compile_gg(k), cabi.compile_stack_task(k)
+    orc = Oracle(k, np.float64)
+    Q, QD, T = stack_clutter_states(k, gm, np.random.default_rng(61), 24)
+    QA = np.zeros_like(QD)
+    qo, qdo, qao = Q.copy(), QD.copy(), QA.copy()
+    info, _ = orc.step(qo, qdo, qao, T, iterations=300, tol=1e-12)
+    q, qd, qa, hinfo = hostsim_stack_step(hostsim, gm, task, Q, QD, QA, T)
+    assert (hinfo[:, 0] == info[:, 0]).all()
+    eq, ev = stack_substep_errors(Q, QD, qo, qdo, q, qd, _asm(orc, Q, QD, T))
+    assert eq.max() < TOL_Q_ABS and ev.max() < 1.0, (eq.max(), ev.max())
