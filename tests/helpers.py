@@ -262,3 +262,27 @@ def pick_clutter_states(m, gg_model, rng, n):
     QD[:, nu:] = rng.normal(0, 0.3, (n, 6))
     T = m.home_q + rng.uniform(-0.5, 0.5, (n, nu))
     return tuple(f32(x).astype(np.float64) for x in (Q, QD, T))
+
+
+# ---- numpy restatement of the device random streams (Philox4x32-10, Random123) -------------------------------------------------------
+# Vectorised over envs so that the full-size tests can reproduce every env's per-step reset draw; pinned to the oracle's generator
+# (tests/test_gpu_fullsize_parity.py::test_philox_numpy_matches_oracle_generator), which is pinned to the Random123 known answers.
+def philox4x32_10_np(c0, c1, c2, c3, k0, k1):
+    c0, c1, c2, c3 = (np.asarray(c, dtype=np.uint32).astype(np.uint64) for c in (c0, c1, c2, c3))
+    k0, k1 = np.uint64(k0), np.uint64(k1)
+    M0, M1, MASK = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57), np.uint64(0xFFFFFFFF)
+    for _ in range(10):
+        p0, p1 = M0 * c0, M1 * c2
+        n0 = (p1 >> np.uint64(32)) ^ c1 ^ k0
+        n1 = p1 & MASK
+        n2 = (p0 >> np.uint64(32)) ^ c3 ^ k1
+        n3 = p0 & MASK
+        c0, c1, c2, c3 = n0, n1, n2, n3
+        k0 = (k0 + np.uint64(0x9E3779B9)) & MASK
+        k1 = (k1 + np.uint64(0xBB67AE85)) & MASK
+    return tuple(c.astype(np.uint32) for c in (c0, c1, c2, c3))
+
+
+def u01_np(x):
+    """uint32 -> float32 in [0, 1): top 24 bits * 2^-24 (gg_math.cuh: u01)."""
+    return (np.asarray(x, dtype=np.uint32) >> np.uint32(8)).astype(np.float32) * np.float32(5.9604644775390625e-8)

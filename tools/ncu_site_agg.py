@@ -1,0 +1,58 @@
+"""Join an ncu source-page CSV (ncu -i X.ncu-rep --page source --csv) with nvdisasm line info of the SAME cubin and aggregate
+executed warp-instructions, stall samples and stall reasons per call site (outermost source line inside the kernel body).
+
+    python tools/ncu_site_agg.py source.csv gg_kernels.sm_100a.cubin step_kernelILi7ELi2ELb0 [--inner] [--min N]
+"""
+import csv
+import re
+import subprocess
+import sys
+from collections import Counter, defaultdict
+
+src_csv, cubin, pat = sys.argv[1:4]
+inner = "--inner" in sys.argv
+minsamp = int(sys.argv[sys.argv.index("--min") + 1]) if "--min" in sys.argv else 10
+
+out = subprocess.run(["nvdisasm", "-gi", "-c", cubin], capture_output=True, text=True).stdout
+on = False
+keys = []
+chain, pending = [], []
+for line in out.splitlines():
+    if line.startswith("//---") and ".text." in line:
+        on = pat in line
+        continue
+    if not on:
+        continue
+    m = re.match(r'\s*//## File "([^"]+)", line (\d+)(.*)', line)
+    if m:
+        pending.append((m.group(1).split("/")[-1], int(m.group(2))))
+        continue
+    if re.match(r"\s+/\*[0-9a-f]{4,6}\*/", line):
+        if pending:
+            chain, pending = pending, []
+        keys.append((chain[0] if inner else chain[-1]) if chain else ("?", 0))
+
+rows = list(csv.reader(open(src_csv)))
+hdr = rows[1]
+body = rows[2:]
+assert len(body) == len(keys), (len(body), len(keys))
+ci = {h: i for i, h in enumerate(hdr)}
+stall_cols = [h for h in hdr if h.startswith("stall_") and "Not Issued" not in h]
+agg = defaultdict(lambda: {"ex": 0, "samp": 0, "static": 0, "st": Counter()})
+tot_ex = tot_s = 0
+for k, r in zip(keys, body):
+    a = agg[k]
+    ex = int(r[ci["Instructions Executed"]]); s = int(r[ci["# Samples"]])
+    a["ex"] += ex; a["samp"] += s; a["static"] += 1
+    tot_ex += ex; tot_s += s
+    for h in stall_cols:
+        v = int(r[ci[h]])
+        if v:
+            a["st"][h[6:]] += v
+print(f"total executed warp-instr {tot_ex}  samples {tot_s}  static rows {len(keys)}")
+print(f"{'site':28s} {'static':>6s} {'exec':>9s} {'ex%':>5s} {'samp':>6s} {'s%':>5s}  top stalls")
+for k, a in sorted(agg.items(), key=lambda x: (x[0][0], x[0][1])):
+    if a["samp"] < minsamp and a["ex"] < tot_ex * 0.005:
+        continue
+    top = " ".join(f"{n}:{v}" for n, v in a["st"].most_common(4))
+    print(f"{k[0] + ':' + str(k[1]):28s} {a['static']:6d} {a['ex']:9d} {100 * a['ex'] / tot_ex:5.1f} {a['samp']:6d} {100 * a['samp'] / tot_s:5.1f}  {top}")
