@@ -60,7 +60,7 @@ class GgConfig(C.Structure):
 
 class GgHostIO(C.Structure):
     _fields_ = [("action", C.c_void_p), ("reward", C.c_void_p), ("terminated", C.c_void_p), ("truncated", C.c_void_p),
-                ("wait", _i)]
+                ("wait", _i), ("reserved0", _i), ("obs_agent", C.c_void_p), ("obs_env", C.c_void_p), ("action_dev", C.c_void_p)]
 
 
 class GgIkConfig(C.Structure):

@@ -96,54 +96,84 @@ template <int NA> struct LinkStoreStrided {      // b points at this lane's colu
     }
 };
 
+// Chain table: the model constants of chain element l (arm link l < NA, finger l - NA) in ONE array, so that the rolled chain loops
+// below read them with a single dynamically indexed constant load (the fingers are children of the last arm link and used to be
+// two further unrolled copies of the loop body: ~700 SASS rows of straight-line code in a kernel that is instruction-fetch bound).
+// Internal to the library (not part of the C ABI): built on the host from GgModel at launch time (make_chain).
+struct GgChain { float e[GG_MAX_DOF][20]; };
+enum { CH_POS = 0, CH_QUAT = 3, CH_MASS = 7, CH_COM = 8, CH_INERTIA = 11, CH_AXIS = 17 };
+inline void make_chain(const GgModel& M, GgChain& C) {
+    for (int l = 0; l < GG_MAX_DOF; l++) for (int k = 0; k < 20; k++) C.e[l][k] = 0.f;
+    for (int l = 0; l < M.n_arm + M.n_fing && l < GG_MAX_DOF; l++) {
+        float* e = C.e[l];
+        const bool fin = l >= M.n_arm; const int f = l - M.n_arm;
+        for (int k = 0; k < 3; k++) { e[CH_POS + k] = fin ? M.fing_pos[f][k] : M.link_pos[l][k]; e[CH_COM + k] = fin ? M.fing_com[f][k] : M.link_com[l][k]; }
+        for (int k = 0; k < 4; k++) e[CH_QUAT + k] = fin ? M.fing_quat[f][k] : M.link_quat[l][k];
+        for (int k = 0; k < 6; k++) e[CH_INERTIA + k] = fin ? M.fing_inertia[f][k] : M.link_inertia[l][k];
+        e[CH_MASS] = fin ? M.fing_mass[f] : M.link_mass[l];
+        for (int k = 0; k < 3; k++) e[CH_AXIS + k] = fin ? M.fing_axis[f][k] : (k == 2 ? 1.f : 0.f);
+    }
+}
+
+// One element of the chain: parent frame (ql, pl, Rl) -> own frame, motion subspace S (world orientation, about the world origin).
+// Hinges turn about their local z axis; `slide` (Panda fingers) translates along the element's axis.
+GG_HD void chain_step(const float* e, bool slide, float qj, Q4& ql, V3& pl, M3& Rl, SV& S) {
+    V3 p0 = pl + mul(Rl, ld3(e + CH_POS));
+    Q4 qn = qmul(ql, ldq(e + CH_QUAT));
+    if (!slide) {
+        float s, c;
+        gg_sincos(0.5f * qj, &s, &c);
+        qn = qmul_z(qn, c, s);
+    }
+    const M3 Rn = qmat(qn);
+    if (slide) {
+        const V3 a = mul(Rn, ld3(e + CH_AXIS));
+        S.a = mk(0.f, 0.f, 0.f); S.l = a; p0 = p0 + a * qj;
+    } else {
+        S.a = Rn.c2; S.l = cross(p0, Rn.c2);
+    }
+    ql = qn; pl = p0; Rl = Rn;
+}
+
+// finger f of a RobotDyn with a statically resolved index (keeps the small per-finger arrays in registers inside the rolled loops)
+template <int NA, int NF> GG_HD void set_finger(RobotDyn<NA, NF>& D, int f, V3 k, V3 o, const M3& R, V3 p) {
+#pragma unroll
+    for (int g = 0; g < NF; g++) if (g == f) { D.fk[g] = k; D.fo[g] = o; D.fR[g] = R; D.fp[g] = p; }
+}
+
 template <int NA, int NF, bool FH, class LS>
-GG_HD void robot_crba(const GgModel& M, const float* q, RobotDyn<NA, NF>& D, LS& ls) {
+GG_HD void robot_crba(const GgModel& M, const GgChain& C, const float* q, RobotDyn<NA, NF>& D, LS& ls) {
     constexpr int NU = NA + NF;
     Q4 ql = ldq(M.base_quat);
     V3 pl = ld3(M.base_pos);
     M3 Rl = qmat(ql);
-    GG_LINK_LOOP
-    for (int l = 0; l < NA; l++) {
-        pl = pl + mul(Rl, ld3(M.link_pos[l]));
-        float s, c;
-        gg_sincos(0.5f * q[l], &s, &c);
-        ql = qmul_z(qmul(ql, ldq(M.link_quat[l])), c, s);
-        Rl = qmat(ql);
-        D.jk[l] = Rl.c2; D.jo[l] = pl;
-        SV Sl; Sl.a = Rl.c2; Sl.l = cross(pl, Rl.c2);
-        ls.setS(l, Sl);
-        ls.setI(l, body_inertia(M.link_mass[l], ld3(M.link_com[l]), M.link_inertia[l], Rl, pl));
-    }
-    D.lq = ql; D.lp = pl; D.lR = Rl;
+    Q4 qa = ql; V3 pa = pl; M3 Ra = Rl;          // frame of the last arm link (parent of the fingers)
     SI Ic; Ic.m = 0.f; Ic.h = mk(0.f, 0.f, 0.f); Ic.I.xx = Ic.I.yy = Ic.I.zz = Ic.I.xy = Ic.I.xz = Ic.I.yz = 0.f;
-#pragma unroll
-    for (int f = 0; f < NF; f++) {
-        Q4 qf = qmul(ql, ldq(M.fing_quat[f]));
-        V3 p0 = pl + mul(Rl, ld3(M.fing_pos[f]));
-        SV Sf; M3 Rf; V3 pf;
-        if (FH) {
-            float s, c;
-            gg_sincos(0.5f * q[NA + f], &s, &c);
-            qf = qmul_z(qf, c, s);
-            Rf = qmat(qf);
-            Sf.a = Rf.c2; Sf.l = cross(p0, Rf.c2); pf = p0;
-            D.fk[f] = Rf.c2; D.fo[f] = p0;
+    GG_LINK_LOOP
+    for (int l = 0; l < NU; l++) {
+        const bool fin = l >= NA;
+        if (fin) { ql = qa; pl = pa; Rl = Ra; }
+        const float* e = C.e[l];
+        SV Sl;
+        chain_step(e, fin && !FH, q[l], ql, pl, Rl, Sl);
+        const SI Il = body_inertia(e[CH_MASS], ld3(e + CH_COM), e + CH_INERTIA, Rl, pl);
+        if (!fin) {
+            D.jk[l] = Rl.c2; D.jo[l] = pl;
+            ls.setS(l, Sl);
+            ls.setI(l, Il);
+            if (l == NA - 1) { qa = ql; pa = pl; Ra = Rl; }
         } else {
-            Rf = qmat(qf);
-            V3 a = mul(Rf, ld3(M.fing_axis[f]));
-            Sf.a = mk(0.f, 0.f, 0.f); Sf.l = a; pf = p0 + a * q[NA + f];
-            D.fk[f] = a; D.fo[f] = pf;
+            // leaf body: its rows of M are complete here (M(f, i) = S_i . (I_f S_f) for the arm dofs, 0 against the other finger)
+            set_finger<NA, NF>(D, l - NA, FH ? Sl.a : Sl.l, pl, Rl, pl);
+            const SV G = apply(Il, Sl);
+            D.Mt[GG_TRI(l, l)] = sdot(Sl, G);
+            GG_LINK_LOOP
+            for (int i = 0; i < NA; i++) D.Mt[GG_TRI(l, i)] = sdot(ls.getS(i), G);
+            for (int g = NA; g < l; g++) D.Mt[GG_TRI(l, g)] = 0.f;
+            Ic = Ic + Il;
         }
-        D.fR[f] = Rf; D.fp[f] = pf;
-        SI If = body_inertia(M.fing_mass[f], ld3(M.fing_com[f]), M.fing_inertia[f], Rf, pf);
-        SV G = apply(If, Sf);
-        D.Mt[GG_TRI(NA + f, NA + f)] = sdot(Sf, G);
-        GG_LINK_LOOP
-        for (int i = 0; i < NA; i++) D.Mt[GG_TRI(NA + f, i)] = sdot(ls.getS(i), G);
-#pragma unroll
-        for (int g = 0; g < f; g++) D.Mt[GG_TRI(NA + f, NA + g)] = 0.f;
-        Ic = Ic + If;
     }
+    D.lq = qa; D.lp = pa; D.lR = Ra;
     GG_LINK_LOOP
     for (int l = NA - 1; l >= 0; l--) {
         Ic = Ic + ls.getI(l);
@@ -167,8 +197,10 @@ struct TargetPtr {
     GG_HD float operator()(int d) const { return t[d]; }
 };
 
+// Dp (optional): receives the frames of the pad-carrying bodies (last arm link, fingers) -- the chain walk of this pass already has
+// them, so the caller's broad phase needs no walk of its own.
 template <int NA, int NF, bool FH, class TF>
-GG_HD void robot_rnea_t(const GgModel& M, const float* q, const float* qd, TF& tf, float* fs) {
+GG_HD void robot_rnea_t(const GgModel& M, const GgChain& C, const float* q, const float* qd, TF& tf, float* fs, RobotDyn<NA, NF>* Dp = nullptr) {
     constexpr int NU = NA + NF;
     float bias[NU];
     SV S[NA]; SV F[NA];
@@ -177,43 +209,64 @@ GG_HD void robot_rnea_t(const GgModel& M, const float* q, const float* qd, TF& t
     M3 Rl = qmat(ql);
     SV V; V.a = mk(0.f, 0.f, 0.f); V.l = mk(0.f, 0.f, 0.f);
     SV A; A.a = mk(0.f, 0.f, 0.f); A.l = mk(0.f, 0.f, M.gravity);   // gravity as base acceleration
-    GG_LINK_LOOP
-    for (int l = 0; l < NA; l++) {
-        pl = pl + mul(Rl, ld3(M.link_pos[l]));
-        float s, c;
-        gg_sincos(0.5f * q[l], &s, &c);
-        ql = qmul_z(qmul(ql, ldq(M.link_quat[l])), c, s);
-        Rl = qmat(ql);
-        S[l].a = Rl.c2; S[l].l = cross(pl, Rl.c2);
-        A = A + crm(V, S[l]) * qd[l];
-        V = V + S[l] * qd[l];
-        SI Il = body_inertia(M.link_mass[l], ld3(M.link_com[l]), M.link_inertia[l], Rl, pl);
-        F[l] = apply(Il, A) + crf(V, apply(Il, V));
-    }
+    Q4 qa = ql; V3 pa = pl; M3 Ra = Rl; SV Va = V, Aa = A;          // last arm link (parent of the fingers)
     SV Fc; Fc.a = mk(0.f, 0.f, 0.f); Fc.l = mk(0.f, 0.f, 0.f);
-#pragma unroll
-    for (int f = 0; f < NF; f++) {
-        Q4 qf = qmul(ql, ldq(M.fing_quat[f]));
-        V3 p0 = pl + mul(Rl, ld3(M.fing_pos[f]));
-        SV Sf; M3 Rf; V3 pf;
-        if (FH) {
-            float s, c;
-            gg_sincos(0.5f * q[NA + f], &s, &c);
-            qf = qmul_z(qf, c, s);
-            Rf = qmat(qf);
-            Sf.a = Rf.c2; Sf.l = cross(p0, Rf.c2); pf = p0;
-        } else {
-            Rf = qmat(qf);
-            V3 a = mul(Rf, ld3(M.fing_axis[f]));
-            Sf.a = mk(0.f, 0.f, 0.f); Sf.l = a; pf = p0 + a * q[NA + f];
+#ifdef GG_SPLIT_RNEA
+    // experiment: two small loops (frames; forces) instead of one loop body that exceeds the L0 instruction cache
+    {
+        SV Sx[NU]; M3 Rx[NU]; V3 px[NU];
+        GG_LINK_LOOP
+        for (int l = 0; l < NU; l++) {
+            const bool fin = l >= NA;
+            if (fin) { ql = qa; pl = pa; Rl = Ra; }
+            SV Sl;
+            chain_step(C.e[l], fin && !FH, q[l], ql, pl, Rl, Sl);
+            Sx[l] = Sl; Rx[l] = Rl; px[l] = pl;
+            if (l == NA - 1) { qa = ql; pa = pl; Ra = Rl; }
+            if (fin && Dp) set_finger<NA, NF>(*Dp, l - NA, FH ? Sl.a : Sl.l, pl, Rl, pl);
         }
-        SV Af = A + crm(V, Sf) * qd[NA + f];
-        SV Vf = V + Sf * qd[NA + f];
-        SI If = body_inertia(M.fing_mass[f], ld3(M.fing_com[f]), M.fing_inertia[f], Rf, pf);
-        SV Ff = apply(If, Af) + crf(Vf, apply(If, Vf));
-        bias[NA + f] = sdot(Sf, Ff);
-        Fc = Fc + Ff;
+        GG_LINK_LOOP
+        for (int l = 0; l < NU; l++) {
+            const bool fin = l >= NA;
+            if (fin) { V = Va; A = Aa; }
+            const float* e = C.e[l];
+            const SV Sl = Sx[l];
+            A = A + crm(V, Sl) * qd[l];
+            V = V + Sl * qd[l];
+            const SI Il = body_inertia(e[CH_MASS], ld3(e + CH_COM), e + CH_INERTIA, Rx[l], px[l]);
+            const SV Fl = apply(Il, A) + crf(V, apply(Il, V));
+            if (!fin) {
+                S[l] = Sl; F[l] = Fl;
+                if (l == NA - 1) { Va = V; Aa = A; }
+            } else {
+                bias[l] = sdot(Sl, Fl);
+                Fc = Fc + Fl;
+            }
+        }
     }
+#else
+    GG_LINK_LOOP
+    for (int l = 0; l < NU; l++) {
+        const bool fin = l >= NA;
+        if (fin) { ql = qa; pl = pa; Rl = Ra; V = Va; A = Aa; }
+        const float* e = C.e[l];
+        SV Sl;
+        chain_step(e, fin && !FH, q[l], ql, pl, Rl, Sl);
+        A = A + crm(V, Sl) * qd[l];
+        V = V + Sl * qd[l];
+        const SI Il = body_inertia(e[CH_MASS], ld3(e + CH_COM), e + CH_INERTIA, Rl, pl);
+        const SV Fl = apply(Il, A) + crf(V, apply(Il, V));
+        if (!fin) {
+            S[l] = Sl; F[l] = Fl;
+            if (l == NA - 1) { qa = ql; pa = pl; Ra = Rl; Va = V; Aa = A; }
+        } else {
+            bias[l] = sdot(Sl, Fl);
+            Fc = Fc + Fl;
+            if (Dp) set_finger<NA, NF>(*Dp, l - NA, FH ? Sl.a : Sl.l, pl, Rl, pl);
+        }
+    }
+#endif
+    if (Dp) { Dp->lq = qa; Dp->lp = pa; Dp->lR = Ra; }
     GG_LINK_LOOP
     for (int l = NA - 1; l >= 0; l--) {
         Fc = Fc + F[l];
@@ -230,16 +283,16 @@ GG_HD void robot_rnea_t(const GgModel& M, const float* q, const float* qd, TF& t
 }
 
 template <int NA, int NF, bool FH>
-GG_HD void robot_rnea(const GgModel& M, const float* q, const float* qd, const float* target, float* fs) {
+GG_HD void robot_rnea(const GgModel& M, const GgChain& C, const float* q, const float* qd, const float* target, float* fs) {
     TargetPtr tf; tf.t = target;
-    robot_rnea_t<NA, NF, FH>(M, q, qd, tf, fs);
+    robot_rnea_t<NA, NF, FH>(M, C, q, qd, tf, fs);
 }
 
 template <int NA, int NF, bool FH>
-GG_HD void robot_dynamics(const GgModel& M, const float* q, const float* qd, const float* target, RobotDyn<NA, NF>& D) {
+GG_HD void robot_dynamics(const GgModel& M, const GgChain& C, const float* q, const float* qd, const float* target, RobotDyn<NA, NF>& D) {
     LinkStoreLocal<NA> ls;
-    robot_crba<NA, NF, FH>(M, q, D, ls);
-    robot_rnea<NA, NF, FH>(M, q, qd, target, D.fs);
+    robot_crba<NA, NF, FH>(M, C, q, D, ls);
+    robot_rnea<NA, NF, FH>(M, C, q, qd, target, D.fs);
 }
 
 // frames of the pad-carrying bodies only (last arm link + fingers): the cube role's broad phase
@@ -1276,10 +1329,10 @@ GG_HD void integrate_cube(const GgModel& M, V3& cp, Q4& cq, V3& cv, V3& cw, floa
 }
 
 template <int NA, int NF, bool FH>
-GG_HD void env_substep(const GgModel& M, EnvState<NA + NF>& s, const float* target, int iterations, float tol, StepInfo& info) {
+GG_HD void env_substep(const GgModel& M, const GgChain& C, EnvState<NA + NF>& s, const float* target, int iterations, float tol, StepInfo& info) {
     constexpr int NU = NA + NF, NV = NU + 6;
     RobotDyn<NA, NF> D;
-    robot_dynamics<NA, NF, FH>(M, s.q, s.qd, target, D);
+    robot_dynamics<NA, NF, FH>(M, C, s.q, s.qd, target, D);
     const M3 cR = qmat(s.cq);
 
     // ---- smooth (unconstrained) acceleration a_s

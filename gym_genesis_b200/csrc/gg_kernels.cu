@@ -33,13 +33,16 @@ int fail(const char* fmt, const char* detail = "") {
     } while (0)
 
 struct StepArgs {
-    GgModel M;
+    GgModel M; gg::GgChain C;
     int n, stride;
     float* state; int32_t* step_count; int32_t* episode; uint8_t* done;
     const float* action; float* obs_agent; float* obs_env; float* reward;
     uint8_t* terminated; uint8_t* truncated;
     const uint8_t* reset_mask; const float* cube_xy;
     float* reward_host; uint8_t* terminated_host; uint8_t* truncated_host;   // nullable pinned-host mirrors (gg_step_host)
+    float* obs_agent_host; float* obs_env_host;   // nullable pinned-host mirrors of the observations (gg_step_host)
+    float* action_dev;        // nullable device copy of the consumed action batch (gg_step_host: PD targets persist on the device)
+    int vec_out;              // 1: observation arrays (and their host mirrors) are 16-byte aligned -> full blocks write 128-bit slabs
     int stage_action;         // 1: action is 16-byte aligned -> full blocks stage their slab with cp.async
     int mode;                 // 0 = env.step, 1 = reset (+ settle) of masked envs, 2 = observe only
     int iterations; float tol;
@@ -86,49 +89,66 @@ template <int NU> __device__ __forceinline__ void store_state(float* __restrict_
 // lane = env, warp = role:
 //   warp 0  MAIN : kinematics + CRBA + Cholesky, smooth acceleration, joint-limit rows, robot-block Newton solve,
 //                  robot integration, end-effector pose, agent_pos
-//   warp 1  RNEA : velocities / accelerations / link forces of the same chain, PD torque -> fs = tau - bias
-//   warp 2  CUBE : pad broad phase, cube-plane contacts + cube-block Newton solve, cube integration, environment_state,
+//   warp 1  RNEA : velocities / accelerations / link forces of the same chain, PD torque -> fs = tau - bias; its chain walk
+//                  yields the frames of the pad-carrying bodies, so it also runs the pad broad phase (coupled flags)
+//   warp 2  CUBE : masked reset / spawn, cube-plane contacts + cube-block Newton solve, cube integration, environment_state,
 //                  reward / terminated / truncated / done, counters, episode statistics
 // The three chains are independent until the points marked by the named barriers below, so the latency of one env.step
 // is the longest role instead of their sum, and 16384 envs put 2.6 warps on every scheduler instead of 0.9.
 // Exchange goes through shared memory ([field][lane], conflict free):
-//   barrier 1 (96 threads): CUBE arrives, RNEA and MAIN wait      -- fs, coupled flags, cube state
+//   barrier 8 (96 threads): CUBE arrives, RNEA and MAIN wait      -- cube state (after a masked reset) for the broad phase
+//   barrier 1 (96 threads): RNEA arrives, MAIN and CUBE wait      -- fs, coupled flags
 //   barrier 2 (64 threads): MAIN arrives, CUBE waits              -- solver statistics of the robot block
 //   barrier 3 (64 threads): MAIN and CUBE wait                    -- end-effector position, non-finite flags
 //   barrier 6 (64 threads): MAIN and RNEA wait                    -- integrated joint positions for the split end-effector chain
 //   barrier 7 (64 threads): RNEA arrives, MAIN waits              -- tail of the end-effector chain
+// The CUBE warp solves its cube block SPECULATIVELY (it does not wait for the broad phase, which sits at the end of the RNEA
+// chain); the result is dropped for the envs that turn out to be coupled.
 //
-// Envs whose pads may touch the cube or the plane ("coupled", decided by the CUBE warp's broad phase) leave the
+// Envs whose pads may touch the cube or the plane ("coupled") leave the
 // thread-per-env mapping: after barrier 1 the three warps of the block become three solver teams and work through the
 // block's coupled envs ONE WARP PER ENV (gg_coop.cuh; 10 KB of shared memory per team).  The MAIN lane of a coupled env
 // publishes its dynamics to the env's slot of a global scratch slab (832 B, L2 resident); after barrier 4 the teams pop
 // envs from a block-local queue (team_queue) until it is empty, barrier 5.  Blocks without coupled envs never execute
 // that code.  (Tried and measured, profiles/r01_notes.md: team buffers in a global scratch slice -- 1.5x slower
 // teams; a second, device-launched kernel for the coupled envs (CUDA dynamic parallelism tail launch) -- 2.6x slower.)
+//
+// Outputs: agent_pos (32 x (7 + NF) floats) and environment_state (32 x 11 floats) of a full block are contiguous slabs of the
+// env-major output arrays; the lanes stage their rows in shared memory and the warp writes the slab with 128-bit stores (and,
+// for gg_step_host callers that ask for them, the same slabs into pinned host memory).  The action slab is staged the other
+// way with 16-byte cp.async and, on request, copied to a device-resident target buffer (PD targets persist across steps).
 // ------------------------------------------------------------------------------------------------
 constexpr int kBlockThreads = 96;
 
 #ifndef GG_MINBLOCKS
 #define GG_MINBLOCKS 4
 #endif
+// -DGG_ONLY_ROLE=r (timing experiment, results are garbage): only role r runs and the named barriers are no-ops -- measures one
+// role's chain when an SM executes nothing but that role's code (instruction-cache footprint experiment, profiles/r02_notes.md)
 __device__ __forceinline__ void bar_sync(int id, int nthreads) {
     __syncwarp();
+#ifndef GG_ONLY_ROLE
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+#endif
 }
 __device__ __forceinline__ void bar_arrive(int id, int nthreads) {
     __threadfence_block();
     __syncwarp();
+#ifndef GG_ONLY_ROLE
     asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+#endif
 }
 
-template <int NU> struct Xchg {
+template <int NU, int AD> struct Xchg {
     alignas(16) float act[32 * NU];   // this block's (32, NU) slab of the action batch, staged by the RNEA warp with cp.async
+    alignas(16) float oa[32 * AD];    // agent_pos slab of the block (MAIN), written out with 128-bit stores
+    alignas(16) float oe[32 * GG_ENV_STATE_DIM];   // environment_state slab (CUBE)
     float fs[NU][32];         // RNEA -> MAIN
-    float cube[19][32];       // CUBE -> MAIN: cp3 cq4 cv3 cw3 qacc6 (the state a coupled solve starts from)
+    float cube[19][32];       // CUBE -> RNEA / MAIN: cp3 cq4 cv3 cw3 qacc6 (the state a coupled solve starts from)
     float aout[NU + 6][32];   // solver teams -> MAIN / CUBE: acceleration of coupled envs
     float ep[3][32];          // MAIN -> CUBE: end-effector position after the step
     float tail[7][32];        // RNEA -> MAIN: end-effector pose relative to arm link KS - 1 after the step (split chain)
-    int coupled[32];          // CUBE -> MAIN
+    int coupled[32];          // RNEA -> MAIN / CUBE
     int iters[32], ncon[32];  // MAIN / teams -> CUBE (statistics)
     int bad[2][32];           // non-finite flags: [0] robot (MAIN), [1] cube (CUBE)
     int next;                 // head of the block's queue of coupled envs (solver teams pop with atomicAdd)
@@ -166,13 +186,24 @@ __device__ __forceinline__ bool reset_decision(const StepArgs& A, int e, uint32_
     return r;
 }
 
+// a warp writes its block's contiguous slab (NF4 float4's staged in shared memory) to one or two destinations
+template <int NF4> __device__ __forceinline__ void store_slab(const float* smem, float* dst, float* dst_host, int lane) {
+    const float4* s4 = reinterpret_cast<const float4*>(smem);
+#pragma unroll
+    for (int c = lane; c < NF4; c += 32) {
+        const float4 v = s4[c];
+        reinterpret_cast<float4*>(dst)[c] = v;
+        if (dst_host) reinterpret_cast<float4*>(dst_host)[c] = v;
+    }
+}
+
 // Solver-team work queue: the three warps of the block pop the block's coupled envs one at a time (X.next), pull the env's
 // published dynamics from the global scratch slab into their shared-memory TeamWork (7 coalesced 128-byte lines) and solve it
 // warp-cooperatively.  No barrier between envs: a team that drew a cheap env (few contacts, warm start already optimal) moves
 // straight on to the next one instead of waiting for the slowest of three (the lock-step rounds this replaces spent 27 % of
 // their stall samples in bar.sync, profiles/r01_v7_grasp_*).
-template <int NA, int NF, bool FH, int NU>
-__device__ __forceinline__ void team_queue(const StepArgs& A, gg::TeamWork<NA, NF>* TW, gg::TeamBuf<NU + 6>* TB, Xchg<NU>& X, unsigned cm,
+template <int NA, int NF, bool FH, class XT>
+__device__ __forceinline__ void team_queue(const StepArgs& A, gg::TeamWork<NA, NF>* TW, gg::TeamBuf<NA + NF + 6>* TB, XT& X, unsigned cm,
                                            int ncpl, int team, int lane) {
     constexpr int TWF = sizeof(gg::TeamWork<NA, NF>) / sizeof(float);
     for (;;) {
@@ -196,22 +227,28 @@ __device__ __forceinline__ void team_queue(const StepArgs& A, gg::TeamWork<NA, N
 
 template <int NA, int NF, bool FH>
 __global__ void __launch_bounds__(kBlockThreads, GG_MINBLOCKS) step_kernel(const __grid_constant__ StepArgs A) {
-    constexpr bool TEAMS = true;
-    constexpr int NU = NA + NF, NV = NU + 6;
+    constexpr int NU = NA + NF, NV = NU + 6, AD = 7 + NF;
     constexpr int KS = (NA - 1) / 2;      // split point of the end-effector chain (links [0, KS) MAIN, [KS, NA) RNEA)
-    __shared__ Xchg<NU> X;
+    typedef Xchg<NU, AD> XT;
+    __shared__ XT X;
     __shared__ gg::TeamWork<NA, NF> TW[3];
     __shared__ gg::TeamBuf<NV> TB[3];
     // until the first team round the team buffers double as scratch for the rolled loops of MAIN (per-link S, I) and CUBE
     // (per-contact J, aref, D, u, w)
     static_assert(sizeof(TB) >= (gg::LinkStoreStrided<NA>::FLOATS + gg::CubeConStrided::FLOATS) * 32 * sizeof(float), "team buffers too small for the scratch views");
     const int lane = threadIdx.x & 31, role = threadIdx.x >> 5;
-    if (threadIdx.x == 64) X.next = 0;                    // CUBE lane 0: ordered before every pop by barrier 1 (arrive) and barrier 4
+#ifdef GG_ONLY_ROLE
+    if (role != GG_ONLY_ROLE) return;
+    X.coupled[lane] = 0;
+    __syncwarp();
+#endif
+    if (threadIdx.x == 64) X.next = 0;                    // CUBE lane 0: ordered before every pop by barrier 8 (arrive) and barrier 4
     const int e0 = blockIdx.x * 32 + lane;
     const bool live = e0 < A.n;
     const int e = live ? e0 : A.n - 1;                    // dead lanes shadow the last env (loads only)
     const uint32_t gid = (uint32_t)(A.first_env + e);
     const bool run_sub = A.mode == 0 || (A.mode == 1 && A.M.settle_steps > 0);     // block-uniform
+    const bool full = blockIdx.x * 32 + 32 <= A.n;                                 // block-uniform: no dead lanes
     bool do_reset = reset_decision(A, e, gid);
     const bool active = do_reset ? (A.M.settle_steps > 0) : (A.mode == 0);         // this env runs a substep
     const float* sp = A.state + e;
@@ -224,7 +261,7 @@ __global__ void __launch_bounds__(kBlockThreads, GG_MINBLOCKS) step_kernel(const
         // bias forces are computed: the targets are only needed by the PD law at the very end of this role, so the fetch
         // latency -- HBM, or PCIe / C2C when the caller passes pinned host memory (gg_step_host, zero-copy) -- is hidden.
 #ifndef GG_NO_STAGE
-        const bool staged = A.mode == 0 && A.stage_action != 0 && blockIdx.x * 32 + 32 <= A.n;      // block-uniform
+        const bool staged = A.mode == 0 && A.stage_action != 0 && full;      // block-uniform
 #else
         const bool staged = false;
 #endif
@@ -245,17 +282,33 @@ __global__ void __launch_bounds__(kBlockThreads, GG_MINBLOCKS) step_kernel(const
         ActionFetch<NU> tf;
         tf.home = A.M.home_q; tf.slab = X.act + lane * NU; tf.global = A.action + (size_t)e * NU;
         tf.staged = staged; tf.use_action = A.mode == 0 && !do_reset;
-        gg::robot_rnea_t<NA, NF, FH>(A.M, q, qd, tf, fs);
+        gg::RobotDyn<NA, NF> D;                               // only the pad-body frames are filled (and kept)
+        gg::robot_rnea_t<NA, NF, FH>(A.M, A.C, q, qd, tf, fs, &D);
 #pragma unroll
         for (int i = 0; i < NU; i++) X.fs[i][lane] = fs[i];
-        if (!TEAMS) { bar_arrive(1, 96); return; }
-        __threadfence_block();
-        bar_sync(1, 96);
-        const unsigned cm = __ballot_sync(0xffffffffu, X.coupled[lane] != 0);
+        if (A.action_dev != nullptr && A.mode == 0) {         // device-resident copy of the consumed targets (host-I/O callers)
+            if (staged) store_slab<32 * NU / 4>(X.act, A.action_dev + (size_t)blockIdx.x * 32 * NU, nullptr, lane);
+            else if (live) {
+#pragma unroll
+                for (int i = 0; i < NU; i++) A.action_dev[(size_t)e * NU + i] = A.action[(size_t)e * NU + i];
+            }
+        }
+        // pad broad phase against the cube state the CUBE warp published (after its masked reset)
+        bar_sync(8, 96);
+        const gg::V3 cp = gg::mk(X.cube[0][lane], X.cube[1][lane], X.cube[2][lane]);
+        const gg::Q4 cq = gg::mkq(X.cube[3][lane], X.cube[4][lane], X.cube[5][lane], X.cube[6][lane]);
+#ifdef GG_ONLY_ROLE
+        const bool coupled = live && gg::pads_may_touch<NA, NF>(A.M, D, cp, cq) && cp.x > 1e30f;
+#else
+        const bool coupled = live && gg::pads_may_touch<NA, NF>(A.M, D, cp, cq);
+#endif
+        X.coupled[lane] = coupled ? 1 : 0;
+        bar_arrive(1, 96);
+        const unsigned cm = __ballot_sync(0xffffffffu, coupled);
         const int ncpl = __popc(cm);
         if (ncpl > 0) {                                   // solver team 1 (see MAIN for the protocol)
             bar_sync(4, 96);
-            team_queue<NA, NF, FH, NU>(A, TW, TB, X, cm, ncpl, 1, lane);
+            team_queue<NA, NF, FH>(A, TW, TB, X, cm, ncpl, 1, lane);
             bar_sync(5, 96);
         }
 #ifndef GG_NO_SPLIT_EEF
@@ -290,7 +343,7 @@ __global__ void __launch_bounds__(kBlockThreads, GG_MINBLOCKS) step_kernel(const
                 // per-link temporaries in the (still idle) team buffers: [element][lane] view of shared memory
                 gg::LinkStoreStrided<NA> ls;
                 ls.b = reinterpret_cast<float*>(TB) + lane;
-                gg::robot_crba<NA, NF, FH>(A.M, q, D, ls);
+                gg::robot_crba<NA, NF, FH>(A.M, A.C, q, D, ls);
             }
             float L[NU * (NU + 1) / 2], dinv[NU];
 #pragma unroll
@@ -298,6 +351,7 @@ __global__ void __launch_bounds__(kBlockThreads, GG_MINBLOCKS) step_kernel(const
             gg::chol_packed<NU>(L, dinv);
             float lsg[NU], laref[NU], lD[NU];
             const int nlim = gg::joint_limit_rows<NU>(A.M, q, qd, lsg, laref, lD);
+            bar_sync(8, 96);
             bar_sync(1, 96);
 #pragma unroll
             for (int i = 0; i < NU; i++) D.fs[i] = X.fs[i][lane];
@@ -309,7 +363,7 @@ __global__ void __launch_bounds__(kBlockThreads, GG_MINBLOCKS) step_kernel(const
 #pragma unroll
             for (int i = 0; i < NU; i++) a[i] = as[i];
             if (commit && !coupled) gg::robot_block_solve<NU>(D.Mt, as, nlim, lsg, laref, lD, qa, a, A.iterations, A.tol, info);
-            if (TEAMS) {
+            {
                 const unsigned cm = __ballot_sync(0xffffffffu, coupled);
                 const int ncpl = __popc(cm);
                 if (ncpl > 0) {
@@ -348,7 +402,7 @@ __global__ void __launch_bounds__(kBlockThreads, GG_MINBLOCKS) step_kernel(const
                     }
                     __threadfence_block();
                     bar_sync(4, 96);
-                    team_queue<NA, NF, FH, NU>(A, TW, TB, X, cm, ncpl, 0, lane);
+                    team_queue<NA, NF, FH>(A, TW, TB, X, cm, ncpl, 0, lane);
                     bar_sync(5, 96);
                 }
                 if (coupled) {
@@ -356,7 +410,7 @@ __global__ void __launch_bounds__(kBlockThreads, GG_MINBLOCKS) step_kernel(const
                     for (int i = 0; i < NU; i++) a[i] = X.aout[i][lane];
                 }
             }
-            if (!(TEAMS && coupled)) X.iters[lane] = info.iters;
+            if (!coupled) X.iters[lane] = info.iters;
             bar_arrive(2, 64);
             if (active) gg::integrate_robot<NU>(A.M, q, qd, qa, a);
         }
@@ -402,16 +456,32 @@ __global__ void __launch_bounds__(kBlockThreads, GG_MINBLOCKS) step_kernel(const
             __threadfence_block();
             bar_sync(3, 64);
         }
-        if (commit) {
-            float* oa = A.obs_agent + (size_t)e * (7 + NF);
+        if (full && A.vec_out) {
+            // agent_pos rows staged in shared memory (row stride AD words: conflict free for the Panda's 9, a 4-way conflict on
+            // eight stores for the SO-101's 8), then one contiguous slab of 32 x AD floats with 128-bit stores
+            float* r = X.oa + lane * AD;
+            r[0] = ep.x; r[1] = ep.y; r[2] = ep.z; r[3] = eq.w; r[4] = eq.x; r[5] = eq.y; r[6] = eq.z;
+#pragma unroll
+            for (int f = 0; f < NF; f++) r[7 + f] = q[NA + f];
+            __syncwarp();
+            store_slab<32 * AD / 4>(X.oa, A.obs_agent + (size_t)blockIdx.x * 32 * AD,
+                                    A.obs_agent_host ? A.obs_agent_host + (size_t)blockIdx.x * 32 * AD : nullptr, lane);
+        } else if (commit) {
+            float* oa = A.obs_agent + (size_t)e * AD;
             oa[0] = ep.x; oa[1] = ep.y; oa[2] = ep.z; oa[3] = eq.w; oa[4] = eq.x; oa[5] = eq.y; oa[6] = eq.z;
 #pragma unroll
             for (int f = 0; f < NF; f++) oa[7 + f] = q[NA + f];
-            if (A.mode != 2 && (active || do_reset)) {
-                float* wp = A.state + e;
+            if (A.obs_agent_host) {
+                float* oh = A.obs_agent_host + (size_t)e * AD;
+                oh[0] = ep.x; oh[1] = ep.y; oh[2] = ep.z; oh[3] = eq.w; oh[4] = eq.x; oh[5] = eq.y; oh[6] = eq.z;
 #pragma unroll
-                for (int i = 0; i < NU; i++) { wp[i * st] = q[i]; wp[(NU + i) * st] = qd[i]; wp[(2 * NU + 13 + i) * st] = qa[i]; }
+                for (int f = 0; f < NF; f++) oh[7 + f] = q[NA + f];
             }
+        }
+        if (commit && A.mode != 2 && (active || do_reset)) {
+            float* wp = A.state + e;
+#pragma unroll
+            for (int i = 0; i < NU; i++) { wp[i * st] = q[i]; wp[(NU + i) * st] = qd[i]; wp[(2 * NU + 13 + i) * st] = qa[i]; }
         }
         return;
     }
@@ -440,47 +510,40 @@ __global__ void __launch_bounds__(kBlockThreads, GG_MINBLOCKS) step_kernel(const
         }
         bool commit = live;
         if (run_sub) {
-            bool coupled;
-            {
-                float q[NU];
-#pragma unroll
-                for (int i = 0; i < NU; i++) q[i] = do_reset ? A.M.home_q[i] : sp[i * st];
-                gg::RobotDyn<NA, NF> D;
-                gg::robot_pad_frames<NA, NF, FH>(A.M, q, D);
-                coupled = live && gg::pads_may_touch<NA, NF>(A.M, D, cp, cq);
-            }
-            X.coupled[lane] = coupled ? 1 : 0;
             X.cube[0][lane] = cp.x; X.cube[1][lane] = cp.y; X.cube[2][lane] = cp.z;
             X.cube[3][lane] = cq.w; X.cube[4][lane] = cq.x; X.cube[5][lane] = cq.y; X.cube[6][lane] = cq.z;
             X.cube[7][lane] = cv.x; X.cube[8][lane] = cv.y; X.cube[9][lane] = cv.z;
             X.cube[10][lane] = cw.x; X.cube[11][lane] = cw.y; X.cube[12][lane] = cw.z;
 #pragma unroll
             for (int i = 0; i < 6; i++) X.cube[13 + i][lane] = qac[i];
-            bar_arrive(1, 96);
+            bar_arrive(8, 96);
             float Mc[6], as_c[6], qd_c[6], a_c[6];
             gg::cube_free_acc(A.M, cv, cw, Mc, as_c, qd_c);
             gg::StepInfo ic; ic.ncon = 0; ic.iters = 0; ic.grad = 0.f;
 #pragma unroll
             for (int i = 0; i < 6; i++) a_c[i] = as_c[i];
-            if (commit && !coupled) {
+            if (commit) {
+                // speculative: the broad phase (end of the RNEA chain) has not reported yet; coupled envs drop this result
                 gg::CubeConStrided cs;                        // per-contact temporaries behind MAIN's slice of the team buffers
                 cs.b = reinterpret_cast<float*>(TB) + gg::LinkStoreStrided<NA>::FLOATS * 32 + lane;
                 gg::cube_block_solve(A.M, cp, gg::qmat(cq), Mc, as_c, qd_c, qac, a_c, A.iterations, A.tol, cs, ic);
             }
-            if (TEAMS) {
+            bar_sync(1, 96);
+            const bool coupled = X.coupled[lane] != 0;
+            {
                 const unsigned cm = __ballot_sync(0xffffffffu, coupled);
                 const int ncpl = __popc(cm);
                 if (ncpl > 0) {                               // solver team 2 (see MAIN for the protocol)
                     bar_sync(4, 96);
-                    team_queue<NA, NF, FH, NU>(A, TW, TB, X, cm, ncpl, 2, lane);
+                    team_queue<NA, NF, FH>(A, TW, TB, X, cm, ncpl, 2, lane);
                     bar_sync(5, 96);
                 }
             }
             bar_sync(2, 64);
-            if (TEAMS && coupled) {
+            if (coupled) {
 #pragma unroll
                 for (int i = 0; i < 6; i++) a_c[i] = X.aout[NU + i][lane];
-                ic.ncon = X.ncon[lane];
+                ic.ncon = X.ncon[lane]; ic.iters = 0;
             }
             const int it = ic.iters > X.iters[lane] ? ic.iters : X.iters[lane];
             if (active) {
@@ -514,10 +577,25 @@ __global__ void __launch_bounds__(kBlockThreads, GG_MINBLOCKS) step_kernel(const
         const bool succ = cp.z > A.M.success_z;
         const float rew = succ ? 1.f : 0.f;
         const bool trunc = A.time_limit && steps >= A.M.horizon;
-        if (commit) {
+        const float dn = sqrtf(gg::dot(d, d));
+        if (full && A.vec_out) {
+            float* r = X.oe + lane * GG_ENV_STATE_DIM;
+            r[0] = cp.x; r[1] = cp.y; r[2] = cp.z; r[3] = cq.w; r[4] = cq.x; r[5] = cq.y; r[6] = cq.z;
+            r[7] = d.x; r[8] = d.y; r[9] = d.z; r[10] = dn;
+            __syncwarp();
+            store_slab<32 * GG_ENV_STATE_DIM / 4>(X.oe, A.obs_env + (size_t)blockIdx.x * 32 * GG_ENV_STATE_DIM,
+                                                  A.obs_env_host ? A.obs_env_host + (size_t)blockIdx.x * 32 * GG_ENV_STATE_DIM : nullptr, lane);
+        } else if (commit) {
             float* oe = A.obs_env + (size_t)e * GG_ENV_STATE_DIM;
             oe[0] = cp.x; oe[1] = cp.y; oe[2] = cp.z; oe[3] = cq.w; oe[4] = cq.x; oe[5] = cq.y; oe[6] = cq.z;
-            oe[7] = d.x; oe[8] = d.y; oe[9] = d.z; oe[10] = sqrtf(gg::dot(d, d));
+            oe[7] = d.x; oe[8] = d.y; oe[9] = d.z; oe[10] = dn;
+            if (A.obs_env_host) {
+                float* oh = A.obs_env_host + (size_t)e * GG_ENV_STATE_DIM;
+                oh[0] = cp.x; oh[1] = cp.y; oh[2] = cp.z; oh[3] = cq.w; oh[4] = cq.x; oh[5] = cq.y; oh[6] = cq.z;
+                oh[7] = d.x; oh[8] = d.y; oh[9] = d.z; oh[10] = dn;
+            }
+        }
+        if (commit) {
             if (A.reward) A.reward[e] = rew;
             if (A.terminated) A.terminated[e] = succ ? 1 : 0;
             if (A.truncated) A.truncated[e] = trunc ? 1 : 0;
@@ -760,12 +838,14 @@ int gg_internal_export(int device, int n, int stride, int F, int32_t** slot, con
 
 static int launch_step(GgSim* sim, StepArgs& A, gg_stream_t stream) {
     if (sim->state == nullptr) return fail("gg_bind_state has not been called%s");
-    A.M = sim->model; A.n = sim->n; A.stride = sim->stride;
+    A.M = sim->model; gg::make_chain(A.M, A.C); A.n = sim->n; A.stride = sim->stride;
     A.state = sim->state; A.step_count = sim->step_count; A.episode = sim->episode; A.done = sim->done;
     A.iterations = sim->cfg.solver_iterations; A.tol = sim->cfg.solver_tolerance;
     A.auto_reset = sim->cfg.auto_reset; A.time_limit = sim->cfg.time_limit; A.reset_prob = sim->cfg.reset_prob;
     A.seed = sim->cfg.seed; A.first_env = sim->cfg.first_env_id; A.step_index = sim->step_index;
     A.stats = sim->stats; A.team_scratch = sim->team_scratch;
+    auto al16 = [](const void* p) { return ((uintptr_t)p & 15u) == 0; };
+    A.vec_out = al16(A.obs_agent) && al16(A.obs_env) && al16(A.obs_agent_host) && al16(A.obs_env_host) && al16(A.action_dev);
     const int grid = (sim->n + 31) / 32;                 // 32 envs x 3 role warps per block
     GG_CUDA(cudaSetDevice(sim->device));
     if (sim->kind == 0) step_kernel<7, 2, false><<<grid, kBlockThreads, 0, (cudaStream_t)stream>>>(A);
@@ -871,11 +951,14 @@ int gg_step_host(GgSim* sim, const GgHostIO* io, float* obs_agent, float* obs_en
     if (io->reward && !pinned_host_ptr(sim, io->reward)) return fail("gg_step_host: reward mirror must be pinned host memory%s");
     if (io->terminated && !pinned_host_ptr(sim, io->terminated)) return fail("gg_step_host: terminated mirror must be pinned host memory%s");
     if (io->truncated && !pinned_host_ptr(sim, io->truncated)) return fail("gg_step_host: truncated mirror must be pinned host memory%s");
+    if (io->obs_agent && !pinned_host_ptr(sim, io->obs_agent)) return fail("gg_step_host: obs_agent mirror must be pinned host memory%s");
+    if (io->obs_env && !pinned_host_ptr(sim, io->obs_env)) return fail("gg_step_host: obs_env mirror must be pinned host memory%s");
     StepArgs A;
     memset(&A, 0, sizeof(A));
     A.action = io->action; A.obs_agent = obs_agent; A.obs_env = obs_env; A.reward = reward;
     A.terminated = terminated; A.truncated = truncated; A.reset_mask = reset_mask; A.cube_xy = nullptr; A.mode = 0;
     A.reward_host = io->reward; A.terminated_host = io->terminated; A.truncated_host = io->truncated;
+    A.obs_agent_host = io->obs_agent; A.obs_env_host = io->obs_env; A.action_dev = io->action_dev;
     A.stage_action = ((uintptr_t)io->action & 15u) == 0;
     int rc = launch_step(sim, A, stream);
     sim->step_index++;

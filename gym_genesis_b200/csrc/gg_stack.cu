@@ -67,7 +67,7 @@ struct WarpDev {
 };
 
 struct StackArgs {
-    GgModel M;
+    GgModel M; gg::GgChain C;
     GgStackTask T;
     int n, stride;
     float* state; int32_t* step_count; int32_t* episode; uint8_t* done;
@@ -220,7 +220,7 @@ __global__ void __launch_bounds__(96, 4) stack_prep_kernel(const __grid_constant
         const bool use_action = A.mode == 0 && !do_reset;
 #pragma unroll
         for (int i = 0; i < NU; i++) target[i] = use_action ? A.action[(size_t)e * NU + i] : A.M.home_q[i];
-        gg::robot_rnea<NA, NF, FH>(A.M, q, qd, target, fs);
+        gg::robot_rnea<NA, NF, FH>(A.M, A.C, q, qd, target, fs);
 #pragma unroll
         for (int i = 0; i < NU; i++) s_fs[i * 32 + lane] = fs[i];
         sk_bar_arrive(1, 64);
@@ -235,7 +235,7 @@ __global__ void __launch_bounds__(96, 4) stack_prep_kernel(const __grid_constant
         int rit = 0;
         FsShared<NU> fsp{s_fs + lane};
         RmaskShared<NA, NF> rmp{s_rmask + lane};
-        gg::stack_prep_robot<NA, NF, FH, K>(A.M, q, qd, warm, A.iterations, A.tol, active && live, In.W, rit, fsp, rmp);
+        gg::stack_prep_robot<NA, NF, FH, K>(A.M, A.C, q, qd, warm, A.iterations, A.tol, active && live, In.W, rit, fsp, rmp);
         s_rit[lane] = rit;
     } else {
         // ---------------------------------------------------------------------------------------------------------- CUBES
@@ -573,7 +573,7 @@ static void stack_launch_t(GgStackSim* sim, const StackArgs& A, cudaStream_t s);
 
 static int stack_launch(GgStackSim* sim, StackArgs& A, gg_stream_t stream) {
     if (sim->state == nullptr) return gg_internal_fail("gg_stack_bind_state has not been called%s", "");
-    A.M = sim->model; A.T = sim->task; A.n = sim->n; A.stride = sim->stride;
+    A.M = sim->model; gg::make_chain(A.M, A.C); A.T = sim->task; A.n = sim->n; A.stride = sim->stride;
     A.state = sim->state; A.step_count = sim->step_count; A.episode = sim->episode; A.done = sim->done;
     A.iterations = sim->cfg.solver_iterations; A.tol = sim->cfg.solver_tolerance;
     A.auto_reset = sim->cfg.auto_reset; A.time_limit = sim->cfg.time_limit; A.reset_prob = sim->cfg.reset_prob;

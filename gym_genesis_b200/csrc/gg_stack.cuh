@@ -143,8 +143,8 @@ GG_HD void stack_pad_reach(const GgModel& M, const RobotDyn<NA, NF>& D, const V3
 // FSP: provider of fs = clamp(PD) - damping qd - bias.  The host harness computes it in place (robot_rnea); the CUDA kernel's ROBOT
 // warp receives it from the RNEA warp, which walks the same chain concurrently (the two halves of the dynamics pass are independent).
 template <int NA, int NF, bool FH> struct FsInline {
-    const GgModel* M; const float* q; const float* qd; const float* target;
-    GG_HD void operator()(float* fs) const { robot_rnea<NA, NF, FH>(*M, q, qd, target, fs); }
+    const GgModel* M; const GgChain* C; const float* q; const float* qd; const float* target;
+    GG_HD void operator()(float* fs) const { robot_rnea<NA, NF, FH>(*M, *C, q, qd, target, fs); }
 };
 
 // RMP: provider of the robot's amask bits (bit 0: a pad may touch the plane or a cube, bit 1 + k: cube k within reach of a pad).
@@ -160,13 +160,13 @@ template <int NA, int NF, int K> struct RmaskInline {
 };
 
 template <int NA, int NF, bool FH, int K, class FSP, class RMP>
-GG_HD unsigned stack_prep_robot(const GgModel& M, const float* q, const float* qd, const float* warm, int iterations, float tol, bool active,
+GG_HD unsigned stack_prep_robot(const GgModel& M, const GgChain& C, const float* q, const float* qd, const float* warm, int iterations, float tol, bool active,
                                 StackWork<NA, NF>& W, int& rob_iters, FSP& fsp, RMP& rmp) {
     constexpr int NU = NA + NF;
     RobotDyn<NA, NF> D;
     {
         LinkStoreLocal<NA> ls;
-        robot_crba<NA, NF, FH>(M, q, D, ls);
+        robot_crba<NA, NF, FH>(M, C, q, D, ls);
     }
     float L[NU * (NU + 1) / 2], dinv[NU];
 #pragma unroll
@@ -261,12 +261,12 @@ GG_HD unsigned stack_prep_cubes(const GgModel& M, const ObjState<K>& O, const fl
 
 // both halves in one thread (host harness)
 template <int NA, int NF, bool FH, int K>
-GG_HD void stack_prep(const GgModel& M, const float* q, const float* qd, const float* warm, const float* target, const ObjState<K>& O,
+GG_HD void stack_prep(const GgModel& M, const GgChain& C, const float* q, const float* qd, const float* warm, const float* target, const ObjState<K>& O,
                       int iterations, float tol, bool active, StackIn<NA, NF, K>& In) {
     int rob_iters, iso_iters, iso_ncon;
-    FsInline<NA, NF, FH> fsp{&M, q, qd, target};
+    FsInline<NA, NF, FH> fsp{&M, &C, q, qd, target};
     RmaskInline<NA, NF, K> rmp{&M, O.p, O.q};
-    const unsigned rmask = stack_prep_robot<NA, NF, FH, K>(M, q, qd, warm, iterations, tol, active, In.W, rob_iters, fsp, rmp);
+    const unsigned rmask = stack_prep_robot<NA, NF, FH, K>(M, C, q, qd, warm, iterations, tol, active, In.W, rob_iters, fsp, rmp);
     const unsigned cmask = stack_prep_cubes<K>(M, O, In.warm_obj, rmask >> 1, iterations, tol, active, In.aobj, iso_iters, iso_ncon);
     In.W.amask = (float)(rmask | cmask);
     In.W.iso_iters = (float)(rob_iters > iso_iters ? rob_iters : iso_iters);

@@ -32,7 +32,7 @@ class BatchedSim:
 
     def __init__(self, scene_model: SceneModel, n_envs: int, device="cuda", solver_iterations: int = 10,
                  solver_tolerance: float = 1e-5, auto_reset: bool = False, time_limit: bool = False, reset_prob: float = 0.0,
-                 seed: int = 0, first_env_id: int = 0):
+                 seed: int = 0, first_env_id: int = 0, fresh_outputs: bool = False):
         if not torch.cuda.is_available():
             raise GgError("gym_genesis_b200 needs a CUDA device: the env.step path has no CPU fallback")
         self.lib = cabi.load_library()
@@ -45,6 +45,8 @@ class BatchedSim:
         self.gg_model = cabi.compile_gg(scene_model)
         self.n_envs = int(n_envs)
         self.nu = scene_model.nu
+        self.fresh_outputs = bool(fresh_outputs)
+        self.env_dim = 11
         self.nq, self.nv = self.nu + 7, self.nu + 6
         self.agent_dim = 7 + scene_model.n_fing
         h = C.c_void_p()
@@ -113,12 +115,27 @@ class BatchedSim:
             raise ValueError(f"mask must have shape ({self.n_envs},), got {tuple(mask.shape)}")
         return mask.to(device=self.device, dtype=torch.uint8).contiguous()
 
+    def _new_outputs(self):
+        """fresh_outputs=True: every step / reset writes into NEWLY allocated output tensors (torch's caching allocator: no kernels,
+        a few microseconds of host time), so tensors returned earlier keep their values -- the reference's getters return fresh
+        tensors too (franka/cube_pick.py:137-157), and its collectors append them step after step
+        (examples/franka/pick_cube_state.py:86-100).  The default (False) reuses one set of buffers: zero allocation, CUDA-graph safe."""
+        n, dev = self.n_envs, self.device
+        self.obs_agent = torch.empty((n, self.agent_dim), dtype=torch.float32, device=dev)
+        self.obs_env = torch.empty((n, self.env_dim), dtype=torch.float32, device=dev)
+        self.reward = torch.empty(n, dtype=torch.float32, device=dev)
+        flags = torch.empty((2, n), dtype=torch.bool, device=dev)
+        self.terminated, self.truncated = flags[0], flags[1]
+        self._out_ptrs = None
+
     def step(self, action, reset_mask=None):
-        """One env.step (= one 0.01 s substep) for all envs; results land in the preallocated
-        obs_agent / obs_env / reward / terminated / truncated tensors (no host sync)."""
+        """One env.step (= one 0.01 s substep) for all envs; results land in the obs_agent / obs_env / reward / terminated /
+        truncated tensors of this object (no host sync)."""
         a = self._as_action(action)
         m = self._as_mask(reset_mask)
         self._last_action = a          # PD targets persist (reference: control_dofs_position semantics)
+        if self.fresh_outputs:
+            self._new_outputs()
         self._check(self.lib.gg_step(self._h, _ptr(a), _ptr(self.obs_agent), _ptr(self.obs_env), _ptr(self.reward),
                                      _ptr(self.terminated), _ptr(self.truncated), _ptr(m), self._stream()))
 
@@ -130,20 +147,31 @@ class BatchedSim:
                 "reward": torch.zeros(n, dtype=torch.float32).pin_memory(),
                 "terminated": torch.zeros(n, dtype=torch.bool).pin_memory(),
                 "truncated": torch.zeros(n, dtype=torch.bool).pin_memory(),
+                "obs_agent": torch.zeros((n, self.agent_dim), dtype=torch.float32).pin_memory(),
+                "obs_env": torch.zeros((n, self.env_dim), dtype=torch.float32).pin_memory(),
             }
+            # device-resident copy of the action batch the last host-fed step consumed (written by the kernel): PD targets persist
+            self._targets_dev = torch.zeros((n, self.nu), dtype=torch.float32, device=self.device)
             self._hio = cabi.GgHostIO(0, self._host["reward"].data_ptr(), self._host["terminated"].data_ptr(),
                                       self._host["truncated"].data_ptr(), 1)
+            self._hio.action_dev = self._targets_dev.data_ptr()
             self._hio_ref = C.byref(self._hio)
-            self._out_ptrs = tuple(_ptr(t) for t in (self.obs_agent, self.obs_env, self.reward, self.terminated, self.truncated))
+            self._out_ptrs = None
             self._pinned_ok = {}
         return self._host
 
-    def step_host(self, action, reset_mask=None, wait=True):
+    def step_host(self, action, reset_mask=None, wait=True, host_obs=False):
         """env.step for a HOST-resident caller (the reference's numpy convention): `action` is a CPU float32 (n_envs, n_dof)
         array; a pinned torch tensor is read in place by the kernel over PCIe (zero-copy), anything else is first copied into
         a pinned staging buffer.  Returns pinned CPU tensors (reward, terminated, truncated) the kernel has written directly;
-        with wait=True (default) they are valid on return.  Observations stay on the device (obs_agent / obs_env)."""
+        with wait=True (default) they are valid on return.  Observations stay on the device (obs_agent / obs_env);
+        host_obs=True additionally has the kernel write them into the pinned mirrors `host_obs_agent` / `host_obs_env`
+        (what a host-resident policy reads every step).  The consumed action batch is also kept on the device (`_last_action`)."""
         h = self._host_buffers()
+        if self.fresh_outputs:
+            self._new_outputs()
+        if self._out_ptrs is None:
+            self._out_ptrs = tuple(_ptr(t) for t in (self.obs_agent, self.obs_env, self.reward, self.terminated, self.truncated))
         # tensors that passed the checks once are recognised by (object id, data pointer): `is_pinned()` is a driver query
         key = (id(action), action.data_ptr()) if isinstance(action, torch.Tensor) else None
         if key is not None and key in self._pinned_ok:
@@ -160,13 +188,25 @@ class BatchedSim:
                 a = h["action"]
                 a.copy_(torch.as_tensor(np.asarray(action) if not isinstance(action, torch.Tensor) else action, dtype=torch.float32))
         m = None if reset_mask is None else self._as_mask(reset_mask)
-        self._last_action = a
+        self._last_action = self._targets_dev      # filled by the kernel from the batch it consumed
         self._hio.action = a.data_ptr()
         self._hio.wait = 1 if wait else 0
+        self._hio.obs_agent = h["obs_agent"].data_ptr() if host_obs else None
+        self._hio.obs_env = h["obs_env"].data_ptr() if host_obs else None
         rc = self._step_host_fn()(self._h, self._hio_ref, *self._out_ptrs, _ptr(m), self._stream())
         if rc != 0:
             self._check(rc)
+        if self.fresh_outputs:                     # detach the results from the pinned mirrors the next step overwrites
+            return h["reward"].clone(), h["terminated"].clone(), h["truncated"].clone()
         return h["reward"], h["terminated"], h["truncated"]
+
+    @property
+    def host_obs_agent(self):
+        return self._host_buffers()["obs_agent"]
+
+    @property
+    def host_obs_env(self):
+        return self._host_buffers()["obs_env"]
 
     def _step_host_fn(self):
         return self.lib.gg_step_host
@@ -180,6 +220,8 @@ class BatchedSim:
                 raise ValueError(f"cube_xy must have shape ({self.n_envs}, 2)")
             xy = xy.to(device=self.device, dtype=torch.float32).contiguous()
         self._last_action = None
+        if self.fresh_outputs:
+            self._new_outputs()
         self._check(self.lib.gg_reset(self._h, _ptr(m), _ptr(xy), _ptr(self.obs_agent), _ptr(self.obs_env), self._stream()))
 
     def observe(self):
@@ -227,7 +269,12 @@ class BatchedSim:
         pos, quat, init_qpos = prep(pos, 3), prep(quat, 4), prep(init_qpos, self.nu)
         idx = None
         if envs_idx is not None:
-            idx = torch.as_tensor(envs_idx).to(device=dev, dtype=torch.int32).reshape(-1).contiguous()
+            idx = torch.as_tensor(envs_idx)
+            if idx.numel() > 0 and not torch.cuda.is_current_stream_capturing():
+                lo, hi = int(idx.min()), int(idx.max())          # host check (one sync): the kernel indexes the state with these
+                if lo < 0 or hi >= self.n_envs:
+                    raise ValueError(f"envs_idx out of range [0, {self.n_envs}): min {lo}, max {hi}")
+            idx = idx.to(device=dev, dtype=torch.int32).reshape(-1).contiguous()
         rows = {t.shape[0] for t in (pos, quat, init_qpos) if t is not None}
         if idx is not None:
             rows.add(idx.shape[0])
@@ -271,7 +318,7 @@ class BatchedStackSim(BatchedSim):
 
     def __init__(self, scene_model: SceneModel, n_envs: int, device="cuda", solver_iterations: int = 10,
                  solver_tolerance: float = 1e-5, auto_reset: bool = False, time_limit: bool = False, reset_prob: float = 0.0,
-                 seed: int = 0, first_env_id: int = 0):
+                 seed: int = 0, first_env_id: int = 0, fresh_outputs: bool = False):
         if not torch.cuda.is_available():
             raise GgError("gym_genesis_b200 needs a CUDA device: the env.step path has no CPU fallback")
         self.lib = cabi.load_library()
@@ -281,6 +328,7 @@ class BatchedStackSim(BatchedSim):
         if self.device.index is None:
             self.device = torch.device("cuda", torch.cuda.current_device())
         self.scene_model = scene_model
+        self.fresh_outputs = bool(fresh_outputs)
         self.gg_model = cabi.compile_gg(scene_model)
         self.gg_task = cabi.compile_stack_task(scene_model)
         self.n_envs = int(n_envs)
@@ -328,6 +376,8 @@ class BatchedStackSim(BatchedSim):
         a = self._as_action(action)
         m = self._as_mask(reset_mask)
         self._last_action = a
+        if self.fresh_outputs:
+            self._new_outputs()
         self._check(self.lib.gg_stack_step(self._h, _ptr(a), _ptr(self.obs_agent), _ptr(self.obs_env), _ptr(self.reward),
                                            _ptr(self.terminated), _ptr(self.truncated), _ptr(m), self._stream()))
 
@@ -343,6 +393,8 @@ class BatchedStackSim(BatchedSim):
                 raise ValueError(f"obj_xy must have shape ({self.n_envs}, {self.n_obj}, 2)")
             xy = xy.to(device=self.device, dtype=torch.float32).contiguous()
         self._last_action = None
+        if self.fresh_outputs:
+            self._new_outputs()
         self._check(self.lib.gg_stack_reset(self._h, _ptr(m), _ptr(xy), _ptr(self.obs_agent), _ptr(self.obs_env), self._stream()))
 
     def observe(self):

@@ -123,6 +123,14 @@ typedef struct GgHostIO {
     uint8_t* terminated;
     uint8_t* truncated;
     int32_t wait;
+    int32_t reserved0;
+    /* optional (NULL = off), gg_step_host only: page-locked host mirrors of the observations -- what a host-resident policy reads
+     * every step (README.md:34 feeds `observation` to policy()) -- written by the same kernel with 128-bit stores ... */
+    float* obs_agent;          /* (n_envs, 7 + n_fing) */
+    float* obs_env;            /* (n_envs, 11)         */
+    /* ... and a DEVICE buffer (n_envs, n_dof) that receives the action batch the step consumed: control_dofs_position targets
+     * persist across steps (cube_pick.py:123-124), so `push()` / masked resets need them on the device after a host-fed step. */
+    float* action_dev;
 } GgHostIO;
 int gg_step_host(GgSim* sim, const GgHostIO* io, float* obs_agent, float* obs_env, float* reward, uint8_t* terminated,
                  uint8_t* truncated, const uint8_t* reset_mask, gg_stream_t stream);

@@ -10,6 +10,7 @@ template <int NA, int NF, bool FH>
 static void run(const GgModel* M, int n, float* q, float* qd, float* qacc, const float* target, int iterations, float tol,
                 int32_t* info, float* grad) {
     constexpr int NU = NA + NF, NQ = NU + 7, NV = NU + 6;
+    gg::GgChain C; gg::make_chain(*M, C);
     for (int e = 0; e < n; e++) {
         gg::EnvState<NU> s;
         float* pq = q + (size_t)e * NQ; float* pv = qd + (size_t)e * NV; float* pa = qacc + (size_t)e * NV;
@@ -18,7 +19,7 @@ static void run(const GgModel* M, int n, float* q, float* qd, float* qacc, const
         s.cv = gg::mk(pv[NU], pv[NU + 1], pv[NU + 2]); s.cw = gg::mk(pv[NU + 3], pv[NU + 4], pv[NU + 5]);
         for (int i = 0; i < NV; i++) s.qacc[i] = pa[i];
         gg::StepInfo si;
-        gg::env_substep<NA, NF, FH>(*M, s, target + (size_t)e * NU, iterations, tol, si);
+        gg::env_substep<NA, NF, FH>(*M, C, s, target + (size_t)e * NU, iterations, tol, si);
         for (int i = 0; i < NU; i++) { pq[i] = s.q[i]; pv[i] = s.qd[i]; }
         pq[NU] = s.cp.x; pq[NU + 1] = s.cp.y; pq[NU + 2] = s.cp.z;
         pq[NU + 3] = s.cq.w; pq[NU + 4] = s.cq.x; pq[NU + 5] = s.cq.y; pq[NU + 6] = s.cq.z;
@@ -32,7 +33,8 @@ static void run(const GgModel* M, int n, float* q, float* qd, float* qacc, const
 template <int NA, int NF, bool FH>
 static void dyn(const GgModel* M, const float* q, const float* qd, const float* target, float* Mt, float* fs) {
     gg::RobotDyn<NA, NF> D;
-    gg::robot_dynamics<NA, NF, FH>(*M, q, qd, target, D);
+    gg::GgChain C; gg::make_chain(*M, C);
+    gg::robot_dynamics<NA, NF, FH>(*M, C, q, qd, target, D);
     constexpr int NU = NA + NF;
     for (int i = 0; i < NU; i++) { fs[i] = D.fs[i]; for (int j = 0; j < NU; j++) Mt[i * NU + j] = D.Mt[i >= j ? GG_TRI(i, j) : GG_TRI(j, i)]; }
 }

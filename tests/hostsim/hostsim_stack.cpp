@@ -39,6 +39,7 @@ void run(const GgModel* M, const GgStackTask* T, int n, float* q, float* qd, flo
     auto* In = new gg::StackIn<NA, NF, K>;
     auto* B = new gg::StackBuf<NU, K>;
     HostWarp hw;
+    gg::GgChain C; gg::make_chain(*M, C);
     for (int e = 0; e < n; e++) {
         float* pq = q + (size_t)e * NQ; float* pv = qd + (size_t)e * NV; float* pa = qacc + (size_t)e * NV;
         gg::ObjState<K> O;
@@ -50,7 +51,7 @@ void run(const GgModel* M, const GgStackTask* T, int n, float* q, float* qd, flo
             for (int i = 0; i < 7; i++) d[i] = o[i];
             for (int i = 0; i < 6; i++) { d[7 + i] = v[i]; In->warm_obj[k][i] = pa[NU + 6 * k + i]; }
         }
-        gg::stack_prep<NA, NF, FH, K>(*M, pq, pv, pa, target + (size_t)e * NU, O, iterations, tol, true, *In);
+        gg::stack_prep<NA, NF, FH, K>(*M, C, pq, pv, pa, target + (size_t)e * NU, O, iterations, tol, true, *In);
         float a[NV];
         for (int i = 0; i < NU; i++) a[i] = In->W.arob[i];
         for (int k = 0; k < K; k++)

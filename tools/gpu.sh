@@ -7,7 +7,7 @@
 #   newtests     the full-size parity tests only
 #   smoke        __graft_entry__.smoke()
 #   quick        tools/quick_bench.py at 16384 / 131072 / 4096 envs + grasp replay
-#   variants     every gym_genesis_b200/variants/*.so through quick_bench (+ grasp replay when GRASP=1)
+#   variants     every gym_genesis_b200/variants/*.so through quick_bench at the env counts in $ENVS (+ grasp replay when GRASP=1)
 #   bench        bench.py (own arm) + reference arm
 #   benchlite    bench.py --no-workload-b --no-workload-c --no-config4 --no-workload-d (headline legs only)
 #   launches     ncu launch list of bench.py
@@ -34,8 +34,7 @@ for stage in "$@"; do
               python tools/grasp_bench.py 2>&1 | tail -3 | tee ${O}_grasp.log ;;
     variants) for so in gym_genesis_b200/variants/*.so; do
                 v=$(basename $so .so)
-                GG_B200_LIB=$PWD/$so python tools/quick_bench.py --tag $v 2>&1 | tail -1 | tee -a ${O}_variants.log
-                if [ -n "$BIG" ]; then GG_B200_LIB=$PWD/$so python tools/quick_bench.py --tag $v --envs 131072 --steps 50 2>&1 | tail -1 | tee -a ${O}_variants.log; fi
+                for n in ${ENVS:-16384}; do GG_B200_LIB=$PWD/$so python tools/quick_bench.py --tag $v --envs $n --steps ${STEPS:-200} 2>&1 | tail -1 | tee -a ${O}_variants.log; done
                 if [ -n "$GRASP" ]; then GG_B200_LIB=$PWD/$so python tools/grasp_bench.py 2>&1 | tail -1 | tee -a ${O}_variants.log; fi
               done ;;
     bench)    python bench.py > ${O}_bench.json 2> ${O}_bench.err; tail -c 1500 ${O}_bench.json; tail -3 ${O}_bench.err
