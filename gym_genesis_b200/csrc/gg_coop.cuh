@@ -26,6 +26,7 @@ template <int NA, int NF> struct TeamWork {          // published by the MAIN la
     float lR[9], lp[3];
     float fR[NF > 0 ? NF : 1][9], fp[NF > 0 ? NF : 1][3];
     float cube[19];                                   // cp3 cq4 cv3 cw3 qacc6
+    float q[NU];                                      // joint positions (the drain warp of step_rs_kernel integrates the env itself)
 };
 
 #ifndef GG_TEAM_CAP

@@ -50,6 +50,10 @@ struct StepArgs {
     uint64_t seed; int64_t first_env; uint32_t step_index;
     double* stats;
     float* team_scratch;      // n_envs x sizeof(TeamWork) / 4 floats: dynamics of coupled envs, published by their MAIN lane
+    // role-per-SM kernel (gg_step_rs.cuh): per-group mailboxes + flags, launch epoch, coupled-env list, role split of the grid
+    float* mbox; uint32_t* mflag; uint32_t epoch;
+    int* ctl; int* clist; uint32_t* cready;
+    int n_main, n_rnea, n_cube;
 };
 
 template <int NU> __device__ __forceinline__ void load_state(const float* __restrict__ st, int stride, int e, gg::EnvState<NU>& s) {
@@ -634,6 +638,8 @@ __global__ void __launch_bounds__(kBlockThreads, GG_MINBLOCKS) step_kernel(const
     }
 }
 
+#include "gg_step_rs.cuh"
+
 // env-major (n, nq) / (n, nv) copies <-> SoA state
 template <int NU>
 __global__ void state_copy_kernel(float* state, int stride, int n, float* q, float* qd, float* qacc, int to_soa) {
@@ -799,6 +805,8 @@ struct GgSim {
     float* state; int32_t* step_count; int32_t* episode;
     uint8_t* done; double* stats;       // library-owned (allocated once in gg_create)
     float* team_scratch;                // library-owned: published dynamics of coupled envs (step_kernel solver teams)
+    float* mbox; uint32_t* mflag; int* ctl; int* clist; uint32_t* cready;   // library-owned: role-per-SM kernel mailboxes / coupled list
+    uint32_t epoch; int n_sm; int use_blocks;   // launch epoch of the mailbox flags; SM count; 1 = round-1 block kernel (GG_STEP_KERNEL=blocks)
     int32_t* slot;                      // library-owned, allocated on first gg_export_successful: env -> compacted episode slot
     uint32_t step_index;
     static constexpr int kPinCache = 16;
@@ -846,10 +854,29 @@ static int launch_step(GgSim* sim, StepArgs& A, gg_stream_t stream) {
     A.stats = sim->stats; A.team_scratch = sim->team_scratch;
     auto al16 = [](const void* p) { return ((uintptr_t)p & 15u) == 0; };
     A.vec_out = al16(A.obs_agent) && al16(A.obs_env) && al16(A.obs_agent_host) && al16(A.obs_env_host) && al16(A.action_dev);
-    const int grid = (sim->n + 31) / 32;                 // 32 envs x 3 role warps per block
     GG_CUDA(cudaSetDevice(sim->device));
-    if (sim->kind == 0) step_kernel<7, 2, false><<<grid, kBlockThreads, 0, (cudaStream_t)stream>>>(A);
-    else step_kernel<5, 1, true><<<grid, kBlockThreads, 0, (cudaStream_t)stream>>>(A);
+    if (sim->use_blocks) {
+        const int grid = (sim->n + 31) / 32;             // 32 envs x 3 role warps per block
+        if (sim->kind == 0) step_kernel<7, 2, false><<<grid, kBlockThreads, 0, (cudaStream_t)stream>>>(A);
+        else step_kernel<5, 1, true><<<grid, kBlockThreads, 0, (cudaStream_t)stream>>>(A);
+    } else {
+        // one persistent CTA per SM, one role per CTA.  Latency regime (every group gets its own warp in every role): equal thirds;
+        // throughput regime: CTAs in proportion to the roles' instruction counts (MAIN 5.5 k, RNEA 3.5 k, CUBE 5 k per group).
+        const int G = sim->n_sm, ngroups = (sim->n + 31) / 32;
+        A.mbox = sim->mbox; A.mflag = sim->mflag; A.ctl = sim->ctl; A.clist = sim->clist; A.cready = sim->cready;
+        A.epoch = ++sim->epoch;
+        if (A.epoch == 0) A.epoch = ++sim->epoch;
+        if (ngroups <= rs::kWarps * (G / 3)) { A.n_rnea = G / 3; A.n_cube = G / 3; }
+        else { A.n_rnea = (int)(G * 0.25f); A.n_cube = (int)(G * 0.36f); }
+        A.n_main = G - A.n_rnea - A.n_cube;
+        void* args[] = {(void*)&A};
+        if (sim->kind == 0)
+            GG_CUDA(cudaLaunchCooperativeKernel((const void*)rs::step_rs_kernel<7, 2, false>, dim3(G), dim3(rs::kThreads), args,
+                                                rs::kWarps * rs::WarpScratch<7, 2>::bytes, (cudaStream_t)stream));
+        else
+            GG_CUDA(cudaLaunchCooperativeKernel((const void*)rs::step_rs_kernel<5, 1, true>, dim3(G), dim3(rs::kThreads), args,
+                                                rs::kWarps * rs::WarpScratch<5, 1>::bytes, (cudaStream_t)stream));
+    }
     g_launches.fetch_add(1);
     GG_CUDA(cudaGetLastError());
     return 0;
@@ -884,12 +911,37 @@ int gg_create(const GgModel* model, int n_envs, int device, GgSim** out) {
     cudaError_t e2 = cudaMalloc(&s->stats, 8 * sizeof(double));
     const size_t twf = kind == 0 ? sizeof(gg::TeamWork<7, 2>) : sizeof(gg::TeamWork<5, 1>);
     cudaError_t e3 = cudaMalloc(&s->team_scratch, (size_t)s->stride * twf);
-    if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) {
-        cudaFree(s->done); cudaFree(s->stats); cudaFree(s->team_scratch); delete s;
+    const size_t ngroups = (size_t)s->stride / 32;
+    const size_t nready = (size_t)s->stride + 4096;       // list slots + the tickets idle warps may over-claim
+    cudaError_t e4 = cudaMalloc(&s->mbox, ngroups * rs::MB_ROWS * 32 * sizeof(float));
+    cudaError_t e5 = cudaMalloc(&s->mflag, ngroups * 4 * sizeof(uint32_t));
+    cudaError_t e6 = cudaMalloc(&s->ctl, 8192 * sizeof(int));
+    cudaError_t e7 = cudaMalloc(&s->clist, nready * sizeof(int));
+    cudaError_t e8 = cudaMalloc(&s->cready, nready * sizeof(uint32_t));
+    if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess || e4 != cudaSuccess || e5 != cudaSuccess || e6 != cudaSuccess ||
+        e7 != cudaSuccess || e8 != cudaSuccess) {
+        cudaFree(s->done); cudaFree(s->stats); cudaFree(s->team_scratch); cudaFree(s->mbox); cudaFree(s->mflag); cudaFree(s->ctl);
+        cudaFree(s->clist); cudaFree(s->cready); delete s;
         return fail("gg_create: cudaMalloc failed%s");
     }
     cudaMemset(s->done, 0, (size_t)s->stride);
     cudaMemset(s->stats, 0, 8 * sizeof(double));
+    cudaMemset(s->mflag, 0, ngroups * 4 * sizeof(uint32_t));
+    cudaMemset(s->ctl, 0, 8192 * sizeof(int));
+    cudaMemset(s->cready, 0, nready * sizeof(uint32_t));
+    cudaMemset(s->mbox, 0, ngroups * rs::MB_ROWS * 32 * sizeof(float));
+    {
+        int coop = 0;
+        cudaDeviceGetAttribute(&s->n_sm, cudaDevAttrMultiProcessorCount, device);
+        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device);
+        // GG_STEP_KERNEL=rs selects the experimental role-per-SM kernel (gg_step_rs.cuh; measured slower, profiles/r02_notes.md)
+        const char* k = getenv("GG_STEP_KERNEL");
+        s->use_blocks = !(k && strcmp(k, "rs") == 0) || !coop || s->n_sm < 3;
+        cudaFuncSetAttribute((const void*)rs::step_rs_kernel<7, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)(rs::kWarps * rs::WarpScratch<7, 2>::bytes));
+        cudaFuncSetAttribute((const void*)rs::step_rs_kernel<5, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)(rs::kWarps * rs::WarpScratch<5, 1>::bytes));
+    }
     *out = s;
     return 0;
 }
@@ -898,6 +950,7 @@ int gg_destroy(GgSim* sim) {
     if (!sim) return 0;
     cudaSetDevice(sim->device);
     cudaFree(sim->done); cudaFree(sim->stats); cudaFree(sim->team_scratch); cudaFree(sim->slot);
+    cudaFree(sim->mbox); cudaFree(sim->mflag); cudaFree(sim->ctl); cudaFree(sim->clist); cudaFree(sim->cready);
     delete sim;
     return 0;
 }
@@ -1028,6 +1081,13 @@ int gg_ik(GgSim* sim, int n_rows, const int32_t* envs_idx, const float* target_p
     else ik_kernel<5, 1><<<grid, 64, 0, (cudaStream_t)stream>>>(A);
     g_launches.fetch_add(1);
     GG_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// developer hook (not in the public header): copies the first n ints of the control block to the host (GG_RS_TRACE timestamps)
+int gg_debug_ctl(GgSim* sim, int* out, int n) {
+    if (!sim || !out || n > 8192) return fail("gg_debug_ctl: bad argument%s");
+    GG_CUDA(cudaMemcpy(out, sim->ctl, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost));
     return 0;
 }
 

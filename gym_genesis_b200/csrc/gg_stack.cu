@@ -75,6 +75,8 @@ struct StackArgs {
     uint8_t* terminated; uint8_t* truncated;
     const uint8_t* reset_mask; const float* obj_xy;
     float* reward_host; uint8_t* terminated_host; uint8_t* truncated_host;   // nullable pinned-host mirrors (gg_stack_step_host)
+    float* obs_agent_host; float* obs_env_host;   // nullable pinned-host observation mirrors
+    float* action_dev;                            // nullable device copy of the consumed action batch
     int mode;                 // 0 = env.step, 1 = reset (+ settle) of masked envs, 2 = observe only
     int iterations; float tol;
     int auto_reset, time_limit; float reset_prob;
@@ -220,6 +222,10 @@ __global__ void __launch_bounds__(96, 4) stack_prep_kernel(const __grid_constant
         const bool use_action = A.mode == 0 && !do_reset;
 #pragma unroll
         for (int i = 0; i < NU; i++) target[i] = use_action ? A.action[(size_t)e * NU + i] : A.M.home_q[i];
+        if (A.action_dev != nullptr && A.mode == 0 && live) {     // PD targets persist on the device after a host-fed step
+#pragma unroll
+            for (int i = 0; i < NU; i++) A.action_dev[(size_t)e * NU + i] = A.action[(size_t)e * NU + i];
+        }
         gg::robot_rnea<NA, NF, FH>(A.M, A.C, q, qd, target, fs);
 #pragma unroll
         for (int i = 0; i < NU; i++) s_fs[i * 32 + lane] = fs[i];
@@ -478,6 +484,16 @@ __global__ void __launch_bounds__(128) stack_finish_kernel(const __grid_constant
         float* oe = A.obs_env + (size_t)e * GG_STACK_ENV_STATE_DIM;
 #pragma unroll
         for (int i = 0; i < GG_STACK_ENV_STATE_DIM; i++) oe[i] = envs[i];
+        if (A.obs_agent_host) {
+            float* oh = A.obs_agent_host + (size_t)e * adim;
+#pragma unroll
+            for (int i = 0; i < 7 + NF; i++) if (i < adim) oh[i] = agent[i];
+        }
+        if (A.obs_env_host) {
+            float* oh = A.obs_env_host + (size_t)e * GG_STACK_ENV_STATE_DIM;
+#pragma unroll
+            for (int i = 0; i < GG_STACK_ENV_STATE_DIM; i++) oh[i] = envs[i];
+        }
         if (A.reward) A.reward[e] = rew;
         if (A.terminated) A.terminated[e] = succ ? 1 : 0;
         if (A.truncated) A.truncated[e] = trunc ? 1 : 0;
@@ -741,8 +757,8 @@ int gg_stack_step_host(GgStackSim* sim, const GgHostIO* io, float* obs_agent, fl
                        uint8_t* truncated, const uint8_t* reset_mask, gg_stream_t stream) {
     if (!sim || !io || !io->action || !obs_agent || !obs_env) return gg_internal_fail("gg_stack_step_host: null argument%s", "");
     // the answer of the driver query is cached per pointer so that the steady-state step pays none
-    const void* ptrs[4] = {io->action, io->reward, io->terminated, io->truncated};
-    for (int k = 0; k < 4; k++) {
+    const void* ptrs[6] = {io->action, io->reward, io->terminated, io->truncated, io->obs_agent, io->obs_env};
+    for (int k = 0; k < 6; k++) {
         if (!ptrs[k]) continue;
         bool known = false;
         for (int i = 0; i < GgStackSim::kPinCache; i++) known = known || sim->pin_ok[i] == ptrs[k];
@@ -757,6 +773,7 @@ int gg_stack_step_host(GgStackSim* sim, const GgHostIO* io, float* obs_agent, fl
     A.action = io->action; A.obs_agent = obs_agent; A.obs_env = obs_env; A.reward = reward; A.terminated = terminated;
     A.truncated = truncated; A.reset_mask = reset_mask; A.mode = 0;
     A.reward_host = io->reward; A.terminated_host = io->terminated; A.truncated_host = io->truncated;
+    A.obs_agent_host = io->obs_agent; A.obs_env_host = io->obs_env; A.action_dev = io->action_dev;
     const int rc = stack_launch(sim, A, stream);
     sim->step_index++;
     if (rc != 0) return rc;

@@ -21,7 +21,7 @@ class GenesisEnv(gym.Env):
 
     def __init__(self, task, robot="so101", enable_pixels=False, observation_height=480, observation_width=640, num_envs=1,
                  env_spacing=(1.0, 1.0), render_mode=None, camera_capture_mode="per_env", strip_environment_state=True,
-                 numpy_flags=False, host_io=False, **sim_kwargs):
+                 numpy_flags=False, host_io=False, host_obs=False, **sim_kwargs):
         super().__init__()
         self.task = task
         self.robot = robot
@@ -35,6 +35,7 @@ class GenesisEnv(gym.Env):
         self.strip_environment_state = strip_environment_state
         self.numpy_flags = numpy_flags
         self.host_io = host_io
+        self.host_obs = host_obs          # host_io only: observations are returned as CPU tensors too (pinned mirrors written by the kernel)
         self._sim_kwargs = sim_kwargs
         self._env = self._make_env_task(self.task)
         self.observation_space = self._env.observation_space
@@ -56,10 +57,15 @@ class GenesisEnv(gym.Env):
         if self.host_io:
             # host-resident policy loop (the reference's numpy convention): zero-copy action read, reward / flags land in
             # pinned host memory, one stream synchronisation per step; observations stay on the device
-            reward, terminated, truncated = self._env.step_host(action, reset_mask)
+            if self.host_obs:
+                reward, terminated, truncated = self._env.step_host(action, reset_mask, host_obs=True)
+                observation = self._env.get_obs_host()
+            else:
+                reward, terminated, truncated = self._env.step_host(action, reset_mask)
+                observation = self._env.get_obs()
             if self.numpy_flags:
                 terminated, truncated = terminated.numpy(), truncated.numpy()
-            return self._env.get_obs(), reward, terminated, truncated, {"is_success": terminated}
+            return observation, reward, terminated, truncated, {"is_success": terminated}
         _, reward, _, observation = self._env.step(action, reset_mask)
         sim = self._env.sim
         is_success = sim.terminated                 # == (reward == 1), computed in-kernel with the strict z > 0.1f test

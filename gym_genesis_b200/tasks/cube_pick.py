@@ -97,7 +97,7 @@ class CubePickBatch:
 
     def __init__(self, enable_pixels, observation_height, observation_width, num_envs, env_spacing, camera_capture_mode,
                  strip_environment_state, device="cuda", auto_reset=False, time_limit=False, solver_iterations=10,
-                 solver_tolerance=1e-5, seed=0, first_env_id=0, reset_prob=0.0, success_height=None):
+                 solver_tolerance=1e-5, seed=0, first_env_id=0, reset_prob=0.0, success_height=None, alias_outputs=False):
         if enable_pixels:
             raise NotImplementedError("state-only path: rendering (enable_pixels=True) is out of scope (SURVEY.md section 5)")
         if num_envs <= 0:
@@ -112,9 +112,13 @@ class CubePickBatch:
         self.model = get_model(self.robot_name)
         if success_height is not None:
             self.model.success_z = float(success_height)
+        # alias_outputs=False (default): every step / reset returns NEW tensors, as the reference's getters do (franka/cube_pick.py:137-157),
+        # so `all_rewards.append(reward)` collectors and (obs, next_obs) replay buffers keep what they stored.  alias_outputs=True reuses
+        # one set of output buffers (zero allocation, CUDA-graph safe): the tensors of step t are overwritten by step t + 1.
+        self.alias_outputs = bool(alias_outputs)
         self.sim = BatchedSim(self.model, num_envs, device=device, solver_iterations=solver_iterations,
                               solver_tolerance=solver_tolerance, auto_reset=auto_reset, time_limit=time_limit,
-                              reset_prob=reset_prob, seed=seed, first_env_id=first_env_id)
+                              reset_prob=reset_prob, seed=seed, first_env_id=first_env_id, fresh_outputs=not self.alias_outputs)
         self.agent_dim = self.sim.agent_dim
         self.observation_space = self._make_obs_space()
         self.action_space = spaces.Box(low=-1.0, high=1.0, shape=(self.sim.nu,), dtype=np.float32)
@@ -173,13 +177,22 @@ class CubePickBatch:
         self._physics_step(a, reset_mask)
         return None, self.compute_reward(), None, self.get_obs()
 
-    def step_host(self, action, reset_mask=None):
+    def step_host(self, action, reset_mask=None, host_obs=False):
         """`step` for a host-resident policy (numpy / CPU-tensor actions, the reference's README convention): the kernel
         reads a pinned action batch in place and writes reward / terminated / truncated straight into pinned host arrays.
-        Returns (reward, terminated, truncated) as CPU tensors valid on return; observations stay on the device."""
-        out = self.sim.step_host(action, reset_mask)
-        self._targets = self.sim._last_action
+        Returns (reward, terminated, truncated) as CPU tensors valid on return; observations stay on the device
+        (host_obs=True: the kernel also mirrors them into pinned host memory, see `get_obs_host`).  The consumed targets are kept
+        ON THE DEVICE by the kernel itself, so `push()`, `control_dofs_position` and masked resets work after a host-fed step."""
+        out = self.sim.step_host(action, reset_mask, host_obs=host_obs)
+        self._targets = self.sim._last_action           # device tensor written by the step kernel
         return out
+
+    def get_obs_host(self):
+        """Pinned host mirrors of the observations written by the last `step_host(..., host_obs=True)`."""
+        oa, oe = self.sim.host_obs_agent, self.sim.host_obs_env
+        if not self.alias_outputs:
+            oa, oe = oa.clone(), oe.clone()
+        return {"agent_pos": oa, "environment_state": oe}
 
     def compute_reward(self):
         return self.sim.reward
