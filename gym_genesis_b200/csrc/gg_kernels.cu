@@ -52,7 +52,7 @@ struct StepArgs {
     float* team_scratch;      // n_envs x sizeof(TeamWork) / 4 floats: dynamics of coupled envs, published by their MAIN lane
     // role-per-SM kernel (gg_step_rs.cuh): per-group mailboxes + flags, launch epoch, coupled-env list, role split of the grid
     float* mbox; uint32_t* mflag; uint32_t epoch;
-    int* ctl; int* clist; uint32_t* cready;
+    int* ctl; int* clist; uint32_t* cready; int list_cap;
     int n_main, n_rnea, n_cube;
 };
 
@@ -112,10 +112,13 @@ template <int NU> __device__ __forceinline__ void store_state(float* __restrict_
 // Envs whose pads may touch the cube or the plane ("coupled") leave the
 // thread-per-env mapping: after barrier 1 the three warps of the block become three solver teams and work through the
 // block's coupled envs ONE WARP PER ENV (gg_coop.cuh; 10 KB of shared memory per team).  The MAIN lane of a coupled env
-// publishes its dynamics to the env's slot of a global scratch slab (832 B, L2 resident); after barrier 4 the teams pop
+// publishes its dynamics to the env's slot of a global scratch slab (0.9 KB, L2 resident); after barrier 4 the teams pop
 // envs from a block-local queue (team_queue) until it is empty, barrier 5.  Blocks without coupled envs never execute
-// that code.  (Tried and measured, profiles/r01_notes.md: team buffers in a global scratch slice -- 1.5x slower
-// teams; a second, device-launched kernel for the coupled envs (CUDA dynamic parallelism tail launch) -- 2.6x slower.)
+// that code.  Tried and measured: team buffers in a global scratch slice -- 1.5x slower teams; a device-launched second kernel
+// -- 2.6x slower (profiles/r01_notes.md); ONE grid-wide list of coupled envs drained by every warp of the launch (gg_drain.cuh, the
+// scheme of the thread-per-env kernel below) -- 19.6 M instead of 32 M env-steps/s on the scripted grasp: 1500 warps at unrelated
+// points of the 155 KB solver stream their instructions separately, while the block-local teams of a launch start together and share
+// most fetches (SM IPC 0.69 vs 0.95, stall_no_instruction 61 % of the solver's samples; profiles/r02_notes.md).
 //
 // Outputs: agent_pos (32 x (7 + NF) floats) and environment_state (32 x 11 floats) of a full block are contiguous slabs of the
 // env-major output arrays; the lanes stage their rows in shared memory and the warp writes the slab with 128-bit stores (and,
@@ -638,7 +641,210 @@ __global__ void __launch_bounds__(kBlockThreads, GG_MINBLOCKS) step_kernel(const
     }
 }
 
+#include "gg_drain.cuh"
+
+// ------------------------------------------------------------------------------------------------
+// step_mono_kernel: ONE THREAD = the whole env.step of one env (no role split).  The role kernel above shortens the dependent chain
+// of a launch that cannot fill the GPU (<= ~32 k envs: 2.6 warps per scheduler) at the price of 41 % more instructions (three roles
+// walk the same kinematic chain); with >= 7 env-warps per scheduler the GPU is instruction-supply bound and the cheaper instruction
+// count wins (profiles/r01_notes.md v5: 749 M vs 504 M env-steps/s at 131072 envs; r02_notes.md for this version).  Same device
+// functions, same arithmetic per env, same coupled-env list / drain; launch_step picks the kernel by env count.
+// ------------------------------------------------------------------------------------------------
+constexpr int kMonoThreads = 64;
+constexpr int kMonoEnvsPerSm = 200;    // >= 200 envs per SM (29600 envs on a B200): thread-per-env kernel (measured cross-over ~28 k)
+
+template <int NA, int NF, bool FH>
+__global__ void __launch_bounds__(kMonoThreads) step_mono_kernel(const __grid_constant__ StepArgs A) {
+    constexpr int NU = NA + NF, NV = NU + 6, AD = 7 + NF;
+    __shared__ gg::TeamWork<NA, NF> TW[kMonoThreads / 32];
+    __shared__ gg::TeamBuf<NV> TB[kMonoThreads / 32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int e0 = blockIdx.x * kMonoThreads + threadIdx.x;
+    const bool live = e0 < A.n;
+    const int e = live ? e0 : A.n - 1;
+    const uint32_t gid = (uint32_t)(A.first_env + e);
+    const bool run_sub = A.mode == 0 || (A.mode == 1 && A.M.settle_steps > 0);
+    bool do_reset = reset_decision(A, e, gid);
+    const bool active = do_reset ? (A.M.settle_steps > 0) : (A.mode == 0);
+    const float* sp = A.state + e;
+    const size_t st = (size_t)A.stride;
+    float q[NU], qd[NU], qa[NU];
+#pragma unroll
+    for (int i = 0; i < NU; i++) {
+        const float lq = sp[i * st], lqd = sp[(NU + i) * st], lqa = sp[(2 * NU + 13 + i) * st];
+        q[i] = do_reset ? A.M.home_q[i] : lq; qd[i] = do_reset ? 0.f : lqd; qa[i] = do_reset ? 0.f : lqa;
+    }
+    const float* cpn = sp + (2 * NU) * st;
+    gg::V3 cp = gg::mk(cpn[0], cpn[st], cpn[2 * st]);
+    gg::Q4 cq = gg::mkq(cpn[3 * st], cpn[4 * st], cpn[5 * st], cpn[6 * st]);
+    gg::V3 cv = gg::mk(cpn[7 * st], cpn[8 * st], cpn[9 * st]);
+    gg::V3 cw = gg::mk(cpn[10 * st], cpn[11 * st], cpn[12 * st]);
+    float qac[6];
+#pragma unroll
+    for (int i = 0; i < 6; i++) qac[i] = sp[(2 * NU + 13 + NU + i) * st];
+    int steps = A.step_count[e], epi = A.episode[e];
+    if (do_reset) {
+        float x, y;
+        if (A.cube_xy != nullptr) { x = A.cube_xy[2 * e]; y = A.cube_xy[2 * e + 1]; }
+        else gg::spawn_draw(A.M, A.seed, gid, (uint32_t)epi, x, y);
+        cp = gg::mk(x, y, A.M.spawn_z); cq = gg::ldq(A.M.spawn_quat);
+        cv = gg::mk(0.f, 0.f, 0.f); cw = gg::mk(0.f, 0.f, 0.f);
+#pragma unroll
+        for (int i = 0; i < 6; i++) qac[i] = 0.f;
+        epi += 1; steps = 0;
+    }
+    cl::Tally T;
+#pragma unroll
+    for (int k = 0; k < 8; k++) T.v[k] = 0.f;
+    bool coupled = false;
+    if (run_sub) {
+        gg::RobotDyn<NA, NF> D;
+        {
+            ActionFetch<NU> tf;
+            tf.home = A.M.home_q; tf.slab = nullptr; tf.global = A.action + (size_t)e * NU;
+            tf.staged = false; tf.use_action = A.mode == 0 && !do_reset;
+            gg::robot_rnea_t<NA, NF, FH>(A.M, A.C, q, qd, tf, D.fs, &D);
+            if (A.action_dev != nullptr && A.mode == 0 && live) {
+#pragma unroll
+                for (int i = 0; i < NU; i++) A.action_dev[(size_t)e * NU + i] = A.action[(size_t)e * NU + i];
+            }
+        }
+        coupled = live && active && gg::pads_may_touch<NA, NF>(A.M, D, cp, cq);
+        {
+            gg::LinkStoreLocal<NA> ls;
+            gg::robot_crba<NA, NF, FH>(A.M, A.C, q, D, ls);
+        }
+        float L[NU * (NU + 1) / 2], dinv[NU];
+#pragma unroll
+        for (int i = 0; i < NU * (NU + 1) / 2; i++) L[i] = D.Mt[i];
+        gg::chol_packed<NU>(L, dinv);
+        float lsg[NU], laref[NU], lD[NU];
+        const int nlim = gg::joint_limit_rows<NU>(A.M, q, qd, lsg, laref, lD);
+        float as[NU], a[NU];
+        gg::chol_solve_packed<NU>(L, dinv, D.fs, as);
+        float Mc[6], as_c[6], qd_c[6], a_c[6];
+        gg::cube_free_acc(A.M, cv, cw, Mc, as_c, qd_c);
+        gg::StepInfo ir, ic;
+        ir.ncon = ic.ncon = 0; ir.iters = ic.iters = 0; ir.grad = ic.grad = 0.f;
+#pragma unroll
+        for (int i = 0; i < NU; i++) a[i] = as[i];
+#pragma unroll
+        for (int i = 0; i < 6; i++) a_c[i] = as_c[i];
+        if (live && !coupled) {
+            gg::robot_block_solve<NU>(D.Mt, as, nlim, lsg, laref, lD, qa, a, A.iterations, A.tol, ir);
+            gg::CubeConLocal cs;
+            gg::cube_block_solve(A.M, cp, gg::qmat(cq), Mc, as_c, qd_c, qac, a_c, A.iterations, A.tol, cs, ic);
+        }
+        const unsigned cm = __ballot_sync(0xffffffffu, coupled);
+        if (cm != 0u) {
+            if (coupled) {
+                constexpr int TWF = sizeof(gg::TeamWork<NA, NF>) / sizeof(float);
+                gg::TeamWork<NA, NF>& W = *reinterpret_cast<gg::TeamWork<NA, NF>*>(A.team_scratch + (size_t)e0 * TWF);
+#pragma unroll
+                for (int i = 0; i < NU * (NU + 1) / 2; i++) W.Mt[i] = D.Mt[i];
+#pragma unroll
+                for (int i = 0; i < NU; i++) {
+                    W.as[i] = as[i]; W.qd[i] = qd[i]; W.warm[i] = qa[i]; W.lsg[i] = lsg[i]; W.laref[i] = laref[i]; W.lD[i] = lD[i];
+                    W.q[i] = q[i];
+                }
+#pragma unroll
+                for (int i = 0; i < NA; i++) {
+                    W.jk[i][0] = D.jk[i].x; W.jk[i][1] = D.jk[i].y; W.jk[i][2] = D.jk[i].z;
+                    W.jo[i][0] = D.jo[i].x; W.jo[i][1] = D.jo[i].y; W.jo[i][2] = D.jo[i].z;
+                }
+#pragma unroll
+                for (int f = 0; f < NF; f++) {
+                    W.fk[f][0] = D.fk[f].x; W.fk[f][1] = D.fk[f].y; W.fk[f][2] = D.fk[f].z;
+                    W.fo[f][0] = D.fo[f].x; W.fo[f][1] = D.fo[f].y; W.fo[f][2] = D.fo[f].z;
+                    W.fR[f][0] = D.fR[f].c0.x; W.fR[f][1] = D.fR[f].c0.y; W.fR[f][2] = D.fR[f].c0.z;
+                    W.fR[f][3] = D.fR[f].c1.x; W.fR[f][4] = D.fR[f].c1.y; W.fR[f][5] = D.fR[f].c1.z;
+                    W.fR[f][6] = D.fR[f].c2.x; W.fR[f][7] = D.fR[f].c2.y; W.fR[f][8] = D.fR[f].c2.z;
+                    W.fp[f][0] = D.fp[f].x; W.fp[f][1] = D.fp[f].y; W.fp[f][2] = D.fp[f].z;
+                }
+                W.lR[0] = D.lR.c0.x; W.lR[1] = D.lR.c0.y; W.lR[2] = D.lR.c0.z;
+                W.lR[3] = D.lR.c1.x; W.lR[4] = D.lR.c1.y; W.lR[5] = D.lR.c1.z;
+                W.lR[6] = D.lR.c2.x; W.lR[7] = D.lR.c2.y; W.lR[8] = D.lR.c2.z;
+                W.lp[0] = D.lp.x; W.lp[1] = D.lp.y; W.lp[2] = D.lp.z;
+                W.cube[0] = cp.x; W.cube[1] = cp.y; W.cube[2] = cp.z; W.cube[3] = cq.w; W.cube[4] = cq.x; W.cube[5] = cq.y; W.cube[6] = cq.z;
+                W.cube[7] = cv.x; W.cube[8] = cv.y; W.cube[9] = cv.z; W.cube[10] = cw.x; W.cube[11] = cw.y; W.cube[12] = cw.z;
+#pragma unroll
+                for (int i = 0; i < 6; i++) W.cube[13 + i] = qac[i];
+            }
+            cl::list_append(A, cm, coupled, e0, lane);
+        }
+        if (active && !coupled) {
+            gg::integrate_robot<NU>(A.M, q, qd, qa, a);
+            gg::integrate_cube(A.M, cp, cq, cv, cw, qac, a_c);
+            T.v[6] = (float)(ic.iters > ir.iters ? ic.iters : ir.iters); T.v[7] = (float)ic.ncon;
+        }
+    }
+    const bool commit = live && !coupled;
+    {
+        float acc = cp.x + cp.y + cp.z + cq.w + cq.x + cq.y + cq.z + cv.x + cv.y + cv.z + cw.x + cw.y + cw.z;
+#pragma unroll
+        for (int i = 0; i < NU; i++) acc += q[i] + qd[i];
+        if (run_sub && active && commit && !isfinite(acc)) {          // diverged env: re-spawn
+            float x, y;
+            gg::spawn_draw(A.M, A.seed, gid, (uint32_t)epi, x, y);
+            cp = gg::mk(x, y, A.M.spawn_z); cq = gg::ldq(A.M.spawn_quat);
+            cv = gg::mk(0.f, 0.f, 0.f); cw = gg::mk(0.f, 0.f, 0.f);
+#pragma unroll
+            for (int i = 0; i < 6; i++) qac[i] = 0.f;
+            // NOTE: fresh array selected element-wise (in-place conditional overwrite of q[] was miscompiled by nvcc 12.9, r01 notes)
+            float qh[NU];
+#pragma unroll
+            for (int i = 0; i < NU; i++) qh[i] = A.M.home_q[i];
+#pragma unroll
+            for (int i = 0; i < NU; i++) { q[i] = qh[i]; qd[i] = 0.f; qa[i] = 0.f; }
+            epi += 1; steps = 0; T.v[5] = 1.f;
+            do_reset = true;
+        }
+    }
+    gg::V3 ep; gg::Q4 eq;
+    gg::robot_eef<NA, NF>(A.M, q, ep, eq);
+    if (commit) {
+        const gg::V3 d = ep - cp;
+        float oa[AD], oe[GG_ENV_STATE_DIM];
+        oa[0] = ep.x; oa[1] = ep.y; oa[2] = ep.z; oa[3] = eq.w; oa[4] = eq.x; oa[5] = eq.y; oa[6] = eq.z;
+#pragma unroll
+        for (int f = 0; f < NF; f++) oa[7 + f] = q[NA + f];
+        oe[0] = cp.x; oe[1] = cp.y; oe[2] = cp.z; oe[3] = cq.w; oe[4] = cq.x; oe[5] = cq.y; oe[6] = cq.z;
+        oe[7] = d.x; oe[8] = d.y; oe[9] = d.z; oe[10] = sqrtf(gg::dot(d, d));
+#pragma unroll
+        for (int i = 0; i < AD; i++) { A.obs_agent[(size_t)e * AD + i] = oa[i]; if (A.obs_agent_host) A.obs_agent_host[(size_t)e * AD + i] = oa[i]; }
+#pragma unroll
+        for (int i = 0; i < GG_ENV_STATE_DIM; i++) {
+            A.obs_env[(size_t)e * GG_ENV_STATE_DIM + i] = oe[i];
+            if (A.obs_env_host) A.obs_env_host[(size_t)e * GG_ENV_STATE_DIM + i] = oe[i];
+        }
+        if (A.mode != 2 && (active || do_reset)) {
+            float* wp = A.state + e;
+#pragma unroll
+            for (int i = 0; i < NU; i++) { wp[i * st] = q[i]; wp[(NU + i) * st] = qd[i]; wp[(2 * NU + 13 + i) * st] = qa[i]; }
+        }
+        cl::commit_cube<NU>(A, e, cp, cq, cv, cw, qac, steps, epi, do_reset, active, T);
+    } else {
+#pragma unroll
+        for (int k = 0; k < 8; k++) T.v[k] = 0.f;
+    }
+    if (A.stats != nullptr && A.mode == 0) {
+        float mine = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            float x = T.v[k];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+            if (lane == k) mine = x;
+        }
+        if (lane < 8 && mine != 0.f) atomicAdd(&A.stats[lane], (double)mine);
+    }
+    // ---- coupled envs of the whole launch (gg_drain.cuh)
+    if (run_sub) cl::drain_all<NA, NF, FH>(A, lane, TB[w], TW[w]);
+}
+
+#ifdef GG_WITH_RS_KERNEL
 #include "gg_step_rs.cuh"
+#endif
 
 // env-major (n, nq) / (n, nv) copies <-> SoA state
 template <int NU>
@@ -806,7 +1012,7 @@ struct GgSim {
     uint8_t* done; double* stats;       // library-owned (allocated once in gg_create)
     float* team_scratch;                // library-owned: published dynamics of coupled envs (step_kernel solver teams)
     float* mbox; uint32_t* mflag; int* ctl; int* clist; uint32_t* cready;   // library-owned: role-per-SM kernel mailboxes / coupled list
-    uint32_t epoch; int n_sm; int use_blocks;   // launch epoch of the mailbox flags; SM count; 1 = round-1 block kernel (GG_STEP_KERNEL=blocks)
+    uint32_t epoch; int n_sm; int use_blocks; int use_mono; int64_t list_budget;   // launch epoch of the mailbox flags; SM count; 1 = round-1 block kernel (GG_STEP_KERNEL=blocks)
     int32_t* slot;                      // library-owned, allocated on first gg_export_successful: env -> compacted episode slot
     uint32_t step_index;
     static constexpr int kPinCache = 16;
@@ -855,17 +1061,21 @@ static int launch_step(GgSim* sim, StepArgs& A, gg_stream_t stream) {
     auto al16 = [](const void* p) { return ((uintptr_t)p & 15u) == 0; };
     A.vec_out = al16(A.obs_agent) && al16(A.obs_env) && al16(A.obs_agent_host) && al16(A.obs_env_host) && al16(A.action_dev);
     GG_CUDA(cudaSetDevice(sim->device));
-    if (sim->use_blocks) {
-        const int grid = (sim->n + 31) / 32;             // 32 envs x 3 role warps per block
-        if (sim->kind == 0) step_kernel<7, 2, false><<<grid, kBlockThreads, 0, (cudaStream_t)stream>>>(A);
-        else step_kernel<5, 1, true><<<grid, kBlockThreads, 0, (cudaStream_t)stream>>>(A);
-    } else {
-        // one persistent CTA per SM, one role per CTA.  Latency regime (every group gets its own warp in every role): equal thirds;
-        // throughput regime: CTAs in proportion to the roles' instruction counts (MAIN 5.5 k, RNEA 3.5 k, CUBE 5 k per group).
+    A.ctl = sim->ctl; A.clist = sim->clist; A.cready = sim->cready; A.list_cap = sim->stride;
+    A.epoch = ++sim->epoch;
+    if (A.epoch == 0) A.epoch = ++sim->epoch;
+    // the list counters grow monotonically (gg_drain.cuh); every launch appends at most n_envs entries: zero them, in stream order,
+    // long before they could reach 2^31
+    sim->list_budget += (int64_t)sim->n;
+    if (sim->list_budget > ((int64_t)1 << 30)) {
+        GG_CUDA(cudaMemsetAsync(sim->ctl, 0, 16 * sizeof(int), (cudaStream_t)stream));
+        sim->list_budget = 0;
+    }
+#ifdef GG_WITH_RS_KERNEL
+    if (!sim->use_blocks) {
+        // experimental (profiles/r02_notes.md): one persistent CTA per SM, one role per CTA
         const int G = sim->n_sm, ngroups = (sim->n + 31) / 32;
-        A.mbox = sim->mbox; A.mflag = sim->mflag; A.ctl = sim->ctl; A.clist = sim->clist; A.cready = sim->cready;
-        A.epoch = ++sim->epoch;
-        if (A.epoch == 0) A.epoch = ++sim->epoch;
+        A.mbox = sim->mbox; A.mflag = sim->mflag;
         if (ngroups <= rs::kWarps * (G / 3)) { A.n_rnea = G / 3; A.n_cube = G / 3; }
         else { A.n_rnea = (int)(G * 0.25f); A.n_cube = (int)(G * 0.36f); }
         A.n_main = G - A.n_rnea - A.n_cube;
@@ -876,6 +1086,21 @@ static int launch_step(GgSim* sim, StepArgs& A, gg_stream_t stream) {
         else
             GG_CUDA(cudaLaunchCooperativeKernel((const void*)rs::step_rs_kernel<5, 1, true>, dim3(G), dim3(rs::kThreads), args,
                                                 rs::kWarps * rs::WarpScratch<5, 1>::bytes, (cudaStream_t)stream));
+        g_launches.fetch_add(1);
+        GG_CUDA(cudaGetLastError());
+        return 0;
+    }
+#endif
+    if (sim->use_mono) {
+        // throughput regime (>= ~7 env-warps per scheduler): thread-per-env kernel, fewest instructions per env
+        const int grid = (sim->n + kMonoThreads - 1) / kMonoThreads;
+        if (sim->kind == 0) step_mono_kernel<7, 2, false><<<grid, kMonoThreads, 0, (cudaStream_t)stream>>>(A);
+        else step_mono_kernel<5, 1, true><<<grid, kMonoThreads, 0, (cudaStream_t)stream>>>(A);
+    } else {
+        // latency regime: 32 envs x 3 role warps per block
+        const int grid = (sim->n + 31) / 32;
+        if (sim->kind == 0) step_kernel<7, 2, false><<<grid, kBlockThreads, 0, (cudaStream_t)stream>>>(A);
+        else step_kernel<5, 1, true><<<grid, kBlockThreads, 0, (cudaStream_t)stream>>>(A);
     }
     g_launches.fetch_add(1);
     GG_CUDA(cudaGetLastError());
@@ -911,37 +1136,47 @@ int gg_create(const GgModel* model, int n_envs, int device, GgSim** out) {
     cudaError_t e2 = cudaMalloc(&s->stats, 8 * sizeof(double));
     const size_t twf = kind == 0 ? sizeof(gg::TeamWork<7, 2>) : sizeof(gg::TeamWork<5, 1>);
     cudaError_t e3 = cudaMalloc(&s->team_scratch, (size_t)s->stride * twf);
-    const size_t ngroups = (size_t)s->stride / 32;
-    const size_t nready = (size_t)s->stride + 4096;       // list slots + the tickets idle warps may over-claim
-    cudaError_t e4 = cudaMalloc(&s->mbox, ngroups * rs::MB_ROWS * 32 * sizeof(float));
-    cudaError_t e5 = cudaMalloc(&s->mflag, ngroups * 4 * sizeof(uint32_t));
+    const size_t nready = (size_t)s->stride + 8192;       // list slots (+ slack for the experimental kernel's over-claimed tickets)
     cudaError_t e6 = cudaMalloc(&s->ctl, 8192 * sizeof(int));
     cudaError_t e7 = cudaMalloc(&s->clist, nready * sizeof(int));
     cudaError_t e8 = cudaMalloc(&s->cready, nready * sizeof(uint32_t));
-    if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess || e4 != cudaSuccess || e5 != cudaSuccess || e6 != cudaSuccess ||
-        e7 != cudaSuccess || e8 != cudaSuccess) {
-        cudaFree(s->done); cudaFree(s->stats); cudaFree(s->team_scratch); cudaFree(s->mbox); cudaFree(s->mflag); cudaFree(s->ctl);
-        cudaFree(s->clist); cudaFree(s->cready); delete s;
+    if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess || e6 != cudaSuccess || e7 != cudaSuccess || e8 != cudaSuccess) {
+        cudaFree(s->done); cudaFree(s->stats); cudaFree(s->team_scratch); cudaFree(s->ctl); cudaFree(s->clist); cudaFree(s->cready); delete s;
         return fail("gg_create: cudaMalloc failed%s");
     }
     cudaMemset(s->done, 0, (size_t)s->stride);
     cudaMemset(s->stats, 0, 8 * sizeof(double));
-    cudaMemset(s->mflag, 0, ngroups * 4 * sizeof(uint32_t));
     cudaMemset(s->ctl, 0, 8192 * sizeof(int));
     cudaMemset(s->cready, 0, nready * sizeof(uint32_t));
-    cudaMemset(s->mbox, 0, ngroups * rs::MB_ROWS * 32 * sizeof(float));
+    s->use_blocks = 1;
+    cudaDeviceGetAttribute(&s->n_sm, cudaDevAttrMultiProcessorCount, device);
     {
-        int coop = 0;
-        cudaDeviceGetAttribute(&s->n_sm, cudaDevAttrMultiProcessorCount, device);
-        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device);
-        // GG_STEP_KERNEL=rs selects the experimental role-per-SM kernel (gg_step_rs.cuh; measured slower, profiles/r02_notes.md)
+        // kernel choice by grid size (GG_STEP_KERNEL=mono / roles overrides it for A/B measurements): the role kernel while the launch
+        // cannot fill the GPU with env-warps, the thread-per-env kernel above kMonoEnvsPerSm envs per SM
         const char* k = getenv("GG_STEP_KERNEL");
-        s->use_blocks = !(k && strcmp(k, "rs") == 0) || !coop || s->n_sm < 3;
-        cudaFuncSetAttribute((const void*)rs::step_rs_kernel<7, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)(rs::kWarps * rs::WarpScratch<7, 2>::bytes));
-        cudaFuncSetAttribute((const void*)rs::step_rs_kernel<5, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)(rs::kWarps * rs::WarpScratch<5, 1>::bytes));
+        s->use_mono = n_envs >= kMonoEnvsPerSm * s->n_sm;
+        if (k && strcmp(k, "mono") == 0) s->use_mono = 1;
+        if (k && strcmp(k, "roles") == 0) s->use_mono = 0;
     }
+#ifdef GG_WITH_RS_KERNEL
+    {
+        const size_t ngroups = (size_t)s->stride / 32;
+        int coop = 0;
+        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device);
+        const char* k = getenv("GG_STEP_KERNEL");
+        if (k && strcmp(k, "rs") == 0 && coop && s->n_sm >= 3 &&
+            cudaMalloc(&s->mbox, ngroups * rs::MB_ROWS * 32 * sizeof(float)) == cudaSuccess &&
+            cudaMalloc(&s->mflag, ngroups * 4 * sizeof(uint32_t)) == cudaSuccess) {
+            cudaMemset(s->mflag, 0, ngroups * 4 * sizeof(uint32_t));
+            cudaMemset(s->mbox, 0, ngroups * rs::MB_ROWS * 32 * sizeof(float));
+            cudaFuncSetAttribute((const void*)rs::step_rs_kernel<7, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)(rs::kWarps * rs::WarpScratch<7, 2>::bytes));
+            cudaFuncSetAttribute((const void*)rs::step_rs_kernel<5, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)(rs::kWarps * rs::WarpScratch<5, 1>::bytes));
+            s->use_blocks = 0;
+        }
+    }
+#endif
     *out = s;
     return 0;
 }

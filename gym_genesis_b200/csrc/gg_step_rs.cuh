@@ -28,6 +28,8 @@
 
 namespace rs {
 
+using cl::Tally; using cl::commit_cube; using cl::drain_one; using cl::ld_relaxed;
+
 #ifndef GG_RS_WARPS
 #define GG_RS_WARPS 11
 #endif
@@ -50,11 +52,6 @@ __device__ __forceinline__ void st_release_f32(float* p, float v) {
 __device__ __forceinline__ void post(uint32_t* f, uint32_t epoch, int lane) {
     __syncwarp();
     if (lane == 0) asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(f), "r"(epoch) : "memory");
-}
-__device__ __forceinline__ uint32_t ld_relaxed(const uint32_t* p) {
-    uint32_t v;
-    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
 }
 __device__ __forceinline__ uint32_t ld_acquire(const uint32_t* p) { return ld_relaxed(p); }   // see above: consumers read through L2 only
 __device__ __forceinline__ void wait(const uint32_t* f, uint32_t epoch, int lane) {
@@ -347,39 +344,6 @@ __device__ __forceinline__ void role_main(const StepArgs& A, int g, int lane, fl
     RS_TRACE(g, 0, 6);
 }
 
-// flags, counters and episode statistics of one env (CUBE role lanes and the lane-0 epilogue of a drained coupled env)
-struct Tally { float v[8]; };      // steps, done, succ, return, length, nan, iterations, contacts
-template <int NU>
-__device__ __forceinline__ void commit_cube(const StepArgs& A, int e, gg::V3 cp, gg::Q4 cq, gg::V3 cv, gg::V3 cw, const float* qac, int steps, int epi,
-                                            bool do_reset, bool active, Tally& T) {
-    const size_t st = (size_t)A.stride;
-    if (A.mode == 0 && !do_reset) { steps += 1; T.v[0] = 1.f; }
-    const bool succ = cp.z > A.M.success_z;
-    const float rew = succ ? 1.f : 0.f;
-    const bool trunc = A.time_limit && steps >= A.M.horizon;
-    if (A.reward) A.reward[e] = rew;
-    if (A.terminated) A.terminated[e] = succ ? 1 : 0;
-    if (A.truncated) A.truncated[e] = trunc ? 1 : 0;
-    if (A.reward_host) A.reward_host[e] = rew;
-    if (A.terminated_host) A.terminated_host[e] = succ ? 1 : 0;
-    if (A.truncated_host) A.truncated_host[e] = trunc ? 1 : 0;
-    if (A.mode != 2) {
-        A.done[e] = (succ || trunc) ? 1 : 0;
-        if (active || do_reset) {
-            float* wp = A.state + e + (2 * NU) * st;
-            wp[0] = cp.x; wp[st] = cp.y; wp[2 * st] = cp.z;
-            wp[3 * st] = cq.w; wp[4 * st] = cq.x; wp[5 * st] = cq.y; wp[6 * st] = cq.z;
-            wp[7 * st] = cv.x; wp[8 * st] = cv.y; wp[9 * st] = cv.z;
-            wp[10 * st] = cw.x; wp[11 * st] = cw.y; wp[12 * st] = cw.z;
-#pragma unroll
-            for (int i = 0; i < 6; i++) wp[(13 + NU + i) * st] = qac[i];
-        }
-        A.step_count[e] = steps; A.episode[e] = epi;
-        if (A.mode == 0 && (succ || trunc)) { T.v[1] = 1.f; T.v[2] = succ ? 1.f : 0.f; T.v[4] = (float)steps; }
-        if (A.mode == 0) T.v[3] = rew;
-    }
-}
-
 // ---------------------------------------------------------------------------------------------------------------- CUBE
 template <int NA, int NF, bool FH>
 __device__ __forceinline__ void role_cube(const StepArgs& A, int g, int lane, float* scratch) {
@@ -495,90 +459,6 @@ __device__ __forceinline__ void role_cube(const StepArgs& A, int g, int lane, fl
     RS_TRACE(g, 2, 6);
 }
 
-// ------------------------------------------------------------------------------------------------- coupled envs: drain
-// One warp = one coupled env: warp-cooperative narrow phase + Newton solve on all NU + 6 dofs (gg_coop.cuh), then the env's
-// integration, observations, flags and counters (every lane computes them redundantly from the broadcast solution, lane 0 stores).
-template <int NA, int NF, bool FH>
-__device__ __forceinline__ void drain_one(const StepArgs& A, int e, int lane, float* scratch) {
-    constexpr int NU = NA + NF, NV = NU + 6, AD = 7 + NF;
-    constexpr int TWF = sizeof(gg::TeamWork<NA, NF>) / sizeof(float);
-    gg::TeamBuf<NV>& TB = *reinterpret_cast<gg::TeamBuf<NV>*>(scratch);
-    float* twp = scratch + sizeof(gg::TeamBuf<NV>) / sizeof(float);
-    gg::TeamWork<NA, NF>& TW = *reinterpret_cast<gg::TeamWork<NA, NF>*>(twp);
-    float* avec = twp + ((sizeof(gg::TeamWork<NA, NF>) + 15) / 16) * 4;      // solution broadcast: NV floats
-    const float* src = A.team_scratch + (size_t)e * TWF;
-#pragma unroll 1
-    for (int i = lane; i < TWF; i += 32) twp[i] = __ldcg(src + i);
-    __syncwarp();
-    int its, nc;
-    gg::team_solve<NA, NF, FH>(A.M, TW, TB, A.iterations, A.tol, lane, avec, 1, its, nc);
-    __syncwarp();
-    const uint32_t gid = (uint32_t)(A.first_env + e);
-    bool do_reset = reset_decision(A, e, gid);
-    int steps = A.step_count[e], epi = A.episode[e];
-    if (do_reset) { epi += 1; steps = 0; }
-    float q[NU], qd[NU], qa[NU], a[NV];
-#pragma unroll
-    for (int i = 0; i < NV; i++) a[i] = avec[i];
-#pragma unroll
-    for (int i = 0; i < NU; i++) { q[i] = TW.q[i]; qd[i] = TW.qd[i]; qa[i] = TW.warm[i]; }
-    gg::V3 cp = gg::mk(TW.cube[0], TW.cube[1], TW.cube[2]);
-    gg::Q4 cq = gg::mkq(TW.cube[3], TW.cube[4], TW.cube[5], TW.cube[6]);
-    gg::V3 cv = gg::mk(TW.cube[7], TW.cube[8], TW.cube[9]), cw = gg::mk(TW.cube[10], TW.cube[11], TW.cube[12]);
-    float qac[6];
-    gg::integrate_robot<NU>(A.M, q, qd, qa, a);            // coupled envs are active by construction (role_rnea)
-    gg::integrate_cube(A.M, cp, cq, cv, cw, qac, a + NU);
-    Tally T;
-#pragma unroll
-    for (int k = 0; k < 8; k++) T.v[k] = 0.f;
-    {
-        float acc = cp.x + cp.y + cp.z + cq.w + cq.x + cq.y + cq.z + cv.x + cv.y + cv.z + cw.x + cw.y + cw.z;
-#pragma unroll
-        for (int i = 0; i < NU; i++) acc += q[i] + qd[i];
-        if (!isfinite(acc)) {                              // diverged env: re-spawn (same rule as the register path)
-            float x, y;
-            gg::spawn_draw(A.M, A.seed, gid, (uint32_t)epi, x, y);
-            cp = gg::mk(x, y, A.M.spawn_z); cq = gg::ldq(A.M.spawn_quat);
-            cv = gg::mk(0.f, 0.f, 0.f); cw = gg::mk(0.f, 0.f, 0.f);
-#pragma unroll
-            for (int i = 0; i < 6; i++) qac[i] = 0.f;
-#pragma unroll
-            for (int i = 0; i < NU; i++) { q[i] = A.M.home_q[i]; qd[i] = 0.f; qa[i] = 0.f; }
-            epi += 1; steps = 0; T.v[5] = 1.f;
-            do_reset = true;
-        }
-    }
-    gg::V3 ep; gg::Q4 eq;
-    gg::robot_eef<NA, NF>(A.M, q, ep, eq);
-    if (lane == 0) {
-        const size_t st = (size_t)A.stride;
-        float oa[AD], oe[GG_ENV_STATE_DIM];
-        oa[0] = ep.x; oa[1] = ep.y; oa[2] = ep.z; oa[3] = eq.w; oa[4] = eq.x; oa[5] = eq.y; oa[6] = eq.z;
-#pragma unroll
-        for (int f = 0; f < NF; f++) oa[7 + f] = q[NA + f];
-        const gg::V3 d = ep - cp;
-        oe[0] = cp.x; oe[1] = cp.y; oe[2] = cp.z; oe[3] = cq.w; oe[4] = cq.x; oe[5] = cq.y; oe[6] = cq.z;
-        oe[7] = d.x; oe[8] = d.y; oe[9] = d.z; oe[10] = sqrtf(gg::dot(d, d));
-#pragma unroll
-        for (int i = 0; i < AD; i++) { A.obs_agent[(size_t)e * AD + i] = oa[i]; if (A.obs_agent_host) A.obs_agent_host[(size_t)e * AD + i] = oa[i]; }
-#pragma unroll
-        for (int i = 0; i < GG_ENV_STATE_DIM; i++) {
-            A.obs_env[(size_t)e * GG_ENV_STATE_DIM + i] = oe[i];
-            if (A.obs_env_host) A.obs_env_host[(size_t)e * GG_ENV_STATE_DIM + i] = oe[i];
-        }
-        float* wp = A.state + e;
-#pragma unroll
-        for (int i = 0; i < NU; i++) { wp[i * st] = q[i]; wp[(NU + i) * st] = qd[i]; wp[(2 * NU + 13 + i) * st] = qa[i]; }
-        T.v[6] = (float)its; T.v[7] = (float)nc;
-        commit_cube<NU>(A, e, cp, cq, cv, cw, qac, steps, epi, do_reset, true, T);
-        if (A.stats != nullptr && A.mode == 0) {
-#pragma unroll
-            for (int k = 0; k < 8; k++) if (T.v[k] != 0.f) atomicAdd(&A.stats[k], (double)T.v[k]);
-        }
-    }
-    __syncwarp();
-}
-
 // Every warp ends here.  A warp always holds ONE ticket (fetch-and-add on the head: never fails, unlike a compare-and-swap loop, which
 // serialised 1600 contending warps) and polls the ready word of ITS slot -- distinct addresses, no hot line.  A ticket beyond the
 // final tail means the list is exhausted: the tail is final once every MAIN CTA has finished its role loop.
@@ -603,7 +483,18 @@ __device__ __forceinline__ void drain(const StepArgs& A, int lane, float* scratc
         }
         e = __shfl_sync(0xffffffffu, e, 0);
         if (e < 0) break;
-        drain_one<NA, NF, FH>(A, e, lane, scratch);
+        {
+            gg::TeamBuf<NA + NF + 6>& TBr = *reinterpret_cast<gg::TeamBuf<NA + NF + 6>*>(scratch);
+            gg::TeamWork<NA, NF>& TWr = *reinterpret_cast<gg::TeamWork<NA, NF>*>(scratch + sizeof(gg::TeamBuf<NA + NF + 6>) / sizeof(float));
+            Tally acc_;
+#pragma unroll
+            for (int k = 0; k < 8; k++) acc_.v[k] = 0.f;
+            drain_one<NA, NF, FH>(A, e, lane, TBr, TWr, acc_);
+            if (lane == 0 && A.stats != nullptr && A.mode == 0) {
+#pragma unroll
+                for (int k = 0; k < 8; k++) if (acc_.v[k] != 0.f) atomicAdd(&A.stats[k], (double)acc_.v[k]);
+            }
+        }
     }
 }
 

@@ -161,3 +161,61 @@ def test_config4_so101_16384_envs_masked_resets(Sim, so101_model, so101_oracle64
     r = _run_fullsize(Sim, so101_model, so101_oracle64, 16384, 10, seed=9, reset_prob=1.0 / 200, auto_reset=True, time_limit=False,
                       amp=0.1, subset=512)
     assert r["resets"] > 10 * 40 and r["checked"] >= 10 * 512
+
+
+# ---- the thread-per-env kernel (launch_step picks it above ~200 envs per SM; GG_STEP_KERNEL=mono forces it at any size) -------------------
+@pytest.fixture
+def mono_kernel(monkeypatch):
+    monkeypatch.setenv("GG_STEP_KERNEL", "mono")
+    yield
+    monkeypatch.delenv("GG_STEP_KERNEL", raising=False)
+
+
+def test_mono_kernel_oracle_parity_with_resets(mono_kernel, Sim, franka_model, oracle64):
+    r = _run_fullsize(Sim, franka_model, oracle64, 4096 + 7, 8, seed=21, reset_prob=1.0 / 100, auto_reset=True, time_limit=True, amp=0.3,
+                      subset=512, host_mask_every=3)
+    assert r["resets"] > 8 * 20 and r["checked"] >= 8 * 512
+
+
+def test_mono_kernel_coupled_envs_through_the_grid_wide_list(mono_kernel, Sim, franka_model, oracle64):
+    """Cube at random poses around the fingers (pads overlapping cube and / or plane): the coupled envs of the thread-per-env kernel go
+    through the grid-wide list and the warp-per-env drain (gg_drain.cuh); same bound as the role kernel's clutter test."""
+    from helpers import pick_clutter_states
+    n = 1024
+    sim = Sim(franka_model, n)
+    Q, QD, T = pick_clutter_states(franka_model, sim.gg_model, np.random.default_rng(57), n)
+    QA = np.zeros_like(QD)
+    sim.set_state(Q, QD, QA)
+    sim.step(torch.as_tensor(f32(T)))
+    q, qd, _ = (_np(t).astype(np.float64) for t in sim.get_state())
+    qo, qdo, qao = Q.copy(), QD.copy(), QA.copy()
+    info, _ = oracle64.step(qo, qdo, qao, T, iterations=300, tol=1e-12)
+    assert (info[:, 0] > 4).sum() > 200
+    scale = np.array([np.abs(oracle64.dynamics(Q[k], QD[k], T[k])["a_smooth"]).max() * 0.01 for k in range(n)])
+    eq, ev = substep_errors(Q, QD, qo, qdo, q, qd, scale)
+    assert eq.max() < TOL_Q_ABS and ev.max() < 1.0, (eq.max(), ev.max(), int(np.argmax(ev)))
+    a, e, r, t = oracle64.obs(q)
+    assert np.abs(_np(sim.obs_agent) - a).max() < 2e-6 and np.abs(_np(sim.obs_env) - e).max() < 2e-6
+    assert np.array_equal(_np(sim.terminated).astype(bool), t)
+    st = _np(sim.stats())
+    assert st[0] == n and st[5] == 0 and st[7] / st[0] > 4          # every env stepped exactly once; contact-rich on average
+    sim.close()
+
+
+def test_kernel_dispatch_by_env_count(Sim, franka_model):
+    """131072 envs on one GPU take the thread-per-env kernel automatically; the result obeys the same invariants."""
+    n = 131072
+    sim = Sim(franka_model, n, seed=3, reset_prob=1.0 / 200, auto_reset=True)
+    sim.reset(None, None)
+    g = torch.Generator(device="cuda").manual_seed(0)
+    home = torch.as_tensor(franka_model.home_q, dtype=torch.float32, device="cuda")
+    for k in range(10):
+        act = home + 0.6 * (torch.rand((n, 9), generator=g, device="cuda") - 0.5)
+        act[:, 7:] = -0.02 + 0.06 * torch.rand((n, 2), generator=g, device="cuda")
+        sim.step(act)
+    q, qd, _ = sim.get_state()
+    assert torch.isfinite(q).all() and torch.isfinite(qd).all()
+    assert (q[:, 12:16].norm(dim=1) - 1).abs().max() < 1e-5 and q[:, 11].min() > 0.0195 and q[:, 11].max() < 0.021
+    st = _np(sim.stats())
+    assert st[5] == 0 and st[0] > 0.98 * n * 10 * (1 - 1 / 200.0)
+    sim.close()

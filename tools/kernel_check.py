@@ -1,4 +1,4 @@
-"""Developer check: the role-per-SM step kernel against the round-1 block kernel on the same inputs (state bit-identical expected for the
+"""Developer check: the thread-per-env (mono) step kernel against the role kernel on the same inputs (state bit-identical expected for the
 register path; observations differ by the rounding of the unsplit end-effector chain)."""
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -9,7 +9,7 @@ from gym_genesis_b200.sim import BatchedSim
 m = franka_cube_pick_model()
 for n in (64, 1000, 16384):
     sims = []
-    for kern in ("blocks", "rs"):
+    for kern in ("roles", "mono"):
         os.environ["GG_STEP_KERNEL"] = kern
         s = BatchedSim(m, n, seed=5, auto_reset=True, reset_prob=0.02, time_limit=True)
         s.reset(None, None)
