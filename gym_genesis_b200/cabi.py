@@ -42,6 +42,7 @@ class GgModel(C.Structure):
         ("tc", _f), ("dr", _f), ("dmin", _f), ("dmax", _f), ("width", _f), ("mid", _f), ("power", _f), ("minval", _f),
         ("home_q", _f * GG_MAX_DOF),
         ("spawn_lo", _f * 2), ("spawn_hi", _f * 2), ("spawn_z", _f), ("spawn_quat", _f * 4), ("success_z", _f),
+        ("reg_scale", _f), ("reserved1", _f * 3),
     ]
 
 
@@ -65,7 +66,7 @@ class GgHostIO(C.Structure):
 
 class GgIkConfig(C.Structure):
     _fields_ = [("max_iters", _i), ("damping", _f), ("pos_tol", _f), ("rot_tol", _f), ("max_step", _f), ("respect_limits", _i),
-                ("pos_mask", _f * 3), ("rot_mask", _f * 3)]
+                ("pos_mask", _f * 3), ("rot_mask", _f * 3), ("max_samples", _i), ("seed_lo", C.c_uint32), ("seed_hi", C.c_uint32)]
 
 
 def _set(arr, values):
@@ -208,6 +209,7 @@ def compile_gg(sm: "mdl.SceneModel") -> GgModel:
     _set(g.home_q, sm.home_q)
     _set(g.spawn_lo, sm.spawn_lo); _set(g.spawn_hi, sm.spawn_hi); g.spawn_z = sm.spawn_z
     _set(g.spawn_quat, sm.spawn_quat); g.success_z = sm.success_z
+    g.reg_scale = sm.reg_scale()
     return g
 
 

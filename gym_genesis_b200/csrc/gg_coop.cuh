@@ -262,7 +262,7 @@ __device__ __noinline__ void team_solve(const GgModel& M, const TeamWork<NA, NF>
             float imp = 1.f, ar[4];
 #pragma unroll
             for (int k = 0; k < 4; k++) imp_aref(M, -B.depth[c], rowval(vel, mu, k), imp, ar[k]);
-            Dk[s] = gg_rcp(fmaxf(M.minval, 2.f * mu * mu * (1.f - imp) / imp * wsum * (1.f + mu * mu)));
+            Dk[s] = gg_rcp(fmaxf(M.minval, M.reg_scale * (1.f - imp) / imp * wsum));
 #pragma unroll
             for (int k = 0; k < 4; k++) {
                 const float jw = rowval(uw, mu, k) - ar[k], js = rowval(us, mu, k) - ar[k];

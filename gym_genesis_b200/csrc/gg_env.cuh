@@ -713,7 +713,7 @@ GG_HD void solve_cube_plane(const GgModel& M, const float* Mc, const float* as, 
         float imp = 1.f, ar[4];
 #pragma unroll
         for (int k = 0; k < 4; k++) imp_aref(M, -depth[c], rowval(vel, mu, k), imp, ar[k]);
-        const float Dk = live ? gg_rcp(fmaxf(M.minval, 2.f * mu * mu * (1.f - imp) / imp * M.cube_invweight * (1.f + mu * mu))) : 0.f;
+        const float Dk = live ? gg_rcp(fmaxf(M.minval, M.reg_scale * (1.f - imp) / imp * M.cube_invweight)) : 0.f;
 #pragma unroll
         for (int k = 0; k < 4; k++) {
             float jw = rowval(uw, mu, k) - ar[k], js = rowval(us, mu, k) - ar[k];
@@ -935,7 +935,7 @@ GG_HD void solve_coupled(const GgModel& M, const RobotDyn<NA, NF>& D, const EnvS
         float imp = 1.f, ar[4];
 #pragma unroll
         for (int k = 0; k < 4; k++) imp_aref(M, -C.depth[c], rowval(vel, mu, k), imp, ar[k]);
-        const float Dk = gg_rcp(fmaxf(M.minval, 2.f * mu * mu * (1.f - imp) / imp * wsum * (1.f + mu * mu)));
+        const float Dk = gg_rcp(fmaxf(M.minval, M.reg_scale * (1.f - imp) / imp * wsum));
         R.D[c] = Dk;
 #pragma unroll
         for (int k = 0; k < 4; k++) {

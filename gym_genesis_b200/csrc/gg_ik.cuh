@@ -5,9 +5,11 @@
 // Algorithm (Genesis `RigidEntity.inverse_kinematics`, restated from its published behaviour, [UPSTREAM-RECALL]):
 // damped least squares on the 6-dim pose error e = [target_pos - pos ; rotvec(target_quat * conj(quat))]
 //     dq = J^T (J J^T + damping^2 I)^-1 e,   |dq_i| clamped to max_step_size,   q clipped to the joint limits,
-// repeated until |e_pos| < pos_tol and |e_rot| < rot_tol or max_solver_iters updates have been applied.  Only the first
-// sample (init_qpos = current joint positions) is run: Genesis' random re-sampling on failure (max_samples) draws from a
-// host RNG stream and is not restated (GENESIS_COMPAT_IK_RESAMPLE in gym_genesis_b200/model.py).
+// repeated until |e_pos| < pos_tol and |e_rot| < rot_tol or max_solver_iters updates have been applied.  Rows that are still
+// unsolved are re-started from random arm configurations (Genesis' max_samples; its draws come from a host RNG stream, ours from
+// the device Philox stream -- same distribution, uniform inside the joint limits): ik_sample_init below.  The samples of a row are
+// independent, so the CUDA path runs them as the 32 LANES of one warp per unsolved row (ik_resample_kernel) and keeps the first
+// success in sample order -- what a sequential loop over the samples returns.
 //
 // Formulation used here: with the motion subspaces S_i = (k_i, o_i x k_i) about the WORLD ORIGIN (the same vectors the
 // dynamics pass uses), the Jacobian at the end-effector point p is J = X(p) S with a fixed 6x6 shift X, so
@@ -37,6 +39,24 @@ GG_HD V3 quat_rotvec(Q4 q) {
     if (s > 1e-9f) k = sg * 2.f * atan2f(s, fabsf(q.w)) / s;
     return v * k;
 }
+
+// start configuration of re-sampling attempt s >= 1 of row `row`: arm joints uniform inside their limits (float32 arithmetic)
+template <int NA>
+GG_HD void ik_sample_init(const GgModel& M, uint32_t seed_lo, uint32_t seed_hi, uint32_t row, uint32_t s, float* q) {
+#pragma unroll
+    for (int blk = 0; blk < (NA + 3) / 4; blk++) {
+        uint32_t o[4];
+        philox4x32_10(row, s, 0x494B5253u, (uint32_t)blk, seed_lo, seed_hi, o);
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int i = blk * 4 + k;
+            if (i < NA) q[i] = fmaf(u01(o[k]), M.lim_hi[i] - M.lim_lo[i], M.lim_lo[i]);
+        }
+    }
+}
+
+// ranking of attempts that miss the tolerances: the larger of the two tolerance-relative errors
+GG_HD float ik_score(const GgIkConfig& K, float perr, float rerr) { return fmaxf(perr / K.pos_tol, rerr / K.rot_tol); }
 
 // one env; q[0 .. NA) is updated in place (gripper coordinates do not move the end-effector link and stay untouched).
 // Returns the number of DLS updates applied; perr / rerr are the error norms of the returned configuration.

@@ -940,6 +940,67 @@ __global__ void __launch_bounds__(64) ik_kernel(const __grid_constant__ IkArgs A
     if (A.iters_out) A.iters_out[r] = it;
 }
 
+// Re-sampling pass (GgIkConfig::max_samples > 1): ONE WARP per row.  A warp whose row was solved by ik_kernel leaves at once; otherwise
+// its 32 lanes run attempts s = 1 + lane, 33 + lane, ... in lock step (independent random starts, ik_sample_init) and the warp keeps
+// the successful attempt with the LOWEST sample index -- the one a sequential loop over the samples would have returned -- or, when
+// no attempt meets the tolerances, the best-ranked one (attempt 0 included).  Rows that cannot be reached (3 % of the hover targets of the
+// reference expert) cost 2 rounds x max_iters updates in ONE warp instead of holding 31 solved rows of their ik_kernel warp hostage.
+template <int NA, int NF>
+__global__ void __launch_bounds__(128) ik_resample_kernel(const __grid_constant__ IkArgs A) {
+    constexpr int NU = NA + NF;
+    const int lane = threadIdx.x & 31;
+    const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (r >= A.n_rows) return;
+    float p0 = A.err_out[2 * r], r0 = A.err_out[2 * r + 1];
+    if (p0 < A.K.pos_tol && r0 < A.K.rot_tol) return;                       // warp-uniform
+    gg::V3 tp = gg::mk(0.f, 0.f, 0.f);
+    gg::Q4 tq = gg::mkq(1.f, 0.f, 0.f, 0.f);
+    if (A.tpos) tp = gg::ld3(A.tpos + (size_t)r * 3);
+    if (A.tquat) tq = gg::ldq(A.tquat + (size_t)r * 4);
+    float qbest[NU];
+#pragma unroll
+    for (int i = 0; i < NU; i++) qbest[i] = A.q_out[(size_t)r * NU + i];    // attempt 0 (fingers are never touched)
+    float best = gg::ik_score(A.K, p0, r0), bp = p0, br = r0;
+    int extra = 0;
+    bool solved = false;
+    for (int base = 1; base < A.K.max_samples && !solved; base += 32) {
+        const int s = base + lane;
+        const bool mine = s < A.K.max_samples;
+        float q[NU];
+#pragma unroll
+        for (int i = 0; i < NU; i++) q[i] = qbest[i];
+        if (mine) gg::ik_sample_init<NA>(A.M, A.K.seed_lo, A.K.seed_hi, (uint32_t)r, (uint32_t)s, q);
+        float pe, re;
+        const int it = gg::env_ik<NA>(A.M, A.K, q, tp, tq, pe, re);         // lanes beyond max_samples re-run the best start (harmless)
+        extra += it;
+        const bool ok = mine && pe < A.K.pos_tol && re < A.K.rot_tol;
+        const unsigned okm = __ballot_sync(0xffffffffu, ok);
+        int src;
+        if (okm != 0u) { src = __ffs(okm) - 1; solved = true; }
+        else {
+            // no success in this round: lane with the smallest score (ties: lowest sample index), if it beats the best so far
+            float sc = mine ? gg::ik_score(A.K, pe, re) : 3.0e38f;
+            float m = sc;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) m = fminf(m, __shfl_xor_sync(0xffffffffu, m, o));
+            const unsigned mm = __ballot_sync(0xffffffffu, sc == m);
+            src = m < best ? __ffs(mm) - 1 : -1;
+        }
+        if (src >= 0) {
+#pragma unroll
+            for (int i = 0; i < NA; i++) qbest[i] = __shfl_sync(0xffffffffu, q[i], src);
+            bp = __shfl_sync(0xffffffffu, pe, src); br = __shfl_sync(0xffffffffu, re, src);
+            best = gg::ik_score(A.K, bp, br);
+        }
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < NA; i++) A.q_out[(size_t)r * NU + i] = qbest[i];
+        A.err_out[2 * r] = bp; A.err_out[2 * r + 1] = br;
+        if (A.iters_out) A.iters_out[r] += extra;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Trajectory store.  Pure data movement, HBM bound:
 //   record_kernel : frame t <- [agent_pos | environment_state | action | reward]; one thread per float, 4 B read + 4 B written,
@@ -1290,6 +1351,7 @@ void gg_ik_defaults(GgIkConfig* cfg) {
     if (!cfg) return;
     cfg->max_iters = 20; cfg->damping = 0.01f; cfg->pos_tol = 5e-4f; cfg->rot_tol = 5e-3f; cfg->max_step = 0.5f;
     cfg->respect_limits = 1;
+    cfg->max_samples = 1; cfg->seed_lo = 0u; cfg->seed_hi = 0u;
     for (int i = 0; i < 3; i++) { cfg->pos_mask[i] = 1.f; cfg->rot_mask[i] = 1.f; }
 }
 
@@ -1306,6 +1368,8 @@ int gg_ik(GgSim* sim, int n_rows, const int32_t* envs_idx, const float* target_p
     if (cfg) A.K = *cfg; else gg_ik_defaults(&A.K);
     if (A.K.max_iters < 0 || A.K.max_iters > 10000) return fail("gg_ik: max_iters out of range%s");
     if (!(A.K.damping > 0.f)) return fail("gg_ik: damping must be positive%s");
+    if (A.K.max_samples < 1) A.K.max_samples = 1;
+    if (A.K.max_samples > 1 && !err_out) return fail("gg_ik: max_samples > 1 needs err_out (the re-sampling pass reads the first pass' errors)%s");
     if (!target_pos) A.K.pos_mask[0] = A.K.pos_mask[1] = A.K.pos_mask[2] = 0.f;
     if (!target_quat) A.K.rot_mask[0] = A.K.rot_mask[1] = A.K.rot_mask[2] = 0.f;
     A.n_rows = n_rows; A.stride = sim->stride; A.state = sim->state; A.envs_idx = envs_idx;
@@ -1315,6 +1379,12 @@ int gg_ik(GgSim* sim, int n_rows, const int32_t* envs_idx, const float* target_p
     if (sim->kind == 0) ik_kernel<7, 2><<<grid, 64, 0, (cudaStream_t)stream>>>(A);
     else ik_kernel<5, 1><<<grid, 64, 0, (cudaStream_t)stream>>>(A);
     g_launches.fetch_add(1);
+    if (A.K.max_samples > 1) {
+        const int g2 = (n_rows + 3) / 4;                    // one warp per row, four rows per block
+        if (sim->kind == 0) ik_resample_kernel<7, 2><<<g2, 128, 0, (cudaStream_t)stream>>>(A);
+        else ik_resample_kernel<5, 1><<<g2, 128, 0, (cudaStream_t)stream>>>(A);
+        g_launches.fetch_add(1);
+    }
     GG_CUDA(cudaGetLastError());
     return 0;
 }

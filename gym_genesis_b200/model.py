@@ -41,6 +41,12 @@ GENESIS_COMPAT_MINVAL = 1e-15            # MuJoCo mjMINVAL floor for the regular
 GENESIS_COMPAT_IMPLICIT_KV = True        # approximate_implicitfast: Mt = M + arm + dt*(damping+kv)
 GENESIS_COMPAT_FREE_ANG_BODYFRAME = True  # free-joint angular dofs in body frame, quat (x)= exp(w dt)
 GENESIS_COMPAT_SELF_COLLISION = False    # pad-pad / pad-link pairs skipped (same entity)
+GENESIS_COMPAT_PYRAMID_MU_SCALING = True  # regulariser of a pyramidal contact row R = 2 mu^2 (1 + mu^2) (1-imp)/imp (w_a + w_b) (MuJoCo-lineage);
+                                          # False: R = (1-imp)/imp (w_a + w_b).  Open risk: with the SO-101 task's friction 5 the
+                                          # scaled form makes the contact 1300x softer than the unscaled one and the resting cube sinks 16 mm
+GENESIS_COMPAT_PANDA_WRIST_FORCE = 87.0   # actuator force range of Panda joints 5-7 when the task never calls set_dofs_force_range (CubePick,
+                                          # franka/cube_pick.py:86-112): 87 = what the stacking tasks set explicitly (franka/cube_stack.py:158-161);
+                                          # the public panda.xml clamps joints 5-7 at +-12 N m (SURVEY.md App. B risk U1) -> pass wrist_force=12
 GENESIS_COMPAT_MAX_PLANE_CONTACTS = 4    # mjc_PlaneBox keeps the first 4 penetrating corners
 GENESIS_COMPAT_MAX_BOXBOX_CONTACTS = 8
 GENESIS_COMPAT_MAX_CONTACTS = 64         # per-env cap (Genesis: max_collision_pairs), deterministic order
@@ -51,8 +57,8 @@ GENESIS_COMPAT_IK_DAMPING = 0.01         # dq = J^T (J J^T + damping^2 I)^-1 e
 GENESIS_COMPAT_IK_POS_TOL = 5e-4         # m
 GENESIS_COMPAT_IK_ROT_TOL = 5e-3         # rad
 GENESIS_COMPAT_IK_MAX_STEP = 0.5         # max_step_size per dof and update
-GENESIS_COMPAT_IK_RESAMPLE = False       # Genesis retries from random qpos (max_samples=50, host RNG) when the first
-                                         # sample fails; not restated -- only the first sample (init = current qpos) runs
+GENESIS_COMPAT_IK_MAX_SAMPLES = 50       # Genesis retries unsolved rows from random qpos (max_samples, host RNG stream); restated with the
+                                         # device Philox stream (same distribution: uniform inside the joint limits), gg_ik.cuh
 
 
 # ----------------------------------------------------------------------------------------------
@@ -182,6 +188,12 @@ class SceneModel:
     stack_min_dist: float = 0.0      # so101/cube_stack_batch.py:70 (0.06): cube_1 / cube_2 re-drawn until this far apart
     agent_mode: str = "eef"          # "eef": eef pose + gripper dofs; "qpos": joint positions (so101/cube_stack_batch.py:176)
     max_contacts: int = GENESIS_COMPAT_MAX_CONTACTS
+    pyramid_mu_scaling: bool = GENESIS_COMPAT_PYRAMID_MU_SCALING
+
+    def reg_scale(self) -> float:
+        """Factor of the pyramidal-row regulariser (see GENESIS_COMPAT_PYRAMID_MU_SCALING)."""
+        mu = float(np.float32(self.friction))
+        return float(np.float32(2.0 * mu * mu * (1.0 + mu * mu))) if self.pyramid_mu_scaling else 1.0
 
     # ---- derived sizes -----------------------------------------------------------------------
     def __post_init__(self):
@@ -359,7 +371,7 @@ class SceneModel:
                      GENESIS_COMPAT_TIMECONST, GENESIS_COMPAT_DAMPRATIO, GENESIS_COMPAT_DMIN,
                      GENESIS_COMPAT_DMAX, GENESIS_COMPAT_WIDTH, GENESIS_COMPAT_MID, GENESIS_COMPAT_POWER,
                      GENESIS_COMPAT_MINVAL, self.success_z, self.spawn_lo[0], self.spawn_hi[0],
-                     self.spawn_lo[1], self.spawn_hi[1], self.spawn_z]),
+                     self.spawn_lo[1], self.spawn_hi[1], self.spawn_z, self.reg_scale()]),
             spawn_quat=f32(self.spawn_quat), home_q=f32(self.home_q),
             max_contacts=self.max_contacts,
         )
@@ -410,7 +422,7 @@ def _cube_body(size=CUBE_SIZE, density=GENESIS_COMPAT_RIGID_DENSITY):
     return Body("cube", -1, (0.65, 0.0, size / 2), (1, 0, 0, 0), jtype=FREE, mass=m, inertia=(i, i, i, 0, 0, 0))
 
 
-def franka_bodies(scale: float = 1.0, base_pos=(0.0, 0.0, 0.0)):
+def franka_bodies(scale: float = 1.0, base_pos=(0.0, 0.0, 0.0), wrist_force: float = 87.0):
     """Panda body table (link0 .. link7, hand, two fingers) and its pad geoms.  `scale` is the MJCF morph scale of the kitchen
     scenes (`tasks/utils.py:369-376`: scale 0.6 at (-0.5, 0, 0.7)): lengths x s, masses x s^3, inertias x s^5; joint ranges, armature,
     damping and the task's explicit gains are kept ([UPSTREAM-RECALL]: Genesis scales geometry and inertial data of a morph)."""
@@ -421,7 +433,8 @@ def franka_bodies(scale: float = 1.0, base_pos=(0.0, 0.0, 0.0)):
     for j, (name, parent, pos, quat, rng, mass, com, inertia) in enumerate(_PANDA_LINKS):
         bodies.append(Body(name, parent, sc(pos), quat, jtype=HINGE, axis=(0, 0, 1), range=rng, limited=True,
                            armature=0.1, damping=1.0, kp=_PANDA_KP[j], kv=_PANDA_KV[j],
-                           frc=(-_PANDA_FRC[j], _PANDA_FRC[j]), mass=mass * s ** 3, com=sc(com), inertia=tuple(i * s ** 5 for i in inertia)))
+                           frc=((-wrist_force, wrist_force) if j >= 4 else (-_PANDA_FRC[j], _PANDA_FRC[j])), mass=mass * s ** 3, com=sc(com),
+                           inertia=tuple(i * s ** 5 for i in inertia)))
     bodies.append(Body("hand", 7, sc((0, 0, 0.107)), (0.9238795, 0, 0, -0.3826834), mass=0.73 * s ** 3, com=sc((-0.01, 0, 0.03)),
                        inertia=tuple(i * s ** 5 for i in (0.001, 0.0025, 0.0017, 0, 0, 0))))
     for f, (name, quat) in enumerate((("left_finger", (1, 0, 0, 0)), ("right_finger", (0, 0, 0, 1)))):
@@ -436,12 +449,15 @@ def franka_bodies(scale: float = 1.0, base_pos=(0.0, 0.0, 0.0)):
     return bodies, geoms
 
 
-def franka_cube_pick_model() -> SceneModel:
-    """Plane + Panda (9 dofs) + free 4 cm cube: the scene of `franka/cube_pick.py:50-54`."""
-    bodies, geoms = franka_bodies()
+def franka_cube_pick_model(wrist_force: float = None, pyramid_mu_scaling: bool = None) -> SceneModel:
+    """Plane + Panda (9 dofs) + free 4 cm cube: the scene of `franka/cube_pick.py:50-54`.
+    wrist_force / pyramid_mu_scaling: the two switchable Genesis-compatibility risks (GENESIS_COMPAT_PANDA_WRIST_FORCE,
+    GENESIS_COMPAT_PYRAMID_MU_SCALING; None = the module constants)."""
+    bodies, geoms = franka_bodies(wrist_force=GENESIS_COMPAT_PANDA_WRIST_FORCE if wrist_force is None else float(wrist_force))
     bodies.append(_cube_body())
     geoms.append(BoxGeom(11, (CUBE_SIZE / 2,) * 3, group=1))
-    return SceneModel("franka", bodies, geoms, eef_body=8, cube_body=11, home_q=FRANKA_HOME.copy(), n_arm=7, n_fing=2)
+    return SceneModel("franka", bodies, geoms, eef_body=8, cube_body=11, home_q=FRANKA_HOME.copy(), n_arm=7, n_fing=2,
+                      pyramid_mu_scaling=GENESIS_COMPAT_PYRAMID_MU_SCALING if pyramid_mu_scaling is None else bool(pyramid_mu_scaling))
 
 
 # cube_1 (picked), cube_2 (target), three distractors: body positions of franka/cube_stack.py:54-77 (the distractors'

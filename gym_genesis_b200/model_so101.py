@@ -72,7 +72,7 @@ def so101_bodies(scale=1.0, base_pos=(0.0, 0.0, 0.0), base_yaw_deg=0.0, friction
     return bodies
 
 
-def so101_cube_pick_model(placement="stack", success_height=None) -> SceneModel:
+def so101_cube_pick_model(placement="stack", success_height=None, pyramid_mu_scaling=None) -> SceneModel:
     if placement == "stack":
         scale, base_pos, yaw, home = 1.3, (-0.5, 0.0, 0.7), 90.0, SO101_STACK_HOME.copy()
     elif placement == "pick_literal":
@@ -92,6 +92,8 @@ def so101_cube_pick_model(placement="stack", success_height=None) -> SceneModel:
                     spawn_z=ISLAND_TOP_Z + 0.02 + 0.001, spawn_quat=(1.0, 0.0, 0.0, 0.0),  # so101/cube_pick.py:66,68
                     success_z=0.1 if success_height is None else float(success_height),    # so101/cube_pick.py:112 (literal; see D11)
                     settle_steps=0)                                                        # so101/cube_pick.py:81 (commented out)
+    if pyramid_mu_scaling is not None:                     # GENESIS_COMPAT_PYRAMID_MU_SCALING override (model.py)
+        sm.pyramid_mu_scaling = bool(pyramid_mu_scaling)
     return sm
 
 

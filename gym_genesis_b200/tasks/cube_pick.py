@@ -66,7 +66,8 @@ class _Robot:
                            rot_mask=(True, True, True), max_step_size=0.5, dofs_idx_local=None, return_error=False, envs_idx=None):
         """Genesis' `robot.inverse_kinematics(link=eef, pos=, quat=, envs_idx=)` as the reference experts call it
         (examples/franka/pick_cube_state.py:46-51): batched damped least squares on the GPU, returns qpos (B, n_dof).
-        Only the end-effector link is supported; `max_samples` is accepted and ignored (first sample only, see gg_ik.cuh)."""
+        Only the end-effector link is supported.  `max_samples` (Genesis default 50): rows that miss the tolerances are re-started from
+        random arm configurations drawn by the device Philox stream; the first success in sample order is returned (gg_ik.cuh)."""
         if link is not None and link is not self._task.eef:
             raise NotImplementedError("inverse_kinematics: only the end-effector link (get_link('hand')) is supported")
         if dofs_idx_local is not None:
@@ -74,7 +75,8 @@ class _Robot:
         return self._task.sim.inverse_kinematics(pos=pos, quat=quat, init_qpos=init_qpos, envs_idx=envs_idx,
                                                  respect_joint_limit=respect_joint_limit, max_solver_iters=max_solver_iters,
                                                  damping=damping, pos_tol=pos_tol, rot_tol=rot_tol, pos_mask=pos_mask,
-                                                 rot_mask=rot_mask, max_step_size=max_step_size, return_error=return_error)
+                                                 rot_mask=rot_mask, max_step_size=max_step_size, return_error=return_error,
+                                                 max_samples=max_samples)
 
     def control_dofs_position(self, position, dofs_idx_local=None):
         idx = slice(None) if dofs_idx_local is None else torch.as_tensor(np.asarray(dofs_idx_local), device=self._task.sim.device)

@@ -78,6 +78,9 @@ typedef struct GgModel {
     float tc, dr, dmin, dmax, width, mid, power, minval;   /* solref / solimp */
     float home_q[GG_MAX_DOF];
     float spawn_lo[2], spawn_hi[2], spawn_z, spawn_quat[4], success_z;
+    float reg_scale;   /* regulariser of a pyramidal contact row: R = reg_scale (1 - imp) / imp (w_a + w_b); the MuJoCo-lineage value is
+                          2 mu^2 (1 + mu^2) (GENESIS_COMPAT_PYRAMID_MU_SCALING on), 1 switches the friction scaling off */
+    float reserved1[3];
 } GgModel;
 
 /* Run-time options; defaults (all zero except iterations/tolerance) reproduce the reference. */
@@ -155,7 +158,7 @@ int gg_observe(GgSim* sim, float* obs_agent, float* obs_env, float* reward, uint
 int gg_stats(GgSim* sim, double* out8, int clear, gg_stream_t stream);
 
 /* Batched inverse kinematics of the observed end-effector link (damped least squares, Genesis'
- * `RigidEntity.inverse_kinematics` defaults below; first sample only, see csrc/gg_ik.cuh).
+ * `RigidEntity.inverse_kinematics` defaults below; random re-sampling of unsolved rows when max_samples > 1, see csrc/gg_ik.cuh).
  * Zero-initialise and call gg_ik_defaults() to get: max_iters 20, damping 0.01, pos_tol 5e-4, rot_tol 5e-3,
  * max_step 0.5, respect_limits 1, masks all 1. */
 typedef struct GgIkConfig {
@@ -165,6 +168,12 @@ typedef struct GgIkConfig {
     float max_step;           /* max_step_size: per-dof clamp of one update (rad)                        */
     int32_t respect_limits;   /* respect_joint_limit: clip to [lim_lo, lim_hi] after every update        */
     float pos_mask[3], rot_mask[3]; /* pos_mask / rot_mask: 1 = constrain this world axis, 0 = free      */
+    int32_t max_samples;      /* max_samples: total attempts per row.  Attempt 0 starts from init_q / the current joints; attempt s >= 1
+                                 of a row that is still unsolved starts from arm joints drawn uniformly inside the joint limits by the
+                                 device Philox stream (key = seed, counter = (row, s, 'IKRS', dof / 4)).  The result is the FIRST attempt
+                                 that meets the tolerances, else the attempt with the smallest max(|e_pos| / pos_tol, |e_rot| / rot_tol).
+                                 gg_ik_defaults: 1 (Genesis' default is 50)                                  */
+    uint32_t seed_lo, seed_hi;
 } GgIkConfig;
 void gg_ik_defaults(GgIkConfig* cfg);
 

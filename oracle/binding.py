@@ -166,7 +166,7 @@ class Oracle:
         self._fn("reset")(self.h, C.c_int(n), _p(q), _p(qd), _p(qacc), _p(m) if m is not None else None, _p(xy))
 
     def ik(self, q_init, target_pos=None, target_quat=None, max_iters=20, damping=0.01, pos_tol=5e-4, rot_tol=5e-3,
-           max_step=0.5, respect_limits=True, mask6=None):
+           max_step=0.5, respect_limits=True, mask6=None, max_samples=1, seed=0):
         """Batched damped-least-squares IK of the eef body (restates robot.inverse_kinematics, reference
         examples/franka/pick_cube_state.py:46-51).  q_init (n, nu) -> (q (n, nu), err (n, 2), iters (n))."""
         q_init = self._a(q_init)
@@ -179,7 +179,8 @@ class Oracle:
         iters = np.zeros(n, np.int32)
         self._fn("ik")(self.h, C.c_int(n), _p(q_init), _p(tp) if tp is not None else None, _p(tq) if tq is not None else None,
                        C.c_int(max_iters), C.c_double(damping), C.c_double(pos_tol), C.c_double(rot_tol), C.c_double(max_step),
-                       C.c_int(int(respect_limits)), _p(mk), _p(q_out), _p(err), _p(iters))
+                       C.c_int(int(respect_limits)), _p(mk), _p(q_out), _p(err), _p(iters), C.c_int(int(max_samples)),
+                       C.c_uint64(int(seed) & (2 ** 64 - 1)), C.c_int(self.model.n_arm))
         return q_out, err, iters
 
     def new_state(self, n):
@@ -210,3 +211,68 @@ def philox(ctr, key):
 
 def num_threads():
     return int(lib().orc_num_threads())
+
+
+# ---- timing builds (bench.py cpu_baseline / --impl reference legs only) ------------------------------------------------------------
+_fast_built = False
+
+
+def build_fast() -> None:
+    """(Re)compile the -O3 -march=native timing libraries ON THIS MACHINE (the in-tree copies may come from another CPU)."""
+    global _fast_built
+    if not _fast_built:
+        subprocess.check_call(["make", "-C", _HERE, "-s", "-B", "liboracle_fast.so", "libhostport.so"])
+        _fast_built = True
+
+
+class FastOracle(Oracle):
+    """The generic oracle built with -O3 -march=native (same source; contraction allowed): timing only, never the checker."""
+
+    def _fn(self, name):
+        if not hasattr(FastOracle, "_flib"):
+            build_fast()
+            FastOracle._flib = C.CDLL(os.path.join(_HERE, "liboracle_fast.so"))
+            FastOracle._flib.orc_create.restype = C.c_void_p
+            FastOracle._flib.orc_create.argtypes = [C.POINTER(_OrcModel)]
+        return getattr(FastOracle._flib, f"orc_{name}_{self.suf}")
+
+
+class HostPort:
+    """The specialised per-env pipeline (gym_genesis_b200/csrc/gg_env.cuh compiled for the host, oracle/hostport.cpp) on host threads:
+    one call = one workload step (masked reset + substep + observation + flags) of n envs, float32, the GPU's solver settings."""
+
+    def __init__(self, scene_model):
+        from gym_genesis_b200 import cabi
+        build_fast()
+        self.lib = C.CDLL(os.path.join(_HERE, "libhostport.so"))
+        self.gg = cabi.compile_gg(scene_model)
+        assert self.lib.hp_sizeof_model() == C.sizeof(self.gg)
+        self.nu = scene_model.nu
+        self.agent_dim = 7 + scene_model.n_fing
+
+    def new_state(self, n):
+        return (np.zeros((n, self.nu + 7), np.float32), np.zeros((n, self.nu + 6), np.float32), np.zeros((n, self.nu + 6), np.float32))
+
+    def step(self, q, qd, qacc, target, reset_mask=None, xy=None, iterations=10, tol=1e-5, nthreads=1):
+        n = q.shape[0]
+        if not hasattr(self, "_out") or self._out[0].shape[0] != n:
+            self._out = (np.zeros((n, self.agent_dim), np.float32), np.zeros((n, 11), np.float32), np.zeros(n, np.float32), np.zeros(n, np.uint8))
+        a, e, r, t = self._out
+        target = np.ascontiguousarray(target, np.float32)
+        m = None if reset_mask is None else np.ascontiguousarray(reset_mask, np.uint8)
+        x = None if xy is None else np.ascontiguousarray(xy, np.float32)
+        self.lib.hp_step(C.byref(self.gg), C.c_int(n), _p(q), _p(qd), _p(qacc), _p(target), _p(m) if m is not None else None,
+                         _p(x) if x is not None else None, C.c_int(iterations), C.c_float(tol), _p(a), _p(e), _p(r), _p(t), C.c_int(nthreads))
+        return a, e, r, t
+
+    def run_workload(self, q, qd, qacc, pool, steps, reset_prob, seed=0, iterations=10, tol=1e-5, nthreads=1):
+        """`steps` workload steps entirely in native code (masked resets + substep + observation per env and step), threads own env
+        ranges for the whole run: the CPU baseline bench.py quotes.  pool: (npool, n, nu) float32 action batches, cycled."""
+        n = q.shape[0]
+        pool = np.ascontiguousarray(pool, np.float32)
+        a, e = np.zeros((n, self.agent_dim), np.float32), np.zeros((n, 11), np.float32)
+        r, t = np.zeros(n, np.float32), np.zeros(n, np.uint8)
+        self.lib.hp_run_workload(C.byref(self.gg), C.c_int(n), C.c_int(steps), C.c_int(nthreads), _p(q), _p(qd), _p(qacc), _p(pool),
+                                 C.c_int(pool.shape[0]), C.c_float(reset_prob), C.c_uint64(seed), C.c_int(iterations), C.c_float(tol),
+                                 _p(a), _p(e), _p(r), _p(t))
+        return a, e, r, t

@@ -57,7 +57,7 @@ namespace {
 enum { FIXED = 0, HINGE = 1, SLIDE = 2, FREE = 3 };
 enum { OPT_DT = 0, OPT_GRAV, OPT_PLANE_Z, OPT_MU, OPT_TC, OPT_DR, OPT_DMIN, OPT_DMAX, OPT_WIDTH, OPT_MID,
        OPT_POWER, OPT_MINVAL, OPT_SUCCESS_Z, OPT_SPAWN_XLO, OPT_SPAWN_XHI, OPT_SPAWN_YLO, OPT_SPAWN_YHI,
-       OPT_SPAWN_Z, OPT_COUNT };
+       OPT_SPAWN_Z, OPT_REG_SCALE, OPT_COUNT };
 
 // ------------------------------------------------------------------------------------ vec helpers
 template <class T> inline void cross(const T* a, const T* b, T* o) {
@@ -619,7 +619,7 @@ template <class T> static void make_rows(const Model<T>& m, const Kin<T>& k, con
             for (int d = 0; d < nv; d++) { T j = Jn[d] + s * mu * Jt[d]; r.J[r.n * nv + d] = j; vel += j * qd[d]; }
             T imp, aref;
             imp_aref(m, -c.depth, vel, imp, aref);
-            T R = std::max(minval, 2 * mu * mu * (1 - imp) / imp * (wa + wb) * (1 + mu * mu));
+            T R = std::max(minval, (T)m.opt[OPT_REG_SCALE] * (1 - imp) / imp * (wa + wb));   // GENESIS_COMPAT_PYRAMID_MU_SCALING: 2 mu^2 (1 + mu^2) or 1
             r.aref.push_back(aref); r.D.push_back(1 / R); r.n++;
         }
     }
@@ -986,21 +986,46 @@ void orc_spawn_xy(const void* hv, uint64_t seed, uint32_t env_id, uint32_t episo
         }                                                                                                            \
     }                                                                                                                \
     /* batched IK of the eef body: q_init / q_out (n, nu); tpos (n,3) / tquat (n,4) nullable; err (n,2); iters (n) */   \
+    /* max_samples > 1: rows that miss the tolerances are re-started SEQUENTIALLY from random arm configurations (uniform  \
+       inside the joint limits, Philox counter (row, sample, 'IKRS', dof / 4), key = seed; float32 draw as on the device);      \
+       result = first attempt that meets the tolerances, else the attempt with the smallest max(e_pos/pos_tol, e_rot/rot_tol). \
+       n_arm = number of leading robot dofs that are re-drawn (the gripper dofs keep their start values).                      */ \
     void orc_ik_##SUF(const void* hv, int n, const T* q_init, const T* tpos, const T* tquat, int max_iters, double damping, \
                       double pos_tol, double rot_tol, double max_step, int respect_limits, const double* mask6, T* q_out, \
-                      T* err, int32_t* iters) {                                                                      \
+                      T* err, int32_t* iters, int max_samples, uint64_t seed, int n_arm) {                          \
         const Model<T>& m = Pick<T>::get((const Handle*)hv);                                                         \
         T mk[6]; for (int i = 0; i < 6; i++) mk[i] = (T)mask6[i];                                                    \
         for (int e = 0; e < n; e++) {                                                                                \
-            std::vector<T> qf(m.nq, 0);                                                                              \
+            std::vector<T> qf(m.nq, 0), best(m.nu);                                                                  \
             for (int i = 0; i < m.nu; i++) qf[i] = q_init[(size_t)e * m.nu + i];                                     \
             qf[m.nu + 3] = 1;                                                                                        \
-            T e2[2];                                                                                                 \
-            int it = inverse_kinematics(m, qf.data(), tpos ? tpos + (size_t)e * 3 : (const T*)nullptr,               \
-                                        tquat ? tquat + (size_t)e * 4 : (const T*)nullptr, max_iters, (T)damping,   \
-                                        (T)pos_tol, (T)rot_tol, (T)max_step, respect_limits, mk, e2);                \
-            for (int i = 0; i < m.nu; i++) q_out[(size_t)e * m.nu + i] = qf[i];                                      \
-            if (err) { err[e * 2] = e2[0]; err[e * 2 + 1] = e2[1]; }                                                 \
+            const T* tp_ = tpos ? tpos + (size_t)e * 3 : (const T*)nullptr;                                          \
+            const T* tq_ = tquat ? tquat + (size_t)e * 4 : (const T*)nullptr;                                        \
+            T e2[2], be[2];                                                                                          \
+            int it = inverse_kinematics(m, qf.data(), tp_, tq_, max_iters, (T)damping, (T)pos_tol, (T)rot_tol, (T)max_step, respect_limits, mk, e2); \
+            for (int i = 0; i < m.nu; i++) best[i] = qf[i];                                                          \
+            be[0] = e2[0]; be[1] = e2[1];                                                                            \
+            T bscore = std::max(e2[0] / (T)pos_tol, e2[1] / (T)rot_tol);                                             \
+            bool ok = e2[0] < (T)pos_tol && e2[1] < (T)rot_tol;                                                      \
+            for (int s = 1; s < max_samples && !ok; s++) {                                                           \
+                for (int i = 0; i < m.nu; i++) qf[i] = best[i];                                                      \
+                for (int blk = 0; blk < (n_arm + 3) / 4; blk++) {                                                    \
+                    uint32_t ctr[4] = {(uint32_t)e, (uint32_t)s, 0x494B5253u, (uint32_t)blk};                       \
+                    uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)}, o[4];                                \
+                    philox4x32_10(ctr, key, o);                                                                      \
+                    for (int k = 0; k < 4 && blk * 4 + k < n_arm; k++) {                                             \
+                        const int i = blk * 4 + k;                                                                   \
+                        const float u = (float)(o[k] >> 8) * 5.9604644775390625e-8f;                                 \
+                        qf[i] = (T)std::fmaf(u, (float)m.lim_hi[i] - (float)m.lim_lo[i], (float)m.lim_lo[i]);        \
+                    }                                                                                                \
+                }                                                                                                    \
+                it += inverse_kinematics(m, qf.data(), tp_, tq_, max_iters, (T)damping, (T)pos_tol, (T)rot_tol, (T)max_step, respect_limits, mk, e2); \
+                ok = e2[0] < (T)pos_tol && e2[1] < (T)rot_tol;                                                       \
+                const T sc = std::max(e2[0] / (T)pos_tol, e2[1] / (T)rot_tol);                                       \
+                if (ok || sc < bscore) { bscore = sc; be[0] = e2[0]; be[1] = e2[1]; for (int i = 0; i < m.nu; i++) best[i] = qf[i]; } \
+            }                                                                                                        \
+            for (int i = 0; i < m.nu; i++) q_out[(size_t)e * m.nu + i] = best[i];                                    \
+            if (err) { err[e * 2] = be[0]; err[e * 2 + 1] = be[1]; }                                                 \
             if (iters) iters[e] = it;                                                                                \
         }                                                                                                            \
     }                                                                                                                \

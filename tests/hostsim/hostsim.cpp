@@ -98,6 +98,21 @@ extern "C" void hs_ik(const GgModel* M, const GgIkConfig* K, int n, const float*
         if (tquat) tq = gg::ldq(tquat + (size_t)e * 4); else k.rot_mask[0] = k.rot_mask[1] = k.rot_mask[2] = 0.f;
         float pe, re;
         int it = M->n_arm == 7 ? gg::env_ik<7>(*M, k, q, tp, tq, pe, re) : gg::env_ik<5>(*M, k, q, tp, tq, pe, re);
+        // re-sampling of unsolved rows, sequential form of ik_resample_kernel (same draws, same selection rule)
+        float qb[GG_MAX_DOF], bp = pe, br = re, best = gg::ik_score(k, pe, re);
+        for (int i = 0; i < nu; i++) qb[i] = q[i];
+        bool ok = pe < k.pos_tol && re < k.rot_tol;
+        for (int s = 1; s < k.max_samples && !ok; s++) {
+            for (int i = 0; i < nu; i++) q[i] = qb[i];
+            if (M->n_arm == 7) gg::ik_sample_init<7>(*M, k.seed_lo, k.seed_hi, (uint32_t)e, (uint32_t)s, q);
+            else gg::ik_sample_init<5>(*M, k.seed_lo, k.seed_hi, (uint32_t)e, (uint32_t)s, q);
+            it += M->n_arm == 7 ? gg::env_ik<7>(*M, k, q, tp, tq, pe, re) : gg::env_ik<5>(*M, k, q, tp, tq, pe, re);
+            ok = pe < k.pos_tol && re < k.rot_tol;
+            const float sc = gg::ik_score(k, pe, re);
+            if (ok || sc < best) { best = sc; bp = pe; br = re; for (int i = 0; i < nu; i++) qb[i] = q[i]; }
+        }
+        for (int i = 0; i < nu; i++) q[i] = qb[i];
+        pe = bp; re = br;
         for (int i = 0; i < nu; i++) q_out[(size_t)e * nu + i] = q[i];
         if (err) { err[2 * e] = pe; err[2 * e + 1] = re; }
         if (iters) iters[e] = it;

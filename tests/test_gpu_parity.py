@@ -377,3 +377,66 @@ def test_gym_surface_host_io():
     assert terminated.dtype == torch.bool and not terminated.any() and not truncated.any()
     assert obs["agent_pos"].is_cuda and obs["environment_state"].shape == (n, 11)
     assert torch.equal(reward, env._env.sim.reward.cpu())
+
+
+def test_step_outputs_are_fresh_by_default_and_alias_on_request():
+    """the reference's getters return fresh tensors (franka/cube_pick.py:137-157) and its collectors append them step after
+    step (examples/franka/pick_cube_state.py:86-100).  Default: what step t returned is untouched by step t + 1; alias_outputs=True is
+    the zero-allocation opt-in."""
+    import gym_genesis  # noqa: F401
+    from gym_genesis_b200.gym_api import gym
+    n = 64
+    rng = np.random.default_rng(0)
+    acts = [f32(mdl.FRANKA_HOME + rng.uniform(-0.3, 0.3, (n, 9))) for _ in range(3)]
+    for host_io in (False, True):
+        env = gym.make("gym_genesis/CubePick-v0", robot="franka", num_envs=n, host_io=host_io).unwrapped
+        obs0, _ = env.reset(seed=1)
+        keep0 = {k: v.clone() for k, v in obs0.items()}
+        outs = []
+        for a in acts:
+            o, r, t, tr, info = env.step(torch.as_tensor(a).pin_memory() if host_io else a)
+            outs.append((o, r, t, {k: v.clone() for k, v in o.items()}, r.clone()))
+        assert all(torch.equal(obs0[k], keep0[k]) for k in obs0)                       # reset's observation survived three steps
+        for o, r, t, oc, rc in outs:
+            assert all(torch.equal(o[k], oc[k]) for k in o) and torch.equal(r, rc)     # each step's results survived the later steps
+        assert not torch.equal(outs[0][0]["agent_pos"], outs[2][0]["agent_pos"])
+        assert outs[0][0]["agent_pos"].data_ptr() != outs[1][0]["agent_pos"].data_ptr()
+        env.close()
+        env = gym.make("gym_genesis/CubePick-v0", robot="franka", num_envs=n, host_io=host_io, alias_outputs=True).unwrapped
+        env.reset(seed=1)
+        o1 = env.step(torch.as_tensor(acts[0]).pin_memory() if host_io else acts[0])[0]
+        o2 = env.step(torch.as_tensor(acts[1]).pin_memory() if host_io else acts[1])[0]
+        assert o1["agent_pos"].data_ptr() == o2["agent_pos"].data_ptr()                # same buffers, overwritten in place
+        env.close()
+
+
+def test_host_io_masked_reset_push_and_control_after_host_step():
+    """after a host-fed step the held PD targets live ON THE DEVICE (written by the kernel from the batch it consumed), so a
+    masked reset, push() and control_dofs_position work, and push() re-applies the consumed action even if the caller has since
+    overwritten its pinned buffer."""
+    import gym_genesis  # noqa: F401
+    from gym_genesis_b200.gym_api import gym
+    n = 96
+    rng = np.random.default_rng(2)
+    env = gym.make("gym_genesis/CubePick-v0", robot="franka", num_envs=n, host_io=True, host_obs=True).unwrapped
+    ref = gym.make("gym_genesis/CubePick-v0", robot="franka", num_envs=n).unwrapped
+    env.reset(seed=5); ref.reset(seed=5)
+    a = torch.as_tensor(f32(mdl.FRANKA_HOME + rng.uniform(-0.3, 0.3, (n, 9)))).pin_memory()
+    obs, reward, term, trunc, info = env.step(a)
+    ref.step(a.numpy().copy())
+    assert obs["agent_pos"].device.type == "cpu" and obs["environment_state"].shape == (n, 11)      # host_obs: observations on the host
+    assert torch.equal(obs["agent_pos"], ref._env.sim.obs_agent.cpu()) and torch.equal(obs["environment_state"], ref._env.sim.obs_env.cpu())
+    assert env._env._targets.is_cuda and torch.equal(env._env._targets.cpu(), a)
+    a.zero_()                                                   # the caller recycles its pinned buffer ...
+    env.push(); ref.push()                                      # ... push() still holds the targets the step consumed
+    for x, y in zip(env._env.sim.get_state(), ref._env.sim.get_state()):
+        assert torch.equal(x, y)
+    mask = torch.zeros(n, dtype=torch.bool); mask[::3] = True
+    env.reset(options={"reset_mask": mask}); ref.reset(options={"reset_mask": mask})
+    assert torch.equal(env._env._targets, ref._env._targets)
+    env.get_robot().control_dofs_position(np.full((n, 2), 0.01, np.float32), [7, 8])
+    ref.get_robot().control_dofs_position(np.full((n, 2), 0.01, np.float32), [7, 8])
+    env.push(); ref.push()
+    for x, y in zip(env._env.sim.get_state(), ref._env.sim.get_state()):
+        assert torch.equal(x, y)
+    env.close(); ref.close()

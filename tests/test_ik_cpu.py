@@ -118,3 +118,41 @@ def test_device_header_ik_matches_oracle(robot, hostsim):
     assert np.abs(qo[same] - qr[same]).max() < TOL_IK_Q
     if robot == "franka":
         assert (err[:, 0] < 5e-4).all() and (err[:, 1] < 5e-3).all()
+
+
+def bad_start_problem(m, orc, rng, n):
+    """Reachable targets, start configurations drawn uniformly inside the joint limits: the first attempt fails for ~60 % of the rows
+    within 20 updates, so the re-sampling path (max_samples) decides the result."""
+    q0, tp, tq = reachable_targets(m, orc, rng, n, spread=0.25)
+    lo, hi = np.asarray(m.flat()["lim_lo"])[:m.n_arm], np.asarray(m.flat()["lim_hi"])[:m.n_arm]
+    q0[:, :m.n_arm] = rng.uniform(lo, hi, (n, m.n_arm))
+    return f32(q0).astype(np.float64), tp, tq
+
+
+def test_ik_resampling_first_success_in_sample_order(hostsim):
+    """max_samples: unsolved rows restart from Philox draws (row, sample) inside the joint limits; result = first success in sample order.
+    Oracle (fp64, sequential) against the device header (fp32, sequential form of ik_resample_kernel): same draws, same choice."""
+    m = franka_cube_pick_model()
+    orc = Oracle(m, np.float64)
+    gm = cabi.compile_gg(m)
+    n = 64
+    q0, tp, tq = bad_start_problem(m, orc, np.random.RandomState(3), n)
+    q1, e1, i1 = orc.ik(q0, tp, tq)
+    ok1 = (e1[:, 0] < 5e-4) & (e1[:, 1] < 5e-3)
+    assert 0.2 < ok1.mean() < 0.7                                  # the first attempt alone fails for many rows
+    seed = (9 << 32) | 7
+    qr, er, ir = orc.ik(q0, tp, tq, max_samples=16, seed=seed)
+    okr = (er[:, 0] < 5e-4) & (er[:, 1] < 5e-3)
+    assert okr.mean() > 0.95 and (ir[~ok1] > 20).all()              # re-sampling solves them, at the cost of further attempts
+    assert np.array_equal(qr[ok1], q1[ok1])                         # rows solved by attempt 0 are untouched
+    assert np.array_equal(orc.ik(q0, tp, tq, max_samples=16, seed=seed)[0], qr)          # deterministic in (seed, row, sample)
+    assert not np.array_equal(orc.ik(q0, tp, tq, max_samples=16, seed=seed + 1)[0][~ok1], qr[~ok1])
+    k = _cfg(max_samples=16, seed_lo=seed & 0xFFFFFFFF, seed_hi=seed >> 32)
+    qo = np.zeros((n, m.nu), np.float32); err = np.zeros((n, 2), np.float32); it = np.zeros(n, np.int32)
+    a, b, c = f32(q0), f32(tp), f32(tq)
+    hostsim.hs_ik(C.byref(gm), C.byref(k), n, a.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_void_p), c.ctypes.data_as(C.c_void_p),
+                  qo.ctypes.data_as(C.c_void_p), err.ctypes.data_as(C.c_void_p), it.ctypes.data_as(C.c_void_p))
+    same = it == ir                                                 # same attempts, same number of updates: the same sample was chosen
+    assert same.mean() > 0.85, same.mean()
+    assert np.abs(qo[same] - qr[same]).max() < 5 * TOL_IK_Q         # random starts amplify fp32 rounding a little more than near-home starts
+    assert ((err[:, 0] < 5e-4) & (err[:, 1] < 5e-3)).mean() > 0.95

@@ -41,9 +41,9 @@ for stage in "$@"; do
               python bench.py --impl reference --steps 20 --warmup 3 > ${O}_bench_ref.json 2>> ${O}_bench.err; tail -c 400 ${O}_bench_ref.json ;;
     benchlite) python bench.py --no-workload-b --no-workload-c --no-config4 --no-workload-d > ${O}_benchlite.json 2> ${O}_benchlite.err; tail -c 1500 ${O}_benchlite.json; tail -3 ${O}_benchlite.err ;;
     launches) timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file ${O}_launches.csv \
-                python bench.py --steps 20 --warmup 10 --no-cpu-baseline --no-workload-b --no-workload-c --no-config4 > ${O}_ncu_bench.log 2>&1; wc -l ${O}_launches.csv ;;
+                python bench.py --steps 20 --warmup 10 --no-cpu-baseline --no-workload-b --no-workload-c --no-config4 --no-config2 > ${O}_ncu_bench.log 2>&1; wc -l ${O}_launches.csv ;;
     ncu_step) timeout 600 ncu --set full --clock-control none --import-source on -k regex:step_kernel -s 12 -c 1 -f -o ${O}_step \
-                python bench.py --steps 20 --warmup 10 --no-cpu-baseline --no-workload-b --no-workload-c --no-config4 --no-workload-d > ${O}_ncu_full.log 2>&1; ls -la ${O}_step.ncu-rep ;;
+                python bench.py --steps 20 --warmup 10 --no-cpu-baseline --no-workload-b --no-workload-c --no-config4 --no-config2 --no-workload-d > ${O}_ncu_full.log 2>&1; ls -la ${O}_step.ncu-rep ;;
     ncu_grasp) timeout 600 ncu --set full --clock-control none --import-source on -k regex:"step_kernel|coupled" -s 130 -c 1 -f -o ${O}_grasp \
                 python tools/profile_grasp.py 140 > ${O}_ncu_grasp.log 2>&1; ls -la ${O}_grasp.ncu-rep ;;
     ncu_stack) timeout 900 ncu --set full --clock-control none --import-source on -k regex:stack_solve -s 12 -c 1 -f -o ${O}_stack_solve \

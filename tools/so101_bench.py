@@ -14,9 +14,9 @@ from gym_genesis_b200.sim import BatchedSim  # noqa: E402
 dev = torch.device("cuda", 0)
 n = 16384
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-CASES = ((0.3, 5.0, 1 / 200.), (0.3, 5.0, 0.0), (0.1, 5.0, 1 / 200.), (0.3, 1.0, 1 / 200.))
-for amp, mu, reset_prob in (CASES[:1] if "--one" in sys.argv else CASES):
-    m = so101_cube_pick_model(success_height=ISLAND_TOP_Z + 0.1)
+CASES = ((0.3, 5.0, 1 / 200., True), (0.3, 5.0, 1 / 200., False), (0.3, 5.0, 0.0, True), (0.1, 5.0, 1 / 200., True), (0.3, 1.0, 1 / 200., True))
+for amp, mu, reset_prob, mu_scaling in (CASES[:2] if "--one" in sys.argv else CASES):
+    m = so101_cube_pick_model(success_height=ISLAND_TOP_Z + 0.1, pyramid_mu_scaling=mu_scaling)     # GENESIS_COMPAT_PYRAMID_MU_SCALING switch
     m.friction = mu
     sim = BatchedSim(m, n, device=dev, auto_reset=True, reset_prob=reset_prob, seed=0)
     sim.reset(None, None)
@@ -33,6 +33,8 @@ for amp, mu, reset_prob in (CASES[:1] if "--one" in sys.argv else CASES):
     torch.cuda.synchronize()
     t = np.mean([a.elapsed_time(b) for a, b in ev])
     st = sim.stats().cpu().numpy()
-    print(json.dumps({"amp": amp, "mu": mu, "reset_prob": reset_prob, "us_per_step": round(t * 1e3, 1), "iters": round(st[6] / st[0], 3),
+    z = sim.get_state()[0][:, 8]
+    print(json.dumps({"amp": amp, "mu": mu, "reset_prob": reset_prob, "pyramid_mu_scaling": mu_scaling,
+                      "median_cube_depth_mm": round(float((m.plane_z + 0.02 - z.median()) * 1e3), 3), "us_per_step": round(t * 1e3, 1), "iters": round(st[6] / st[0], 3),
                       "contacts": round(st[7] / st[0], 3), "nonfinite": st[5]}))
     sim.close()
