@@ -9,10 +9,13 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <dlfcn.h>
+
 #include <atomic>
 #include <new>
 
 #include "gg_b200.h"
+#include "gg_internal.h"
 #include "gg_env.cuh"
 #include "gg_coop.cuh"
 #include "gg_ik.cuh"
@@ -1076,9 +1079,44 @@ struct GgSim {
     uint32_t epoch; int n_sm; int use_blocks; int use_mono; int64_t list_budget;   // launch epoch of the mailbox flags; SM count; 1 = round-1 block kernel (GG_STEP_KERNEL=blocks)
     int32_t* slot;                      // library-owned, allocated on first gg_export_successful: env -> compacted episode slot
     uint32_t step_index;
-    static constexpr int kPinCache = 16;
-    const void* pin_ok[kPinCache]; int pin_next;   // pointers already verified as pinned host memory (gg_step_host)
+    GgPinCache pins;                    // address ranges already verified as pinned host memory (gg_step_host)
 };
+
+// Is `p` page-locked host memory the device can address (cudaHostAlloc / cudaHostRegister)?  The verdict is cached per ALLOCATION
+// RANGE (driver attribute RANGE_START_ADDR / RANGE_SIZE, resolved lazily so that the library loads without a driver): callers that
+// hand out a fresh slot of one pinned batch every step (gym_genesis_b200.sim fresh outputs) pay no driver query in the steady
+// state.  A cached range is re-verified every 1024 hits, so a range that was freed and re-used by pageable memory is not trusted
+// for long (the per-pointer cache of round 1 was never invalidated).
+bool gg_internal_pinned(GgPinCache* pc, const void* p) {
+    const uintptr_t a = (uintptr_t)p;
+    for (int i = 0; i < GgPinCache::kN; i++) {
+        if (pc->size[i] != 0 && a >= pc->base[i] && a < pc->base[i] + pc->size[i]) {
+            if (++pc->hits[i] < 1024) return true;
+            pc->size[i] = 0;                              // age out: fall through to a fresh query
+            break;
+        }
+    }
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    if (at.type != cudaMemoryTypeHost && at.type != cudaMemoryTypeManaged) return false;
+    typedef int (*PtrAttrFn)(void*, int, unsigned long long);
+    static PtrAttrFn fn = []() -> PtrAttrFn {
+        void* h = dlopen("libcuda.so.1", RTLD_LAZY | RTLD_GLOBAL);
+        return h ? (PtrAttrFn)dlsym(h, "cuPointerGetAttribute") : nullptr;
+    }();
+    unsigned long long start = 0;
+    size_t size = 0;
+    const unsigned long long dp = (unsigned long long)(at.devicePointer ? at.devicePointer : p);
+    if (fn && fn(&start, 11 /* CU_POINTER_ATTRIBUTE_RANGE_START_ADDR */, dp) == 0 && fn(&size, 12 /* ..._RANGE_SIZE */, dp) == 0 && size != 0 &&
+        a >= (uintptr_t)start && a < (uintptr_t)start + size) {
+        pc->base[pc->next] = (uintptr_t)start; pc->size[pc->next] = size;
+    } else {
+        pc->base[pc->next] = a; pc->size[pc->next] = 1;  // range unknown: cache the exact pointer only
+    }
+    pc->hits[pc->next] = 0;
+    pc->next = (pc->next + 1) % GgPinCache::kN;
+    return true;
+}
 
 // hooks for the other translation units of the library (gg_stack.cu): shared error string and launch counter
 int gg_internal_fail(const char* fmt, const char* detail) { return fail(fmt, detail); }
@@ -1281,17 +1319,7 @@ int gg_step(GgSim* sim, const float* action, float* obs_agent, float* obs_env, f
     return rc;
 }
 
-// Is `p` page-locked host memory the device can address (cudaHostAlloc / cudaHostRegister)?  The answer is cached per
-// pointer so that the steady-state step pays no driver query.
-static bool pinned_host_ptr(GgSim* sim, const void* p) {
-    for (int i = 0; i < GgSim::kPinCache; i++) if (sim->pin_ok[i] == p) return true;
-    cudaPointerAttributes at;
-    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
-    if (at.type != cudaMemoryTypeHost && at.type != cudaMemoryTypeManaged) return false;
-    sim->pin_ok[sim->pin_next] = p;
-    sim->pin_next = (sim->pin_next + 1) % GgSim::kPinCache;
-    return true;
-}
+static bool pinned_host_ptr(GgSim* sim, const void* p) { return gg_internal_pinned(&sim->pins, p); }
 
 int gg_step_host(GgSim* sim, const GgHostIO* io, float* obs_agent, float* obs_env, float* reward, uint8_t* terminated,
                  uint8_t* truncated, const uint8_t* reset_mask, gg_stream_t stream) {

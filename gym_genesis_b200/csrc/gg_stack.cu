@@ -21,6 +21,7 @@
 #include <new>
 
 #include "gg_b200.h"
+#include "gg_internal.h"
 #include "gg_stack.cuh"
 
 int gg_internal_fail(const char* fmt, const char* detail);
@@ -571,8 +572,7 @@ struct GgStackSim {
     int32_t* amask; uint8_t* rob_it; uint8_t* iso_nc; uint8_t* iso_it;
     int32_t* slot;                                            // allocated on first gg_stack_export_successful
     uint32_t step_index;
-    static constexpr int kPinCache = 16;
-    const void* pin_ok[kPinCache]; int pin_next;             // pointers already verified as pinned host memory
+    GgPinCache pins;                                          // address ranges already verified as pinned host memory
     size_t solve_smem;
     int solve_blocks;                                         // persistent grid of the cooperative solver
     cudaStream_t side;                                        // the cubes kernel runs beside the cooperative solve (fork / join per step)
@@ -747,27 +747,13 @@ int gg_stack_step(GgStackSim* sim, const float* action, float* obs_agent, float*
     return rc;
 }
 
-static bool stack_host_ptr(const void* p) {
-    cudaPointerAttributes at;
-    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
-    return at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeManaged;
-}
-
 int gg_stack_step_host(GgStackSim* sim, const GgHostIO* io, float* obs_agent, float* obs_env, float* reward, uint8_t* terminated,
                        uint8_t* truncated, const uint8_t* reset_mask, gg_stream_t stream) {
     if (!sim || !io || !io->action || !obs_agent || !obs_env) return gg_internal_fail("gg_stack_step_host: null argument%s", "");
-    // the answer of the driver query is cached per pointer so that the steady-state step pays none
     const void* ptrs[6] = {io->action, io->reward, io->terminated, io->truncated, io->obs_agent, io->obs_env};
-    for (int k = 0; k < 6; k++) {
-        if (!ptrs[k]) continue;
-        bool known = false;
-        for (int i = 0; i < GgStackSim::kPinCache; i++) known = known || sim->pin_ok[i] == ptrs[k];
-        if (!known) {
-            if (!stack_host_ptr(ptrs[k])) return gg_internal_fail("gg_stack_step_host: action / mirrors must be page-locked (pinned) host memory%s", "");
-            sim->pin_ok[sim->pin_next] = ptrs[k];
-            sim->pin_next = (sim->pin_next + 1) % GgStackSim::kPinCache;
-        }
-    }
+    for (int k = 0; k < 6; k++)
+        if (ptrs[k] && !gg_internal_pinned(&sim->pins, ptrs[k]))
+            return gg_internal_fail("gg_stack_step_host: action / mirrors must be page-locked (pinned) host memory%s", "");
     StackArgs A;
     memset(&A, 0, sizeof(A));
     A.action = io->action; A.obs_agent = obs_agent; A.obs_env = obs_env; A.reward = reward; A.terminated = terminated;

@@ -66,6 +66,7 @@ class BatchedSim:
         self.terminated = torch.zeros(self.n_envs, dtype=torch.bool, device=dev)
         self.truncated = torch.zeros(self.n_envs, dtype=torch.bool, device=dev)
         self._stats = torch.zeros(8, dtype=torch.float64, device=dev)
+        self._out_ptrs = tuple(t.data_ptr() for t in (self.obs_agent, self.obs_env, self.reward, self.terminated, self.truncated))
         self.cfg = cabi.GgConfig(solver_iterations, solver_tolerance, int(auto_reset), int(time_limit), float(reset_prob),
                                  int(seed) & (2 ** 64 - 1), int(first_env_id))
         self._check(self.lib.gg_configure(h, C.byref(self.cfg)))
@@ -115,26 +116,45 @@ class BatchedSim:
             raise ValueError(f"mask must have shape ({self.n_envs},), got {tuple(mask.shape)}")
         return mask.to(device=self.device, dtype=torch.uint8).contiguous()
 
+    # ---- fresh outputs ------------------------------------------------------------------------------------------------------------
+    # fresh_outputs=True: every step / reset writes into output tensors nobody has seen before, so tensors returned earlier keep their
+    # values -- the reference's getters return fresh tensors (franka/cube_pick.py:137-157) and its collectors append them step after
+    # step (examples/franka/pick_cube_state.py:86-100).  Creating five tensors per step costs ~25 us of host time (allocator + Python
+    # tensor objects), as much as the step kernel itself; so the sets are made in BATCHES: one allocation per output kind for K steps,
+    # split into K views by a single unbind() call, and a step just takes the next set.  The default (False) reuses one set of buffers:
+    # zero allocation, CUDA-graph safe.
+    _POOL_BYTES = 64 << 20
+
+    def _pool_size(self):
+        per_step = self.n_envs * (self.agent_dim + self.env_dim + 1) * 4 + 2 * self.n_envs
+        return int(max(1, min(32, self._POOL_BYTES // per_step)))
+
     def _new_outputs(self):
-        """fresh_outputs=True: every step / reset writes into NEWLY allocated output tensors (torch's caching allocator: no kernels,
-        a few microseconds of host time), so tensors returned earlier keep their values -- the reference's getters return fresh
-        tensors too (franka/cube_pick.py:137-157), and its collectors append them step after step
-        (examples/franka/pick_cube_state.py:86-100).  The default (False) reuses one set of buffers: zero allocation, CUDA-graph safe."""
-        n, dev = self.n_envs, self.device
-        na, ne = n * self.agent_dim, n * self.env_dim
-        if na % 4 == 0 and ne % 4 == 0:
-            # one float allocation carved into the three float outputs (every slab stays 16-byte aligned for the kernel's 128-bit stores)
-            buf = torch.empty(na + ne + n, dtype=torch.float32, device=dev)
-            self.obs_agent = buf[:na].view(n, self.agent_dim)
-            self.obs_env = buf[na:na + ne].view(n, self.env_dim)
-            self.reward = buf[na + ne:]
-        else:
-            self.obs_agent = torch.empty((n, self.agent_dim), dtype=torch.float32, device=dev)
-            self.obs_env = torch.empty((n, self.env_dim), dtype=torch.float32, device=dev)
-            self.reward = torch.empty(n, dtype=torch.float32, device=dev)
-        flags = torch.empty((2, n), dtype=torch.bool, device=dev)
-        self.terminated, self.truncated = flags[0], flags[1]
-        self._out_ptrs = None
+        pool = getattr(self, "_out_pool", None)
+        if not pool:
+            n, dev, K = self.n_envs, self.device, self._pool_size()
+            A = torch.empty((K, n, self.agent_dim), dtype=torch.float32, device=dev).unbind(0)
+            E = torch.empty((K, n, self.env_dim), dtype=torch.float32, device=dev).unbind(0)
+            R = torch.empty((K, n), dtype=torch.float32, device=dev).unbind(0)
+            F = torch.empty((2, K, n), dtype=torch.bool, device=dev)
+            T, U = F[0].unbind(0), F[1].unbind(0)
+            pool = self._out_pool = [(A[k], E[k], R[k], T[k], U[k], (A[k].data_ptr(), E[k].data_ptr(), R[k].data_ptr(), T[k].data_ptr(),
+                                                                    U[k].data_ptr())) for k in range(K)]
+        self.obs_agent, self.obs_env, self.reward, self.terminated, self.truncated, self._out_ptrs = pool.pop()
+
+    def _new_host_results(self):
+        """Same batching for the pinned host mirrors of step_host: the kernel writes each step's results into a pinned slot nobody has
+        seen before, so the returned CPU tensors are fresh without a copy."""
+        pool = getattr(self, "_host_pool", None)
+        if not pool:
+            n, K = self.n_envs, self._pool_size()
+            R = torch.empty((K, n), dtype=torch.float32, pin_memory=True).unbind(0)
+            F = torch.empty((2, K, n), dtype=torch.bool, pin_memory=True)
+            T, U = F[0].unbind(0), F[1].unbind(0)
+            pool = self._host_pool = [(R[k], T[k], U[k], R[k].data_ptr(), T[k].data_ptr(), U[k].data_ptr()) for k in range(K)]
+        r, t, u, pr, pt, pu = pool.pop()
+        self._hio.reward, self._hio.terminated, self._hio.truncated = pr, pt, pu
+        self._host["reward"], self._host["terminated"], self._host["truncated"] = r, t, u
 
     def step(self, action, reset_mask=None):
         """One env.step (= one 0.01 s substep) for all envs; results land in the obs_agent / obs_env / reward / terminated /
@@ -144,28 +164,28 @@ class BatchedSim:
         self._last_action = a          # PD targets persist (reference: control_dofs_position semantics)
         if self.fresh_outputs:
             self._new_outputs()
-        self._check(self.lib.gg_step(self._h, _ptr(a), _ptr(self.obs_agent), _ptr(self.obs_env), _ptr(self.reward),
-                                     _ptr(self.terminated), _ptr(self.truncated), _ptr(m), self._stream()))
+        self._check(self._step_fn()(self._h, a.data_ptr(), *self._out_ptrs, _ptr(m), self._stream()))
+
+    def _step_fn(self):
+        return self.lib.gg_step
 
     def _host_buffers(self):
         if getattr(self, "_host", None) is None:
             n = self.n_envs
             self._host = {
                 "action": torch.empty((n, self.nu), dtype=torch.float32).pin_memory(),      # staging for unpinned callers
-                # reward f32 | terminated u8 | truncated u8 in ONE float32 buffer: a single clone detaches all three (float32 on purpose:
-                # torch's clone of a uint8 CPU tensor of this size takes 600 us, of a float32 one 6 us)
-                "packed": torch.zeros(n + (2 * n + 3) // 4, dtype=torch.float32).pin_memory(),
+                "reward": torch.zeros(n, dtype=torch.float32).pin_memory(),
+                "terminated": torch.zeros(n, dtype=torch.bool).pin_memory(),
+                "truncated": torch.zeros(n, dtype=torch.bool).pin_memory(),
                 "obs_agent": torch.zeros((n, self.agent_dim), dtype=torch.float32).pin_memory(),
                 "obs_env": torch.zeros((n, self.env_dim), dtype=torch.float32).pin_memory(),
             }
             # device-resident copy of the action batch the last host-fed step consumed (written by the kernel): PD targets persist
             self._targets_dev = torch.zeros((n, self.nu), dtype=torch.float32, device=self.device)
-            self._host.update(self._unpack_host(self._host["packed"]))
             self._hio = cabi.GgHostIO(0, self._host["reward"].data_ptr(), self._host["terminated"].data_ptr(),
                                       self._host["truncated"].data_ptr(), 1)
             self._hio.action_dev = self._targets_dev.data_ptr()
             self._hio_ref = C.byref(self._hio)
-            self._out_ptrs = None
             self._pinned_ok = {}
         return self._host
 
@@ -179,8 +199,7 @@ class BatchedSim:
         h = self._host_buffers()
         if self.fresh_outputs:
             self._new_outputs()
-        if self._out_ptrs is None:
-            self._out_ptrs = tuple(_ptr(t) for t in (self.obs_agent, self.obs_env, self.reward, self.terminated, self.truncated))
+            self._new_host_results()
         # tensors that passed the checks once are recognised by (object id, data pointer): `is_pinned()` is a driver query
         key = (id(action), action.data_ptr()) if isinstance(action, torch.Tensor) else None
         if key is not None and key in self._pinned_ok:
@@ -205,15 +224,7 @@ class BatchedSim:
         rc = self._step_host_fn()(self._h, self._hio_ref, *self._out_ptrs, _ptr(m), self._stream())
         if rc != 0:
             self._check(rc)
-        if self.fresh_outputs:                     # detach the results from the pinned mirrors the next step overwrites (one 6n-byte copy)
-            u = self._unpack_host(h["packed"].clone())
-            return u["reward"], u["terminated"], u["truncated"]
         return h["reward"], h["terminated"], h["truncated"]
-
-    def _unpack_host(self, packed):
-        n = self.n_envs
-        flags = packed[n:].view(torch.bool)
-        return {"reward": packed[:n], "terminated": flags[:n], "truncated": flags[n:2 * n]}
 
     @property
     def host_obs_agent(self):
@@ -369,6 +380,7 @@ class BatchedStackSim(BatchedSim):
         self.terminated = torch.zeros(self.n_envs, dtype=torch.bool, device=dev)
         self.truncated = torch.zeros(self.n_envs, dtype=torch.bool, device=dev)
         self._stats = torch.zeros(8, dtype=torch.float64, device=dev)
+        self._out_ptrs = tuple(t.data_ptr() for t in (self.obs_agent, self.obs_env, self.reward, self.terminated, self.truncated))
         self.cfg = cabi.GgConfig(solver_iterations, solver_tolerance, int(auto_reset), int(time_limit), float(reset_prob),
                                  int(seed) & (2 ** 64 - 1), int(first_env_id))
         self._check(self.lib.gg_stack_configure(h, C.byref(self.cfg)))
@@ -389,14 +401,8 @@ class BatchedStackSim(BatchedSim):
             self.lib.gg_stack_destroy(self._h)
             self._h = None
 
-    def step(self, action, reset_mask=None):
-        a = self._as_action(action)
-        m = self._as_mask(reset_mask)
-        self._last_action = a
-        if self.fresh_outputs:
-            self._new_outputs()
-        self._check(self.lib.gg_stack_step(self._h, _ptr(a), _ptr(self.obs_agent), _ptr(self.obs_env), _ptr(self.reward),
-                                           _ptr(self.terminated), _ptr(self.truncated), _ptr(m), self._stream()))
+    def _step_fn(self):
+        return self.lib.gg_stack_step
 
     def _step_host_fn(self):
         return self.lib.gg_stack_step_host

@@ -191,7 +191,7 @@ class CubePickBatch:
 
     def get_obs_host(self):
         """Pinned host mirrors of the observations written by the last `step_host(..., host_obs=True)`."""
-        oa, oe = self.sim.host_obs_agent, self.sim.host_obs_env
+        oa, oe = self.sim.host_obs_agent, self.sim.host_obs_env     # persistent pinned mirrors, overwritten by the next step
         if not self.alias_outputs:
             oa, oe = oa.clone(), oe.clone()
         return {"agent_pos": oa, "environment_state": oe}
