@@ -164,6 +164,13 @@ template <int NU, int AD> struct Xchg {
     int next;                 // head of the block's queue of coupled envs (solver teams pop with atomicAdd)
 };
 
+// shared memory of one group of 32 envs (three role warps); a block holds SUB of them (dynamic shared memory)
+template <int NA, int NF> struct StepSmem {
+    Xchg<NA + NF, 7 + NF> X;
+    gg::TeamWork<NA, NF> TW[3];
+    gg::TeamBuf<NA + NF + 6> TB[3];
+};
+
 // PD targets of one env for robot_rnea_t: the staged slab in shared memory (after the cp.async group has landed), the action
 // row in global memory (partial tail block / unaligned batch), or the home pose (envs being reset, settle steps).
 template <int NU> struct ActionFetch {
@@ -214,7 +221,7 @@ template <int NF4> __device__ __forceinline__ void store_slab(const float* smem,
 // their stall samples in bar.sync, profiles/r01_v7_grasp_*).
 template <int NA, int NF, bool FH, class XT>
 __device__ __forceinline__ void team_queue(const StepArgs& A, gg::TeamWork<NA, NF>* TW, gg::TeamBuf<NA + NF + 6>* TB, XT& X, unsigned cm,
-                                           int ncpl, int team, int lane) {
+                                           int ncpl, int team, int lane, int blk) {
     constexpr int TWF = sizeof(gg::TeamWork<NA, NF>) / sizeof(float);
     for (;;) {
         int k = 0;
@@ -222,7 +229,7 @@ __device__ __forceinline__ void team_queue(const StepArgs& A, gg::TeamWork<NA, N
         k = __shfl_sync(0xffffffffu, k, 0);
         if (k >= ncpl) break;
         const int el = __fns(cm, 0, k + 1);
-        const float* src = A.team_scratch + (size_t)(blockIdx.x * 32 + el) * TWF;
+        const float* src = A.team_scratch + (size_t)(blk * 32 + el) * TWF;
         float* dst = reinterpret_cast<float*>(&TW[team]);
 #pragma unroll 1
         for (int i = lane; i < TWF; i += 32) dst[i] = __ldcg(src + i);
@@ -235,30 +242,37 @@ __device__ __forceinline__ void team_queue(const StepArgs& A, gg::TeamWork<NA, N
     __threadfence_block();
 }
 
-template <int NA, int NF, bool FH>
-__global__ void __launch_bounds__(kBlockThreads, GG_MINBLOCKS) step_kernel(const __grid_constant__ StepArgs A) {
+template <int NA, int NF, bool FH, int SUB>
+__global__ void __launch_bounds__(kBlockThreads * SUB, GG_MINBLOCKS / SUB) step_kernel(const __grid_constant__ StepArgs A) {
     constexpr int NU = NA + NF, NV = NU + 6, AD = 7 + NF;
     constexpr int KS = (NA - 1) / 2;      // split point of the end-effector chain (links [0, KS) MAIN, [KS, NA) RNEA)
     typedef Xchg<NU, AD> XT;
-    __shared__ XT X;
-    __shared__ gg::TeamWork<NA, NF> TW[3];
-    __shared__ gg::TeamBuf<NV> TB[3];
+    typedef StepSmem<NA, NF> SM;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
     // until the first team round the team buffers double as scratch for the rolled loops of MAIN (per-link S, I) and CUBE
     // (per-contact J, aref, D, u, w)
-    static_assert(sizeof(TB) >= (gg::LinkStoreStrided<NA>::FLOATS + gg::CubeConStrided::FLOATS) * 32 * sizeof(float), "team buffers too small for the scratch views");
-    const int lane = threadIdx.x & 31, role = threadIdx.x >> 5;
+    static_assert(sizeof(SM::TB) >= (gg::LinkStoreStrided<NA>::FLOATS + gg::CubeConStrided::FLOATS) * 32 * sizeof(float), "team buffers too small for the scratch views");
+    // SUB groups of 32 envs per block: warp w = role * SUB + sub, so the SUB warps of one role sit on different schedulers and meet
+    // at the same (SUB times wider) named barriers -- they run the role's instruction stream in step (see the header comment)
+    const int lane = threadIdx.x & 31, role = (threadIdx.x >> 5) / SUB, sub = (threadIdx.x >> 5) % SUB;
+    const int blk = blockIdx.x * SUB + sub;               // index of this warp's group of 32 envs
+    const int pbar = 9 + sub;                             // named barrier private to the three warps of this group
+    SM& S = reinterpret_cast<SM*>(smem_raw)[sub];
+    XT& X = S.X;
+    gg::TeamWork<NA, NF>* TW = S.TW;
+    gg::TeamBuf<NV>* TB = S.TB;
 #ifdef GG_ONLY_ROLE
     if (role != GG_ONLY_ROLE) return;
     X.coupled[lane] = 0;
     __syncwarp();
 #endif
-    if (threadIdx.x == 64) X.next = 0;                    // CUBE lane 0: ordered before every pop by barrier 8 (arrive) and barrier 4
-    const int e0 = blockIdx.x * 32 + lane;
+    if (role == 2 && lane == 0) X.next = 0;                    // CUBE lane 0: ordered before every pop by barrier 8 (arrive) and barrier 4
+    const int e0 = blk * 32 + lane;
     const bool live = e0 < A.n;
     const int e = live ? e0 : A.n - 1;                    // dead lanes shadow the last env (loads only)
     const uint32_t gid = (uint32_t)(A.first_env + e);
     const bool run_sub = A.mode == 0 || (A.mode == 1 && A.M.settle_steps > 0);     // block-uniform
-    const bool full = blockIdx.x * 32 + 32 <= A.n;                                 // block-uniform: no dead lanes
+    const bool full = blk * 32 + 32 <= A.n;                                 // block-uniform: no dead lanes
     bool do_reset = reset_decision(A, e, gid);
     const bool active = do_reset ? (A.M.settle_steps > 0) : (A.mode == 0);         // this env runs a substep
     const float* sp = A.state + e;
@@ -276,7 +290,7 @@ __global__ void __launch_bounds__(kBlockThreads, GG_MINBLOCKS) step_kernel(const
         const bool staged = false;
 #endif
         if (staged) {
-            const float* src = A.action + (size_t)blockIdx.x * 32 * NU;
+            const float* src = A.action + (size_t)blk * 32 * NU;
             const unsigned dst = (unsigned)__cvta_generic_to_shared(X.act);
 #pragma unroll
             for (int c = lane; c < 32 * NU / 4; c += 32)
@@ -297,14 +311,14 @@ __global__ void __launch_bounds__(kBlockThreads, GG_MINBLOCKS) step_kernel(const
 #pragma unroll
         for (int i = 0; i < NU; i++) X.fs[i][lane] = fs[i];
         if (A.action_dev != nullptr && A.mode == 0) {         // device-resident copy of the consumed targets (host-I/O callers)
-            if (staged) store_slab<32 * NU / 4>(X.act, A.action_dev + (size_t)blockIdx.x * 32 * NU, nullptr, lane);
+            if (staged) store_slab<32 * NU / 4>(X.act, A.action_dev + (size_t)blk * 32 * NU, nullptr, lane);
             else if (live) {
 #pragma unroll
                 for (int i = 0; i < NU; i++) A.action_dev[(size_t)e * NU + i] = A.action[(size_t)e * NU + i];
             }
         }
         // pad broad phase against the cube state the CUBE warp published (after its masked reset)
-        bar_sync(8, 96);
+        bar_sync(8, 96 * SUB);
         const gg::V3 cp = gg::mk(X.cube[0][lane], X.cube[1][lane], X.cube[2][lane]);
         const gg::Q4 cq = gg::mkq(X.cube[3][lane], X.cube[4][lane], X.cube[5][lane], X.cube[6][lane]);
 #ifdef GG_ONLY_ROLE
@@ -313,18 +327,18 @@ __global__ void __launch_bounds__(kBlockThreads, GG_MINBLOCKS) step_kernel(const
         const bool coupled = live && gg::pads_may_touch<NA, NF>(A.M, D, cp, cq);
 #endif
         X.coupled[lane] = coupled ? 1 : 0;
-        bar_arrive(1, 96);
+        bar_arrive(1, 96 * SUB);
         const unsigned cm = __ballot_sync(0xffffffffu, coupled);
         const int ncpl = __popc(cm);
         if (ncpl > 0) {                                   // solver team 1 (see MAIN for the protocol)
-            bar_sync(4, 96);
-            team_queue<NA, NF, FH>(A, TW, TB, X, cm, ncpl, 1, lane);
-            bar_sync(5, 96);
+            bar_sync(pbar, 96);
+            team_queue<NA, NF, FH>(A, TW, TB, X, cm, ncpl, 1, lane, blk);
+            bar_sync(pbar, 96);
         }
 #ifndef GG_NO_SPLIT_EEF
         {
             // post-step refresh of the end-effector pose, second half of the chain (MAIN walks the first half meanwhile)
-            bar_sync(6, 64);
+            bar_sync(6, 64 * SUB);
             float qt[NA - KS];
 #pragma unroll
             for (int i = 0; i < NA - KS; i++) qt[i] = X.fs[KS + i][lane];
@@ -332,7 +346,7 @@ __global__ void __launch_bounds__(kBlockThreads, GG_MINBLOCKS) step_kernel(const
             gg::robot_chain_tail<NA>(A.M, qt, KS, tp, tq);
             X.tail[0][lane] = tp.x; X.tail[1][lane] = tp.y; X.tail[2][lane] = tp.z;
             X.tail[3][lane] = tq.w; X.tail[4][lane] = tq.x; X.tail[5][lane] = tq.y; X.tail[6][lane] = tq.z;
-            bar_arrive(7, 64);
+            bar_arrive(7, 64 * SUB);
         }
 #endif
         return;
@@ -361,8 +375,8 @@ __global__ void __launch_bounds__(kBlockThreads, GG_MINBLOCKS) step_kernel(const
             gg::chol_packed<NU>(L, dinv);
             float lsg[NU], laref[NU], lD[NU];
             const int nlim = gg::joint_limit_rows<NU>(A.M, q, qd, lsg, laref, lD);
-            bar_sync(8, 96);
-            bar_sync(1, 96);
+            bar_sync(8, 96 * SUB);
+            bar_sync(1, 96 * SUB);
 #pragma unroll
             for (int i = 0; i < NU; i++) D.fs[i] = X.fs[i][lane];
             float as[NU], a[NU];
@@ -411,9 +425,9 @@ __global__ void __launch_bounds__(kBlockThreads, GG_MINBLOCKS) step_kernel(const
                         for (int i = 0; i < 19; i++) W.cube[i] = X.cube[i][lane];
                     }
                     __threadfence_block();
-                    bar_sync(4, 96);
-                    team_queue<NA, NF, FH>(A, TW, TB, X, cm, ncpl, 0, lane);
-                    bar_sync(5, 96);
+                    bar_sync(pbar, 96);
+                    team_queue<NA, NF, FH>(A, TW, TB, X, cm, ncpl, 0, lane, blk);
+                    bar_sync(pbar, 96);
                 }
                 if (coupled) {
 #pragma unroll
@@ -421,7 +435,7 @@ __global__ void __launch_bounds__(kBlockThreads, GG_MINBLOCKS) step_kernel(const
                 }
             }
             if (!coupled) X.iters[lane] = info.iters;
-            bar_arrive(2, 64);
+            bar_arrive(2, 64 * SUB);
             if (active) gg::integrate_robot<NU>(A.M, q, qd, qa, a);
         }
         gg::V3 ep; gg::Q4 eq;
@@ -431,10 +445,10 @@ __global__ void __launch_bounds__(kBlockThreads, GG_MINBLOCKS) step_kernel(const
 #pragma unroll
             for (int i = KS; i < NA; i++) X.fs[i][lane] = q[i];
             __threadfence_block();
-            bar_sync(6, 64);
+            bar_sync(6, 64 * SUB);
             gg::Q4 ql; gg::V3 pl; gg::M3 Rl;
             gg::robot_chain_head<NA>(A.M, q, KS, ql, pl, Rl);
-            bar_sync(7, 64);
+            bar_sync(7, 64 * SUB);
             gg::compose_eef(ql, pl, Rl, gg::mk(X.tail[0][lane], X.tail[1][lane], X.tail[2][lane]),
                             gg::mkq(X.tail[3][lane], X.tail[4][lane], X.tail[5][lane], X.tail[6][lane]), ep, eq);
         } else
@@ -448,7 +462,7 @@ __global__ void __launch_bounds__(kBlockThreads, GG_MINBLOCKS) step_kernel(const
         }
         X.ep[0][lane] = ep.x; X.ep[1][lane] = ep.y; X.ep[2][lane] = ep.z;
         __threadfence_block();
-        bar_sync(3, 64);
+        bar_sync(3, 64 * SUB);
         const bool bad = (X.bad[0][lane] | X.bad[1][lane]) != 0;
         if (__any_sync(0xffffffffu, bad)) {              // diverged env: re-spawn (rare; both roles take this branch together)
             // NOTE: the home pose goes into a FRESH array selected element-wise; conditionally overwriting q[] in place
@@ -464,7 +478,7 @@ __global__ void __launch_bounds__(kBlockThreads, GG_MINBLOCKS) step_kernel(const
             X.ep[0][lane] = ep.x; X.ep[1][lane] = ep.y; X.ep[2][lane] = ep.z;
             do_reset = do_reset || bad;
             __threadfence_block();
-            bar_sync(3, 64);
+            bar_sync(pbar, 64);
         }
         if (full && A.vec_out) {
             // agent_pos rows staged in shared memory (row stride AD words: conflict free for the Panda's 9, a 4-way conflict on
@@ -474,8 +488,8 @@ __global__ void __launch_bounds__(kBlockThreads, GG_MINBLOCKS) step_kernel(const
 #pragma unroll
             for (int f = 0; f < NF; f++) r[7 + f] = q[NA + f];
             __syncwarp();
-            store_slab<32 * AD / 4>(X.oa, A.obs_agent + (size_t)blockIdx.x * 32 * AD,
-                                    A.obs_agent_host ? A.obs_agent_host + (size_t)blockIdx.x * 32 * AD : nullptr, lane);
+            store_slab<32 * AD / 4>(X.oa, A.obs_agent + (size_t)blk * 32 * AD,
+                                    A.obs_agent_host ? A.obs_agent_host + (size_t)blk * 32 * AD : nullptr, lane);
         } else if (commit) {
             float* oa = A.obs_agent + (size_t)e * AD;
             oa[0] = ep.x; oa[1] = ep.y; oa[2] = ep.z; oa[3] = eq.w; oa[4] = eq.x; oa[5] = eq.y; oa[6] = eq.z;
@@ -526,7 +540,7 @@ __global__ void __launch_bounds__(kBlockThreads, GG_MINBLOCKS) step_kernel(const
             X.cube[10][lane] = cw.x; X.cube[11][lane] = cw.y; X.cube[12][lane] = cw.z;
 #pragma unroll
             for (int i = 0; i < 6; i++) X.cube[13 + i][lane] = qac[i];
-            bar_arrive(8, 96);
+            bar_arrive(8, 96 * SUB);
             float Mc[6], as_c[6], qd_c[6], a_c[6];
             gg::cube_free_acc(A.M, cv, cw, Mc, as_c, qd_c);
             gg::StepInfo ic; ic.ncon = 0; ic.iters = 0; ic.grad = 0.f;
@@ -538,18 +552,18 @@ __global__ void __launch_bounds__(kBlockThreads, GG_MINBLOCKS) step_kernel(const
                 cs.b = reinterpret_cast<float*>(TB) + gg::LinkStoreStrided<NA>::FLOATS * 32 + lane;
                 gg::cube_block_solve(A.M, cp, gg::qmat(cq), Mc, as_c, qd_c, qac, a_c, A.iterations, A.tol, cs, ic);
             }
-            bar_sync(1, 96);
+            bar_sync(1, 96 * SUB);
             const bool coupled = X.coupled[lane] != 0;
             {
                 const unsigned cm = __ballot_sync(0xffffffffu, coupled);
                 const int ncpl = __popc(cm);
                 if (ncpl > 0) {                               // solver team 2 (see MAIN for the protocol)
-                    bar_sync(4, 96);
-                    team_queue<NA, NF, FH>(A, TW, TB, X, cm, ncpl, 2, lane);
-                    bar_sync(5, 96);
+                    bar_sync(pbar, 96);
+                    team_queue<NA, NF, FH>(A, TW, TB, X, cm, ncpl, 2, lane, blk);
+                    bar_sync(pbar, 96);
                 }
             }
-            bar_sync(2, 64);
+            bar_sync(2, 64 * SUB);
             if (coupled) {
 #pragma unroll
                 for (int i = 0; i < 6; i++) a_c[i] = X.aout[NU + i][lane];
@@ -566,7 +580,7 @@ __global__ void __launch_bounds__(kBlockThreads, GG_MINBLOCKS) step_kernel(const
             X.bad[1][lane] = (run_sub && active && commit && !isfinite(acc)) ? 1 : 0;
         }
         __threadfence_block();
-        bar_sync(3, 64);
+        bar_sync(3, 64 * SUB);
         const bool bad = (X.bad[0][lane] | X.bad[1][lane]) != 0;
         if (__any_sync(0xffffffffu, bad)) {
             if (bad) {
@@ -579,7 +593,7 @@ __global__ void __launch_bounds__(kBlockThreads, GG_MINBLOCKS) step_kernel(const
                 epi += 1; steps = 0; st_nan = 1.f;
                 do_reset = true;
             }
-            bar_sync(3, 64);
+            bar_sync(pbar, 64);
         }
         const gg::V3 ep = gg::mk(X.ep[0][lane], X.ep[1][lane], X.ep[2][lane]);
         if (A.mode == 0 && !do_reset) { steps += 1; st_steps = 1.f; }
@@ -593,8 +607,8 @@ __global__ void __launch_bounds__(kBlockThreads, GG_MINBLOCKS) step_kernel(const
             r[0] = cp.x; r[1] = cp.y; r[2] = cp.z; r[3] = cq.w; r[4] = cq.x; r[5] = cq.y; r[6] = cq.z;
             r[7] = d.x; r[8] = d.y; r[9] = d.z; r[10] = dn;
             __syncwarp();
-            store_slab<32 * GG_ENV_STATE_DIM / 4>(X.oe, A.obs_env + (size_t)blockIdx.x * 32 * GG_ENV_STATE_DIM,
-                                                  A.obs_env_host ? A.obs_env_host + (size_t)blockIdx.x * 32 * GG_ENV_STATE_DIM : nullptr, lane);
+            store_slab<32 * GG_ENV_STATE_DIM / 4>(X.oe, A.obs_env + (size_t)blk * 32 * GG_ENV_STATE_DIM,
+                                                  A.obs_env_host ? A.obs_env_host + (size_t)blk * 32 * GG_ENV_STATE_DIM : nullptr, lane);
         } else if (commit) {
             float* oe = A.obs_env + (size_t)e * GG_ENV_STATE_DIM;
             oe[0] = cp.x; oe[1] = cp.y; oe[2] = cp.z; oe[3] = cq.w; oe[4] = cq.x; oe[5] = cq.y; oe[6] = cq.z;
@@ -1076,7 +1090,7 @@ struct GgSim {
     uint8_t* done; double* stats;       // library-owned (allocated once in gg_create)
     float* team_scratch;                // library-owned: published dynamics of coupled envs (step_kernel solver teams)
     float* mbox; uint32_t* mflag; int* ctl; int* clist; uint32_t* cready;   // library-owned: role-per-SM kernel mailboxes / coupled list
-    uint32_t epoch; int n_sm; int use_blocks; int use_mono; int64_t list_budget;   // launch epoch of the mailbox flags; SM count; 1 = round-1 block kernel (GG_STEP_KERNEL=blocks)
+    uint32_t epoch; int n_sm; int use_blocks; int use_mono; int sub; int64_t list_budget;   // launch epoch of the mailbox flags; SM count; 1 = round-1 block kernel (GG_STEP_KERNEL=blocks)
     int32_t* slot;                      // library-owned, allocated on first gg_export_successful: env -> compacted episode slot
     uint32_t step_index;
     GgPinCache pins;                    // address ranges already verified as pinned host memory (gg_step_host)
@@ -1149,6 +1163,16 @@ int gg_internal_export(int device, int n, int stride, int F, int32_t** slot, con
     return 0;
 }
 
+template <int SUB> static void launch_roles(int kind, int ngroups, const StepArgs& A, cudaStream_t stream) {
+    const int grid = (ngroups + SUB - 1) / SUB;
+    if (kind == 0) step_kernel<7, 2, false, SUB><<<grid, kBlockThreads * SUB, SUB * sizeof(StepSmem<7, 2>), stream>>>(A);
+    else step_kernel<5, 1, true, SUB><<<grid, kBlockThreads * SUB, SUB * sizeof(StepSmem<5, 1>), stream>>>(A);
+}
+template <int SUB> static void prepare_roles() {
+    cudaFuncSetAttribute((const void*)step_kernel<7, 2, false, SUB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SUB * sizeof(StepSmem<7, 2>)));
+    cudaFuncSetAttribute((const void*)step_kernel<5, 1, true, SUB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SUB * sizeof(StepSmem<5, 1>)));
+}
+
 static int launch_step(GgSim* sim, StepArgs& A, gg_stream_t stream) {
     if (sim->state == nullptr) return fail("gg_bind_state has not been called%s");
     A.M = sim->model; gg::make_chain(A.M, A.C); A.n = sim->n; A.stride = sim->stride;
@@ -1197,9 +1221,12 @@ static int launch_step(GgSim* sim, StepArgs& A, gg_stream_t stream) {
         else step_mono_kernel<5, 1, true><<<grid, kMonoThreads, 0, (cudaStream_t)stream>>>(A);
     } else {
         // latency regime: 32 envs x 3 role warps per block
-        const int grid = (sim->n + 31) / 32;
-        if (sim->kind == 0) step_kernel<7, 2, false><<<grid, kBlockThreads, 0, (cudaStream_t)stream>>>(A);
-        else step_kernel<5, 1, true><<<grid, kBlockThreads, 0, (cudaStream_t)stream>>>(A);
+        const int ngroups = (sim->n + 31) / 32;
+        switch (sim->sub) {
+        case 4: launch_roles<4>(sim->kind, ngroups, A, (cudaStream_t)stream); break;
+        case 2: launch_roles<2>(sim->kind, ngroups, A, (cudaStream_t)stream); break;
+        default: launch_roles<1>(sim->kind, ngroups, A, (cudaStream_t)stream); break;
+        }
     }
     g_launches.fetch_add(1);
     GG_CUDA(cudaGetLastError());
@@ -1256,6 +1283,13 @@ int gg_create(const GgModel* model, int n_envs, int device, GgSim** out) {
         s->use_mono = n_envs >= kMonoEnvsPerSm * s->n_sm;
         if (k && strcmp(k, "mono") == 0) s->use_mono = 1;
         if (k && strcmp(k, "roles") == 0) s->use_mono = 0;
+        // groups of 32 envs per block of the role kernel.  Wider blocks (GG_STEP_SUB=2 / 4: the same-role warps of a block meet at
+        // SUB-times wider named barriers and run their instruction stream in step) were measured at 4096 .. 24576 envs and change
+        // nothing (16384 envs: 35.4 / 35.6 / 36.1 us for 1 / 2 / 4, profiles/r02_notes.md), so one group per block stays the default
+        s->sub = 1;
+        const char* sb = getenv("GG_STEP_SUB");
+        if (sb && (atoi(sb) == 1 || atoi(sb) == 2 || atoi(sb) == 4)) s->sub = atoi(sb);
+        prepare_roles<1>(); prepare_roles<2>(); prepare_roles<4>();
     }
 #ifdef GG_WITH_RS_KERNEL
     {
