@@ -3,7 +3,7 @@
 // Newton with exact line search, same stop criteria) mapped onto 32 lanes:
 //   * narrow phase          lane = pad box (plane-box and box-box run concurrently for all pads), ordered compaction
 //   * per-contact rows      lane = contact (2 per lane at the 64-contact cap): residuals x = J a - aref live in registers
-//   * pair stiffness        lane = one of the 21 + 6 entries of (Phi, gF) of a body pair, looping over the contacts
+//   * pair stiffness        lane = (row i of (Phi, gF) of a body pair, one of five contact subsets); fixed-order sum of the five partials
 //   * projection            lane = dof for Y = Phi B_j, then lane = Hessian entry (4 per lane) for H += B_i . Y_j
 //   * Cholesky / solves     lane = row of the 15 x 15 factor kept in registers, columns broadcast with shuffles
 //   * line search           every lane evaluates its own limit row / contacts, butterfly reduction of (phi', phi'')
@@ -39,6 +39,8 @@ template <int NV> struct TeamBuf {
                                   // (a [contact][8] layout is an 8-way bank conflict), the readers broadcast one contact
     float depth[GG_MAX_CONTACTS];
     int code[GG_MAX_CONTACTS];
+    int perm[GG_MAX_CONTACTS];        // contact indices grouped by body pair (stable), see team_solve
+    float part[5 * 42];               // partial pair-stiffness sums of the five contact subsets
     float TB[NV][6];                  // twist of every dof about O (angular, linear)
     float T[3][7][6];                 // relative pair twists for qd / warm start / a_smooth (slot 2 reused for the search direction)
     float Phi[7][21], gF[7][6];
@@ -290,6 +292,51 @@ __device__ __noinline__ void team_solve(const GgModel& M, const TeamWork<NA, NF>
             for (int k = 0; k < 4; k++) x[s][k] = jv[s][k];
     }
 
+    // ---- contacts grouped by body pair (stable counting sort; the narrow phase emits them pair after pair already unless the
+    //      model lists its pads out of body order): perm = contact indices pair after pair, lane pc keeps the range of pair pc
+    int pstart = 0, pcnt = 0;
+    {
+        const int c0 = lane < ncon ? B.code[lane] : 31, c1 = lane + 32 < ncon ? B.code[lane + 32] : 31;
+        const unsigned lt = (1u << lane) - 1u;
+        int r0 = 0, r1 = 0, run = 0;
+#pragma unroll
+        for (int pc = 0; pc < 7; pc++) {
+            const unsigned b0 = __ballot_sync(kFull, c0 == pc), b1 = __ballot_sync(kFull, c1 == pc);
+            const int n0 = __popc(b0), n1 = __popc(b1);
+            if (c0 == pc) r0 = run + __popc(b0 & lt);
+            if (c1 == pc) r1 = run + n0 + __popc(b1 & lt);
+            if (lane == pc) { pstart = run; pcnt = n0 + n1; }
+            run += n0 + n1;
+        }
+        if (lane < ncon) B.perm[r0] = lane;
+        if (lane + 32 < ncon) B.perm[r1] = lane + 32;
+    }
+    // packed Hessian entries owned by this lane (4 per lane) and their constant part (mass matrix / cube inertia)
+    float Hbase[4];
+    int hi[4], hj[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int e = lane + 32 * k;
+        int i = (int)((sqrtf(8.f * (float)e + 1.f) - 1.f) * 0.5f);
+        if ((i + 1) * (i + 2) / 2 <= e) i++;                     // guard the float round-off of the closed form
+        if (i * (i + 1) / 2 > e) i--;
+        hi[k] = i; hj[k] = e - i * (i + 1) / 2;
+        float base = 0.f;
+        if (e < NH) {
+            if (i < NU) base = W.Mt[e];                          // robot block shares the packed index
+            else if (hj[k] == i) base = (i - NU < 3) ? M.cube_mass : M.cube_inertia[i - NU - 3];
+        }
+        Hbase[k] = base;
+    }
+    // pair-stiffness lanes: row pi of (Phi | gF), contact subset pg (lanes 30, 31 idle); entry (ei, ej) for the final sum
+    const int pi = lane % 6, pg = lane / 6;
+    int ei = 0, ej = 0;
+    if (lane < 21) {
+        ei = lane < 1 ? 0 : (lane < 3 ? 1 : (lane < 6 ? 2 : (lane < 10 ? 3 : (lane < 15 ? 4 : 5))));
+        ej = lane - ei * (ei + 1) / 2;
+    } else if (lane < 27) { ei = lane - 21; ej = 6; }
+    __syncwarp();
+
     int it = 0;
 #pragma unroll 1
     for (; it < iterations; it++) {
@@ -300,9 +347,7 @@ __device__ __noinline__ void team_solve(const GgModel& M, const TeamWork<NA, NF>
             const float jar = lsg_d * a_d - laref_d;
             if (lsg_d != 0.f && jar < 0.f) { hlim = lD_d; g_d += lD_d * jar * lsg_d; }
         }
-        // ---- stage the per-contact weights, clear the pair accumulators
-        for (int i = lane; i < 7 * 21; i += 32) (&B.Phi[0][0])[i] = 0.f;
-        for (int i = lane; i < 7 * 6; i += 32) (&B.gF[0][0])[i] = 0.f;
+        // ---- stage the per-contact weights
 #pragma unroll
         for (int s = 0; s < 2; s++) {
             const int c = lane + 32 * s;
@@ -323,52 +368,43 @@ __device__ __noinline__ void team_solve(const GgModel& M, const TeamWork<NA, NF>
             }
         }
         __syncwarp();
-        // ---- pair stiffness in spatial-force space: lane < 21 owns Phi entry (i, j), lanes 21..26 own gF[i]
+        // ---- pair stiffness in spatial-force space, Phi = sum_c F_c^T W_c F_c, gF = sum_c F_c^T g_c per body pair: lane (pi, pg) sums
+        //      row pi over the contacts pg, pg + 5, ... of the pair; the five partials are added in a fixed order (bit-reproducible)
         {
-            int ei = 0, ej = 0;
-            if (lane < 21) {
-                ei = lane < 1 ? 0 : (lane < 3 ? 1 : (lane < 6 ? 2 : (lane < 10 ? 3 : (lane < 15 ? 4 : 5))));
-                ej = lane - ei * (ei + 1) / 2;
-            } else if (lane < 27) ei = lane - 21;
-            float acc = 0.f;
-            int cur = -1;
+            float* part = B.part;
 #pragma unroll 1
-            for (int c = 0; c < ncon; c++) {
-                if (B.Wc[0][c] == 0.f) continue;                // no active row (uniform across the warp)
-                const float w[8] = {B.Wc[0][c], B.Wc[1][c], B.Wc[2][c], B.Wc[3][c], B.Wc[4][c], B.Wc[5][c], B.Wc[6][c], B.Wc[7][c]};
-                const int code = B.code[c];
-                if (code != cur) {
-                    if (cur >= 0) { if (lane < 21) B.Phi[cur][lane] += acc; else if (lane < 27) B.gF[cur][lane - 21] += acc; }
-                    cur = code; acc = 0.f;
+            for (int pc = 0; pc < 7; pc++) {
+                if (!((used >> pc) & 1u)) continue;
+                const int s0 = __shfl_sync(kFull, pstart, pc), n = __shfl_sync(kFull, pcnt, pc);
+                if (pg < 5) {
+                    float acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, accg = 0.f;
+                    for (int k = pg; k < n; k += 5) {
+                        const int c = B.perm[s0 + k];
+                        const float w0 = B.Wc[0][c], w1 = B.Wc[1][c], w2 = B.Wc[2][c], w3 = B.Wc[3][c], w4 = B.Wc[4][c];
+                        const float* f = B.F[c];
+                        const float fni = f[pi], f1i = f[6 + pi], f2i = f[12 + pi];
+                        const float a = w0 * fni + w1 * f1i + w3 * f2i, b = w1 * fni + w2 * f1i, cc = w3 * fni + w4 * f2i;
+#pragma unroll
+                        for (int j = 0; j < 6; j++) acc[j] += a * f[j] + b * f[6 + j] + cc * f[12 + j];
+                        accg += fni * B.Wc[5][c] + f1i * B.Wc[6][c] + f2i * B.Wc[7][c];
+                    }
+#pragma unroll
+                    for (int j = 0; j < 6; j++) part[pg * 42 + pi * 7 + j] = acc[j];
+                    part[pg * 42 + pi * 7 + 6] = accg;
                 }
-                const float* f = B.F[c];
-                const float fni = f[ei], f1i = f[6 + ei], f2i = f[12 + ei];
-                if (lane < 21) {
-                    const float fnj = f[ej], f1j = f[6 + ej], f2j = f[12 + ej];
-                    acc += fni * (w[0] * fnj + w[1] * f1j + w[3] * f2j) + f1i * (w[1] * fnj + w[2] * f1j) + f2i * (w[3] * fnj + w[4] * f2j);
-                } else {
-                    acc += fni * w[5] + f1i * w[6] + f2i * w[7];
+                __syncwarp();
+                if (lane < 27) {
+                    const int idx = ei * 7 + ej;
+                    const float v = (((part[idx] + part[42 + idx]) + part[84 + idx]) + part[126 + idx]) + part[168 + idx];
+                    if (lane < 21) B.Phi[pc][lane] = v; else B.gF[pc][lane - 21] = v;
                 }
+                __syncwarp();
             }
-            if (cur >= 0) { if (lane < 21) B.Phi[cur][lane] += acc; else if (lane < 27) B.gF[cur][lane - 21] += acc; }
         }
-        __syncwarp();
         // ---- project every used pair onto its dofs: H += P^T Phi P, g += P^T gF
         float Hacc[4];
-        int hi[4], hj[4];
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
-            const int e = lane + 32 * k;
-            int i = 0;
-            while ((i + 1) * (i + 2) / 2 <= e) i++;              // row of packed entry e
-            hi[k] = i; hj[k] = e - i * (i + 1) / 2;
-            float base = 0.f;
-            if (e < NH) {
-                if (i < NU) base = W.Mt[e];                      // robot block shares the packed index
-                else if (hj[k] == i) base = (i - NU < 3) ? M.cube_mass : M.cube_inertia[i - NU - 3];
-            }
-            Hacc[k] = base;
-        }
+        for (int k = 0; k < 4; k++) Hacc[k] = Hbase[k];
 #pragma unroll 1
         for (int pc = 0; pc < 7; pc++) {
             if (!((used >> pc) & 1u)) continue;

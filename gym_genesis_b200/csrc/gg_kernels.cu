@@ -668,10 +668,13 @@ __global__ void __launch_bounds__(kBlockThreads * SUB, GG_MINBLOCKS / SUB) step_
 // functions, same arithmetic per env, same coupled-env list / drain; launch_step picks the kernel by env count.
 // ------------------------------------------------------------------------------------------------
 constexpr int kMonoThreads = 64;
+#ifndef GG_MONO_MINBLOCKS
+#define GG_MONO_MINBLOCKS 4
+#endif
 constexpr int kMonoEnvsPerSm = 200;    // >= 200 envs per SM (29600 envs on a B200): thread-per-env kernel (measured cross-over ~28 k)
 
 template <int NA, int NF, bool FH>
-__global__ void __launch_bounds__(kMonoThreads) step_mono_kernel(const __grid_constant__ StepArgs A) {
+__global__ void __launch_bounds__(kMonoThreads, GG_MONO_MINBLOCKS) step_mono_kernel(const __grid_constant__ StepArgs A) {
     constexpr int NU = NA + NF, NV = NU + 6, AD = 7 + NF;
     __shared__ gg::TeamWork<NA, NF> TW[kMonoThreads / 32];
     __shared__ gg::TeamBuf<NV> TB[kMonoThreads / 32];
