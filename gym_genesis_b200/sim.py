@@ -23,6 +23,48 @@ def _ptr(t: Optional[torch.Tensor]):
     return None if t is None else C.c_void_p(t.data_ptr())
 
 
+def _storage_uses(t) -> int:
+    return torch._C._storage_Use_Count(t.untyped_storage()._cdata)
+
+
+class _SlabRing:
+    """Hands out per-step tensor sets cut from K-step slabs and recycles a slab once nobody references its storage any more."""
+    MAX_SLABS = 4
+
+    def __init__(self, make_bases, split):
+        self.make_bases, self.split = make_bases, split
+        self.slabs = []             # [base tensors, storage use counts with no views alive]
+        self.cur = -1
+        self.pool = []
+
+    def next(self):
+        if not self.pool:
+            n = len(self.slabs)
+            for i in range(1, n + 1):               # the other slabs first: the current one still backs the latest results
+                j = (self.cur + i) % n
+                bases, idle = self.slabs[j]
+                if all(_storage_uses(b) <= c for b, c in zip(bases, idle)):
+                    self.cur = j
+                    break
+            else:
+                bases = self.make_bases()
+                slab = [bases, [_storage_uses(b) for b in bases]]
+                if n == 0:
+                    # a steady loop alternates between two slabs: make both on the first call (the caller's warm-up), so that no
+                    # allocation (pinned slabs: milliseconds of page locking) lands K steps into a loop somebody is timing
+                    spare = self.make_bases()
+                    self.slabs.append([spare, [_storage_uses(b) for b in spare]])
+                    n = 1
+                if n < self.MAX_SLABS:
+                    self.slabs.append(slab)
+                    self.cur = n
+                else:                               # the caller keeps old results alive: they own those slabs now
+                    self.cur = (self.cur + 1) % n
+                    self.slabs[self.cur] = slab
+            self.pool = self.split(self.slabs[self.cur][0])
+        return self.pool.pop()
+
+
 class BatchedSim:
     """N independent worlds (arm + gripper + free cube + plane) stepped by one CUDA kernel per env.step.
 
@@ -125,8 +167,11 @@ class BatchedSim:
     # fresh_outputs=True: every step / reset writes into output tensors nobody has seen before, so tensors returned earlier keep their
     # values -- the reference's getters return fresh tensors (franka/cube_pick.py:137-157) and its collectors append them step after
     # step (examples/franka/pick_cube_state.py:86-100).  Creating five tensors per step costs ~25 us of host time (allocator + Python
-    # tensor objects), as much as the step kernel itself; so the sets are made in BATCHES: one allocation per output kind for K steps,
-    # split into K views by a single unbind() call, and a step just takes the next set.  The default (False) reuses one set of buffers:
+    # tensor objects), as much as the step kernel itself; so the sets are made in SLABS: one allocation per output kind for K steps,
+    # split into K views by a single unbind() call, and a step just takes the next set.  Slabs are recycled (`_SlabRing`): once every
+    # view of a slab has been dropped by the caller -- the storage use count is back to its baseline -- the slab is split again, so a
+    # steady loop allocates nothing (pinned allocations are driver calls that take milliseconds when several ranks share a host).
+    # A caller that keeps results simply makes the ring allocate new slabs.  The default (False) reuses one set of buffers:
     # zero allocation, CUDA-graph safe.
     _POOL_BYTES = 64 << 20
 
@@ -134,32 +179,53 @@ class BatchedSim:
         per_step = self.n_envs * (self.agent_dim + self.env_dim + 1) * 4 + 2 * self.n_envs
         return int(max(1, min(32, self._POOL_BYTES // per_step)))
 
+    def _ring(self, name, make, split):
+        r = self.__dict__.get(name)
+        if r is None:
+            r = self.__dict__[name] = _SlabRing(make, split)
+        return r
+
     def _new_outputs(self):
-        pool = getattr(self, "_out_pool", None)
-        if not pool:
+        def make():
             n, dev, K = self.n_envs, self.device, self._pool_size()
-            A = torch.empty((K, n, self.agent_dim), dtype=torch.float32, device=dev).unbind(0)
-            E = torch.empty((K, n, self.env_dim), dtype=torch.float32, device=dev).unbind(0)
-            R = torch.empty((K, n), dtype=torch.float32, device=dev).unbind(0)
-            F = torch.empty((2, K, n), dtype=torch.bool, device=dev)
-            T, U = F[0].unbind(0), F[1].unbind(0)
-            pool = self._out_pool = [(A[k], E[k], R[k], T[k], U[k], (A[k].data_ptr(), E[k].data_ptr(), R[k].data_ptr(), T[k].data_ptr(),
-                                                                    U[k].data_ptr())) for k in range(K)]
-        self.obs_agent, self.obs_env, self.reward, self.terminated, self.truncated, self._out_ptrs = pool.pop()
+            return (torch.empty((K, n, self.agent_dim), dtype=torch.float32, device=dev), torch.empty((K, n, self.env_dim), dtype=torch.float32, device=dev),
+                    torch.empty((K, n), dtype=torch.float32, device=dev), torch.empty((2, K, n), dtype=torch.bool, device=dev))
+
+        def split(bases):
+            A, E, R = (b.unbind(0) for b in bases[:3])
+            T, U = bases[3][0].unbind(0), bases[3][1].unbind(0)
+            return [(A[k], E[k], R[k], T[k], U[k], (A[k].data_ptr(), E[k].data_ptr(), R[k].data_ptr(), T[k].data_ptr(), U[k].data_ptr()))
+                    for k in range(len(A))]
+        self.obs_agent, self.obs_env, self.reward, self.terminated, self.truncated, self._out_ptrs = self._ring("_out_ring", make, split).next()
 
     def _new_host_results(self):
-        """Same batching for the pinned host mirrors of step_host: the kernel writes each step's results into a pinned slot nobody has
+        """Same slabs for the pinned host mirrors of step_host: the kernel writes each step's results into a pinned slot nobody has
         seen before, so the returned CPU tensors are fresh without a copy."""
-        pool = getattr(self, "_host_pool", None)
-        if not pool:
+        def make():
             n, K = self.n_envs, self._pool_size()
-            R = torch.empty((K, n), dtype=torch.float32, pin_memory=True).unbind(0)
-            F = torch.empty((2, K, n), dtype=torch.bool, pin_memory=True)
-            T, U = F[0].unbind(0), F[1].unbind(0)
-            pool = self._host_pool = [(R[k], T[k], U[k], R[k].data_ptr(), T[k].data_ptr(), U[k].data_ptr()) for k in range(K)]
-        r, t, u, pr, pt, pu = pool.pop()
+            return (torch.empty((K, n), dtype=torch.float32, pin_memory=True), torch.empty((2, K, n), dtype=torch.bool, pin_memory=True))
+
+        def split(bases):
+            R, T, U = bases[0].unbind(0), bases[1][0].unbind(0), bases[1][1].unbind(0)
+            return [(R[k], T[k], U[k], R[k].data_ptr(), T[k].data_ptr(), U[k].data_ptr()) for k in range(len(R))]
+        r, t, u, pr, pt, pu = self._ring("_host_ring", make, split).next()
         self._hio.reward, self._hio.terminated, self._hio.truncated = pr, pt, pu
         self._host["reward"], self._host["terminated"], self._host["truncated"] = r, t, u
+
+    def _new_host_obs(self):
+        """Fresh pinned observation mirrors (host_obs=True callers): the kernel writes agent_pos / environment_state of the step
+        straight into them, so a host-resident policy gets fresh CPU tensors without a copy."""
+        def make():
+            n, K = self.n_envs, self._pool_size()
+            return (torch.empty((K, n, self.agent_dim), dtype=torch.float32, pin_memory=True),
+                    torch.empty((K, n, self.env_dim), dtype=torch.float32, pin_memory=True))
+
+        def split(bases):
+            A, E = bases[0].unbind(0), bases[1].unbind(0)
+            return [(A[k], E[k], A[k].data_ptr(), E[k].data_ptr()) for k in range(len(A))]
+        a, e, pa, pe = self._ring("_host_obs_ring", make, split).next()
+        self._host["obs_agent"], self._host["obs_env"] = a, e
+        self._host_obs_ptrs = (pa, pe)
 
     def step(self, action, reset_mask=None):
         """One env.step (= one 0.01 s substep) for all envs; results land in the obs_agent / obs_env / reward / terminated /
@@ -224,8 +290,14 @@ class BatchedSim:
         self._last_action = self._targets_dev      # filled by the kernel from the batch it consumed
         self._hio.action = a.data_ptr()
         self._hio.wait = 1 if wait else 0
-        self._hio.obs_agent = h["obs_agent"].data_ptr() if host_obs else None
-        self._hio.obs_env = h["obs_env"].data_ptr() if host_obs else None
+        if host_obs:
+            if self.fresh_outputs:
+                self._new_host_obs()
+            elif getattr(self, "_host_obs_ptrs", None) is None:
+                self._host_obs_ptrs = (h["obs_agent"].data_ptr(), h["obs_env"].data_ptr())
+            self._hio.obs_agent, self._hio.obs_env = self._host_obs_ptrs
+        else:
+            self._hio.obs_agent = self._hio.obs_env = None
         rc = self._step_host_fn()(self._h, self._hio_ref, *self._out_ptrs, _ptr(m), self._stream())
         if rc != 0:
             self._check(rc)

@@ -191,10 +191,9 @@ class CubePickBatch:
 
     def get_obs_host(self):
         """Pinned host mirrors of the observations written by the last `step_host(..., host_obs=True)`."""
-        oa, oe = self.sim.host_obs_agent, self.sim.host_obs_env     # persistent pinned mirrors, overwritten by the next step
-        if not self.alias_outputs:
-            oa, oe = oa.clone(), oe.clone()
-        return {"agent_pos": oa, "environment_state": oe}
+        # alias_outputs: persistent pinned mirrors, overwritten by the next step; default: pinned slots nobody has seen before
+        # (the kernel wrote them directly, no copy)
+        return {"agent_pos": self.sim.host_obs_agent, "environment_state": self.sim.host_obs_env}
 
     def compute_reward(self):
         return self.sim.reward

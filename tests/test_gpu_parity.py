@@ -440,3 +440,35 @@ def test_host_io_masked_reset_push_and_control_after_host_step():
     for x, y in zip(env._env.sim.get_state(), ref._env.sim.get_state()):
         assert torch.equal(x, y)
     env.close(); ref.close()
+
+
+def test_fresh_host_results_and_observations_without_steady_state_allocation():
+    """Default (fresh) outputs on the host-I/O path: reward / flags / host observations of a step keep their values after later steps,
+    and a loop that drops its results recycles a bounded set of slabs (sim.py: _SlabRing) instead of allocating."""
+    import gym_genesis  # noqa: F401
+    from gym_genesis_b200.gym_api import gym
+    n = 64
+    rng = np.random.default_rng(4)
+    env = gym.make("gym_genesis/CubePick-v0", robot="franka", num_envs=n, host_io=True, host_obs=True).unwrapped
+    env.reset(seed=2)
+    acts = [torch.as_tensor(f32(mdl.FRANKA_HOME + rng.uniform(-0.3, 0.3, (n, 9)))).pin_memory() for _ in range(3)]
+    held = []
+    for a in acts:
+        obs, reward, term, trunc, info = env.step(a)
+        assert obs["agent_pos"].device.type == "cpu" and obs["agent_pos"].is_pinned()
+        held.append((obs, {k: v.clone() for k, v in obs.items()}, reward, reward.clone()))
+    for obs, oc, r, rc in held:
+        assert all(torch.equal(obs[k], oc[k]) for k in obs) and torch.equal(r, rc)
+    assert not torch.equal(held[0][0]["agent_pos"], held[2][0]["agent_pos"])
+    sim = env._env.sim
+    del held, obs, reward, term, trunc
+    K = sim._pool_size()
+    for k in range(5 * K):
+        env.step(acts[k % 3])
+    rings = [sim._out_ring, sim._host_ring, sim._host_obs_ring]
+    assert all(len(r.slabs) <= 3 for r in rings), [len(r.slabs) for r in rings]
+    ids = [[id(s[0][0]) for s in r.slabs] for r in rings]
+    for k in range(5 * K):
+        env.step(acts[k % 3])
+    assert ids == [[id(s[0][0]) for s in r.slabs] for r in rings]           # the same slabs again: nothing was allocated
+    env.close()

@@ -15,7 +15,8 @@
 #   ncu_stack    ncu --set full of the stacking solver (random workload)
 #   stack        tools/stack_bench.py at 16384 / 131072 envs
 #   sanitize     compute-sanitizer memcheck + racecheck on the pick and stack kernels
-#   c5           BASELINE configs[4]: --total-envs 131072 on the visible GPUs (run under gpurun --gpus N with torchrun)
+#   multi / c5   NG=N: the driver's torchrun launch line on N GPUs (run under gpurun --gpus N): default workload (weak scaling) /
+#                BASELINE configs[4] --total-envs 131072 (strong scaling); headline legs only
 TAG=${1:-run}; shift
 mkdir -p gpurun_out
 O=gpurun_out/${TAG}
@@ -52,6 +53,12 @@ for stage in "$@"; do
               timeout 600 python tools/stack_bench.py --envs 131072 --steps 60 --warmup 10 > ${O}_stack_bench_131k.json; cut -c1-300 ${O}_stack_bench_131k.json ;;
     sanitize) timeout 900 compute-sanitizer --tool memcheck --print-limit 20 python tools/sanitize_stack.py > ${O}_memcheck.log 2>&1; tail -3 ${O}_memcheck.log
               timeout 900 compute-sanitizer --tool racecheck --racecheck-report analysis --print-limit 20 python tools/sanitize_stack.py > ${O}_racecheck.log 2>&1; tail -2 ${O}_racecheck.log ;;
+    multi)    NG=${NG:-2}; LITE="--no-workload-b --no-workload-c --no-config4 --no-workload-d --no-config2 --no-cpu-baseline"
+              timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus $NG $LITE \
+                > ${O}_bench_${NG}gpu.json 2> ${O}_bench_${NG}gpu.err; tail -c 900 ${O}_bench_${NG}gpu.json; tail -2 ${O}_bench_${NG}gpu.err ;;
+    c5)       NG=${NG:-2}; LITE="--no-workload-b --no-workload-c --no-config4 --no-workload-d --no-config2 --no-cpu-baseline"
+              timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29519 bench.py --gpus $NG --total-envs 131072 $LITE \
+                > ${O}_c5_${NG}gpu.json 2> ${O}_c5_${NG}gpu.err; tail -c 900 ${O}_c5_${NG}gpu.json; tail -2 ${O}_c5_${NG}gpu.err ;;
     *)        echo "unknown stage $stage" ;;
   esac
 done
