@@ -12,6 +12,14 @@
 
 namespace gg {
 
+GG_HD int popc32(unsigned v) {
+#if defined(__CUDA_ARCH__)
+    return __popc(v);
+#else
+    return __builtin_popcount(v);
+#endif
+}
+
 struct V3 { float x, y, z; };
 GG_HD V3 mk(float x, float y, float z) { V3 r; r.x = x; r.y = y; r.z = z; return r; }
 GG_HD V3 ld3(const float* p) { return mk(p[0], p[1], p[2]); }

@@ -57,6 +57,7 @@ struct WarpDev {
         return v;
     }
     __device__ __forceinline__ bool any(bool p) const { return __any_sync(kFullMask, p) != 0; }
+    __device__ __forceinline__ unsigned ballot(bool p) const { return __ballot_sync(kFullMask, p); }
     __device__ __forceinline__ int scan_incl(int v) const {
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {

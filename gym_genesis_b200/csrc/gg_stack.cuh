@@ -12,7 +12,7 @@
 //                                  spatial-force space, projection onto the dofs of each body pair, dense Cholesky of the
 //                                  coupled block in shared memory, line search with butterfly reductions.
 //   stack_finish  thread per env   semi-implicit Euler of robot and cubes, observations, reward / flags.
-// The warp-level code is written against a small warp-context interface (sync / shfl / sum / max / any / scan) so that the
+// The warp-level code is written against a small warp-context interface (sync / shfl / sum / max / any / ballot / scan) so that the
 // CPU-tier test harness (tests/hostsim) can run the SAME source with 32 host threads per emulated warp.
 //
 // Body numbering inside an env: 0 world (plane), 1 last arm link (hand), 2 + f finger f, 4 + k cube k.
@@ -72,6 +72,9 @@ template <int NU, int K> struct StackBuf {
     float dinv[NV], vx[NV];
     int lo[NV];               // dof -> local (compacted) row index of the active dofs
     int plist[NPAIR];         // ids of the body pairs in contact
+    int pstart[NPAIR], pcnt[NPAIR];   // range of every pair in perm
+    int perm[SK_CAP];         // contact indices grouped by body pair
+    float part[5 * 42];       // partial pair-stiffness sums of the five contact subsets
     int tlist[SK_CAP];        // geom pairs that survive the narrow phase's cull, in task order (<= 5 + 12 + 60 + 10 tasks)
 };
 
@@ -633,6 +636,34 @@ GG_WD void stack_solve(const GgModel& M, int max_contacts, const StackIn<NA, NF,
             for (int k = 0; k < 4; k++) x[s][k] = jv[s][k];
     }
 
+    // ---- contacts grouped by body pair: perm lists the contact indices pair after pair (contact order within a pair)
+    {
+        const unsigned lt = (1u << lane) - 1u;
+        int run = 0;
+        for (int u = 0; u < npair; u++) {
+            const int pid = B.plist[u];
+            int base = run;
+            for (int s = 0; s < SK_CPL; s++) {
+                if (32 * s >= ncon) break;                       // uniform
+                const int c = lane + 32 * s;
+                const bool mine = c < ncon && (B.code[c] & 0xff) == pid;
+                const unsigned m = wc.ballot(mine);
+                if (mine) B.perm[base + popc32(m & lt)] = c;
+                base += popc32(m);
+            }
+            if (lane == 0) { B.pstart[pid] = run; B.pcnt[pid] = base - run; }
+            run = base;
+        }
+        wc.sync();
+    }
+    // pair-stiffness lanes: row pi of (Phi | gF), contact subset pg (lanes 30, 31 idle); entry (ei, ej) for the final sum
+    const int pi = lane % 6, pg = lane / 6;
+    int ei = 0, ej = 0;
+    if (lane < 21) {
+        ei = lane < 1 ? 0 : (lane < 3 ? 1 : (lane < 6 ? 2 : (lane < 10 ? 3 : (lane < 15 ? 4 : 5))));
+        ej = lane - ei * (ei + 1) / 2;
+    } else if (lane < 27) { ei = lane - 21; ej = 6; }
+
     int it = 0;
     for (; it < iterations; it++) {
         // ---- gradient of the smooth part and of the limit rows
@@ -646,10 +677,6 @@ GG_WD void stack_solve(const GgModel& M, int max_contacts, const StackIn<NA, NF,
             if (lsg_d != 0.f && jar < 0.f) { hlim = lD_d; g_d[0] += lD_d * jar * lsg_d; }
         }
         // ---- per-contact weights, clear the accumulators of the pairs in contact
-        for (int u = 0; u < npair; u++) {
-            const int pid = B.plist[u];
-            if (lane < 21) B.Phi[pid][lane] = 0.f; else if (lane < 27) B.gF[pid][lane - 21] = 0.f;
-        }
         for (int i = lane; i < n * (n + 1) / 2; i += 32) B.H[i] = 0.f;
 #pragma unroll
         for (int s = 0; s < SK_CPL; s++) {
@@ -671,33 +698,34 @@ GG_WD void stack_solve(const GgModel& M, int max_contacts, const StackIn<NA, NF,
             }
         }
         wc.sync();
-        // ---- pair stiffness in spatial-force space: lane < 21 owns Phi entry (i, j), lanes 21..26 own gF[i]
-        {
-            int ei = 0, ej = 0;
-            if (lane < 21) {
-                ei = lane < 1 ? 0 : (lane < 3 ? 1 : (lane < 6 ? 2 : (lane < 10 ? 3 : (lane < 15 ? 4 : 5))));
-                ej = lane - ei * (ei + 1) / 2;
-            } else if (lane < 27) ei = lane - 21;
-            float acc = 0.f;
-            int cur = -1;
-            for (int c = 0; c < ncon; c++) {
-                if (B.Wc[0][c] == 0.f) continue;                // no active row (uniform across the warp)
-                const float w0 = B.Wc[0][c], w1 = B.Wc[1][c], w2 = B.Wc[2][c], w3 = B.Wc[3][c], w4 = B.Wc[4][c];
-                const int pid = B.code[c] & 0xff;
-                if (pid != cur) {
-                    if (cur >= 0) { if (lane < 21) B.Phi[cur][lane] += acc; else if (lane < 27) B.gF[cur][lane - 21] += acc; }
-                    cur = pid; acc = 0.f;
+        // ---- pair stiffness in spatial-force space, Phi = sum_c F_c^T W_c F_c, gF = sum_c F_c^T g_c per body pair: lane (pi, pg) sums
+        //      row pi over the contacts pg, pg + 5, ... of the pair; the five partials are added in a fixed order (bit-reproducible)
+        for (int u = 0; u < npair; u++) {
+            const int pid = B.plist[u];
+            const int s0 = B.pstart[pid], n_c = B.pcnt[pid];
+            if (pg < 5) {
+                float acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, accg = 0.f;
+                for (int k = pg; k < n_c; k += 5) {
+                    const int c = B.perm[s0 + k];
+                    const float w0 = B.Wc[0][c], w1 = B.Wc[1][c], w2 = B.Wc[2][c], w3 = B.Wc[3][c], w4 = B.Wc[4][c];
+                    const float* f = B.F[c];
+                    const float fni = f[pi], f1i = f[6 + pi], f2i = f[12 + pi];
+                    const float a = w0 * fni + w1 * f1i + w3 * f2i, b = w1 * fni + w2 * f1i, cc = w3 * fni + w4 * f2i;
+#pragma unroll
+                    for (int j = 0; j < 6; j++) acc[j] += a * f[j] + b * f[6 + j] + cc * f[12 + j];
+                    accg += fni * B.Wc[5][c] + f1i * B.Wc[6][c] + f2i * B.Wc[7][c];
                 }
-                const float* f = B.F[c];
-                const float fni = f[ei], f1i = f[6 + ei], f2i = f[12 + ei];
-                if (lane < 21) {
-                    const float fnj = f[ej], f1j = f[6 + ej], f2j = f[12 + ej];
-                    acc += fni * (w0 * fnj + w1 * f1j + w3 * f2j) + f1i * (w1 * fnj + w2 * f1j) + f2i * (w3 * fnj + w4 * f2j);
-                } else {
-                    acc += fni * B.Wc[5][c] + f1i * B.Wc[6][c] + f2i * B.Wc[7][c];
-                }
+#pragma unroll
+                for (int j = 0; j < 6; j++) B.part[pg * 42 + pi * 7 + j] = acc[j];
+                B.part[pg * 42 + pi * 7 + 6] = accg;
             }
-            if (cur >= 0) { if (lane < 21) B.Phi[cur][lane] += acc; else if (lane < 27) B.gF[cur][lane - 21] += acc; }
+            wc.sync();
+            if (lane < 27) {
+                const int idx = ei * 7 + ej;
+                const float v = (((B.part[idx] + B.part[42 + idx]) + B.part[84 + idx]) + B.part[126 + idx]) + B.part[168 + idx];
+                if (lane < 21) B.Phi[pid][lane] = v; else B.gF[pid][lane - 21] = v;
+            }
+            wc.sync();
         }
         // ---- H = Mt (robot block, cube diagonal) ...
         if (cpl) for (int e = lane; e < NU * (NU + 1) / 2; e += 32) B.H[e] = W.Mt[e];

@@ -29,6 +29,7 @@ struct WarpHost {
     float sum(float v) { w->f[lane] = v; sync(); float r = 0.f; for (int l = 0; l < 32; l++) r += w->f[l]; sync(); return r; }
     float max(float v) { w->f[lane] = v; sync(); float r = w->f[0]; for (int l = 1; l < 32; l++) r = fmaxf(r, w->f[l]); sync(); return r; }
     bool any(bool p) { w->i[lane] = p ? 1 : 0; sync(); int r = 0; for (int l = 0; l < 32; l++) r |= w->i[l]; sync(); return r != 0; }
+    unsigned ballot(bool p) { w->i[lane] = p ? 1 : 0; sync(); unsigned r = 0; for (int l = 0; l < 32; l++) r |= (unsigned)w->i[l] << l; sync(); return r; }
     int scan_incl(int v) { w->i[lane] = v; sync(); int r = 0; for (int l = 0; l <= lane; l++) r += w->i[l]; sync(); return r; }
 };
 
