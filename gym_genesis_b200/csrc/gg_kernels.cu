@@ -1145,7 +1145,7 @@ int gg_internal_record(int device, int n, int AD, int ED, int NU, float* traj, i
     if (!traj || !ever || !action || !obs_agent || !obs_env || !reward) return fail("gg_record: null argument%s");
     if (t < 0 || t >= horizon) return fail("gg_record: frame index outside the horizon%s");
     const int F = AD + ED + NU + 1;
-    GG_CUDA(cudaSetDevice(device));
+    GgDeviceGuard dev_guard(device); GG_CUDA(dev_guard.err);
     const int total = n * F;
     record_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(traj + (size_t)t * n * F, ever, n, AD, ED, NU, obs_agent, obs_env, action, reward);
     g_launches.fetch_add(1);
@@ -1156,7 +1156,7 @@ int gg_internal_export(int device, int n, int stride, int F, int32_t** slot, con
                        int32_t* out_env_ids, int32_t* out_count, gg_stream_t stream) {
     if (!traj || !ever || !out || !out_env_ids || !out_count) return fail("gg_export_successful: null argument%s");
     if (horizon <= 0) return fail("gg_export_successful: horizon must be positive%s");
-    GG_CUDA(cudaSetDevice(device));
+    GgDeviceGuard dev_guard(device); GG_CUDA(dev_guard.err);
     if (!*slot) GG_CUDA(cudaMalloc(slot, (size_t)stride * sizeof(int32_t)));   // first use only
     select_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(ever, n, *slot, out_env_ids, out_count);
     dim3 grid((horizon * F + 255) / 256, n);
@@ -1186,7 +1186,7 @@ static int launch_step(GgSim* sim, StepArgs& A, gg_stream_t stream) {
     A.stats = sim->stats; A.team_scratch = sim->team_scratch;
     auto al16 = [](const void* p) { return ((uintptr_t)p & 15u) == 0; };
     A.vec_out = al16(A.obs_agent) && al16(A.obs_env) && al16(A.obs_agent_host) && al16(A.obs_env_host) && al16(A.action_dev);
-    GG_CUDA(cudaSetDevice(sim->device));
+    GgDeviceGuard dev_guard(sim->device); GG_CUDA(dev_guard.err);
     A.ctl = sim->ctl; A.clist = sim->clist; A.cready = sim->cready; A.list_cap = sim->stride;
     A.epoch = ++sim->epoch;
     if (A.epoch == 0) A.epoch = ++sim->epoch;
@@ -1254,7 +1254,7 @@ int gg_create(const GgModel* model, int n_envs, int device, GgSim** out) {
     int ndev = 0;
     GG_CUDA(cudaGetDeviceCount(&ndev));
     if (device < 0 || device >= ndev) return fail("gg_create: bad device index%s");
-    GG_CUDA(cudaSetDevice(device));
+    GgDeviceGuard dev_guard(device); GG_CUDA(dev_guard.err);
     GgSim* s = new (std::nothrow) GgSim();
     if (!s) return fail("gg_create: out of host memory%s");
     memset(s, 0, sizeof(*s));
@@ -1319,7 +1319,7 @@ int gg_create(const GgModel* model, int n_envs, int device, GgSim** out) {
 
 int gg_destroy(GgSim* sim) {
     if (!sim) return 0;
-    cudaSetDevice(sim->device);
+    GgDeviceGuard dev_guard(sim->device);
     cudaFree(sim->done); cudaFree(sim->stats); cudaFree(sim->team_scratch); cudaFree(sim->slot);
     cudaFree(sim->mbox); cudaFree(sim->mflag); cudaFree(sim->ctl); cudaFree(sim->clist); cudaFree(sim->cready);
     delete sim;
@@ -1399,7 +1399,7 @@ int gg_observe(GgSim* sim, float* obs_agent, float* obs_env, float* reward, uint
 
 static int state_copy(GgSim* sim, float* q, float* qd, float* qacc, int to_soa, gg_stream_t stream) {
     if (!sim || sim->state == nullptr) return fail("state copy: state not bound%s");
-    GG_CUDA(cudaSetDevice(sim->device));
+    GgDeviceGuard dev_guard(sim->device); GG_CUDA(dev_guard.err);
     const int grid = (sim->n + 127) / 128;
     if (sim->kind == 0) state_copy_kernel<9><<<grid, 128, 0, (cudaStream_t)stream>>>(sim->state, sim->stride, sim->n, q, qd, qacc, to_soa);
     else state_copy_kernel<6><<<grid, 128, 0, (cudaStream_t)stream>>>(sim->state, sim->stride, sim->n, q, qd, qacc, to_soa);
@@ -1439,7 +1439,7 @@ int gg_ik(GgSim* sim, int n_rows, const int32_t* envs_idx, const float* target_p
     if (!target_quat) A.K.rot_mask[0] = A.K.rot_mask[1] = A.K.rot_mask[2] = 0.f;
     A.n_rows = n_rows; A.stride = sim->stride; A.state = sim->state; A.envs_idx = envs_idx;
     A.tpos = target_pos; A.tquat = target_quat; A.init_q = init_q; A.q_out = q_out; A.err_out = err_out; A.iters_out = iters_out;
-    GG_CUDA(cudaSetDevice(sim->device));
+    GgDeviceGuard dev_guard(sim->device); GG_CUDA(dev_guard.err);
     const int grid = (n_rows + 63) / 64;
     if (sim->kind == 0) ik_kernel<7, 2><<<grid, 64, 0, (cudaStream_t)stream>>>(A);
     else ik_kernel<5, 1><<<grid, 64, 0, (cudaStream_t)stream>>>(A);
@@ -1478,7 +1478,7 @@ int gg_export_successful(GgSim* sim, const float* traj, const int32_t* ever, int
 
 int gg_stats(GgSim* sim, double* out8, int clear, gg_stream_t stream) {
     if (!sim || !out8) return fail("gg_stats: null argument%s");
-    GG_CUDA(cudaSetDevice(sim->device));
+    GgDeviceGuard dev_guard(sim->device); GG_CUDA(dev_guard.err);
     stats_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(sim->stats, out8, clear);
     g_launches.fetch_add(1);
     GG_CUDA(cudaGetLastError());

@@ -599,7 +599,7 @@ static int stack_launch(GgStackSim* sim, StackArgs& A, gg_stream_t stream) {
     A.coop_list = sim->coop_list; A.coop_ctr = sim->coop_ctr;
     A.amask = sim->amask; A.rob_it = sim->rob_it; A.iso_nc = sim->iso_nc; A.iso_it = sim->iso_it;
     cudaStream_t s = (cudaStream_t)stream;
-    SK_CUDA(cudaSetDevice(sim->device));
+    GgDeviceGuard dev_guard(sim->device); SK_CUDA(dev_guard.err);
     if (sim->kind == 0) stack_launch_t<7, 2, false, 5>(sim, A, s);
     else stack_launch_t<5, 1, true, 5>(sim, A, s);
     gg_internal_count_launches(A.mode != 2 ? 4 : 1);
@@ -642,7 +642,7 @@ int gg_stack_create(const GgModel* model, const GgStackTask* task, int n_envs, i
     int ndev = 0;
     SK_CUDA(cudaGetDeviceCount(&ndev));
     if (device < 0 || device >= ndev) return gg_internal_fail("gg_stack_create: bad device index%s", "");
-    SK_CUDA(cudaSetDevice(device));
+    GgDeviceGuard dev_guard(device); SK_CUDA(dev_guard.err);
     GgStackSim* s = new (std::nothrow) GgStackSim();
     if (!s) return gg_internal_fail("gg_stack_create: out of host memory%s", "");
     memset(s, 0, sizeof(*s));
@@ -707,7 +707,7 @@ int gg_stack_create(const GgModel* model, const GgStackTask* task, int n_envs, i
 
 int gg_stack_destroy(GgStackSim* s) {
     if (!s) return 0;
-    cudaSetDevice(s->device);
+    GgDeviceGuard dev_guard(s->device);
     if (s->side) { cudaStreamSynchronize(s->side); cudaStreamDestroy(s->side); }
     if (s->ev_fork) cudaEventDestroy(s->ev_fork);
     if (s->ev_join) cudaEventDestroy(s->ev_join);
@@ -720,7 +720,8 @@ int gg_stack_destroy(GgStackSim* s) {
 
 int gg_stack_configure(GgStackSim* sim, const GgConfig* cfg) {
     if (!sim || !cfg) return gg_internal_fail("gg_stack_configure: null argument%s", "");
-    if (cfg->solver_iterations < 1 || cfg->solver_iterations > 1000) return gg_internal_fail("gg_stack_configure: solver_iterations out of range%s", "");
+    // <= 255: the per-env iteration counters of the register solves (rob_it, iso_it) are bytes
+    if (cfg->solver_iterations < 1 || cfg->solver_iterations > 255) return gg_internal_fail("gg_stack_configure: solver_iterations out of range [1, 255]%s", "");
     if (!(cfg->reset_prob >= 0.f && cfg->reset_prob <= 1.f)) return gg_internal_fail("gg_stack_configure: reset_prob out of range%s", "");
     sim->cfg = *cfg;
     return 0;
@@ -786,7 +787,7 @@ int gg_stack_observe(GgStackSim* sim, float* obs_agent, float* obs_env, float* r
 
 static int stack_state_copy(GgStackSim* sim, float* q, float* qd, float* qacc, int to_soa, gg_stream_t stream) {
     if (!sim || sim->state == nullptr) return gg_internal_fail("stack state copy: state not bound%s", "");
-    SK_CUDA(cudaSetDevice(sim->device));
+    GgDeviceGuard dev_guard(sim->device); SK_CUDA(dev_guard.err);
     stack_state_copy_kernel<<<(sim->n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(sim->state, sim->stride, sim->n, sim->nu, sim->task.n_obj, q, qd,
                                                                                    qacc, to_soa);
     gg_internal_count_launches(1);
@@ -800,7 +801,7 @@ int gg_stack_set_state(GgStackSim* sim, const float* q, const float* qd, const f
 
 int gg_stack_stats(GgStackSim* sim, double* out8, int clear, gg_stream_t stream) {
     if (!sim || !out8) return gg_internal_fail("gg_stack_stats: null argument%s", "");
-    SK_CUDA(cudaSetDevice(sim->device));
+    GgDeviceGuard dev_guard(sim->device); SK_CUDA(dev_guard.err);
     stack_stats_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(sim->stats, out8, clear);
     gg_internal_count_launches(1);
     SK_CUDA(cudaGetLastError());
@@ -825,7 +826,7 @@ int gg_stack_export_successful(GgStackSim* sim, const float* traj, const int32_t
 
 int gg_stack_info(GgStackSim* sim, int32_t* ncon, int32_t* iters, gg_stream_t stream) {
     if (!sim) return gg_internal_fail("gg_stack_info: null argument%s", "");
-    SK_CUDA(cudaSetDevice(sim->device));
+    GgDeviceGuard dev_guard(sim->device); SK_CUDA(dev_guard.err);
     if (ncon) SK_CUDA(cudaMemcpyAsync(ncon, sim->ncon, (size_t)sim->n * sizeof(int32_t), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
     if (iters) SK_CUDA(cudaMemcpyAsync(iters, sim->iters, (size_t)sim->n * sizeof(int32_t), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
     return 0;

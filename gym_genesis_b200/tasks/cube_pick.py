@@ -114,6 +114,12 @@ class CubePickBatch:
         self.model = get_model(self.robot_name)
         if success_height is not None:
             self.model.success_z = float(success_height)
+        elif self.model.success_z <= self.model.spawn_z:
+            # the reference's literal threshold (so101/cube_pick.py:112: z > 0.1) with the cube spawned ABOVE it (stack placement: the island
+            # top is at z = 0.7): reward = 1 and terminated = True on every step, and auto_reset would reset every step
+            import warnings
+            warnings.warn(f"{type(self).__name__}: success height {self.model.success_z} is below the cube's spawn height {self.model.spawn_z:.3f}; "
+                          "every step reports success (the reference's literal threshold) -- pass success_height= to change it", stacklevel=3)
         # alias_outputs=False (default): every step / reset returns NEW tensors, as the reference's getters do (franka/cube_pick.py:137-157),
         # so `all_rewards.append(reward)` collectors and (obs, next_obs) replay buffers keep what they stored.  alias_outputs=True reuses
         # one set of output buffers (zero allocation, CUDA-graph safe): the tensors of step t are overwritten by step t + 1.

@@ -472,3 +472,21 @@ def test_fresh_host_results_and_observations_without_steady_state_allocation():
         env.step(acts[k % 3])
     assert ids == [[id(s[0][0]) for s in r.slabs] for r in rings]           # the same slabs again: nothing was allocated
     env.close()
+
+
+def test_calls_restore_the_callers_current_device(Sim):
+    """a simulator on another GPU must not change the caller's current CUDA device (torch reads it from the runtime)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    torch.cuda.set_device(0)
+    m = mdl.franka_cube_pick_model()
+    sim = Sim(m, 64, device="cuda:1")
+    assert torch.cuda.current_device() == 0
+    sim.reset()
+    sim.step(torch.as_tensor(np.tile(f32(m.home_q), (64, 1)), device="cuda:1"))
+    sim.step_host(torch.as_tensor(np.tile(f32(m.home_q), (64, 1))).pin_memory())
+    assert torch.cuda.current_device() == 0
+    assert torch.empty(1, device="cuda").device.index == 0
+    assert sim.obs_agent.device.index == 1 and torch.isfinite(sim.obs_agent).all()
+    sim.close()
+    assert torch.cuda.current_device() == 0
