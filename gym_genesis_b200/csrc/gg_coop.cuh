@@ -328,6 +328,22 @@ __device__ __noinline__ void team_solve(const GgModel& M, const TeamWork<NA, NF>
         }
         Hbase[k] = base;
     }
+    // pair signs of this lane's dof and of the rows of its Hessian entries, two bits per pair (bit 2 pc: involved, bit 2 pc + 1: negative)
+    unsigned sgn_d = 0u, sgn_h[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+    for (int pc = 0; pc < 7; pc++) {
+        const float sd = d < NV ? pair_sign<NA, NF>(pc, d) : 0.f;
+        sgn_d |= (sd != 0.f ? 1u : 0u) << (2 * pc) | (sd < 0.f ? 2u : 0u) << (2 * pc);
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const float sh = lane + 32 * k < NH ? pair_sign<NA, NF>(pc, hi[k]) : 0.f;
+            sgn_h[k] |= (sh != 0.f ? 1u : 0u) << (2 * pc) | (sh < 0.f ? 2u : 0u) << (2 * pc);
+        }
+    }
+    auto sgn_of = [](unsigned m, int pc) -> float {
+        const unsigned b = m >> (2 * pc);
+        return (b & 1u) ? ((b & 2u) ? -1.f : 1.f) : 0.f;
+    };
     // pair-stiffness lanes: row pi of (Phi | gF), contact subset pg (lanes 30, 31 idle); entry (ei, ej) for the final sum
     const int pi = lane % 6, pg = lane / 6;
     int ei = 0, ej = 0;
@@ -408,7 +424,7 @@ __device__ __noinline__ void team_solve(const GgModel& M, const TeamWork<NA, NF>
 #pragma unroll 1
         for (int pc = 0; pc < 7; pc++) {
             if (!((used >> pc) & 1u)) continue;
-            const float sj = d < NV ? pair_sign<NA, NF>(pc, d) : 0.f;
+            const float sj = sgn_of(sgn_d, pc);
             if (d < NV) {
                 float y[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
                 if (sj != 0.f) {
@@ -428,10 +444,8 @@ __device__ __noinline__ void team_solve(const GgModel& M, const TeamWork<NA, NF>
             __syncwarp();
 #pragma unroll
             for (int k = 0; k < 4; k++) {
-                if (lane + 32 * k < NH) {
-                    const float si = pair_sign<NA, NF>(pc, hi[k]);
-                    if (si != 0.f) Hacc[k] += si * dot6(B.TB[hi[k]], B.Y[hj[k]]);
-                }
+                const float si = sgn_of(sgn_h[k], pc);
+                if (si != 0.f) Hacc[k] += si * dot6(B.TB[hi[k]], B.Y[hj[k]]);
             }
             __syncwarp();
         }

@@ -656,6 +656,14 @@ GG_WD void stack_solve(const GgModel& M, int max_contacts, const StackIn<NA, NF,
         }
         wc.sync();
     }
+    // local (row, column) of the packed entries this lane owns in the projection of a pair onto its <= NA + 1 + 6 dofs
+    static_assert((NA + 1 + 6) * (NA + 1 + 6 + 1) / 2 <= 128, "four packed entries per lane cover a body pair");
+    int eli[4], elj[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int e = lane + 32 * k;
+        eli[k] = sk_tri_row(e); elj[k] = e - eli[k] * (eli[k] + 1) / 2;
+    }
     // pair-stiffness lanes: row pi of (Phi | gF), contact subset pg (lanes 30, 31 idle); entry (ei, ej) for the final sum
     const int pi = lane % 6, pg = lane / 6;
     int ei = 0, ej = 0;
@@ -761,8 +769,11 @@ GG_WD void stack_solve(const GgModel& M, int max_contacts, const StackIn<NA, NF,
             }
             wc.sync();
             const int nA = sk_ndof<NA, NF>(A), nl = nA + sk_ndof<NA, NF>(Bb);
-            for (int e = lane; e < nl * (nl + 1) / 2; e += 32) {
-                const int li = sk_tri_row(e), lj = e - li * (li + 1) / 2;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const int e = lane + 32 * k;
+                if (e >= nl * (nl + 1) / 2) continue;
+                const int li = eli[k], lj = elj[k];
                 const int i = li < nA ? sk_dof<NA, NF>(A, li) : sk_dof<NA, NF>(Bb, li - nA);
                 const int j = lj < nA ? sk_dof<NA, NF>(A, lj) : sk_dof<NA, NF>(Bb, lj - nA);
                 const float si = sk_sign<NA, NF>(A, Bb, i);
