@@ -401,8 +401,10 @@ template <class CT> GG_HD void add_contact(CT& C, int maxc, V3 p, V3 n, float de
 // plane z = h against a box: the first <= 4 corners (corner-index order) with signed distance <= 0
 template <class CT> GG_HD void plane_box(float h, V3 c, const M3& R, V3 half, int code, int maxc, CT& C) {
     int cnt = 0;
-#pragma unroll
-    for (int i = 0; i < 8; i++) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+    for (int i = 0; i < 8; i++) {        // rolled: one copy of the contact append instead of eight (cold code, size matters)
         V3 l = mk((i & 1) ? half.x : -half.x, (i & 2) ? half.y : -half.y, (i & 4) ? half.z : -half.z);
         V3 w = c + mul(R, l);
         float dist = w.z - h;
@@ -507,10 +509,18 @@ template <class CT> GG_HD void box_box(V3 cA, const M3& RA, V3 hA3, V3 cB, const
         poly0[k] = mk(dot(wv, Rf[u]), dot(wv, Rf[v]), dot(wv, nref));
     }
     int n = 4;
-    n = clip_poly(poly0, n, poly1, 0, 1.f, hR[u]);
-    n = clip_poly(poly1, n, poly0, 0, -1.f, hR[u]);
-    n = clip_poly(poly0, n, poly1, 1, 1.f, hR[v]);
-    n = clip_poly(poly1, n, poly0, 1, -1.f, hR[v]);
+    {
+        // four clips against the side planes of the reference face, ping-pong between the two buffers; ONE copy of the clipping code
+        // (rolled on purpose: this path is cold code executed once per env and step, its size is what costs -- profiles/r02_notes.md)
+        V3* src = poly0; V3* dst = poly1;
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+        for (int c = 0; c < 4; c++) {
+            n = clip_poly(src, n, dst, c >> 1, (c & 1) ? -1.f : 1.f, c < 2 ? hR[u] : hR[v]);
+            V3* t2 = src; src = dst; dst = t2;
+        }
+    }
     for (int k = 0; k < n; k++) {
         float depth = hR[ax] - poly0[k].z;
         if (depth < 0.f) continue;

@@ -43,3 +43,35 @@ hp = torch.as_tensor(f32(np.tile(FRANKA_HOME, (100, 1))), device="cuda")
 for _ in range(3):
     p.step(hp)
 print("pick ok", float(p.get_state()[0].abs().sum()))
+p.close()
+
+# ---- round 2: coupled pick states (warp-per-env solver teams / the grid-wide coupled list) through BOTH step kernels, host I/O with
+#      observation mirrors, IK with random re-starts
+from gym_genesis_b200 import cabi  # noqa: E402
+from helpers import pick_clutter_states  # noqa: E402
+
+mp = franka_cube_pick_model()
+gm = cabi.compile_gg(mp)
+Qp, QDp, Tp = pick_clutter_states(mp, gm, np.random.default_rng(7), 150)
+QAp = np.zeros_like(QDp)
+for kern in ("roles", "mono"):
+    os.environ["GG_STEP_KERNEL"] = kern
+    ps = BatchedSim(mp, Qp.shape[0], seed=4, auto_reset=True, reset_prob=0.05)
+    ps.set_state(f32(Qp), f32(QDp), f32(QAp))
+    ap = torch.as_tensor(f32(Tp), device="cuda")
+    for _ in range(3):
+        ps.step(ap)
+    hpin = torch.as_tensor(f32(Tp)).pin_memory()
+    for _ in range(2):
+        ps.step_host(hpin, host_obs=True)
+    print(f"pick coupled ({kern}) ok", float(ps.get_state()[0].abs().sum()), float(ps.host_obs_agent.abs().sum()))
+    ps.close()
+os.environ.pop("GG_STEP_KERNEL", None)
+pi = BatchedSim(mp, 96, seed=5)
+pi.reset(None, None)
+rng = np.random.RandomState(3)
+tp = np.stack([rng.uniform(0.3, 0.9, 96), rng.uniform(-0.4, 0.4, 96), rng.uniform(0.05, 0.6, 96)], 1)      # some targets out of reach
+tq = np.tile(np.array([0.0, 1.0, 0.0, 0.0]), (96, 1))
+qik, eik = pi.inverse_kinematics(pos=f32(tp), quat=f32(tq), return_error=True, max_samples=50)
+print("ik resample ok", float(qik.abs().sum()), float(eik.abs().sum()))
+pi.close()
