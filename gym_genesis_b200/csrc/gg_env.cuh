@@ -20,6 +20,15 @@
 #define GG_LINK_LOOP _Pragma("unroll")
 #endif
 
+// inner loops of the mass-matrix rows (independent iterations): -DGG_MROW_UNROLL=k trades code size for instruction-level parallelism
+#if defined(GG_MROW_UNROLL) && defined(__CUDA_ARCH__)
+#define GG_STR2(x) #x
+#define GG_STR(x) GG_STR2(x)
+#define GG_MROW_LOOP _Pragma(GG_STR(unroll GG_MROW_UNROLL))
+#else
+#define GG_MROW_LOOP GG_LINK_LOOP
+#endif
+
 // Same for the per-contact loops of the cube-plane solver (42.9 vs 48.9 us cold at 16384 envs).
 #if !defined(GG_UNROLL_CONTACTS) && defined(__CUDA_ARCH__)
 #define GG_CON_LOOP _Pragma("unroll 1")
@@ -167,7 +176,7 @@ GG_HD void robot_crba(const GgModel& M, const GgChain& C, const float* q, RobotD
             set_finger<NA, NF>(D, l - NA, FH ? Sl.a : Sl.l, pl, Rl, pl);
             const SV G = apply(Il, Sl);
             D.Mt[GG_TRI(l, l)] = sdot(Sl, G);
-            GG_LINK_LOOP
+            GG_MROW_LOOP
             for (int i = 0; i < NA; i++) D.Mt[GG_TRI(l, i)] = sdot(ls.getS(i), G);
             for (int g = NA; g < l; g++) D.Mt[GG_TRI(l, g)] = 0.f;
             Ic = Ic + Il;
@@ -178,7 +187,7 @@ GG_HD void robot_crba(const GgModel& M, const GgChain& C, const float* q, RobotD
     for (int l = NA - 1; l >= 0; l--) {
         Ic = Ic + ls.getI(l);
         SV G = apply(Ic, ls.getS(l));
-        GG_LINK_LOOP
+        GG_MROW_LOOP
         for (int i = 0; i <= l; i++) D.Mt[GG_TRI(l, i)] = sdot(ls.getS(i), G);
     }
     // armature; approximate implicit-fast diagonal

@@ -667,17 +667,33 @@ __global__ void __launch_bounds__(kBlockThreads * SUB, GG_MINBLOCKS / SUB) step_
 // count wins (profiles/r01_notes.md v5: 749 M vs 504 M env-steps/s at 131072 envs; r02_notes.md for this version).  Same device
 // functions, same arithmetic per env, same coupled-env list / drain; launch_step picks the kernel by env count.
 // ------------------------------------------------------------------------------------------------
-constexpr int kMonoThreads = 64;
-#ifndef GG_MONO_MINBLOCKS
-#define GG_MONO_MINBLOCKS 4
+#ifndef GG_MONO_THREADS
+#define GG_MONO_THREADS 64
 #endif
+constexpr int kMonoThreads = GG_MONO_THREADS;
+#ifndef GG_MONO_MINBLOCKS
+#define GG_MONO_MINBLOCKS (256 / GG_MONO_THREADS)
+#endif
+// -DGG_MONO_SYNC (experiment): block-wide barriers between the stages of the thread-per-env kernel keep the warps of a block at the same
+// point of the instruction stream
+#ifdef GG_MONO_SYNC
+#define MONO_SYNC() __syncthreads()
+#else
+#define MONO_SYNC()
+#endif
+template <int NA, int NF> struct MonoSmem {
+    gg::TeamWork<NA, NF> TW[kMonoThreads / 32];
+    gg::TeamBuf<NA + NF + 6> TB[kMonoThreads / 32];
+};
 constexpr int kMonoEnvsPerSm = 200;    // >= 200 envs per SM (29600 envs on a B200): thread-per-env kernel (measured cross-over ~28 k)
 
 template <int NA, int NF, bool FH>
 __global__ void __launch_bounds__(kMonoThreads, GG_MONO_MINBLOCKS) step_mono_kernel(const __grid_constant__ StepArgs A) {
     constexpr int NU = NA + NF, NV = NU + 6, AD = 7 + NF;
-    __shared__ gg::TeamWork<NA, NF> TW[kMonoThreads / 32];
-    __shared__ gg::TeamBuf<NV> TB[kMonoThreads / 32];
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    MonoSmem<NA, NF>& S = *reinterpret_cast<MonoSmem<NA, NF>*>(smem_raw);
+    gg::TeamWork<NA, NF>* TW = S.TW;
+    gg::TeamBuf<NV>* TB = S.TB;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int e0 = blockIdx.x * kMonoThreads + threadIdx.x;
     const bool live = e0 < A.n;
@@ -730,10 +746,12 @@ __global__ void __launch_bounds__(kMonoThreads, GG_MONO_MINBLOCKS) step_mono_ker
             }
         }
         coupled = live && active && gg::pads_may_touch<NA, NF>(A.M, D, cp, cq);
+        MONO_SYNC();
         {
             gg::LinkStoreLocal<NA> ls;
             gg::robot_crba<NA, NF, FH>(A.M, A.C, q, D, ls);
         }
+        MONO_SYNC();
         float L[NU * (NU + 1) / 2], dinv[NU];
 #pragma unroll
         for (int i = 0; i < NU * (NU + 1) / 2; i++) L[i] = D.Mt[i];
@@ -750,11 +768,14 @@ __global__ void __launch_bounds__(kMonoThreads, GG_MONO_MINBLOCKS) step_mono_ker
         for (int i = 0; i < NU; i++) a[i] = as[i];
 #pragma unroll
         for (int i = 0; i < 6; i++) a_c[i] = as_c[i];
+        MONO_SYNC();
+        if (live && !coupled) gg::robot_block_solve<NU>(D.Mt, as, nlim, lsg, laref, lD, qa, a, A.iterations, A.tol, ir);
+        MONO_SYNC();
         if (live && !coupled) {
-            gg::robot_block_solve<NU>(D.Mt, as, nlim, lsg, laref, lD, qa, a, A.iterations, A.tol, ir);
             gg::CubeConLocal cs;
             gg::cube_block_solve(A.M, cp, gg::qmat(cq), Mc, as_c, qd_c, qac, a_c, A.iterations, A.tol, cs, ic);
         }
+        MONO_SYNC();
         const unsigned cm = __ballot_sync(0xffffffffu, coupled);
         if (cm != 0u) {
             if (coupled) {
@@ -1220,8 +1241,8 @@ static int launch_step(GgSim* sim, StepArgs& A, gg_stream_t stream) {
     if (sim->use_mono) {
         // throughput regime (>= ~7 env-warps per scheduler): thread-per-env kernel, fewest instructions per env
         const int grid = (sim->n + kMonoThreads - 1) / kMonoThreads;
-        if (sim->kind == 0) step_mono_kernel<7, 2, false><<<grid, kMonoThreads, 0, (cudaStream_t)stream>>>(A);
-        else step_mono_kernel<5, 1, true><<<grid, kMonoThreads, 0, (cudaStream_t)stream>>>(A);
+        if (sim->kind == 0) step_mono_kernel<7, 2, false><<<grid, kMonoThreads, sizeof(MonoSmem<7, 2>), (cudaStream_t)stream>>>(A);
+        else step_mono_kernel<5, 1, true><<<grid, kMonoThreads, sizeof(MonoSmem<5, 1>), (cudaStream_t)stream>>>(A);
     } else {
         // latency regime: 32 envs x 3 role warps per block
         const int ngroups = (sim->n + 31) / 32;
@@ -1293,6 +1314,8 @@ int gg_create(const GgModel* model, int n_envs, int device, GgSim** out) {
         const char* sb = getenv("GG_STEP_SUB");
         if (sb && (atoi(sb) == 1 || atoi(sb) == 2 || atoi(sb) == 4)) s->sub = atoi(sb);
         prepare_roles<1>(); prepare_roles<2>(); prepare_roles<4>();
+        cudaFuncSetAttribute((const void*)step_mono_kernel<7, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MonoSmem<7, 2>));
+        cudaFuncSetAttribute((const void*)step_mono_kernel<5, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MonoSmem<5, 1>));
     }
 #ifdef GG_WITH_RS_KERNEL
     {
