@@ -594,6 +594,26 @@ GG_HD float rowval(const float* v3, float mu, int k) {
 // (an estimate of the remaining acceleration error per dof) relative to 1 + |a|_inf.  Unlike a gradient
 // norm scaled by the mean inertia of the whole system it stays meaningful for the cube's rotational dofs,
 // whose inertia (3.4e-6 kg m^2) is six orders below the arm's.
+// Second stop test of the Newton loops: the step just taken changed no acceleration by more than tol (1 + |a|_inf).  Without it a
+// solve whose gradient test cannot pass in float32 (|g_i| / H_ii with H_ii ~ 1e-5 for the rotation of a softly supported cube: the
+// SO-101 task's friction 5 makes the pyramidal regulariser 650x softer) keeps taking noise-sized steps that flip rows sitting at
+// x = 0 until the iteration cap -- and a warp runs as long as its slowest lane (9 % of the lanes at the cap = every warp at the cap).
+template <int N> GG_HD bool newton_step_small(const float* sd, float al, const float* a, float tol) {
+    float sm = 0.f, am = 0.f;
+#pragma unroll
+    for (int i = 0; i < N; i++) { sm = fmaxf(sm, fabsf(al * sd[i])); am = fmaxf(am, fabsf(a[i])); }
+    return sm <= tol * (1.f + am);
+}
+// Float32 noise floor of a gradient component: g_i = (M (a - a_smooth))_i + sum_rows J_row,i f_row is a sum of terms that cancel at
+// the optimum, so |g_i| cannot be resolved below a few ulps of the LARGEST term; GG_GRAD_ULPS ulps of sum |term| count as zero.
+// (A cube resting flat: four corner forces of 0.25 N at 28 mm lever arms cancel to a torque of 1e-10 .. 5e-10 N m = 1 .. 5 ulps of
+// 7e-3 N m, which the rotational H_ii ~ 6e-6 of a softly supported cube -- the SO-101 task's friction 5 makes the pyramidal
+// regulariser 650x softer -- turns into 2e-5 .. 8e-5 > tol: the gradient test could never pass and every step ran Newton
+// iterations and nine-step line searches on noise, 9 % of the lanes up to the iteration cap.)
+#ifndef GG_GRAD_ULPS
+#define GG_GRAD_ULPS 8.f
+#endif
+GG_HD float grad_above_noise(float g, float sum_abs_terms) { return fmaxf(fabsf(g) - GG_GRAD_ULPS * 1.1920929e-7f * sum_abs_terms, 0.f); }
 template <int N> GG_HD float newton_residual(const float* g, const float* H, const float* a) {
     float r = 0.f, am = 0.f;
 #pragma unroll
@@ -760,11 +780,11 @@ GG_HD void solve_cube_plane(const GgModel& M, const float* Mc, const float* as, 
     }
     int it = 0;
     for (; it < iterations; it++) {
-        float H[21], g[6], dinv[6], sd[6];
+        float H[21], g[6], gabs[6], dinv[6], sd[6];
 #pragma unroll
         for (int i = 0; i < 21; i++) H[i] = 0.f;
 #pragma unroll
-        for (int i = 0; i < 6; i++) { H[GG_TRI(i, i)] = Mc[i]; g[i] = Mc[i] * (a[i] - as[i]); }
+        for (int i = 0; i < 6; i++) { H[GG_TRI(i, i)] = Mc[i]; g[i] = Mc[i] * (a[i] - as[i]); gabs[i] = fabsf(g[i]); }
         GG_CON_LOOP
         for (int c = 0; c < 4; c++) {
             float J[3][6], u[3], ar[4];
@@ -791,6 +811,7 @@ GG_HD void solve_cube_plane(const GgModel& M, const float* Mc, const float* as, 
 #pragma unroll
             for (int i = 0; i < 6; i++) {
                 g[i] += J[0][i] * gn + J[1][i] * g1 + J[2][i] * g2;
+                gabs[i] += fabsf(J[0][i] * gn) + fabsf(J[1][i] * g1) + fabsf(J[2][i] * g2);
                 Pn[i] = Wnn * J[0][i] + Wn1 * J[1][i] + Wn2 * J[2][i];
                 P1[i] = Wn1 * J[0][i] + W11 * J[1][i];
                 P2[i] = Wn2 * J[0][i] + W22 * J[2][i];
@@ -800,7 +821,16 @@ GG_HD void solve_cube_plane(const GgModel& M, const float* Mc, const float* as, 
 #pragma unroll
                 for (int j = 0; j <= i; j++) H[GG_TRI(i, j)] += J[0][i] * Pn[j] + J[1][i] * P1[j] + J[2][i] * P2[j];
         }
-        gnorm = newton_residual<6>(g, H, a);
+        {
+            // stop test on the gradient above its float32 noise floor
+            float r = 0.f, am = 0.f;
+#pragma unroll
+            for (int i = 0; i < 6; i++) {
+                r = fmaxf(r, grad_above_noise(g[i], gabs[i]) * gg_rcp(H[GG_TRI(i, i)]));
+                am = fmaxf(am, fabsf(a[i]));
+            }
+            gnorm = gg_div(r, 1.f + am);
+        }
         if (gnorm < tol) break;
         chol_packed<6>(H, dinv);
 #pragma unroll
@@ -849,7 +879,7 @@ GG_HD void solve_cube_plane(const GgModel& M, const float* Mc, const float* as, 
         }
 #pragma unroll
         for (int i = 0; i < 6; i++) a[i] += L.al * sd[i];
-        if (changed == 0 && fabsf(L.al - 1.f) < 1e-3f) { it++; break; }
+        if ((changed == 0 && fabsf(L.al - 1.f) < 1e-3f) || newton_step_small<6>(sd, L.al, a, tol)) { it++; break; }
     }
     iters = it;
 }
