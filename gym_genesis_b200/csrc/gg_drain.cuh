@@ -22,7 +22,7 @@
 
 namespace cl {
 
-enum { CTL_TAIL = 0, CTL_HEAD = 1, CTL_AVAIL = 2 };
+enum { CTL_TAIL = 0, CTL_HEAD = 1, CTL_AVAIL = 2, CTL_COUPLED = kCtlCoupled };    // CTL_COUPLED: running count of coupled envs (both step kernels)
 
 __device__ __forceinline__ uint32_t ld_relaxed(const uint32_t* p) {
     uint32_t v;
@@ -44,7 +44,7 @@ __device__ __forceinline__ void list_append(const StepArgs& A, unsigned cm, bool
         asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(A.cready + pos), "r"(A.epoch) : "memory");
     }
     __syncwarp();
-    if (lane == 0) { __threadfence(); atomicAdd(&A.ctl[CTL_AVAIL], __popc(cm)); }
+    if (lane == 0) { __threadfence(); atomicAdd(&A.ctl[CTL_AVAIL], __popc(cm)); atomicAdd(&A.ctl[CTL_COUPLED], __popc(cm)); }
 }
 
 // claim one env of the list for this warp: env id, or -1 when the list is empty

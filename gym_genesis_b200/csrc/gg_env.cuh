@@ -206,13 +206,32 @@ struct TargetPtr {
     GG_HD float operator()(int d) const { return t[d]; }
 };
 
+// per-link motion subspace / force of the bias-force pass: thread-local arrays, or this lane's column of a shared-memory scratch
+template <int NA> struct RneaStoreLocal {
+    SV S[NA]; SV F[NA];
+    GG_HD SV getS(int l) const { return S[l]; }
+    GG_HD SV getF(int l) const { return F[l]; }
+    GG_HD void set(int l, const SV& s, const SV& f) { S[l] = s; F[l] = f; }
+};
+template <int NA> struct RneaStoreStrided {      // element e of link l at b[(l * 12 + e) * STRIDE]
+    enum { STRIDE = 32, FLOATS = NA * 12 };
+    float* b;
+    GG_HD SV get6(const float* p) const { SV v; v.a = mk(p[0], p[STRIDE], p[2 * STRIDE]); v.l = mk(p[3 * STRIDE], p[4 * STRIDE], p[5 * STRIDE]); return v; }
+    GG_HD SV getS(int l) const { return get6(b + l * 12 * STRIDE); }
+    GG_HD SV getF(int l) const { return get6(b + (l * 12 + 6) * STRIDE); }
+    GG_HD void set(int l, const SV& s, const SV& f) {
+        float* p = b + l * 12 * STRIDE;
+        p[0] = s.a.x; p[STRIDE] = s.a.y; p[2 * STRIDE] = s.a.z; p[3 * STRIDE] = s.l.x; p[4 * STRIDE] = s.l.y; p[5 * STRIDE] = s.l.z;
+        p[6 * STRIDE] = f.a.x; p[7 * STRIDE] = f.a.y; p[8 * STRIDE] = f.a.z; p[9 * STRIDE] = f.l.x; p[10 * STRIDE] = f.l.y; p[11 * STRIDE] = f.l.z;
+    }
+};
+
 // Dp (optional): receives the frames of the pad-carrying bodies (last arm link, fingers) -- the chain walk of this pass already has
 // them, so the caller's broad phase needs no walk of its own.
-template <int NA, int NF, bool FH, class TF>
-GG_HD void robot_rnea_t(const GgModel& M, const GgChain& C, const float* q, const float* qd, TF& tf, float* fs, RobotDyn<NA, NF>* Dp = nullptr) {
+template <int NA, int NF, bool FH, class TF, class RS>
+GG_HD void robot_rnea_t(const GgModel& M, const GgChain& C, const float* q, const float* qd, TF& tf, float* fs, RS& rs, RobotDyn<NA, NF>* Dp = nullptr) {
     constexpr int NU = NA + NF;
     float bias[NU];
-    SV S[NA]; SV F[NA];
     Q4 ql = ldq(M.base_quat);
     V3 pl = ld3(M.base_pos);
     M3 Rl = qmat(ql);
@@ -220,40 +239,6 @@ GG_HD void robot_rnea_t(const GgModel& M, const GgChain& C, const float* q, cons
     SV A; A.a = mk(0.f, 0.f, 0.f); A.l = mk(0.f, 0.f, M.gravity);   // gravity as base acceleration
     Q4 qa = ql; V3 pa = pl; M3 Ra = Rl; SV Va = V, Aa = A;          // last arm link (parent of the fingers)
     SV Fc; Fc.a = mk(0.f, 0.f, 0.f); Fc.l = mk(0.f, 0.f, 0.f);
-#ifdef GG_SPLIT_RNEA
-    // experiment: two small loops (frames; forces) instead of one loop body that exceeds the L0 instruction cache
-    {
-        SV Sx[NU]; M3 Rx[NU]; V3 px[NU];
-        GG_LINK_LOOP
-        for (int l = 0; l < NU; l++) {
-            const bool fin = l >= NA;
-            if (fin) { ql = qa; pl = pa; Rl = Ra; }
-            SV Sl;
-            chain_step(C.e[l], fin && !FH, q[l], ql, pl, Rl, Sl);
-            Sx[l] = Sl; Rx[l] = Rl; px[l] = pl;
-            if (l == NA - 1) { qa = ql; pa = pl; Ra = Rl; }
-            if (fin && Dp) set_finger<NA, NF>(*Dp, l - NA, FH ? Sl.a : Sl.l, pl, Rl, pl);
-        }
-        GG_LINK_LOOP
-        for (int l = 0; l < NU; l++) {
-            const bool fin = l >= NA;
-            if (fin) { V = Va; A = Aa; }
-            const float* e = C.e[l];
-            const SV Sl = Sx[l];
-            A = A + crm(V, Sl) * qd[l];
-            V = V + Sl * qd[l];
-            const SI Il = body_inertia(e[CH_MASS], ld3(e + CH_COM), e + CH_INERTIA, Rx[l], px[l]);
-            const SV Fl = apply(Il, A) + crf(V, apply(Il, V));
-            if (!fin) {
-                S[l] = Sl; F[l] = Fl;
-                if (l == NA - 1) { Va = V; Aa = A; }
-            } else {
-                bias[l] = sdot(Sl, Fl);
-                Fc = Fc + Fl;
-            }
-        }
-    }
-#else
     GG_LINK_LOOP
     for (int l = 0; l < NU; l++) {
         const bool fin = l >= NA;
@@ -266,7 +251,7 @@ GG_HD void robot_rnea_t(const GgModel& M, const GgChain& C, const float* q, cons
         const SI Il = body_inertia(e[CH_MASS], ld3(e + CH_COM), e + CH_INERTIA, Rl, pl);
         const SV Fl = apply(Il, A) + crf(V, apply(Il, V));
         if (!fin) {
-            S[l] = Sl; F[l] = Fl;
+            rs.set(l, Sl, Fl);
             if (l == NA - 1) { qa = ql; pa = pl; Ra = Rl; Va = V; Aa = A; }
         } else {
             bias[l] = sdot(Sl, Fl);
@@ -274,12 +259,11 @@ GG_HD void robot_rnea_t(const GgModel& M, const GgChain& C, const float* q, cons
             if (Dp) set_finger<NA, NF>(*Dp, l - NA, FH ? Sl.a : Sl.l, pl, Rl, pl);
         }
     }
-#endif
     if (Dp) { Dp->lq = qa; Dp->lp = pa; Dp->lR = Ra; }
     GG_LINK_LOOP
     for (int l = NA - 1; l >= 0; l--) {
-        Fc = Fc + F[l];
-        bias[l] = sdot(S[l], Fc);
+        Fc = Fc + rs.getF(l);
+        bias[l] = sdot(rs.getS(l), Fc);
     }
     // PD position control with force clamp; passive damping
     tf.ready();
@@ -294,7 +278,8 @@ GG_HD void robot_rnea_t(const GgModel& M, const GgChain& C, const float* q, cons
 template <int NA, int NF, bool FH>
 GG_HD void robot_rnea(const GgModel& M, const GgChain& C, const float* q, const float* qd, const float* target, float* fs) {
     TargetPtr tf; tf.t = target;
-    robot_rnea_t<NA, NF, FH>(M, C, q, qd, tf, fs);
+    RneaStoreLocal<NA> rs;
+    robot_rnea_t<NA, NF, FH>(M, C, q, qd, tf, fs, rs);
 }
 
 template <int NA, int NF, bool FH>

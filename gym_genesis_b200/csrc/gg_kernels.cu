@@ -55,7 +55,7 @@ struct StepArgs {
     float* team_scratch;      // n_envs x sizeof(TeamWork) / 4 floats: dynamics of coupled envs, published by their MAIN lane
     // role-per-SM kernel (gg_step_rs.cuh): per-group mailboxes + flags, launch epoch, coupled-env list, role split of the grid
     float* mbox; uint32_t* mflag; uint32_t epoch;
-    int* ctl; int* clist; uint32_t* cready; int list_cap;
+    int* ctl; int* clist; uint32_t* cready; int list_cap; int defer_drain;   // defer_drain: step_mono_kernel leaves the coupled list to drain_kernel
     int n_main, n_rnea, n_cube;
 };
 
@@ -129,6 +129,7 @@ template <int NU> __device__ __forceinline__ void store_state(float* __restrict_
 // way with 16-byte cp.async and, on request, copied to a device-resident target buffer (PD targets persist across steps).
 // ------------------------------------------------------------------------------------------------
 constexpr int kBlockThreads = 96;
+constexpr int kCtlCoupled = 3;         // StepArgs::ctl slot: running count of coupled envs (both step kernels; read back lagged by launch_step)
 
 #ifndef GG_MINBLOCKS
 #define GG_MINBLOCKS 4
@@ -166,9 +167,14 @@ template <int NU, int AD> struct Xchg {
 
 // shared memory of one group of 32 envs (three role warps); a block holds SUB of them (dynamic shared memory)
 template <int NA, int NF> struct StepSmem {
+    // until the first team round the team buffers double as [element][lane] scratch of the rolled loops of MAIN (per-link S, I) and CUBE
+    // (per-contact rows); `pad` makes the region starting at TB large enough for both views
+    static constexpr size_t kScratch = (size_t)(gg::LinkStoreStrided<NA>::FLOATS + gg::CubeConStrided::FLOATS) * 32 * sizeof(float);
+    static constexpr size_t kTB = 3 * sizeof(gg::TeamBuf<NA + NF + 6>);
     Xchg<NA + NF, 7 + NF> X;
     gg::TeamWork<NA, NF> TW[3];
     gg::TeamBuf<NA + NF + 6> TB[3];
+    float pad[kScratch > kTB ? (kScratch - kTB + 3) / 4 : 1];
 };
 
 // PD targets of one env for robot_rnea_t: the staged slab in shared memory (after the cp.async group has landed), the action
@@ -251,7 +257,7 @@ __global__ void __launch_bounds__(kBlockThreads * SUB, GG_MINBLOCKS / SUB) step_
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // until the first team round the team buffers double as scratch for the rolled loops of MAIN (per-link S, I) and CUBE
     // (per-contact J, aref, D, u, w)
-    static_assert(sizeof(SM::TB) >= (gg::LinkStoreStrided<NA>::FLOATS + gg::CubeConStrided::FLOATS) * 32 * sizeof(float), "team buffers too small for the scratch views");
+    static_assert(sizeof(SM::TB) + sizeof(SM::pad) >= SM::kScratch && offsetof(SM, pad) == offsetof(SM, TB) + sizeof(SM::TB), "team buffers too small for the scratch views");
     // SUB groups of 32 envs per block: warp w = role * SUB + sub, so the SUB warps of one role sit on different schedulers and meet
     // at the same (SUB times wider) named barriers -- they run the role's instruction stream in step (see the header comment)
     const int lane = threadIdx.x & 31, role = (threadIdx.x >> 5) / SUB, sub = (threadIdx.x >> 5) % SUB;
@@ -307,7 +313,8 @@ __global__ void __launch_bounds__(kBlockThreads * SUB, GG_MINBLOCKS / SUB) step_
         tf.home = A.M.home_q; tf.slab = X.act + lane * NU; tf.global = A.action + (size_t)e * NU;
         tf.staged = staged; tf.use_action = A.mode == 0 && !do_reset;
         gg::RobotDyn<NA, NF> D;                               // only the pad-body frames are filled (and kept)
-        gg::robot_rnea_t<NA, NF, FH>(A.M, A.C, q, qd, tf, fs, &D);
+        gg::RneaStoreLocal<NA> rs;
+        gg::robot_rnea_t<NA, NF, FH>(A.M, A.C, q, qd, tf, fs, rs, &D);
 #pragma unroll
         for (int i = 0; i < NU; i++) X.fs[i][lane] = fs[i];
         if (A.action_dev != nullptr && A.mode == 0) {         // device-resident copy of the consumed targets (host-I/O callers)
@@ -391,6 +398,7 @@ __global__ void __launch_bounds__(kBlockThreads * SUB, GG_MINBLOCKS / SUB) step_
                 const unsigned cm = __ballot_sync(0xffffffffu, coupled);
                 const int ncpl = __popc(cm);
                 if (ncpl > 0) {
+                    if (lane == 0) atomicAdd(&A.ctl[kCtlCoupled], ncpl);     // running count for the host's kernel choice (launch_step)
                     // protocol: the MAIN lane of every coupled env publishes its dynamics to the env's slot of the global scratch
                     // slab (L2 resident), barrier 4 (the team buffers are free of MAIN's / CUBE's scratch views from here on),
                     // the three warps drain the block's queue of coupled envs, barrier 5 (accelerations are in X.aout)
@@ -681,20 +689,26 @@ constexpr int kMonoThreads = GG_MONO_THREADS;
 #else
 #define MONO_SYNC()
 #endif
-template <int NA, int NF> struct MonoSmem {
-    gg::TeamWork<NA, NF> TW[kMonoThreads / 32];
-    gg::TeamBuf<NA + NF + 6> TB[kMonoThreads / 32];
+// Shared memory of one warp of the thread-per-env kernel: until the warp starts draining the coupled list its team buffers double as the
+// [element][lane] scratch of the rolled loops (per-link S / I of the CRBA, then per-contact rows of the cube block) -- in local memory these
+// arrays were the kernel's top stall (ncu: 2.0 of 6.1 cycles per issue waiting on L1TEX, 113 MB of live stack against a 126 MB L2,
+// 223 MB of DRAM write-back per launch at 131072 envs; profiles/r02_step_mono_details.txt)
+template <int NA, int NF> struct MonoWarp {
+    static constexpr int SCRATCH = (gg::LinkStoreStrided<NA>::FLOATS > gg::CubeConStrided::FLOATS ? gg::LinkStoreStrided<NA>::FLOATS : gg::CubeConStrided::FLOATS) * 32;
+    struct Team { gg::TeamWork<NA, NF> TW; gg::TeamBuf<NA + NF + 6> TB; };
+    union { Team t; float scratch[SCRATCH]; };
 };
-constexpr int kMonoEnvsPerSm = 200;    // >= 200 envs per SM (29600 envs on a B200): thread-per-env kernel (measured cross-over ~28 k)
+template <int NA, int NF> struct MonoSmem { MonoWarp<NA, NF> w[kMonoThreads / 32]; };
+constexpr int kMonoEnvsPerSm = 32 * GG_MINBLOCKS;   // more groups of 32 envs than ONE wave of role blocks holds (4 per SM: 18944 envs on a B200): the role
+                                                    // kernel would need a second wave (16384 envs 36 us, 20480 envs 54 us), the thread-per-env kernel
+                                                    // does not (42.6 / 44.4 us) -- profiles/r02_notes.md
 
 template <int NA, int NF, bool FH>
 __global__ void __launch_bounds__(kMonoThreads, GG_MONO_MINBLOCKS) step_mono_kernel(const __grid_constant__ StepArgs A) {
     constexpr int NU = NA + NF, NV = NU + 6, AD = 7 + NF;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    MonoSmem<NA, NF>& S = *reinterpret_cast<MonoSmem<NA, NF>*>(smem_raw);
-    gg::TeamWork<NA, NF>* TW = S.TW;
-    gg::TeamBuf<NV>* TB = S.TB;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    MonoWarp<NA, NF>& SW = reinterpret_cast<MonoSmem<NA, NF>*>(smem_raw)->w[w];
     const int e0 = blockIdx.x * kMonoThreads + threadIdx.x;
     const bool live = e0 < A.n;
     const int e = live ? e0 : A.n - 1;
@@ -739,7 +753,9 @@ __global__ void __launch_bounds__(kMonoThreads, GG_MONO_MINBLOCKS) step_mono_ker
             ActionFetch<NU> tf;
             tf.home = A.M.home_q; tf.slab = nullptr; tf.global = A.action + (size_t)e * NU;
             tf.staged = false; tf.use_action = A.mode == 0 && !do_reset;
-            gg::robot_rnea_t<NA, NF, FH>(A.M, A.C, q, qd, tf, D.fs, &D);
+            gg::RneaStoreStrided<NA> rs;                    // scratch view 1 of 3 (bias forces, then CRBA, then cube block)
+            rs.b = SW.scratch + lane;
+            gg::robot_rnea_t<NA, NF, FH>(A.M, A.C, q, qd, tf, D.fs, rs, &D);
             if (A.action_dev != nullptr && A.mode == 0 && live) {
 #pragma unroll
                 for (int i = 0; i < NU; i++) A.action_dev[(size_t)e * NU + i] = A.action[(size_t)e * NU + i];
@@ -748,7 +764,8 @@ __global__ void __launch_bounds__(kMonoThreads, GG_MONO_MINBLOCKS) step_mono_ker
         coupled = live && active && gg::pads_may_touch<NA, NF>(A.M, D, cp, cq);
         MONO_SYNC();
         {
-            gg::LinkStoreLocal<NA> ls;
+            gg::LinkStoreStrided<NA> ls;
+            ls.b = SW.scratch + lane;
             gg::robot_crba<NA, NF, FH>(A.M, A.C, q, D, ls);
         }
         MONO_SYNC();
@@ -772,7 +789,8 @@ __global__ void __launch_bounds__(kMonoThreads, GG_MONO_MINBLOCKS) step_mono_ker
         if (live && !coupled) gg::robot_block_solve<NU>(D.Mt, as, nlim, lsg, laref, lD, qa, a, A.iterations, A.tol, ir);
         MONO_SYNC();
         if (live && !coupled) {
-            gg::CubeConLocal cs;
+            gg::CubeConStrided cs;                          // the CRBA is done with the scratch
+            cs.b = SW.scratch + lane;
             gg::cube_block_solve(A.M, cp, gg::qmat(cq), Mc, as_c, qd_c, qac, a_c, A.iterations, A.tol, cs, ic);
         }
         MONO_SYNC();
@@ -880,7 +898,28 @@ __global__ void __launch_bounds__(kMonoThreads, GG_MONO_MINBLOCKS) step_mono_ker
         if (lane < 8 && mine != 0.f) atomicAdd(&A.stats[lane], (double)mine);
     }
     // ---- coupled envs of the whole launch (gg_drain.cuh)
-    if (run_sub) cl::drain_all<NA, NF, FH>(A, lane, TB[w], TW[w]);
+    __syncwarp();                                           // every lane is done with the scratch view
+    if (run_sub && !A.defer_drain) cl::drain_all<NA, NF, FH>(A, lane, SW.t.TB, SW.t.TW);
+}
+
+// ------------------------------------------------------------------------------------------------
+// drain_kernel: the coupled envs the thread-per-env kernel listed, one WARP per env, as a kernel of its own (launched right behind
+// step_mono_kernel on the same stream).  The warp-per-env solve is latency bound per warp, so its throughput is the number of resident
+// warps: inside step_mono_kernel that is 8 per SM (254 registers of the thread-per-env code), here 16 (<= 128 registers, 12 KB of
+// shared memory per warp) -- scripted grasp at 131072 envs: 22.9 M env-steps/s drained in-kernel, 30.4 M with this kernel, 32.7 M with the role
+// kernel's block-local teams.  Opt-in (GG_SPLIT_DRAIN=1): an empty list costs ~5 us per step, and launch_step switches to the role kernel
+// anyway once more than a few per cent of the envs are coupled.
+// ------------------------------------------------------------------------------------------------
+constexpr int kDrainThreads = 128;
+#ifndef GG_DRAIN_MINBLOCKS
+#define GG_DRAIN_MINBLOCKS 4
+#endif
+template <int NA, int NF, bool FH>
+__global__ void __launch_bounds__(kDrainThreads, GG_DRAIN_MINBLOCKS) drain_kernel(const __grid_constant__ StepArgs A) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    typedef typename MonoWarp<NA, NF>::Team Team;
+    Team& T = reinterpret_cast<Team*>(smem_raw)[threadIdx.x >> 5];
+    cl::drain_all<NA, NF, FH>(A, threadIdx.x & 31, T.TB, T.TW);
 }
 
 #ifdef GG_WITH_RS_KERNEL
@@ -1114,10 +1153,13 @@ struct GgSim {
     uint8_t* done; double* stats;       // library-owned (allocated once in gg_create)
     float* team_scratch;                // library-owned: published dynamics of coupled envs (step_kernel solver teams)
     float* mbox; uint32_t* mflag; int* ctl; int* clist; uint32_t* cready;   // library-owned: role-per-SM kernel mailboxes / coupled list
-    uint32_t epoch; int n_sm; int use_blocks; int use_mono; int sub; int64_t list_budget;   // launch epoch of the mailbox flags; SM count; 1 = round-1 block kernel (GG_STEP_KERNEL=blocks)
+    uint32_t epoch; int n_sm; int use_blocks; int use_mono; int sub; int split_drain; int kernel_forced; int64_t list_budget;   // launch epoch of the mailbox flags; SM count; 1 = round-1 block kernel (GG_STEP_KERNEL=blocks)
     int32_t* slot;                      // library-owned, allocated on first gg_export_successful: env -> compacted episode slot
     uint32_t step_index;
     GgPinCache pins;                    // address ranges already verified as pinned host memory (gg_step_host)
+    // adaptive kernel choice above one wave of role blocks: lagged fraction of coupled envs (device counter copied to pinned memory every
+    // 16 steps, read one window later -- never waited for)
+    int* coupled_host; cudaEvent_t coupled_ev; int coupled_pending; int coupled_prev; uint32_t adapt_tick; float coupled_frac; int prefer_roles;
 };
 
 // Is `p` page-locked host memory the device can address (cudaHostAlloc / cudaHostRegister)?  The verdict is cached per ALLOCATION
@@ -1238,11 +1280,44 @@ static int launch_step(GgSim* sim, StepArgs& A, gg_stream_t stream) {
         return 0;
     }
 #endif
-    if (sim->use_mono) {
+    bool mono = sim->use_mono != 0;
+    if (mono && sim->kernel_forced < 0 && A.mode == 0) {
+        // Above one wave of role blocks the thread-per-env kernel wins on free-space steps (131072 envs: 147 vs 259 us), but its coupled envs
+        // are solved by 8 warps per SM instead of 12 (scripted grasp: 23 M vs 33 M env-steps/s).  Break-even is ~2 - 4 % of the envs coupled;
+        // the choice follows the measured fraction with hysteresis.  Both kernels produce bit-identical states, so switching is seamless.
+        cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+        if ((sim->adapt_tick++ & 15u) == 0u && cudaStreamIsCapturing((cudaStream_t)stream, &cap) == cudaSuccess && cap == cudaStreamCaptureStatusNone) {
+            if (sim->coupled_pending && cudaEventQuery(sim->coupled_ev) == cudaSuccess) {
+                const int cur = sim->coupled_host[0], delta = cur - sim->coupled_prev;
+                if (delta >= 0) sim->coupled_frac = (float)delta / (16.f * (float)sim->n);     // < 0: the counters were just re-zeroed
+                sim->coupled_prev = cur;
+                sim->coupled_pending = 0;
+                if (sim->coupled_frac > 0.04f) sim->prefer_roles = 1;
+                else if (sim->coupled_frac < 0.02f) sim->prefer_roles = 0;
+            }
+            if (!sim->coupled_pending) {
+                GG_CUDA(cudaMemcpyAsync(sim->coupled_host, sim->ctl + kCtlCoupled, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+                GG_CUDA(cudaEventRecord(sim->coupled_ev, (cudaStream_t)stream));
+                sim->coupled_pending = 1;
+            }
+        }
+        if (sim->prefer_roles) mono = false;
+    }
+    if (mono) {
         // throughput regime (>= ~7 env-warps per scheduler): thread-per-env kernel, fewest instructions per env
         const int grid = (sim->n + kMonoThreads - 1) / kMonoThreads;
+        const bool run_sub = A.mode == 0 || (A.mode == 1 && A.M.settle_steps > 0);
+        A.defer_drain = (sim->split_drain && run_sub) ? 1 : 0;
         if (sim->kind == 0) step_mono_kernel<7, 2, false><<<grid, kMonoThreads, sizeof(MonoSmem<7, 2>), (cudaStream_t)stream>>>(A);
         else step_mono_kernel<5, 1, true><<<grid, kMonoThreads, sizeof(MonoSmem<5, 1>), (cudaStream_t)stream>>>(A);
+        if (A.defer_drain) {
+            // persistent warps, one per listed env at a time; an empty list costs one look at the counter per warp
+            const int dgrid = sim->n_sm * GG_DRAIN_MINBLOCKS;
+            constexpr int dw = kDrainThreads / 32;
+            if (sim->kind == 0) drain_kernel<7, 2, false><<<dgrid, kDrainThreads, dw * sizeof(MonoWarp<7, 2>::Team), (cudaStream_t)stream>>>(A);
+            else drain_kernel<5, 1, true><<<dgrid, kDrainThreads, dw * sizeof(MonoWarp<5, 1>::Team), (cudaStream_t)stream>>>(A);
+            g_launches.fetch_add(1);
+        }
     } else {
         // latency regime: 32 envs x 3 role warps per block
         const int ngroups = (sim->n + 31) / 32;
@@ -1304,9 +1379,16 @@ int gg_create(const GgModel* model, int n_envs, int device, GgSim** out) {
         // kernel choice by grid size (GG_STEP_KERNEL=mono / roles overrides it for A/B measurements): the role kernel while the launch
         // cannot fill the GPU with env-warps, the thread-per-env kernel above kMonoEnvsPerSm envs per SM
         const char* k = getenv("GG_STEP_KERNEL");
-        s->use_mono = n_envs >= kMonoEnvsPerSm * s->n_sm;
-        if (k && strcmp(k, "mono") == 0) s->use_mono = 1;
-        if (k && strcmp(k, "roles") == 0) s->use_mono = 0;
+        s->use_mono = n_envs > kMonoEnvsPerSm * s->n_sm;
+        s->kernel_forced = -1;
+        if (k && strcmp(k, "mono") == 0) { s->use_mono = 1; s->kernel_forced = 1; }
+        if (k && strcmp(k, "roles") == 0) { s->use_mono = 0; s->kernel_forced = 0; }
+        s->coupled_pending = 0; s->coupled_prev = 0; s->adapt_tick = 0; s->coupled_frac = 0.f; s->prefer_roles = 0;
+        s->coupled_host = nullptr; s->coupled_ev = nullptr;
+        if (cudaHostAlloc((void**)&s->coupled_host, 2 * sizeof(int), cudaHostAllocDefault) != cudaSuccess ||
+            cudaEventCreateWithFlags(&s->coupled_ev, cudaEventDisableTiming) != cudaSuccess) {
+            s->kernel_forced = s->use_mono;          // no adaptive choice without the mirror
+        } else s->coupled_host[0] = 0;
         // groups of 32 envs per block of the role kernel.  Wider blocks (GG_STEP_SUB=2 / 4: the same-role warps of a block meet at
         // SUB-times wider named barriers and run their instruction stream in step) were measured at 4096 .. 24576 envs and change
         // nothing (16384 envs: 35.4 / 35.6 / 36.1 us for 1 / 2 / 4, profiles/r02_notes.md), so one group per block stays the default
@@ -1316,6 +1398,13 @@ int gg_create(const GgModel* model, int n_envs, int device, GgSim** out) {
         prepare_roles<1>(); prepare_roles<2>(); prepare_roles<4>();
         cudaFuncSetAttribute((const void*)step_mono_kernel<7, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MonoSmem<7, 2>));
         cudaFuncSetAttribute((const void*)step_mono_kernel<5, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MonoSmem<5, 1>));
+        cudaFuncSetAttribute((const void*)drain_kernel<7, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kDrainThreads / 32 * sizeof(MonoWarp<7, 2>::Team)));
+        cudaFuncSetAttribute((const void*)drain_kernel<5, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kDrainThreads / 32 * sizeof(MonoWarp<5, 1>::Team)));
+        // coupled envs of the thread-per-env kernel: drained inside step_mono_kernel (GG_SPLIT_DRAIN=1: by a kernel of their own, 16 instead
+        // of 8 warps per SM -- 30 M instead of 23 M env-steps/s on the scripted grasp, but +5 us per step when the list is empty)
+        s->split_drain = 0;
+        const char* sd = getenv("GG_SPLIT_DRAIN");
+        if (sd) s->split_drain = atoi(sd) != 0;
     }
 #ifdef GG_WITH_RS_KERNEL
     {
@@ -1345,6 +1434,8 @@ int gg_destroy(GgSim* sim) {
     GgDeviceGuard dev_guard(sim->device);
     cudaFree(sim->done); cudaFree(sim->stats); cudaFree(sim->team_scratch); cudaFree(sim->slot);
     cudaFree(sim->mbox); cudaFree(sim->mflag); cudaFree(sim->ctl); cudaFree(sim->clist); cudaFree(sim->cready);
+    if (sim->coupled_ev) { cudaEventSynchronize(sim->coupled_ev); cudaEventDestroy(sim->coupled_ev); }
+    if (sim->coupled_host) cudaFreeHost(sim->coupled_host);
     delete sim;
     return 0;
 }
@@ -1478,6 +1569,13 @@ int gg_ik(GgSim* sim, int n_rows, const int32_t* envs_idx, const float* target_p
 }
 
 // developer hook (not in the public header): copies the first n ints of the control block to the host (GG_RS_TRACE timestamps)
+// introspection for tests / tools: out = {size-based choice (1 = thread-per-env kernel), adaptive override towards the role kernel, lagged coupled fraction}
+int gg_debug_dispatch(GgSim* sim, float* out) {
+    if (!sim || !out) return fail("gg_debug_dispatch: bad argument%s");
+    out[0] = (float)sim->use_mono; out[1] = (float)sim->prefer_roles; out[2] = sim->coupled_frac;
+    return 0;
+}
+
 int gg_debug_ctl(GgSim* sim, int* out, int n) {
     if (!sim || !out || n > 8192) return fail("gg_debug_ctl: bad argument%s");
     GG_CUDA(cudaMemcpy(out, sim->ctl, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost));

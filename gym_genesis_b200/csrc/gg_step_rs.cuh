@@ -139,7 +139,8 @@ __device__ __forceinline__ void role_rnea(const StepArgs& A, int g, int lane, fl
     tf.home = A.M.home_q; tf.slab = scratch + lane * NU; tf.global = A.action + (size_t)v.e * NU;
     tf.staged = staged; tf.use_action = A.mode == 0 && !v.do_reset;
     gg::RobotDyn<NA, NF> D;                               // only the pad-body frames are filled (and kept)
-    gg::robot_rnea_t<NA, NF, FH>(A.M, A.C, q, qd, tf, fs, &D);
+    gg::RneaStoreLocal<NA> rs;
+    gg::robot_rnea_t<NA, NF, FH>(A.M, A.C, q, qd, tf, fs, rs, &D);
     RS_TRACE(g, 1, 1);
 #pragma unroll
     for (int i = 0; i < NU; i++) mb[(MB_FS + i) * 32] = fs[i];

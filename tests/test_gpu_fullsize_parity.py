@@ -14,7 +14,7 @@ import numpy as np
 import pytest
 import torch
 
-from helpers import TOL_Q_ABS, f32, philox4x32_10_np, substep_errors, u01_np
+from helpers import TOL_Q_ABS, f32, philox4x32_10_np, pick_clutter_states, substep_errors, u01_np
 
 pytestmark = pytest.mark.gpu
 
@@ -163,7 +163,8 @@ def test_config4_so101_16384_envs_masked_resets(Sim, so101_model, so101_oracle64
     assert r["resets"] > 10 * 40 and r["checked"] >= 10 * 512
 
 
-# ---- the thread-per-env kernel (launch_step picks it above ~200 envs per SM; GG_STEP_KERNEL=mono forces it at any size) -------------------
+# ---- the thread-per-env kernel (launch_step picks it above one wave of role blocks = 128 envs per SM, unless more than a few per cent of the
+#      envs are coupled; GG_STEP_KERNEL=mono forces it at any size) ---------------------------------------------------------------------
 @pytest.fixture
 def mono_kernel(monkeypatch):
     monkeypatch.setenv("GG_STEP_KERNEL", "mono")
@@ -219,3 +220,52 @@ def test_kernel_dispatch_by_env_count(Sim, franka_model):
     st = _np(sim.stats())
     assert st[5] == 0 and st[0] > 0.98 * n * 10 * (1 - 1 / 200.0)
     sim.close()
+
+
+def test_adaptive_kernel_choice_follows_the_coupled_fraction(Sim, franka_model):
+    """Above one wave of role blocks the thread-per-env kernel runs the free-space steps; once the (lagged) fraction of coupled envs passes
+    4 % launch_step switches to the role kernel, whose block-local solver teams are faster on contact-rich steps.  Both kernels write
+    bit-identical states, so the switch must be invisible: same final state as a run forced onto the role kernel."""
+    import ctypes as C
+    import os
+    from gym_genesis_b200 import cabi
+    n_sm = torch.cuda.get_device_properties(0).multi_processor_count
+    tile = 512
+    n = ((128 * n_sm) // tile + 2) * tile                         # just above one wave of role blocks
+    rng = np.random.default_rng(11)
+    Q, QD, T = pick_clutter_states(franka_model, cabi.compile_gg(franka_model), rng, tile)
+    Qn, QDn, Tn = (np.tile(x, (n // tile, 1)) for x in (Q, QD, T))
+    home = np.tile(f32(franka_model.home_q), (n, 1))
+
+    def run(forced):
+        if forced:
+            os.environ["GG_STEP_KERNEL"] = forced
+        try:
+            sim = Sim(franka_model, n, seed=4)
+        finally:
+            os.environ.pop("GG_STEP_KERNEL", None)
+        sim.lib.gg_debug_dispatch.argtypes = [C.c_void_p, C.c_void_p]
+        probe = (C.c_float * 3)()
+        trace = []
+        sim.reset(None, None)
+        a_free, a_cl = torch.as_tensor(home, device="cuda"), torch.as_tensor(f32(Tn), device="cuda")
+        for k in range(48):                                       # free space: nothing coupled
+            sim.step(a_free)
+        torch.cuda.synchronize()
+        sim.lib.gg_debug_dispatch(sim._h, probe); trace.append(tuple(probe))
+        for rep in range(3):                                      # contact rich: every env starts with the cube between / around the pads
+            sim.set_state(f32(Qn), f32(QDn), np.zeros_like(f32(QDn)))
+            for k in range(34):
+                sim.step(a_cl)
+                torch.cuda.synchronize()
+        sim.lib.gg_debug_dispatch(sim._h, probe); trace.append(tuple(probe))
+        out = [t.clone() for t in sim.get_state()]
+        sim.close()
+        return trace, out
+
+    trace, out = run(None)
+    assert trace[0][0] == 1.0 and trace[0][1] == 0.0 and trace[0][2] == 0.0          # thread-per-env kernel, nothing coupled seen
+    assert trace[1][1] == 1.0 and trace[1][2] > 0.04, trace                           # switched to the role kernel
+    _, ref = run("roles")
+    for x, y in zip(out, ref):
+        assert torch.equal(x, y)
