@@ -551,7 +551,7 @@ def run_gpu(args):
                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if args.total_envs else "weak", "vs_baseline": None, "dtype": "f32",
                "data": "synthetic", "config": workload_config(n, args.total_envs),
                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                            "traffic": traffic_per_launch(n), "peak_source": peak_src, "kernel": "step_mono_kernel<7,2,false>" if n >= 200 * 148 else "step_kernel<7,2,false>",
+                            "traffic": traffic_per_launch(n), "peak_source": peak_src, "kernel": "step_mono_kernel<7,2,false>" if n > 128 * torch.cuda.get_device_properties(dev).multi_processor_count else "step_kernel<7,2,false>",
                             "algorithmic_bytes_per_launch": BYTES_PER_ENV_STEP * n,
                             "note": "latency / fp32-issue bound by design: the per-env pipeline is ~1e4 flop per 508 B"},
                "e2e": {"value": n * world * e2e_steps / (e2e_ms * 1e-3), "unit": "env-steps/s", "h2d_bytes_per_step": n * 9 * 4,
