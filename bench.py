@@ -196,7 +196,9 @@ def run_reference(args):
     from oracle.binding import build, num_threads
     build()
     threads = num_threads()
-    steps, warmup = max(50, min(args.steps, 600)), max(1, min(args.warmup, 5))      # one "step" = one pass of the workload over the sample
+    # one "step" of this arm = one pass of the workload over the sample; at least 300 of them (x16 for the fast implementation: ~10 s of CPU
+    # work over the three implementations), whatever K the caller asks for -- a 20-step sample of a 0.4 ms step would time thread start-up
+    steps, warmup = max(300, min(args.steps, 600)), max(1, min(args.warmup, 5))
     v, dt, cb = cpu_arms(steps, warmup, threads)
     cfg = workload_config(N_ENVS_PER_GPU)
     cfg["workload"] += f"; CPU arm: timed on a bounded sample of {CPU_SAMPLE_ENVS} envs (env-steps/s is a rate)"
