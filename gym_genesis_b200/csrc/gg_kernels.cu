@@ -248,8 +248,11 @@ __device__ __forceinline__ void team_queue(const StepArgs& A, gg::TeamWork<NA, N
     __threadfence_block();
 }
 
-template <int NA, int NF, bool FH, int SUB>
-__global__ void __launch_bounds__(kBlockThreads * SUB, GG_MINBLOCKS / SUB) step_kernel(const __grid_constant__ StepArgs A) {
+// MB = resident blocks per SM the register allocation aims at: 4 (168 registers) for launches that need them (16384 envs = 3.5 blocks per SM),
+// 2 (246 registers: the packed Cholesky factor and the limit rows of the MAIN role stop spilling) for launches of at most two blocks per SM
+// (4096 envs: 31.7 -> 27.9 us, 8192 envs: 33.7 -> 29.0 us; profiles/r02_notes.md)
+template <int NA, int NF, bool FH, int SUB, int MB>
+__global__ void __launch_bounds__(kBlockThreads * SUB, MB / SUB) step_kernel(const __grid_constant__ StepArgs A) {
     constexpr int NU = NA + NF, NV = NU + 6, AD = 7 + NF;
     constexpr int KS = (NA - 1) / 2;      // split point of the end-effector chain (links [0, KS) MAIN, [KS, NA) RNEA)
     typedef Xchg<NU, AD> XT;
@@ -1153,7 +1156,7 @@ struct GgSim {
     uint8_t* done; double* stats;       // library-owned (allocated once in gg_create)
     float* team_scratch;                // library-owned: published dynamics of coupled envs (step_kernel solver teams)
     float* mbox; uint32_t* mflag; int* ctl; int* clist; uint32_t* cready;   // library-owned: role-per-SM kernel mailboxes / coupled list
-    uint32_t epoch; int n_sm; int use_blocks; int use_mono; int sub; int split_drain; int kernel_forced; int64_t list_budget;   // launch epoch of the mailbox flags; SM count; 1 = round-1 block kernel (GG_STEP_KERNEL=blocks)
+    uint32_t epoch; int n_sm; int use_blocks; int use_mono; int sub; int roomy; int split_drain; int kernel_forced; int64_t list_budget;   // launch epoch of the mailbox flags; SM count; 1 = round-1 block kernel (GG_STEP_KERNEL=blocks)
     int32_t* slot;                      // library-owned, allocated on first gg_export_successful: env -> compacted episode slot
     uint32_t step_index;
     GgPinCache pins;                    // address ranges already verified as pinned host memory (gg_step_host)
@@ -1229,14 +1232,14 @@ int gg_internal_export(int device, int n, int stride, int F, int32_t** slot, con
     return 0;
 }
 
-template <int SUB> static void launch_roles(int kind, int ngroups, const StepArgs& A, cudaStream_t stream) {
+template <int SUB, int MB> static void launch_roles(int kind, int ngroups, const StepArgs& A, cudaStream_t stream) {
     const int grid = (ngroups + SUB - 1) / SUB;
-    if (kind == 0) step_kernel<7, 2, false, SUB><<<grid, kBlockThreads * SUB, SUB * sizeof(StepSmem<7, 2>), stream>>>(A);
-    else step_kernel<5, 1, true, SUB><<<grid, kBlockThreads * SUB, SUB * sizeof(StepSmem<5, 1>), stream>>>(A);
+    if (kind == 0) step_kernel<7, 2, false, SUB, MB><<<grid, kBlockThreads * SUB, SUB * sizeof(StepSmem<7, 2>), stream>>>(A);
+    else step_kernel<5, 1, true, SUB, MB><<<grid, kBlockThreads * SUB, SUB * sizeof(StepSmem<5, 1>), stream>>>(A);
 }
-template <int SUB> static void prepare_roles() {
-    cudaFuncSetAttribute((const void*)step_kernel<7, 2, false, SUB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SUB * sizeof(StepSmem<7, 2>)));
-    cudaFuncSetAttribute((const void*)step_kernel<5, 1, true, SUB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SUB * sizeof(StepSmem<5, 1>)));
+template <int SUB, int MB> static void prepare_roles() {
+    cudaFuncSetAttribute((const void*)step_kernel<7, 2, false, SUB, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SUB * sizeof(StepSmem<7, 2>)));
+    cudaFuncSetAttribute((const void*)step_kernel<5, 1, true, SUB, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SUB * sizeof(StepSmem<5, 1>)));
 }
 
 static int launch_step(GgSim* sim, StepArgs& A, gg_stream_t stream) {
@@ -1322,9 +1325,12 @@ static int launch_step(GgSim* sim, StepArgs& A, gg_stream_t stream) {
         // latency regime: 32 envs x 3 role warps per block
         const int ngroups = (sim->n + 31) / 32;
         switch (sim->sub) {
-        case 4: launch_roles<4>(sim->kind, ngroups, A, (cudaStream_t)stream); break;
-        case 2: launch_roles<2>(sim->kind, ngroups, A, (cudaStream_t)stream); break;
-        default: launch_roles<1>(sim->kind, ngroups, A, (cudaStream_t)stream); break;
+        case 4: launch_roles<4, GG_MINBLOCKS>(sim->kind, ngroups, A, (cudaStream_t)stream); break;
+        case 2: launch_roles<2, GG_MINBLOCKS>(sim->kind, ngroups, A, (cudaStream_t)stream); break;
+        default:
+            if (sim->roomy) launch_roles<1, 2>(sim->kind, ngroups, A, (cudaStream_t)stream);
+            else launch_roles<1, GG_MINBLOCKS>(sim->kind, ngroups, A, (cudaStream_t)stream);
+            break;
         }
     }
     g_launches.fetch_add(1);
@@ -1395,7 +1401,11 @@ int gg_create(const GgModel* model, int n_envs, int device, GgSim** out) {
         s->sub = 1;
         const char* sb = getenv("GG_STEP_SUB");
         if (sb && (atoi(sb) == 1 || atoi(sb) == 2 || atoi(sb) == 4)) s->sub = atoi(sb);
-        prepare_roles<1>(); prepare_roles<2>(); prepare_roles<4>();
+        prepare_roles<1, GG_MINBLOCKS>(); prepare_roles<2, GG_MINBLOCKS>(); prepare_roles<4, GG_MINBLOCKS>(); prepare_roles<1, 2>();
+        // launches of at most two role blocks per SM (9472 envs on 148 SMs) take the 246-register build of the role kernel
+        s->roomy = (n_envs + 31) / 32 <= 2 * s->n_sm;
+        const char* rm = getenv("GG_STEP_ROOMY");
+        if (rm) s->roomy = atoi(rm) != 0 && (n_envs + 31) / 32 <= 2 * s->n_sm;
         cudaFuncSetAttribute((const void*)step_mono_kernel<7, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MonoSmem<7, 2>));
         cudaFuncSetAttribute((const void*)step_mono_kernel<5, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MonoSmem<5, 1>));
         cudaFuncSetAttribute((const void*)drain_kernel<7, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kDrainThreads / 32 * sizeof(MonoWarp<7, 2>::Team)));
