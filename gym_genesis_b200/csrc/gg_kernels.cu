@@ -163,6 +163,7 @@ template <int NU, int AD> struct Xchg {
     int iters[32], ncon[32];  // MAIN / teams -> CUBE (statistics)
     int bad[2][32];           // non-finite flags: [0] robot (MAIN), [1] cube (CUBE)
     int next;                 // head of the block's queue of coupled envs (solver teams pop with atomicAdd)
+    alignas(8) unsigned long long mbar;   // transaction barrier of the bulk copy that stages `act`
 };
 
 // shared memory of one group of 32 envs (three role warps); a block holds SUB of them (dynamic shared memory)
@@ -182,9 +183,16 @@ template <int NA, int NF> struct StepSmem {
 template <int NU> struct ActionFetch {
     const float* home; const float* slab; const float* global;
     bool staged, use_action;
+    unsigned mbar = 0;                                  // shared-memory address of the transaction barrier (bulk copy), 0: cp.async groups
     __device__ __forceinline__ void ready() {
         if (staged) {                                   // block-uniform
-            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            if (mbar != 0u) {
+                unsigned done = 0;
+                do {
+                    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                                 : "=r"(done) : "r"(mbar), "r"(0u) : "memory");
+                } while (!done);
+            } else asm volatile("cp.async.wait_group 0;" ::: "memory");
             __syncwarp();
         }
     }
@@ -298,13 +306,29 @@ __global__ void __launch_bounds__(kBlockThreads * SUB, MB / SUB) step_kernel(con
 #else
         const bool staged = false;
 #endif
+        unsigned mbar_addr = 0;
         if (staged) {
             const float* src = A.action + (size_t)blk * 32 * NU;
             const unsigned dst = (unsigned)__cvta_generic_to_shared(X.act);
+#ifndef GG_ACTION_CP_ASYNC
+            // ONE bulk copy of the block's 32 x NU slab (1152 B for the Panda) with a transaction barrier: when the batch lives in pinned
+            // host memory the read crosses PCIe as a few large requests instead of 72 16-byte ones
+            constexpr unsigned kBytes = 32u * NU * sizeof(float);
+            mbar_addr = (unsigned)__cvta_generic_to_shared(&X.mbar);
+            if (lane == 0) {
+                asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar_addr) : "memory");
+                asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar_addr), "r"(kBytes) : "memory");
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"(dst), "l"(src), "r"(kBytes), "r"(mbar_addr) : "memory");
+            }
+            __syncwarp();
+#else
 #pragma unroll
             for (int c = lane; c < 32 * NU / 4; c += 32)
                 asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16u * c), "l"(src + 4 * c) : "memory");
             asm volatile("cp.async.commit_group;" ::: "memory");
+#endif
         }
         float q[NU], qd[NU], fs[NU];
 #pragma unroll
@@ -314,7 +338,7 @@ __global__ void __launch_bounds__(kBlockThreads * SUB, MB / SUB) step_kernel(con
         }
         ActionFetch<NU> tf;
         tf.home = A.M.home_q; tf.slab = X.act + lane * NU; tf.global = A.action + (size_t)e * NU;
-        tf.staged = staged; tf.use_action = A.mode == 0 && !do_reset;
+        tf.staged = staged; tf.use_action = A.mode == 0 && !do_reset; tf.mbar = mbar_addr;
         gg::RobotDyn<NA, NF> D;                               // only the pad-body frames are filled (and kept)
         gg::RneaStoreLocal<NA> rs;
         gg::robot_rnea_t<NA, NF, FH>(A.M, A.C, q, qd, tf, fs, rs, &D);

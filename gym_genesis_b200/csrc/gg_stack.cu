@@ -222,11 +222,14 @@ __global__ void __launch_bounds__(96, 4) stack_prep_kernel(const __grid_constant
             q[i] = do_reset ? A.M.home_q[i] : lq; qd[i] = do_reset ? 0.f : lqd;
         }
         const bool use_action = A.mode == 0 && !do_reset;
+        // the action row is read ONCE (it may live in pinned host memory: every read crosses PCIe) and, for host-fed steps, kept on the
+        // device so that the PD targets persist
+        const bool keep = A.action_dev != nullptr && A.mode == 0 && live;
 #pragma unroll
-        for (int i = 0; i < NU; i++) target[i] = use_action ? A.action[(size_t)e * NU + i] : A.M.home_q[i];
-        if (A.action_dev != nullptr && A.mode == 0 && live) {     // PD targets persist on the device after a host-fed step
-#pragma unroll
-            for (int i = 0; i < NU; i++) A.action_dev[(size_t)e * NU + i] = A.action[(size_t)e * NU + i];
+        for (int i = 0; i < NU; i++) {
+            const float av = (use_action || keep) ? A.action[(size_t)e * NU + i] : 0.f;
+            target[i] = use_action ? av : A.M.home_q[i];
+            if (keep) A.action_dev[(size_t)e * NU + i] = av;
         }
         gg::robot_rnea<NA, NF, FH>(A.M, A.C, q, qd, target, fs);
 #pragma unroll
