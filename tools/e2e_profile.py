@@ -34,6 +34,28 @@ def loop(env, k0, k1):
     return chk
 
 
+def loop_full(env, k0, k1):
+    chk = 0.0
+    for k in range(k0, k1):
+        obs, reward, terminated, truncated, info = env.step(acts[k % 4])
+        r_, t_ = reward.numpy(), terminated.numpy()
+        chk += r_[0] + t_[-1] + r_[n // 2] + obs["agent_pos"].numpy()[n // 2, 0] + obs["environment_state"].numpy()[-1, 10]
+    return chk
+
+
+if "--full" in sys.argv:
+    for rep in range(3):
+        env = gym.make("gym_genesis/CubePick-v0", robot="franka", num_envs=n, device=dev, auto_reset=True, reset_prob=0.005, seed=1,
+                       host_io=True, host_obs=True).unwrapped
+        env.reset(seed=1)
+        loop_full(env, 0, 200)
+        t0 = time.perf_counter()
+        loop_full(env, 0, steps)
+        t1 = time.perf_counter()
+        print(f"full-observation mode: {(t1 - t0) / steps * 1e6:.1f} us / step  ({n * steps / (t1 - t0) / 1e6:.1f} M env-steps/s)")
+        env.close()
+    sys.exit(0)
+
 for kw in ({}, {"alias_outputs": True}):
     env = gym.make("gym_genesis/CubePick-v0", robot="franka", num_envs=n, device=dev, auto_reset=True, reset_prob=0.005, seed=1,
                    host_io=True, **kw).unwrapped
