@@ -490,3 +490,33 @@ def test_calls_restore_the_callers_current_device(Sim):
     assert sim.obs_agent.device.index == 1 and torch.isfinite(sim.obs_agent).all()
     sim.close()
     assert torch.cuda.current_device() == 0
+
+
+def test_action_staging_paths_agree(Sim):
+    """The block's action slab is staged with one bulk copy when the batch pointer is 16-byte aligned and the block is full; an unaligned
+    batch (or the partial tail block) reads its rows directly.  Same results bit for bit, device-resident and pinned host batches."""
+    m = mdl.franka_cube_pick_model()
+    n = 32 * 7 + 13                                               # seven full blocks + a partial tail
+    rng = np.random.default_rng(6)
+    act = f32(m.home_q + rng.uniform(-0.3, 0.3, (n, 9)))
+    outs = []
+    for variant in ("aligned", "unaligned", "host_aligned", "host_unaligned"):
+        sim = Sim(m, n, seed=9)
+        sim.reset(None, None)
+        flat = torch.zeros(n * 9 + 8, dtype=torch.float32, device="cpu" if variant.startswith("host") else "cuda")
+        if variant.startswith("host"):
+            flat = flat.pin_memory()
+        off = 0 if variant.endswith("_aligned") or variant == "aligned" else 1
+        a = flat[off:off + n * 9].view(n, 9)
+        a.copy_(torch.as_tensor(act))
+        assert (a.data_ptr() % 16 == 0) == (off == 0)
+        for _ in range(3):
+            if variant.startswith("host"):
+                sim.step_host(a)
+            else:
+                sim.step(a)
+        outs.append([t.clone() for t in sim.get_state()] + [sim.obs_agent.clone(), sim.obs_env.clone()])
+        sim.close()
+    for other in outs[1:]:
+        for x, y in zip(outs[0], other):
+            assert torch.equal(x, y)
