@@ -179,51 +179,70 @@ class BatchedSim:
         per_step = self.n_envs * (self.agent_dim + self.env_dim + 1) * 4 + 2 * self.n_envs
         return int(max(1, min(32, self._POOL_BYTES // per_step)))
 
-    def _ring(self, name, make, split):
-        r = self.__dict__.get(name)
-        if r is None:
-            r = self.__dict__[name] = _SlabRing(make, split)
-        return r
+    # The three rings are built on first use; a step only pops the next prepared set (views + their raw pointers, computed from the slab's
+    # base pointer so that splitting a slab costs one unbind() per tensor kind and no per-view data_ptr() call).
+    def _make_out(self):
+        n, dev, K = self.n_envs, self.device, self._pool_size()
+        return (torch.empty((K, n, self.agent_dim), dtype=torch.float32, device=dev), torch.empty((K, n, self.env_dim), dtype=torch.float32, device=dev),
+                torch.empty((K, n), dtype=torch.float32, device=dev), torch.empty((2, K, n), dtype=torch.bool, device=dev))
+
+    def _split_out(self, bases):
+        A, E, R = (b.unbind(0) for b in bases[:3])
+        T, U = bases[3][0].unbind(0), bases[3][1].unbind(0)
+        n, K = self.n_envs, len(A)
+        pa, pe, pr, pt = (b.data_ptr() for b in bases)
+        sa, se, sr, pu = 4 * n * self.agent_dim, 4 * n * self.env_dim, 4 * n, pt + K * n
+        return [(A[k], E[k], R[k], T[k], U[k], (pa + k * sa, pe + k * se, pr + k * sr, pt + k * n, pu + k * n)) for k in range(K)]
 
     def _new_outputs(self):
-        def make():
-            n, dev, K = self.n_envs, self.device, self._pool_size()
-            return (torch.empty((K, n, self.agent_dim), dtype=torch.float32, device=dev), torch.empty((K, n, self.env_dim), dtype=torch.float32, device=dev),
-                    torch.empty((K, n), dtype=torch.float32, device=dev), torch.empty((2, K, n), dtype=torch.bool, device=dev))
+        ring = self.__dict__.get("_out_ring")
+        if ring is None:
+            ring = self._out_ring = _SlabRing(self._make_out, self._split_out)
+        pool = ring.pool
+        self.obs_agent, self.obs_env, self.reward, self.terminated, self.truncated, self._out_ptrs = pool.pop() if pool else ring.next()
 
-        def split(bases):
-            A, E, R = (b.unbind(0) for b in bases[:3])
-            T, U = bases[3][0].unbind(0), bases[3][1].unbind(0)
-            return [(A[k], E[k], R[k], T[k], U[k], (A[k].data_ptr(), E[k].data_ptr(), R[k].data_ptr(), T[k].data_ptr(), U[k].data_ptr()))
-                    for k in range(len(A))]
-        self.obs_agent, self.obs_env, self.reward, self.terminated, self.truncated, self._out_ptrs = self._ring("_out_ring", make, split).next()
+    def _make_host(self):
+        n, K = self.n_envs, self._pool_size()
+        return (torch.empty((K, n), dtype=torch.float32, pin_memory=True), torch.empty((2, K, n), dtype=torch.bool, pin_memory=True))
+
+    def _split_host(self, bases):
+        R, T, U = bases[0].unbind(0), bases[1][0].unbind(0), bases[1][1].unbind(0)
+        n, K = self.n_envs, len(R)
+        pr, pt = bases[0].data_ptr(), bases[1].data_ptr()
+        pu = pt + K * n
+        return [(R[k], T[k], U[k], pr + 4 * n * k, pt + n * k, pu + n * k) for k in range(K)]
 
     def _new_host_results(self):
         """Same slabs for the pinned host mirrors of step_host: the kernel writes each step's results into a pinned slot nobody has
         seen before, so the returned CPU tensors are fresh without a copy."""
-        def make():
-            n, K = self.n_envs, self._pool_size()
-            return (torch.empty((K, n), dtype=torch.float32, pin_memory=True), torch.empty((2, K, n), dtype=torch.bool, pin_memory=True))
+        ring = self.__dict__.get("_host_ring")
+        if ring is None:
+            ring = self._host_ring = _SlabRing(self._make_host, self._split_host)
+        pool = ring.pool
+        r, t, u, pr, pt, pu = pool.pop() if pool else ring.next()
+        hio, h = self._hio, self._host
+        hio.reward, hio.terminated, hio.truncated = pr, pt, pu
+        h["reward"], h["terminated"], h["truncated"] = r, t, u
 
-        def split(bases):
-            R, T, U = bases[0].unbind(0), bases[1][0].unbind(0), bases[1][1].unbind(0)
-            return [(R[k], T[k], U[k], R[k].data_ptr(), T[k].data_ptr(), U[k].data_ptr()) for k in range(len(R))]
-        r, t, u, pr, pt, pu = self._ring("_host_ring", make, split).next()
-        self._hio.reward, self._hio.terminated, self._hio.truncated = pr, pt, pu
-        self._host["reward"], self._host["terminated"], self._host["truncated"] = r, t, u
+    def _make_host_obs(self):
+        n, K = self.n_envs, self._pool_size()
+        return (torch.empty((K, n, self.agent_dim), dtype=torch.float32, pin_memory=True),
+                torch.empty((K, n, self.env_dim), dtype=torch.float32, pin_memory=True))
+
+    def _split_host_obs(self, bases):
+        A, E = bases[0].unbind(0), bases[1].unbind(0)
+        n = self.n_envs
+        pa, pe = bases[0].data_ptr(), bases[1].data_ptr()
+        return [(A[k], E[k], pa + 4 * n * self.agent_dim * k, pe + 4 * n * self.env_dim * k) for k in range(len(A))]
 
     def _new_host_obs(self):
         """Fresh pinned observation mirrors (host_obs=True callers): the kernel writes agent_pos / environment_state of the step
         straight into them, so a host-resident policy gets fresh CPU tensors without a copy."""
-        def make():
-            n, K = self.n_envs, self._pool_size()
-            return (torch.empty((K, n, self.agent_dim), dtype=torch.float32, pin_memory=True),
-                    torch.empty((K, n, self.env_dim), dtype=torch.float32, pin_memory=True))
-
-        def split(bases):
-            A, E = bases[0].unbind(0), bases[1].unbind(0)
-            return [(A[k], E[k], A[k].data_ptr(), E[k].data_ptr()) for k in range(len(A))]
-        a, e, pa, pe = self._ring("_host_obs_ring", make, split).next()
+        ring = self.__dict__.get("_host_obs_ring")
+        if ring is None:
+            ring = self._host_obs_ring = _SlabRing(self._make_host_obs, self._split_host_obs)
+        pool = ring.pool
+        a, e, pa, pe = pool.pop() if pool else ring.next()
         self._host["obs_agent"], self._host["obs_env"] = a, e
         self._host_obs_ptrs = (pa, pe)
 
