@@ -1303,15 +1303,80 @@ GG_HD void cube_block_solve(const GgModel& M, V3 cp, const M3& cR, const float* 
     }
 }
 
-// robot block on the decoupled path: joint-limit rows only
+// Joint-limit rows are unit rows (J = +-e_d), so for a GIVEN active set A the minimiser of the robot block has a closed form through
+// the factor of the mass matrix the caller already has (Woodbury):
+//     lambda = (D_A^-1 + E^T M^-1 E)^-1 (a_s - s r)_A,   a = a_s - M^-1 E lambda          (E = [e_d], d in A)
+// and A is right iff row d is violated at a exactly for d in A (KKT of the convex problem: then a IS the minimiser).  With at most
+// two active rows (the two fingers riding their stops is the common case) this costs |A| triangular solve pairs instead of a Newton
+// iteration with its own 9 x 9 factorisation, mass-matrix products and line search.  The active set starts from the rows the
+// unconstrained solution a_s violates (right at the first pass in every case of the random-target workload; the previous step's
+// solution is a worse guess when the targets change every step) and is corrected from the solution; more than two active rows, or no
+// fixed point after three passes, fall back to Newton.
+template <int NU> GG_HD float sel_dyn(const float* v, int d) {
+    float r = 0.f;
+#pragma unroll
+    for (int i = 0; i < NU; i++) r = i == d ? v[i] : r;
+    return r;
+}
 template <int NU>
-GG_HD void robot_block_solve(const float* Mt, const float* as, int nlim, const float* lsg, const float* laref, const float* lD,
-                             const float* warm, float* a, int iterations, float tol, StepInfo& info) {
+GG_HD bool solve_robot_limits_direct(const float* L, const float* dinv, const float* as, const float* lsg, const float* laref, const float* lD,
+                                     float* a, int& passes) {
+    unsigned act = 0u;
+#pragma unroll
+    for (int d = 0; d < NU; d++) act |= (lsg[d] != 0.f && lsg[d] * as[d] - laref[d] < 0.f) ? 1u << d : 0u;
+    for (passes = 1; passes <= 3; passes++) {
+        if (popc32(act) > 2) return false;
+        int d0 = -1, d1 = -1;
+#pragma unroll
+        for (int d = NU - 1; d >= 0; d--) if ((act >> d) & 1u) { d1 = d0; d0 = d; }      // d0 < d1: the active dofs
+#pragma unroll
+        for (int i = 0; i < NU; i++) a[i] = as[i];
+        if (d0 >= 0) {
+            float b[NU], z0[NU];
+#pragma unroll
+            for (int i = 0; i < NU; i++) b[i] = i == d0 ? 1.f : 0.f;
+            chol_solve_packed<NU>(L, dinv, b, z0);
+            const float c0 = sel_dyn<NU>(as, d0) - sel_dyn<NU>(lsg, d0) * sel_dyn<NU>(laref, d0);
+            const float h00 = gg_rcp(sel_dyn<NU>(lD, d0)) + sel_dyn<NU>(z0, d0);
+            if (d1 < 0) {
+                const float lam0 = gg_div(c0, h00);
+#pragma unroll
+                for (int i = 0; i < NU; i++) a[i] -= z0[i] * lam0;
+            } else {
+                float z1[NU];
+#pragma unroll
+                for (int i = 0; i < NU; i++) b[i] = i == d1 ? 1.f : 0.f;
+                chol_solve_packed<NU>(L, dinv, b, z1);
+                const float c1 = sel_dyn<NU>(as, d1) - sel_dyn<NU>(lsg, d1) * sel_dyn<NU>(laref, d1);
+                const float h11 = gg_rcp(sel_dyn<NU>(lD, d1)) + sel_dyn<NU>(z1, d1), h01 = sel_dyn<NU>(z0, d1);
+                const float idet = gg_rcp(h00 * h11 - h01 * h01);
+                const float lam0 = (c0 * h11 - c1 * h01) * idet, lam1 = (c1 * h00 - c0 * h01) * idet;
+#pragma unroll
+                for (int i = 0; i < NU; i++) a[i] -= z0[i] * lam0 + z1[i] * lam1;
+            }
+        }
+        unsigned now = 0u;
+#pragma unroll
+        for (int d = 0; d < NU; d++) now |= (lsg[d] != 0.f && lsg[d] * a[d] - laref[d] < 0.f) ? 1u << d : 0u;
+        if (now == act) return true;
+        act = now;
+    }
+    return false;
+}
+
+// robot block on the decoupled path: joint-limit rows only (L, dinv: packed Cholesky factor of Mt)
+template <int NU>
+GG_HD void robot_block_solve(const float* Mt, const float* L, const float* dinv, const float* as, int nlim, const float* lsg, const float* laref,
+                             const float* lD, const float* warm, float* a, int iterations, float tol, StepInfo& info) {
     info.ncon = 0; info.iters = 0; info.grad = 0.f;
     if (nlim == 0) {
 #pragma unroll
         for (int i = 0; i < NU; i++) a[i] = as[i];
     } else {
+#ifndef GG_NO_DIRECT_LIMITS
+        int passes = 0;
+        if (solve_robot_limits_direct<NU>(L, dinv, as, lsg, laref, lD, a, passes)) { info.iters = passes; return; }
+#endif
         solve_robot_limits<NU>(Mt, as, lsg, laref, lD, warm, a, iterations, tol, 1.f, info.iters, info.grad);
     }
 }
@@ -1371,8 +1436,8 @@ GG_HD void env_substep(const GgModel& M, const GgChain& C, EnvState<NA + NF>& s,
 
     // ---- smooth (unconstrained) acceleration a_s
     float Mc[6], as[NV], qdv[NV];
+    float L[NU * (NU + 1) / 2], dinv[NU];
     {
-        float L[NU * (NU + 1) / 2], dinv[NU];
 #pragma unroll
         for (int i = 0; i < NU * (NU + 1) / 2; i++) L[i] = D.Mt[i];
         chol_packed<NU>(L, dinv);
@@ -1389,7 +1454,7 @@ GG_HD void env_substep(const GgModel& M, const GgChain& C, EnvState<NA + NF>& s,
         // ---- decoupled fast path: robot block (limits only) and cube block (plane contacts only)
         StepInfo ir, ic;
         CubeConLocal cs;
-        robot_block_solve<NU>(D.Mt, as, nlim, lsg, laref, lD, s.qacc, a, iterations, tol, ir);
+        robot_block_solve<NU>(D.Mt, L, dinv, as, nlim, lsg, laref, lD, s.qacc, a, iterations, tol, ir);
         cube_block_solve(M, s.cp, cR, Mc, as + NU, qdv + NU, s.qacc + NU, a + NU, iterations, tol, cs, ic);
         info.ncon = ic.ncon;
         info.iters = ic.iters > ir.iters ? ic.iters : ir.iters;

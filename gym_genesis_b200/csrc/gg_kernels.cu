@@ -420,7 +420,7 @@ __global__ void __launch_bounds__(kBlockThreads * SUB, MB / SUB) step_kernel(con
             const bool coupled = X.coupled[lane] != 0;
 #pragma unroll
             for (int i = 0; i < NU; i++) a[i] = as[i];
-            if (commit && !coupled) gg::robot_block_solve<NU>(D.Mt, as, nlim, lsg, laref, lD, qa, a, A.iterations, A.tol, info);
+            if (commit && !coupled) gg::robot_block_solve<NU>(D.Mt, L, dinv, as, nlim, lsg, laref, lD, qa, a, A.iterations, A.tol, info);
             {
                 const unsigned cm = __ballot_sync(0xffffffffu, coupled);
                 const int ncpl = __popc(cm);
@@ -813,7 +813,7 @@ __global__ void __launch_bounds__(kMonoThreads, GG_MONO_MINBLOCKS) step_mono_ker
 #pragma unroll
         for (int i = 0; i < 6; i++) a_c[i] = as_c[i];
         MONO_SYNC();
-        if (live && !coupled) gg::robot_block_solve<NU>(D.Mt, as, nlim, lsg, laref, lD, qa, a, A.iterations, A.tol, ir);
+        if (live && !coupled) gg::robot_block_solve<NU>(D.Mt, L, dinv, as, nlim, lsg, laref, lD, qa, a, A.iterations, A.tol, ir);
         MONO_SYNC();
         if (live && !coupled) {
             gg::CubeConStrided cs;                          // the CRBA is done with the scratch

@@ -184,7 +184,7 @@ GG_HD unsigned stack_prep_robot(const GgModel& M, const GgChain& C, const float*
     StepInfo ir; ir.ncon = 0; ir.iters = 0; ir.grad = 0.f;
 #pragma unroll
     for (int i = 0; i < NU; i++) a[i] = as[i];
-    if (active && !(rmask & 1u)) robot_block_solve<NU>(D.Mt, as, nlim, lsg, laref, lD, warm, a, iterations, tol, ir);
+    if (active && !(rmask & 1u)) robot_block_solve<NU>(D.Mt, L, dinv, as, nlim, lsg, laref, lD, warm, a, iterations, tol, ir);
     rob_iters = ir.iters;
 #pragma unroll
     for (int i = 0; i < NU * (NU + 1) / 2; i++) W.Mt[i] = D.Mt[i];

@@ -220,7 +220,7 @@ __device__ __forceinline__ void role_main(const StepArgs& A, int g, int lane, fl
 #pragma unroll
         for (int i = 0; i < NU; i++) a[i] = as[i];
         RS_TRACE(g, 0, 9);
-        if (v.live && !coupled) gg::robot_block_solve<NU>(D.Mt, as, nlim, lsg, laref, lD, qa, a, A.iterations, A.tol, info);
+        if (v.live && !coupled) gg::robot_block_solve<NU>(D.Mt, L, dinv, as, nlim, lsg, laref, lD, qa, a, A.iterations, A.tol, info);
         RS_TRACE(g, 0, 10);
         rob_iters = coupled ? 0 : info.iters;
         const unsigned cm = __ballot_sync(0xffffffffu, coupled);

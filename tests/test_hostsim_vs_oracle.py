@@ -208,3 +208,28 @@ def test_substep_gripper_cube_clutter(hostsim, gg, franka_model, oracle64):
     assert (hinfo[:, 0] == info[:, 0]).all() and (info[:, 0] > 4).sum() > 50
     eq, ev = substep_errors(Q, QD, qo, qdo, q, qd, _a_smooth_scale(oracle64, Q, QD, T))
     assert eq.max() < TOL_Q_ABS and ev.max() < 1.0, (eq.max(), ev.max(), int(np.argmax(ev)))
+
+
+@pytest.mark.parametrize("n_beyond", [1, 2, 3, 5])
+def test_robot_block_with_k_joints_at_their_limits(hostsim, gg, franka_model, oracle64, n_beyond):
+    """The robot block's joint-limit rows: the closed-form active-set solve (<= 2 active rows, gg_env.cuh solve_robot_limits_direct)
+    and its Newton fallback (more rows) against the converged fp64 oracle.  k joints start beyond their limits, moving outwards, with
+    targets that push further out; the others are random."""
+    rng = np.random.default_rng(20 + n_beyond)
+    n = 48
+    Q, QD, T = random_states(franka_model, rng, n, cube_on_ground=False)
+    lo, hi = np.array(list(gg.lim_lo)[:9]), np.array(list(gg.lim_hi)[:9])
+    for e in range(n):
+        for d in rng.choice(9, n_beyond, replace=False):
+            up = rng.random() < 0.5
+            Q[e, d] = (hi[d] + rng.uniform(1e-4, 3e-3)) if up else (lo[d] - rng.uniform(1e-4, 3e-3))
+            QD[e, d] = rng.uniform(0.0, 0.3) * (1 if up else -1)
+            T[e, d] = Q[e, d] + (0.2 if up else -0.2) * (0.02 if d >= 7 else 1.0)
+    Q, QD, T = (f32(x).astype(np.float64) for x in (Q, QD, T))
+    QA = np.zeros_like(QD)
+    qo, qdo, qao = Q.copy(), QD.copy(), QA.copy()
+    oracle64.step(qo, qdo, qao, T, iterations=200, tol=1e-12)
+    q, qd, qa, hinfo, _ = hostsim_step(hostsim, gg, Q, QD, QA, T)
+    eq, ev = substep_errors(Q, QD, qo, qdo, q, qd, _a_smooth_scale(oracle64, Q, QD, T))
+    assert eq.max() < TOL_Q_ABS and ev.max() < 1.0, (eq.max(), ev.max())
+    assert hinfo[:, 1].min() >= 1                                  # every env had limit rows to solve
