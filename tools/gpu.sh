@@ -12,7 +12,8 @@
 #   benchlite    bench.py --no-workload-b --no-workload-c --no-config4 --no-workload-d (headline legs only)
 #   launches     ncu launch list of bench.py
 #   ncu_mono     ncu --set full of the thread-per-env step kernel at 131072 envs (BASELINE configs[4] on one GPU)
-#   ncu_step     ncu --set full of the step kernel (bench workload)      ncu_grasp: contact-rich step 130 of the grasp replay
+#   ncu_step     ncu --set full of the step kernel (bench workload; launch 212 = steady state after 200 warm-up steps: the fingers ride their
+#                stops only after a few dozen steps, earlier launches skip the limit-row solve)      ncu_grasp: contact-rich step 130 of the grasp replay
 #   ncu_stack    ncu --set full of the stacking solver (random workload)
 #   stack        tools/stack_bench.py at 16384 / 131072 envs
 #   sanitize     compute-sanitizer memcheck + racecheck on the pick and stack kernels
@@ -44,10 +45,10 @@ for stage in "$@"; do
     benchlite) python bench.py --no-workload-b --no-workload-c --no-config4 --no-workload-d > ${O}_benchlite.json 2> ${O}_benchlite.err; tail -c 1500 ${O}_benchlite.json; tail -3 ${O}_benchlite.err ;;
     launches) timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file ${O}_launches.csv \
                 python bench.py --steps 20 --warmup 10 --no-cpu-baseline --no-workload-b --no-workload-c --no-config4 --no-config2 > ${O}_ncu_bench.log 2>&1; wc -l ${O}_launches.csv ;;
-    ncu_step) timeout 600 ncu --set full --clock-control none --import-source on -k regex:step_kernel -s 12 -c 1 -f -o ${O}_step \
-                python bench.py --steps 20 --warmup 10 --no-cpu-baseline --no-workload-b --no-workload-c --no-config4 --no-config2 --no-workload-d > ${O}_ncu_full.log 2>&1; ls -la ${O}_step.ncu-rep ;;
-    ncu_mono) timeout 600 ncu --set full --clock-control none --import-source on -k regex:step_mono_kernel -s 12 -c 1 -f -o ${O}_step_mono \
-                python bench.py --total-envs 131072 --steps 20 --warmup 10 --no-cpu-baseline --no-workload-b --no-workload-c --no-config4 --no-config2 --no-workload-d > ${O}_ncu_mono.log 2>&1; ls -la ${O}_step_mono.ncu-rep ;;
+    ncu_step) timeout 600 ncu --set full --clock-control none --import-source on -k regex:step_kernel -s 212 -c 1 -f -o ${O}_step \
+                python bench.py --steps 20 --warmup 200 --no-cpu-baseline --no-workload-b --no-workload-c --no-config4 --no-config2 --no-workload-d > ${O}_ncu_full.log 2>&1; ls -la ${O}_step.ncu-rep ;;
+    ncu_mono) timeout 600 ncu --set full --clock-control none --import-source on -k regex:step_mono_kernel -s 212 -c 1 -f -o ${O}_step_mono \
+                python bench.py --total-envs 131072 --steps 20 --warmup 200 --no-cpu-baseline --no-workload-b --no-workload-c --no-config4 --no-config2 --no-workload-d > ${O}_ncu_mono.log 2>&1; ls -la ${O}_step_mono.ncu-rep ;;
     ncu_grasp) timeout 600 ncu --set full --clock-control none --import-source on -k regex:"step_kernel|coupled" -s 130 -c 1 -f -o ${O}_grasp \
                 python tools/profile_grasp.py 140 > ${O}_ncu_grasp.log 2>&1; ls -la ${O}_grasp.ncu-rep ;;
     ncu_stack) timeout 900 ncu --set full --clock-control none --import-source on -k regex:stack_solve -s 12 -c 1 -f -o ${O}_stack_solve \
