@@ -262,8 +262,7 @@ __device__ __noinline__ void team_solve(const GgModel& M, const TeamWork<NA, NF>
             const int rb = code == 0 ? -1 : (code - 1) % 3;
             const float wsum = (rb >= 0 ? M.body_invweight[rb] : 0.f) + ((code == 0 || code >= 4) ? M.cube_invweight : 0.f);
             float imp = 1.f, ar[4];
-#pragma unroll
-            for (int k = 0; k < 4; k++) imp_aref(M, -B.depth[c], rowval(vel, mu, k), imp, ar[k]);
+            imp_aref4(M, -B.depth[c], vel, mu, imp, ar);
             Dk[s] = gg_rcp(fmaxf(M.minval, M.reg_scale * (1.f - imp) / imp * wsum));
 #pragma unroll
             for (int k = 0; k < 4; k++) {

@@ -532,16 +532,27 @@ GG_HD void tangent_basis(V3 n, V3& t1, V3& t2) {
 }
 
 // solref / solimp impedance (power fixed at 2, checked by the host model compiler)
-GG_HD void imp_aref(const GgModel& M, float pos, float vel, float& imp, float& aref) {
+GG_HD float impedance(const GgModel& M, float pos) {
     float x = fabsf(pos) / M.width;
-    if (x >= 1.f) imp = M.dmax;
-    else if (x <= 0.f) imp = M.dmin;
-    else {
-        float y = x <= M.mid ? x * x / M.mid : 1.f - (1.f - x) * (1.f - x) / (1.f - M.mid);
-        imp = M.dmin + y * (M.dmax - M.dmin);
-    }
+    if (x >= 1.f) return M.dmax;
+    if (x <= 0.f) return M.dmin;
+    float y = x <= M.mid ? x * x / M.mid : 1.f - (1.f - x) * (1.f - x) / (1.f - M.mid);
+    return M.dmin + y * (M.dmax - M.dmin);
+}
+GG_HD void imp_aref(const GgModel& M, float pos, float vel, float& imp, float& aref) {
+    imp = impedance(M, pos);
     float Bc = 2.f / (M.dmax * M.tc), Kc = 1.f / (M.dmax * M.dmax * M.tc * M.tc * M.dr * M.dr);
     aref = -Bc * vel - Kc * imp * pos;
+}
+GG_HD float rowval(const float* v3, float mu, int k);
+// the four pyramidal rows of ONE contact share the position (hence the impedance) and the two solref constants: one impedance
+// evaluation and one pair of divisions per contact instead of four (same operations in the same order per row: bit-identical)
+GG_HD void imp_aref4(const GgModel& M, float pos, const float* vel3, float mu, float& imp, float* ar) {
+    imp = impedance(M, pos);
+    const float Bc = 2.f / (M.dmax * M.tc), Kc = 1.f / (M.dmax * M.dmax * M.tc * M.tc * M.dr * M.dr);
+    const float kp = Kc * imp * pos;
+#pragma unroll
+    for (int k = 0; k < 4; k++) ar[k] = -Bc * rowval(vel3, mu, k) - kp;
 }
 
 template <int N> GG_HD float dotn(const float* a, const float* b) {
@@ -735,8 +746,7 @@ GG_HD void solve_cube_plane(const GgModel& M, const float* Mc, const float* as, 
         for (int k = 0; k < 3; k++) { vel[k] = dotn<6>(J[k], qd); uw[k] = dotn<6>(J[k], warm); us[k] = dotn<6>(J[k], as); }
         const bool live = c < ncp;
         float imp = 1.f, ar[4];
-#pragma unroll
-        for (int k = 0; k < 4; k++) imp_aref(M, -depth[c], rowval(vel, mu, k), imp, ar[k]);
+        imp_aref4(M, -depth[c], vel, mu, imp, ar);
         const float Dk = live ? gg_rcp(fmaxf(M.minval, M.reg_scale * (1.f - imp) / imp * M.cube_invweight)) : 0.f;
 #pragma unroll
         for (int k = 0; k < 4; k++) {
@@ -967,8 +977,7 @@ GG_HD void solve_coupled(const GgModel& M, const RobotDyn<NA, NF>& D, const EnvS
         const int rb = code == 0 ? -1 : (code - 1) % 3;
         const float wsum = (rb >= 0 ? M.body_invweight[rb] : 0.f) + ((code == 0 || code >= 4) ? M.cube_invweight : 0.f);
         float imp = 1.f, ar[4];
-#pragma unroll
-        for (int k = 0; k < 4; k++) imp_aref(M, -C.depth[c], rowval(vel, mu, k), imp, ar[k]);
+        imp_aref4(M, -C.depth[c], vel, mu, imp, ar);
         const float Dk = gg_rcp(fmaxf(M.minval, M.reg_scale * (1.f - imp) / imp * wsum));
         R.D[c] = Dk;
 #pragma unroll

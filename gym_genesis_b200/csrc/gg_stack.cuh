@@ -601,8 +601,7 @@ GG_WD void stack_solve(const GgModel& M, int max_contacts, const StackIn<NA, NF,
             const float wsum = (A == 0 ? 0.f : (A < 4 ? M.body_invweight[A - 1] : M.cube_invweight)) +
                                (Bb < 4 ? M.body_invweight[Bb - 1] : M.cube_invweight);
             float imp = 1.f, ar[4];
-#pragma unroll
-            for (int k = 0; k < 4; k++) imp_aref(M, -B.depth[c], rowval(vel, mu, k), imp, ar[k]);
+            imp_aref4(M, -B.depth[c], vel, mu, imp, ar);
             Dk[s] = gg_rcp(fmaxf(M.minval, M.reg_scale * (1.f - imp) / imp * wsum));
 #pragma unroll
             for (int k = 0; k < 4; k++) {
