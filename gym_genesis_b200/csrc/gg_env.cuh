@@ -206,15 +206,33 @@ struct TargetPtr {
     GG_HD float operator()(int d) const { return t[d]; }
 };
 
+// Mass-matrix pass without kinematics: S and I of the arm links and the summed finger inertias come from the store the bias-force
+// pass filled (DynStoreStrided; the finger rows are complete already).  Same sums in the same order as robot_crba, hence the same bits.
+template <int NA, int NF, bool FH, class RS>
+GG_HD void robot_crba_backward(const GgModel& M, RobotDyn<NA, NF>& D, const RS& rs) {
+    constexpr int NU = NA + NF;
+    SI Ic = rs.getIfingers();
+    GG_LINK_LOOP
+    for (int l = NA - 1; l >= 0; l--) {
+        Ic = Ic + rs.getI(l);
+        SV G = apply(Ic, rs.getS(l));
+        GG_MROW_LOOP
+        for (int i = 0; i <= l; i++) D.Mt[GG_TRI(l, i)] = sdot(rs.getS(i), G);
+    }
+#pragma unroll
+    for (int d = 0; d < NU; d++) D.Mt[GG_TRI(d, d)] += M.armature[d] + M.dt * (M.damping[d] + M.kv[d]);
+}
+
 // per-link motion subspace / force of the bias-force pass: thread-local arrays, or this lane's column of a shared-memory scratch
 template <int NA> struct RneaStoreLocal {
+    enum { kFull = 0 };
     SV S[NA]; SV F[NA];
     GG_HD SV getS(int l) const { return S[l]; }
     GG_HD SV getF(int l) const { return F[l]; }
     GG_HD void set(int l, const SV& s, const SV& f) { S[l] = s; F[l] = f; }
 };
 template <int NA> struct RneaStoreStrided {      // element e of link l at b[(l * 12 + e) * STRIDE]
-    enum { STRIDE = 32, FLOATS = NA * 12 };
+    enum { STRIDE = 32, FLOATS = NA * 12, kFull = 0 };
     float* b;
     GG_HD SV get6(const float* p) const { SV v; v.a = mk(p[0], p[STRIDE], p[2 * STRIDE]); v.l = mk(p[3 * STRIDE], p[4 * STRIDE], p[5 * STRIDE]); return v; }
     GG_HD SV getS(int l) const { return get6(b + l * 12 * STRIDE); }
@@ -224,6 +242,41 @@ template <int NA> struct RneaStoreStrided {      // element e of link l at b[(l 
         p[0] = s.a.x; p[STRIDE] = s.a.y; p[2 * STRIDE] = s.a.z; p[3 * STRIDE] = s.l.x; p[4 * STRIDE] = s.l.y; p[5 * STRIDE] = s.l.z;
         p[6 * STRIDE] = f.a.x; p[7 * STRIDE] = f.a.y; p[8 * STRIDE] = f.a.z; p[9 * STRIDE] = f.l.x; p[10 * STRIDE] = f.l.y; p[11 * STRIDE] = f.l.z;
     }
+};
+
+// The thread-per-env kernel runs the bias-force pass and the mass-matrix pass in ONE thread: with this store the first pass keeps the
+// motion subspace S and the world-frame spatial inertia I of every arm link in shared memory (the layout of LinkStoreStrided, + one slot
+// for the summed finger inertias; the link forces F stay thread-local), fills the finger rows of the mass matrix on the way, and the
+// second pass (robot_crba_backward) needs no kinematics of its own -- the chain walk and the inertia rotation are done once per step
+// instead of twice (~270 instructions per link).
+template <int NA> struct DynStoreStrided {
+    enum { STRIDE = 32, FLOATS = NA * 16 + 10, kFull = 1 };
+    float* b;
+    SV F[NA];
+    GG_HD SV getS(int l) const {
+        const float* p = b + l * 16 * STRIDE;
+        SV v; v.a = mk(p[0], p[STRIDE], p[2 * STRIDE]); v.l = mk(p[3 * STRIDE], p[4 * STRIDE], p[5 * STRIDE]);
+        return v;
+    }
+    GG_HD SV getF(int l) const { return F[l]; }
+    GG_HD void set(int l, const SV& v, const SV& f) {
+        float* p = b + l * 16 * STRIDE;
+        p[0] = v.a.x; p[STRIDE] = v.a.y; p[2 * STRIDE] = v.a.z; p[3 * STRIDE] = v.l.x; p[4 * STRIDE] = v.l.y; p[5 * STRIDE] = v.l.z;
+        F[l] = f;
+    }
+    GG_HD SI getIat(const float* p) const {
+        SI v; v.m = p[0]; v.h = mk(p[STRIDE], p[2 * STRIDE], p[3 * STRIDE]);
+        v.I.xx = p[4 * STRIDE]; v.I.yy = p[5 * STRIDE]; v.I.zz = p[6 * STRIDE]; v.I.xy = p[7 * STRIDE]; v.I.xz = p[8 * STRIDE]; v.I.yz = p[9 * STRIDE];
+        return v;
+    }
+    GG_HD void setIat(float* p, const SI& v) const {
+        p[0] = v.m; p[STRIDE] = v.h.x; p[2 * STRIDE] = v.h.y; p[3 * STRIDE] = v.h.z;
+        p[4 * STRIDE] = v.I.xx; p[5 * STRIDE] = v.I.yy; p[6 * STRIDE] = v.I.zz; p[7 * STRIDE] = v.I.xy; p[8 * STRIDE] = v.I.xz; p[9 * STRIDE] = v.I.yz;
+    }
+    GG_HD SI getI(int l) const { return getIat(b + (l * 16 + 6) * STRIDE); }
+    GG_HD void setI(int l, const SI& v) { setIat(b + (l * 16 + 6) * STRIDE, v); }
+    GG_HD SI getIfingers() const { return getIat(b + NA * 16 * STRIDE); }
+    GG_HD void setIfingers(const SI& v) { setIat(b + NA * 16 * STRIDE, v); }
 };
 
 // Dp (optional): receives the frames of the pad-carrying bodies (last arm link, fingers) -- the chain walk of this pass already has
@@ -239,6 +292,7 @@ GG_HD void robot_rnea_t(const GgModel& M, const GgChain& C, const float* q, cons
     SV A; A.a = mk(0.f, 0.f, 0.f); A.l = mk(0.f, 0.f, M.gravity);   // gravity as base acceleration
     Q4 qa = ql; V3 pa = pl; M3 Ra = Rl; SV Va = V, Aa = A;          // last arm link (parent of the fingers)
     SV Fc; Fc.a = mk(0.f, 0.f, 0.f); Fc.l = mk(0.f, 0.f, 0.f);
+    SI Icf; Icf.m = 0.f; Icf.h = mk(0.f, 0.f, 0.f); Icf.I.xx = Icf.I.yy = Icf.I.zz = Icf.I.xy = Icf.I.xz = Icf.I.yz = 0.f;   // fingers (kFull stores)
     GG_LINK_LOOP
     for (int l = 0; l < NU; l++) {
         const bool fin = l >= NA;
@@ -250,6 +304,20 @@ GG_HD void robot_rnea_t(const GgModel& M, const GgChain& C, const float* q, cons
         V = V + Sl * qd[l];
         const SI Il = body_inertia(e[CH_MASS], ld3(e + CH_COM), e + CH_INERTIA, Rl, pl);
         const SV Fl = apply(Il, A) + crf(V, apply(Il, V));
+        if constexpr (RS::kFull != 0) {                  // everything the mass-matrix pass needs (robot_crba_backward); Dp is not null
+            if (!fin) {
+                rs.setI(l, Il);
+                Dp->jk[l] = Rl.c2; Dp->jo[l] = pl;
+            } else {
+                // leaf body: its rows of M are complete here (every arm S_i is in the store already), same sums as robot_crba
+                const SV G = apply(Il, Sl);
+                Dp->Mt[GG_TRI(l, l)] = sdot(Sl, G);
+                GG_MROW_LOOP
+                for (int i = 0; i < NA; i++) Dp->Mt[GG_TRI(l, i)] = sdot(rs.getS(i), G);
+                for (int g = NA; g < l; g++) Dp->Mt[GG_TRI(l, g)] = 0.f;
+                Icf = Icf + Il;
+            }
+        }
         if (!fin) {
             rs.set(l, Sl, Fl);
             if (l == NA - 1) { qa = ql; pa = pl; Ra = Rl; Va = V; Aa = A; }
@@ -260,6 +328,7 @@ GG_HD void robot_rnea_t(const GgModel& M, const GgChain& C, const float* q, cons
         }
     }
     if (Dp) { Dp->lq = qa; Dp->lp = pa; Dp->lR = Ra; }
+    if constexpr (RS::kFull != 0) rs.setIfingers(Icf);
     GG_LINK_LOOP
     for (int l = NA - 1; l >= 0; l--) {
         Fc = Fc + rs.getF(l);

@@ -721,7 +721,7 @@ constexpr int kMonoThreads = GG_MONO_THREADS;
 // arrays were the kernel's top stall (ncu: 2.0 of 6.1 cycles per issue waiting on L1TEX, 113 MB of live stack against a 126 MB L2,
 // 223 MB of DRAM write-back per launch at 131072 envs; profiles/r02_step_mono_details.txt)
 template <int NA, int NF> struct MonoWarp {
-    static constexpr int SCRATCH = (gg::LinkStoreStrided<NA>::FLOATS > gg::CubeConStrided::FLOATS ? gg::LinkStoreStrided<NA>::FLOATS : gg::CubeConStrided::FLOATS) * 32;
+    static constexpr int SCRATCH = (gg::DynStoreStrided<NA>::FLOATS > gg::CubeConStrided::FLOATS ? gg::DynStoreStrided<NA>::FLOATS : gg::CubeConStrided::FLOATS) * 32;
     struct Team { gg::TeamWork<NA, NF> TW; gg::TeamBuf<NA + NF + 6> TB; };
     union { Team t; float scratch[SCRATCH]; };
 };
@@ -780,7 +780,7 @@ __global__ void __launch_bounds__(kMonoThreads, GG_MONO_MINBLOCKS) step_mono_ker
             ActionFetch<NU> tf;
             tf.home = A.M.home_q; tf.slab = nullptr; tf.global = A.action + (size_t)e * NU;
             tf.staged = false; tf.use_action = A.mode == 0 && !do_reset;
-            gg::RneaStoreStrided<NA> rs;                    // scratch view 1 of 3 (bias forces, then CRBA, then cube block)
+            gg::DynStoreStrided<NA> rs;                     // S, I of every arm link stay in the scratch: the mass-matrix pass below re-uses them
             rs.b = SW.scratch + lane;
             gg::robot_rnea_t<NA, NF, FH>(A.M, A.C, q, qd, tf, D.fs, rs, &D);
             if (A.action_dev != nullptr && A.mode == 0 && live) {
@@ -791,9 +791,9 @@ __global__ void __launch_bounds__(kMonoThreads, GG_MONO_MINBLOCKS) step_mono_ker
         coupled = live && active && gg::pads_may_touch<NA, NF>(A.M, D, cp, cq);
         MONO_SYNC();
         {
-            gg::LinkStoreStrided<NA> ls;
-            ls.b = SW.scratch + lane;
-            gg::robot_crba<NA, NF, FH>(A.M, A.C, q, D, ls);
+            gg::DynStoreStrided<NA> rs;                     // no second chain walk: frames and inertias come from the bias-force pass
+            rs.b = SW.scratch + lane;
+            gg::robot_crba_backward<NA, NF, FH>(A.M, D, rs);
         }
         MONO_SYNC();
         float L[NU * (NU + 1) / 2], dinv[NU];
